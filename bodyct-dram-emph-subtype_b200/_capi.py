@@ -1,0 +1,100 @@
+"""ctypes binding of libdram_b200.so (include/dram_b200.h).
+
+This is the only place that touches the shared library.  Loading never needs a GPU (the
+library links cudart statically and resolves the driver lazily), so the symbol table can be
+checked on a CPU box; every compute entry point needs a B200.
+There is no fallback: if the library is missing, `load()` raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdram_b200.so")
+
+DRAM_OK = 0
+
+
+class ConvDesc(C.Structure):
+    """Mirror of `dram_conv_desc` (include/dram_b200.h)."""
+
+    _fields_ = [
+        ("n", C.c_int32), ("di", C.c_int32), ("hi", C.c_int32), ("wi", C.c_int32),
+        ("c1", C.c_int32), ("c2", C.c_int32),
+        ("cout", C.c_int32),
+        ("kd", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("sd", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("dd", C.c_int32), ("dh", C.c_int32), ("dw", C.c_int32),
+        ("pd", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("relu", C.c_int32),
+        ("res_c", C.c_int32), ("res_stride", C.c_int32),
+        ("res_d", C.c_int32), ("res_h", C.c_int32), ("res_w", C.c_int32),
+        ("n_heads", C.c_int32), ("head_ch", C.c_int32 * 2), ("head_sigmoid", C.c_int32),
+        ("store_out", C.c_int32),
+        ("tw", C.c_int32), ("th", C.c_int32), ("td", C.c_int32),
+    ]
+
+
+_vp, _i32, _i64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+_pi32 = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); must list every symbol include/dram_b200.h declares.
+SIGNATURES = {
+    "dram_version": (C.c_int, []),
+    "dram_last_error": (C.c_int, [C.c_char_p, _sz]),
+    "dram_sm_count": (C.c_int, []),
+    "dram_conv3d_out_dims": (C.c_int, [C.POINTER(ConvDesc), _pi32, _pi32, _pi32]),
+    "dram_conv3d_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _vp, C.POINTER(_vp)]),
+    "dram_conv3d_plan_destroy": (C.c_int, [_vp]),
+    "dram_conv3d_run": (C.c_int, [_vp, _i32, _vp]),
+    "dram_conv3d_plan_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, _pi32, _pi32, _pi32]),
+    "dram_stem_expand": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_pool_workspace_bytes": (_sz, [_i32, _i32]),
+    "dram_masked_pool": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_dram_workspace_bytes": (_sz, [_i32]),
+    "dram_dram_upsample_mask": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
+                                          _i32, _i32, _i32, _i32, _vp]),
+    "dram_preprocess_workspace_bytes": (_sz, []),
+    "dram_window_standardize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _vp]),
+    "dram_resize_image": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_resize_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_ncdhw_f32_to_ndhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_ndhwc_bf16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+class DramError(RuntimeError):
+    """A libdram_b200 call returned a negative status."""
+
+
+def load():
+    """Loads the library once and types every entry point.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python {os.path.join(HERE, 'build.py')}` "
+            "(there is no CPU or library fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    buf = C.create_string_buffer(512)
+    load().dram_last_error(buf, len(buf))
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(status, what):
+    if status != DRAM_OK:
+        raise DramError(f"{what} failed ({status}): {last_error()}")

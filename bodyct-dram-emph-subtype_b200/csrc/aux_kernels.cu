@@ -1,0 +1,649 @@
+// Memory-bound kernels of the hot path (K2a, K3, K4, K6, K7, K8, K8b + layout helpers).
+// All are grid-stride kernels with 16-byte vector accesses on the contiguous (channel or W)
+// axis and grids sized as a multiple of the SM count; none has data reuse worth staging in
+// shared memory beyond what L1/L2 already give (each input element is touched by <= 27
+// neighbouring outputs that sit in the same or the adjacent CTA).
+#include <math.h>
+
+#include "common.h"
+
+namespace dram {
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  bf162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf162(uint32_t u) {
+  bf162 h = *reinterpret_cast<bf162 *>(&u);
+  return make_float2(__low2float(h), __high2float(h));
+}
+
+// ATen's source index for linear modes with align_corners=True
+// (area_pixel_compute_scale + compute_source_index_and_lambda): scale = (in-1)/(out-1) in fp32.
+struct LinIdx {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ LinIdx lin_index_ac(int dst, float scale, int in_size) {
+  LinIdx r;
+  const float real = scale * (float)dst;
+  int i0 = (int)real;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  r.i0 = i0;
+  r.i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  float l1 = real - (float)i0;
+  l1 = fminf(fmaxf(l1, 0.0f), 1.0f);
+  r.w1 = l1;
+  r.w0 = 1.0f - l1;
+  return r;
+}
+__host__ __device__ __forceinline__ float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;
+}
+// ATen's legacy `nearest` source index (nearest_idx in UpSample.h).
+__device__ __forceinline__ int nearest_index(int dst, int in_size, int out_size) {
+  if (out_size == in_size) return dst;
+  if (out_size == 2 * in_size) return dst >> 1;
+  const float scale = (float)in_size / (float)out_size;
+  const int s = (int)floorf((float)dst * scale);
+  return s < in_size - 1 ? s : in_size - 1;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum of `v`; result valid in thread 0.  `scratch` has >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    v = lane < nw ? scratch[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2a stem unfold: one 16-byte store per thread (8 pseudo-channels = one kh row of taps).
+// ---------------------------------------------------------------------------------------
+__global__ void stem_expand_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int n, int d,
+                                   int h, int w, int h2, int w2) {
+  const int64_t total = (int64_t)n * d * h2 * w2 * 8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int kh = (int)(t & 7);
+    int64_t v = t >> 3;
+    const int ow = (int)(v % w2);
+    v /= w2;
+    const int oh = (int)(v % h2);
+    v /= h2;  // v = n*d + z
+    const int ih = 2 * oh - 3 + kh;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+    if (kh < 7 && ih >= 0 && ih < h) {
+      const float *row = x + (v * h + ih) * (int64_t)w;
+      const int iw0 = 2 * ow - 3;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int iw = iw0 + j;
+        if (iw >= 0 && iw < w) f[j] = __ldg(row + iw);
+      }
+    }
+    out[t] = make_uint4(pack_bf162(f[0], f[1]), pack_bf162(f[2], f[3]), pack_bf162(f[4], f[5]),
+                        pack_bf162(f[6], f[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 max-pool 3^3 s2 p1, NDHWC bf16, 8 channels per thread.
+// ---------------------------------------------------------------------------------------
+__global__ void maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d,
+                                 int h, int w, int cg, int od, int oh, int ow) {
+  const int64_t total = (int64_t)n * od * oh * ow * cg;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    int64_t v = t / cg;
+    const int xw = (int)(v % ow);
+    v /= ow;
+    const int xh = (int)(v % oh);
+    v /= oh;
+    const int xd = (int)(v % od);
+    const int b = (int)(v / od);
+    bf162 m[4];
+    const bf162 ninf = __float2bfloat162_rn(-INFINITY);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = ninf;
+    for (int zd = 0; zd < 3; ++zd) {
+      const int id = 2 * xd - 1 + zd;
+      if (id < 0 || id >= d) continue;
+      for (int zh = 0; zh < 3; ++zh) {
+        const int ih = 2 * xh - 1 + zh;
+        if (ih < 0 || ih >= h) continue;
+#pragma unroll
+        for (int zw = 0; zw < 3; ++zw) {
+          const int iw = 2 * xw - 1 + zw;
+          if (iw < 0 || iw >= w) continue;
+          const uint4 u = __ldg(x + ((((int64_t)b * d + id) * h + ih) * w + iw) * cg + g);
+          const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], *reinterpret_cast<const bf162 *>(&uu[q]));
+        }
+      }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t *>(&m[0]);
+    o.y = *reinterpret_cast<uint32_t *>(&m[1]);
+    o.z = *reinterpret_cast<uint32_t *>(&m[2]);
+    o.w = *reinterpret_cast<uint32_t *>(&m[3]);
+    out[t] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 trilinear x2 (align_corners=True), NDHWC bf16, 8 channels per thread, fp32 math in
+// ATen's nesting order (W innermost, D outermost).
+// ---------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d,
+                                  int h, int w, int cg, float sd, float sh, float sw) {
+  const int od = 2 * d, oh = 2 * h, ow = 2 * w;
+  const int64_t total = (int64_t)n * od * oh * ow * cg;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    int64_t v = t / cg;
+    const int xw = (int)(v % ow);
+    v /= ow;
+    const int xh = (int)(v % oh);
+    v /= oh;
+    const int xd = (int)(v % od);
+    const int b = (int)(v / od);
+    const LinIdx id = lin_index_ac(xd, sd, d), ih = lin_index_ac(xh, sh, h), iw = lin_index_ac(xw, sw, w);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int zd = a ? id.i1 : id.i0;
+      const float wd = a ? id.w1 : id.w0;
+      float accd[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) accd[j] = 0.0f;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int zh = bb ? ih.i1 : ih.i0;
+        const float wh = bb ? ih.w1 : ih.w0;
+        const int64_t rowbase = (((int64_t)b * d + zd) * h + zh) * w;
+        const uint4 u0 = __ldg(x + (rowbase + iw.i0) * cg + g);
+        const uint4 u1 = __ldg(x + (rowbase + iw.i1) * cg + g);
+        const uint32_t a0[4] = {u0.x, u0.y, u0.z, u0.w};
+        const uint32_t a1[4] = {u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 p0 = unpack_bf162(a0[q]), p1 = unpack_bf162(a1[q]);
+          accd[2 * q + 0] += wh * (iw.w0 * p0.x + iw.w1 * p1.x);
+          accd[2 * q + 1] += wh * (iw.w0 * p0.y + iw.w1 * p1.y);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wd * accd[j];
+    }
+    out[t] = make_uint4(pack_bf162(acc[0], acc[1]), pack_bf162(acc[2], acc[3]),
+                        pack_bf162(acc[4], acc[5]), pack_bf162(acc[6], acc[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6 lobe-masked (or plain) mean of each dense channel.
+// grid = (blocks, ch, n).  sums: double [n][ch+1] (last slot = sum of mask / voxel count).
+// ---------------------------------------------------------------------------------------
+__global__ void masked_pool_partial_kernel(const float *__restrict__ dense,
+                                           const uint8_t *__restrict__ mask, double *__restrict__ sums,
+                                           int ch, int d, int h, int w, int md, int mh, int mw) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int64_t plane = (int64_t)d * h * w;
+  const float *src = dense + ((int64_t)b * ch + c) * plane;
+  const uint8_t *mk = mask ? mask + (int64_t)b * md * mh * mw : nullptr;
+  double s = 0.0, ms = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float m = 1.0f;
+    if (mk) {
+      const int xw = (int)(i % w);
+      const int64_t r = i / w;
+      const int xh = (int)(r % h);
+      const int xd = (int)(r / h);
+      const int zd = nearest_index(xd, md, d), zh = nearest_index(xh, mh, h), zw = nearest_index(xw, mw, w);
+      m = mk[((int64_t)zd * mh + zh) * mw + zw] ? 1.0f : 0.0f;
+    }
+    s += (double)(__ldg(src + i) * m);
+    ms += (double)m;
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[(int64_t)b * (ch + 1) + c], s);
+  if (c == 0) {
+    ms = block_sum(ms, scratch);
+    if (threadIdx.x == 0) atomicAdd(&sums[(int64_t)b * (ch + 1) + ch], ms);
+  }
+}
+__global__ void masked_pool_finalize_kernel(const double *__restrict__ sums, float *__restrict__ out,
+                                            int n, int ch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * ch) return;
+  const int b = i / ch, c = i % ch;
+  out[i] = (float)sums[(int64_t)b * (ch + 1) + c] / (float)sums[(int64_t)b * (ch + 1) + ch];
+}
+
+// ---------------------------------------------------------------------------------------
+// K7 dRAM: both maps in one pass.  One thread per 4 consecutive output voxels along W when
+// W % 4 == 0 (float4 stores, uchar4 mask loads), scalar otherwise.
+// sums: double [2*n + n]: sum(out0[b]), sum(out1[b]), sum(lungs[b]).
+// ---------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void dram_upsample_mask_kernel(const float *__restrict__ dense0, const float *__restrict__ dense1,
+                                          const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
+                                          float *__restrict__ out0, float *__restrict__ out1,
+                                          double *__restrict__ sums, int n, int d, int h, int w, int D,
+                                          int H, int W, float sd, float sh, float sw, int blocks_per_sample) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x / blocks_per_sample;
+  const int blk = blockIdx.x - b * blocks_per_sample;
+  const int Wv = W / VEC;
+  const int64_t per_sample = (int64_t)D * H * Wv;
+  const int64_t splane = (int64_t)d * h * w;
+  const float *s0 = dense0 + (int64_t)b * splane;
+  const float *s1 = dense1 + (int64_t)b * splane;
+  double acc0 = 0.0, acc1 = 0.0, accl = 0.0;
+  for (int64_t t = (int64_t)blk * blockDim.x + threadIdx.x; t < per_sample;
+       t += (int64_t)blocks_per_sample * blockDim.x) {
+    const int xv = (int)(t % Wv);
+    const int64_t r = t / Wv;
+    const int xh = (int)(r % H);
+    const int xd = (int)(r / H);
+    const int64_t o = (((int64_t)b * D + xd) * H + xh) * W + (int64_t)xv * VEC;
+    uint8_t e[VEC], l[VEC];
+    if constexpr (VEC == 4) {
+      const uchar4 e4 = *reinterpret_cast<const uchar4 *>(ess + o);
+      const uchar4 l4 = *reinterpret_cast<const uchar4 *>(lungs + o);
+      e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+      l[0] = l4.x; l[1] = l4.y; l[2] = l4.z; l[3] = l4.w;
+    } else {
+      e[0] = ess[o];
+      l[0] = lungs[o];
+    }
+    const LinIdx id = lin_index_ac(xd, sd, d), ih = lin_index_ac(xh, sh, h);
+    const int64_t r00 = ((int64_t)id.i0 * h + ih.i0) * w, r01 = ((int64_t)id.i0 * h + ih.i1) * w;
+    const int64_t r10 = ((int64_t)id.i1 * h + ih.i0) * w, r11 = ((int64_t)id.i1 * h + ih.i1) * w;
+    float v0[VEC], v1[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float a = 0.0f, c = 0.0f;
+      if (e[j]) {  // the product with ess == 0 is an exact 0 either way; skip the 16 loads
+        const LinIdx iw = lin_index_ac(xv * VEC + j, sw, w);
+        a = id.w0 * (ih.w0 * (iw.w0 * __ldg(s0 + r00 + iw.i0) + iw.w1 * __ldg(s0 + r00 + iw.i1)) +
+                     ih.w1 * (iw.w0 * __ldg(s0 + r01 + iw.i0) + iw.w1 * __ldg(s0 + r01 + iw.i1))) +
+            id.w1 * (ih.w0 * (iw.w0 * __ldg(s0 + r10 + iw.i0) + iw.w1 * __ldg(s0 + r10 + iw.i1)) +
+                     ih.w1 * (iw.w0 * __ldg(s0 + r11 + iw.i0) + iw.w1 * __ldg(s0 + r11 + iw.i1)));
+        c = id.w0 * (ih.w0 * (iw.w0 * __ldg(s1 + r00 + iw.i0) + iw.w1 * __ldg(s1 + r00 + iw.i1)) +
+                     ih.w1 * (iw.w0 * __ldg(s1 + r01 + iw.i0) + iw.w1 * __ldg(s1 + r01 + iw.i1))) +
+            id.w1 * (ih.w0 * (iw.w0 * __ldg(s1 + r10 + iw.i0) + iw.w1 * __ldg(s1 + r10 + iw.i1)) +
+                     ih.w1 * (iw.w0 * __ldg(s1 + r11 + iw.i0) + iw.w1 * __ldg(s1 + r11 + iw.i1)));
+      }
+      v0[j] = a;
+      v1[j] = c;
+      acc0 += (double)a;
+      acc1 += (double)c;
+      accl += l[j] ? 1.0 : 0.0;
+    }
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<float4 *>(out0 + o) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+      *reinterpret_cast<float4 *>(out1 + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+    } else {
+      out0[o] = v0[0];
+      out1[o] = v1[0];
+    }
+  }
+  acc0 = block_sum(acc0, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[b], acc0);
+  acc1 = block_sum(acc1, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[n + b], acc1);
+  accl = block_sum(accl, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[2 * n + b], accl);
+}
+__global__ void dram_finalize_kernel(const double *__restrict__ sums, float *__restrict__ pct, int n,
+                                     int per_sample) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n) return;
+  const int b = i % n;
+  double den = 0.0;
+  if (per_sample) den = sums[2 * n + b];
+  else
+    for (int j = 0; j < n; ++j) den += sums[2 * n + j];
+  pct[i] = (float)sums[i] / (float)den;
+}
+
+// ---------------------------------------------------------------------------------------
+// K8 HU window + standardise: pass 1 accumulates sum and sum of squares of the windowed
+// values in fp64, pass 2 derives mean / unbiased std and writes (v - mean) / std in fp32.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float window_value(short hu, float lo, float hi) {
+  float f = (float)hu;
+  f = fminf(fmaxf(f, lo), hi);
+  return (f - lo) / (hi - lo);
+}
+__global__ void window_stats_kernel(const short *__restrict__ hu, double *__restrict__ sums,
+                                    int64_t count, float lo, float hi) {
+  __shared__ double scratch[32];
+  double s = 0.0, s2 = 0.0;
+  const int64_t nvec = count / 8;
+  const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(hv + i);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    float ls = 0.0f, ls2 = 0.0f;  // 8 values in [0,1]: fp32 is exact enough before widening
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float a = window_value((short)(uu[q] & 0xffff), lo, hi);
+      const float b = window_value((short)(uu[q] >> 16), lo, hi);
+      ls += a + b;
+      ls2 += a * a + b * b;
+    }
+    s += (double)ls;
+    s2 += (double)ls2;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = nvec * 8; i < count; ++i) {
+      const float a = window_value(hu[i], lo, hi);
+      s += (double)a;
+      s2 += (double)a * a;
+    }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[0], s);
+  s2 = block_sum(s2, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[1], s2);
+}
+__global__ void window_finalize_kernel(const double *__restrict__ sums, float *__restrict__ stats,
+                                       float *__restrict__ stats_out, int64_t count) {
+  const double n = (double)count;
+  const double mean = sums[0] / n;
+  double var = (sums[1] - n * mean * mean) / (n - 1.0);
+  if (var < 0.0) var = 0.0;
+  stats[0] = (float)mean;
+  stats[1] = (float)sqrt(var);
+  if (stats_out) {
+    stats_out[0] = stats[0];
+    stats_out[1] = stats[1];
+  }
+}
+__global__ void window_apply_kernel(const short *__restrict__ hu, float *__restrict__ out,
+                                    const float *__restrict__ stats, int64_t count, float lo, float hi) {
+  const float mean = stats[0], sd = stats[1];
+  const int64_t nvec = count / 8;
+  const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
+  float4 *ov = reinterpret_cast<float4 *>(out);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(hv + i);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f[2 * q + 0] = (window_value((short)(uu[q] & 0xffff), lo, hi) - mean) / sd;
+      f[2 * q + 1] = (window_value((short)(uu[q] >> 16), lo, hi) - mean) / sd;
+    }
+    ov[2 * i + 0] = make_float4(f[0], f[1], f[2], f[3]);
+    ov[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = nvec * 8; i < count; ++i) out[i] = (window_value(hu[i], lo, hi) - mean) / sd;
+}
+
+// ---------------------------------------------------------------------------------------
+// K8b Interpolate transform: in-plane bilinear (image) / legacy nearest (mask) + slice pick.
+// ---------------------------------------------------------------------------------------
+__global__ void resize_image_kernel(const float *__restrict__ x, float *__restrict__ out,
+                                    const int *__restrict__ d_idx, int H, int W, int D2, int H2, int W2,
+                                    float sh, float sw) {
+  const int64_t total = (int64_t)D2 * H2 * W2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(t % W2);
+    const int64_t r = t / W2;
+    const int xh = (int)(r % H2);
+    const int xd = (int)(r / H2);
+    const float *src = x + (int64_t)__ldg(d_idx + xd) * H * W;
+    const LinIdx ih = lin_index_ac(xh, sh, H), iw = lin_index_ac(xw, sw, W);
+    const float *r0 = src + (int64_t)ih.i0 * W, *r1 = src + (int64_t)ih.i1 * W;
+    out[t] = ih.w0 * (iw.w0 * __ldg(r0 + iw.i0) + iw.w1 * __ldg(r0 + iw.i1)) +
+             ih.w1 * (iw.w0 * __ldg(r1 + iw.i0) + iw.w1 * __ldg(r1 + iw.i1));
+  }
+}
+__global__ void resize_mask_kernel(const uint8_t *__restrict__ x, uint8_t *__restrict__ out,
+                                   const int *__restrict__ d_idx, int H, int W, int D2, int H2, int W2) {
+  const int64_t total = (int64_t)D2 * H2 * W2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(t % W2);
+    const int64_t r = t / W2;
+    const int xh = (int)(r % H2);
+    const int xd = (int)(r / H2);
+    const int zh = nearest_index(xh, H, H2), zw = nearest_index(xw, W, W2);
+    out[t] = x[((int64_t)__ldg(d_idx + xd) * H + zh) * W + zw] ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------------------
+__global__ void ncdhw_to_ndhwc_kernel(const float *__restrict__ x, bf16 *__restrict__ out, int n, int c,
+                                      int64_t plane) {
+  const int64_t total = (int64_t)n * c * plane;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(t % c);
+    const int64_t v = t / c;  // b*plane + s
+    const int64_t b = v / plane, s = v % plane;
+    out[t] = __float2bfloat16_rn(x[(b * c + ch) * plane + s]);
+  }
+}
+__global__ void ndhwc_to_ncdhw_kernel(const bf16 *__restrict__ x, float *__restrict__ out, int n, int c,
+                                      int64_t plane) {
+  const int64_t total = (int64_t)n * c * plane;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = t % plane;
+    const int64_t r = t / plane;  // b*c + ch
+    const int64_t b = r / c;
+    const int ch = (int)(r % c);
+    out[t] = __bfloat162float(x[(b * plane + s) * c + ch]);
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+static const int kThreads = 256;
+
+extern "C" int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                                void *stream) {
+  DRAM_REQUIRE(x && out, "dram_stem_expand: null pointer");
+  DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, "dram_stem_expand: empty volume");
+  const int h2 = (h - 1) / 2 + 1, w2 = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)n * d * h2 * w2 * 8;
+  stem_expand_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<uint4 *>(out), n, d, h, w, h2, w2);
+  DRAM_CHECK_LAUNCH("stem_expand_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                              int32_t c, void *stream) {
+  DRAM_REQUIRE(x && out, "dram_maxpool3d: null pointer");
+  DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
+               "dram_maxpool3d: bad shape (c must be a multiple of 8)");
+  const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
+  const int64_t total = (int64_t)n * od * oh * ow * (c / 8);
+  maxpool3d_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow);
+  DRAM_CHECK_LAUNCH("maxpool3d_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                               int32_t c, void *stream) {
+  DRAM_REQUIRE(x && out, "dram_upsample2x: null pointer");
+  DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
+               "dram_upsample2x: bad shape (c must be a multiple of 8)");
+  const int64_t total = (int64_t)n * d * h * w * 8 * (c / 8);
+  upsample2x_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8,
+      ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w));
+  DRAM_CHECK_LAUNCH("upsample2x_kernel");
+  return DRAM_OK;
+}
+
+extern "C" size_t dram_pool_workspace_bytes(int32_t n, int32_t ch) {
+  if (n <= 0 || ch <= 0) return 0;
+  return sizeof(double) * (size_t)n * (size_t)(ch + 1);
+}
+
+extern "C" int dram_masked_pool(const float *dense, const uint8_t *mask, float *out, void *workspace,
+                                int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w, int32_t md,
+                                int32_t mh, int32_t mw, void *stream) {
+  DRAM_REQUIRE(dense && out && workspace, "dram_masked_pool: null pointer");
+  DRAM_REQUIRE(n > 0 && ch > 0 && ch <= 65535 && d > 0 && h > 0 && w > 0, "dram_masked_pool: bad shape");
+  DRAM_REQUIRE(mask == nullptr || (md > 0 && mh > 0 && mw > 0), "dram_masked_pool: bad mask shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_cuda(cudaMemsetAsync(workspace, 0, dram_pool_workspace_bytes(n, ch), st),
+                      "dram_masked_pool memset");
+  if (rc != DRAM_OK) return rc;
+  const int64_t plane = (int64_t)d * h * w;
+  int blocks = stream_grid(plane, kThreads, 4);
+  int per = blocks / (n * ch);
+  if (per < 1) per = 1;
+  dim3 grid(per, ch, n);
+  masked_pool_partial_kernel<<<grid, kThreads, 0, st>>>(dense, mask, reinterpret_cast<double *>(workspace),
+                                                        ch, d, h, w, md, mh, mw);
+  DRAM_CHECK_LAUNCH("masked_pool_partial_kernel");
+  masked_pool_finalize_kernel<<<ceil_div(n * ch, 128), 128, 0, st>>>(
+      reinterpret_cast<const double *>(workspace), out, n, ch);
+  DRAM_CHECK_LAUNCH("masked_pool_finalize_kernel");
+  return DRAM_OK;
+}
+
+extern "C" size_t dram_dram_workspace_bytes(int32_t n) {
+  if (n <= 0) return 0;
+  return sizeof(double) * 3 * (size_t)n;
+}
+
+extern "C" int dram_dram_upsample_mask(const float *dense0, const float *dense1, const uint8_t *ess,
+                                       const uint8_t *lungs, float *out0, float *out1, float *pct,
+                                       void *workspace, int32_t n, int32_t d, int32_t h, int32_t w,
+                                       int32_t D, int32_t H, int32_t W, int32_t per_sample_denominator,
+                                       void *stream) {
+  DRAM_REQUIRE(dense0 && dense1 && ess && lungs && out0 && out1 && pct && workspace,
+               "dram_dram_upsample_mask: null pointer");
+  DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && D > 0 && H > 0 && W > 0,
+               "dram_dram_upsample_mask: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_cuda(cudaMemsetAsync(workspace, 0, dram_dram_workspace_bytes(n), st),
+                      "dram_dram_upsample_mask memset");
+  if (rc != DRAM_OK) return rc;
+  const float sd = ac_scale(d, D), sh = ac_scale(h, H), sw = ac_scale(w, W);
+  const bool vec = (W % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 4 == 0) &&
+                   (((uintptr_t)out0 | (uintptr_t)out1) % 16 == 0);
+  const int64_t per_sample = (int64_t)D * H * (vec ? W / 4 : W);
+  int bps = stream_grid(per_sample, kThreads, 8) / n;
+  if (bps < 1) bps = 1;
+  double *sums = reinterpret_cast<double *>(workspace);
+  if (vec)
+    dram_upsample_mask_kernel<4><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
+                                                               n, d, h, w, D, H, W, sd, sh, sw, bps);
+  else
+    dram_upsample_mask_kernel<1><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
+                                                               n, d, h, w, D, H, W, sd, sh, sw, bps);
+  DRAM_CHECK_LAUNCH("dram_upsample_mask_kernel");
+  dram_finalize_kernel<<<ceil_div(2 * n, 128), 128, 0, st>>>(sums, pct, n, per_sample_denominator);
+  DRAM_CHECK_LAUNCH("dram_finalize_kernel");
+  return DRAM_OK;
+}
+
+extern "C" size_t dram_preprocess_workspace_bytes(void) { return 2 * sizeof(double) + 2 * sizeof(float); }
+
+extern "C" int dram_window_standardize(const int16_t *hu, float *out, float *stats_out, void *workspace,
+                                       int64_t count, float lo, float hi, void *stream) {
+  DRAM_REQUIRE(hu && out && workspace, "dram_window_standardize: null pointer");
+  DRAM_REQUIRE(count > 1, "dram_window_standardize: need at least 2 voxels for an unbiased std");
+  DRAM_REQUIRE(hi > lo, "dram_window_standardize: empty window");
+  DRAM_REQUIRE(((uintptr_t)hu % 16 == 0) && ((uintptr_t)out % 16 == 0),
+               "dram_window_standardize: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  double *sums = reinterpret_cast<double *>(workspace);
+  float *stats = reinterpret_cast<float *>(sums + 2);
+  int rc = check_cuda(cudaMemsetAsync(workspace, 0, dram_preprocess_workspace_bytes(), st),
+                      "dram_window_standardize memset");
+  if (rc != DRAM_OK) return rc;
+  const int grid = stream_grid(count / 8 + 1, kThreads, 8);
+  window_stats_kernel<<<grid, kThreads, 0, st>>>(hu, sums, count, lo, hi);
+  DRAM_CHECK_LAUNCH("window_stats_kernel");
+  window_finalize_kernel<<<1, 1, 0, st>>>(sums, stats, stats_out, count);
+  DRAM_CHECK_LAUNCH("window_finalize_kernel");
+  window_apply_kernel<<<grid, kThreads, 0, st>>>(hu, out, stats, count, lo, hi);
+  DRAM_CHECK_LAUNCH("window_apply_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_resize_image(const float *x, float *out, const int32_t *d_idx, int32_t D, int32_t H,
+                                 int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream) {
+  DRAM_REQUIRE(x && out && d_idx, "dram_resize_image: null pointer");
+  DRAM_REQUIRE(D > 0 && H > 0 && W > 0 && D2 > 0 && H2 > 0 && W2 > 0, "dram_resize_image: bad shape");
+  const int64_t total = (int64_t)D2 * H2 * W2;
+  resize_image_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, out, d_idx, H, W, D2, H2, W2, ac_scale(H, H2), ac_scale(W, W2));
+  DRAM_CHECK_LAUNCH("resize_image_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_resize_mask(const uint8_t *x, uint8_t *out, const int32_t *d_idx, int32_t D, int32_t H,
+                                int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream) {
+  DRAM_REQUIRE(x && out && d_idx, "dram_resize_mask: null pointer");
+  DRAM_REQUIRE(D > 0 && H > 0 && W > 0 && D2 > 0 && H2 > 0 && W2 > 0, "dram_resize_mask: bad shape");
+  const int64_t total = (int64_t)D2 * H2 * W2;
+  resize_mask_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, out, d_idx, H, W, D2, H2, W2);
+  DRAM_CHECK_LAUNCH("resize_mask_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_ncdhw_f32_to_ndhwc_bf16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
+                                            int32_t h, int32_t w, void *stream) {
+  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ncdhw_f32_to_ndhwc_bf16: bad argument");
+  const int64_t plane = (int64_t)d * h * w;
+  ncdhw_to_ndhwc_kernel<<<stream_grid(plane * n * c, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      x, reinterpret_cast<bf16 *>(out), n, c, plane);
+  DRAM_CHECK_LAUNCH("ncdhw_to_ndhwc_kernel");
+  return DRAM_OK;
+}
+
+extern "C" int dram_ndhwc_bf16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
+                                            int32_t h, int32_t w, void *stream) {
+  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ndhwc_bf16_to_ncdhw_f32: bad argument");
+  const int64_t plane = (int64_t)d * h * w;
+  ndhwc_to_ncdhw_kernel<<<stream_grid(plane * n * c, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16 *>(x), out, n, c, plane);
+  DRAM_CHECK_LAUNCH("ndhwc_to_ncdhw_kernel");
+  return DRAM_OK;
+}

@@ -1,0 +1,749 @@
+// K1 — conv3d as an implicit GEMM on the sm_100a tensor cores.
+//
+//   A (activations) : NDHWC bf16.  One TMA box load per (filter tap, 64-channel chunk)
+//                     fetches the tap-shifted [td][th][tw][64] brick of the input straight
+//                     into the canonical K-major SWIZZLE_128B UMMA layout (128 rows x 128 B).
+//                     Zero padding = TMA out-of-bounds fill; dilation = tap offset;
+//                     stride = tensor-map elementStrides.  A second tensor map supplies the
+//                     channels of the skip tensor, so cat([up(x), skip]) is never built
+//                     (med3d.py:39-48, 85-89).
+//   B (weights)     : bf16 [Cout][tap][Cin] (K-major), BatchNorm scale folded in, one 2-D TMA
+//                     box per K-chunk.
+//   D (accumulator) : fp32 in TMEM, two buffers of BLOCK_N columns so the epilogue of tile i
+//                     overlaps the MMAs of tile i+1.
+//   Epilogue        : tcgen05.ld -> +bias -> +residual (full, or shortcut type A: strided
+//                     read, channels < res_c only; med3d.py:103-112,141) -> ReLU -> bf16
+//                     NDHWC store; for the 32-channel us3 layer optionally the 1x1x1 heads
+//                     (+sigmoid) in fp32 (med3d.py:329-332, 382 / 230-233, 283).
+//
+// Roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 lane 0 TMA
+// producer, warp 5 lane 0 MMA issuer (warp 5 also owns the TMEM allocation).
+// Persistent: grid <= #SMs, tile = blockIdx.x + i * gridDim.x, n-tile fastest.
+// Filter taps whose whole brick lies in the zero padding are skipped by producer and issuer.
+#include <cuda.h>
+
+#include "common.h"
+
+namespace dram {
+
+static constexpr int BLOCK_M = 128;       // output voxels per tile == TMEM lanes
+static constexpr int BLOCK_K = 64;        // bf16 channels per K-chunk == one 128-byte swizzle row
+static constexpr int UMMA_K = 16;         // K per tcgen05.mma for 16-bit inputs
+static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+static constexpr int NUM_THREADS = 192;
+static constexpr int PRODUCER_WARP = 4;
+static constexpr int MMA_WARP = 5;
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  // 1 KiB alignment slack + stages + barriers
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+};
+
+struct ConvKParams {
+  int n, Do, Ho, Wo, Di, Hi, Wi;
+  int cout;
+  int tw, th, td;              // tile extents (powers of two, product 128)
+  int tw_log2, th_log2;        // row -> (w,h,d) decode
+  int tiles_w, tiles_h, tiles_d, tiles_per_sample, num_n_tiles, total_tiles;
+  int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
+  int chunks1, chunks_total;   // 64-channel chunks of source 1 / of both sources
+  int relu;
+  const float *bias;
+  __nv_bfloat16 *out;
+  const __nv_bfloat16 *res;
+  int res_c, res_stride, res_d, res_h, res_w;
+  int n_heads, head_ch0, head_ch1, head_sigmoid, store_out;
+  const float *head_w;
+  const float *head_b;
+  float *head_out0;
+  float *head_out1;
+};
+
+// ----------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Waits for the phase with the given parity.  A wait longer than ~4 s of SM clocks is a
+// protocol bug: trap instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 8000000000LL) {
+      printf("dram_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+             blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has retired.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 8 rows * 128 B,
+// [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and
+// B, n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+struct TileCoord {
+  int n0, sample, d0, h0, w0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int tile, int block_n) {
+  TileCoord t;
+  int n_tile = tile % p.num_n_tiles;
+  int m_tile = tile / p.num_n_tiles;
+  t.n0 = n_tile * block_n;
+  t.sample = m_tile / p.tiles_per_sample;
+  int r = m_tile - t.sample * p.tiles_per_sample;
+  int iw = r % p.tiles_w;
+  int r2 = r / p.tiles_w;
+  int ih = r2 % p.tiles_h;
+  int id = r2 / p.tiles_h;
+  t.w0 = iw * p.tw;
+  t.h0 = ih * p.th;
+  t.d0 = id * p.td;
+  return t;
+}
+// True when every input coordinate the tile reads along one axis for this tap is padding.
+__device__ __forceinline__ bool tap_is_padding(int i0, int extent, int stride, int in_size) {
+  return (i0 + (extent - 1) * stride < 0) || (i0 >= in_size);
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
+                   const __grid_constant__ CUtensorMap map_a2,
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1 KiB alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == PRODUCER_WARP && lane == 0) {
+    prefetch_tensormap(&map_a1);
+    prefetch_tensormap(&map_a2);
+    prefetch_tensormap(&map_w);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BLOCK_N);
+        for (int zd = 0; zd < p.kd; ++zd) {
+          const int id0 = t.d0 * p.sd + zd * p.dd - p.pd;
+          if (tap_is_padding(id0, p.td, p.sd, p.Di)) continue;
+          for (int zh = 0; zh < p.kh; ++zh) {
+            const int ih0 = t.h0 * p.sh + zh * p.dh - p.ph;
+            if (tap_is_padding(ih0, p.th, p.sh, p.Hi)) continue;
+            for (int zw = 0; zw < p.kw; ++zw) {
+              const int iw0 = t.w0 * p.sw + zw * p.dw - p.pw;
+              if (tap_is_padding(iw0, p.tw, p.sw, p.Wi)) continue;
+              const int tap = (zd * p.kh + zh) * p.kw + zw;
+              for (int ch = 0; ch < p.chunks_total; ++ch) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                if (ch < p.chunks1)
+                  tma_load_5d(smem_a(stage), &map_a1, full_bar(stage), ch * BLOCK_K, iw0, ih0, id0,
+                              t.sample);
+                else
+                  tma_load_5d(smem_a(stage), &map_a2, full_bar(stage), (ch - p.chunks1) * BLOCK_K,
+                              iw0, ih0, id0, t.sample);
+                tma_load_2d(smem_b(stage), &map_w, full_bar(stage),
+                            (tap * p.chunks_total + ch) * BLOCK_K, t.n0);
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BLOCK_N);
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        uint32_t accumulate = 0;
+        for (int zd = 0; zd < p.kd; ++zd) {
+          if (tap_is_padding(t.d0 * p.sd + zd * p.dd - p.pd, p.td, p.sd, p.Di)) continue;
+          for (int zh = 0; zh < p.kh; ++zh) {
+            if (tap_is_padding(t.h0 * p.sh + zh * p.dh - p.ph, p.th, p.sh, p.Hi)) continue;
+            for (int zw = 0; zw < p.kw; ++zw) {
+              if (tap_is_padding(t.w0 * p.sw + zw * p.dw - p.pw, p.tw, p.sw, p.Wi)) continue;
+              for (int ch = 0; ch < p.chunks_total; ++ch) {
+                mbar_wait(full_bar(stage), phase);
+                tcgen05_fence_after();
+                const uint64_t da = make_sw128_desc(smem_a(stage));
+                const uint64_t db = make_sw128_desc(smem_b(stage));
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  // +32 bytes along K inside the 128-byte swizzle row = +2 in the >>4 address field
+                  umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                            accumulate);
+                  accumulate = 1;
+                }
+                umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+        }
+        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue warps 0..3 -------------------------------
+    const int row = warp * 32 + lane;  // TMEM lane == row of the 128-voxel tile
+    const int lw = row & (p.tw - 1);
+    const int lh = (row >> p.tw_log2) & (p.th - 1);
+    const int ld = row >> (p.tw_log2 + p.th_log2);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int od = t.d0 + ld, oh = t.h0 + lh, ow = t.w0 + lw;
+      const bool valid = (od < p.Do) && (oh < p.Ho) && (ow < p.Wo);
+      const size_t vox = (((size_t)t.sample * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+      const __nv_bfloat16 *res_row = nullptr;
+      if (p.res != nullptr && valid) {
+        const size_t rvox = (((size_t)t.sample * p.res_d + (size_t)od * p.res_stride) * p.res_h +
+                             (size_t)oh * p.res_stride) * p.res_w + (size_t)ow * p.res_stride;
+        res_row = p.res + rvox * p.res_c;
+      }
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        tmem_wait_ld();
+        if (valid) {
+          const int cg = t.n0 + c0;  // first global output channel of this 32-column group
+          float y[32];
+          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cg);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+            y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+            y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+            y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          }
+          if (res_row != nullptr && cg < p.res_c) {
+            const uint4 *r4 = reinterpret_cast<const uint4 *>(res_row + cg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = __ldg(r4 + j);
+              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[q]);
+                y[8 * j + 2 * q + 0] += __low2float(h2);
+                y[8 * j + 2 * q + 1] += __high2float(h2);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+          }
+          if (p.store_out) {
+            uint4 *o4 = reinterpret_cast<uint4 *>(p.out + vox * p.cout + cg);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * q], y[8 * j + 2 * q + 1]);
+                w[q] = *reinterpret_cast<const uint32_t *>(&h2);
+              }
+              o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (BLOCK_N == 32 && p.n_heads > 0) {
+            // 1x1x1 heads on the fp32 post-ReLU vector; dense maps are fp32 NCDHW.
+            const size_t plane = (size_t)p.Do * p.Ho * p.Wo;
+            const size_t sp = ((size_t)od * p.Ho + oh) * p.Wo + ow;
+            const int total = p.head_ch0 + p.head_ch1;
+            for (int hc = 0; hc < total; ++hc) {
+              const float4 *w4 = reinterpret_cast<const float4 *>(p.head_w + hc * 32);
+              float s = __ldg(p.head_b + hc);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w = __ldg(w4 + j);
+                s = fmaf(w.x, y[4 * j + 0], s);
+                s = fmaf(w.y, y[4 * j + 1], s);
+                s = fmaf(w.z, y[4 * j + 2], s);
+                s = fmaf(w.w, y[4 * j + 3], s);
+              }
+              if (p.head_sigmoid) s = 1.0f / (1.0f + expf(-s));
+              if (hc < p.head_ch0)
+                p.head_out0[((size_t)t.sample * p.head_ch0 + hc) * plane + sp] = s;
+              else
+                p.head_out1[((size_t)t.sample * p.head_ch1 + (hc - p.head_ch0)) * plane + sp] = s;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));  // 128 arrivals hand the accumulator back to the issuer
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Host side: tensor maps + plan
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *sym = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || sym == nullptr) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c,
+                          int bw, int bh, int bd, int sw, int sh, int sd) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return DRAM_E_DRIVER;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+  cuuint64_t gstr[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                        (cuuint64_t)d * h * w * c * 2};
+  // With a traversal stride s the box spans (t-1)*s+1 input elements and lands t of them.
+  cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)((bw - 1) * sw + 1),
+                       (cuuint32_t)((bh - 1) * sh + 1), (cuuint32_t)((bd - 1) * sd + 1), 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%dx%d box %dx%dx%d stride %d,%d,%d) -> %d",
+              n, d, h, w, c, bw, bh, bd, sw, sh, sd, (int)r);
+    return DRAM_E_DRIVER;
+  }
+  return DRAM_OK;
+}
+
+static int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64_t ktot,
+                             int block_n) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return DRAM_E_DRIVER;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)ktot, (cuuint64_t)cout};
+  cuuint64_t gstr[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weight %d x %lld, box_n %d) -> %d", cout, (long long)ktot,
+              block_n, (int)r);
+    return DRAM_E_DRIVER;
+  }
+  return DRAM_OK;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int conv_out(int in, int k, int s, int d, int p) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
+
+}  // namespace dram
+
+struct dram_conv_plan {
+  CUtensorMap map_a1, map_a2, map_w;
+  dram::ConvKParams p;
+  int block_n;
+  int stages;
+  size_t smem_bytes;
+  int64_t flops;
+  int m_tiles;
+};
+
+using namespace dram;
+
+extern "C" int dram_conv3d_out_dims(const dram_conv_desc *d, int32_t *dout, int32_t *hout,
+                                    int32_t *wout) {
+  DRAM_REQUIRE(d && dout && hout && wout, "dram_conv3d_out_dims: null argument");
+  DRAM_REQUIRE(d->sd > 0 && d->sh > 0 && d->sw > 0, "dram_conv3d_out_dims: stride must be positive");
+  *dout = conv_out(d->di, d->kd, d->sd, d->dd, d->pd);
+  *hout = conv_out(d->hi, d->kh, d->sh, d->dh, d->ph);
+  *wout = conv_out(d->wi, d->kw, d->sw, d->dw, d->pw);
+  return DRAM_OK;
+}
+
+template <int BN>
+static int set_smem_attr() {
+  return check_cuda(cudaFuncSetAttribute(conv3d_umma_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ConvCfg<BN>::SMEM_BYTES),
+                    "cudaFuncSetAttribute(conv3d_umma_kernel)");
+}
+
+extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,
+                                       const void *weight, const float *bias, const void *residual,
+                                       void *out, const float *head_w, const float *head_b,
+                                       float *head_out0, float *head_out1, dram_conv_plan **plan) {
+  DRAM_REQUIRE(d && plan, "dram_conv3d_plan_create: null descriptor or plan pointer");
+  *plan = nullptr;
+  DRAM_REQUIRE(src1 && weight && bias, "dram_conv3d_plan_create: src1, weight and bias are required");
+  DRAM_REQUIRE(d->n > 0 && d->di > 0 && d->hi > 0 && d->wi > 0, "conv3d: empty input");
+  DRAM_REQUIRE(d->c1 > 0 && d->c1 % 64 == 0, "conv3d: c1=%d must be a positive multiple of 64", d->c1);
+  DRAM_REQUIRE(d->c2 >= 0 && d->c2 % 64 == 0, "conv3d: c2=%d must be a multiple of 64", d->c2);
+  DRAM_REQUIRE((d->c2 == 0) == (src2 == nullptr), "conv3d: src2 must be given exactly when c2 > 0");
+  DRAM_REQUIRE(d->cout > 0 && d->cout % 32 == 0, "conv3d: cout=%d must be a multiple of 32", d->cout);
+  DRAM_REQUIRE(d->kd >= 1 && d->kh >= 1 && d->kw >= 1 && d->kd <= 7 && d->kh <= 7 && d->kw <= 7,
+               "conv3d: filter extent must be in 1..7");
+  DRAM_REQUIRE(d->sd >= 1 && d->sh >= 1 && d->sw >= 1 && d->sd <= 8 && d->sh <= 8 && d->sw <= 8,
+               "conv3d: stride must be in 1..8");
+  DRAM_REQUIRE(d->dd >= 1 && d->dh >= 1 && d->dw >= 1, "conv3d: dilation must be >= 1");
+  DRAM_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv3d: padding must be >= 0");
+  DRAM_REQUIRE(d->store_out == 0 || out != nullptr, "conv3d: out is required when store_out != 0");
+  DRAM_REQUIRE(d->store_out != 0 || d->n_heads > 0, "conv3d: nothing to write");
+
+  int Do, Ho, Wo;
+  dram_conv3d_out_dims(d, &Do, &Ho, &Wo);
+  DRAM_REQUIRE(Do > 0 && Ho > 0 && Wo > 0, "conv3d: empty output");
+
+  int block_n;
+  if (d->cout % 256 == 0) block_n = 256;
+  else if (d->cout % 128 == 0) block_n = 128;
+  else if (d->cout % 64 == 0) block_n = 64;
+  else block_n = 32;
+  if (d->cout == 32) block_n = 32;
+  DRAM_REQUIRE(d->cout % block_n == 0, "conv3d: cout=%d is not tileable", d->cout);
+
+  if (d->n_heads > 0) {
+    DRAM_REQUIRE(d->cout == 32, "conv3d: fused heads need cout == 32 (got %d)", d->cout);
+    DRAM_REQUIRE(d->n_heads <= 2 && head_w && head_b && head_out0, "conv3d: bad head arguments");
+    DRAM_REQUIRE(d->head_ch[0] >= 1 && (d->n_heads == 1 || (d->head_ch[1] >= 1 && head_out1)),
+                 "conv3d: bad head channel counts");
+    DRAM_REQUIRE(d->head_ch[0] + (d->n_heads == 2 ? d->head_ch[1] : 0) <= 16,
+                 "conv3d: at most 16 head channels");
+  }
+  if (d->res_c > 0) {
+    DRAM_REQUIRE(residual != nullptr, "conv3d: res_c > 0 but residual is NULL");
+    DRAM_REQUIRE(d->res_c % 32 == 0 && d->res_c <= d->cout, "conv3d: res_c=%d must be a multiple of 32 and <= cout", d->res_c);
+    DRAM_REQUIRE(d->res_stride >= 1, "conv3d: res_stride must be >= 1");
+    DRAM_REQUIRE((Do - 1) * d->res_stride < d->res_d && (Ho - 1) * d->res_stride < d->res_h &&
+                     (Wo - 1) * d->res_stride < d->res_w,
+                 "conv3d: residual tensor %dx%dx%d too small for output %dx%dx%d at stride %d",
+                 d->res_d, d->res_h, d->res_w, Do, Ho, Wo, d->res_stride);
+  }
+
+  // Tile shape: caller's choice or the candidate with the fewest tiles.
+  int tw = d->tw, th = d->th, td = d->td;
+  if (tw == 0 || th == 0 || td == 0) {
+    static const int cand[][3] = {{8, 4, 4}, {4, 8, 4}, {4, 4, 8}, {8, 8, 2},  {8, 2, 8}, {2, 8, 8},
+                                  {16, 4, 2}, {4, 16, 2}, {16, 2, 4}, {2, 16, 4}, {16, 8, 1}, {8, 16, 1},
+                                  {32, 4, 1}, {4, 32, 1}, {32, 2, 2}, {16, 1, 8}, {128, 1, 1}};
+    int64_t best = -1;
+    for (auto &c : cand) {
+      int64_t tiles = (int64_t)ceil_div(Wo, c[0]) * ceil_div(Ho, c[1]) * ceil_div(Do, c[2]);
+      if (best < 0 || tiles < best) {
+        best = tiles;
+        tw = c[0];
+        th = c[1];
+        td = c[2];
+      }
+    }
+  }
+  DRAM_REQUIRE(is_pow2(tw) && is_pow2(th) && is_pow2(td) && tw * th * td == BLOCK_M,
+               "conv3d: tile %dx%dx%d must be powers of two with product 128", tw, th, td);
+  DRAM_REQUIRE((tw - 1) * d->sw + 1 <= 256 && (th - 1) * d->sh + 1 <= 256 && (td - 1) * d->sd + 1 <= 256,
+               "conv3d: TMA box too large for tile/stride");
+
+  dram_conv_plan *pl = new dram_conv_plan();
+  memset(pl, 0, sizeof(*pl));
+  ConvKParams &p = pl->p;
+  p.n = d->n; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Di = d->di; p.Hi = d->hi; p.Wi = d->wi;
+  p.cout = d->cout;
+  p.tw = tw; p.th = th; p.td = td; p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
+  p.tiles_w = ceil_div(Wo, tw); p.tiles_h = ceil_div(Ho, th); p.tiles_d = ceil_div(Do, td);
+  p.tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
+  p.num_n_tiles = d->cout / block_n;
+  int64_t total = (int64_t)p.tiles_per_sample * d->n * p.num_n_tiles;
+  if (total > 0x7fffffffLL) {
+    delete pl;
+    set_error("conv3d: too many tiles");
+    return DRAM_E_ARG;
+  }
+  p.total_tiles = (int)total;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+  p.dd = d->dd; p.dh = d->dh; p.dw = d->dw; p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.chunks1 = d->c1 / BLOCK_K;
+  p.chunks_total = (d->c1 + d->c2) / BLOCK_K;
+  p.relu = d->relu;
+  p.bias = bias;
+  p.out = reinterpret_cast<__nv_bfloat16 *>(out);
+  p.res = d->res_c > 0 ? reinterpret_cast<const __nv_bfloat16 *>(residual) : nullptr;
+  p.res_c = d->res_c; p.res_stride = d->res_stride > 0 ? d->res_stride : 1;
+  p.res_d = d->res_d; p.res_h = d->res_h; p.res_w = d->res_w;
+  p.n_heads = d->n_heads;
+  p.head_ch0 = d->n_heads > 0 ? d->head_ch[0] : 0;
+  p.head_ch1 = d->n_heads > 1 ? d->head_ch[1] : 0;
+  p.head_sigmoid = d->head_sigmoid;
+  p.store_out = d->store_out;
+  p.head_w = head_w; p.head_b = head_b; p.head_out0 = head_out0; p.head_out1 = head_out1;
+
+  const int taps = d->kd * d->kh * d->kw;
+  const int64_t ktot = (int64_t)taps * (d->c1 + d->c2);
+  pl->block_n = block_n;
+  pl->m_tiles = p.tiles_per_sample * d->n;
+  pl->flops = 2LL * d->n * Do * Ho * Wo * (int64_t)d->cout * ktot;
+
+  int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, tw, th, td, d->sw,
+                          d->sh, d->sd);
+  if (rc == DRAM_OK) {
+    if (d->c2 > 0)
+      rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, tw, th, td, d->sw,
+                          d->sh, d->sd);
+    else
+      pl->map_a2 = pl->map_a1;
+  }
+  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n);
+  if (rc == DRAM_OK) {
+    switch (block_n) {
+      case 32: pl->stages = ConvCfg<32>::STAGES; pl->smem_bytes = ConvCfg<32>::SMEM_BYTES; rc = set_smem_attr<32>(); break;
+      case 64: pl->stages = ConvCfg<64>::STAGES; pl->smem_bytes = ConvCfg<64>::SMEM_BYTES; rc = set_smem_attr<64>(); break;
+      case 128: pl->stages = ConvCfg<128>::STAGES; pl->smem_bytes = ConvCfg<128>::SMEM_BYTES; rc = set_smem_attr<128>(); break;
+      default: pl->stages = ConvCfg<256>::STAGES; pl->smem_bytes = ConvCfg<256>::SMEM_BYTES; rc = set_smem_attr<256>(); break;
+    }
+  }
+  if (rc != DRAM_OK) {
+    delete pl;
+    return rc;
+  }
+  *plan = pl;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_plan_destroy(dram_conv_plan *plan) {
+  delete plan;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops, int32_t *m_tiles,
+                                     int32_t *n_tiles, int32_t *block_n, int32_t *stages) {
+  DRAM_REQUIRE(plan, "dram_conv3d_plan_info: null plan");
+  if (flops) *flops = plan->flops;
+  if (m_tiles) *m_tiles = plan->m_tiles;
+  if (n_tiles) *n_tiles = plan->p.num_n_tiles;
+  if (block_n) *block_n = plan->block_n;
+  if (stages) *stages = plan->stages;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, void *stream) {
+  DRAM_REQUIRE(plan, "dram_conv3d_run: null plan");
+  int ctas = sm_count();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  if (plan->p.total_tiles < ctas) ctas = plan->p.total_tiles;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ctas), block(NUM_THREADS);
+  switch (plan->block_n) {
+    case 32:
+      conv3d_umma_kernel<32><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
+      break;
+    case 64:
+      conv3d_umma_kernel<64><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
+      break;
+    case 128:
+      conv3d_umma_kernel<128><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
+      break;
+    default:
+      conv3d_umma_kernel<256><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
+      break;
+  }
+  DRAM_CHECK_LAUNCH("conv3d_umma_kernel launch");
+  return DRAM_OK;
+}

@@ -1,0 +1,329 @@
+"""Torch-facing wrappers of the C-ABI kernels (one function per kernel family of SURVEY §7.1b).
+
+Each wrapper checks shapes/dtypes, allocates the output with torch's caching allocator, passes
+raw device pointers plus the current CUDA stream to libdram_b200.so and returns torch tensors.
+Stateless kernels are also registered as `torch.library` custom ops in the `dram_b200::`
+namespace so they show up in profiler traces and can be captured into CUDA graphs.
+
+Activations are NDHWC bf16: a tensor of shape [N, D, H, W, C].  There is no CPU path: every
+function raises on a non-CUDA tensor.
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import ConvDesc, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (libdram_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def sm_count():
+    return _capi.load().dram_sm_count()
+
+
+# --------------------------------------------------------------------------------------------
+# K1 conv3d
+# --------------------------------------------------------------------------------------------
+def _triple(v):
+    return (v, v, v) if isinstance(v, int) else tuple(v)
+
+
+class Conv3dPlan:
+    """A frozen conv3d launch: TMA tensor maps for fixed buffers + geometry.
+
+    x1 (and optional x2, concatenated after x1 along channels) are NDHWC bf16; `weight` is the
+    packed bf16 [Cout, taps*(C1+C2)] matrix from `pack_conv_weight`; `bias` fp32 [Cout].
+    `residual` is NDHWC bf16 with `res_c <= Cout` channels read at `res_stride` (shortcut A).
+    `heads = (head_w [sum_ch, 32] fp32, head_b [sum_ch] fp32, (ch0, ch1), sigmoid)` fuses the
+    1x1x1 heads into the epilogue of a 32-channel conv.
+    """
+
+    def __init__(self, x1, weight, bias, *, x2=None, kernel=3, stride=1, dilation=1, padding=None,
+                 relu=True, residual=None, res_stride=1, heads=None, store_out=True, out=None,
+                 tile=None):
+        lib = _capi.load()
+        _need(x1, torch.bfloat16, "conv3d x1", 5)
+        n, di, hi, wi, c1 = x1.shape
+        c2 = 0
+        if x2 is not None:
+            _need(x2, torch.bfloat16, "conv3d x2", 5)
+            if tuple(x2.shape[:4]) != (n, di, hi, wi):
+                raise ValueError(f"conv3d: x2 {tuple(x2.shape)} does not match x1 {tuple(x1.shape)}")
+            c2 = x2.shape[4]
+        k, s, dl = _triple(kernel), _triple(stride), _triple(dilation)
+        pad = tuple(dl[i] * (k[i] - 1) // 2 for i in range(3)) if padding is None else _triple(padding)
+        _need(weight, torch.bfloat16, "conv3d weight", 2)
+        _need(bias, torch.float32, "conv3d bias", 1)
+        cout = weight.shape[0]
+        taps = k[0] * k[1] * k[2]
+        if weight.shape[1] != taps * (c1 + c2):
+            raise ValueError(f"conv3d: packed weight K={weight.shape[1]} != taps*(c1+c2)={taps * (c1 + c2)}")
+        if bias.shape[0] != cout:
+            raise ValueError("conv3d: bias length != cout")
+
+        d = ConvDesc()
+        d.n, d.di, d.hi, d.wi, d.c1, d.c2, d.cout = n, di, hi, wi, c1, c2, cout
+        d.kd, d.kh, d.kw = k
+        d.sd, d.sh, d.sw = s
+        d.dd, d.dh, d.dw = dl
+        d.pd, d.ph, d.pw = pad
+        d.relu = 1 if relu else 0
+        if residual is not None:
+            _need(residual, torch.bfloat16, "conv3d residual", 5)
+            d.res_c = residual.shape[4]
+            d.res_stride = res_stride
+            d.res_d, d.res_h, d.res_w = residual.shape[1:4]
+            if residual.shape[0] != n:
+                raise ValueError("conv3d: residual batch mismatch")
+        else:
+            d.res_stride = 1
+        head_w = head_b = None
+        if heads is not None:
+            head_w, head_b, head_ch, sigmoid = heads
+            _need(head_w, torch.float32, "conv3d head_w", 2)
+            _need(head_b, torch.float32, "conv3d head_b", 1)
+            d.n_heads = len(head_ch)
+            for i, ch in enumerate(head_ch):
+                d.head_ch[i] = ch
+            d.head_sigmoid = 1 if sigmoid else 0
+            if head_w.shape != (sum(head_ch), 32) or head_b.shape[0] != sum(head_ch):
+                raise ValueError("conv3d: head weight/bias shape mismatch")
+        d.store_out = 1 if store_out else 0
+        if tile is not None:
+            d.tw, d.th, d.td = tile
+
+        do, ho, wo = C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.dram_conv3d_out_dims(C.byref(d), C.byref(do), C.byref(ho), C.byref(wo)), "dram_conv3d_out_dims")
+        self.out_shape = (n, do.value, ho.value, wo.value, cout)
+        if store_out:
+            if out is None:
+                out = torch.empty(self.out_shape, dtype=torch.bfloat16, device=x1.device)
+            else:
+                _need(out, torch.bfloat16, "conv3d out", 5)
+                if tuple(out.shape) != self.out_shape:
+                    raise ValueError(f"conv3d: out shape {tuple(out.shape)} != {self.out_shape}")
+        else:
+            out = None
+        self.out = out
+        self.head_outs = []
+        if heads is not None:
+            for ch in heads[2]:
+                self.head_outs.append(torch.empty((n, ch, do.value, ho.value, wo.value), dtype=torch.float32,
+                                                  device=x1.device))
+        ho0 = self.head_outs[0] if len(self.head_outs) > 0 else None
+        ho1 = self.head_outs[1] if len(self.head_outs) > 1 else None
+
+        handle = C.c_void_p()
+        check(lib.dram_conv3d_plan_create(C.byref(d), _p(x1), _p(x2), _p(weight), _p(bias), _p(residual),
+                                          _p(out), _p(head_w), _p(head_b), _p(ho0), _p(ho1),
+                                          C.byref(handle)), "dram_conv3d_plan_create")
+        self._handle = handle
+        self._lib = lib
+        # keep every buffer the tensor maps point at alive for the life of the plan
+        self._keep = (x1, x2, weight, bias, residual, out, head_w, head_b, ho0, ho1)
+        flops, mt, nt, bn, st = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.dram_conv3d_plan_info(handle, C.byref(flops), C.byref(mt), C.byref(nt), C.byref(bn),
+                                        C.byref(st)), "dram_conv3d_plan_info")
+        self.flops, self.m_tiles, self.n_tiles, self.block_n, self.stages = (
+            flops.value, mt.value, nt.value, bn.value, st.value)
+        self.desc = d
+
+    def run(self, max_ctas=0):
+        check(self._lib.dram_conv3d_run(self._handle, max_ctas, _stream()), "dram_conv3d_run")
+        return self.out
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.dram_conv3d_plan_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+
+def pack_conv_weight(weight, scale=None, splits=None):
+    """[Cout, Cin, kd, kh, kw] fp32 -> bf16 [Cout, kd*kh*kw*Cin] (tap-major, channel-minor).
+
+    `scale` (fp32 [Cout]) is the folded BatchNorm factor gamma/sqrt(var+eps), multiplied in
+    fp32 before the single rounding to bf16.
+    """
+    w = weight.detach().to(torch.float32)
+    if scale is not None:
+        w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
+    cout = w.shape[0]
+    return w.permute(0, 2, 3, 4, 1).reshape(cout, -1).to(torch.bfloat16).contiguous()
+
+
+def fold_bn(bn, conv_bias=None, eps=None):
+    """Eval-mode BatchNorm3d as (scale, shift) fp32: y = conv*scale + shift."""
+    eps = bn.eps if eps is None else eps
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.detach().float() * scale
+    return scale, shift
+
+
+# --------------------------------------------------------------------------------------------
+# stateless kernels
+# --------------------------------------------------------------------------------------------
+def stem_expand(x, out=None):
+    """fp32 [N, D, H, W] -> bf16 [N, D, ceil(H/2), ceil(W/2), 64] (K2a)."""
+    _need(x, torch.float32, "stem_expand x", 4)
+    n, d, h, w = x.shape
+    shape = (n, d, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    check(_capi.load().dram_stem_expand(_p(x), _p(out), n, d, h, w, _stream()), "dram_stem_expand")
+    return out
+
+
+def pack_stem_weight(weight, scale=None):
+    """conv1.weight [64, 1, 7, 7, 7] -> bf16 [64, 7*64] matching `stem_expand` (k = kd*64 + kh*8 + kw)."""
+    w = weight.detach().to(torch.float32)
+    if scale is not None:
+        w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
+    cout = w.shape[0]
+    packed = torch.zeros((cout, 7, 8, 8), dtype=torch.float32, device=w.device)
+    packed[:, :, :7, :7] = w[:, 0]
+    return packed.reshape(cout, 7 * 64).to(torch.bfloat16).contiguous()
+
+
+def maxpool3d(x, out=None):
+    _need(x, torch.bfloat16, "maxpool3d x", 5)
+    n, d, h, w, c = x.shape
+    shape = (n, (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    check(_capi.load().dram_maxpool3d(_p(x), _p(out), n, d, h, w, c, _stream()), "dram_maxpool3d")
+    return out
+
+
+def upsample2x(x, out=None):
+    _need(x, torch.bfloat16, "upsample2x x", 5)
+    n, d, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, 2 * d, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    check(_capi.load().dram_upsample2x(_p(x), _p(out), n, d, h, w, c, _stream()), "dram_upsample2x")
+    return out
+
+
+def masked_pool(dense, mask=None):
+    """dense fp32 [N, C, d, h, w]; mask uint8 [N, D, H, W] or None -> fp32 [N, C]."""
+    lib = _capi.load()
+    _need(dense, torch.float32, "masked_pool dense", 5)
+    n, ch, d, h, w = dense.shape
+    md = mh = mw = 0
+    if mask is not None:
+        _need(mask, torch.uint8, "masked_pool mask", 4)
+        if mask.shape[0] != n:
+            raise ValueError("masked_pool: mask batch mismatch")
+        md, mh, mw = mask.shape[1:]
+    ws = torch.empty(lib.dram_pool_workspace_bytes(n, ch), dtype=torch.uint8, device=dense.device)
+    out = torch.empty((n, ch), dtype=torch.float32, device=dense.device)
+    check(lib.dram_masked_pool(_p(dense), _p(mask), _p(out), _p(ws), n, ch, d, h, w, md, mh, mw, _stream()),
+          "dram_masked_pool")
+    return out
+
+
+def dram_upsample_mask(dense0, dense1, ess, lungs, size, per_sample_denominator=False):
+    """K7: returns (out0, out1 fp32 [N,1,D,H,W], pct fp32 [2, N])."""
+    lib = _capi.load()
+    _need(dense0, torch.float32, "dram dense0", 5)
+    _need(dense1, torch.float32, "dram dense1", 5)
+    _need(ess, torch.uint8, "dram ess", 4)
+    _need(lungs, torch.uint8, "dram lungs", 4)
+    n, ch, d, h, w = dense0.shape
+    if ch != 1 or dense1.shape != dense0.shape:
+        raise ValueError("dram_upsample_mask: dense maps must be [N,1,d,h,w] and alike")
+    D, H, W = size
+    if tuple(ess.shape) != (n, D, H, W) or tuple(lungs.shape) != (n, D, H, W):
+        raise ValueError("dram_upsample_mask: mask shape mismatch")
+    out0 = torch.empty((n, 1, D, H, W), dtype=torch.float32, device=dense0.device)
+    out1 = torch.empty_like(out0)
+    pct = torch.empty((2, n), dtype=torch.float32, device=dense0.device)
+    ws = torch.empty(lib.dram_dram_workspace_bytes(n), dtype=torch.uint8, device=dense0.device)
+    check(lib.dram_dram_upsample_mask(_p(dense0), _p(dense1), _p(ess), _p(lungs), _p(out0), _p(out1), _p(pct),
+                                      _p(ws), n, d, h, w, D, H, W, 1 if per_sample_denominator else 0,
+                                      _stream()), "dram_dram_upsample_mask")
+    return out0, out1, pct
+
+
+def window_standardize(hu, lo=-1150.0, hi=-300.0, out=None):
+    """K8: int16 HU volume (any shape, one volume) -> fp32 standardised window; returns (out, stats)."""
+    lib = _capi.load()
+    _need(hu, torch.int16, "window_standardize hu")
+    if out is None:
+        out = torch.empty(hu.shape, dtype=torch.float32, device=hu.device)
+    stats = torch.empty(2, dtype=torch.float32, device=hu.device)
+    ws = torch.empty(lib.dram_preprocess_workspace_bytes(), dtype=torch.uint8, device=hu.device)
+    check(lib.dram_window_standardize(_p(hu), _p(out), _p(stats), _p(ws), hu.numel(), lo, hi, _stream()),
+          "dram_window_standardize")
+    return out, stats
+
+
+def slice_index(d_in, d_out, device):
+    """The D-slice pick of Interpolate (spatial_transforms.py:66), built with the same torch ops."""
+    return torch.linspace(0, d_in - 1, d_out).long().to(torch.int32).to(device)
+
+
+def resize_image(x, size):
+    _need(x, torch.float32, "resize_image x", 3)
+    D, H, W = x.shape
+    D2, H2, W2 = size
+    idx = slice_index(D, D2, x.device)
+    out = torch.empty((D2, H2, W2), dtype=torch.float32, device=x.device)
+    check(_capi.load().dram_resize_image(_p(x), _p(out), _p(idx), D, H, W, D2, H2, W2, _stream()),
+          "dram_resize_image")
+    return out
+
+
+def resize_mask(x, size):
+    _need(x, torch.uint8, "resize_mask x", 3)
+    D, H, W = x.shape
+    D2, H2, W2 = size
+    idx = slice_index(D, D2, x.device)
+    out = torch.empty((D2, H2, W2), dtype=torch.uint8, device=x.device)
+    check(_capi.load().dram_resize_mask(_p(x), _p(out), _p(idx), D, H, W, D2, H2, W2, _stream()),
+          "dram_resize_mask")
+    return out
+
+
+def to_ndhwc_bf16(x):
+    """fp32 NCDHW -> bf16 NDHWC."""
+    _need(x, torch.float32, "to_ndhwc_bf16 x", 5)
+    n, c, d, h, w = x.shape
+    out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
+    check(_capi.load().dram_ncdhw_f32_to_ndhwc_bf16(_p(x), _p(out), n, c, d, h, w, _stream()),
+          "dram_ncdhw_f32_to_ndhwc_bf16")
+    return out
+
+
+def to_ncdhw_f32(x):
+    """bf16 NDHWC -> fp32 NCDHW."""
+    _need(x, torch.bfloat16, "to_ncdhw_f32 x", 5)
+    n, d, h, w, c = x.shape
+    out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
+    check(_capi.load().dram_ndhwc_bf16_to_ncdhw_f32(_p(x), _p(out), n, c, d, h, w, _stream()),
+          "dram_ndhwc_bf16_to_ncdhw_f32")
+    return out

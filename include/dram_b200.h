@@ -1,0 +1,195 @@
+/*
+ * dram_b200.h — C-ABI of libdram_b200.so: the B200 (sm_100a) device side of the
+ * Med3D + dRAM inference hot path of DIAGNijmegen/bodyct-dram-emph-subtype.
+ *
+ * The reference has no native code: every entry below replaces a call site in
+ * the reference's Python that reaches a stock ATen/cuDNN kernel.  The citation
+ * on each function names that call site (file:line relative to the reference
+ * checkout).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer owned by the caller unless the
+ *     name says host; nothing here allocates device memory, synchronises the
+ *     device or changes the current device;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
+ *   - activations are NDHWC bf16 ("channels-last 3-D"), dense maps and
+ *     scores are fp32 NCDHW exactly as the reference returns them;
+ *   - return value: 0 = DRAM_OK, negative = DRAM_E_*; a message for the last
+ *     failure on the calling thread is available from dram_last_error();
+ *   - re-entrant; the only global state is the per-thread error string and
+ *     the lazily resolved driver entry point for tensor-map encoding.
+ */
+#ifndef DRAM_B200_H_
+#define DRAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRAM_OK 0
+#define DRAM_E_ARG (-1)     /* bad argument / unsupported shape            */
+#define DRAM_E_ARCH (-2)    /* device is not sm_100                         */
+#define DRAM_E_LAUNCH (-3)  /* CUDA launch / runtime error                  */
+#define DRAM_E_DRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed  */
+
+#define DRAM_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------- */
+int dram_version(void);
+/* Copies the calling thread's last error text (NUL terminated) into buf. */
+int dram_last_error(char *buf, size_t len);
+/* Number of SMs of the current device (persistent-grid sizing). */
+int dram_sm_count(void);
+
+/* ---- K1: conv3d implicit GEMM on tcgen05/TMEM, fed by TMA -------------- */
+/*
+ * Replaces every nn.Conv3d + BatchNorm3d(eval) + ReLU (+ residual add,
+ * + shortcut-A) of the network:
+ *   med3d.py:93-100 (conv3x3x3), 152-157 (Bottleneck convs), 129-144 and
+ *   164-184 (block forward: bn, relu, `out += residual`), 103-112 (shortcut
+ *   A), 67/76 (decoder convs, bias=True), 85-89 (crop_concat as a second
+ *   K-source), 226-233 / 325-332 (us3 + fcs heads), 382 (sigmoid).
+ * The stem (med3d.py:296-304) runs through the same kernel after
+ * dram_stem_expand() has unfolded (kh,kw) into 64 pseudo-channels.
+ *
+ * GEMM view: M = N*Do*Ho*Wo output voxels (tiles of tw*th*td = 128 voxels),
+ * N = Cout, K = taps * (C1 + C2).  Weights are packed by the caller as bf16
+ * [Cout][kd][kh][kw][C1+C2] (K-major) with the eval BatchNorm scale folded in;
+ * `bias` is the folded fp32 per-channel shift.
+ */
+typedef struct dram_conv_desc {
+  /* input geometry (source 1; source 2, if any, has identical N,D,H,W) */
+  int32_t n, di, hi, wi;
+  int32_t c1;          /* channels of source 1, multiple of 64               */
+  int32_t c2;          /* channels of source 2 (concat after source 1), or 0 */
+  /* filter */
+  int32_t cout;        /* multiple of 32                                     */
+  int32_t kd, kh, kw;  /* filter extent per axis (1, 3 or 7)                 */
+  int32_t sd, sh, sw;  /* stride                                             */
+  int32_t dd, dh, dw;  /* dilation                                           */
+  int32_t pd, ph, pw;  /* zero padding                                       */
+  /* epilogue */
+  int32_t relu;        /* 1: clamp at zero after bias (+ residual)           */
+  int32_t res_c;       /* residual channels (<= cout), 0 = none.  Channels   */
+                       /* >= res_c get no residual: shortcut type A          */
+  int32_t res_stride;  /* residual is read at (d,h,w)*res_stride             */
+  int32_t res_d, res_h, res_w; /* residual tensor spatial dims               */
+  /* fused 1x1x1 heads (only with cout == 32): out_k = act(W_k . y + b_k)    */
+  int32_t n_heads;     /* 0 = none; else 1..2 head groups                    */
+  int32_t head_ch[2];  /* channels per head group (1 for reg; 6,3 for cls)   */
+  int32_t head_sigmoid;/* 1: sigmoid (med3d.py:382); 0: raw logits (:283)    */
+  int32_t store_out;   /* 0: do not write the bf16 activation (heads only)   */
+  /* tile shape chosen by the caller (tw*th*td must be 128); 0 = library     */
+  /* picks the shape with the fewest tiles                                   */
+  int32_t tw, th, td;
+} dram_conv_desc;
+
+typedef struct dram_conv_plan dram_conv_plan; /* opaque: tensor maps + launch geometry */
+
+/* Output spatial size of the convolution described by d. */
+int dram_conv3d_out_dims(const dram_conv_desc *d, int32_t *dout, int32_t *hout, int32_t *wout);
+
+/*
+ * Builds the TMA tensor maps for the given device buffers and freezes the
+ * launch geometry.  Buffers must stay valid and fixed until plan_destroy.
+ *   src1, src2 : bf16 NDHWC inputs (src2 may be NULL when c2 == 0)
+ *   weight     : bf16 [cout][taps*(c1+c2)]
+ *   bias       : fp32 [cout]
+ *   residual   : bf16 NDHWC [n][res_d][res_h][res_w][res_c] or NULL
+ *   out        : bf16 NDHWC [n][do][ho][wo][cout] (may be NULL if !store_out)
+ *   head_w     : fp32 [sum(head_ch)][32], head_b fp32 [sum(head_ch)]
+ *   head_out   : fp32 NCDHW [n][head_ch[k]][do][ho][wo] per head group
+ */
+int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,
+                            const void *weight, const float *bias, const void *residual,
+                            void *out, const float *head_w, const float *head_b,
+                            float *head_out0, float *head_out1, dram_conv_plan **plan);
+int dram_conv3d_plan_destroy(dram_conv_plan *plan);
+/* Launches the persistent kernel (grid = min(tiles, max_ctas or #SMs)). */
+int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, void *stream);
+/* Introspection for tests / roofline accounting. */
+int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops, int32_t *m_tiles,
+                          int32_t *n_tiles, int32_t *block_n, int32_t *stages);
+
+/* ---- K2a: stem unfold (feeds K1 with taps 7x1x1, stride 2x1x1) --------- */
+/*
+ * med3d.py:296-304,371 conv1 = Conv3d(1,64,k7,s2,p3).  Writes
+ *   out[n][d][h'][w'][kh*8+j] = x[n][d][2h'-3+kh][2w'-3+j]   (0 outside, 0 for kh==7 or j==7)
+ * as bf16, so that the 7^3 stride-2 convolution becomes a 7x1x1 convolution
+ * over 64 pseudo-channels.  x is fp32 [n][d][h][w] (the predict_step
+ * `image`, models.py:432), h' = (h-1)/2+1, w' = (w-1)/2+1.
+ */
+int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                     void *stream);
+
+/* ---- K3: max-pool 3x3x3 stride 2 pad 1 (med3d.py:305, 374) ------------- */
+int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                   int32_t c, void *stream);
+
+/* ---- K4: trilinear x2 up-sampling, align_corners=True (med3d.py:83,86) - */
+int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                    int32_t c, void *stream);
+
+/* ---- K6: lobe-masked / global pooling (med3d.py:383-387, 284) ---------- */
+/*
+ * dense: fp32 [n][ch][d][h][w].  mask: uint8 [n][md][mh][mw] (non-zero = lung)
+ * resampled on the fly with ATen's legacy `nearest` rule (med3d.py:386), or
+ * NULL for the unmasked mean (lungs=None, med3d.py:383-384 and the cls path).
+ * out: fp32 [n][ch]  = sum(dense*mask)/sum(mask)  (or the plain mean).
+ * workspace: at least dram_pool_workspace_bytes(n, ch) bytes.
+ */
+size_t dram_pool_workspace_bytes(int32_t n, int32_t ch);
+int dram_masked_pool(const float *dense, const uint8_t *mask, float *out, void *workspace,
+                     int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w, int32_t md,
+                     int32_t mh, int32_t mw, void *stream);
+
+/* ---- K7: dRAM = trilinear(dense -> scan size, align_corners) * ess ----- */
+/*
+ * models.py:438-441 (predict_step).  dense0/dense1: fp32 [n][1][d][h][w];
+ * ess, lungs: uint8 [n][D][H][W]; out0/out1: fp32 [n][1][D][H][W];
+ * pct: fp32 [2][n] = sum_b(out_k[b]) / sum over the WHOLE batch of lungs
+ * (reference quirk Q1) or per sample when per_sample_denominator != 0.
+ */
+size_t dram_dram_workspace_bytes(int32_t n);
+int dram_dram_upsample_mask(const float *dense0, const float *dense1, const uint8_t *ess,
+                            const uint8_t *lungs, float *out0, float *out1, float *pct,
+                            void *workspace, int32_t n, int32_t d, int32_t h, int32_t w,
+                            int32_t D, int32_t H, int32_t W, int32_t per_sample_denominator,
+                            void *stream);
+
+/* ---- K8: HU window + standardise (functional.py:13-26,                   */
+/*          intensity_transforms.py:104-114; wired at models.py:60-61) ---- */
+/*
+ * hu: int16 [count]; out: fp32 [count] = (v - mean(v)) / std_unbiased(v) with
+ * v = (clamp(hu, lo, hi) - lo) / (hi - lo) in fp32.  One volume per call
+ * (statistics are per volume).  stats_out (optional, fp32[2]) = mean, std.
+ */
+size_t dram_preprocess_workspace_bytes(void);
+int dram_window_standardize(const int16_t *hu, float *out, float *stats_out, void *workspace,
+                            int64_t count, float lo, float hi, void *stream);
+
+/* ---- K8b: Interpolate transform (spatial_transforms.py:55-97) ---------- */
+/*
+ * Image: in-plane bilinear (align_corners=True) to (H2,W2) then slice pick
+ * d_idx[k] (the caller builds d_idx with torch.linspace(0,D-1,D2).long(),
+ * spatial_transforms.py:66).  Mask: in-plane legacy nearest + same slice pick.
+ */
+int dram_resize_image(const float *x, float *out, const int32_t *d_idx, int32_t D, int32_t H,
+                      int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream);
+int dram_resize_mask(const uint8_t *x, uint8_t *out, const int32_t *d_idx, int32_t D, int32_t H,
+                     int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream);
+
+/* ---- layout helpers ---------------------------------------------------- */
+/* fp32 NCDHW -> bf16 NDHWC and back (test / debugging / hook support). */
+int dram_ncdhw_f32_to_ndhwc_bf16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
+                                 int32_t h, int32_t w, void *stream);
+int dram_ndhwc_bf16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
+                                 int32_t h, int32_t w, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRAM_B200_H_ */

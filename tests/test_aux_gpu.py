@@ -1,0 +1,139 @@
+"""Parity of the memory-bound kernels (K2a, K3, K4, K6, K7, K8, K8b) against the torch CPU ops the
+reference calls.  Index/mask work is bit-exact; floating point within the stated tolerance."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def test_layout_roundtrip(cuda, lib):
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    x = _bf(torch.randn(2, 24, 3, 5, 7, generator=g))
+    y = ops.to_ncdhw_f32(ops.to_ndhwc_bf16(x.to(cuda))).cpu()
+    assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 12), (16, 6, 10)])
+def test_maxpool(cuda, lib, dims):
+    """med3d.py:305 MaxPool3d(3, stride 2, pad 1): exact (max of bf16 values)."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    x = _bf(torch.randn((2, 64) + dims, generator=g))
+    ref = F.max_pool3d(x, 3, 2, 1)
+    got = ops.to_ncdhw_f32(ops.maxpool3d(ops.to_ndhwc_bf16(x.to(cuda)))).cpu()
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("dims", [(4, 4, 4), (3, 5, 6), (8, 7, 9)])
+def test_upsample2x(cuda, lib, dims):
+    """med3d.py:83 nn.Upsample(scale 2, trilinear, align_corners=True); fp32 math, one bf16 rounding."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(2)
+    x = _bf(torch.randn((2, 64) + dims, generator=g))
+    ref = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    got = ops.to_ncdhw_f32(ops.upsample2x(ops.to_ndhwc_bf16(x.to(cuda)))).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-6
+
+
+def test_stem_expand_layout(cuda, lib):
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.randn(2, 5, 9, 12, generator=g))
+    got = ops.stem_expand(x.to(cuda)).float().cpu()
+    n, d, h, w = x.shape
+    h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    xp = F.pad(x, (3, 5, 3, 5))
+    ref = torch.zeros(n, d, h2, w2, 8, 8)
+    for kh in range(7):
+        for j in range(7):
+            ref[..., kh, j] = xp[:, :, kh:kh + 2 * h2:2, j:j + 2 * w2:2][:, :, :h2, :w2]
+    assert torch.equal(got, ref.reshape(n, d, h2, w2, 64))
+
+
+@pytest.mark.parametrize("mask_dims,dims", [((16, 16, 16), (8, 8, 8)), ((10, 14, 18), (5, 7, 9)),
+                                            ((9, 11, 13), (4, 6, 5))])
+def test_masked_pool(cuda, lib, mask_dims, dims):
+    """med3d.py:383-387: nearest-resampled lung mask (bit-exact indexing), masked mean in fp32."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    dense = torch.rand((2, 3) + dims, generator=g)
+    lungs = (torch.rand((2, 1) + mask_dims, generator=g) > 0.6).float()
+    m = F.interpolate(lungs, dims, mode="nearest")
+    ref = (dense * m).view(2, 3, -1).sum(-1) / m.view(2, 1, -1).sum(-1)
+    got = ops.masked_pool(dense.to(cuda), lungs[:, 0].to(torch.uint8).to(cuda)).cpu()
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7), (got, ref)
+    ref_plain = dense.view(2, 3, -1).mean(-1)
+    got_plain = ops.masked_pool(dense.to(cuda), None).cpu()
+    assert torch.allclose(got_plain, ref_plain, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("dims,size", [((4, 6, 8), (8, 12, 16)), ((5, 7, 9), (10, 14, 18)),
+                                       ((4, 4, 6), (9, 11, 13))])
+def test_dram_upsample_mask(cuda, lib, dims, size):
+    """models.py:438-441: dRAM = trilinear(dense -> scan size, align_corners) * ess; pct over batch lungs."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    d0 = torch.rand((2, 1) + dims, generator=g)
+    d1 = torch.rand((2, 1) + dims, generator=g)
+    lungs = (torch.rand((2, 1) + size, generator=g) > 0.4).float()
+    ess = lungs * (torch.rand((2, 1) + size, generator=g) > 0.5).float()
+    r0 = F.interpolate(d0, size=size, mode="trilinear", align_corners=True) * ess
+    r1 = F.interpolate(d1, size=size, mode="trilinear", align_corners=True) * ess
+    p0 = r0.view(2, -1).sum(-1) / lungs.sum()
+    p1 = r1.view(2, -1).sum(-1) / lungs.sum()
+    o0, o1, pct = ops.dram_upsample_mask(d0.to(cuda), d1.to(cuda), ess[:, 0].to(torch.uint8).to(cuda),
+                                         lungs[:, 0].to(torch.uint8).to(cuda), size)
+    assert (o0.cpu() - r0).abs().max().item() < 1e-5
+    assert (o1.cpu() - r1).abs().max().item() < 1e-5
+    assert torch.equal(o0.cpu() == 0, r0 == 0)
+    assert torch.allclose(pct.cpu(), torch.stack([p0, p1]), rtol=1e-5)
+    _, _, pct_s = ops.dram_upsample_mask(d0.to(cuda), d1.to(cuda), ess[:, 0].to(torch.uint8).to(cuda),
+                                         lungs[:, 0].to(torch.uint8).to(cuda), size, per_sample_denominator=True)
+    ps = r0.view(2, -1).sum(-1) / lungs.view(2, -1).sum(-1)
+    assert torch.allclose(pct_s.cpu()[0], ps, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (7, 9, 11)])
+def test_window_standardize(cuda, lib, shape):
+    """functional.py:13-26 + intensity_transforms.py:104-114 (unbiased std)."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(6)
+    hu = (torch.randn(shape, generator=g) * 400 - 700).round().clamp(-2048, 1500).to(torch.int16)
+    v = torch.clamp(hu.float(), min=-1150, max=-300)
+    v = ((v - (-1150)) / (-300 - (-1150))) * (1 - 0) + 0
+    ref = (v - v.mean()) / (v - v.mean()).std()
+    got, stats = ops.window_standardize(hu.to(cuda))
+    assert (got.cpu() - ref).abs().max().item() < 2e-5
+    assert abs(stats[0].item() - v.mean().item()) < 1e-6
+
+
+@pytest.mark.parametrize("shape,size", [((10, 12, 14), (8, 16, 24)), ((40, 30, 50), (32, 24, 40)),
+                                        ((9, 17, 13), (16, 8, 8))])
+def test_resize(cuda, lib, shape, size):
+    """spatial_transforms.py:55-97 Interpolate(only_in_plane=True): mask path bit-exact."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(shape, generator=g)
+    m = torch.rand(shape, generator=g) > 0.5
+    idx = torch.linspace(0, shape[0] - 1, size[0]).long()
+    ref = F.interpolate(x[None], size=size[1:], mode="bilinear", align_corners=True)[:, idx][0]
+    refm = F.interpolate(m[None].float(), size=size[1:], mode="nearest")[:, idx][0].bool()
+    got = ops.resize_image(x.to(cuda), size).cpu()
+    gotm = ops.resize_mask(m.to(torch.uint8).to(cuda), size).cpu().bool()
+    assert (got - ref).abs().max().item() < 1e-5
+    assert torch.equal(gotm, refm)

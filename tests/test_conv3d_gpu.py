@@ -1,0 +1,159 @@
+"""K1 parity: the tcgen05 implicit-GEMM conv3d against torch's CPU fp32 conv3d on the same
+bf16-rounded operands (so the only differences are fp32 accumulation order and the single
+bf16 rounding of the output).  Tolerance: |err| <= 2^-7 * |ref| + 2^-8 * max|ref|.
+Covers every conv shape family of the network: 3^3 with dilation 1/2/4,
+stride 2 with shortcut A, 1x1x1, two K-sources (skip concat), 32-channel conv with fused heads,
+the unfolded 7^3 stem, ragged volumes (partial tiles) and batch > 1.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale).to(torch.bfloat16).float()
+
+
+def _close(got, ref, what):
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + ref.abs().max() * 2.0 ** -8
+    bad = err > tol
+    if bad.any():
+        idx = torch.nonzero(bad)[0].tolist()
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance; max err {err.max().item():.4g} "
+            f"(ref max {ref.abs().max().item():.4g}); first bad index {idx}: got {got[tuple(idx)].item():.5g} "
+            f"ref {ref[tuple(idx)].item():.5g}")
+
+
+def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=None, res_stride=1,
+              heads=None, seed=0, tile=None):
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(seed)
+    d, h, w = dims
+    k3 = (k, k, k) if isinstance(k, int) else k
+    x1 = _rand((n, c1, d, h, w), g)
+    x2 = _rand((n, c2, d, h, w), g) if c2 else None
+    cin = c1 + c2
+    fan = cin * k3[0] * k3[1] * k3[2]
+    wgt = _rand((cout, cin) + k3, g, scale=fan ** -0.5)
+    bias = torch.randn(cout, generator=g) * 0.1
+    pad = tuple(dil * (kk - 1) // 2 for kk in k3)
+    xin = x1 if x2 is None else torch.cat([x1, x2], 1)
+    ref = F.conv3d(xin, wgt, None, stride=stride, padding=pad, dilation=dil) + bias.view(1, -1, 1, 1, 1)
+    res_t = None
+    if residual is not None:
+        rc = residual
+        res = _rand((n, rc, d, h, w), g)
+        sub = res[:, :, ::res_stride, ::res_stride, ::res_stride]
+        ref[:, :rc] += sub[:, :, :ref.shape[2], :ref.shape[3], :ref.shape[4]]
+        res_t = ops.to_ndhwc_bf16(res.to(cuda))
+    if relu:
+        ref = ref.relu()
+    head_ref = None
+    hk = None
+    if heads is not None:
+        chs, sig = heads
+        hw = torch.randn(sum(chs), 32, generator=g) * 0.3
+        hb = torch.randn(sum(chs), generator=g) * 0.1
+        dense = torch.einsum("oc,ncdhw->nodhw", hw, ref) + hb.view(1, -1, 1, 1, 1)
+        if sig:
+            dense = torch.sigmoid(dense)
+        head_ref = torch.split(dense, list(chs), dim=1)
+        hk = (hw.to(cuda), hb.to(cuda), tuple(chs), sig)
+    plan = ops.Conv3dPlan(
+        ops.to_ndhwc_bf16(x1.to(cuda)), ops.pack_conv_weight(wgt).to(cuda), bias.to(cuda),
+        x2=None if x2 is None else ops.to_ndhwc_bf16(x2.to(cuda)), kernel=k3, stride=stride, dilation=dil,
+        relu=relu, residual=res_t, res_stride=res_stride, heads=hk, tile=tile)
+    out = plan.run()
+    torch.cuda.synchronize()
+    got = ops.to_ncdhw_f32(out).cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    _close(got, ref, f"conv {c1}+{c2}->{cout} k{k} s{stride} d{dil} {dims}")
+    if head_ref is not None:
+        for i, hr in enumerate(head_ref):
+            hg = plan.head_outs[i].cpu()
+            assert hg.shape == hr.shape
+            err = (hg - hr).abs().max().item()
+            assert err < 2e-2 * max(1.0, hr.abs().max().item()), f"head {i}: max err {err}"
+    return plan
+
+
+def test_conv_64_64_plain(cuda, lib):
+    _run_conv(cuda, 1, (16, 16, 16), 64, 0, 64, 3, 1, 1)
+
+
+def test_conv_64_64_residual_ragged(cuda, lib):
+    _run_conv(cuda, 1, (10, 12, 20), 64, 0, 64, 3, 1, 1, residual=64)
+
+
+def test_conv_128_256_dil2(cuda, lib):
+    _run_conv(cuda, 1, (12, 16, 20), 128, 0, 256, 3, 1, 2, residual=128)  # layer3.0: shortcut A, stride 1
+
+
+def test_conv_256_512_dil4_batch2(cuda, lib):
+    _run_conv(cuda, 2, (8, 12, 16), 256, 0, 512, 3, 1, 4, residual=512)
+
+
+def test_conv_stride2_shortcut_a(cuda, lib):
+    _run_conv(cuda, 1, (16, 16, 16), 64, 0, 128, 3, 2, 1, relu=True)
+    p = _run_conv(cuda, 1, (16, 24, 32), 64, 0, 128, 3, 2, 1, relu=False)
+    assert p.out_shape == (1, 8, 12, 16, 128)
+
+
+def test_conv_stride2_with_residual(cuda, lib):
+    # conv2 of layer2.0: stride-1 conv whose residual is the stride-2 subsample of the block input
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    x = _rand((1, 128, 8, 8, 8), g)
+    res = _rand((1, 64, 16, 16, 16), g)
+    wgt = _rand((128, 128, 3, 3, 3), g, scale=(128 * 27) ** -0.5)
+    bias = torch.randn(128, generator=g) * 0.1
+    ref = F.conv3d(x, wgt, None, padding=1) + bias.view(1, -1, 1, 1, 1)
+    ref[:, :64] += res[:, :, ::2, ::2, ::2]
+    ref = ref.relu()
+    plan = ops.Conv3dPlan(ops.to_ndhwc_bf16(x.to(cuda)), ops.pack_conv_weight(wgt).to(cuda), bias.to(cuda),
+                          residual=ops.to_ndhwc_bf16(res.to(cuda)), res_stride=2)
+    got = ops.to_ncdhw_f32(plan.run()).cpu()
+    _close(got, ref, "layer2.0.conv2 + shortcut A")
+
+
+def test_conv_two_sources(cuda, lib):
+    _run_conv(cuda, 1, (8, 16, 16), 128, 64, 64, 3, 1, 1)
+
+
+def test_conv_1x1(cuda, lib):
+    _run_conv(cuda, 1, (8, 12, 16), 256, 0, 128, 1, 1, 1)
+    _run_conv(cuda, 1, (8, 8, 16), 64, 0, 256, 1, 1, 1, residual=64)  # R50 layer1.0 conv3 + shortcut A
+
+
+def test_conv_heads_reg_and_cls(cuda, lib):
+    _run_conv(cuda, 1, (8, 16, 16), 64, 0, 32, 3, 1, 1, heads=((1, 1), True))
+    _run_conv(cuda, 2, (8, 8, 12), 64, 0, 32, 3, 1, 1, heads=((6, 3), False))
+
+
+def test_conv_tile_shapes(cuda, lib):
+    for tile in [(8, 4, 4), (4, 4, 8), (16, 8, 1), (32, 2, 2), (128, 1, 1)]:
+        _run_conv(cuda, 1, (8, 16, 36), 64, 0, 64, 3, 1, 1, tile=tile, seed=7)
+
+
+def test_stem_unfold(cuda, lib):
+    """7^3 stride-2 conv (med3d.py:296-304) = stem_expand + 7x1x1 conv over 64 pseudo-channels."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for dims in [(16, 16, 32), (12, 20, 24)]:
+        x = _rand((2, 1) + dims, g)
+        wgt = _rand((64, 1, 7, 7, 7), g, scale=343 ** -0.5)
+        bias = torch.randn(64, generator=g) * 0.1
+        ref = (F.conv3d(x, wgt, None, stride=2, padding=3) + bias.view(1, -1, 1, 1, 1)).relu()
+        xe = ops.stem_expand(x[:, 0].contiguous().to(cuda))
+        plan = ops.Conv3dPlan(xe, ops.pack_stem_weight(wgt).to(cuda), bias.to(cuda), kernel=(7, 1, 1),
+                              stride=(2, 1, 1), padding=(3, 0, 0), tile=(16, 8, 1))
+        got = ops.to_ncdhw_f32(plan.run()).cpu()
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        _close(got, ref, f"stem {dims}")
