@@ -1,0 +1,140 @@
+"""Pins the CPU oracle (oracle/*.py) against golden vectors produced by the unmodified reference
+(oracle/make_golden.py) and — where /root/reference is mounted — against the live reference.
+No GPU needed."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import med3d_oracle as M
+from oracle import pipeline_oracle as P
+from oracle import ref_shim, synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FORWARD_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "forward_*.pt")))
+
+
+def test_state_layout_matches_reference_modules():
+    with open(os.path.join(GOLDEN, "state_layouts.json")) as f:
+        layouts = json.load(f)
+    assert set(layouts) == set(M.ARCHS)
+    for arch, info in layouts.items():
+        mine = M.state_layout(arch)
+        assert [k for k, _, _ in mine] == [k for k, _, _ in info["keys"]], arch
+        assert [list(s) for _, s, _ in mine] == [s for _, s, _ in info["keys"]], arch
+        n_params = sum(int(np.prod(s)) for k, s, kind in mine if kind in ("conv_w", "conv_b", "bn_w", "bn_b"))
+        assert n_params == info["params"], arch
+    assert len(layouts["med3ddram18"]["keys"]) == 141 and len(layouts["med3ddram"]["keys"]) == 237
+    assert len(layouts["med3ddram50"]["keys"]) == 333
+
+
+@pytest.mark.parametrize("path", FORWARD_FIXTURES, ids=[os.path.basename(p)[:-3] for p in FORWARD_FIXTURES])
+def test_forward_oracle_matches_reference_golden(path):
+    fix = torch.load(path)
+    arch, dims, batch = fix["arch"], tuple(fix["dims"]), fix["batch"]
+    sd = synthetic.make_state_dict(arch, seed=fix["weight_seed"], calib_dims=dims)
+    assert abs(synthetic.state_dict_checksum(sd) - fix["weight_checksum"]) <= 1e-6 * abs(fix["weight_checksum"]), \
+        "synthetic weights drifted from the ones the golden vectors were made with"
+    xs, ls, _ = zip(*[synthetic.make_network_input(i, dims) for i in range(batch)])
+    x = torch.stack(xs).unsqueeze(1)
+    lungs = torch.stack(ls).unsqueeze(1).float() if fix["with_lungs"] else None
+    dense, scores = M.forward(sd, arch, x, lungs)
+    for got, ref in zip(dense, fix["dense_outs"]):
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    for got, ref in zip(scores, fix["scores"]):
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+    if M.ARCHS[arch][2] == "cls":
+        for got, ref in zip(scores, fix["scores"]):
+            assert torch.equal(got.argmax(-1), ref.argmax(-1))
+
+
+def test_predict_step_oracle_matches_reference_golden():
+    fix = torch.load(os.path.join(GOLDEN, "predict_step_med3ddram18.pt"))
+    dims, batch = tuple(fix["dims"]), fix["batch"]
+    sd = synthetic.make_state_dict(fix["arch"], seed=fix["weight_seed"], calib_dims=dims)
+    xs, ls, es = zip(*[synthetic.make_network_input(i, dims) for i in range(batch)])
+    out = P.predict_step(sd, fix["arch"], {"image": torch.stack(xs), "lung_mask": torch.stack(ls).bool(),
+                                           "ess_mask": torch.stack(es).bool()})
+    assert list(out.keys()) == fix["keys"]  # 7 keys, reference spelling (`precentages`)
+    for k in ("cle_dense_outs", "pse_dense_outs"):
+        assert (out[k] - fix[k]).abs().max().item() < 2e-5
+        assert torch.equal(out[k] == 0, fix[k] == 0)
+    for k in ("cle_precentages", "pse_precentages"):
+        assert torch.allclose(out[k], fix[k], rtol=1e-4)
+    cle = [P.ratio_to_label(r.item(), P.CLE_RATIO_MAP) for r in out["cle_precentages"]]
+    pse = [P.ratio_to_label(r.item(), P.PSE_RATIO_MAP) for r in out["pse_precentages"]]
+    assert cle == fix["cle_labels"].tolist() and pse == fix["pse_labels"].tolist()
+
+
+def test_transforms_oracle_matches_reference_golden():
+    fix = torch.load(os.path.join(GOLDEN, "transforms.pt"))
+    ct, lobes = synthetic.make_volume(fix["scan_index"], tuple(fix["scan_dims"]))
+    sample = P.lung_crop_sample(ct.numpy(), lobes.numpy(), crop_border=5, uid="s3")
+    assert sample["crop_slice"].tolist() == fix["ref_crop"]
+    out = P.inference_transform(sample, tuple(fix["target_size"]))
+    assert torch.equal(out["lung_mask"], fix["lung_mask"]) and out["lung_mask"].dtype == torch.bool
+    assert torch.equal(out["ess_mask"], fix["ess_mask"])
+    assert (out["image"] - fix["image"]).abs().max().item() < 1e-6
+    assert (out["original_image"] - fix["original_image"]).abs().max().item() < 1e-6
+    assert out["image"].dtype == torch.float32
+    assert torch.equal(torch.as_tensor(out["crop_slice"]), torch.as_tensor(fix["crop_slice"]))
+
+
+def test_labels_match_reference_golden():
+    with open(os.path.join(GOLDEN, "labels.json")) as f:
+        fix = json.load(f)
+    ratios = torch.tensor(fix["ratios"], dtype=torch.float32)
+    assert [P.ratio_to_label(r.item(), P.CLE_RATIO_MAP) for r in ratios] == fix["cle"]
+    assert [P.ratio_to_label(r.item(), P.PSE_RATIO_MAP) for r in ratios] == fix["pse"]
+    assert {str(k): list(v) for k, v in P.CLE_RATIO_MAP.items()} == fix["cle_map"]
+    assert {str(k): list(v) for k, v in P.PSE_RATIO_MAP.items()} == fix["pse_map"]
+    with pytest.raises(IndexError):
+        P.ratio_to_label(1.5, P.CLE_RATIO_MAP)
+
+
+def test_slice_pick_matches_golden():
+    with open(os.path.join(GOLDEN, "index_luts.json")) as f:
+        fix = json.load(f)
+    for key, ref in fix["slice"].items():
+        a, b = (int(v) for v in key.split("->"))
+        assert P.slice_indices(a, b).tolist() == ref
+
+
+def test_conv_flops_match_survey():
+    # algorithmic conv FLOPs per volume
+    assert abs(M.conv_flops("med3ddram", (256, 256, 256)) / 1e12 - 6.746) < 2e-3
+    assert abs(M.conv_flops("med3ddram18", (256, 256, 256)) / 1e12 - 4.658) < 2e-3
+    assert abs(M.conv_flops("med3d18", (128, 128, 128)) / 1e12 - 0.582) < 1e-3
+    assert abs(M.conv_flops("med3ddram50", (400, 512, 512)) / 1e12 - 43.164) < 2e-2
+
+
+def test_synthetic_volume_statistics():
+    ct, lobes = synthetic.make_volume(0, (48, 48, 48))
+    assert ct.dtype == torch.int16 and lobes.dtype == torch.uint8
+    assert set(lobes.unique().tolist()) == {0, 1, 2, 3, 4, 5}
+    lung = lobes > 0
+    assert 0.18 < lung.float().mean().item() < 0.30
+    ess = (ct < -910) & lung
+    assert 0.15 < ess.sum().item() / lung.sum().item() < 0.6
+    ct2, _ = synthetic.make_volume(0, (48, 48, 48))
+    assert torch.equal(ct, ct2)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+def test_oracle_against_live_reference():
+    arch, dims = "med3ddram18", (16, 24, 32)
+    sd = synthetic.make_state_dict(arch, seed=3, calib_dims=dims)
+    ref = ref_shim.model(arch)
+    ref.load_state_dict(sd)
+    x, lung, _ = synthetic.make_network_input(5, dims)
+    with torch.no_grad():
+        d_ref, r_ref = ref(x[None, None].clone(), lung[None, None].float())
+    d_or, r_or = M.forward(sd, arch, x[None, None], lung[None, None].float())
+    for a, b in zip(d_ref, d_or):
+        assert torch.equal(a, b)
+    for a, b in zip(r_ref, r_or):
+        assert torch.equal(a, b)
