@@ -52,7 +52,7 @@ SIGNATURES = {
     "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_pool_workspace_bytes": (_sz, [_i32, _i32]),
-    "dram_masked_pool": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_masked_pool": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_dram_workspace_bytes": (_sz, [_i32]),
     "dram_dram_upsample_mask": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32,
                                           _i32, _i32, _i32, _i32, _vp]),

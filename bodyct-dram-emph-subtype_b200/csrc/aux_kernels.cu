@@ -207,14 +207,15 @@ __global__ void upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict
 // K6 lobe-masked (or plain) mean of each dense channel.
 // grid = (blocks, ch, n).  sums: double [n][ch+1] (last slot = sum of mask / voxel count).
 // ---------------------------------------------------------------------------------------
+template <typename MaskT>
 __global__ void masked_pool_partial_kernel(const float *__restrict__ dense,
-                                           const uint8_t *__restrict__ mask, double *__restrict__ sums,
+                                           const MaskT *__restrict__ mask, double *__restrict__ sums,
                                            int ch, int d, int h, int w, int md, int mh, int mw) {
   __shared__ double scratch[32];
   const int c = blockIdx.y, b = blockIdx.z;
   const int64_t plane = (int64_t)d * h * w;
   const float *src = dense + ((int64_t)b * ch + c) * plane;
-  const uint8_t *mk = mask ? mask + (int64_t)b * md * mh * mw : nullptr;
+  const MaskT *mk = mask ? mask + (int64_t)b * md * mh * mw : nullptr;
   double s = 0.0, ms = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -225,7 +226,9 @@ __global__ void masked_pool_partial_kernel(const float *__restrict__ dense,
       const int xh = (int)(r % h);
       const int xd = (int)(r / h);
       const int zd = nearest_index(xd, md, d), zh = nearest_index(xh, mh, h), zw = nearest_index(xw, mw, w);
-      m = mk[((int64_t)zd * mh + zh) * mw + zw] ? 1.0f : 0.0f;
+      const MaskT mv = mk[((int64_t)zd * mh + zh) * mw + zw];
+      if constexpr (sizeof(MaskT) == 1) m = mv ? 1.0f : 0.0f;
+      else m = (float)mv;  // float lungs are used as weights, exactly like `dout * lungs` (med3d.py:387)
     }
     s += (double)(__ldg(src + i) * m);
     ms += (double)m;
@@ -520,9 +523,9 @@ extern "C" size_t dram_pool_workspace_bytes(int32_t n, int32_t ch) {
   return sizeof(double) * (size_t)n * (size_t)(ch + 1);
 }
 
-extern "C" int dram_masked_pool(const float *dense, const uint8_t *mask, float *out, void *workspace,
-                                int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w, int32_t md,
-                                int32_t mh, int32_t mw, void *stream) {
+extern "C" int dram_masked_pool(const float *dense, const void *mask, int32_t mask_is_f32, float *out,
+                                void *workspace, int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w,
+                                int32_t md, int32_t mh, int32_t mw, void *stream) {
   DRAM_REQUIRE(dense && out && workspace, "dram_masked_pool: null pointer");
   DRAM_REQUIRE(n > 0 && ch > 0 && ch <= 65535 && d > 0 && h > 0 && w > 0, "dram_masked_pool: bad shape");
   DRAM_REQUIRE(mask == nullptr || (md > 0 && mh > 0 && mw > 0), "dram_masked_pool: bad mask shape");
@@ -535,8 +538,12 @@ extern "C" int dram_masked_pool(const float *dense, const uint8_t *mask, float *
   int per = blocks / (n * ch);
   if (per < 1) per = 1;
   dim3 grid(per, ch, n);
-  masked_pool_partial_kernel<<<grid, kThreads, 0, st>>>(dense, mask, reinterpret_cast<double *>(workspace),
-                                                        ch, d, h, w, md, mh, mw);
+  if (mask_is_f32)
+    masked_pool_partial_kernel<float><<<grid, kThreads, 0, st>>>(
+        dense, reinterpret_cast<const float *>(mask), reinterpret_cast<double *>(workspace), ch, d, h, w, md, mh, mw);
+  else
+    masked_pool_partial_kernel<uint8_t><<<grid, kThreads, 0, st>>>(
+        dense, reinterpret_cast<const uint8_t *>(mask), reinterpret_cast<double *>(workspace), ch, d, h, w, md, mh, mw);
   DRAM_CHECK_LAUNCH("masked_pool_partial_kernel");
   masked_pool_finalize_kernel<<<ceil_div(n * ch, 128), 128, 0, st>>>(
       reinterpret_cast<const double *>(workspace), out, n, ch);

@@ -1,0 +1,218 @@
+"""Static execution plan of one Med3D seg-reg / seg-cls forward on one B200.
+
+For a fixed (batch, D, H, W) the planner folds eval-mode BatchNorm into bf16 weights, lays out every
+activation as NDHWC bf16 in HBM, builds one `Conv3dPlan` (TMA tensor maps + tile geometry) per
+convolution and records the launch sequence.  `run()` replays it on the current CUDA stream; nothing
+is allocated and no host<->device synchronisation happens after the plan exists.
+
+Data flow (reference: med3d.py:369-388 / 270-285), all kernels from libdram_b200.so:
+    image fp32 --K2a stem_expand--> 64 pseudo-channels --K1(7x1x1,s2)--> x (64ch, /2)
+    x --K3 maxpool--> xp (/4) --K1 blocks layer1..4--> x1 (/4), x4 (/8, dilated)
+    x4 --K4 up2x--> up1;  K1([up1 | x1]) -> K1 -> xup1 (/4)
+    xup1 --K4 up2x--> up2; K1([up2 | x]) -> K1 -> xup2 (/2)
+    xup2 --K1(64->32)+heads(+sigmoid) in the epilogue--> dense maps fp32 NCDHW (xup3 never stored)
+    dense (+ lungs) --K6 masked/global pooling--> scores
+"""
+import torch
+
+from . import ops
+
+LAYER_CFG = ((64, 1, 1), (128, 2, 1), (256, 1, 2), (512, 1, 4))  # planes, stride, dilation
+
+
+def _conv_out(n, k, s, d, p):
+    return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class _Step:
+    """One launch of the recorded sequence."""
+
+    __slots__ = ("name", "fn", "flops")
+
+    def __init__(self, name, fn, flops=0):
+        self.name, self.fn, self.flops = name, fn, flops
+
+
+class Med3DEngine:
+    def __init__(self, model, batch, dims, device):
+        if device.type != "cuda":
+            raise RuntimeError("Med3DEngine needs a CUDA device: this path has no CPU implementation")
+        self.model = model
+        self.batch, self.dims, self.device = batch, tuple(dims), device
+        self.head_kind = model.head_kind
+        self._weights = {}    # name -> (packed weight bf16, bias fp32) device buffers (stable addresses)
+        self._packers = []    # closures that (re)fill the buffers from the module's parameters
+        self.steps = []
+        self.conv_flops = 0
+        self._build()
+        self._weight_version = self._current_weight_version()
+
+    # ---------------------------------------------------------------- weights
+    def _current_weight_version(self):
+        v = 0
+        for t in list(self.model.parameters()) + list(self.model.buffers()):
+            v = (v * 1000003 + t._version + (t.data_ptr() & 0xFFFFFF)) & 0xFFFFFFFFFFFF
+        return v
+
+    def _register_weight(self, name, pack_fn):
+        """pack_fn() -> (bf16 [cout, K], fp32 [cout]) on self.device; buffers are refilled in place."""
+        w, b = pack_fn()
+        w = w.to(self.device).contiguous()
+        b = b.to(self.device).contiguous()
+        self._weights[name] = (w, b)
+
+        def refill(w=w, b=b, pack_fn=pack_fn):
+            nw, nb = pack_fn()
+            w.copy_(nw)
+            b.copy_(nb)
+
+        self._packers.append(refill)
+        return w, b
+
+    def refresh_weights(self):
+        """Re-folds BatchNorm and re-packs every weight in place (after load_state_dict etc.)."""
+        for refill in self._packers:
+            refill()
+        self._weight_version = self._current_weight_version()
+
+    def _conv_bn(self, name, conv, bn, stem=False):
+        def pack():
+            scale, shift = ops.fold_bn(bn, conv.bias)
+            w = conv.weight.detach().to(self.device)
+            packed = ops.pack_stem_weight(w, scale.to(self.device)) if stem else ops.pack_conv_weight(w, scale.to(self.device))
+            return packed, shift.to(self.device).float()
+
+        return self._register_weight(name, pack)
+
+    # ---------------------------------------------------------------- plan
+    def _add_conv(self, name, x1, wb, *, x2=None, kernel=3, stride=1, dilation=1, padding=None, relu=True,
+                  residual=None, res_stride=1, heads=None, store_out=True, tile=None, flops=None):
+        plan = ops.Conv3dPlan(x1, wb[0], wb[1], x2=x2, kernel=kernel, stride=stride, dilation=dilation,
+                              padding=padding, relu=relu, residual=residual, res_stride=res_stride,
+                              heads=heads, store_out=store_out, tile=tile)
+        fl = plan.flops if flops is None else flops
+        self.conv_flops += fl
+        self.steps.append(_Step(name, plan.run, fl))
+        return plan
+
+    def _build(self):
+        m, dev, B = self.model, self.device, self.batch
+        D, H, W = self.dims
+        e = m.expansion
+        bf = torch.bfloat16
+        D1, H1, W1 = (_conv_out(n, 7, 2, 1, 3) for n in (D, H, W))
+        D2, H2, W2 = (_conv_out(n, 3, 2, 1, 1) for n in (D1, H1, W1))
+        D3, H3, W3 = (_conv_out(n, 3, 2, 1, 1) for n in (D2, H2, W2))
+        if (2 * D3, 2 * H3, 2 * W3) != (D2, H2, W2) or (2 * D2, 2 * H2, 2 * W2) != (D1, H1, W1):
+            # the reference centre-crops the skip tensor in this case (med3d.py:39-48)
+            raise NotImplementedError(
+                f"input size {self.dims}: each of D,H,W must be 8k or 8k-1 so that the x2 up-sampled maps match "
+                "their skip tensors; cropping skips is not implemented")
+
+        # ---- stem: image -> unfolded pseudo-channels -> conv(7,1,1) stride (2,1,1) + BN + ReLU
+        self.image = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+        self.xe = torch.empty((B, D, H1, W1, 64), dtype=bf, device=dev)
+        self.steps.append(_Step("stem_expand", lambda: ops.stem_expand(self.image, out=self.xe)))
+        wb = self._conv_bn("conv1", m.conv1, m.bn1, stem=True)
+        stem = self._add_conv("conv1", self.xe, wb, kernel=(7, 1, 1), stride=(2, 1, 1), padding=(3, 0, 0),
+                              tile=(16, 8, 1), flops=2 * B * D1 * H1 * W1 * 64 * 343)
+        x = stem.out
+        # ---- maxpool
+        self.xp = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)
+        self.steps.append(_Step("maxpool", lambda x=x: ops.maxpool3d(x, out=self.xp)))
+        # ---- residual layers
+        cur, inplanes = self.xp, 64
+        feats = []
+        for li, ((planes, stride, dil), layer) in enumerate(zip(LAYER_CFG, (m.layer1, m.layer2, m.layer3, m.layer4)), 1):
+            for bi, blk in enumerate(layer):
+                s = stride if bi == 0 else 1
+                name = f"layer{li}.{bi}"
+                # residual source
+                if blk.downsample is None:
+                    res, res_stride = cur, 1
+                elif blk.shortcut_type == "A":
+                    res, res_stride = cur, s      # strided read, channels < inplanes only (med3d.py:103-112)
+                else:  # type B: 1x1x1 strided conv + BN (med3d.py:251-257)
+                    wbd = self._conv_bn(name + ".downsample", blk.downsample[0], blk.downsample[1])
+                    res = self._add_conv(name + ".downsample", cur, wbd, kernel=1, stride=s, relu=False).out
+                    res_stride = 1
+                if m.block_kind == "basic":
+                    t = self._add_conv(name + ".conv1", cur, self._conv_bn(name + ".conv1", blk.conv1, blk.bn1),
+                                       stride=s, dilation=dil).out
+                    cur = self._add_conv(name + ".conv2", t, self._conv_bn(name + ".conv2", blk.conv2, blk.bn2),
+                                         dilation=dil, residual=res, res_stride=res_stride).out
+                else:
+                    t = self._add_conv(name + ".conv1", cur, self._conv_bn(name + ".conv1", blk.conv1, blk.bn1),
+                                       kernel=1).out
+                    t = self._add_conv(name + ".conv2", t, self._conv_bn(name + ".conv2", blk.conv2, blk.bn2),
+                                       stride=s, dilation=dil).out
+                    cur = self._add_conv(name + ".conv3", t, self._conv_bn(name + ".conv3", blk.conv3, blk.bn3),
+                                         kernel=1, residual=res, res_stride=res_stride).out
+                inplanes = planes * e
+            feats.append(cur)
+        x1, x4 = feats[0], feats[3]
+        # ---- decoder
+        self.up1 = torch.empty((B, D2, H2, W2, x4.shape[4]), dtype=bf, device=dev)
+        self.steps.append(_Step("us1.upsample", lambda: ops.upsample2x(x4, out=self.up1)))
+        cb = m.us1.conv_blocks
+        t = self._add_conv("us1.0", self.up1, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1).out
+        xup1 = self._add_conv("us1.1", t, self._conv_bn("us1.1", cb[1][0], cb[1][1])).out
+        self.up2 = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
+        self.steps.append(_Step("us2.upsample", lambda: ops.upsample2x(xup1, out=self.up2)))
+        cb = m.us2.conv_blocks
+        t = self._add_conv("us2.0", self.up2, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x).out
+        xup2 = self._add_conv("us2.1", t, self._conv_bn("us2.1", cb[1][0], cb[1][1])).out
+        # ---- us3 + heads fused
+        head_ch = tuple(fc.weight.shape[0] for fc in m.fcs)
+
+        def pack_heads():
+            w = torch.cat([fc.weight.detach().reshape(fc.weight.shape[0], 32) for fc in m.fcs]).float()
+            b = torch.cat([fc.bias.detach() for fc in m.fcs]).float()
+            return w.to(dev), b.to(dev)
+
+        hw, hb = pack_heads()
+        self._head_w, self._head_b = hw.contiguous(), hb.contiguous()
+
+        def refill_heads():
+            w, b = pack_heads()
+            self._head_w.copy_(w)
+            self._head_b.copy_(b)
+
+        self._packers.append(refill_heads)
+        us3 = self._add_conv("us3+heads", xup2, self._conv_bn("us3", m.us3[0], m.us3[1]),
+                             heads=(self._head_w, self._head_b, head_ch, self.head_kind == "reg"),
+                             store_out=False)
+        self.conv_flops += 2 * B * D1 * H1 * W1 * 32 * sum(head_ch)
+        self.dense = us3.head_outs
+        self.half_dims = (D1, H1, W1)
+        self._plans_alive = [s.fn for s in self.steps]
+
+    # ---------------------------------------------------------------- run
+    def run(self, image, lungs=None):
+        """image: fp32 [B, D, H, W] (or [B,1,D,H,W]) on the device.  lungs: None, uint8/bool [B,D,H,W]
+        or float [B,(1,)D,H,W].  Returns (dense list fp32 [B,C,d,h,w] — engine-owned buffers that the
+        next run overwrites — and the pooled scores list)."""
+        if self._current_weight_version() != self._weight_version:
+            self.refresh_weights()
+        B = self.batch
+        img = image.reshape(B, *self.dims)
+        if img.data_ptr() != self.image.data_ptr():
+            self.image.copy_(img)
+        for st in self.steps:
+            st.fn()
+        mask = None
+        if lungs is not None:
+            mask = lungs.reshape(B, *lungs.shape[-3:])
+            if mask.dtype == torch.bool:
+                mask = mask.view(torch.uint8)
+            elif mask.dtype != torch.uint8:
+                mask = mask.to(torch.float32)
+            mask = mask.contiguous()
+        pooled = [ops.masked_pool(d, mask if self.head_kind == "reg" else None) for d in self.dense]
+        if self.head_kind == "reg":
+            pooled = [p.reshape(B) for p in pooled]
+        return self.dense, pooled
+
+    def launches_per_run(self):
+        """Kernel launches of one run(): recorded steps + 2 pooling calls x (partial + finalize)."""
+        return len(self.steps) + 4

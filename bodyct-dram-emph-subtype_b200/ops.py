@@ -229,19 +229,21 @@ def upsample2x(x, out=None):
 
 
 def masked_pool(dense, mask=None):
-    """dense fp32 [N, C, d, h, w]; mask uint8 [N, D, H, W] or None -> fp32 [N, C]."""
+    """dense fp32 [N, C, d, h, w]; mask uint8 (binary) or fp32 (weights) [N, D, H, W] or None -> fp32 [N, C]."""
     lib = _capi.load()
     _need(dense, torch.float32, "masked_pool dense", 5)
     n, ch, d, h, w = dense.shape
     md = mh = mw = 0
+    is_f32 = 0
     if mask is not None:
-        _need(mask, torch.uint8, "masked_pool mask", 4)
+        is_f32 = 1 if mask.dtype == torch.float32 else 0
+        _need(mask, torch.float32 if is_f32 else torch.uint8, "masked_pool mask", 4)
         if mask.shape[0] != n:
             raise ValueError("masked_pool: mask batch mismatch")
         md, mh, mw = mask.shape[1:]
     ws = torch.empty(lib.dram_pool_workspace_bytes(n, ch), dtype=torch.uint8, device=dense.device)
     out = torch.empty((n, ch), dtype=torch.float32, device=dense.device)
-    check(lib.dram_masked_pool(_p(dense), _p(mask), _p(out), _p(ws), n, ch, d, h, w, md, mh, mw, _stream()),
+    check(lib.dram_masked_pool(_p(dense), _p(mask), is_f32, _p(out), _p(ws), n, ch, d, h, w, md, mh, mw, _stream()),
           "dram_masked_pool")
     return out
 

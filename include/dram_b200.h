@@ -135,16 +135,17 @@ int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, i
 
 /* ---- K6: lobe-masked / global pooling (med3d.py:383-387, 284) ---------- */
 /*
- * dense: fp32 [n][ch][d][h][w].  mask: uint8 [n][md][mh][mw] (non-zero = lung)
+ * dense: fp32 [n][ch][d][h][w].  mask: [n][md][mh][mw], uint8 (non-zero = lung)
+ * or, with mask_is_f32 != 0, fp32 weights exactly as `dout * lungs` uses them,
  * resampled on the fly with ATen's legacy `nearest` rule (med3d.py:386), or
  * NULL for the unmasked mean (lungs=None, med3d.py:383-384 and the cls path).
  * out: fp32 [n][ch]  = sum(dense*mask)/sum(mask)  (or the plain mean).
  * workspace: at least dram_pool_workspace_bytes(n, ch) bytes.
  */
 size_t dram_pool_workspace_bytes(int32_t n, int32_t ch);
-int dram_masked_pool(const float *dense, const uint8_t *mask, float *out, void *workspace,
-                     int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w, int32_t md,
-                     int32_t mh, int32_t mw, void *stream);
+int dram_masked_pool(const float *dense, const void *mask, int32_t mask_is_f32, float *out,
+                     void *workspace, int32_t n, int32_t ch, int32_t d, int32_t h, int32_t w,
+                     int32_t md, int32_t mh, int32_t mw, void *stream);
 
 /* ---- K7: dRAM = trilinear(dense -> scan size, align_corners) * ess ----- */
 /*
