@@ -12,6 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdram_b200.so")
 
 DRAM_OK = 0
+DRAM_DTYPE_BF16 = 0
+DRAM_DTYPE_F16 = 1
 
 
 class ConvDesc(C.Structure):
@@ -31,6 +33,7 @@ class ConvDesc(C.Structure):
         ("n_heads", C.c_int32), ("head_ch", C.c_int32 * 2), ("head_sigmoid", C.c_int32),
         ("store_out", C.c_int32),
         ("tw", C.c_int32), ("th", C.c_int32), ("td", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 
@@ -43,14 +46,14 @@ SIGNATURES = {
     "dram_last_error": (C.c_int, [C.c_char_p, _sz]),
     "dram_sm_count": (C.c_int, []),
     "dram_conv3d_out_dims": (C.c_int, [C.POINTER(ConvDesc), _pi32, _pi32, _pi32]),
-    "dram_conv3d_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "dram_conv3d_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _vp, C.POINTER(_vp)]),
     "dram_conv3d_plan_destroy": (C.c_int, [_vp]),
     "dram_conv3d_run": (C.c_int, [_vp, _i32, _vp]),
     "dram_conv3d_plan_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, _pi32, _pi32, _pi32]),
-    "dram_stem_expand": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_stem_expand": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_pool_workspace_bytes": (_sz, [_i32, _i32]),
     "dram_masked_pool": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_dram_workspace_bytes": (_sz, [_i32]),
@@ -60,8 +63,8 @@ SIGNATURES = {
     "dram_window_standardize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _vp]),
     "dram_resize_image": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_resize_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "dram_ncdhw_f32_to_ndhwc_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "dram_ndhwc_bf16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

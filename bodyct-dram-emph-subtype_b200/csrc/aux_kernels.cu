@@ -12,13 +12,32 @@ namespace dram {
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
-__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+// Two packed 16-bit activations <-> fp32 for either storage type (f16 != 0: IEEE half, else bf16).
+__device__ __forceinline__ uint32_t pack2(float a, float b, int f16) {
+  if (f16) {
+    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
+    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+  }
   bf162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&h);
 }
-__device__ __forceinline__ float2 unpack_bf162(uint32_t u) {
+__device__ __forceinline__ float2 unpack2(uint32_t u, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<__half2 *>(&u));
   bf162 h = *reinterpret_cast<bf162 *>(&u);
   return make_float2(__low2float(h), __high2float(h));
+}
+__device__ __forceinline__ float load16(const uint16_t *p, int f16) {
+  return f16 ? __half2float(*reinterpret_cast<const __half *>(p)) : __bfloat162float(*reinterpret_cast<const bf16 *>(p));
+}
+__device__ __forceinline__ uint16_t store16(float v, int f16) {
+  if (f16) {
+    __half h = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
+    return *reinterpret_cast<uint16_t *>(&h);
+  }
+  bf16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t *>(&h);
 }
 
 // ATen's source index for linear modes with align_corners=True
@@ -76,7 +95,7 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
 // K2a stem unfold: one 16-byte store per thread (8 pseudo-channels = one kh row of taps).
 // ---------------------------------------------------------------------------------------
 __global__ void stem_expand_kernel(const float *__restrict__ x, uint4 *__restrict__ out, int n, int d,
-                                   int h, int w, int h2, int w2) {
+                                   int h, int w, int h2, int w2, int f16) {
   const int64_t total = (int64_t)n * d * h2 * w2 * 8;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -99,8 +118,8 @@ __global__ void stem_expand_kernel(const float *__restrict__ x, uint4 *__restric
         if (iw >= 0 && iw < w) f[j] = __ldg(row + iw);
       }
     }
-    out[t] = make_uint4(pack_bf162(f[0], f[1]), pack_bf162(f[2], f[3]), pack_bf162(f[4], f[5]),
-                        pack_bf162(f[6], f[7]));
+    out[t] = make_uint4(pack2(f[0], f[1], f16), pack2(f[2], f[3], f16), pack2(f[4], f[5], f16),
+                        pack2(f[6], f[7], f16));
   }
 }
 
@@ -108,7 +127,7 @@ __global__ void stem_expand_kernel(const float *__restrict__ x, uint4 *__restric
 // K3 max-pool 3^3 s2 p1, NDHWC bf16, 8 channels per thread.
 // ---------------------------------------------------------------------------------------
 __global__ void maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d,
-                                 int h, int w, int cg, int od, int oh, int ow) {
+                                 int h, int w, int cg, int od, int oh, int ow, int f16) {
   const int64_t total = (int64_t)n * od * oh * ow * cg;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -120,10 +139,9 @@ __global__ void maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict_
     v /= oh;
     const int xd = (int)(v % od);
     const int b = (int)(v / od);
-    bf162 m[4];
-    const bf162 ninf = __float2bfloat162_rn(-INFINITY);
+    float m[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) m[q] = ninf;
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
     for (int zd = 0; zd < 3; ++zd) {
       const int id = 2 * xd - 1 + zd;
       if (id < 0 || id >= d) continue;
@@ -137,16 +155,16 @@ __global__ void maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict_
           const uint4 u = __ldg(x + ((((int64_t)b * d + id) * h + ih) * w + iw) * cg + g);
           const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], *reinterpret_cast<const bf162 *>(&uu[q]));
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack2(uu[q], f16);  // max over exactly representable values: exact
+            m[2 * q] = fmaxf(m[2 * q], f.x);
+            m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
+          }
         }
       }
     }
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t *>(&m[0]);
-    o.y = *reinterpret_cast<uint32_t *>(&m[1]);
-    o.z = *reinterpret_cast<uint32_t *>(&m[2]);
-    o.w = *reinterpret_cast<uint32_t *>(&m[3]);
-    out[t] = o;
+    out[t] = make_uint4(pack2(m[0], m[1], f16), pack2(m[2], m[3], f16), pack2(m[4], m[5], f16),
+                        pack2(m[6], m[7], f16));
   }
 }
 
@@ -155,7 +173,7 @@ __global__ void maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict_
 // ATen's nesting order (W innermost, D outermost).
 // ---------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d,
-                                  int h, int w, int cg, float sd, float sh, float sw) {
+                                  int h, int w, int cg, float sd, float sh, float sw, int f16) {
   const int od = 2 * d, oh = 2 * h, ow = 2 * w;
   const int64_t total = (int64_t)n * od * oh * ow * cg;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -190,7 +208,7 @@ __global__ void upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict
         const uint32_t a1[4] = {u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 p0 = unpack_bf162(a0[q]), p1 = unpack_bf162(a1[q]);
+          const float2 p0 = unpack2(a0[q], f16), p1 = unpack2(a1[q], f16);
           accd[2 * q + 0] += wh * (iw.w0 * p0.x + iw.w1 * p1.x);
           accd[2 * q + 1] += wh * (iw.w0 * p0.y + iw.w1 * p1.y);
         }
@@ -198,8 +216,8 @@ __global__ void upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += wd * accd[j];
     }
-    out[t] = make_uint4(pack_bf162(acc[0], acc[1]), pack_bf162(acc[2], acc[3]),
-                        pack_bf162(acc[4], acc[5]), pack_bf162(acc[6], acc[7]));
+    out[t] = make_uint4(pack2(acc[0], acc[1], f16), pack2(acc[2], acc[3], f16),
+                        pack2(acc[4], acc[5], f16), pack2(acc[6], acc[7], f16));
   }
 }
 
@@ -450,19 +468,19 @@ __global__ void resize_mask_kernel(const uint8_t *__restrict__ x, uint8_t *__res
 // ---------------------------------------------------------------------------------------
 // layout helpers
 // ---------------------------------------------------------------------------------------
-__global__ void ncdhw_to_ndhwc_kernel(const float *__restrict__ x, bf16 *__restrict__ out, int n, int c,
-                                      int64_t plane) {
+__global__ void ncdhw_to_ndhwc_kernel(const float *__restrict__ x, uint16_t *__restrict__ out, int n, int c,
+                                      int64_t plane, int f16) {
   const int64_t total = (int64_t)n * c * plane;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(t % c);
     const int64_t v = t / c;  // b*plane + s
     const int64_t b = v / plane, s = v % plane;
-    out[t] = __float2bfloat16_rn(x[(b * c + ch) * plane + s]);
+    out[t] = store16(x[(b * c + ch) * plane + s], f16);
   }
 }
-__global__ void ndhwc_to_ncdhw_kernel(const bf16 *__restrict__ x, float *__restrict__ out, int n, int c,
-                                      int64_t plane) {
+__global__ void ndhwc_to_ncdhw_kernel(const uint16_t *__restrict__ x, float *__restrict__ out, int n, int c,
+                                      int64_t plane, int f16) {
   const int64_t total = (int64_t)n * c * plane;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -470,7 +488,7 @@ __global__ void ndhwc_to_ncdhw_kernel(const bf16 *__restrict__ x, float *__restr
     const int64_t r = t / plane;  // b*c + ch
     const int64_t b = r / c;
     const int ch = (int)(r % c);
-    out[t] = __bfloat162float(x[(b * plane + s) * c + ch]);
+    out[t] = load16(x + (b * plane + s) * c + ch, f16);
   }
 }
 
@@ -480,40 +498,52 @@ using namespace dram;
 
 static const int kThreads = 256;
 
+static int dtype_flag(int32_t dtype, int *f16) {
+  DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dtype must be DRAM_DTYPE_BF16 or DRAM_DTYPE_F16");
+  *f16 = dtype == DRAM_DTYPE_F16;
+  return DRAM_OK;
+}
+
 extern "C" int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                                void *stream) {
+                                int32_t dtype, void *stream) {
+  int f16;
+  if (int rc = dtype_flag(dtype, &f16)) return rc;
   DRAM_REQUIRE(x && out, "dram_stem_expand: null pointer");
   DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, "dram_stem_expand: empty volume");
   const int h2 = (h - 1) / 2 + 1, w2 = (w - 1) / 2 + 1;
   const int64_t total = (int64_t)n * d * h2 * w2 * 8;
   stem_expand_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<uint4 *>(out), n, d, h, w, h2, w2);
+      x, reinterpret_cast<uint4 *>(out), n, d, h, w, h2, w2, f16);
   DRAM_CHECK_LAUNCH("stem_expand_kernel");
   return DRAM_OK;
 }
 
 extern "C" int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                              int32_t c, void *stream) {
+                              int32_t c, int32_t dtype, void *stream) {
+  int f16;
+  if (int rc = dtype_flag(dtype, &f16)) return rc;
   DRAM_REQUIRE(x && out, "dram_maxpool3d: null pointer");
   DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
                "dram_maxpool3d: bad shape (c must be a multiple of 8)");
   const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
   const int64_t total = (int64_t)n * od * oh * ow * (c / 8);
   maxpool3d_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow);
+      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow, f16);
   DRAM_CHECK_LAUNCH("maxpool3d_kernel");
   return DRAM_OK;
 }
 
 extern "C" int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                               int32_t c, void *stream) {
+                               int32_t c, int32_t dtype, void *stream) {
+  int f16;
+  if (int rc = dtype_flag(dtype, &f16)) return rc;
   DRAM_REQUIRE(x && out, "dram_upsample2x: null pointer");
   DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0,
                "dram_upsample2x: bad shape (c must be a multiple of 8)");
   const int64_t total = (int64_t)n * d * h * w * 8 * (c / 8);
   upsample2x_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8,
-      ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w));
+      ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w), f16);
   DRAM_CHECK_LAUNCH("upsample2x_kernel");
   return DRAM_OK;
 }
@@ -635,22 +665,26 @@ extern "C" int dram_resize_mask(const uint8_t *x, uint8_t *out, const int32_t *d
   return DRAM_OK;
 }
 
-extern "C" int dram_ncdhw_f32_to_ndhwc_bf16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
-                                            int32_t h, int32_t w, void *stream) {
-  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ncdhw_f32_to_ndhwc_bf16: bad argument");
+extern "C" int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
+                                          int32_t h, int32_t w, int32_t dtype, void *stream) {
+  int f16;
+  if (int rc = dtype_flag(dtype, &f16)) return rc;
+  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ncdhw_f32_to_ndhwc_16: bad argument");
   const int64_t plane = (int64_t)d * h * w;
   ncdhw_to_ndhwc_kernel<<<stream_grid(plane * n * c, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      x, reinterpret_cast<bf16 *>(out), n, c, plane);
+      x, reinterpret_cast<uint16_t *>(out), n, c, plane, f16);
   DRAM_CHECK_LAUNCH("ncdhw_to_ndhwc_kernel");
   return DRAM_OK;
 }
 
-extern "C" int dram_ndhwc_bf16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
-                                            int32_t h, int32_t w, void *stream) {
-  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ndhwc_bf16_to_ncdhw_f32: bad argument");
+extern "C" int dram_ndhwc_16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
+                                          int32_t h, int32_t w, int32_t dtype, void *stream) {
+  int f16;
+  if (int rc = dtype_flag(dtype, &f16)) return rc;
+  DRAM_REQUIRE(x && out && n > 0 && c > 0 && d > 0 && h > 0 && w > 0, "dram_ndhwc_16_to_ncdhw_f32: bad argument");
   const int64_t plane = (int64_t)d * h * w;
   ndhwc_to_ncdhw_kernel<<<stream_grid(plane * n * c, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const bf16 *>(x), out, n, c, plane);
+      reinterpret_cast<const uint16_t *>(x), out, n, c, plane, f16);
   DRAM_CHECK_LAUNCH("ndhwc_to_ncdhw_kernel");
   return DRAM_OK;
 }

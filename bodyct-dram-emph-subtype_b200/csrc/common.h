@@ -1,6 +1,7 @@
 // Shared host/device helpers for libdram_b200.so (internal; the public ABI is include/dram_b200.h).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>

@@ -53,9 +53,11 @@ struct ConvKParams {
   int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
   int chunks1, chunks_total;   // 64-channel chunks of source 1 / of both sources
   int relu;
+  int is_f16;                  // operand/activation storage: 0 = bf16, 1 = fp16 (same 2-byte layout)
   const float *bias;
-  __nv_bfloat16 *out;
-  const __nv_bfloat16 *res;
+  const float *scale;          // optional fp32 per-channel multiplier applied to the accumulator
+  uint16_t *out;
+  const uint16_t *res;
   int res_c, res_stride, res_d, res_h, res_w;
   int n_heads, head_ch0, head_ch1, head_sigmoid, store_out;
   const float *head_w;
@@ -185,11 +187,28 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major A and
-// B, n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format (0 = F16, 1 = BF16) at bits 7 and
+// 10, K-major A and B, n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc_16bit(int m, int n, int is_f16) {
+  return (1u << 4) | ((is_f16 ? 0u : 1u) << 7) | ((is_f16 ? 0u : 1u) << 10) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// Two packed 16-bit activations <-> fp32, for either storage type.
+__device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
+  if (is_f16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&u);
+  return make_float2(__low2float(h), __high2float(h));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
+  if (is_f16) {
+    // saturate instead of overflowing to inf
+    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
+    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&h);
 }
 
 struct TileCoord {
@@ -301,7 +320,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
     __syncwarp();
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc_16bit(BLOCK_M, BLOCK_N, p.is_f16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -360,7 +379,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       const int od = t.d0 + ld, oh = t.h0 + lh, ow = t.w0 + lw;
       const bool valid = (od < p.Do) && (oh < p.Ho) && (ow < p.Wo);
       const size_t vox = (((size_t)t.sample * p.Do + od) * p.Ho + oh) * p.Wo + ow;
-      const __nv_bfloat16 *res_row = nullptr;
+      const uint16_t *res_row = nullptr;
       if (p.res != nullptr && valid) {
         const size_t rvox = (((size_t)t.sample * p.res_d + (size_t)od * p.res_stride) * p.res_h +
                              (size_t)oh * p.res_stride) * p.res_w + (size_t)ow * p.res_stride;
@@ -378,13 +397,25 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
           const int cg = t.n0 + c0;  // first global output channel of this 32-column group
           float y[32];
           const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cg);
+          if (p.scale != nullptr) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(p.scale + cg);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-            y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-            y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-            y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j), sc = __ldg(s4 + j);
+              y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, b.x);
+              y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, b.y);
+              y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, b.z);
+              y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+              y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+              y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+              y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+            }
           }
           if (res_row != nullptr && cg < p.res_c) {
             const uint4 *r4 = reinterpret_cast<const uint4 *>(res_row + cg);
@@ -394,9 +425,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
               const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[q]);
-                y[8 * j + 2 * q + 0] += __low2float(h2);
-                y[8 * j + 2 * q + 1] += __high2float(h2);
+                const float2 f = unpack2(w[q], p.is_f16);
+                y[8 * j + 2 * q + 0] += f.x;
+                y[8 * j + 2 * q + 1] += f.y;
               }
             }
           }
@@ -410,10 +441,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
             for (int j = 0; j < 4; ++j) {
               uint32_t w[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[8 * j + 2 * q], y[8 * j + 2 * q + 1]);
-                w[q] = *reinterpret_cast<const uint32_t *>(&h2);
-              }
+              for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.is_f16);
               o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
@@ -482,7 +510,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c,
-                          int bw, int bh, int bd, int sw, int sh, int sd) {
+                          int bw, int bh, int bd, int sw, int sh, int sd, int is_f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -495,7 +523,8 @@ static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int 
   cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)((bw - 1) * sw + 1),
                        (cuuint32_t)((bh - 1) * sh + 1), (cuuint32_t)((bd - 1) * sd + 1), 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), gdim, gstr,
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                   const_cast<void *>(base), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -507,7 +536,7 @@ static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int 
 }
 
 static int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64_t ktot,
-                             int block_n) {
+                             int block_n, int is_f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -517,7 +546,8 @@ static int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64
   cuuint64_t gstr[1] = {(cuuint64_t)ktot * 2};
   cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstr,
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void *>(base), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -570,9 +600,10 @@ static int set_smem_attr() {
 }
 
 extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,
-                                       const void *weight, const float *bias, const void *residual,
-                                       void *out, const float *head_w, const float *head_b,
-                                       float *head_out0, float *head_out1, dram_conv_plan **plan) {
+                                       const void *weight, const float *bias, const float *scale,
+                                       const void *residual, void *out, const float *head_w,
+                                       const float *head_b, float *head_out0, float *head_out1,
+                                       dram_conv_plan **plan) {
   DRAM_REQUIRE(d && plan, "dram_conv3d_plan_create: null descriptor or plan pointer");
   *plan = nullptr;
   DRAM_REQUIRE(src1 && weight && bias, "dram_conv3d_plan_create: src1, weight and bias are required");
@@ -587,6 +618,7 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
                "conv3d: stride must be in 1..8");
   DRAM_REQUIRE(d->dd >= 1 && d->dh >= 1 && d->dw >= 1, "conv3d: dilation must be >= 1");
   DRAM_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv3d: padding must be >= 0");
+  DRAM_REQUIRE(d->dtype == DRAM_DTYPE_BF16 || d->dtype == DRAM_DTYPE_F16, "conv3d: dtype must be bf16 (0) or fp16 (1)");
   DRAM_REQUIRE(d->store_out == 0 || out != nullptr, "conv3d: out is required when store_out != 0");
   DRAM_REQUIRE(d->store_out != 0 || d->n_heads > 0, "conv3d: nothing to write");
 
@@ -663,9 +695,11 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   p.chunks1 = d->c1 / BLOCK_K;
   p.chunks_total = (d->c1 + d->c2) / BLOCK_K;
   p.relu = d->relu;
+  p.is_f16 = d->dtype == DRAM_DTYPE_F16;
   p.bias = bias;
-  p.out = reinterpret_cast<__nv_bfloat16 *>(out);
-  p.res = d->res_c > 0 ? reinterpret_cast<const __nv_bfloat16 *>(residual) : nullptr;
+  p.scale = scale;
+  p.out = reinterpret_cast<uint16_t *>(out);
+  p.res = d->res_c > 0 ? reinterpret_cast<const uint16_t *>(residual) : nullptr;
   p.res_c = d->res_c; p.res_stride = d->res_stride > 0 ? d->res_stride : 1;
   p.res_d = d->res_d; p.res_h = d->res_h; p.res_w = d->res_w;
   p.n_heads = d->n_heads;
@@ -682,15 +716,15 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   pl->flops = 2LL * d->n * Do * Ho * Wo * (int64_t)d->cout * ktot;
 
   int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, tw, th, td, d->sw,
-                          d->sh, d->sd);
+                          d->sh, d->sd, p.is_f16);
   if (rc == DRAM_OK) {
     if (d->c2 > 0)
       rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, tw, th, td, d->sw,
-                          d->sh, d->sd);
+                          d->sh, d->sd, p.is_f16);
     else
       pl->map_a2 = pl->map_a1;
   }
-  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n);
+  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, p.is_f16);
   if (rc == DRAM_OK) {
     switch (block_n) {
       case 32: pl->stages = ConvCfg<32>::STAGES; pl->smem_bytes = ConvCfg<32>::SMEM_BYTES; rc = set_smem_attr<32>(); break;

@@ -34,10 +34,11 @@ class _Step:
 
 
 class Med3DEngine:
-    def __init__(self, model, batch, dims, device):
+    def __init__(self, model, batch, dims, device, act_dtype=None):
         if device.type != "cuda":
             raise RuntimeError("Med3DEngine needs a CUDA device: this path has no CPU implementation")
         self.model = model
+        self.act_dtype = ops.default_act_dtype() if act_dtype is None else act_dtype
         self.batch, self.dims, self.device = batch, tuple(dims), device
         self.head_kind = model.head_kind
         self._weights = {}    # name -> (packed weight bf16, bias fp32) device buffers (stable addresses)
@@ -55,19 +56,17 @@ class Med3DEngine:
         return v
 
     def _register_weight(self, name, pack_fn):
-        """pack_fn() -> (bf16 [cout, K], fp32 [cout]) on self.device; buffers are refilled in place."""
-        w, b = pack_fn()
-        w = w.to(self.device).contiguous()
-        b = b.to(self.device).contiguous()
-        self._weights[name] = (w, b)
+        """pack_fn() -> (16-bit [cout, K], fp32 bias [cout], fp32 multiplier [cout]) on self.device;
+        the buffers are refilled in place so the tensor maps built on them stay valid."""
+        bufs = tuple(t.to(self.device).contiguous() for t in pack_fn())
+        self._weights[name] = bufs
 
-        def refill(w=w, b=b, pack_fn=pack_fn):
-            nw, nb = pack_fn()
-            w.copy_(nw)
-            b.copy_(nb)
+        def refill(bufs=bufs, pack_fn=pack_fn):
+            for dst, src in zip(bufs, pack_fn()):
+                dst.copy_(src)
 
         self._packers.append(refill)
-        return w, b
+        return bufs
 
     def refresh_weights(self):
         """Re-folds BatchNorm and re-packs every weight in place (after load_state_dict etc.)."""
@@ -79,15 +78,16 @@ class Med3DEngine:
         def pack():
             scale, shift = ops.fold_bn(bn, conv.bias)
             w = conv.weight.detach().to(self.device)
-            packed = ops.pack_stem_weight(w, scale.to(self.device)) if stem else ops.pack_conv_weight(w, scale.to(self.device))
-            return packed, shift.to(self.device).float()
+            fn = ops.pack_stem_weight if stem else ops.pack_conv_weight
+            packed, mult = fn(w, scale.to(self.device), dtype=self.act_dtype, normalize=True)
+            return packed, shift.to(self.device).float(), mult
 
         return self._register_weight(name, pack)
 
     # ---------------------------------------------------------------- plan
     def _add_conv(self, name, x1, wb, *, x2=None, kernel=3, stride=1, dilation=1, padding=None, relu=True,
                   residual=None, res_stride=1, heads=None, store_out=True, tile=None, flops=None):
-        plan = ops.Conv3dPlan(x1, wb[0], wb[1], x2=x2, kernel=kernel, stride=stride, dilation=dilation,
+        plan = ops.Conv3dPlan(x1, wb[0], wb[1], x2=x2, scale=wb[2], kernel=kernel, stride=stride, dilation=dilation,
                               padding=padding, relu=relu, residual=residual, res_stride=res_stride,
                               heads=heads, store_out=store_out, tile=tile)
         fl = plan.flops if flops is None else flops
@@ -99,7 +99,7 @@ class Med3DEngine:
         m, dev, B = self.model, self.device, self.batch
         D, H, W = self.dims
         e = m.expansion
-        bf = torch.bfloat16
+        bf = self.act_dtype
         D1, H1, W1 = (_conv_out(n, 7, 2, 1, 3) for n in (D, H, W))
         D2, H2, W2 = (_conv_out(n, 3, 2, 1, 1) for n in (D1, H1, W1))
         D3, H3, W3 = (_conv_out(n, 3, 2, 1, 1) for n in (D2, H2, W2))

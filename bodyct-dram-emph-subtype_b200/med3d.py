@@ -116,6 +116,8 @@ class _Med3DSegNet(nn.Module):
                 m.weight.data.fill_(1)
                 m.bias.data.zero_()
         self._engines = {}
+        # 16-bit storage type of activations/weights: None -> ops.default_act_dtype() (env DRAM_B200_DTYPE)
+        self.act_dtype = None
 
     def get_target_layer(self):
         return self.us3
@@ -128,10 +130,11 @@ class _Med3DSegNet(nn.Module):
     # ------------------------------------------------------------------ engine cache
     def engine(self, batch, dims, device):
         """The static plan for this (batch, D, H, W) on `device` (built on first use)."""
-        key = (batch, tuple(dims), device.index if device.index is not None else torch.cuda.current_device())
+        key = (batch, tuple(dims), device.index if device.index is not None else torch.cuda.current_device(),
+               self.act_dtype)
         eng = self._engines.get(key)
         if eng is None:
-            eng = Med3DEngine(self, batch, dims, device)
+            eng = Med3DEngine(self, batch, dims, device, self.act_dtype)
             self._engines[key] = eng
         return eng
 

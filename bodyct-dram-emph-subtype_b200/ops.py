@@ -5,15 +5,35 @@ raw device pointers plus the current CUDA stream to libdram_b200.so and returns 
 Stateless kernels are also registered as `torch.library` custom ops in the `dram_b200::`
 namespace so they show up in profiler traces and can be captured into CUDA graphs.
 
-Activations are NDHWC bf16: a tensor of shape [N, D, H, W, C].  There is no CPU path: every
-function raises on a non-CUDA tensor.
+Activations are NDHWC 16-bit tensors of shape [N, D, H, W, C]: torch.bfloat16 or torch.float16
+(`ACT_DTYPES`; both run at the same tensor-core rate, fp16 carries 3 more mantissa bits).  There
+is no CPU path: every function raises on a non-CUDA tensor.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _capi
 from ._capi import ConvDesc, check
+
+ACT_DTYPES = {torch.bfloat16: _capi.DRAM_DTYPE_BF16, torch.float16: _capi.DRAM_DTYPE_F16}
+
+
+def default_act_dtype():
+    """Storage type of activations/weights: env DRAM_B200_DTYPE = fp16 (default) | bf16."""
+    name = os.environ.get("DRAM_B200_DTYPE", "fp16").lower()
+    if name in ("fp16", "f16", "float16", "half"):
+        return torch.float16
+    if name in ("bf16", "bfloat16"):
+        return torch.bfloat16
+    raise ValueError(f"DRAM_B200_DTYPE={name!r}: expected fp16 or bf16")
+
+
+def _need16(t, name, ndim=None):
+    if isinstance(t, torch.Tensor) and t.dtype not in ACT_DTYPES:
+        raise TypeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")
+    return _need(t, t.dtype, name, ndim)
 
 
 def _stream():
@@ -51,28 +71,34 @@ class Conv3dPlan:
     """A frozen conv3d launch: TMA tensor maps for fixed buffers + geometry.
 
     x1 (and optional x2, concatenated after x1 along channels) are NDHWC bf16; `weight` is the
-    packed bf16 [Cout, taps*(C1+C2)] matrix from `pack_conv_weight`; `bias` fp32 [Cout].
+    packed 16-bit [Cout, taps*(C1+C2)] matrix from `pack_conv_weight`; `bias` fp32 [Cout]; the
+    optional fp32 `scale` [Cout] multiplies the accumulator before the bias.
     `residual` is NDHWC bf16 with `res_c <= Cout` channels read at `res_stride` (shortcut A).
     `heads = (head_w [sum_ch, 32] fp32, head_b [sum_ch] fp32, (ch0, ch1), sigmoid)` fuses the
     1x1x1 heads into the epilogue of a 32-channel conv.
     """
 
-    def __init__(self, x1, weight, bias, *, x2=None, kernel=3, stride=1, dilation=1, padding=None,
-                 relu=True, residual=None, res_stride=1, heads=None, store_out=True, out=None,
-                 tile=None):
+    def __init__(self, x1, weight, bias, *, x2=None, scale=None, kernel=3, stride=1, dilation=1,
+                 padding=None, relu=True, residual=None, res_stride=1, heads=None, store_out=True,
+                 out=None, tile=None):
         lib = _capi.load()
-        _need(x1, torch.bfloat16, "conv3d x1", 5)
+        _need16(x1, "conv3d x1", 5)
+        adt = x1.dtype
         n, di, hi, wi, c1 = x1.shape
         c2 = 0
         if x2 is not None:
-            _need(x2, torch.bfloat16, "conv3d x2", 5)
+            _need(x2, adt, "conv3d x2", 5)
             if tuple(x2.shape[:4]) != (n, di, hi, wi):
                 raise ValueError(f"conv3d: x2 {tuple(x2.shape)} does not match x1 {tuple(x1.shape)}")
             c2 = x2.shape[4]
         k, s, dl = _triple(kernel), _triple(stride), _triple(dilation)
         pad = tuple(dl[i] * (k[i] - 1) // 2 for i in range(3)) if padding is None else _triple(padding)
-        _need(weight, torch.bfloat16, "conv3d weight", 2)
+        _need(weight, adt, "conv3d weight", 2)
         _need(bias, torch.float32, "conv3d bias", 1)
+        if scale is not None:
+            _need(scale, torch.float32, "conv3d scale", 1)
+            if scale.shape[0] != weight.shape[0]:
+                raise ValueError("conv3d: scale length != cout")
         cout = weight.shape[0]
         taps = k[0] * k[1] * k[2]
         if weight.shape[1] != taps * (c1 + c2):
@@ -87,8 +113,9 @@ class Conv3dPlan:
         d.dd, d.dh, d.dw = dl
         d.pd, d.ph, d.pw = pad
         d.relu = 1 if relu else 0
+        d.dtype = ACT_DTYPES[adt]
         if residual is not None:
-            _need(residual, torch.bfloat16, "conv3d residual", 5)
+            _need(residual, adt, "conv3d residual", 5)
             d.res_c = residual.shape[4]
             d.res_stride = res_stride
             d.res_d, d.res_h, d.res_w = residual.shape[1:4]
@@ -116,9 +143,9 @@ class Conv3dPlan:
         self.out_shape = (n, do.value, ho.value, wo.value, cout)
         if store_out:
             if out is None:
-                out = torch.empty(self.out_shape, dtype=torch.bfloat16, device=x1.device)
+                out = torch.empty(self.out_shape, dtype=adt, device=x1.device)
             else:
-                _need(out, torch.bfloat16, "conv3d out", 5)
+                _need(out, adt, "conv3d out", 5)
                 if tuple(out.shape) != self.out_shape:
                     raise ValueError(f"conv3d: out shape {tuple(out.shape)} != {self.out_shape}")
         else:
@@ -133,13 +160,13 @@ class Conv3dPlan:
         ho1 = self.head_outs[1] if len(self.head_outs) > 1 else None
 
         handle = C.c_void_p()
-        check(lib.dram_conv3d_plan_create(C.byref(d), _p(x1), _p(x2), _p(weight), _p(bias), _p(residual),
-                                          _p(out), _p(head_w), _p(head_b), _p(ho0), _p(ho1),
+        check(lib.dram_conv3d_plan_create(C.byref(d), _p(x1), _p(x2), _p(weight), _p(bias), _p(scale),
+                                          _p(residual), _p(out), _p(head_w), _p(head_b), _p(ho0), _p(ho1),
                                           C.byref(handle)), "dram_conv3d_plan_create")
         self._handle = handle
         self._lib = lib
         # keep every buffer the tensor maps point at alive for the life of the plan
-        self._keep = (x1, x2, weight, bias, residual, out, head_w, head_b, ho0, ho1)
+        self._keep = (x1, x2, weight, bias, scale, residual, out, head_w, head_b, ho0, ho1)
         flops, mt, nt, bn, st = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         check(lib.dram_conv3d_plan_info(handle, C.byref(flops), C.byref(mt), C.byref(nt), C.byref(bn),
                                         C.byref(st)), "dram_conv3d_plan_info")
@@ -161,17 +188,29 @@ class Conv3dPlan:
             self._handle = None
 
 
-def pack_conv_weight(weight, scale=None, splits=None):
-    """[Cout, Cin, kd, kh, kw] fp32 -> bf16 [Cout, kd*kh*kw*Cin] (tap-major, channel-minor).
+def pow2_normalizer(w2d):
+    """Per-row power of two m with max|row| / m in [0.5, 1): dividing by it is exact and keeps every
+    packed weight in the normal range of fp16; the kernel multiplies the accumulator by m again."""
+    amax = w2d.abs().amax(dim=1).clamp_min(2.0 ** -100)
+    return torch.exp2(torch.floor(torch.log2(amax)) + 1.0)
 
-    `scale` (fp32 [Cout]) is the folded BatchNorm factor gamma/sqrt(var+eps), multiplied in
-    fp32 before the single rounding to bf16.
+
+def pack_conv_weight(weight, scale=None, dtype=torch.bfloat16, normalize=False):
+    """[Cout, Cin, kd, kh, kw] fp32 -> 16-bit [Cout, kd*kh*kw*Cin] (tap-major, channel-minor).
+
+    `scale` (fp32 [Cout]) is the folded BatchNorm factor gamma/sqrt(var+eps), multiplied in fp32
+    before the single rounding to `dtype`.  With `normalize` the rows are divided by a power of two
+    (exact) and `(packed, multiplier fp32 [Cout])` is returned for the epilogue `scale` argument.
     """
     w = weight.detach().to(torch.float32)
     if scale is not None:
         w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
     cout = w.shape[0]
-    return w.permute(0, 2, 3, 4, 1).reshape(cout, -1).to(torch.bfloat16).contiguous()
+    w = w.permute(0, 2, 3, 4, 1).reshape(cout, -1)
+    if normalize:
+        mult = pow2_normalizer(w)
+        return (w / mult.view(-1, 1)).to(dtype).contiguous(), mult.contiguous()
+    return w.to(dtype).contiguous()
 
 
 def fold_bn(bn, conv_bias=None, eps=None):
@@ -187,44 +226,54 @@ def fold_bn(bn, conv_bias=None, eps=None):
 # --------------------------------------------------------------------------------------------
 # stateless kernels
 # --------------------------------------------------------------------------------------------
-def stem_expand(x, out=None):
-    """fp32 [N, D, H, W] -> bf16 [N, D, ceil(H/2), ceil(W/2), 64] (K2a)."""
+def stem_expand(x, out=None, dtype=torch.bfloat16):
+    """fp32 [N, D, H, W] -> 16-bit [N, D, ceil(H/2), ceil(W/2), 64] (K2a)."""
     _need(x, torch.float32, "stem_expand x", 4)
     n, d, h, w = x.shape
     shape = (n, d, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
     if out is None:
-        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
-    check(_capi.load().dram_stem_expand(_p(x), _p(out), n, d, h, w, _stream()), "dram_stem_expand")
+        out = torch.empty(shape, dtype=dtype, device=x.device)
+    _need16(out, "stem_expand out", 5)
+    check(_capi.load().dram_stem_expand(_p(x), _p(out), n, d, h, w, ACT_DTYPES[out.dtype], _stream()),
+          "dram_stem_expand")
     return out
 
 
-def pack_stem_weight(weight, scale=None):
-    """conv1.weight [64, 1, 7, 7, 7] -> bf16 [64, 7*64] matching `stem_expand` (k = kd*64 + kh*8 + kw)."""
+def pack_stem_weight(weight, scale=None, dtype=torch.bfloat16, normalize=False):
+    """conv1.weight [64, 1, 7, 7, 7] -> 16-bit [64, 7*64] matching `stem_expand` (k = kd*64 + kh*8 + kw)."""
     w = weight.detach().to(torch.float32)
     if scale is not None:
         w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
     cout = w.shape[0]
     packed = torch.zeros((cout, 7, 8, 8), dtype=torch.float32, device=w.device)
     packed[:, :, :7, :7] = w[:, 0]
-    return packed.reshape(cout, 7 * 64).to(torch.bfloat16).contiguous()
+    packed = packed.reshape(cout, 7 * 64)
+    if normalize:
+        mult = pow2_normalizer(packed)
+        return (packed / mult.view(-1, 1)).to(dtype).contiguous(), mult.contiguous()
+    return packed.to(dtype).contiguous()
 
 
 def maxpool3d(x, out=None):
-    _need(x, torch.bfloat16, "maxpool3d x", 5)
+    _need16(x, "maxpool3d x", 5)
     n, d, h, w, c = x.shape
     shape = (n, (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c)
     if out is None:
-        out = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
-    check(_capi.load().dram_maxpool3d(_p(x), _p(out), n, d, h, w, c, _stream()), "dram_maxpool3d")
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    _need(out, x.dtype, "maxpool3d out", 5)
+    check(_capi.load().dram_maxpool3d(_p(x), _p(out), n, d, h, w, c, ACT_DTYPES[x.dtype], _stream()),
+          "dram_maxpool3d")
     return out
 
 
 def upsample2x(x, out=None):
-    _need(x, torch.bfloat16, "upsample2x x", 5)
+    _need16(x, "upsample2x x", 5)
     n, d, h, w, c = x.shape
     if out is None:
-        out = torch.empty((n, 2 * d, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
-    check(_capi.load().dram_upsample2x(_p(x), _p(out), n, d, h, w, c, _stream()), "dram_upsample2x")
+        out = torch.empty((n, 2 * d, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+    _need(out, x.dtype, "upsample2x out", 5)
+    check(_capi.load().dram_upsample2x(_p(x), _p(out), n, d, h, w, c, ACT_DTYPES[x.dtype], _stream()),
+          "dram_upsample2x")
     return out
 
 
@@ -311,21 +360,25 @@ def resize_mask(x, size):
     return out
 
 
-def to_ndhwc_bf16(x):
-    """fp32 NCDHW -> bf16 NDHWC."""
-    _need(x, torch.float32, "to_ndhwc_bf16 x", 5)
+def to_ndhwc_16(x, dtype=torch.bfloat16):
+    """fp32 NCDHW -> 16-bit NDHWC."""
+    _need(x, torch.float32, "to_ndhwc_16 x", 5)
     n, c, d, h, w = x.shape
-    out = torch.empty((n, d, h, w, c), dtype=torch.bfloat16, device=x.device)
-    check(_capi.load().dram_ncdhw_f32_to_ndhwc_bf16(_p(x), _p(out), n, c, d, h, w, _stream()),
-          "dram_ncdhw_f32_to_ndhwc_bf16")
+    out = torch.empty((n, d, h, w, c), dtype=dtype, device=x.device)
+    check(_capi.load().dram_ncdhw_f32_to_ndhwc_16(_p(x), _p(out), n, c, d, h, w, ACT_DTYPES[dtype], _stream()),
+          "dram_ncdhw_f32_to_ndhwc_16")
     return out
 
 
+def to_ndhwc_bf16(x):
+    return to_ndhwc_16(x, torch.bfloat16)
+
+
 def to_ncdhw_f32(x):
-    """bf16 NDHWC -> fp32 NCDHW."""
-    _need(x, torch.bfloat16, "to_ncdhw_f32 x", 5)
+    """16-bit NDHWC -> fp32 NCDHW."""
+    _need16(x, "to_ncdhw_f32 x", 5)
     n, d, h, w, c = x.shape
     out = torch.empty((n, c, d, h, w), dtype=torch.float32, device=x.device)
-    check(_capi.load().dram_ndhwc_bf16_to_ncdhw_f32(_p(x), _p(out), n, c, d, h, w, _stream()),
-          "dram_ndhwc_bf16_to_ncdhw_f32")
+    check(_capi.load().dram_ndhwc_16_to_ncdhw_f32(_p(x), _p(out), n, c, d, h, w, ACT_DTYPES[x.dtype], _stream()),
+          "dram_ndhwc_16_to_ncdhw_f32")
     return out

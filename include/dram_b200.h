@@ -35,7 +35,11 @@ extern "C" {
 #define DRAM_E_LAUNCH (-3)  /* CUDA launch / runtime error                  */
 #define DRAM_E_DRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
-#define DRAM_ABI_VERSION 1
+#define DRAM_ABI_VERSION 2
+
+/* 16-bit storage type of activations and packed weights (same layout, same tensor-core rate). */
+#define DRAM_DTYPE_BF16 0
+#define DRAM_DTYPE_F16 1
 
 /* ---- library ---------------------------------------------------------- */
 int dram_version(void);
@@ -85,6 +89,7 @@ typedef struct dram_conv_desc {
   /* tile shape chosen by the caller (tw*th*td must be 128); 0 = library     */
   /* picks the shape with the fewest tiles                                   */
   int32_t tw, th, td;
+  int32_t dtype;       /* DRAM_DTYPE_BF16 or DRAM_DTYPE_F16: type of src/weight/residual/out */
 } dram_conv_desc;
 
 typedef struct dram_conv_plan dram_conv_plan; /* opaque: tensor maps + launch geometry */
@@ -95,18 +100,21 @@ int dram_conv3d_out_dims(const dram_conv_desc *d, int32_t *dout, int32_t *hout, 
 /*
  * Builds the TMA tensor maps for the given device buffers and freezes the
  * launch geometry.  Buffers must stay valid and fixed until plan_destroy.
- *   src1, src2 : bf16 NDHWC inputs (src2 may be NULL when c2 == 0)
+ *   src1, src2 : 16-bit NDHWC inputs (src2 may be NULL when c2 == 0)
  *   weight     : bf16 [cout][taps*(c1+c2)]
  *   bias       : fp32 [cout]
- *   residual   : bf16 NDHWC [n][res_d][res_h][res_w][res_c] or NULL
- *   out        : bf16 NDHWC [n][do][ho][wo][cout] (may be NULL if !store_out)
+ *   scale      : optional fp32 [cout]; y = acc * scale + bias (lets the caller keep packed weights
+ *                in the normal range of the 16-bit type); NULL = 1
+ *   residual   : 16-bit NDHWC [n][res_d][res_h][res_w][res_c] or NULL
+ *   out        : 16-bit NDHWC [n][do][ho][wo][cout] (may be NULL if !store_out)
  *   head_w     : fp32 [sum(head_ch)][32], head_b fp32 [sum(head_ch)]
  *   head_out   : fp32 NCDHW [n][head_ch[k]][do][ho][wo] per head group
  */
 int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,
-                            const void *weight, const float *bias, const void *residual,
-                            void *out, const float *head_w, const float *head_b,
-                            float *head_out0, float *head_out1, dram_conv_plan **plan);
+                            const void *weight, const float *bias, const float *scale,
+                            const void *residual, void *out, const float *head_w,
+                            const float *head_b, float *head_out0, float *head_out1,
+                            dram_conv_plan **plan);
 int dram_conv3d_plan_destroy(dram_conv_plan *plan);
 /* Launches the persistent kernel (grid = min(tiles, max_ctas or #SMs)). */
 int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, void *stream);
@@ -123,15 +131,15 @@ int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops, int32_t *m
  * `image`, models.py:432), h' = (h-1)/2+1, w' = (w-1)/2+1.
  */
 int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                     void *stream);
+                     int32_t dtype, void *stream);
 
 /* ---- K3: max-pool 3x3x3 stride 2 pad 1 (med3d.py:305, 374) ------------- */
 int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                   int32_t c, void *stream);
+                   int32_t c, int32_t dtype, void *stream);
 
 /* ---- K4: trilinear x2 up-sampling, align_corners=True (med3d.py:83,86) - */
 int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
-                    int32_t c, void *stream);
+                    int32_t c, int32_t dtype, void *stream);
 
 /* ---- K6: lobe-masked / global pooling (med3d.py:383-387, 284) ---------- */
 /*
@@ -184,11 +192,11 @@ int dram_resize_mask(const uint8_t *x, uint8_t *out, const int32_t *d_idx, int32
                      int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream);
 
 /* ---- layout helpers ---------------------------------------------------- */
-/* fp32 NCDHW -> bf16 NDHWC and back (test / debugging / hook support). */
-int dram_ncdhw_f32_to_ndhwc_bf16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
-                                 int32_t h, int32_t w, void *stream);
-int dram_ndhwc_bf16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
-                                 int32_t h, int32_t w, void *stream);
+/* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
+int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,
+                               int32_t h, int32_t w, int32_t dtype, void *stream);
+int dram_ndhwc_16_to_ncdhw_f32(const void *x, float *out, int32_t n, int32_t c, int32_t d,
+                               int32_t h, int32_t w, int32_t dtype, void *stream);
 
 #ifdef __cplusplus
 }

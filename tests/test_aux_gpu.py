@@ -7,50 +7,54 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def _bf(t):
-    return t.to(torch.bfloat16).float()
+DTYPES = [torch.bfloat16, torch.float16]
 
 
-def test_layout_roundtrip(cuda, lib):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_layout_roundtrip(cuda, lib, dt):
     from dram_b200 import ops
 
     g = torch.Generator().manual_seed(0)
-    x = _bf(torch.randn(2, 24, 3, 5, 7, generator=g))
-    y = ops.to_ncdhw_f32(ops.to_ndhwc_bf16(x.to(cuda))).cpu()
+    x = torch.randn(2, 24, 3, 5, 7, generator=g).to(dt).float()
+    y = ops.to_ncdhw_f32(ops.to_ndhwc_16(x.to(cuda), dt)).cpu()
     assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 12), (16, 6, 10)])
-def test_maxpool(cuda, lib, dims):
-    """med3d.py:305 MaxPool3d(3, stride 2, pad 1): exact (max of bf16 values)."""
+def test_maxpool(cuda, lib, dims, dt):
+    """med3d.py:305 MaxPool3d(3, stride 2, pad 1): exact (max of 16-bit values)."""
     from dram_b200 import ops
 
     g = torch.Generator().manual_seed(1)
-    x = _bf(torch.randn((2, 64) + dims, generator=g))
+    x = torch.randn((2, 64) + dims, generator=g).to(dt).float()
     ref = F.max_pool3d(x, 3, 2, 1)
-    got = ops.to_ncdhw_f32(ops.maxpool3d(ops.to_ndhwc_bf16(x.to(cuda)))).cpu()
+    got = ops.to_ncdhw_f32(ops.maxpool3d(ops.to_ndhwc_16(x.to(cuda), dt))).cpu()
     assert torch.equal(got, ref)
 
 
+@pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("dims", [(4, 4, 4), (3, 5, 6), (8, 7, 9)])
-def test_upsample2x(cuda, lib, dims):
-    """med3d.py:83 nn.Upsample(scale 2, trilinear, align_corners=True); fp32 math, one bf16 rounding."""
+def test_upsample2x(cuda, lib, dims, dt):
+    """med3d.py:83 nn.Upsample(scale 2, trilinear, align_corners=True); fp32 math, one 16-bit rounding."""
     from dram_b200 import ops
 
     g = torch.Generator().manual_seed(2)
-    x = _bf(torch.randn((2, 64) + dims, generator=g))
+    x = torch.randn((2, 64) + dims, generator=g).to(dt).float()
     ref = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
-    got = ops.to_ncdhw_f32(ops.upsample2x(ops.to_ndhwc_bf16(x.to(cuda)))).cpu()
+    got = ops.to_ncdhw_f32(ops.upsample2x(ops.to_ndhwc_16(x.to(cuda), dt))).cpu()
     assert got.shape == ref.shape
-    assert (got - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() + 1e-6
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    assert (got - ref).abs().max().item() <= ulp * ref.abs().max().item() + 1e-6
 
 
-def test_stem_expand_layout(cuda, lib):
+@pytest.mark.parametrize("dt", DTYPES)
+def test_stem_expand_layout(cuda, lib, dt):
     from dram_b200 import ops
 
     g = torch.Generator().manual_seed(3)
-    x = _bf(torch.randn(2, 5, 9, 12, generator=g))
-    got = ops.stem_expand(x.to(cuda)).float().cpu()
+    x = torch.randn(2, 5, 9, 12, generator=g).to(dt).float()
+    got = ops.stem_expand(x.to(cuda), dtype=dt).float().cpu()
     n, d, h, w = x.shape
     h2, w2 = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     xp = F.pad(x, (3, 5, 3, 5))

@@ -12,8 +12,11 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-def _rand(shape, gen, scale=1.0):
-    return (torch.randn(shape, generator=gen) * scale).to(torch.bfloat16).float()
+DT = torch.bfloat16  # storage type under test; the fp16 variants re-run a subset
+
+
+def _rand(shape, gen, scale=1.0, dtype=None):
+    return (torch.randn(shape, generator=gen) * scale).to(dtype or DT).float()
 
 
 def _close(got, ref, what):
@@ -29,9 +32,11 @@ def _close(got, ref, what):
 
 
 def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=None, res_stride=1,
-              heads=None, seed=0, tile=None):
+              heads=None, seed=0, tile=None, dtype=torch.bfloat16, normalize=False):
     from dram_b200 import ops
 
+    global DT
+    DT = dtype
     g = torch.Generator().manual_seed(seed)
     d, h, w = dims
     k3 = (k, k, k) if isinstance(k, int) else k
@@ -50,7 +55,7 @@ def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=N
         res = _rand((n, rc, d, h, w), g)
         sub = res[:, :, ::res_stride, ::res_stride, ::res_stride]
         ref[:, :rc] += sub[:, :, :ref.shape[2], :ref.shape[3], :ref.shape[4]]
-        res_t = ops.to_ndhwc_bf16(res.to(cuda))
+        res_t = ops.to_ndhwc_16(res.to(cuda), dtype)
     if relu:
         ref = ref.relu()
     head_ref = None
@@ -64,9 +69,13 @@ def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=N
             dense = torch.sigmoid(dense)
         head_ref = torch.split(dense, list(chs), dim=1)
         hk = (hw.to(cuda), hb.to(cuda), tuple(chs), sig)
+    if normalize:
+        wp, mult = ops.pack_conv_weight(wgt.to(cuda), dtype=dtype, normalize=True)
+    else:
+        wp, mult = ops.pack_conv_weight(wgt, dtype=dtype).to(cuda), None
     plan = ops.Conv3dPlan(
-        ops.to_ndhwc_bf16(x1.to(cuda)), ops.pack_conv_weight(wgt).to(cuda), bias.to(cuda),
-        x2=None if x2 is None else ops.to_ndhwc_bf16(x2.to(cuda)), kernel=k3, stride=stride, dilation=dil,
+        ops.to_ndhwc_16(x1.to(cuda), dtype), wp, bias.to(cuda), scale=mult,
+        x2=None if x2 is None else ops.to_ndhwc_16(x2.to(cuda), dtype), kernel=k3, stride=stride, dilation=dil,
         relu=relu, residual=res_t, res_stride=res_stride, heads=hk, tile=tile)
     out = plan.run()
     torch.cuda.synchronize()
@@ -134,6 +143,18 @@ def test_conv_1x1(cuda, lib):
 def test_conv_heads_reg_and_cls(cuda, lib):
     _run_conv(cuda, 1, (8, 16, 16), 64, 0, 32, 3, 1, 1, heads=((1, 1), True))
     _run_conv(cuda, 2, (8, 8, 12), 64, 0, 32, 3, 1, 1, heads=((6, 3), False))
+
+
+def test_conv_fp16_storage(cuda, lib):
+    """Same kernel with IEEE fp16 operands/activations (DRAM_DTYPE_F16) and the per-channel power-of-two
+    weight normaliser applied in the epilogue."""
+    h = torch.float16
+    _run_conv(cuda, 1, (10, 12, 20), 64, 0, 64, 3, 1, 1, residual=64, dtype=h)
+    _run_conv(cuda, 2, (8, 12, 16), 256, 0, 512, 3, 1, 4, residual=512, dtype=h, normalize=True)
+    _run_conv(cuda, 1, (16, 16, 16), 64, 0, 128, 3, 2, 1, residual=64, res_stride=1, dtype=h, normalize=True)
+    _run_conv(cuda, 1, (8, 16, 16), 128, 64, 64, 3, 1, 1, dtype=h)
+    _run_conv(cuda, 1, (8, 16, 16), 64, 0, 32, 3, 1, 1, heads=((1, 1), True), dtype=h, normalize=True)
+    _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 1, dtype=torch.bfloat16, normalize=True)
 
 
 def test_conv_tile_shapes(cuda, lib):

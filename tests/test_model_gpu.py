@@ -18,11 +18,12 @@ FACTORY = {"med3d": "resnet34segcls", "med3d18": "resnet18segcls", "med3d50": "r
            "med3ddram": "resnet34segreg", "med3ddram18": "resnet18segreg", "med3ddram50": "resnet50segreg"}
 
 
-def build_model(arch, sd, device):
+def build_model(arch, sd, device, dtype=None):
     from dram_b200 import med3d
 
     model = getattr(med3d, FACTORY[arch])()
     model.load_state_dict(sd)
+    model.act_dtype = dtype  # None -> the library default (fp16 storage)
     return model.to(device).eval()
 
 
