@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: med3ddram (ResNet-34) + dRAM inference on synthetic 256^3 CT volumes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--size 256] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the device-resident hot path over one batch of B volumes per GPU:
+K8 HU window+standardise -> stem unfold -> 38 tcgen05 conv launches (BN/ReLU/residual/heads fused) ->
+max-pool / x2 up-sampling -> lobe-masked pooling -> dRAM (trilinear to CT size x ess mask) + lesion %.
+Prints ONE JSON line (rank 0).  `value` = volumes/s with the int16 HU volumes and masks already in HBM;
+`e2e` = the same through ScanRegLightningModule.predict_step with pinned HOST buffers (fp32 image + bool
+masks copied host->device and the percentages read back every step).  Multi-GPU: volumes are sharded
+across ranks, no data-path collective (weak scaling); time = max over ranks.
+
+`--impl reference` times the reference's algorithm on the host cores (the oracle port of the reference's
+PyTorch CPU path; /root/reference itself does not exist on the GPU box) on the same config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from argparse import Namespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = "med3ddram"
+METRIC = "CT volumes/sec med3ddram inference"
+FALLBACK_TFLOPS = 1590.0  # B200_PROFILING.md fallback (burst); used only when MEASURED_PEAKS.json is absent
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs generated on the device, and bounded random weights
+# --------------------------------------------------------------------------------------------
+def make_volumes(batch, dims, device, seed):
+    """int16 HU [B,D,H,W], lung uint8, ess uint8: two ellipsoid lungs, emphysema-like low-HU blobs."""
+    D, H, W = dims
+    g = torch.Generator(device=device).manual_seed(20261018 + seed)
+    z = ((torch.arange(D, device=device, dtype=torch.float32) + 0.5) / D)[:, None, None]
+    y = ((torch.arange(H, device=device, dtype=torch.float32) + 0.5) / H)[None, :, None]
+    x = ((torch.arange(W, device=device, dtype=torch.float32) + 0.5) / W)[None, None, :]
+    lung = torch.zeros((D, H, W), dtype=torch.bool, device=device)
+    for cx in (0.30, 0.70):
+        lung |= ((z - 0.5) / 0.42) ** 2 + ((y - 0.5) / 0.36) ** 2 + ((x - cx) / 0.19) ** 2 <= 1.0
+    hu, lungs, ess = [], [], []
+    for _ in range(batch):
+        ct = torch.randn((D, H, W), generator=g, device=device) * 150.0 + 20.0
+        ct = torch.where(lung, torch.randn((D, H, W), generator=g, device=device) * 120.0 - 850.0, ct)
+        coarse = torch.rand((1, 1, D // 8, H // 8, W // 8), generator=g, device=device)
+        field = torch.nn.functional.interpolate(coarse, size=(D, H, W), mode="trilinear", align_corners=True)[0, 0]
+        blob = lung & (field > 0.78)
+        ct = torch.where(blob, torch.randn((D, H, W), generator=g, device=device) * 25.0 - 960.0, ct)
+        ct = ct.round().clamp(-1024, 1500).to(torch.int16)
+        hu.append(ct)
+        lungs.append(lung.to(torch.uint8))
+        ess.append(((ct < -910) & lung).to(torch.uint8))
+    return torch.stack(hu), torch.stack(lungs), torch.stack(ess)
+
+
+def tame_weights_(model, seed=0):
+    """Random-init weights (no checkpoint can be downloaded; paper.ckpt is a Git-LFS pointer) with
+    BatchNorm statistics chosen so that activations stay O(1): running_var = fan_in/fan_out of the
+    preceding kaiming(fan_out) convolution, small gain on the last BN of each residual block."""
+    g = torch.Generator().manual_seed(seed)
+    convs = {}
+    last = None
+    for name, m in model.named_modules():
+        if isinstance(m, torch.nn.Conv3d):
+            last = m
+        elif isinstance(m, torch.nn.BatchNorm3d) and last is not None:
+            convs[name] = last
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if isinstance(m, torch.nn.BatchNorm3d):
+                conv = convs[name]
+                k = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+                fan_in, fan_out = conv.in_channels * k, conv.out_channels * k
+                m.running_var.fill_(max(fan_in / fan_out, 0.05))
+                m.running_mean.zero_()
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.5 + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                if name.endswith("bn2") and "layer" in name:
+                    m.weight.mul_(0.3)
+        for fc in model.fcs:
+            fc.weight.mul_(0.2)
+            fc.bias.fill_(-2.0)
+    return model
+
+
+def build_module(device):
+    import dram_b200  # noqa: F401
+    from dram_b200.models import ScanRegLightningModule
+
+    torch.manual_seed(0)
+    module = ScanRegLightningModule(Namespace(model_arch=ARCH))
+    tame_weights_(module.model)
+    return module.to(device).eval()
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return FALLBACK_TFLOPS, "fallback (B200_PROFILING.md)"
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, local, world
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
+def max_over_ranks(value, world, device):
+    if world <= 1:
+        return value
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's PyTorch path on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_predict_seconds(sd, dims, batch=1, repeats=1, warmup=0):
+    """Median seconds of one oracle predict_step (transform-equivalent standardise + network + dRAM)."""
+    from oracle import pipeline_oracle as P
+    from oracle import synthetic
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs, ls, es = zip(*[synthetic.make_network_input(i, dims) for i in range(batch)])
+    b = {"image": torch.stack(xs), "lung_mask": torch.stack(ls).bool(), "ess_mask": torch.stack(es).bool()}
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            P.predict_step(sd, ARCH, b)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return statistics.median(times)
+
+
+def cpu_state_dict(module):
+    return {k: v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu()
+            for k, v in module.model.state_dict().items()}
+
+
+def cpu_baseline(module, size, budget_s=30.0):
+    """Bounded sample: a 128^3 sub-volume first; the full volume only if it fits the time budget."""
+    sd = cpu_state_dict(module)
+    small = (min(size, 128),) * 3
+    t_small = cpu_predict_seconds(sd, small)
+    scale = (size / small[0]) ** 3
+    if small[0] == size or t_small * scale > budget_s:
+        t, sample = t_small * scale, f"1 volume of {small[0]}^3 timed ({t_small:.2f} s), scaled x{scale:.0f} by voxel count to {size}^3"
+    else:
+        t = cpu_predict_seconds(sd, (size,) * 3)
+        sample = f"1 full {size}^3 volume, one pass ({t:.2f} s)"
+    return {"value": 1.0 / t, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import dram_b200  # noqa: F401
+    from dram_b200.models import ScanRegLightningModule
+
+    torch.manual_seed(0)
+    module = ScanRegLightningModule(Namespace(model_arch=ARCH))
+    tame_weights_(module.model)
+    sd = cpu_state_dict(module)
+    size = args.size
+    # each step = one bounded sample: a full volume if (steps+warmup) of them fit ~4 minutes, else a 128^3 one
+    probe = cpu_predict_seconds(sd, (min(size, 128),) * 3)
+    scale = (size / min(size, 128)) ** 3
+    full = probe * scale * (args.steps + args.warmup) <= 240.0
+    dims = (size,) * 3 if full else (min(size, 128),) * 3
+    vol_frac = 1.0 if full else 1.0 / scale
+    t = cpu_predict_seconds(sd, dims, repeats=args.steps, warmup=args.warmup)
+    value = vol_frac / t
+    sample = (f"{args.steps} steps x 1 volume of {dims[0]}^3" + ("" if full else f" (= 1/{scale:.0f} of a {size}^3 volume by voxel count)"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"med3ddram (ResNet-34) + dRAM inference, synthetic {size}^3 CT, reference algorithm on host CPU"},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# main arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    rank, local, world = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dims = (args.size,) * 3
+    B = args.batch
+    module = build_module(device)
+    hu, lungs, ess = make_volumes(B, dims, device, seed=rank)
+    eng = module.model.engine(B, dims, device)
+
+    def step():
+        return module.predict_step_from_hu(hu, lungs, ess)
+
+    # ---- device-resident throughput ----------------------------------------------------------
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    barrier(world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    launches_per_step = eng.launches_per_run() + 3 * B + 2  # K8: 3 kernels per volume; K7: kernel + finalize
+
+    # ---- end to end through the public predict_step with pinned host buffers -----------------
+    win = eng.image.detach().cpu()  # the standardised fp32 volumes predict_step receives from the transforms
+    host = {"image": win.pin_memory(), "lung_mask": lungs.bool().cpu().pin_memory(),
+            "ess_mask": ess.bool().cpu().pin_memory()}
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    res_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        p = module.predict_step(host, 0)
+    torch.cuda.synchronize()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        p = module.predict_step(host, 0)
+        res_host[0].copy_(p["cle_precentages"], non_blocking=True)
+        res_host[1].copy_(p["pse_precentages"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the scores of every step
+    t1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
+    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": e2e_ms,
+           "api": "ScanRegLightningModule.predict_step(host pinned fp32 image + bool masks) -> percentages to host"}
+
+    # ---- roofline of the dominant kernel (conv3d_umma_kernel): per-launch CUDA events ----------
+    conv_steps = [s for s in eng.steps if s.flops > 0]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in conv_steps]
+    conv_ms = 0.0
+    reps = min(args.steps, 5)
+    for _ in range(reps):
+        ci = 0
+        for s in eng.steps:
+            if s.flops > 0:
+                evs[ci][0].record()
+                s.fn()
+                evs[ci][1].record()
+                ci += 1
+            else:
+                s.fn()
+        torch.cuda.synchronize()
+        conv_ms += sum(a.elapsed_time(b) for a, b in evs)
+    conv_ms /= reps
+    conv_flops = sum(s.flops for s in conv_steps)
+    peak, peak_src = measured_peaks()
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv3d_umma_kernel (38 launches/step, all template instances)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
+                "share_of_step": conv_ms / ms_per_step}
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+        "config": {"workload": f"med3ddram (ResNet-34) + dRAM inference, synthetic {args.size}^3 CT volumes, "
+                               f"batch {B} per GPU, random-init weights (paper.ckpt is a Git-LFS pointer)",
+                   "global_batch": world * B, "parallelism": f"volume-sharded x{world}, no collective",
+                   "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+                   "storage_dtype": str(eng.act_dtype)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(module, args.size)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,223 @@
+"""Drop-in `models` module: `ScanRegLightningModule`, `ScanCLSLightningModule`, `SubtypeDataModule`.
+
+Same constructor (`args` namespace with `model_arch`, `target_size`, `scan_path`, ...), same
+attributes (`.model`, `.args`) and the same `forward(x, lungs)` / `predict_step(batch, batch_idx)`
+contract as models.py:160-181, 397-450 and 36-96 of the reference — the returned dict keeps the
+reference's seven keys and their spelling.  If pytorch_lightning is importable the classes derive
+from its LightningModule/LightningDataModule; otherwise from light stand-ins with the same surface,
+so `processor.py` runs without Lightning.
+
+Only inference is implemented: the training/validation/test steps of the reference need the
+backward kernels that are a later row of the plan, and raise NotImplementedError here.
+"""
+import enum
+
+import torch
+
+from . import ops
+from .dataset import SubtypingInference
+from .transforms import InferenceTransform
+from .utils import get_model_by_name
+
+try:  # pragma: no cover - not installed in the build image
+    import pytorch_lightning as pl
+    from pytorch_lightning.trainer.states import RunningStage
+
+    _ModuleBase, _DataModuleBase = pl.LightningModule, pl.LightningDataModule
+except ImportError:
+    class RunningStage(str, enum.Enum):
+        TRAINING = "train"
+        VALIDATING = "validate"
+        TESTING = "test"
+        PREDICTING = "predict"
+
+    class _ModuleBase(torch.nn.Module):
+        def save_hyperparameters(self, *args, **kwargs):
+            pass
+
+    class _DataModuleBase:
+        def __init__(self, *args, **kwargs):
+            pass
+
+TRAIN_PHASE = RunningStage.TRAINING
+VALID_PHASE = RunningStage.VALIDATING
+TEST_PHASE = RunningStage.TESTING
+PREDICT_PHASE = RunningStage.PREDICTING
+
+CLE_RATIO_MAP = {0: (0.0, 0.01), 1: (0.01, 0.05), 2: (0.05, 0.1), 3: (0.1, 0.2), 4: (0.2, 0.3), 5: (0.3, 1.0001)}
+PSE_RATIO_MAP = {0: (0.0, 0.01), 1: (0.01, 0.05), 2: (0.05, 1.0001)}
+
+
+def ratio_to_label(ratio, ratio_mapping):
+    """First bin with lo <= ratio < hi (processor.py:34-38, models.py:533-537); IndexError outside."""
+    hits = [label for label, (lo, hi) in ratio_mapping.items() if lo <= ratio and ratio < hi]
+    return hits[0]
+
+
+def _as_u8(mask):
+    """bool/uint8 [B,D,H,W] device mask as uint8 without a copy when possible."""
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    return (mask != 0).to(torch.uint8)
+
+
+class SubtypeDataModule(_DataModuleBase):
+    """models.py:36-96 (prediction part): builds `SubtypingInference` with the inference transform."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.datasets = {TRAIN_PHASE: TRAIN_PHASE, VALID_PHASE: VALID_PHASE, TEST_PHASE: TEST_PHASE,
+                         PREDICT_PHASE: PREDICT_PHASE}
+
+    def _make_transforms(self, mode):
+        if mode == TRAIN_PHASE:
+            raise NotImplementedError("training augmentations are outside the inference hot path")
+        device = getattr(self.args, "device", None)
+        return InferenceTransform(tuple(self.args.target_size), device=device)
+
+    def predict_dataset(self):
+        self.datasets[PREDICT_PHASE] = SubtypingInference(
+            scan_path=self.args.scan_path, lobe_path=self.args.lobe_path,
+            transforms=self._make_transforms(TEST_PHASE))
+        return self.datasets[PREDICT_PHASE]
+
+    def predict_dataloader(self, rank=0, world_size=1):
+        """Batches of the rank's shard: index r, r+N, ... of the sorted file list, padded by wrap-around
+        to equal length, like DistributedSampler(shuffle=False) (models.py:92)."""
+        ds = self.predict_dataset()
+        indices = shard_indices(len(ds), rank, world_size)
+        bs = int(getattr(self.args, "batch_size", 2))
+        for i in range(0, len(indices), bs):
+            yield collate([ds[j] for j in indices[i:i + bs]])
+
+    def train_dataloader(self):
+        raise NotImplementedError("training is not part of this build")
+
+    val_dataloader = test_dataloader = train_dataloader
+
+
+def shard_indices(n, rank, world_size):
+    """DistributedSampler(shuffle=False, drop_last=False): pad to a multiple of world_size by repeating
+    from the start, then take every world_size-th index starting at `rank`."""
+    if n == 0:
+        return []
+    total = -(-n // world_size) * world_size
+    idx = list(range(n))
+    while len(idx) < total:
+        idx += idx[: total - len(idx)]
+    return idx[rank:total:world_size]
+
+
+def collate(samples):
+    """torch's default_collate for the dataset dicts: tensors stacked, strings listed."""
+    out = {}
+    for key in samples[0]:
+        vals = [s[key] for s in samples]
+        if isinstance(vals[0], torch.Tensor):
+            out[key] = torch.stack(vals)
+        elif isinstance(vals[0], str):
+            out[key] = list(vals)
+        else:
+            out[key] = torch.as_tensor(vals)
+    return out
+
+
+class _ScanModule(_ModuleBase):
+    def __init__(self, args):
+        self.args = args
+        super().__init__()
+        self.model = get_model_by_name(args.model_arch)
+        self.save_hyperparameters()
+        self.trace = True
+
+    def forward(self, x, lungs):
+        return self.model(x, lungs)
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("dram_b200 implements the inference path (forward / predict_step) only")
+
+    training_step = validation_step = test_step = configure_optimizers = _unsupported
+
+    def _to_device(self, t):
+        dev = next(self.model.parameters()).device
+        return t if t.device == dev else t.to(dev, non_blocking=True)
+
+
+class ScanRegLightningModule(_ScanModule):
+    """models.py:397-450.  `per_sample_percentage=True` divides each sample's dRAM sum by its own lung
+    volume instead of the whole batch's (reference quirk Q1, models.py:440-441); default = reference."""
+
+    def __init__(self, args):
+        super().__init__(args)
+        self.beta, self.gamma = 0.7338, 0.2578
+        self.per_sample_percentage = bool(getattr(args, "per_sample_percentage", False))
+
+    def predict_step(self, batch, batch_idx, dataloader_idx=0):
+        with torch.no_grad():
+            image = self._to_device(batch["image"]).float().contiguous()
+            lungs = _as_u8(self._to_device(batch["lung_mask"]))
+            ess = _as_u8(self._to_device(batch["ess_mask"]))
+            if self.model.head_kind != "reg":
+                raise RuntimeError(f"{type(self).__name__} needs a *dram (regression) architecture, got a "
+                                   "classification one; use ScanCLSLightningModule for med3d/med3d18/med3d50")
+            B, D, H, W = image.shape
+            eng = self.model.eval().engine(B, (D, H, W), image.device)
+            dense, _ = eng.run(image, lungs)
+            cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
+                                                   per_sample_denominator=self.per_sample_percentage)
+            return {
+                "cle_dense_outs": cle,
+                "pse_dense_outs": pse,
+                "cle_precentages": pct[0],
+                "pse_precentages": pct[1],
+                "crop_slices": batch.get("crop_slice"),
+                "original_size": batch.get("original_size"),
+                "uids": batch.get("uid"),
+            }
+
+    def predict_step_from_hu(self, hu, lung_mask, ess_mask):
+        """The device-resident hot path of SURVEY §8d: int16 HU volumes already at network size
+        [B,D,H,W] -> K8 window+standardise (per volume) -> network -> pooling -> dRAM.  Returns the
+        same dict as predict_step (without the bookkeeping keys)."""
+        with torch.no_grad():
+            if not hu.is_cuda or hu.dtype != torch.int16:
+                raise RuntimeError("predict_step_from_hu: expected an int16 CUDA tensor [B,D,H,W]")
+            B, D, H, W = hu.shape
+            eng = self.model.eval().engine(B, (D, H, W), hu.device)
+            for b in range(B):  # statistics are per volume (intensity_transforms.py:104-114)
+                ops.window_standardize(hu[b], out=eng.image[b])
+            lungs, ess = _as_u8(lung_mask), _as_u8(ess_mask)
+            dense, _ = eng.run(eng.image, lungs)
+            cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
+                                                   per_sample_denominator=self.per_sample_percentage)
+            return {"cle_dense_outs": cle, "pse_dense_outs": pse, "cle_precentages": pct[0],
+                    "pse_precentages": pct[1]}
+
+    def _ratio_to_label(self, ratios, ratio_mapping):
+        labels = [ratio_to_label(r.item(), ratio_mapping) for r in ratios]
+        return torch.as_tensor(labels).long().to(ratios.device)
+
+
+class ScanCLSLightningModule(_ScanModule):
+    """models.py:160-181; prediction = argmax of the pooled class logits (models.py:245-247)."""
+
+    def predict_step(self, batch, batch_idx, dataloader_idx=0):
+        with torch.no_grad():
+            image = self._to_device(batch["image"]).float().contiguous()
+            if self.model.head_kind != "cls":
+                raise RuntimeError(f"{type(self).__name__} needs a classification architecture (med3d*)")
+            B, D, H, W = image.shape
+            eng = self.model.eval().engine(B, (D, H, W), image.device)
+            _, logits = eng.run(image, None)
+            return {
+                "cle_logits": logits[0].clone(),
+                "pse_logits": logits[1].clone(),
+                "cle_labels": logits[0].argmax(-1),
+                "pse_labels": logits[1].argmax(-1),
+                "crop_slices": batch.get("crop_slice"),
+                "original_size": batch.get("original_size"),
+                "uids": batch.get("uid"),
+            }

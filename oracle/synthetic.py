@@ -106,12 +106,14 @@ def make_state_dict(arch, seed=0, calib_dims=(32, 32, 32), prefix="", logit_std=
             sd[key] = torch.ones(shape, dtype=torch.float64)
         else:
             sd[key] = torch.zeros(shape, dtype=torch.int64)
-    # residual branches get a smaller gain so the trunk does not drown in the last BN of each block
+    # Residual branches get a small gain (gamma of the last BN of each block ~ U(0.15, 0.45)), in the
+    # spirit of zero-init-residual training: with O(1) gains a random, untrained ResNet is chaotic (a
+    # 1e-3 perturbation of an early activation grows to O(1) at the heads), which trained networks are not.
     kind, layers, head = M.ARCHS[arch]
     last_bn = "bn3" if kind == "bottleneck" else "bn2"
     for li, nb in enumerate(layers, start=1):
         for bi in range(nb):
-            sd[f"layer{li}.{bi}.{last_bn}.weight"] *= 0.5
+            sd[f"layer{li}.{bi}.{last_bn}.weight"] *= 0.3
     # calibration pass (fp64): sets every BN's running statistics from the activations it sees
     img, _, _ = make_network_input(9000 + seed, calib_dims)
     x = img.double()[None, None]

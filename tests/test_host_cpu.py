@@ -1,0 +1,200 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, argument
+validation works without a GPU, and the drop-in Python surface (factories, state_dict layout, config
+resolution, checkpoint loading, sharding, .mha I/O, labels, result merging) behaves like the reference's."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from dram_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "dram_b200.h")).read()
+    declared = set(re.findall(r"\b(dram_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dram_last_error"} - {"dram_last_error"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.SIGNATURES), (declared ^ set(_capi.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/dram_b200.h but not exported"
+    assert lib.dram_version() == 2
+
+
+def test_argument_validation_without_gpu(lib):
+    import ctypes as C
+
+    from dram_b200 import _capi
+
+    d = _capi.ConvDesc()
+    handle = C.c_void_p()
+    rc = lib.dram_conv3d_plan_create(C.byref(d), None, None, None, None, None, None, None, None, None, None, None,
+                                     C.byref(handle))
+    assert rc == -1 and "required" in _capi.last_error()
+    d.n, d.di, d.hi, d.wi, d.c1, d.cout = 1, 8, 8, 8, 60, 64
+    d.kd = d.kh = d.kw = 3
+    d.sd = d.sh = d.sw = d.dd = d.dh = d.dw = 1
+    rc = lib.dram_conv3d_plan_create(C.byref(d), 16, None, 16, 16, None, None, 16, None, None, None, None, C.byref(handle))
+    assert rc == -1 and "multiple of 64" in _capi.last_error()
+    do, ho, wo = C.c_int32(), C.c_int32(), C.c_int32()
+    d.di, d.hi, d.wi, d.pd, d.ph, d.pw, d.sd = 256, 128, 128, 3, 0, 0, 2
+    d.kd, d.kh, d.kw = 7, 1, 1
+    assert lib.dram_conv3d_out_dims(C.byref(d), C.byref(do), C.byref(ho), C.byref(wo)) == 0
+    assert (do.value, ho.value, wo.value) == (128, 128, 128)
+    assert lib.dram_maxpool3d(None, None, 1, 8, 8, 8, 64, 0, None) == -1
+    assert lib.dram_stem_expand(None, None, 1, 8, 8, 8, 7, None) == -1  # bad dtype code
+    assert lib.dram_pool_workspace_bytes(2, 3) == 8 * 2 * 4
+
+
+def test_ops_refuse_cpu_tensors(lib):
+    from dram_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.maxpool3d(torch.zeros(1, 4, 4, 4, 64, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        ops.window_standardize(torch.zeros(4, 4, 4, dtype=torch.int16))
+
+
+def test_factories_and_state_dict_layout():
+    from dram_b200 import med3d
+
+    with open(os.path.join(GOLDEN, "state_layouts.json")) as f:
+        layouts = json.load(f)
+    fac = {"med3d": med3d.resnet34segcls, "med3d18": med3d.resnet18segcls, "med3d50": med3d.resnet50segcls,
+           "med3ddram": med3d.resnet34segreg, "med3ddram18": med3d.resnet18segreg, "med3ddram50": med3d.resnet50segreg}
+    for arch, f in fac.items():
+        m = f(n_classes=[6, 3]) if "dram" not in arch else f()
+        got = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+        assert got == layouts[arch]["keys"], arch
+        assert type(m).__name__ == layouts[arch]["class"]
+        assert m.get_target_layer() is m.us3
+        assert sum(p.numel() for p in m.parameters()) == layouts[arch]["params"]
+
+
+def test_get_model_by_name_and_greedy_load(tmp_path):
+    from dram_b200 import utils
+
+    m = utils.get_model_by_name("med3ddram18")
+    assert type(m).__name__ == "ResNetSegReg" and len(m.state_dict()) == 141
+    c = utils.get_model_by_name("med3d18")
+    assert type(c).__name__ == "ResNetSegCls" and c.n_classes == [6, 3]
+    with pytest.raises(FileNotFoundError):
+        utils.get_model_by_name("nope")
+    sd = {k: torch.full_like(v, 0.5) if v.is_floating_point() else v for k, v in m.state_dict().items()}
+    sd["conv1.weight"] = torch.zeros(3, 3)      # shape mismatch -> skipped
+    sd["not.a.key"] = torch.zeros(1)            # unexpected -> skipped
+    del sd["bn1.bias"]                          # missing -> kept
+    before = m.conv1.weight.clone()
+    utils.load_state_dict_greedy(m, sd)
+    assert torch.equal(m.conv1.weight, before)
+    assert float(m.layer1[0].conv1.weight.mean()) == 0.5
+    # Lightning checkpoints carry the `model.` prefix of the module attribute (models.py:408)
+    from argparse import Namespace
+
+    from dram_b200.models import ScanRegLightningModule
+
+    module = ScanRegLightningModule(Namespace(model_arch="med3ddram18"))
+    utils.load_state_dict_greedy(module, {"model." + k: v for k, v in sd.items()})
+    assert float(module.model.layer1[0].conv1.weight.mean()) == 0.5
+
+
+def test_shard_indices_equal_distributed_sampler():
+    from torch.utils.data import DistributedSampler
+
+    from dram_b200.models import shard_indices
+
+    for n in (1, 2, 5, 8, 13):
+        for world in (1, 2, 3, 4, 8):
+            for rank in range(world):
+                ref = list(DistributedSampler(range(n), num_replicas=world, rank=rank, shuffle=False))
+                assert shard_indices(n, rank, world) == ref, (n, world, rank)
+
+
+def test_mha_roundtrip(tmp_path):
+    from dram_b200 import mha_io
+
+    rng = np.random.default_rng(0)
+    for dtype, compress in ((np.int16, True), (np.uint8, True), (np.float32, False)):
+        arr = (rng.standard_normal((5, 7, 9)) * 100).astype(dtype)
+        p = str(tmp_path / f"a_{np.dtype(dtype).name}.mha")
+        mha_io.write_mha(p, arr, spacing=(0.7, 0.7, 1.25), origin=(-10.0, 3.5, 8.0), compress=compress)
+        back, meta = mha_io.read_mha(p)
+        assert back.dtype == arr.dtype and np.array_equal(back, arr)
+        assert meta["spacing"] == (0.7, 0.7, 1.25) and meta["origin"] == (-10.0, 3.5, 8.0)
+        assert meta["direction"] == (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+
+
+def test_labels_and_result_merging(tmp_path):
+    from argparse import Namespace
+
+    from dram_b200 import processor
+    from dram_b200.models import CLE_RATIO_MAP, PSE_RATIO_MAP, ratio_to_label
+
+    with open(os.path.join(GOLDEN, "labels.json")) as f:
+        fix = json.load(f)
+    ratios = torch.tensor(fix["ratios"], dtype=torch.float32)
+    assert [ratio_to_label(r.item(), CLE_RATIO_MAP) for r in ratios] == fix["cle"]
+    assert [ratio_to_label(r.item(), PSE_RATIO_MAP) for r in ratios] == fix["pse"]
+    rec = lambda uid, s: {"entity": uid, "error_messages": [], "metrics": {  # noqa: E731
+        "cle_severity_score": str(s), "cle_lesion_percentage_per_lung": "0.120",
+        "pse_severity_score": "1", "pse_lesion_percentage_per_lung": "0.020"}}
+    args = Namespace(output_path=str(tmp_path))
+    merged = processor.write_results(args, [rec("b", 3), rec("a", 2), rec("b", 3)])  # wrap-around duplicate dropped
+    assert [r["entity"] for r in merged] == ["a", "b"]
+    assert json.load(open(tmp_path / "centrilobular-emphysema-score.json")) == {"score": 2, "percentage": 0.12}
+    assert json.load(open(tmp_path / "araseptal-emphysema-score.json")) == {"score": 1, "percentage": 0.02}
+    assert len(json.load(open(tmp_path / "results.json"))) == 2
+
+
+def test_cli_surface():
+    from dram_b200 import processor
+
+    args, extra = processor.build_parser().parse_known_args(
+        ["--scan_path", "/a", "--lobe_path", "/b", "--output_path", "/c", "--ngpus", "8", "--target_size", "64,96,128",
+         "--accelerator", "gpu", "--max_epochs", "3"])
+    assert (args.scan_path, args.lobe_path, args.output_path, args.ngpus) == ("/a", "/b", "/c", 8)
+    assert args.target_size == (64, 96, 128) and args.model_arch == "med3ddram" and args.batch_size == 2
+    assert extra == ["--accelerator", "gpu", "--max_epochs", "3"]
+    assert processor.build_parser().parse_args([]).target_size == (128, 224, 288)
+
+
+GLOO_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+import dram_b200
+from dram_b200.models import shard_indices
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = shard_indices(5, rank, world)
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)          # bench.py's max-over-ranks timing reduction
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"shards": gathered, "max": t.item()}))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    """World-size-2 run of the multi-GPU host logic on CPU (gloo): every volume lands on exactly one rank
+    (plus the wrap-around pad), and the max-over-ranks reduction bench.py times with works."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29653", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["shards"] == [[0, 2, 4], [1, 3, 0]] and res["max"] == 2.0
+    assert set(sum(res["shards"], [])) == set(range(5))

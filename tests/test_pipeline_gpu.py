@@ -1,0 +1,137 @@
+"""predict_step, the GPU inference transform and the processor CLI against the reference goldens / the oracle."""
+import json
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline_oracle as P
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _module(arch, sd, cuda, cls=False):
+    from dram_b200.models import ScanCLSLightningModule, ScanRegLightningModule
+
+    module = (ScanCLSLightningModule if cls else ScanRegLightningModule)(Namespace(model_arch=arch))
+    module.model.load_state_dict(sd)
+    return module.to(cuda).eval()
+
+
+def test_predict_step_matches_reference_golden(cuda, lib):
+    fix = torch.load(os.path.join(GOLDEN, "predict_step_med3ddram18.pt"))
+    dims, batch = tuple(fix["dims"]), fix["batch"]
+    sd = synthetic.make_state_dict(fix["arch"], seed=fix["weight_seed"], calib_dims=dims)
+    module = _module(fix["arch"], sd, cuda)
+    xs, ls, es = zip(*[synthetic.make_network_input(i, dims) for i in range(batch)])
+    b = {"image": torch.stack(xs).to(cuda), "lung_mask": torch.stack(ls).bool().to(cuda),
+         "ess_mask": torch.stack(es).bool().to(cuda), "crop_slice": torch.zeros(batch, 3, 2), "uid": ["a", "b"],
+         "original_size": torch.tensor([dims] * batch)}
+    out = module.predict_step(b, 0)
+    assert list(out.keys()) == fix["keys"]
+    for k in ("cle_dense_outs", "pse_dense_outs"):
+        got = out[k].cpu()
+        assert got.shape == fix[k].shape and got.dtype == torch.float32
+        assert (got - fix[k]).abs().max().item() <= 2e-2        # dRAM voxels, north-star tolerance
+        assert torch.equal(got == 0, fix[k] == 0)               # ess-mask support is bit-exact
+    for k in ("cle_precentages", "pse_precentages"):
+        assert torch.allclose(out[k].cpu(), fix[k], rtol=1e-2)
+    assert module._ratio_to_label(out["cle_precentages"], P.CLE_RATIO_MAP).cpu().tolist() == fix["cle_labels"].tolist()
+    assert module._ratio_to_label(out["pse_precentages"], P.PSE_RATIO_MAP).cpu().tolist() == fix["pse_labels"].tolist()
+    # quirk Q1: the reference divides by the lungs of the whole batch; the per-sample switch undoes it
+    module.per_sample_percentage = True
+    out_ps = module.predict_step(b, 0)
+    lung_sums = torch.stack(ls).float().view(batch, -1).sum(-1)
+    expect = out["cle_precentages"].cpu() * lung_sums.sum() / lung_sums
+    assert torch.allclose(out_ps["cle_precentages"].cpu(), expect, rtol=1e-5)
+
+
+def test_predict_step_from_hu_matches_oracle(cuda, lib):
+    arch, dims = "med3ddram18", (32, 48, 40)
+    sd = synthetic.make_state_dict(arch, seed=6, calib_dims=dims)
+    module = _module(arch, sd, cuda)
+    vols = [synthetic.make_volume(20 + i, dims) for i in range(2)]
+    hu = torch.stack([v[0] for v in vols])
+    lung = torch.stack([v[1] > 0 for v in vols])
+    ess = (hu < -910) & lung
+    ref = P.predict_step(sd, arch, {"image": torch.stack([P.standardize(P.intensity_window(h)) for h in hu]),
+                                    "lung_mask": lung, "ess_mask": ess})
+    out = module.predict_step_from_hu(hu.to(cuda), lung.to(cuda), ess.to(cuda))
+    for k in ("cle_dense_outs", "pse_dense_outs"):
+        assert (out[k].cpu() - ref[k]).abs().max().item() <= 2e-2
+    for k in ("cle_precentages", "pse_precentages"):
+        assert torch.allclose(out[k].cpu(), ref[k], rtol=1e-2)
+
+
+def test_cls_module_argmax_matches_oracle(cuda, lib):
+    from oracle import med3d_oracle as M
+
+    arch, dims = "med3d18", (32, 32, 32)
+    sd = synthetic.make_state_dict(arch, seed=0, calib_dims=dims)
+    module = _module(arch, sd, cuda, cls=True)
+    xs = torch.stack([synthetic.make_network_input(i, dims)[0] for i in range(2)])
+    _, ref = M.forward(sd, arch, xs.unsqueeze(1))
+    out = module.predict_step({"image": xs.to(cuda)}, 0)
+    assert torch.equal(out["cle_labels"].cpu(), ref[0].argmax(-1))
+    assert torch.equal(out["pse_labels"].cpu(), ref[1].argmax(-1))
+
+
+def test_gpu_transform_matches_reference_golden(cuda, lib):
+    from dram_b200.transforms import InferenceTransform
+
+    fix = torch.load(os.path.join(GOLDEN, "transforms.pt"))
+    ct, lobes = synthetic.make_volume(fix["scan_index"], tuple(fix["scan_dims"]))
+    sample = P.lung_crop_sample(ct.numpy(), lobes.numpy(), crop_border=5, uid="s3")
+    out = InferenceTransform(tuple(fix["target_size"]), device=cuda, keep_original_image=True)(sample)
+    assert out["lung_mask"].dtype == torch.bool and torch.equal(out["lung_mask"].cpu(), fix["lung_mask"])
+    assert torch.equal(out["ess_mask"].cpu(), fix["ess_mask"])
+    assert (out["image"].cpu() - fix["image"]).abs().max().item() < 2e-5
+    assert (out["original_image"].cpu() - fix["original_image"]).abs().max().item() < 2e-5
+    assert out["uid"] == "s3" and torch.equal(out["crop_slice"], torch.as_tensor(fix["crop_slice"]))
+
+
+def test_processor_end_to_end(cuda, lib, tmp_path):
+    """Three synthetic scans written as .mha -> processor.py surface -> heat-maps + JSON, against the oracle pipeline."""
+    from dram_b200 import mha_io, processor
+    from dram_b200.models import ScanRegLightningModule  # noqa: F401
+
+    arch, scan_dims, target = "med3ddram18", (40, 48, 56), (32, 40, 48)
+    scan_dir, lobe_dir, out_dir = tmp_path / "ct", tmp_path / "lobes", tmp_path / "out"
+    scan_dir.mkdir()
+    lobe_dir.mkdir()
+    vols = {}
+    for i in range(3):
+        ct, lobes = synthetic.make_volume(40 + i, scan_dims)
+        mha_io.write_mha(str(scan_dir / f"scan{i}.mha"), ct.numpy(), spacing=(1.0, 1.0, 1.0), origin=(1.0, 2.0, 3.0))
+        mha_io.write_mha(str(lobe_dir / f"scan{i}.mha"), lobes.numpy(), spacing=(1.0, 1.0, 1.0), origin=(1.0, 2.0, 3.0))
+        vols[f"scan{i}"] = (ct, lobes)
+    sd = synthetic.make_state_dict(arch, seed=7, calib_dims=target, prefix="model.")
+    ckpt = tmp_path / "best.ckpt"
+    # a >4 KiB file: anything smaller is treated as a Git-LFS pointer
+    torch.save({"state_dict": sd}, ckpt)
+    argv = ["--scan_path", str(scan_dir), "--lobe_path", str(lobe_dir), "--output_path", str(out_dir),
+            "--model_arch", arch, "--target_size", "32,40,48", "--batch_size", "1", "--ckpt_path", str(ckpt)]
+    records = processor.run_testing_job(argv)
+    assert [r["entity"] for r in records] == ["scan0", "scan1", "scan2"]
+    plain = {k[len("model."):]: v for k, v in sd.items()}
+    for uid, (ct, lobes) in vols.items():
+        sample = P.inference_transform(P.lung_crop_sample(ct.numpy(), lobes.numpy(), crop_border=5, uid=uid), target)
+        ref = P.predict_step(plain, arch, {k: (v[None] if isinstance(v, torch.Tensor) else v) for k, v in sample.items()
+                                           if k in ("image", "lung_mask", "ess_mask")})
+        rec = [r for r in records if r["entity"] == uid][0]["metrics"]
+        assert abs(float(rec["cle_lesion_percentage_per_lung"]) - ref["cle_precentages"][0].item()) <= 1.5e-3
+        assert int(rec["cle_severity_score"]) == P.ratio_to_label(ref["cle_precentages"][0].item(), P.CLE_RATIO_MAP)
+        assert int(rec["pse_severity_score"]) == P.ratio_to_label(ref["pse_precentages"][0].item(), P.PSE_RATIO_MAP)
+        heat, meta = mha_io.read_mha(str(out_dir / "images" / "centrilobular-emphysema-heatmap" / f"{uid}.mha"))
+        expect = P.postprocess_scan(ref["cle_dense_outs"][0], sample["crop_slice"], sample["original_size"])
+        assert heat.dtype == np.uint8 and heat.shape == tuple(scan_dims)
+        diff = np.abs(heat.astype(np.int32) - expect.astype(np.int32))
+        assert diff.max() <= 6, diff.max()          # 2e-2 of the [0,1] range = 5.1 grey levels (+1 for truncation)
+        assert meta["origin"] == (1.0, 2.0, 3.0)
+    first = json.load(open(out_dir / "centrilobular-emphysema-score.json"))
+    assert first["score"] == int(records[0]["metrics"]["cle_severity_score"])
+    assert os.path.isfile(out_dir / "araseptal-emphysema-score.json") and os.path.isfile(out_dir / "results.json")
