@@ -113,25 +113,40 @@ class ClockSampler:
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu_index, self.proc = gpu_index, None
+        self.gpu_index, self.proc, self.path = gpu_index, None, None
 
     def start(self):
+        import tempfile
+
         try:
+            fd, self.path = tempfile.mkstemp(prefix="dram_clocks_", suffix=".csv")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def mark(self):
+        """Number of samples taken so far (samples before the mark belong to the warm-up)."""
+        try:
+            with open(self.path) as f:
+                return sum(1 for _ in f)
+        except (OSError, TypeError):
+            return 0
+
+    def stop(self, skip=0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
+        with open(self.path) as f:
+            lines = f.read().strip().splitlines()
+        os.remove(self.path)
+        out = "\n".join(lines[skip:] if len(lines) > skip else lines)
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
@@ -268,7 +283,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
     ap.add_argument("--size", type=int, default=256)
@@ -293,14 +308,15 @@ def main():
         return module.predict_step_from_hu(hu, lungs, ess)
 
     # ---- device-resident throughput ----------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~0.5 s to produce its first sample: start it before the warm-up
     for _ in range(args.warmup):
         out = step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     barrier(world)
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
+    first_sample = sampler.mark() if rank == 0 else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -309,7 +325,7 @@ def main():
     torch.cuda.synchronize()
     barrier(world)
     ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(skip=first_sample) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
     launches_per_step = eng.launches_per_run() + 3 * B + 2  # K8: 3 kernels per volume; K7: kernel + finalize
