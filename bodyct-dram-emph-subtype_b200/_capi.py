@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdram_b200.so")
 DRAM_OK = 0
 DRAM_DTYPE_BF16 = 0
 DRAM_DTYPE_F16 = 1
+CONV_ALGO = {"auto": 0, "tiles": 1, "planes": 2}
 
 
 class ConvDesc(C.Structure):
@@ -34,6 +35,7 @@ class ConvDesc(C.Structure):
         ("store_out", C.c_int32),
         ("tw", C.c_int32), ("th", C.c_int32), ("td", C.c_int32),
         ("dtype", C.c_int32),
+        ("algo", C.c_int32),
     ]
 
 

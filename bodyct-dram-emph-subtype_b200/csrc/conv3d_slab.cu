@@ -1,0 +1,354 @@
+// K1, plane-ring variant — 3x3x3 / stride 1 / dilation 1 / pad 1 convolutions with Cout of 32 or 64
+// (layer1, the whole decoder: 61 % of the round-1 step time).
+//
+// Why: with one TMA box per (tap, chunk) every 128-clock MMA chunk ingests a 16 KiB activation tile and an
+// 8 KiB weight tile, ~190 B/clk/SM against the ~36 B/clk/SM the L2->SM fabric sustains
+// (profiles/conv_ncu_r1.md): the tensor pipe idles 80 % of the time.  Here
+//   * the CTA owns a column of the volume, 8 (W) x 16 (H) voxels wide, and marches along D;
+//   * every input plane of the column (10 x 18 voxels with halo, 64 channels = 23 KiB) is fetched ONCE by
+//     one TMA box into an 8-slot shared-memory ring; zero padding = TMA out-of-bounds fill;
+//   * an output tile is one 8 x 16 slab (128 voxels); its A operand for tap (kd,kh,kw) is the plane
+//     d+kd-1 viewed through a UMMA descriptor whose start address is shifted by (kh*10+kw) rows and whose
+//     8-row-group stride (SBO) is the plane pitch 10*128 B — no data is moved per tap;
+//   * four consecutive output planes accumulate side by side in TMEM (two sets of 4 x N columns for
+//     double buffering), so each 8 KiB weight tile (one TMA box) feeds 4 x 4 MMAs.
+// Operand ingest per 128-clock chunk drops from 24 KiB to ~3.3 KiB.
+//
+// Roles (224 threads): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 lane 0 MMA issuer (warp 5
+// owns TMEM), warp 6 lane 0 weight producer.  Work items = (column, group of 4 planes); every CTA takes a
+// contiguous range of items (D fastest), so consecutive groups of a column reuse two resident planes.
+#include "conv_plan.h"
+
+namespace dram {
+
+static constexpr int SL_W = 8, SL_H = 16, SL_GROUP = 4;      // slab = 8 x 16 voxels, 4 planes per item
+static constexpr int PL_W = SL_W + 2, PL_H = SL_H + 2;       // input plane with halo
+static constexpr int PLANE_BYTES = PL_W * PL_H * 128;        // 23040
+static constexpr int PLANE_PITCH = 23 * 1024;                // slot pitch, 1 KiB aligned for SWIZZLE_128B
+static constexpr int RING = 8;
+static constexpr int B_STAGES = 4;
+static constexpr int SL_THREADS = 224;
+static constexpr int SL_A_WARP = 4, SL_MMA_WARP = 5, SL_B_WARP = 6;
+static constexpr int SL_BLOCK_K = 64;
+
+template <int BLOCK_N>
+struct SlabCfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  static constexpr int TMEM_COLS = 2 * SL_GROUP * BLOCK_N;  // 512 (N=64) / 256 (N=32)
+  static constexpr int SMEM_BYTES = 1024 + RING * PLANE_PITCH + B_STAGES * B_STAGE_BYTES + 256;
+};
+
+struct SlabItem {
+  int sample, w0, h0, q0, g;
+};
+__device__ __forceinline__ SlabItem decode_item(const SlabParams &p, int item) {
+  SlabItem it;
+  const int col = item / p.groups_d;
+  it.g = item - col * p.groups_d;
+  it.q0 = it.g * SL_GROUP;
+  const int per_sample = p.cols_w * p.cols_h;
+  it.sample = col / per_sample;
+  const int r = col - it.sample * per_sample;
+  const int ih = r / p.cols_w;
+  it.w0 = (r - ih * p.cols_w) * SL_W;
+  it.h0 = ih * SL_H;
+  return it;
+}
+
+// K-major SWIZZLE_128B descriptor with an arbitrary (16-byte aligned) start and 8-row-group stride.
+__device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, int base_offset_mode) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_offset_mode) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ SlabParams p) {
+  using Cfg = SlabCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_base = smem_base + RING * PLANE_PITCH;
+  const uint32_t bar_base = b_base + B_STAGES * Cfg::B_STAGE_BYTES;
+  auto plane_addr = [&](int s) { return smem_base + (uint32_t)s * PLANE_PITCH; };
+  auto plane_full = [&](int s) { return bar_base + 8u * s; };
+  auto plane_empty = [&](int s) { return bar_base + 8u * (RING + s); };
+  auto b_addr = [&](int s) { return b_base + (uint32_t)s * Cfg::B_STAGE_BYTES; };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * RING + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * RING + B_STAGES + s); };
+  auto tmem_full = [&](int a) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + a); };
+  auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * RING + 2 * B_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(plane_full(s), 1);
+      mbar_init(plane_empty(s), 1);
+    }
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == SL_MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == SL_A_WARP && lane == 0) {
+    prefetch_tensormap(&map_a1);
+    prefetch_tensormap(&map_a2);
+  }
+  if (warp == SL_B_WARP && lane == 0) prefetch_tensormap(&map_w);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // contiguous, balanced range of work items for this CTA
+  const int item_begin = (int)(((long long)blockIdx.x * p.items_total) / gridDim.x);
+  const int item_end = (int)(((long long)(blockIdx.x + 1) * p.items_total) / gridDim.x);
+  const bool single_chunk = p.chunks_total == 1;
+
+  if (warp == SL_A_WARP) {
+    if (lane == 0) {
+      unsigned seq_end = 0;
+      for (int item = item_begin; item < item_end; ++item) {
+        const SlabItem it = decode_item(p, item);
+        for (int c = 0; c < p.chunks_total; ++c) {
+          const bool reuse = single_chunk && item > item_begin && it.g > 0;
+          const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
+          for (int j = reuse ? 2 : 0; j < SL_GROUP + 2; ++j) {
+            const unsigned seq = seq_base + j;
+            const int slot = seq % RING;
+            mbar_wait(plane_empty(slot), ((seq / RING) & 1u) ^ 1u);
+            mbar_expect_tx(plane_full(slot), PLANE_BYTES);
+            if (c < p.chunks1)
+              tma_load_5d(plane_addr(slot), &map_a1, plane_full(slot), c * SL_BLOCK_K, it.w0 - 1, it.h0 - 1,
+                          it.q0 - 1 + j, it.sample);
+            else
+              tma_load_5d(plane_addr(slot), &map_a2, plane_full(slot), (c - p.chunks1) * SL_BLOCK_K, it.w0 - 1,
+                          it.h0 - 1, it.q0 - 1 + j, it.sample);
+          }
+          seq_end = seq_base + SL_GROUP + 2;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == SL_B_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item_begin; item < item_end; ++item) {
+        for (int c = 0; c < p.chunks_total; ++c) {
+          for (int tap = 0; tap < 27; ++tap) {
+            mbar_wait(b_empty(stage), phase ^ 1u);
+            mbar_expect_tx(b_full(stage), Cfg::B_STAGE_BYTES);
+            tma_load_2d(b_addr(stage), &map_w, b_full(stage), (tap * p.chunks_total + c) * SL_BLOCK_K, 0);
+            if (++stage == B_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == SL_MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_16bit(128, BLOCK_N, p.epi.is_f16);
+      int stage = 0;
+      uint32_t phase = 0;
+      unsigned seq_end = 0;
+      int buf = 0;
+      uint32_t buf_phase = 0;
+      for (int item = item_begin; item < item_end; ++item) {
+        const SlabItem it = decode_item(p, item);
+        mbar_wait(tmem_empty(buf), buf_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t tmem_d0 = tmem_base + (uint32_t)(buf * SL_GROUP * BLOCK_N);
+        for (int c = 0; c < p.chunks_total; ++c) {
+          const bool reuse = single_chunk && item > item_begin && it.g > 0;
+          const bool next_reuse = single_chunk && (item + 1 < item_end) && (it.g + 1 < p.groups_d);
+          const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
+          seq_end = seq_base + SL_GROUP + 2;
+          auto wait_plane = [&](int j) {
+            const unsigned seq = seq_base + j;
+            mbar_wait(plane_full(seq % RING), (seq / RING) & 1u);
+          };
+          auto free_plane = [&](int j) { umma_commit(plane_empty((seq_base + j) % RING)); };
+          for (int kd = 0; kd < 3; ++kd) {
+            if (kd == 0) {
+              for (int j = 0; j < SL_GROUP; ++j) wait_plane(j);
+            } else {
+              wait_plane(SL_GROUP - 1 + kd);
+            }
+            tcgen05_fence_after();
+            for (int kh = 0; kh < 3; ++kh) {
+              for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(b_full(stage), phase);
+                tcgen05_fence_after();
+                const uint64_t db = make_sw128_desc(b_addr(stage));
+                const uint32_t row_off = (uint32_t)(kh * PL_W + kw) * 128u;
+#pragma unroll
+                for (int t = 0; t < SL_GROUP; ++t) {
+                  const unsigned seq = seq_base + t + kd;
+                  const uint64_t da = make_sw128_desc_sbo(plane_addr(seq % RING) + row_off, PL_W * 128,
+                                                          p.desc_base_offset_mode);
+                  const uint32_t acc = (c > 0 || kd > 0 || kh > 0 || kw > 0) ? 1u : 0u;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_d0 + (uint32_t)(t * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (k > 0) ? 1u : acc);
+                }
+                umma_commit(b_empty(stage));
+                if (++stage == B_STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+            // plane j is last read by the kd = j block of tile 0 (j = 0, 1); planes 2..5 live to the end
+            if (kd < 2) free_plane(kd);
+          }
+          free_plane(2);
+          free_plane(3);
+          if (!next_reuse) {
+            free_plane(4);
+            free_plane(5);
+          }
+        }
+        umma_commit(tmem_full(buf));
+        if (++buf == 2) {
+          buf = 0;
+          buf_phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue warps 0..3 -------------------------------
+    const int row = warp * 32 + lane;
+    const int lw = row & (SL_W - 1);
+    const int lh = row >> 3;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const SlabItem it = decode_item(p, item);
+      const int oh = it.h0 + lh, ow = it.w0 + lw;
+      mbar_wait(tmem_full(buf), buf_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < SL_GROUP; ++t) {
+        const int od = it.q0 + t;
+        const bool valid = (od < p.D) && (oh < p.H) && (ow < p.W);
+        const uint16_t *res_row = residual_row(p.epi, valid, it.sample, od, oh, ow);
+        const uint32_t taddr = tmem_base + (uint32_t)((buf * SL_GROUP + t) * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          tmem_wait_ld();
+          if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res_row);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty(buf));
+      if (++buf == 2) {
+        buf = 0;
+        buf_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == SL_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------
+int slab_plan_supported(const dram_conv_desc *d) {
+  return d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->dd == 1 &&
+         d->dh == 1 && d->dw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && (d->cout == 32 || d->cout == 64);
+}
+
+template <int BN>
+static int slab_set_attr() {
+  return check_cuda(cudaFuncSetAttribute(conv3d_slab_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SlabCfg<BN>::SMEM_BYTES),
+                    "cudaFuncSetAttribute(conv3d_slab_kernel)");
+}
+
+int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1, const void *src2,
+                   const void *weight, const EpiParams &epi) {
+  pl->kind = 1;
+  SlabParams &sp = pl->sp;
+  sp.n = d->n; sp.D = d->di; sp.H = d->hi; sp.W = d->wi;
+  sp.cols_w = ceil_div(d->wi, SL_W);
+  sp.cols_h = ceil_div(d->hi, SL_H);
+  sp.groups_d = ceil_div(d->di, SL_GROUP);
+  const int64_t items = (int64_t)d->n * sp.cols_w * sp.cols_h * sp.groups_d;
+  if (items > 0x7fffffffLL) {
+    set_error("conv3d(planes): too many work items");
+    return DRAM_E_ARG;
+  }
+  sp.items_total = (int)items;
+  sp.chunks1 = d->c1 / SL_BLOCK_K;
+  sp.chunks_total = (d->c1 + d->c2) / SL_BLOCK_K;
+  const char *knob = getenv("DRAM_B200_DESC_BASE_OFFSET");
+  sp.desc_base_offset_mode = knob ? atoi(knob) : 0;
+  sp.epi = epi;
+  pl->block_n = d->cout;
+  pl->stages = RING;
+  pl->m_tiles = sp.items_total * SL_GROUP;
+  pl->n_tiles = 1;
+  const int64_t ktot = 27LL * (d->c1 + d->c2);
+  int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, SL_BLOCK_K, PL_W, PL_H, 1, 1, 1, 1,
+                          epi.is_f16);
+  if (rc == DRAM_OK) {
+    if (d->c2 > 0)
+      rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, SL_BLOCK_K, PL_W, PL_H, 1, 1, 1, 1,
+                          epi.is_f16);
+    else
+      pl->map_a2 = pl->map_a1;
+  }
+  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, d->cout, epi.is_f16);
+  if (rc == DRAM_OK) {
+    if (d->cout == 64) {
+      pl->smem_bytes = SlabCfg<64>::SMEM_BYTES;
+      rc = slab_set_attr<64>();
+    } else {
+      pl->smem_bytes = SlabCfg<32>::SMEM_BYTES;
+      rc = slab_set_attr<32>();
+    }
+  }
+  return rc;
+}
+
+int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
+  if (pl->sp.items_total < ctas) ctas = pl->sp.items_total;
+  dim3 grid(ctas), block(SL_THREADS);
+  if (pl->block_n == 64)
+    conv3d_slab_kernel<64><<<grid, block, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+  else
+    conv3d_slab_kernel<32><<<grid, block, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+  DRAM_CHECK_LAUNCH("conv3d_slab_kernel launch");
+  return DRAM_OK;
+}
+
+}  // namespace dram

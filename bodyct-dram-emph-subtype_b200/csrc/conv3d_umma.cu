@@ -20,9 +20,8 @@
 // producer, warp 5 lane 0 MMA issuer (warp 5 also owns the TMEM allocation).
 // Persistent: grid <= #SMs, tile = blockIdx.x + i * gridDim.x, n-tile fastest.
 // Filter taps whose whole brick lies in the zero padding are skipped by producer and issuer.
-#include <cuda.h>
-
-#include "common.h"
+#include "umma_common.cuh"
+#include "conv_plan.h"
 
 namespace dram {
 
@@ -43,173 +42,6 @@ struct ConvCfg {
   // 1 KiB alignment slack + stages + barriers
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
 };
-
-struct ConvKParams {
-  int n, Do, Ho, Wo, Di, Hi, Wi;
-  int cout;
-  int tw, th, td;              // tile extents (powers of two, product 128)
-  int tw_log2, th_log2;        // row -> (w,h,d) decode
-  int tiles_w, tiles_h, tiles_d, tiles_per_sample, num_n_tiles, total_tiles;
-  int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
-  int chunks1, chunks_total;   // 64-channel chunks of source 1 / of both sources
-  int relu;
-  int is_f16;                  // operand/activation storage: 0 = bf16, 1 = fp16 (same 2-byte layout)
-  const float *bias;
-  const float *scale;          // optional fp32 per-channel multiplier applied to the accumulator
-  uint16_t *out;
-  const uint16_t *res;
-  int res_c, res_stride, res_d, res_h, res_w;
-  int n_heads, head_ch0, head_ch1, head_sigmoid, store_out;
-  const float *head_w;
-  const float *head_b;
-  float *head_out0;
-  float *head_out1;
-};
-
-// ----------------------------------------------------------------------------------------
-// PTX wrappers
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Waits for the phase with the given parity.  A wait longer than ~4 s of SM clocks is a
-// protocol bug: trap instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > 8000000000LL) {
-      printf("dram_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
-             blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by one thread for the CTA.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Arrives on the mbarrier once every tcgen05.mma issued so far by this thread has retired.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
-        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4 = 8 rows * 128 B,
-// [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format (0 = F16, 1 = BF16) at bits 7 and
-// 10, K-major A and B, n_dim = N>>3 at bit 17, m_dim = M>>4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc_16bit(int m, int n, int is_f16) {
-  return (1u << 4) | ((is_f16 ? 0u : 1u) << 7) | ((is_f16 ? 0u : 1u) << 10) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-// Two packed 16-bit activations <-> fp32, for either storage type.
-__device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
-  if (is_f16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
-  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&u);
-  return make_float2(__low2float(h), __high2float(h));
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
-  if (is_f16) {
-    // saturate instead of overflowing to inf
-    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
-    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-  }
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t *>(&h);
-}
 
 struct TileCoord {
   int n0, sample, d0, h0, w0;
@@ -320,7 +152,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
     __syncwarp();
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_16bit(BLOCK_M, BLOCK_N, p.is_f16);
+      const uint32_t idesc = make_idesc_16bit(BLOCK_M, BLOCK_N, p.epi.is_f16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -378,13 +210,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int od = t.d0 + ld, oh = t.h0 + lh, ow = t.w0 + lw;
       const bool valid = (od < p.Do) && (oh < p.Ho) && (ow < p.Wo);
-      const size_t vox = (((size_t)t.sample * p.Do + od) * p.Ho + oh) * p.Wo + ow;
-      const uint16_t *res_row = nullptr;
-      if (p.res != nullptr && valid) {
-        const size_t rvox = (((size_t)t.sample * p.res_d + (size_t)od * p.res_stride) * p.res_h +
-                             (size_t)oh * p.res_stride) * p.res_w + (size_t)ow * p.res_stride;
-        res_row = p.res + rvox * p.res_c;
-      }
+      const uint16_t *res_row = residual_row(p.epi, valid, t.sample, od, oh, ow);
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
@@ -393,82 +219,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
         tmem_wait_ld();
-        if (valid) {
-          const int cg = t.n0 + c0;  // first global output channel of this 32-column group
-          float y[32];
-          const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + cg);
-          if (p.scale != nullptr) {
-            const float4 *s4 = reinterpret_cast<const float4 *>(p.scale + cg);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j), sc = __ldg(s4 + j);
-              y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, b.x);
-              y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, b.y);
-              y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, b.z);
-              y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, b.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-              y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-              y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-              y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
-            }
-          }
-          if (res_row != nullptr && cg < p.res_c) {
-            const uint4 *r4 = reinterpret_cast<const uint4 *>(res_row + cg);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 r = __ldg(r4 + j);
-              const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 f = unpack2(w[q], p.is_f16);
-                y[8 * j + 2 * q + 0] += f.x;
-                y[8 * j + 2 * q + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
-          }
-          if (p.store_out) {
-            uint4 *o4 = reinterpret_cast<uint4 *>(p.out + vox * p.cout + cg);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.is_f16);
-              o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
-          if (BLOCK_N == 32 && p.n_heads > 0) {
-            // 1x1x1 heads on the fp32 post-ReLU vector; dense maps are fp32 NCDHW.
-            const size_t plane = (size_t)p.Do * p.Ho * p.Wo;
-            const size_t sp = ((size_t)od * p.Ho + oh) * p.Wo + ow;
-            const int total = p.head_ch0 + p.head_ch1;
-            for (int hc = 0; hc < total; ++hc) {
-              const float4 *w4 = reinterpret_cast<const float4 *>(p.head_w + hc * 32);
-              float s = __ldg(p.head_b + hc);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w = __ldg(w4 + j);
-                s = fmaf(w.x, y[4 * j + 0], s);
-                s = fmaf(w.y, y[4 * j + 1], s);
-                s = fmaf(w.z, y[4 * j + 2], s);
-                s = fmaf(w.w, y[4 * j + 3], s);
-              }
-              if (p.head_sigmoid) s = 1.0f / (1.0f + expf(-s));
-              if (hc < p.head_ch0)
-                p.head_out0[((size_t)t.sample * p.head_ch0 + hc) * plane + sp] = s;
-              else
-                p.head_out1[((size_t)t.sample * p.head_ch1 + (hc - p.head_ch0)) * plane + sp] = s;
-            }
-          }
-        }
+        if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, t.n0 + c0, t.sample, od, oh, ow, res_row);
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty_bar(acc));  // 128 arrivals hand the accumulator back to the issuer
@@ -509,8 +260,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c,
-                          int bw, int bh, int bd, int sw, int sh, int sd, int is_f16) {
+// NDHWC activation tensor as a 5-D map (C, W, H, D, N); box = box_c channels x bw x bh x bd voxels.
+int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c, int box_c, int bw,
+                   int bh, int bd, int sw, int sh, int sd, int is_f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -520,13 +272,13 @@ static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int 
   cuuint64_t gstr[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
                         (cuuint64_t)d * h * w * c * 2};
   // With a traversal stride s the box spans (t-1)*s+1 input elements and lands t of them.
-  cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)((bw - 1) * sw + 1),
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)((bw - 1) * sw + 1),
                        (cuuint32_t)((bh - 1) * sh + 1), (cuuint32_t)((bd - 1) * sd + 1), 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
   CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
-                   const_cast<void *>(base), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%dx%d box %dx%dx%d stride %d,%d,%d) -> %d",
               n, d, h, w, c, bw, bh, bd, sw, sh, sd, (int)r);
@@ -535,8 +287,7 @@ static int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int 
   return DRAM_OK;
 }
 
-static int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64_t ktot,
-                             int block_n, int is_f16) {
+int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64_t ktot, int block_n, int is_f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -547,9 +298,9 @@ static int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64
   cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void *>(base), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(weight %d x %lld, box_n %d) -> %d", cout, (long long)ktot,
               block_n, (int)r);
@@ -567,17 +318,13 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 static int conv_out(int in, int k, int s, int d, int p) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
 
-}  // namespace dram
+// plane-ring kernel (conv3d_slab.cu)
+int slab_plan_supported(const dram_conv_desc *d);
+int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1, const void *src2,
+                   const void *weight, const EpiParams &epi);
+int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st);
 
-struct dram_conv_plan {
-  CUtensorMap map_a1, map_a2, map_w;
-  dram::ConvKParams p;
-  int block_n;
-  int stages;
-  size_t smem_bytes;
-  int64_t flops;
-  int m_tiles;
-};
+}  // namespace dram
 
 using namespace dram;
 
@@ -619,6 +366,7 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   DRAM_REQUIRE(d->dd >= 1 && d->dh >= 1 && d->dw >= 1, "conv3d: dilation must be >= 1");
   DRAM_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv3d: padding must be >= 0");
   DRAM_REQUIRE(d->dtype == DRAM_DTYPE_BF16 || d->dtype == DRAM_DTYPE_F16, "conv3d: dtype must be bf16 (0) or fp16 (1)");
+  DRAM_REQUIRE(d->algo >= DRAM_CONV_ALGO_AUTO && d->algo <= DRAM_CONV_ALGO_PLANES, "conv3d: bad algo %d", d->algo);
   DRAM_REQUIRE(d->store_out == 0 || out != nullptr, "conv3d: out is required when store_out != 0");
   DRAM_REQUIRE(d->store_out != 0 || d->n_heads > 0, "conv3d: nothing to write");
 
@@ -652,6 +400,52 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
                  d->res_d, d->res_h, d->res_w, Do, Ho, Wo, d->res_stride);
   }
 
+  EpiParams epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.Do = Do; epi.Ho = Ho; epi.Wo = Wo;
+  epi.cout = d->cout;
+  epi.relu = d->relu;
+  epi.is_f16 = d->dtype == DRAM_DTYPE_F16;
+  epi.bias = bias;
+  epi.scale = scale;
+  epi.out = reinterpret_cast<uint16_t *>(out);
+  epi.res = d->res_c > 0 ? reinterpret_cast<const uint16_t *>(residual) : nullptr;
+  epi.res_c = d->res_c; epi.res_stride = d->res_stride > 0 ? d->res_stride : 1;
+  epi.res_d = d->res_d; epi.res_h = d->res_h; epi.res_w = d->res_w;
+  epi.n_heads = d->n_heads;
+  epi.head_ch0 = d->n_heads > 0 ? d->head_ch[0] : 0;
+  epi.head_ch1 = d->n_heads > 1 ? d->head_ch[1] : 0;
+  epi.head_sigmoid = d->head_sigmoid;
+  epi.store_out = d->store_out;
+  epi.head_w = head_w; epi.head_b = head_b; epi.head_out0 = head_out0; epi.head_out1 = head_out1;
+
+  const int taps = d->kd * d->kh * d->kw;
+  const int64_t ktot = (int64_t)taps * (d->c1 + d->c2);
+
+  dram_conv_plan *pl = new dram_conv_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->flops = 2LL * d->n * Do * Ho * Wo * (int64_t)d->cout * ktot;
+  pl->block_n = block_n;
+
+  // ---- plane-ring kernel for 3x3x3 / stride 1 / dilation 1 / Cout <= 64 ----------------------
+  const bool want_planes = d->algo == DRAM_CONV_ALGO_PLANES ||
+                           (d->algo == DRAM_CONV_ALGO_AUTO && d->tw == 0 && slab_plan_supported(d));
+  if (want_planes) {
+    if (!slab_plan_supported(d)) {
+      delete pl;
+      set_error("conv3d: DRAM_CONV_ALGO_PLANES needs a 3x3x3 stride-1 dilation-1 pad-1 filter and cout of 32 or 64");
+      return DRAM_E_ARG;
+    }
+    int rc = slab_plan_fill(pl, d, src1, src2, weight, epi);
+    if (rc != DRAM_OK) {
+      delete pl;
+      return rc;
+    }
+    *plan = pl;
+    return DRAM_OK;
+  }
+
+  // ---- per-tap TMA tile kernel ------------------------------------------------------------------
   // Tile shape: caller's choice or the candidate with the fewest tiles.
   int tw = d->tw, th = d->th, td = d->td;
   if (tw == 0 || th == 0 || td == 0) {
@@ -669,16 +463,20 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
       }
     }
   }
-  DRAM_REQUIRE(is_pow2(tw) && is_pow2(th) && is_pow2(td) && tw * th * td == BLOCK_M,
-               "conv3d: tile %dx%dx%d must be powers of two with product 128", tw, th, td);
-  DRAM_REQUIRE((tw - 1) * d->sw + 1 <= 256 && (th - 1) * d->sh + 1 <= 256 && (td - 1) * d->sd + 1 <= 256,
-               "conv3d: TMA box too large for tile/stride");
+  if (!(is_pow2(tw) && is_pow2(th) && is_pow2(td) && tw * th * td == BLOCK_M)) {
+    delete pl;
+    set_error("conv3d: tile %dx%dx%d must be powers of two with product 128", tw, th, td);
+    return DRAM_E_ARG;
+  }
+  if (!((tw - 1) * d->sw + 1 <= 256 && (th - 1) * d->sh + 1 <= 256 && (td - 1) * d->sd + 1 <= 256)) {
+    delete pl;
+    set_error("conv3d: TMA box too large for tile/stride");
+    return DRAM_E_ARG;
+  }
 
-  dram_conv_plan *pl = new dram_conv_plan();
-  memset(pl, 0, sizeof(*pl));
+  pl->kind = 0;
   ConvKParams &p = pl->p;
   p.n = d->n; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.Di = d->di; p.Hi = d->hi; p.Wi = d->wi;
-  p.cout = d->cout;
   p.tw = tw; p.th = th; p.td = td; p.tw_log2 = ilog2(tw); p.th_log2 = ilog2(th);
   p.tiles_w = ceil_div(Wo, tw); p.tiles_h = ceil_div(Ho, th); p.tiles_d = ceil_div(Do, td);
   p.tiles_per_sample = p.tiles_w * p.tiles_h * p.tiles_d;
@@ -694,37 +492,20 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   p.dd = d->dd; p.dh = d->dh; p.dw = d->dw; p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   p.chunks1 = d->c1 / BLOCK_K;
   p.chunks_total = (d->c1 + d->c2) / BLOCK_K;
-  p.relu = d->relu;
-  p.is_f16 = d->dtype == DRAM_DTYPE_F16;
-  p.bias = bias;
-  p.scale = scale;
-  p.out = reinterpret_cast<uint16_t *>(out);
-  p.res = d->res_c > 0 ? reinterpret_cast<const uint16_t *>(residual) : nullptr;
-  p.res_c = d->res_c; p.res_stride = d->res_stride > 0 ? d->res_stride : 1;
-  p.res_d = d->res_d; p.res_h = d->res_h; p.res_w = d->res_w;
-  p.n_heads = d->n_heads;
-  p.head_ch0 = d->n_heads > 0 ? d->head_ch[0] : 0;
-  p.head_ch1 = d->n_heads > 1 ? d->head_ch[1] : 0;
-  p.head_sigmoid = d->head_sigmoid;
-  p.store_out = d->store_out;
-  p.head_w = head_w; p.head_b = head_b; p.head_out0 = head_out0; p.head_out1 = head_out1;
-
-  const int taps = d->kd * d->kh * d->kw;
-  const int64_t ktot = (int64_t)taps * (d->c1 + d->c2);
-  pl->block_n = block_n;
+  p.epi = epi;
   pl->m_tiles = p.tiles_per_sample * d->n;
-  pl->flops = 2LL * d->n * Do * Ho * Wo * (int64_t)d->cout * ktot;
+  pl->n_tiles = p.num_n_tiles;
 
-  int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, tw, th, td, d->sw,
-                          d->sh, d->sd, p.is_f16);
+  int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, BLOCK_K, tw, th, td, d->sw,
+                          d->sh, d->sd, epi.is_f16);
   if (rc == DRAM_OK) {
     if (d->c2 > 0)
-      rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, tw, th, td, d->sw,
-                          d->sh, d->sd, p.is_f16);
+      rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, BLOCK_K, tw, th, td, d->sw,
+                          d->sh, d->sd, epi.is_f16);
     else
       pl->map_a2 = pl->map_a1;
   }
-  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, p.is_f16);
+  if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, epi.is_f16);
   if (rc == DRAM_OK) {
     switch (block_n) {
       case 32: pl->stages = ConvCfg<32>::STAGES; pl->smem_bytes = ConvCfg<32>::SMEM_BYTES; rc = set_smem_attr<32>(); break;
@@ -751,9 +532,9 @@ extern "C" int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops,
   DRAM_REQUIRE(plan, "dram_conv3d_plan_info: null plan");
   if (flops) *flops = plan->flops;
   if (m_tiles) *m_tiles = plan->m_tiles;
-  if (n_tiles) *n_tiles = plan->p.num_n_tiles;
+  if (n_tiles) *n_tiles = plan->n_tiles;
   if (block_n) *block_n = plan->block_n;
-  if (stages) *stages = plan->stages;
+  if (stages) *stages = plan->kind == 1 ? -plan->stages : plan->stages;  // negative: plane-ring kernel
   return DRAM_OK;
 }
 
@@ -761,8 +542,9 @@ extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, voi
   DRAM_REQUIRE(plan, "dram_conv3d_run: null plan");
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-  if (plan->p.total_tiles < ctas) ctas = plan->p.total_tiles;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (plan->kind == 1) return slab_plan_run(plan, ctas, st);
+  if (plan->p.total_tiles < ctas) ctas = plan->p.total_tiles;
   dim3 grid(ctas), block(NUM_THREADS);
   switch (plan->block_n) {
     case 32:

@@ -80,7 +80,7 @@ class Conv3dPlan:
 
     def __init__(self, x1, weight, bias, *, x2=None, scale=None, kernel=3, stride=1, dilation=1,
                  padding=None, relu=True, residual=None, res_stride=1, heads=None, store_out=True,
-                 out=None, tile=None):
+                 out=None, tile=None, algo="auto"):
         lib = _capi.load()
         _need16(x1, "conv3d x1", 5)
         adt = x1.dtype
@@ -114,6 +114,7 @@ class Conv3dPlan:
         d.pd, d.ph, d.pw = pad
         d.relu = 1 if relu else 0
         d.dtype = ACT_DTYPES[adt]
+        d.algo = _capi.CONV_ALGO[algo]
         if residual is not None:
             _need(residual, adt, "conv3d residual", 5)
             d.res_c = residual.shape[4]
@@ -171,7 +172,8 @@ class Conv3dPlan:
         check(lib.dram_conv3d_plan_info(handle, C.byref(flops), C.byref(mt), C.byref(nt), C.byref(bn),
                                         C.byref(st)), "dram_conv3d_plan_info")
         self.flops, self.m_tiles, self.n_tiles, self.block_n, self.stages = (
-            flops.value, mt.value, nt.value, bn.value, st.value)
+            flops.value, mt.value, nt.value, bn.value, abs(st.value))
+        self.algo = "planes" if st.value < 0 else "tiles"
         self.desc = d
 
     def run(self, max_ctas=0):

@@ -41,6 +41,15 @@ extern "C" {
 #define DRAM_DTYPE_BF16 0
 #define DRAM_DTYPE_F16 1
 
+/* K1 has two kernels behind one entry point:
+ *   TILES  - one TMA box per (filter tap, 64-channel chunk): any filter/stride/dilation, any Cout;
+ *   PLANES - 3x3x3 / stride 1 / dilation 1 / pad 1 with Cout 32 or 64: input planes stream once
+ *            through a shared-memory ring and the 27 taps read them as shifted UMMA views, each
+ *            weight tile feeding four accumulators (operand traffic /7 for the decoder layers). */
+#define DRAM_CONV_ALGO_AUTO 0
+#define DRAM_CONV_ALGO_TILES 1
+#define DRAM_CONV_ALGO_PLANES 2
+
 /* ---- library ---------------------------------------------------------- */
 int dram_version(void);
 /* Copies the calling thread's last error text (NUL terminated) into buf. */
@@ -90,6 +99,7 @@ typedef struct dram_conv_desc {
   /* picks the shape with the fewest tiles                                   */
   int32_t tw, th, td;
   int32_t dtype;       /* DRAM_DTYPE_BF16 or DRAM_DTYPE_F16: type of src/weight/residual/out */
+  int32_t algo;        /* DRAM_CONV_ALGO_*: AUTO picks PLANES when the shape allows it         */
 } dram_conv_desc;
 
 typedef struct dram_conv_plan dram_conv_plan; /* opaque: tensor maps + launch geometry */

@@ -32,7 +32,8 @@ def _close(got, ref, what):
 
 
 def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=None, res_stride=1,
-              heads=None, seed=0, tile=None, dtype=torch.bfloat16, normalize=False):
+              heads=None, seed=0, tile=None, dtype=torch.bfloat16, normalize=False, algo="auto", max_ctas=0,
+              expect_algo=None):
     from dram_b200 import ops
 
     global DT
@@ -76,8 +77,10 @@ def _run_conv(cuda, n, dims, c1, c2, cout, k, stride, dil, relu=True, residual=N
     plan = ops.Conv3dPlan(
         ops.to_ndhwc_16(x1.to(cuda), dtype), wp, bias.to(cuda), scale=mult,
         x2=None if x2 is None else ops.to_ndhwc_16(x2.to(cuda), dtype), kernel=k3, stride=stride, dilation=dil,
-        relu=relu, residual=res_t, res_stride=res_stride, heads=hk, tile=tile)
-    out = plan.run()
+        relu=relu, residual=res_t, res_stride=res_stride, heads=hk, tile=tile, algo=algo)
+    if expect_algo is not None:
+        assert plan.algo == expect_algo, (plan.algo, expect_algo)
+    out = plan.run(max_ctas)
     torch.cuda.synchronize()
     got = ops.to_ncdhw_f32(out).cpu()
     assert got.shape == ref.shape, (got.shape, ref.shape)
@@ -155,6 +158,39 @@ def test_conv_fp16_storage(cuda, lib):
     _run_conv(cuda, 1, (8, 16, 16), 128, 64, 64, 3, 1, 1, dtype=h)
     _run_conv(cuda, 1, (8, 16, 16), 64, 0, 32, 3, 1, 1, heads=((1, 1), True), dtype=h, normalize=True)
     _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 1, dtype=torch.bfloat16, normalize=True)
+
+
+PLANE_CASES = [
+    # n, dims, c1, c2, cout, kwargs
+    (1, (8, 16, 16), 64, 0, 64, {}),
+    (1, (10, 20, 12), 64, 0, 64, {"residual": 64}),                   # ragged: partial slabs and groups
+    (2, (12, 32, 24), 64, 0, 64, {"max_ctas": 3}),                    # several items per CTA: plane reuse, column changes
+    (1, (16, 16, 8), 64, 0, 64, {"max_ctas": 1, "residual": 64}),     # one CTA marches through everything
+    (1, (8, 16, 16), 128, 64, 64, {"max_ctas": 2}),                   # two sources, 3 K-chunks (no plane reuse)
+    (1, (9, 18, 10), 64, 64, 64, {}),
+    (1, (8, 16, 16), 64, 0, 32, {"heads": ((1, 1), True)}),           # us3 + regression heads
+    (2, (6, 16, 24), 64, 0, 32, {"heads": ((6, 3), False), "max_ctas": 2}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(PLANE_CASES)))
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conv_plane_ring_kernel(cuda, lib, case, dt):
+    """DRAM_CONV_ALGO_PLANES: same results as the reference conv for every shape family it serves."""
+    n, dims, c1, c2, cout, kw = PLANE_CASES[case]
+    _run_conv(cuda, n, dims, c1, c2, cout, 3, 1, 1, dtype=dt, algo="planes", expect_algo="planes", seed=11 + case,
+              normalize=(case % 2 == 0), **kw)
+
+
+def test_conv_algo_dispatch(cuda, lib):
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 1)                 # auto -> planes
+    assert p.algo == "planes"
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 1, algo="tiles")
+    assert p.algo == "tiles"
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 2)                 # dilation 2 -> tiles
+    assert p.algo == "tiles"
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 128, 3, 1, 1)                # cout 128 -> tiles
+    assert p.algo == "tiles"
 
 
 def test_conv_tile_shapes(cuda, lib):
