@@ -85,7 +85,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * RING + 2 * B_STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -114,6 +114,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
 
   // contiguous, balanced range of work items for this CTA
   const int item_begin = (int)(((long long)blockIdx.x * p.items_total) / gridDim.x);
@@ -165,7 +166,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     }
     __syncwarp();
   } else if (warp == SL_MMA_WARP) {
-    if (lane == 0) {
+    {  // the whole warp walks the loops (uniform control flow); one elected lane issues
       const uint32_t idesc = make_idesc_16bit(128, BLOCK_N, p.epi.is_f16);
       int stage = 0;
       uint32_t phase = 0;
@@ -186,7 +187,10 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             const unsigned seq = seq_base + j;
             mbar_wait(plane_full(seq % RING), (seq / RING) & 1u);
           };
-          auto free_plane = [&](int j) { umma_commit(plane_empty((seq_base + j) % RING)); };
+          auto free_plane = [&](int j) {
+            if (elect_one_sync()) umma_commit(plane_empty((seq_base + j) % RING));
+            __syncwarp();
+          };
           for (int kd = 0; kd < 3; ++kd) {
             if (kd == 0) {
               for (int j = 0; j < SL_GROUP; ++j) wait_plane(j);
@@ -200,18 +204,25 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
                 tcgen05_fence_after();
                 const uint64_t db = make_sw128_desc(b_addr(stage));
                 const uint32_t row_off = (uint32_t)(kh * PL_W + kw) * 128u;
+                // k outer, tile inner: consecutive MMAs target different accumulators, so the
+                // read-modify-write latency of one TMEM tile never serialises the tensor pipe
+                uint64_t da[SL_GROUP];
 #pragma unroll
-                for (int t = 0; t < SL_GROUP; ++t) {
-                  const unsigned seq = seq_base + t + kd;
-                  const uint64_t da = make_sw128_desc_sbo(plane_addr(seq % RING) + row_off, PL_W * 128,
-                                                          p.desc_base_offset_mode);
-                  const uint32_t acc = (c > 0 || kd > 0 || kh > 0 || kw > 0) ? 1u : 0u;
+                for (int t = 0; t < SL_GROUP; ++t)
+                  da[t] = make_sw128_desc_sbo(plane_addr((seq_base + t + kd) % RING) + row_off, PL_W * 128,
+                                              p.desc_base_offset_mode);
+                const uint32_t acc = (c > 0 || kd > 0 || kh > 0 || kw > 0) ? 1u : 0u;
+                if (elect_one_sync()) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_d0 + (uint32_t)(t * BLOCK_N), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (k > 0) ? 1u : acc);
+                  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int t = 0; t < SL_GROUP; ++t)
+                      umma_bf16(tmem_d0 + (uint32_t)(t * BLOCK_N), da[t] + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
+                                idesc, (k > 0) ? 1u : acc);
+                  }
+                  umma_commit(b_empty(stage));
                 }
-                umma_commit(b_empty(stage));
+                __syncwarp();
                 if (++stage == B_STAGES) {
                   stage = 0;
                   phase ^= 1u;
@@ -228,7 +239,8 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
             free_plane(5);
           }
         }
-        umma_commit(tmem_full(buf));
+        if (elect_one_sync()) umma_commit(tmem_full(buf));
+        __syncwarp();
         if (++buf == 2) {
           buf = 0;
           buf_phase ^= 1u;

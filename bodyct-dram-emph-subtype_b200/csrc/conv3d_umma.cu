@@ -86,7 +86,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
   auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + A_STAGE_BYTES; };
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -111,6 +111,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
 
   if (warp == PRODUCER_WARP) {
     if (lane == 0) {
@@ -151,7 +152,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
     }
     __syncwarp();
   } else if (warp == MMA_WARP) {
-    if (lane == 0) {
+    {  // the whole warp walks the loops (uniform control flow); one elected lane issues
       const uint32_t idesc = make_idesc_16bit(BLOCK_M, BLOCK_N, p.epi.is_f16);
       int stage = 0;
       uint32_t phase = 0;
@@ -174,14 +175,17 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
                 tcgen05_fence_after();
                 const uint64_t da = make_sw128_desc(smem_a(stage));
                 const uint64_t db = make_sw128_desc(smem_b(stage));
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                  // +32 bytes along K inside the 128-byte swizzle row = +2 in the >>4 address field
-                  umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                            accumulate);
-                  accumulate = 1;
+                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // +32 bytes along K inside the 128-byte swizzle row = +2 in the >>4 address field
+                    umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (k > 0) ? 1u : accumulate);
+                  }
+                  umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
                 }
-                umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+                __syncwarp();
+                accumulate = 1;
                 if (++stage == STAGES) {
                   stage = 0;
                   phase ^= 1u;
@@ -190,7 +194,8 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
             }
           }
         }
-        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;

@@ -14,6 +14,8 @@ from dram_b200 import ops  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+ALGO = sys.argv[3] if len(sys.argv) > 3 else "auto"
+DT = torch.float16
 dev = torch.device("cuda:0")
 
 # name, count, spatial divisor of input, c1, c2, cout, kernel, stride, dil, tile
@@ -41,17 +43,17 @@ def main():
         dv = (div, div, div) if isinstance(div, int) else div
         dims = tuple(S // q for q in dv)
         k3 = (k, k, k) if isinstance(k, int) else k
-        x1 = torch.randn((B,) + dims + (c1,), device=dev).to(torch.bfloat16)
-        x2 = torch.randn((B,) + dims + (c2,), device=dev).to(torch.bfloat16) if c2 else None
+        x1 = torch.randn((B,) + dims + (c1,), device=dev).to(DT)
+        x2 = torch.randn((B,) + dims + (c2,), device=dev).to(DT) if c2 else None
         taps = k3[0] * k3[1] * k3[2]
-        w = (torch.randn(cout, taps * (c1 + c2), device=dev) * 0.02).to(torch.bfloat16)
+        w = (torch.randn(cout, taps * (c1 + c2), device=dev) * 0.02).to(DT)
         b = torch.zeros(cout, device=dev)
         heads = None
         if cout == 32:
             heads = (torch.randn(2, 32, device=dev), torch.zeros(2, device=dev), (1, 1), True)
         pad = (3, 0, 0) if k3 == (7, 1, 1) else None
         plan = ops.Conv3dPlan(x1, w, b, x2=x2, kernel=k3, stride=s, dilation=dl, padding=pad, heads=heads,
-                              store_out=heads is None, tile=tile)
+                              store_out=heads is None, tile=tile, algo=ALGO if tile is None else "tiles")
         for _ in range(2):
             plan.run()
         times = []
@@ -68,7 +70,7 @@ def main():
         if k3 == (7, 1, 1):
             fl = fl * 343 // 448
         print(f"{name:22s} x{count:2d} tiles {plan.m_tiles:6d}x{plan.n_tiles} bn {plan.block_n:3d} "
-              f"{t:8.3f} ms {fl / t / 1e9:8.1f} TFLOP/s  (alg {fl / 1e9:8.1f} GF)", flush=True)
+              f"{t:8.3f} ms {fl / t / 1e9:8.1f} TFLOP/s  (alg {fl / 1e9:8.1f} GF) {plan.algo}", flush=True)
         tot_t += t * count
         tot_f += fl * count
         del plan, x1, x2, w
