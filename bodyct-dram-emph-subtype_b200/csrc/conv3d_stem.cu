@@ -1,0 +1,309 @@
+// K2, fused stem — conv1 = Conv3d(1, 64, k7, s2, p3) + BN + ReLU (med3d.py:296-304, 371-373) straight from
+// the fp32 image: no unfolded copy in HBM (K2a + K1 wrote and re-read 537 MB per 256^3 volume).
+//
+// GEMM view per input plane z: K = 64 pseudo-channels (kh*8 + j), j <-> input column 2*ow - 4 + j, so the
+// filter tap kw = j - 1 and the j = 0 / kh = 7 weights are zero.  Because (kh, j) only index the INPUT plane,
+// the A operand of plane z is the same for every (output plane, kd) pair that touches it:
+//   * the CTA owns a column of 8 (W) x 16 (H) output voxels and marches along D;
+//   * producer warps unfold kw only: slot[r][ow] = 8 halves x[z][2*h0 - 3 + r][2*(w0 + ow) - 4 .. + 3]
+//     (38 rows x 8 x 16 B = 4.75 KiB per input plane, 20-slot ring);
+//   * kh is NOT unfolded: output row oh reads slot rows 2*oh + kh, so the A tile of a (kd, kh pair) MMA is a
+//     no-swizzle K-major UMMA view of the slot: 8-row group stride (SBO) = two slot rows, K core-matrix
+//     stride (LBO) = one slot row, start = slot + 2*pair rows.  Nothing is copied per tap;
+//   * all 7 x 64 x 64 packed weights (56 KiB) stay resident in shared memory;
+//   * four consecutive output planes accumulate in TMEM (4 x 64 columns, double buffered); each input plane
+//     is unfolded once per column and used by the 3-4 output planes that touch it.
+//
+// Roles (288 threads): warps 0-3 epilogue, warp 4 MMA issuer (owns TMEM), warps 5-8 producers.
+#include "conv_plan.h"
+
+namespace dram {
+
+static constexpr int ST_W = 8, ST_H = 16, ST_GROUP = 4;
+static constexpr int ST_ROWS = 2 * ST_H + 6;                 // 37 rows read by kh < 7, +1 read by the zero tap
+static constexpr int ST_PLANE_BYTES = ST_ROWS * ST_W * 16;   // 4864
+static constexpr int ST_RING = 20;
+static constexpr int ST_ITEM_PLANES = 2 * ST_GROUP + 5;      // 13 input planes feed 4 output planes
+static constexpr int ST_KEEP = 5;                            // planes shared with the next group of the column
+static constexpr int ST_WEIGHT_BYTES = 7 * 8 * 64 * 16;      // [kd][kh][cout][8 halves] = 57344
+static constexpr int ST_THREADS = 288;
+static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_THREADS = 128;
+static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
+static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512;
+
+struct StemParams {
+  const float *x;       // fp32 [n][D][H][W]
+  const uint4 *weight;  // 16-bit [7][8][64][8]
+  int n, D, H, W;       // input dims
+  int cols_w, cols_h, groups_d, items_total;
+  EpiParams epi;
+};
+
+struct StemItem {
+  int sample, w0, h0, q0, g;
+};
+__device__ __forceinline__ StemItem decode_stem_item(const StemParams &p, int item) {
+  StemItem it;
+  const int col = item / p.groups_d;
+  it.g = item - col * p.groups_d;
+  it.q0 = it.g * ST_GROUP;
+  const int per_sample = p.cols_w * p.cols_h;
+  it.sample = col / per_sample;
+  const int r = col - it.sample * per_sample;
+  const int ih = r / p.cols_w;
+  it.w0 = (r - ih * p.cols_w) * ST_W;
+  it.h0 = ih * ST_H;
+  return it;
+}
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; lbo = byte distance of the second K core
+// matrix, sbo = byte distance between 8-row groups (cute::UMMA canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO))).
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, int is_f16) {
+  if (is_f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base + ST_RING * ST_PLANE_BYTES;
+  const uint32_t bar_base = w_base + ST_WEIGHT_BYTES;
+  auto plane_addr = [&](int s) { return smem_base + (uint32_t)s * ST_PLANE_BYTES; };
+  auto plane_full = [&](int s) { return bar_base + 8u * s; };
+  auto plane_empty = [&](int s) { return bar_base + 8u * (ST_RING + s); };
+  auto tmem_full = [&](int a) { return bar_base + 8u * (2 * ST_RING + a); };
+  auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * ST_RING + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * ST_RING + 4);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_RING; ++s) {
+      mbar_init(plane_full(s), ST_PROD_THREADS);
+      mbar_init(plane_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == ST_MMA_WARP) tmem_alloc(tmem_slot, ST_TMEM_COLS);
+  // resident weights: plain 16-byte copies, made visible to the tensor-core (async) proxy below
+  for (int i = threadIdx.x; i < ST_WEIGHT_BYTES / 16; i += ST_THREADS) {
+    const uint4 v = __ldg(p.weight + i);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(w_base + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int item_begin = (int)(((long long)blockIdx.x * p.items_total) / gridDim.x);
+  const int item_end = (int)(((long long)(blockIdx.x + 1) * p.items_total) / gridDim.x);
+
+  if (warp >= ST_PROD_WARP0) {
+    // ------------------------------- producers: unfold kw of one input plane per step -------------
+    const int tid = threadIdx.x - ST_PROD_WARP0 * 32;
+    const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
+    unsigned seq_end = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const StemItem it = decode_stem_item(p, item);
+      const bool reuse = item > item_begin && it.g > 0;
+      const unsigned seq_base = seq_end - (reuse ? (unsigned)ST_KEEP : 0u);
+      seq_end = seq_base + ST_ITEM_PLANES;
+      const int ih_base = 2 * it.h0 - 3, iw_base = 2 * it.w0 - 4;
+      for (int j = reuse ? ST_KEEP : 0; j < ST_ITEM_PLANES; ++j) {
+        const unsigned seq = seq_base + j;
+        const int slot = seq % ST_RING;
+        const int z = 2 * it.q0 - 3 + j;
+        mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
+        const bool zok = z >= 0 && z < p.D;
+        const float *xz = p.x + ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int chunk = tid + c * ST_PROD_THREADS;
+          if (chunk < ST_ROWS * ST_W) {
+            const int r = chunk >> 3, owl = chunk & 7;
+            const int ih = ih_base + r, iw0 = iw_base + 2 * owl;
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = 0.0f;
+            if (zok && ih >= 0 && ih < p.H) {
+              const float *row = xz + (size_t)ih * p.W;
+              if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
+                  f[2 * q] = v.x;
+                  f[2 * q + 1] = v.y;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int iw = iw0 + q;
+                  if (iw >= 0 && iw < p.W) f[q] = __ldg(row + iw);
+                }
+              }
+            }
+            const uint32_t dst = plane_addr(slot) + (uint32_t)chunk * 16u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "r"(pack_pair(f[0], f[1], p.epi.is_f16)), "r"(pack_pair(f[2], f[3], p.epi.is_f16)),
+                         "r"(pack_pair(f[4], f[5], p.epi.is_f16)), "r"(pack_pair(f[6], f[7], p.epi.is_f16))
+                         : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(plane_full(slot));
+      }
+    }
+  } else if (warp == ST_MMA_WARP) {
+    const uint32_t idesc = make_idesc_16bit(128, 64, p.epi.is_f16);
+    unsigned seq_end = 0;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const StemItem it = decode_stem_item(p, item);
+      const bool reuse = item > item_begin && it.g > 0;
+      const bool next_reuse = (item + 1 < item_end) && (it.g + 1 < p.groups_d);
+      const unsigned seq_base = seq_end - (reuse ? (unsigned)ST_KEEP : 0u);
+      seq_end = seq_base + ST_ITEM_PLANES;
+      mbar_wait(tmem_empty(buf), buf_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d0 = tmem_base + (uint32_t)(buf * ST_GROUP * 64);
+      for (int j = 0; j < ST_ITEM_PLANES; ++j) {
+        const unsigned seq = seq_base + j;
+        const int slot = seq % ST_RING;
+        mbar_wait(plane_full(slot), (seq / ST_RING) & 1u);
+        tcgen05_fence_after();
+        const uint32_t a_base = plane_addr(slot);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {  // kh pairs (0,1) (2,3) (4,5) (6,7): K = 16 per MMA
+            const uint64_t da = make_nosw_desc(a_base + (uint32_t)(2 * pr) * 128u, 128u, 256u);
+#pragma unroll
+            for (int t = 0; t < ST_GROUP; ++t) {
+              const int kd = j - 2 * t;
+              if (kd >= 0 && kd < 7) {
+                const uint64_t db = make_nosw_desc(w_base + (uint32_t)(kd * 8 + 2 * pr) * 1024u, 1024u, 128u);
+                umma_bf16(tmem_d0 + (uint32_t)(t * 64), da, db, idesc, (kd > 0 || pr > 0) ? 1u : 0u);
+              }
+            }
+          }
+          if (j < ST_ITEM_PLANES - ST_KEEP || !next_reuse) umma_commit(plane_empty(slot));
+        }
+        __syncwarp();
+      }
+      if (elect_one_sync()) umma_commit(tmem_full(buf));
+      __syncwarp();
+      if (++buf == 2) {
+        buf = 0;
+        buf_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps 0..3 -------------------------------
+    const int row = warp * 32 + lane;
+    const int lw = row & (ST_W - 1);
+    const int lh = row >> 3;
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const StemItem it = decode_stem_item(p, item);
+      const int oh = it.h0 + lh, ow = it.w0 + lw;
+      mbar_wait(tmem_full(buf), buf_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < ST_GROUP; ++t) {
+        const int od = it.q0 + t;
+        const bool valid = (od < p.epi.Do) && (oh < p.epi.Ho) && (ow < p.epi.Wo);
+        const uint32_t taddr = tmem_base + (uint32_t)((buf * ST_GROUP + t) * 64) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          tmem_wait_ld();
+          if (valid) epilogue_group<false>(p.epi, v, c0, it.sample, od, oh, ow, nullptr);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty(buf));
+      if (++buf == 2) {
+        buf = 0;
+        buf_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == ST_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, ST_TMEM_COLS);
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+extern "C" size_t dram_stem_weight_bytes(void) { return ST_WEIGHT_BYTES; }
+
+extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *bias, const float *scale,
+                               void *out, int32_t n, int32_t d, int32_t h, int32_t w, int32_t relu,
+                               int32_t dtype, int32_t max_ctas, void *stream) {
+  DRAM_REQUIRE(x && weight && bias && out, "dram_stem_conv7: null pointer");
+  DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, "dram_stem_conv7: empty volume");
+  DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_stem_conv7: dtype must be bf16 (0) or fp16 (1)");
+  DRAM_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "dram_stem_conv7: weight and out must be 16-byte aligned");
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.weight = reinterpret_cast<const uint4 *>(weight);
+  p.n = n; p.D = d; p.H = h; p.W = w;
+  const int Do = (d - 1) / 2 + 1, Ho = (h - 1) / 2 + 1, Wo = (w - 1) / 2 + 1;
+  p.cols_w = ceil_div(Wo, ST_W);
+  p.cols_h = ceil_div(Ho, ST_H);
+  p.groups_d = ceil_div(Do, ST_GROUP);
+  const int64_t items = (int64_t)n * p.cols_w * p.cols_h * p.groups_d;
+  DRAM_REQUIRE(items <= 0x7fffffffLL, "dram_stem_conv7: too many work items");
+  p.items_total = (int)items;
+  p.epi.Do = Do; p.epi.Ho = Ho; p.epi.Wo = Wo;
+  p.epi.cout = 64;
+  p.epi.relu = relu;
+  p.epi.is_f16 = dtype == DRAM_DTYPE_F16;
+  p.epi.bias = bias;
+  p.epi.scale = scale;
+  p.epi.out = reinterpret_cast<uint16_t *>(out);
+  p.epi.res_stride = 1;
+  p.epi.store_out = 1;
+  int rc = check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           ST_SMEM_BYTES),
+                      "cudaFuncSetAttribute(conv3d_stem_kernel)");
+  if (rc != DRAM_OK) return rc;
+  int ctas = sm_count();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  if (p.items_total < ctas) ctas = p.items_total;
+  conv3d_stem_kernel<<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  DRAM_CHECK_LAUNCH("conv3d_stem_kernel launch");
+  return DRAM_OK;
+}

@@ -13,6 +13,8 @@ Data flow (reference: med3d.py:369-388 / 270-285), all kernels from libdram_b200
     xup2 --K1(64->32)+heads(+sigmoid) in the epilogue--> dense maps fp32 NCDHW (xup3 never stored)
     dense (+ lungs) --K6 masked/global pooling--> scores
 """
+import os
+
 import torch
 
 from . import ops
@@ -109,14 +111,28 @@ class Med3DEngine:
                 f"input size {self.dims}: each of D,H,W must be 8k or 8k-1 so that the x2 up-sampled maps match "
                 "their skip tensors; cropping skips is not implemented")
 
-        # ---- stem: image -> unfolded pseudo-channels -> conv(7,1,1) stride (2,1,1) + BN + ReLU
+        # ---- stem: conv(7^3, s2, p3) + BN + ReLU straight from the fp32 image (K2); the older two-kernel
+        # route (K2a unfold + K1 7x1x1) stays selectable for A/B runs with DRAM_B200_STEM=unfold
         self.image = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
-        self.xe = torch.empty((B, D, H1, W1, 64), dtype=bf, device=dev)
-        self.steps.append(_Step("stem_expand", lambda: ops.stem_expand(self.image, out=self.xe)))
-        wb = self._conv_bn("conv1", m.conv1, m.bn1, stem=True)
-        stem = self._add_conv("conv1", self.xe, wb, kernel=(7, 1, 1), stride=(2, 1, 1), padding=(3, 0, 0),
-                              tile=(16, 8, 1), flops=2 * B * D1 * H1 * W1 * 64 * 343)
-        x = stem.out
+        stem_flops = 2 * B * D1 * H1 * W1 * 64 * 343
+        if os.environ.get("DRAM_B200_STEM", "fused").lower() == "unfold":
+            self.xe = torch.empty((B, D, H1, W1, 64), dtype=bf, device=dev)
+            self.steps.append(_Step("stem_expand", lambda: ops.stem_expand(self.image, out=self.xe)))
+            wb = self._conv_bn("conv1", m.conv1, m.bn1, stem=True)
+            x = self._add_conv("conv1", self.xe, wb, kernel=(7, 1, 1), stride=(2, 1, 1), padding=(3, 0, 0),
+                               tile=(16, 8, 1), flops=stem_flops).out
+        else:
+            def pack_stem():
+                scale, shift = ops.fold_bn(m.bn1, m.conv1.bias)
+                packed, mult = ops.pack_stem_weight_fused(m.conv1.weight.detach().to(dev), scale.to(dev),
+                                                          dtype=bf, normalize=True)
+                return packed, shift.to(dev).float(), mult
+
+            sw = self._register_weight("conv1", pack_stem)
+            x = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
+            self.conv_flops += stem_flops
+            self.steps.append(_Step("conv1", lambda: ops.stem_conv7(self.image, sw[0], sw[1], sw[2], out=x),
+                                    stem_flops))
         # ---- maxpool
         self.xp = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)
         self.steps.append(_Step("maxpool", lambda x=x: ops.maxpool3d(x, out=self.xp)))

@@ -256,6 +256,50 @@ def pack_stem_weight(weight, scale=None, dtype=torch.bfloat16, normalize=False):
     return packed.to(dtype).contiguous()
 
 
+def pack_stem_weight_fused(weight, scale=None, dtype=torch.bfloat16, normalize=False):
+    """conv1.weight [64, 1, 7, 7, 7] -> 16-bit [7 (kd), 8 (kh), 64 (cout), 8 (j)] for `stem_conv7`:
+    element = w[cout, 0, kd, kh, j-1] (* scale[cout]) for kh < 7 and j >= 1, zero otherwise (the
+    kernel's pseudo-channel j reads input column 2*ow - 4 + j).  With `normalize` the per-output-channel
+    power-of-two multiplier is returned as well (see `pow2_normalizer`)."""
+    w = weight.detach().to(torch.float32)
+    if scale is not None:
+        w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
+    cout = w.shape[0]
+    if tuple(w.shape) != (64, 1, 7, 7, 7):
+        raise ValueError(f"pack_stem_weight_fused: expected conv1.weight [64,1,7,7,7], got {tuple(w.shape)}")
+    mult = pow2_normalizer(w.reshape(cout, -1)) if normalize else None
+    if normalize:
+        w = w / mult.view(-1, 1, 1, 1, 1)
+    packed = torch.zeros((7, 8, cout, 8), dtype=torch.float32, device=w.device)
+    packed[:, :7, :, 1:] = w[:, 0].permute(1, 2, 0, 3)  # [kd, kh, cout, kw]
+    packed = packed.to(dtype).contiguous()
+    return (packed, mult.contiguous()) if normalize else packed
+
+
+def stem_conv7(x, weight, bias, scale=None, out=None, relu=True, max_ctas=0):
+    """K2: fp32 [N, D, H, W] -> 16-bit NDHWC [N, D', H', W', 64] = relu(conv7^3 s2 p3 * scale + bias)."""
+    lib = _capi.load()
+    _need(x, torch.float32, "stem_conv7 x", 4)
+    _need16(weight, "stem_conv7 weight", 4)
+    if tuple(weight.shape) != (7, 8, 64, 8):
+        raise ValueError(f"stem_conv7: weight must be [7,8,64,8] (pack_stem_weight_fused), got {tuple(weight.shape)}")
+    _need(bias, torch.float32, "stem_conv7 bias", 1)
+    if scale is not None:
+        _need(scale, torch.float32, "stem_conv7 scale", 1)
+    if bias.shape[0] != 64 or (scale is not None and scale.shape[0] != 64):
+        raise ValueError("stem_conv7: bias/scale must have 64 entries")
+    n, d, h, w = x.shape
+    shape = (n, (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
+    if out is None:
+        out = torch.empty(shape, dtype=weight.dtype, device=x.device)
+    _need(out, weight.dtype, "stem_conv7 out", 5)
+    if tuple(out.shape) != shape:
+        raise ValueError(f"stem_conv7: out shape {tuple(out.shape)} != {shape}")
+    check(lib.dram_stem_conv7(_p(x), _p(weight), _p(bias), _p(scale), _p(out), n, d, h, w, 1 if relu else 0,
+                              ACT_DTYPES[weight.dtype], max_ctas, _stream()), "dram_stem_conv7")
+    return out
+
+
 def maxpool3d(x, out=None):
     _need16(x, "maxpool3d x", 5)
     n, d, h, w, c = x.shape

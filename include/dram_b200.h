@@ -143,6 +143,23 @@ int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops, int32_t *m
 int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
                      int32_t dtype, void *stream);
 
+/* ---- K2: fused stem, conv1 + bn1 + relu straight from the fp32 image ---- */
+/*
+ * med3d.py:296-304, 371-373: Conv3d(1, 64, k7, s2, p3, bias=False) + BatchNorm3d(eval) + ReLU.
+ * One tcgen05 kernel: producer warps unfold kw of each input plane into shared memory once, kh/kd
+ * are shifted UMMA views / accumulation steps, the 7x64x64 weights stay resident (no unfolded copy
+ * of the volume in HBM, unlike dram_stem_expand + dram_conv3d_run).
+ *   x      : fp32 [n][d][h][w] (the predict_step `image`, models.py:432)
+ *   weight : 16-bit [kd=7][kh=8][cout=64][j=8], element = w[cout][0][kd][kh][j-1] * bn_scale for
+ *            kh < 7 and j >= 1, else 0; dram_stem_weight_bytes() bytes
+ *   bias   : fp32 [64] folded BN shift; scale: optional fp32 [64] accumulator multiplier
+ *   out    : 16-bit NDHWC [n][(d-1)/2+1][(h-1)/2+1][(w-1)/2+1][64]
+ */
+size_t dram_stem_weight_bytes(void);
+int dram_stem_conv7(const float *x, const void *weight, const float *bias, const float *scale,
+                    void *out, int32_t n, int32_t d, int32_t h, int32_t w, int32_t relu,
+                    int32_t dtype, int32_t max_ctas, void *stream);
+
 /* ---- K3: max-pool 3x3x3 stride 2 pad 1 (med3d.py:305, 374) ------------- */
 int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
                    int32_t c, int32_t dtype, void *stream);

@@ -21,7 +21,7 @@ def test_layout_roundtrip(cuda, lib, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 12), (16, 6, 10)])
+@pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 12), (16, 6, 10), (20, 6, 10), (33, 5, 7), (1, 1, 1), (2, 3, 1)])
 def test_maxpool(cuda, lib, dims, dt):
     """med3d.py:305 MaxPool3d(3, stride 2, pad 1): exact (max of 16-bit values)."""
     from dram_b200 import ops
@@ -34,7 +34,7 @@ def test_maxpool(cuda, lib, dims, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("dims", [(4, 4, 4), (3, 5, 6), (8, 7, 9)])
+@pytest.mark.parametrize("dims", [(4, 4, 4), (3, 5, 6), (8, 7, 9), (9, 3, 5), (21, 2, 3), (1, 1, 1), (1, 4, 2)])
 def test_upsample2x(cuda, lib, dims, dt):
     """med3d.py:83 nn.Upsample(scale 2, trilinear, align_corners=True); fp32 math, one 16-bit rounding."""
     from dram_b200 import ops

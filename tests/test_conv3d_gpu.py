@@ -214,3 +214,54 @@ def test_stem_unfold(cuda, lib):
         got = ops.to_ncdhw_f32(plan.run()).cpu()
         assert got.shape == ref.shape, (got.shape, ref.shape)
         _close(got, ref, f"stem {dims}")
+
+
+STEM_CASES = [
+    # (batch, dims, max_ctas): even/odd sizes, several columns and D-groups, partial tiles, CTA counts that
+    # split columns mid-way (plane reuse across groups on and off)
+    (1, (16, 16, 32), 0),
+    (2, (12, 20, 24), 0),
+    (1, (9, 13, 17), 0),
+    (1, (40, 34, 36), 3),
+    (2, (33, 40, 20), 5),
+    (1, (64, 32, 16), 1),
+    (1, (7, 8, 8), 0),
+]
+
+
+@pytest.mark.parametrize("case", range(len(STEM_CASES)))
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_stem_fused(cuda, lib, case, dt):
+    """K2: Conv3d(1,64,k7,s2,p3)+shift+ReLU straight from the fp32 image (med3d.py:296-304, 371-373)."""
+    from dram_b200 import ops
+
+    n, dims, max_ctas = STEM_CASES[case]
+    g = torch.Generator().manual_seed(40 + case)
+    x = _rand((n, 1) + dims, g, dtype=dt)
+    wgt = _rand((64, 1, 7, 7, 7), g, scale=343 ** -0.5, dtype=dt)
+    bias = torch.randn(64, generator=g) * 0.1
+    ref = (F.conv3d(x, wgt, None, stride=2, padding=3) + bias.view(1, -1, 1, 1, 1)).relu()
+    wp, mult = ops.pack_stem_weight_fused(wgt.to(cuda), dtype=dt, normalize=True)
+    out = ops.stem_conv7(x[:, 0].contiguous().to(cuda), wp, bias.to(cuda), mult, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    got = ops.to_ncdhw_f32(out).cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    _close(got, ref, f"fused stem {dims} x{n} ctas {max_ctas}")
+
+
+def test_stem_fused_matches_unfold_route(cuda, lib):
+    """Both stem routes compute the same dot products from the same 16-bit operands."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(77)
+    x = _rand((1, 1, 24, 32, 40), g, dtype=torch.float16)
+    wgt = _rand((64, 1, 7, 7, 7), g, scale=343 ** -0.5, dtype=torch.float16)
+    bias = (torch.randn(64, generator=g) * 0.1).to(cuda)
+    xc = x[:, 0].contiguous().to(cuda)
+    xe = ops.stem_expand(xc, dtype=torch.float16)
+    plan = ops.Conv3dPlan(xe, ops.pack_stem_weight(wgt, dtype=torch.float16).to(cuda), bias, kernel=(7, 1, 1),
+                          stride=(2, 1, 1), padding=(3, 0, 0), tile=(16, 8, 1))
+    a = plan.run().float().cpu()
+    b = ops.stem_conv7(xc, ops.pack_stem_weight_fused(wgt.to(cuda), dtype=torch.float16), bias).float().cpu()
+    torch.cuda.synchronize()
+    assert (a - b).abs().max().item() <= 2.0 ** -9 * a.abs().max().item()
