@@ -14,7 +14,8 @@
 //   * four consecutive output planes accumulate in TMEM (4 x 64 columns, double buffered); each input plane
 //     is unfolded once per column and used by the 3-4 output planes that touch it.
 //
-// Roles (288 threads): warps 0-3 epilogue, warp 4 MMA issuer (owns TMEM), warps 5-8 producers.
+// Roles (416 threads): warps 0-3 epilogue, warp 4 MMA issuer (owns TMEM), warps 5-12 producers (one input
+// plane each, round robin).
 #include "conv_plan.h"
 
 namespace dram {
@@ -26,8 +27,8 @@ static constexpr int ST_RING = 20;
 static constexpr int ST_ITEM_PLANES = 2 * ST_GROUP + 5;      // 13 input planes feed 4 output planes
 static constexpr int ST_KEEP = 5;                            // planes shared with the next group of the column
 static constexpr int ST_WEIGHT_BYTES = 7 * 8 * 64 * 16;      // [kd][kh][cout][8 halves] = 57344
-static constexpr int ST_THREADS = 288;
-static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_THREADS = 128;
+static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = 8;
+static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 416
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
 static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512;
 
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_RING; ++s) {
-      mbar_init(plane_full(s), ST_PROD_THREADS);
+      mbar_init(plane_full(s), 32);
       mbar_init(plane_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -122,8 +123,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
 
   if (warp >= ST_PROD_WARP0) {
     // ------------------------------- producers: unfold kw of one input plane per step -------------
-    const int tid = threadIdx.x - ST_PROD_WARP0 * 32;
+    // Each producer warp owns every ST_PROD_WARPS-th plane of the stream, so that many planes' global
+    // loads are in flight at once; a lane builds its chunks in two batches of five (20 8-byte loads
+    // outstanding per lane).
+    const int pw = warp - ST_PROD_WARP0;
     const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
+    const int is_f16 = p.epi.is_f16;
     unsigned seq_end = 0;
     for (int item = item_begin; item < item_end; ++item) {
       const StemItem it = decode_stem_item(p, item);
@@ -133,42 +138,49 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
       const int ih_base = 2 * it.h0 - 3, iw_base = 2 * it.w0 - 4;
       for (int j = reuse ? ST_KEEP : 0; j < ST_ITEM_PLANES; ++j) {
         const unsigned seq = seq_base + j;
+        if ((int)(seq % ST_PROD_WARPS) != pw) continue;
         const int slot = seq % ST_RING;
         const int z = 2 * it.q0 - 3 + j;
         mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
         const bool zok = z >= 0 && z < p.D;
         const float *xz = p.x + ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
+        const uint32_t dst0 = plane_addr(slot);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int chunk = tid + c * ST_PROD_THREADS;
-          if (chunk < ST_ROWS * ST_W) {
+        for (int half = 0; half < 2; ++half) {
+          float f[5][8];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int chunk = lane + 32 * (half * 5 + c);
             const int r = chunk >> 3, owl = chunk & 7;
             const int ih = ih_base + r, iw0 = iw_base + 2 * owl;
-            float f[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = 0.0f;
-            if (zok && ih >= 0 && ih < p.H) {
+            for (int q = 0; q < 8; ++q) f[c][q] = 0.0f;
+            if (chunk < ST_ROWS * ST_W && zok && ih >= 0 && ih < p.H) {
               const float *row = xz + (size_t)ih * p.W;
               if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
-                  f[2 * q] = v.x;
-                  f[2 * q + 1] = v.y;
+                  f[c][2 * q] = v.x;
+                  f[c][2 * q + 1] = v.y;
                 }
               } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                   const int iw = iw0 + q;
-                  if (iw >= 0 && iw < p.W) f[q] = __ldg(row + iw);
+                  if (iw >= 0 && iw < p.W) f[c][q] = __ldg(row + iw);
                 }
               }
             }
-            const uint32_t dst = plane_addr(slot) + (uint32_t)chunk * 16u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                         "r"(pack_pair(f[0], f[1], p.epi.is_f16)), "r"(pack_pair(f[2], f[3], p.epi.is_f16)),
-                         "r"(pack_pair(f[4], f[5], p.epi.is_f16)), "r"(pack_pair(f[6], f[7], p.epi.is_f16))
-                         : "memory");
+          }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int chunk = lane + 32 * (half * 5 + c);
+            if (chunk < ST_ROWS * ST_W)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)chunk * 16u),
+                           "r"(pack_pair(f[c][0], f[c][1], is_f16)), "r"(pack_pair(f[c][2], f[c][3], is_f16)),
+                           "r"(pack_pair(f[c][4], f[c][5], is_f16)), "r"(pack_pair(f[c][6], f[c][7], is_f16))
+                           : "memory");
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -125,6 +125,63 @@ def collate(samples):
     return out
 
 
+class DevicePrefetcher:
+    """Wraps an iterable of host batch dicts (the `predict_dataloader` contract, ideally pinned memory):
+    the tensors of batch i+1 are copied host->device on a side stream while the caller computes on batch
+    i.  Two device buffer sets are reused in turn; a set is overwritten only after the compute stream has
+    passed the point where the caller asked for the following batch.  Non-tensor entries pass through.
+
+        for batch in DevicePrefetcher(loader, device):
+            pred = module.predict_step(batch, i)
+    """
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+
+    def _stage(self, host, bufs, done):
+        with torch.cuda.stream(self.copy_stream):
+            if done is not None:
+                self.copy_stream.wait_event(done)
+            out = {}
+            for key, val in host.items():
+                if isinstance(val, torch.Tensor) and not val.is_cuda:
+                    dst = bufs.get(key)
+                    if dst is None or dst.shape != val.shape or dst.dtype != val.dtype:
+                        dst = bufs[key] = torch.empty(val.shape, dtype=val.dtype, device=self.device)
+                    dst.copy_(val, non_blocking=True)
+                    out[key] = dst
+                else:
+                    out[key] = val
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return out, ready
+
+    def __iter__(self):
+        it = iter(self.loader)
+        bufs, done = ({}, {}), [None, None]
+        try:
+            staged = self._stage(next(it), bufs[0], None)
+        except StopIteration:
+            return
+        k = 0
+        while staged is not None:
+            cur, ready = staged
+            try:
+                nxt = next(it)
+            except StopIteration:
+                nxt = None
+            # batch k+1 goes into the set batch k-1 used; the caller finished issuing work on k-1 before
+            # asking for k, and `done` was recorded on its stream at that moment
+            staged = self._stage(nxt, bufs[(k + 1) % 2], done[(k + 1) % 2]) if nxt is not None else None
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            yield cur
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            done[k % 2] = ev
+            k += 1
+
+
 class _ScanModule(_ModuleBase):
     def __init__(self, args):
         self.args = args

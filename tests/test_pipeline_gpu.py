@@ -135,3 +135,28 @@ def test_processor_end_to_end(cuda, lib, tmp_path):
     first = json.load(open(out_dir / "centrilobular-emphysema-score.json"))
     assert first["score"] == int(records[0]["metrics"]["cle_severity_score"])
     assert os.path.isfile(out_dir / "araseptal-emphysema-score.json") and os.path.isfile(out_dir / "results.json")
+
+
+def test_device_prefetcher_delivers_every_batch_intact(cuda, lib):
+    """The double-buffered host->device staging of the predict loop: contents, order, pass-through keys."""
+    from dram_b200.models import DevicePrefetcher
+
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for i in range(5):
+        batches.append({"image": torch.randn(2, 8, 16, 16, generator=g).pin_memory(),
+                        "lung_mask": (torch.rand(2, 8, 16, 16, generator=g) > 0.5).pin_memory(),
+                        "uid": [f"scan{i}a", f"scan{i}b"]})
+    seen = 0
+    for i, dev_batch in enumerate(DevicePrefetcher(iter(batches), cuda)):
+        assert dev_batch["image"].is_cuda and dev_batch["lung_mask"].dtype == torch.bool
+        # a long-running consumer kernel: the set must not be overwritten while it is still being read
+        acc = dev_batch["image"].clone()
+        for _ in range(50):
+            acc = acc * 1.0
+        assert torch.equal(acc.cpu(), batches[i]["image"])
+        assert torch.equal(dev_batch["lung_mask"].cpu(), batches[i]["lung_mask"])
+        assert dev_batch["uid"] == batches[i]["uid"]
+        seen += 1
+    assert seen == 5
+    assert list(DevicePrefetcher(iter([]), cuda)) == []
