@@ -1,21 +1,26 @@
 // K1, plane-ring variant — 3x3x3 / stride 1 / dilation 1 / pad 1 convolutions with Cout of 32 or 64
-// (layer1, the whole decoder: 61 % of the round-1 step time).
+// (layer1, the whole decoder).
 //
 // Why: with one TMA box per (tap, chunk) every 128-clock MMA chunk ingests a 16 KiB activation tile and an
 // 8 KiB weight tile, ~190 B/clk/SM against the ~36 B/clk/SM the L2->SM fabric sustains
-// (profiles/conv_ncu_r1.md): the tensor pipe idles 80 % of the time.  Here
+// (profiles/conv_ncu_r1.md).  Here
 //   * the CTA owns a column of the volume, 8 (W) x 16 (H) voxels wide, and marches along D;
 //   * every input plane of the column (10 x 18 voxels with halo, 64 channels = 23 KiB) is fetched ONCE by
-//     one TMA box into an 8-slot shared-memory ring; zero padding = TMA out-of-bounds fill;
+//     one TMA box into a shared-memory ring; zero padding = TMA out-of-bounds fill;
 //   * an output tile is one 8 x 16 slab (128 voxels); its A operand for tap (kd,kh,kw) is the plane
 //     d+kd-1 viewed through a UMMA descriptor whose start address is shifted by (kh*10+kw) rows and whose
 //     8-row-group stride (SBO) is the plane pitch 10*128 B — no data is moved per tap;
-//   * four consecutive output planes accumulate side by side in TMEM (two sets of 4 x N columns for
-//     double buffering), so each 8 KiB weight tile (one TMA box) feeds 4 x 4 MMAs.
-// Operand ingest per 128-clock chunk drops from 24 KiB to ~3.3 KiB.
+//   * four consecutive output planes accumulate side by side in TMEM (two sets of 4 x N columns);
+//   * kd is stacked along the MMA's N dimension: with Cout <= 64 the tensor pipe is bound by the
+//     shared-memory read of the A operand (4 KiB per M128 x N64 x K16 MMA = the full 128 B/clk; ncu:
+//     l1tex__data_pipe_tc_wavefronts_mem_shared 72 %, profiles/aux_ncu_r1d.md).  Input plane j of an item
+//     contributes to output planes j, j-1, j-2 through kd = 0, 1, 2, and those accumulators sit in adjacent
+//     TMEM columns, so ONE MMA with B = [W(kd=2); W(kd=1); W(kd=0)] (N = 3*Cout) replaces three: the A
+//     tile is read once for up to 192 output channels.  A weight stage therefore holds the three kd taps
+//     of one (kh,kw).
 //
-// Roles (224 threads): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 lane 0 MMA issuer (warp 5
-// owns TMEM), warp 6 lane 0 weight producer.  Work items = (column, group of 4 planes); every CTA takes a
+// Roles (224 threads): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 MMA issuer (owns TMEM),
+// warp 6 lane 0 weight producer.  Work items = (column, group of 4 planes); every CTA takes a
 // contiguous range of items (D fastest), so consecutive groups of a column reuse two resident planes.
 #include "conv_plan.h"
 
@@ -25,15 +30,17 @@ static constexpr int SL_W = 8, SL_H = 16, SL_GROUP = 4;      // slab = 8 x 16 vo
 static constexpr int PL_W = SL_W + 2, PL_H = SL_H + 2;       // input plane with halo
 static constexpr int PLANE_BYTES = PL_W * PL_H * 128;        // 23040
 static constexpr int PLANE_PITCH = 23 * 1024;                // slot pitch, 1 KiB aligned for SWIZZLE_128B
-static constexpr int RING = 8;
-static constexpr int B_STAGES = 4;
+static constexpr int RING = 7;
+static constexpr int ITEM_PLANES = SL_GROUP + 2;             // 6 input planes feed 4 output planes
 static constexpr int SL_THREADS = 224;
 static constexpr int SL_A_WARP = 4, SL_MMA_WARP = 5, SL_B_WARP = 6;
 static constexpr int SL_BLOCK_K = 64;
 
 template <int BLOCK_N>
 struct SlabCfg {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * 128;
+  static constexpr int B_BLOCK_BYTES = BLOCK_N * 128;       // one tap: Cout rows x 64 channels
+  static constexpr int B_STAGE_BYTES = 3 * B_BLOCK_BYTES;   // [kd=2; kd=1; kd=0] of one (kh,kw)
+  static constexpr int B_STAGES = BLOCK_N == 64 ? 2 : 4;
   static constexpr int TMEM_COLS = 2 * SL_GROUP * BLOCK_N;  // 512 (N=64) / 256 (N=32)
   static constexpr int SMEM_BYTES = 1024 + RING * PLANE_PITCH + B_STAGES * B_STAGE_BYTES + 256;
 };
@@ -71,6 +78,7 @@ __global__ void __launch_bounds__(SL_THREADS, 1)
 conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ SlabParams p) {
   using Cfg = SlabCfg<BLOCK_N>;
+  constexpr int B_STAGES = Cfg::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + RING * PLANE_PITCH;
@@ -129,7 +137,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
         for (int c = 0; c < p.chunks_total; ++c) {
           const bool reuse = single_chunk && item > item_begin && it.g > 0;
           const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
-          for (int j = reuse ? 2 : 0; j < SL_GROUP + 2; ++j) {
+          for (int j = reuse ? 2 : 0; j < ITEM_PLANES; ++j) {
             const unsigned seq = seq_base + j;
             const int slot = seq % RING;
             mbar_wait(plane_empty(slot), ((seq / RING) & 1u) ^ 1u);
@@ -141,7 +149,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               tma_load_5d(plane_addr(slot), &map_a2, plane_full(slot), (c - p.chunks1) * SL_BLOCK_K, it.w0 - 1,
                           it.h0 - 1, it.q0 - 1 + j, it.sample);
           }
-          seq_end = seq_base + SL_GROUP + 2;
+          seq_end = seq_base + ITEM_PLANES;
         }
       }
     }
@@ -152,10 +160,15 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       uint32_t phase = 0;
       for (int item = item_begin; item < item_end; ++item) {
         for (int c = 0; c < p.chunks_total; ++c) {
-          for (int tap = 0; tap < 27; ++tap) {
+          for (int hw = 0; hw < 9; ++hw) {  // one stage = the three kd taps of (kh,kw), kd descending
             mbar_wait(b_empty(stage), phase ^ 1u);
             mbar_expect_tx(b_full(stage), Cfg::B_STAGE_BYTES);
-            tma_load_2d(b_addr(stage), &map_w, b_full(stage), (tap * p.chunks_total + c) * SL_BLOCK_K, 0);
+#pragma unroll
+            for (int blk = 0; blk < 3; ++blk) {
+              const int tap = (2 - blk) * 9 + hw;
+              tma_load_2d(b_addr(stage) + (uint32_t)(blk * Cfg::B_BLOCK_BYTES), &map_w, b_full(stage),
+                          (tap * p.chunks_total + c) * SL_BLOCK_K, 0);
+            }
             if (++stage == B_STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -167,7 +180,9 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     __syncwarp();
   } else if (warp == SL_MMA_WARP) {
     {  // the whole warp walks the loops (uniform control flow); one elected lane issues
-      const uint32_t idesc = make_idesc_16bit(128, BLOCK_N, p.epi.is_f16);
+      uint32_t idesc[3];
+#pragma unroll
+      for (int nb = 0; nb < 3; ++nb) idesc[nb] = make_idesc_16bit(128, (nb + 1) * BLOCK_N, p.epi.is_f16);
       int stage = 0;
       uint32_t phase = 0;
       unsigned seq_end = 0;
@@ -182,61 +197,54 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
           const bool reuse = single_chunk && item > item_begin && it.g > 0;
           const bool next_reuse = single_chunk && (item + 1 < item_end) && (it.g + 1 < p.groups_d);
           const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
-          seq_end = seq_base + SL_GROUP + 2;
-          auto wait_plane = [&](int j) {
-            const unsigned seq = seq_base + j;
-            mbar_wait(plane_full(seq % RING), (seq / RING) & 1u);
-          };
-          auto free_plane = [&](int j) {
-            if (elect_one_sync()) umma_commit(plane_empty((seq_base + j) % RING));
-            __syncwarp();
-          };
-          for (int kd = 0; kd < 3; ++kd) {
-            if (kd == 0) {
-              for (int j = 0; j < SL_GROUP; ++j) wait_plane(j);
-            } else {
-              wait_plane(SL_GROUP - 1 + kd);
-            }
+          seq_end = seq_base + ITEM_PLANES;
+          for (int hw = 0; hw < 9; ++hw) {
+            const int kh = hw / 3, kw = hw - 3 * kh;
+            mbar_wait(b_full(stage), phase);
             tcgen05_fence_after();
-            for (int kh = 0; kh < 3; ++kh) {
-              for (int kw = 0; kw < 3; ++kw) {
-                mbar_wait(b_full(stage), phase);
+            const uint32_t row_off = (uint32_t)(kh * PL_W + kw) * 128u;
+            const bool first = (c == 0 && hw == 0);  // accumulators are initialised tile by tile
+#pragma unroll
+            for (int j = 0; j < ITEM_PLANES; ++j) {
+              const unsigned seq = seq_base + j;
+              const int slot = seq % RING;
+              if (hw == 0) {  // planes of this chunk arrive in order during its first stage
+                mbar_wait(plane_full(slot), (seq / RING) & 1u);
                 tcgen05_fence_after();
-                const uint64_t db = make_sw128_desc(b_addr(stage));
-                const uint32_t row_off = (uint32_t)(kh * PL_W + kw) * 128u;
-                // k outer, tile inner: consecutive MMAs target different accumulators, so the
-                // read-modify-write latency of one TMEM tile never serialises the tensor pipe
-                uint64_t da[SL_GROUP];
-#pragma unroll
-                for (int t = 0; t < SL_GROUP; ++t)
-                  da[t] = make_sw128_desc_sbo(plane_addr((seq_base + t + kd) % RING) + row_off, PL_W * 128,
-                                              p.desc_base_offset_mode);
-                const uint32_t acc = (c > 0 || kd > 0 || kh > 0 || kw > 0) ? 1u : 0u;
-                if (elect_one_sync()) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                    for (int t = 0; t < SL_GROUP; ++t)
-                      umma_bf16(tmem_d0 + (uint32_t)(t * BLOCK_N), da[t] + (uint64_t)(2 * k), db + (uint64_t)(2 * k),
-                                idesc, (k > 0) ? 1u : acc);
-                  }
-                  umma_commit(b_empty(stage));
-                }
-                __syncwarp();
-                if (++stage == B_STAGES) {
-                  stage = 0;
-                  phase ^= 1u;
-                }
               }
+              // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
+              const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+              const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+              const uint64_t da = make_sw128_desc_sbo(plane_addr(slot) + row_off, PL_W * 128, p.desc_base_offset_mode);
+              const uint64_t db = make_sw128_desc(b_addr(stage) + (uint32_t)((2 - kd_hi) * Cfg::B_BLOCK_BYTES));
+              const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
+              if (elect_one_sync()) {
+                if (first) {
+#pragma unroll
+                  for (int q = 0; q < nblk; ++q) {  // tile t_min + q, kd = kd_hi - q; its first touch is kd == 0
+                    const uint64_t dbq = db + (uint64_t)((q * Cfg::B_BLOCK_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16(dcol + (uint32_t)(q * BLOCK_N), da + (uint64_t)(2 * k), dbq + (uint64_t)(2 * k), idesc[0],
+                                (k > 0 || kd_hi - q > 0) ? 1u : 0u);
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
+                }
+                // last stage of the chunk: hand each plane back as soon as its MMAs are issued so the
+                // producer refills the ring while the remaining planes of this stage are still computing
+                if (hw == 8 && (j < SL_GROUP || !next_reuse)) umma_commit(plane_empty(slot));
+              }
+              __syncwarp();
             }
-            // plane j is last read by the kd = j block of tile 0 (j = 0, 1); planes 2..5 live to the end
-            if (kd < 2) free_plane(kd);
-          }
-          free_plane(2);
-          free_plane(3);
-          if (!next_reuse) {
-            free_plane(4);
-            free_plane(5);
+            if (elect_one_sync()) umma_commit(b_empty(stage));
+            __syncwarp();
+            if (++stage == B_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         if (elect_one_sync()) umma_commit(tmem_full(buf));
