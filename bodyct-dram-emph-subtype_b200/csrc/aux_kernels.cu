@@ -133,8 +133,9 @@ __global__ void stem_expand_kernel(const float *__restrict__ x, uint4 *__restric
 // ---------------------------------------------------------------------------------------
 static constexpr int POOL_DCHUNK = 8;
 
-__device__ __forceinline__ void max8(uint4 &m, const uint4 u, int f16) {
-  if (f16) {
+template <bool F16>
+__device__ __forceinline__ void max8(uint4 &m, const uint4 u) {
+  if constexpr (F16) {
     __half2 *a = reinterpret_cast<__half2 *>(&m);
     const __half2 *b = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
@@ -147,11 +148,13 @@ __device__ __forceinline__ void max8(uint4 &m, const uint4 u, int f16) {
   }
 }
 
-__global__ void __launch_bounds__(256)
+template <bool F16>
+__global__ void __launch_bounds__(256, 3)
 maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d, int h, int w, int cg,
-                 int od, int oh, int ow, int dchunks, int f16) {
+                 int od, int oh, int ow, int dchunks) {
   const int64_t total = (int64_t)n * dchunks * oh * ow * cg;
-  const int64_t row = (int64_t)w * cg, plane = (int64_t)h * row;
+  const int row = w * cg;
+  const int64_t plane = (int64_t)h * row;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(t % cg);
@@ -162,23 +165,21 @@ maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, in
     v /= oh;
     const int ck = (int)(v % dchunks);
     const int b = (int)(v / dchunks);
-    int hh[3], ww[3];
+    int off[9];  // in-plane offsets of the 3x3 window (clamped taps repeat a voxel of the window)
 #pragma unroll
-    for (int z = 0; z < 3; ++z) {
-      hh[z] = min(max(2 * xh - 1 + z, 0), h - 1);
-      ww[z] = min(max(2 * xw - 1 + z, 0), w - 1);
-    }
-    const uint4 *xb = x + (int64_t)b * d * plane + g;
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        off[a * 3 + c] = min(max(2 * xh - 1 + a, 0), h - 1) * row + min(max(2 * xw - 1 + c, 0), w - 1) * cg + g;
+    const uint4 *xb = x + (int64_t)b * d * plane;
     auto plane_max = [&](int z) {
       const uint4 *p = xb + (int64_t)min(max(z, 0), d - 1) * plane;
       uint4 u[9];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) u[a * 3 + c] = __ldg(p + hh[a] * row + (int64_t)ww[c] * cg);
+      for (int i = 0; i < 9; ++i) u[i] = __ldg(p + off[i]);
       uint4 m = u[0];
 #pragma unroll
-      for (int i = 1; i < 9; ++i) max8(m, u[i], f16);
+      for (int i = 1; i < 9; ++i) max8<F16>(m, u[i]);
       return m;
     };
     const int xd0 = ck * POOL_DCHUNK, xd1 = min(od, xd0 + POOL_DCHUNK);
@@ -187,9 +188,9 @@ maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, in
     const int64_t ostride = (int64_t)oh * ow * cg;
     for (int xd = xd0; xd < xd1; ++xd) {
       uint4 m = carry;
-      max8(m, plane_max(2 * xd), f16);
+      max8<F16>(m, plane_max(2 * xd));
       carry = plane_max(2 * xd + 1);
-      max8(m, carry, f16);
+      max8<F16>(m, carry);
       *o = m;
       o += ostride;
     }
@@ -200,14 +201,35 @@ maxpool3d_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, in
 // K4 trilinear x2 (align_corners=True), NDHWC 16-bit, 8 channels per thread, fp32 math in ATen's
 // nesting order (W innermost, D outermost).  A thread owns one (h, w, channel group) of the output
 // and marches over a chunk of output planes; the in-plane bilinear combinations of the two
-// bracketing input planes stay in registers, and the source plane advances on every other step:
-// ~2.75 instead of 8 16-byte loads per output.
+// bracketing input planes stay in registers, and because the source step (d-1)/(2d-1) is below one
+// half the lower plane advances by at most one per output: ~2.5 instead of 8 16-byte loads per
+// output, and the storage type is a template parameter (no per-value type branches).
 // ---------------------------------------------------------------------------------------
 static constexpr int UP_DCHUNK = 8;
 
-__global__ void __launch_bounds__(256)
+template <bool F16>
+__device__ __forceinline__ float2 unpack2t(uint32_t u) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+  // bf16 -> fp32 is a 16-bit shift
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2t(float a, float b) {
+  if constexpr (F16) {
+    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
+    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  } else {
+    const bf162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256, 3)
 upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, int d, int h, int w, int cg,
-                  float sd, float sh, float sw, int dchunks, int f16) {
+                  float sd, float sh, float sw, int dchunks) {
   const int od = 2 * d, oh = 2 * h, ow = 2 * w;
   const int64_t total = (int64_t)n * dchunks * oh * ow * cg;
   const int64_t plane = (int64_t)h * w * cg;
@@ -222,9 +244,9 @@ upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, i
     const int ck = (int)(v % dchunks);
     const int b = (int)(v / dchunks);
     const LinIdx ih = lin_index_ac(xh, sh, h), iw = lin_index_ac(xw, sw, w);
-    const uint4 *xb = x + (int64_t)b * d * plane + g;
-    const int64_t o00 = ((int64_t)ih.i0 * w + iw.i0) * cg, o01 = ((int64_t)ih.i0 * w + iw.i1) * cg;
-    const int64_t o10 = ((int64_t)ih.i1 * w + iw.i0) * cg, o11 = ((int64_t)ih.i1 * w + iw.i1) * cg;
+    const int o00 = (ih.i0 * w + iw.i0) * cg + g, o01 = (ih.i0 * w + iw.i1) * cg + g;
+    const int o10 = (ih.i1 * w + iw.i0) * cg + g, o11 = (ih.i1 * w + iw.i1) * cg + g;
+    const uint4 *xb = x + (int64_t)b * d * plane;
     // in-plane bilinear combination of input plane z: h0*(w0*a + w1*b) + h1*(w0*c + w1*d)
     auto plane_val = [&](int z, float (&P)[8]) {
       const uint4 *p = xb + (int64_t)z * plane;
@@ -233,42 +255,31 @@ upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, i
       const uint32_t c_[4] = {uc.x, uc.y, uc.z, uc.w}, d_[4] = {ud.x, ud.y, ud.z, ud.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float2 fa = unpack2(a_[q], f16), fb = unpack2(b_[q], f16), fc = unpack2(c_[q], f16),
-                     fd = unpack2(d_[q], f16);
+        const float2 fa = unpack2t<F16>(a_[q]), fb = unpack2t<F16>(b_[q]), fc = unpack2t<F16>(c_[q]),
+                     fd = unpack2t<F16>(d_[q]);
         P[2 * q + 0] = ih.w0 * (iw.w0 * fa.x + iw.w1 * fb.x) + ih.w1 * (iw.w0 * fc.x + iw.w1 * fd.x);
         P[2 * q + 1] = ih.w0 * (iw.w0 * fa.y + iw.w1 * fb.y) + ih.w1 * (iw.w0 * fc.y + iw.w1 * fd.y);
       }
     };
     const int xd0 = ck * UP_DCHUNK, xd1 = min(od, xd0 + UP_DCHUNK);
     float P0[8], P1[8];
-    int cur0 = -1, cur1 = -1;
+    int cur = lin_index_ac(xd0, sd, d).i0;
+    plane_val(cur, P0);
+    plane_val(min(cur + 1, d - 1), P1);
     uint4 *o = out + ((((int64_t)b * od + xd0) * oh + xh) * ow + xw) * cg + g;
     const int64_t ostride = (int64_t)oh * ow * cg;
     for (int xd = xd0; xd < xd1; ++xd) {
       const LinIdx id = lin_index_ac(xd, sd, d);
-      if (id.i0 != cur0) {
-        if (id.i0 == cur1) {
+      if (id.i0 != cur) {  // the lower plane moved up by one: the old upper plane becomes the lower one
+        cur = id.i0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) P0[j] = P1[j];
-        } else {
-          plane_val(id.i0, P0);
-        }
-        cur0 = id.i0;
+        for (int j = 0; j < 8; ++j) P0[j] = P1[j];
+        if (cur + 1 < d) plane_val(cur + 1, P1);  // at the last plane i1 == i0 and P1 == P0 already
       }
-      if (id.i1 != cur1) {
-        if (id.i1 == cur0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) P1[j] = P0[j];
-        } else {
-          plane_val(id.i1, P1);
-        }
-        cur1 = id.i1;
-      }
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = id.w0 * P0[j] + id.w1 * P1[j];
-      *o = make_uint4(pack2(acc[0], acc[1], f16), pack2(acc[2], acc[3], f16), pack2(acc[4], acc[5], f16),
-                      pack2(acc[6], acc[7], f16));
+      *o = make_uint4(pack2t<F16>(id.w0 * P0[0] + id.w1 * P1[0], id.w0 * P0[1] + id.w1 * P1[1]),
+                      pack2t<F16>(id.w0 * P0[2] + id.w1 * P1[2], id.w0 * P0[3] + id.w1 * P1[3]),
+                      pack2t<F16>(id.w0 * P0[4] + id.w1 * P1[4], id.w0 * P0[5] + id.w1 * P1[5]),
+                      pack2t<F16>(id.w0 * P0[6] + id.w1 * P1[6], id.w0 * P0[7] + id.w1 * P1[7]));
       o += ostride;
     }
   }
@@ -276,33 +287,50 @@ upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, i
 
 // ---------------------------------------------------------------------------------------
 // K6 lobe-masked (or plain) mean of each dense channel.
-// grid = (blocks, ch, n).  sums: double [n][ch+1] (last slot = sum of mask / voxel count).
+// grid = (blocks, ch, n); one warp per (d, h) row of the map, so the row's mask indices are decoded
+// once and the lanes stream the row with 16-byte loads (VEC = 4) when w % 4 == 0.
+// sums: double [n][ch+1] (last slot = sum of mask / voxel count).
 // ---------------------------------------------------------------------------------------
-template <typename MaskT>
-__global__ void masked_pool_partial_kernel(const float *__restrict__ dense,
-                                           const MaskT *__restrict__ mask, double *__restrict__ sums,
-                                           int ch, int d, int h, int w, int md, int mh, int mw) {
+template <typename MaskT, int VEC>
+__global__ void __launch_bounds__(256)
+masked_pool_partial_kernel(const float *__restrict__ dense, const MaskT *__restrict__ mask,
+                           double *__restrict__ sums, int ch, int d, int h, int w, int md, int mh, int mw) {
   __shared__ double scratch[32];
   const int c = blockIdx.y, b = blockIdx.z;
   const int64_t plane = (int64_t)d * h * w;
   const float *src = dense + ((int64_t)b * ch + c) * plane;
   const MaskT *mk = mask ? mask + (int64_t)b * md * mh * mw : nullptr;
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int rows = d * h, wv = w / VEC;
   double s = 0.0, ms = 0.0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float m = 1.0f;
-    if (mk) {
-      const int xw = (int)(i % w);
-      const int64_t r = i / w;
-      const int xh = (int)(r % h);
-      const int xd = (int)(r / h);
-      const int zd = nearest_index(xd, md, d), zh = nearest_index(xh, mh, h), zw = nearest_index(xw, mw, w);
-      const MaskT mv = mk[((int64_t)zd * mh + zh) * mw + zw];
-      if constexpr (sizeof(MaskT) == 1) m = mv ? 1.0f : 0.0f;
-      else m = (float)mv;  // float lungs are used as weights, exactly like `dout * lungs` (med3d.py:387)
+  for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps) {
+    const int xd = r / h, xh = r - xd * h;
+    const float *row = src + (int64_t)r * w;
+    const MaskT *mrow = nullptr;
+    if (mk) mrow = mk + ((int64_t)nearest_index(xd, md, d) * mh + nearest_index(xh, mh, h)) * mw;
+    float fs = 0.0f, fm = 0.0f;  // a row chunk per lane: at most a few hundred values in [0,1]-ish range
+    for (int xv = lane; xv < wv; xv += 32) {
+      float v[VEC];
+      if constexpr (VEC == 4) {
+        const float4 f = __ldg(reinterpret_cast<const float4 *>(row) + xv);
+        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+      } else {
+        v[0] = __ldg(row + xv);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float m = 1.0f;
+        if (mrow) {
+          const MaskT mv = mrow[nearest_index(xv * VEC + j, mw, w)];
+          if constexpr (sizeof(MaskT) == 1) m = mv ? 1.0f : 0.0f;
+          else m = (float)mv;  // float lungs are used as weights, exactly like `dout * lungs` (med3d.py:387)
+        }
+        fs += v[j] * m;
+        fm += m;
+      }
     }
-    s += (double)(__ldg(src + i) * m);
-    ms += (double)m;
+    s += (double)fs;
+    ms += (double)fm;
   }
   s = block_sum(s, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[(int64_t)b * (ch + 1) + c], s);
@@ -320,79 +348,81 @@ __global__ void masked_pool_finalize_kernel(const double *__restrict__ sums, flo
 }
 
 // ---------------------------------------------------------------------------------------
-// K7 dRAM: both maps in one pass.  One thread per 4 consecutive output voxels along W when
-// W % 4 == 0 (float4 stores, uchar4 mask loads), scalar otherwise.
-// sums: double [2*n + n]: sum(out0[b]), sum(out1[b]), sum(lungs[b]).
+// K7 dRAM: both maps in one pass.  One warp per output row (d, h): the D/H source planes and weights
+// are decoded once per row; a lane produces 4 consecutive voxels along W per step when W % 4 == 0
+// (float4 stores, uchar4 mask loads), one otherwise.  Voxels outside `ess` are exact zeros and cost
+// no loads.  sums: double [2*n + n]: sum(out0[b]), sum(out1[b]), sum(lungs[b]).
 // ---------------------------------------------------------------------------------------
 template <int VEC>
-__global__ void dram_upsample_mask_kernel(const float *__restrict__ dense0, const float *__restrict__ dense1,
-                                          const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
-                                          float *__restrict__ out0, float *__restrict__ out1,
-                                          double *__restrict__ sums, int n, int d, int h, int w, int D,
-                                          int H, int W, float sd, float sh, float sw, int blocks_per_sample) {
+__global__ void __launch_bounds__(256)
+dram_upsample_mask_kernel(const float *__restrict__ dense0, const float *__restrict__ dense1,
+                          const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
+                          float *__restrict__ out0, float *__restrict__ out1, double *__restrict__ sums, int n,
+                          int d, int h, int w, int D, int H, int W, float sd, float sh, float sw,
+                          int blocks_per_sample) {
   __shared__ double scratch[32];
   const int b = blockIdx.x / blocks_per_sample;
   const int blk = blockIdx.x - b * blocks_per_sample;
-  const int Wv = W / VEC;
-  const int64_t per_sample = (int64_t)D * H * Wv;
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int Wv = W / VEC, rows = D * H;
   const int64_t splane = (int64_t)d * h * w;
   const float *s0 = dense0 + (int64_t)b * splane;
   const float *s1 = dense1 + (int64_t)b * splane;
-  double acc0 = 0.0, acc1 = 0.0, accl = 0.0;
-  for (int64_t t = (int64_t)blk * blockDim.x + threadIdx.x; t < per_sample;
-       t += (int64_t)blocks_per_sample * blockDim.x) {
-    const int xv = (int)(t % Wv);
-    const int64_t r = t / Wv;
-    const int xh = (int)(r % H);
-    const int xd = (int)(r / H);
-    const int64_t o = (((int64_t)b * D + xd) * H + xh) * W + (int64_t)xv * VEC;
-    uint8_t e[VEC], l[VEC];
-    if constexpr (VEC == 4) {
-      const uchar4 e4 = *reinterpret_cast<const uchar4 *>(ess + o);
-      const uchar4 l4 = *reinterpret_cast<const uchar4 *>(lungs + o);
-      e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
-      l[0] = l4.x; l[1] = l4.y; l[2] = l4.z; l[3] = l4.w;
-    } else {
-      e[0] = ess[o];
-      l[0] = lungs[o];
-    }
+  double acc0 = 0.0, acc1 = 0.0;
+  unsigned lung_count = 0;
+  for (int r = blk * warps + (threadIdx.x >> 5); r < rows; r += blocks_per_sample * warps) {
+    const int xd = r / H, xh = r - xd * H;
     const LinIdx id = lin_index_ac(xd, sd, d), ih = lin_index_ac(xh, sh, h);
-    const int64_t r00 = ((int64_t)id.i0 * h + ih.i0) * w, r01 = ((int64_t)id.i0 * h + ih.i1) * w;
-    const int64_t r10 = ((int64_t)id.i1 * h + ih.i0) * w, r11 = ((int64_t)id.i1 * h + ih.i1) * w;
-    float v0[VEC], v1[VEC];
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float a = 0.0f, c = 0.0f;
-      if (e[j]) {  // the product with ess == 0 is an exact 0 either way; skip the 16 loads
-        const LinIdx iw = lin_index_ac(xv * VEC + j, sw, w);
-        a = id.w0 * (ih.w0 * (iw.w0 * __ldg(s0 + r00 + iw.i0) + iw.w1 * __ldg(s0 + r00 + iw.i1)) +
-                     ih.w1 * (iw.w0 * __ldg(s0 + r01 + iw.i0) + iw.w1 * __ldg(s0 + r01 + iw.i1))) +
-            id.w1 * (ih.w0 * (iw.w0 * __ldg(s0 + r10 + iw.i0) + iw.w1 * __ldg(s0 + r10 + iw.i1)) +
-                     ih.w1 * (iw.w0 * __ldg(s0 + r11 + iw.i0) + iw.w1 * __ldg(s0 + r11 + iw.i1)));
-        c = id.w0 * (ih.w0 * (iw.w0 * __ldg(s1 + r00 + iw.i0) + iw.w1 * __ldg(s1 + r00 + iw.i1)) +
-                     ih.w1 * (iw.w0 * __ldg(s1 + r01 + iw.i0) + iw.w1 * __ldg(s1 + r01 + iw.i1))) +
-            id.w1 * (ih.w0 * (iw.w0 * __ldg(s1 + r10 + iw.i0) + iw.w1 * __ldg(s1 + r10 + iw.i1)) +
-                     ih.w1 * (iw.w0 * __ldg(s1 + r11 + iw.i0) + iw.w1 * __ldg(s1 + r11 + iw.i1)));
+    const int r00 = (id.i0 * h + ih.i0) * w, r01 = (id.i0 * h + ih.i1) * w;
+    const int r10 = (id.i1 * h + ih.i0) * w, r11 = (id.i1 * h + ih.i1) * w;
+    const int64_t obase = ((int64_t)b * rows + r) * W;
+    for (int xv = lane; xv < Wv; xv += 32) {
+      const int64_t o = obase + (int64_t)xv * VEC;
+      uint8_t e[VEC], l[VEC];
+      if constexpr (VEC == 4) {
+        const uchar4 e4 = *reinterpret_cast<const uchar4 *>(ess + o);
+        const uchar4 l4 = *reinterpret_cast<const uchar4 *>(lungs + o);
+        e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+        l[0] = l4.x; l[1] = l4.y; l[2] = l4.z; l[3] = l4.w;
+      } else {
+        e[0] = ess[o];
+        l[0] = lungs[o];
       }
-      v0[j] = a;
-      v1[j] = c;
-      acc0 += (double)a;
-      acc1 += (double)c;
-      accl += l[j] ? 1.0 : 0.0;
-    }
-    if constexpr (VEC == 4) {
-      *reinterpret_cast<float4 *>(out0 + o) = make_float4(v0[0], v0[1], v0[2], v0[3]);
-      *reinterpret_cast<float4 *>(out1 + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
-    } else {
-      out0[o] = v0[0];
-      out1[o] = v1[0];
+      float v0[VEC], v1[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float a = 0.0f, c = 0.0f;
+        if (e[j]) {  // the product with ess == 0 is an exact 0 either way; skip the 16 loads
+          const LinIdx iw = lin_index_ac(xv * VEC + j, sw, w);
+          a = id.w0 * (ih.w0 * (iw.w0 * __ldg(s0 + r00 + iw.i0) + iw.w1 * __ldg(s0 + r00 + iw.i1)) +
+                       ih.w1 * (iw.w0 * __ldg(s0 + r01 + iw.i0) + iw.w1 * __ldg(s0 + r01 + iw.i1))) +
+              id.w1 * (ih.w0 * (iw.w0 * __ldg(s0 + r10 + iw.i0) + iw.w1 * __ldg(s0 + r10 + iw.i1)) +
+                       ih.w1 * (iw.w0 * __ldg(s0 + r11 + iw.i0) + iw.w1 * __ldg(s0 + r11 + iw.i1)));
+          c = id.w0 * (ih.w0 * (iw.w0 * __ldg(s1 + r00 + iw.i0) + iw.w1 * __ldg(s1 + r00 + iw.i1)) +
+                       ih.w1 * (iw.w0 * __ldg(s1 + r01 + iw.i0) + iw.w1 * __ldg(s1 + r01 + iw.i1))) +
+              id.w1 * (ih.w0 * (iw.w0 * __ldg(s1 + r10 + iw.i0) + iw.w1 * __ldg(s1 + r10 + iw.i1)) +
+                       ih.w1 * (iw.w0 * __ldg(s1 + r11 + iw.i0) + iw.w1 * __ldg(s1 + r11 + iw.i1)));
+          acc0 += (double)a;
+          acc1 += (double)c;
+        }
+        v0[j] = a;
+        v1[j] = c;
+        lung_count += l[j] ? 1u : 0u;
+      }
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(out0 + o) = make_float4(v0[0], v0[1], v0[2], v0[3]);
+        *reinterpret_cast<float4 *>(out1 + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+      } else {
+        out0[o] = v0[0];
+        out1[o] = v1[0];
+      }
     }
   }
   acc0 = block_sum(acc0, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[b], acc0);
   acc1 = block_sum(acc1, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[n + b], acc1);
-  accl = block_sum(accl, scratch);
+  double accl = block_sum((double)lung_count, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[2 * n + b], accl);
 }
 __global__ void dram_finalize_kernel(const double *__restrict__ sums, float *__restrict__ pct, int n,
@@ -581,9 +611,14 @@ extern "C" int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, in
   const int od = (d - 1) / 2 + 1, oh = (h - 1) / 2 + 1, ow = (w - 1) / 2 + 1;
   const int dchunks = ceil_div(od, POOL_DCHUNK);
   const int64_t total = (int64_t)n * dchunks * oh * ow * (c / 8);
-  maxpool3d_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow, dchunks,
-      f16);
+  DRAM_REQUIRE((int64_t)h * w * (c / 8) < 0x7fffffffLL, "dram_maxpool3d: plane too large");
+  const int grid = stream_grid(total, kThreads);
+  if (f16)
+    maxpool3d_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow, dchunks);
+  else
+    maxpool3d_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8, od, oh, ow, dchunks);
   DRAM_CHECK_LAUNCH("maxpool3d_kernel");
   return DRAM_OK;
 }
@@ -597,9 +632,16 @@ extern "C" int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, i
                "dram_upsample2x: bad shape (c must be a multiple of 8)");
   const int dchunks = ceil_div(2 * d, UP_DCHUNK);
   const int64_t total = (int64_t)n * dchunks * (2 * h) * (2 * w) * (c / 8);
-  upsample2x_kernel<<<stream_grid(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8,
-      ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w), dchunks, f16);
+  DRAM_REQUIRE((int64_t)h * w * (c / 8) < 0x7fffffffLL, "dram_upsample2x: plane too large");
+  const int grid = stream_grid(total, kThreads);
+  if (f16)
+    upsample2x_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8,
+        ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w), dchunks);
+  else
+    upsample2x_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(x), reinterpret_cast<uint4 *>(out), n, d, h, w, c / 8,
+        ac_scale(d, 2 * d), ac_scale(h, 2 * h), ac_scale(w, 2 * w), dchunks);
   DRAM_CHECK_LAUNCH("upsample2x_kernel");
   return DRAM_OK;
 }
@@ -619,17 +661,22 @@ extern "C" int dram_masked_pool(const float *dense, const void *mask, int32_t ma
   int rc = check_cuda(cudaMemsetAsync(workspace, 0, dram_pool_workspace_bytes(n, ch), st),
                       "dram_masked_pool memset");
   if (rc != DRAM_OK) return rc;
-  const int64_t plane = (int64_t)d * h * w;
-  int blocks = stream_grid(plane, kThreads, 4);
+  DRAM_REQUIRE((int64_t)d * h < 0x7fffffffLL, "dram_masked_pool: too many rows");
+  const bool vec = (w % 4 == 0) && ((uintptr_t)dense % 16 == 0);
+  int blocks = stream_grid((int64_t)d * h * 32, kThreads, 8);  // one warp per row
   int per = blocks / (n * ch);
   if (per < 1) per = 1;
   dim3 grid(per, ch, n);
-  if (mask_is_f32)
-    masked_pool_partial_kernel<float><<<grid, kThreads, 0, st>>>(
-        dense, reinterpret_cast<const float *>(mask), reinterpret_cast<double *>(workspace), ch, d, h, w, md, mh, mw);
-  else
-    masked_pool_partial_kernel<uint8_t><<<grid, kThreads, 0, st>>>(
-        dense, reinterpret_cast<const uint8_t *>(mask), reinterpret_cast<double *>(workspace), ch, d, h, w, md, mh, mw);
+  double *ws = reinterpret_cast<double *>(workspace);
+  if (mask_is_f32) {
+    const float *mf = reinterpret_cast<const float *>(mask);
+    if (vec) masked_pool_partial_kernel<float, 4><<<grid, kThreads, 0, st>>>(dense, mf, ws, ch, d, h, w, md, mh, mw);
+    else masked_pool_partial_kernel<float, 1><<<grid, kThreads, 0, st>>>(dense, mf, ws, ch, d, h, w, md, mh, mw);
+  } else {
+    const uint8_t *mu = reinterpret_cast<const uint8_t *>(mask);
+    if (vec) masked_pool_partial_kernel<uint8_t, 4><<<grid, kThreads, 0, st>>>(dense, mu, ws, ch, d, h, w, md, mh, mw);
+    else masked_pool_partial_kernel<uint8_t, 1><<<grid, kThreads, 0, st>>>(dense, mu, ws, ch, d, h, w, md, mh, mw);
+  }
   DRAM_CHECK_LAUNCH("masked_pool_partial_kernel");
   masked_pool_finalize_kernel<<<ceil_div(n * ch, 128), 128, 0, st>>>(
       reinterpret_cast<const double *>(workspace), out, n, ch);
@@ -658,8 +705,9 @@ extern "C" int dram_dram_upsample_mask(const float *dense0, const float *dense1,
   const float sd = ac_scale(d, D), sh = ac_scale(h, H), sw = ac_scale(w, W);
   const bool vec = (W % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 4 == 0) &&
                    (((uintptr_t)out0 | (uintptr_t)out1) % 16 == 0);
-  const int64_t per_sample = (int64_t)D * H * (vec ? W / 4 : W);
-  int bps = stream_grid(per_sample, kThreads, 8) / n;
+  DRAM_REQUIRE((int64_t)D * H < 0x7fffffffLL && (int64_t)d * h * w < 0x7fffffffLL,
+               "dram_dram_upsample_mask: volume too large for 32-bit row indices");
+  int bps = stream_grid((int64_t)D * H * 32, kThreads, 8) / n;  // one warp per output row
   if (bps < 1) bps = 1;
   double *sums = reinterpret_cast<double *>(workspace);
   if (vec)
