@@ -30,7 +30,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ARCH = "med3ddram"
+ARCH_NAMES = {"med3ddram": "med3ddram (ResNet-34)", "med3ddram18": "med3ddram18 (ResNet-18)",
+              "med3ddram50": "med3ddram50 (ResNet-50 bottleneck)"}
 METRIC = "CT volumes/sec med3ddram inference"
+
+
+def workload_name(arch, dims, batch):
+    size = f"{dims[0]}^3" if dims[0] == dims[1] == dims[2] else "x".join(str(v) for v in dims)
+    return (f"{ARCH_NAMES[arch]} + dRAM inference, synthetic {size} CT volumes, batch {batch} per GPU, "
+            "random-init weights (paper.ckpt is a Git-LFS pointer)")
+
+
+def parse_dims(args):
+    if args.dims:
+        d = tuple(int(v) for v in args.dims.replace("x", ",").split(","))
+        if len(d) != 3:
+            raise SystemExit("--dims expects D,H,W")
+        return d
+    return (args.size,) * 3
 FALLBACK_TFLOPS = 1590.0  # B200_PROFILING.md fallback (burst); used only when MEASURED_PEAKS.json is absent
 
 
@@ -92,12 +109,12 @@ def tame_weights_(model, seed=0):
     return model
 
 
-def build_module(device):
+def build_module(device, arch=ARCH):
     import dram_b200  # noqa: F401
     from dram_b200.models import ScanRegLightningModule
 
     torch.manual_seed(0)
-    module = ScanRegLightningModule(Namespace(model_arch=ARCH))
+    module = ScanRegLightningModule(Namespace(model_arch=arch))
     tame_weights_(module.model)
     return module.to(device).eval()
 
@@ -175,6 +192,20 @@ def measured_peaks():
     return FALLBACK_TFLOPS, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(arch, dims, batch):
+    """DRAM bytes (read + write) of the conv launches of one step, from the committed ncu --set full capture
+    (profiles/conv_traffic.json, measured per volume at batch 1); None when no capture matches the workload."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if not os.path.isfile(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    key = f"{arch}:{'x'.join(str(v) for v in dims)}"
+    if key not in t:
+        return None, None
+    return t[key]["dram_bytes_per_volume"] * batch, t[key]["source"]
+
+
 def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,7 +239,7 @@ def max_over_ranks(value, world, device):
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference's PyTorch path on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_predict_seconds(sd, dims, batch=1, repeats=1, warmup=0):
+def cpu_predict_seconds(sd, dims, batch=1, repeats=1, warmup=0, arch=ARCH):
     """Median seconds of one oracle predict_step (transform-equivalent standardise + network + dRAM)."""
     from oracle import pipeline_oracle as P
     from oracle import synthetic
@@ -220,7 +251,7 @@ def cpu_predict_seconds(sd, dims, batch=1, repeats=1, warmup=0):
     with torch.no_grad():
         for i in range(warmup + repeats):
             t0 = time.perf_counter()
-            P.predict_step(sd, ARCH, b)
+            P.predict_step(sd, arch, b)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return statistics.median(times)
@@ -231,17 +262,23 @@ def cpu_state_dict(module):
             for k, v in module.model.state_dict().items()}
 
 
-def cpu_baseline(module, size, budget_s=30.0):
-    """Bounded sample: a 128^3 sub-volume first; the full volume only if it fits the time budget."""
+def _voxels(dims):
+    return dims[0] * dims[1] * dims[2]
+
+
+def cpu_baseline(module, dims, arch=ARCH, budget_s=30.0):
+    """Bounded sample: a sub-volume of at most 128 per axis first; the full volume only if it fits the budget."""
     sd = cpu_state_dict(module)
-    small = (min(size, 128),) * 3
-    t_small = cpu_predict_seconds(sd, small)
-    scale = (size / small[0]) ** 3
-    if small[0] == size or t_small * scale > budget_s:
-        t, sample = t_small * scale, f"1 volume of {small[0]}^3 timed ({t_small:.2f} s), scaled x{scale:.0f} by voxel count to {size}^3"
+    small = tuple(min(v, 128) for v in dims)
+    t_small = cpu_predict_seconds(sd, small, arch=arch)
+    scale = _voxels(dims) / _voxels(small)
+    if small == tuple(dims) or t_small * scale > budget_s:
+        t = t_small * scale
+        sample = (f"1 volume of {'x'.join(map(str, small))} timed ({t_small:.2f} s), scaled x{scale:.1f} by voxel "
+                  f"count to {'x'.join(map(str, dims))}")
     else:
-        t = cpu_predict_seconds(sd, (size,) * 3)
-        sample = f"1 full {size}^3 volume, one pass ({t:.2f} s)"
+        t = cpu_predict_seconds(sd, tuple(dims), arch=arch)
+        sample = f"1 full {'x'.join(map(str, dims))} volume, one pass ({t:.2f} s)"
     return {"value": 1.0 / t, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
 
@@ -253,24 +290,28 @@ def run_reference_arm(args):
     from dram_b200.models import ScanRegLightningModule
 
     torch.manual_seed(0)
-    module = ScanRegLightningModule(Namespace(model_arch=ARCH))
+    arch, dims = args.arch, parse_dims(args)
+    module = ScanRegLightningModule(Namespace(model_arch=arch))
     tame_weights_(module.model)
     sd = cpu_state_dict(module)
-    size = args.size
-    # each step = one bounded sample: a full volume if (steps+warmup) of them fit ~4 minutes, else a 128^3 one
-    probe = cpu_predict_seconds(sd, (min(size, 128),) * 3)
-    scale = (size / min(size, 128)) ** 3
+    # each step = one bounded sample: a full volume if (steps+warmup) of them fit ~4 minutes, else a sub-volume
+    small = tuple(min(v, 128) for v in dims)
+    probe = cpu_predict_seconds(sd, small, arch=arch)
+    scale = _voxels(dims) / _voxels(small)
     full = probe * scale * (args.steps + args.warmup) <= 240.0
-    dims = (size,) * 3 if full else (min(size, 128),) * 3
+    run_dims = tuple(dims) if full else small
     vol_frac = 1.0 if full else 1.0 / scale
-    t = cpu_predict_seconds(sd, dims, repeats=args.steps, warmup=args.warmup)
+    t = cpu_predict_seconds(sd, run_dims, repeats=args.steps, warmup=args.warmup, arch=arch)
     value = vol_frac / t
-    sample = (f"{args.steps} steps x 1 volume of {dims[0]}^3" + ("" if full else f" (= 1/{scale:.0f} of a {size}^3 volume by voxel count)"))
+    sample = (f"{args.steps} steps x 1 volume of {'x'.join(map(str, run_dims))}" +
+              ("" if full else f" (= 1/{scale:.1f} of a full volume by voxel count)"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"med3ddram (ResNet-34) + dRAM inference, synthetic {size}^3 CT, reference algorithm on host CPU"},
+        "config": {"workload": workload_name(arch, dims, args.batch),
+                   "arm": "the reference's algorithm (oracle port of its PyTorch CPU path) on the host cores, "
+                          "one volume per step"},
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -287,6 +328,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="volumes per GPU per step")
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--dims", default="", help="D,H,W (overrides --size), e.g. 400,512,512")
+    ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -298,9 +341,9 @@ def main():
     rank, local, world = dist_setup(args.gpus)
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    dims = (args.size,) * 3
+    dims = parse_dims(args)
     B = args.batch
-    module = build_module(device)
+    module = build_module(device, args.arch)
     hu, lungs, ess = make_volumes(B, dims, device, seed=rank)
     eng = module.model.engine(B, dims, device)
 
@@ -385,8 +428,11 @@ def main():
     conv_flops = sum(s.flops for s in conv_steps)
     peak, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv3d_umma_kernel (38 launches/step, all template instances)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_src = measured_traffic(args.arch, dims, B)
+    roofline = {"bound": "tensor",
+                "kernel": f"conv3d_stem_kernel + conv3d_slab_kernel + conv3d_umma_kernel ({len(conv_steps)} launches/step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                 "share_of_step": conv_ms / ms_per_step}
 
@@ -396,15 +442,14 @@ def main():
         "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
-        "config": {"workload": f"med3ddram (ResNet-34) + dRAM inference, synthetic {args.size}^3 CT volumes, "
-                               f"batch {B} per GPU, random-init weights (paper.ckpt is a Git-LFS pointer)",
+        "config": {"workload": workload_name(args.arch, dims, B),
                    "global_batch": world * B, "parallelism": f"volume-sharded x{world}, no collective",
                    "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                    "storage_dtype": str(eng.act_dtype)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
     }
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(module, args.size)
+        line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
     print(json.dumps(line), flush=True)
 
 
