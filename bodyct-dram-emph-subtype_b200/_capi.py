@@ -67,6 +67,10 @@ SIGNATURES = {
     "dram_window_standardize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _vp]),
     "dram_resize_image": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_resize_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_mask_bbox": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "dram_lung_crop_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "dram_lung_crop": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "dram_heatmap_u8": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

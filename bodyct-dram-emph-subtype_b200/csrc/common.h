@@ -46,4 +46,30 @@ inline int stream_grid(int64_t work_items, int threads, int ctas_per_sm = 8) {
   return (int)(want < cap ? want : cap);
 }
 
+
+#ifdef __CUDACC__
+// ATen's source index for linear modes with align_corners=True
+// (area_pixel_compute_scale + compute_source_index_and_lambda): scale = (in-1)/(out-1) in fp32.
+struct LinIdx {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ LinIdx lin_index_ac(int dst, float scale, int in_size) {
+  LinIdx r;
+  const float real = scale * (float)dst;
+  int i0 = (int)real;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  r.i0 = i0;
+  r.i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+  float l1 = real - (float)i0;
+  l1 = fminf(fmaxf(l1, 0.0f), 1.0f);
+  r.w1 = l1;
+  r.w0 = 1.0f - l1;
+  return r;
+}
+__host__ __device__ __forceinline__ float ac_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;
+}
+#endif
+
 }  // namespace dram

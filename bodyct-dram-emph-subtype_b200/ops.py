@@ -406,6 +406,51 @@ def resize_mask(x, size):
     return out
 
 
+def mask_bbox(mask):
+    """f1: uint8 [D,H,W] device mask -> int32[6] device tensor {zmin, zmax+1, ymin, ymax+1, xmin, xmax+1}
+    of mask != 0 ({D,0,H,0,W,0} when the mask is empty)."""
+    _need(mask, torch.uint8, "mask_bbox mask", 3)
+    D, H, W = mask.shape
+    bbox = torch.empty(6, dtype=torch.int32, device=mask.device)
+    check(_capi.load().dram_mask_bbox(_p(mask), D, H, W, _p(bbox), _stream()), "dram_mask_bbox")
+    return bbox
+
+
+def lung_crop(scan, lobe, crop):
+    """f1 (dataset.py:66-80): int16 scan + uint8 lobe labels [D,H,W] and crop ((z0,z1),(y0,y1),(x0,x1)) ->
+    (image int16, lung uint8, ess uint8) of the crop size: blanking outside the twice-dilated lung, LAA-910."""
+    lib = _capi.load()
+    _need(scan, torch.int16, "lung_crop scan", 3)
+    _need(lobe, torch.uint8, "lung_crop lobe", 3)
+    if scan.shape != lobe.shape:
+        raise ValueError("scan and lobe segmentation have different shapes.")
+    D, H, W = scan.shape
+    (z0, z1), (y0, y1), (x0, x1) = [(int(a), int(b)) for a, b in crop]
+    cd, ch, cw = z1 - z0, y1 - y0, x1 - x0
+    image = torch.empty((cd, ch, cw), dtype=torch.int16, device=scan.device)
+    lung = torch.empty((cd, ch, cw), dtype=torch.uint8, device=scan.device)
+    ess = torch.empty_like(lung)
+    ws = torch.empty(lib.dram_lung_crop_workspace_bytes(cd, ch, cw), dtype=torch.uint8, device=scan.device)
+    check(lib.dram_lung_crop(_p(scan), _p(lobe), D, H, W, z0, y0, x0, cd, ch, cw, _p(image), _p(lung), _p(ess),
+                             _p(ws), _stream()), "dram_lung_crop")
+    return image, lung, ess
+
+
+def heatmap_u8(dram_map, crop, original_size, out=None):
+    """f2 (processor.py:111-158): one fp32 dRAM [d,h,w] -> uint8 [D,H,W] of the original scan: trilinear
+    (align_corners) to the crop size, pasted at `crop`, windowed (0,1)->(0,255) with truncation."""
+    _need(dram_map, torch.float32, "heatmap_u8 map", 3)
+    d, h, w = dram_map.shape
+    OD, OH, OW = (int(v) for v in original_size)
+    (z0, z1), (y0, y1), (x0, x1) = [(int(a), int(b)) for a, b in crop]
+    if out is None:
+        out = torch.empty((OD, OH, OW), dtype=torch.uint8, device=dram_map.device)
+    _need(out, torch.uint8, "heatmap_u8 out", 3)
+    check(_capi.load().dram_heatmap_u8(_p(dram_map), d, h, w, _p(out), OD, OH, OW, z0, y0, x0, z1 - z0, y1 - y0,
+                                       x1 - x0, _stream()), "dram_heatmap_u8")
+    return out
+
+
 def to_ndhwc_16(x, dtype=torch.bfloat16):
     """fp32 NCDHW -> 16-bit NDHWC."""
     _need(x, torch.float32, "to_ndhwc_16 x", 5)

@@ -83,14 +83,12 @@ def postprocess_reg(pred, data_module, out_cle, out_pse):
     B = pred["cle_dense_outs"].shape[0]
     for b in range(B):
         crop = pred["crop_slices"][b]
-        recon = tuple(int(s[1]) - int(s[0]) for s in crop)
         orig = tuple(int(v) for v in pred["original_size"][b])
         uid = pred["uids"][b]
-        ones = torch.ones((1,) + recon, dtype=torch.uint8, device=pred["cle_dense_outs"].device)
-        # trilinear (align_corners=True) resample of both heat-maps to the crop size: K7 with an all-ones mask
-        cle, pse, _ = ops.dram_upsample_mask(pred["cle_dense_outs"][b:b + 1].contiguous(),
-                                             pred["pse_dense_outs"][b:b + 1].contiguous(), ones, ones, recon)
-        sl = tuple(slice(int(s[0]), int(s[1])) for s in crop)
+        # f2: resample to the crop, paste into the full volume and window to uint8 in one kernel per map;
+        # only uint8 leaves the GPU (processor.py:115-122, 143, 152 of the reference do this in numpy/float64)
+        heat = [ops.heatmap_u8(pred[k][b, 0].contiguous(), crop.tolist(), orig).cpu().numpy()
+                for k in ("cle_dense_outs", "pse_dense_outs")]
         cle_pct, pse_pct = pred["cle_precentages"][b].item(), pred["pse_precentages"][b].item()
         metrics = {
             "cle_severity_score": "{:d}".format(ratio_to_label(cle_pct, CLE_RATIO_MAP)),
@@ -102,10 +100,8 @@ def postprocess_reg(pred, data_module, out_cle, out_pse):
         meta = meta_cache[uid]
         kw = dict(type=np.uint8, origin=meta["origin"][::-1], spacing=meta["spacing"][::-1],
                   direction=np.asarray(meta["direction"]).reshape(3, 3)[::-1].flatten().tolist())
-        for heat, folder in ((cle, out_cle), (pse, out_pse)):
-            full = np.zeros(orig)
-            full[sl] = heat[0, 0].cpu().numpy()
-            write_array_to_mha_itk(folder, [windowing(full, from_span=(0, 1)).astype(np.uint8)], [uid], **kw)
+        for full, folder in zip(heat, (out_cle, out_pse)):
+            write_array_to_mha_itk(folder, [full], [uid], **kw)
     return records
 
 

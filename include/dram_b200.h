@@ -218,6 +218,40 @@ int dram_resize_image(const float *x, float *out, const int32_t *d_idx, int32_t 
 int dram_resize_mask(const uint8_t *x, uint8_t *out, const int32_t *d_idx, int32_t D, int32_t H,
                      int32_t W, int32_t D2, int32_t H2, int32_t W2, void *stream);
 
+/* ---- f1: device pre-steps of SubtypingInference.get_data (dataset.py:66-80) ---- */
+/*
+ * dram_mask_bbox: bbox (device int32[6]) = {zmin, zmax+1, ymin, ymax+1, xmin, xmax+1} of mask != 0
+ * ({D,0,H,0,W,0} for an empty mask) — scipy.ndimage.find_objects(mask > 0)[0] of utils.py:54.  The
+ * caller grows it by ceil(border / spacing) and clips (utils.py:55-60).
+ */
+int dram_mask_bbox(const uint8_t *mask, int32_t D, int32_t H, int32_t W, int32_t *bbox, void *stream);
+/*
+ * dram_lung_crop: for the crop window [z0,z0+cd) x [y0,y0+ch) x [x0,x0+cw) of a D x H x W scan
+ *   lung    = lobe > 0                                                   (dataset.py:67)
+ *   dlung   = binary_dilation(lung, 3x3x3 full structure, iterations=2)  (:68; a 5x5x5 box maximum
+ *             over the WHOLE volume with a zero border, not just the crop)
+ *   image_c = dlung ? scan : -2048                                        (:69, :71)
+ *   lung_c  = lung                                                        (:72, :77)
+ *   ess_c   = (image_c < -910) & lung                                     (:78)
+ * scan int16, lobe uint8 (labels), outputs int16 / uint8 / uint8 of the crop size; workspace of
+ * dram_lung_crop_workspace_bytes(cd, ch, cw) bytes.  Bit-exact.
+ */
+size_t dram_lung_crop_workspace_bytes(int32_t cd, int32_t ch, int32_t cw);
+int dram_lung_crop(const int16_t *scan, const uint8_t *lobe, int32_t D, int32_t H, int32_t W, int32_t z0,
+                   int32_t y0, int32_t x0, int32_t cd, int32_t ch, int32_t cw, int16_t *image_c,
+                   uint8_t *lung_c, uint8_t *ess_c, void *workspace, void *stream);
+
+/* ---- f2: device post-processing of one scan (processor.py:111-158, utils.py:28-37) ---- */
+/*
+ * out uint8 [OD][OH][OW] = 0 outside the crop window; inside,
+ *   trunc(clip(trilinear_align_corners(map [d][h][w] -> [cd][ch][cw]), 0, 1) * 255.0)   (fp64 product)
+ * i.e. F.interpolate(size=recon_size) -> paste into np.zeros(original_size) -> windowing((0,1)) ->
+ * astype(uint8), in one pass; only uint8 has to leave the GPU.
+ */
+int dram_heatmap_u8(const float *map, int32_t d, int32_t h, int32_t w, uint8_t *out, int32_t OD, int32_t OH,
+                    int32_t OW, int32_t z0, int32_t y0, int32_t x0, int32_t cd, int32_t ch, int32_t cw,
+                    void *stream);
+
 /* ---- layout helpers ---------------------------------------------------- */
 /* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
 int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,

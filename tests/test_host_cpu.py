@@ -198,3 +198,23 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert res["shards"] == [[0, 2, 4], [1, 3, 0]] and res["max"] == 2.0
     assert set(sum(res["shards"], [])) == set(range(5))
+
+
+def test_grow_bbox_equals_reference_find_crops():
+    """dataset.grow_bbox (host half of row f1) == utils.find_crops of the reference (oracle restatement)."""
+    import numpy as np
+
+    from dram_b200.dataset import grow_bbox
+    from oracle import pipeline_oracle as P
+
+    rng = np.random.default_rng(0)
+    for spacing in [(1.0, 1.0, 1.0), (2.5, 0.7, 0.7), (0.5, 3.0, 1.3)]:
+        mask = np.zeros((30, 40, 50), bool)
+        lo = rng.integers(0, 10, 3)
+        hi = lo + rng.integers(1, 20, 3)
+        mask[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = True
+        nz = np.nonzero(mask)
+        bbox = [v for ax in range(3) for v in (nz[ax].min(), nz[ax].max() + 1)]
+        want = [(s.start, s.stop) for s in P.find_crops(mask, spacing, 5)]
+        assert grow_bbox(bbox, mask.shape, spacing, 5) == want
+        assert grow_bbox(bbox, mask.shape, spacing, 0) == [(bbox[0], bbox[1]), (bbox[2], bbox[3]), (bbox[4], bbox[5])]
