@@ -381,6 +381,19 @@ def main():
     res_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
     from dram_b200.models import DevicePrefetcher
 
+    # host->device bandwidth of this box for the same buffers (explains e2e when the PCIe link is the limit)
+    probe_dst = {k: torch.empty_like(v, device=device) for k, v in host.items()}
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    p0.record()
+    for _ in range(3):
+        for k, v in host.items():
+            probe_dst[k].copy_(v, non_blocking=True)
+    p1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del probe_dst
+
     def e2e_pass(n_steps):
         # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's
         # side stream, overlapping the previous step's kernels) and reads its scores back before the next
@@ -404,6 +417,7 @@ def main():
     e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": e2e_ms,
+           "h2d_gbs_idle_probe": h2d_gbs,
            "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> "
                   "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered)"}
 
@@ -448,7 +462,7 @@ def main():
                    "storage_dtype": str(eng.act_dtype)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
     print(json.dumps(line), flush=True)
 

@@ -14,8 +14,8 @@ for w in $WHAT; do
     launches)
       ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}.csv \
           $BENCH > gpurun_out/ncu_launches_${TAG}.log 2>&1 ;;
-    conv)  # one full step of conv launches (the second timed step; 39 conv launches per step)
-      ncu --set full --clock-control none -k regex:'conv3d_' -s 156 -c 39 -o /tmp/conv_${TAG} \
+    conv)  # one full step of conv launches (the second timed step; 38 conv launches per step)
+      ncu --set full --clock-control none -k regex:'conv3d_' -s 152 -c 38 -o /tmp/conv_${TAG} \
           $BENCH > gpurun_out/ncu_conv_${TAG}.log 2>&1
       ncu -i /tmp/conv_${TAG}.ncu-rep --page raw --csv > gpurun_out/conv_${TAG}.raw.csv ;;
     stem)
