@@ -282,7 +282,7 @@ def cpu_baseline(module, dims, arch=ARCH, budget_s=30.0):
     return {"value": 1.0 / t, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -315,12 +315,26 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------
 # main arm
 # --------------------------------------------------------------------------------------------
+class _StdoutToStderr:
+    """Everything libraries print to fd 1 while the benchmark runs (NCCL's version banner, ...) goes to
+    stderr; `emit()` writes the one JSON line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,8 +348,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = _StdoutToStderr()
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, out)
         return
 
     rank, local, world = dist_setup(args.gpus)
@@ -450,6 +465,11 @@ def main():
                 "peak_source": peak_src, "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                 "share_of_step": conv_ms / ms_per_step}
 
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -464,7 +484,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 if __name__ == "__main__":
