@@ -348,9 +348,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    out = _StdoutToStderr()
+    sink = _StdoutToStderr()
     if args.impl == "reference":
-        run_reference_arm(args, out)
+        run_reference_arm(args, sink)
         return
 
     rank, local, world = dist_setup(args.gpus)
@@ -484,7 +484,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
-    out.emit(json.dumps(line))
+    sink.emit(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdram_b200.so")
+# DRAM_B200_LIB selects another build of the same sources (kernel tuning experiments, build.build_variant)
+LIB_PATH = os.environ.get("DRAM_B200_LIB") or os.path.join(HERE, "libdram_b200.so")
 
 DRAM_OK = 0
 DRAM_DTYPE_BF16 = 0
@@ -36,6 +37,7 @@ class ConvDesc(C.Structure):
         ("tw", C.c_int32), ("th", C.c_int32), ("td", C.c_int32),
         ("dtype", C.c_int32),
         ("algo", C.c_int32),
+        ("src1_up2x", C.c_int32),
     ]
 
 

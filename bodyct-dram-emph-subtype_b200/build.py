@@ -36,6 +36,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out_path, defines):
+    """Dev tool: the same sources with extra -D flags into another file (kernel tuning experiments;
+    load it with DRAM_B200_LIB=<path>)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-I", INCLUDE, "-I", CSRC] + sources() + ["-o", out_path]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out_path
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB

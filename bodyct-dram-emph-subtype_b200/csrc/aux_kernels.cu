@@ -235,8 +235,8 @@ upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, i
       for (int q = 0; q < 4; ++q) {
         const float2 fa = unpack2t<F16>(a_[q]), fb = unpack2t<F16>(b_[q]), fc = unpack2t<F16>(c_[q]),
                      fd = unpack2t<F16>(d_[q]);
-        P[2 * q + 0] = ih.w0 * (iw.w0 * fa.x + iw.w1 * fb.x) + ih.w1 * (iw.w0 * fc.x + iw.w1 * fd.x);
-        P[2 * q + 1] = ih.w0 * (iw.w0 * fa.y + iw.w1 * fb.y) + ih.w1 * (iw.w0 * fc.y + iw.w1 * fd.y);
+        P[2 * q + 0] = bilerp_hw(fa.x, fb.x, fc.x, fd.x, iw.w0, iw.w1, ih.w0, ih.w1);
+        P[2 * q + 1] = bilerp_hw(fa.y, fb.y, fc.y, fd.y, iw.w0, iw.w1, ih.w0, ih.w1);
       }
     };
     const int xd0 = ck * UP_DCHUNK, xd1 = min(od, xd0 + UP_DCHUNK);
@@ -254,10 +254,11 @@ upsample2x_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ out, int n, i
         for (int j = 0; j < 8; ++j) P0[j] = P1[j];
         if (cur + 1 < d) plane_val(cur + 1, P1);  // at the last plane i1 == i0 and P1 == P0 already
       }
-      *o = make_uint4(pack2t<F16>(id.w0 * P0[0] + id.w1 * P1[0], id.w0 * P0[1] + id.w1 * P1[1]),
-                      pack2t<F16>(id.w0 * P0[2] + id.w1 * P1[2], id.w0 * P0[3] + id.w1 * P1[3]),
-                      pack2t<F16>(id.w0 * P0[4] + id.w1 * P1[4], id.w0 * P0[5] + id.w1 * P1[5]),
-                      pack2t<F16>(id.w0 * P0[6] + id.w1 * P1[6], id.w0 * P0[7] + id.w1 * P1[7]));
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o8[j] = lerp_d(P0[j], P1[j], id.w0, id.w1);
+      *o = make_uint4(pack2t<F16>(o8[0], o8[1]), pack2t<F16>(o8[2], o8[3]), pack2t<F16>(o8[4], o8[5]),
+                      pack2t<F16>(o8[6], o8[7]));
       o += ostride;
     }
   }

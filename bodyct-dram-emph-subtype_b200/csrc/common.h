@@ -67,6 +67,14 @@ __device__ __forceinline__ LinIdx lin_index_ac(int dst, float scale, int in_size
   r.w0 = 1.0f - l1;
   return r;
 }
+// Trilinear pieces in ATen's nesting order with explicit roundings, shared by K4 and the conv kernel that
+// up-samples its first source on the fly, so that both produce bit-identical values.
+__device__ __forceinline__ float bilerp_hw(float a, float b, float c, float d, float w0, float w1, float h0, float h1) {
+  return __fmaf_rn(h1, __fmaf_rn(w1, d, __fmul_rn(w0, c)), __fmul_rn(h0, __fmaf_rn(w1, b, __fmul_rn(w0, a))));
+}
+__device__ __forceinline__ float lerp_d(float p0, float p1, float d0, float d1) {
+  return __fmaf_rn(d1, p1, __fmul_rn(d0, p0));
+}
 __host__ __device__ __forceinline__ float ac_scale(int in_size, int out_size) {
   return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;
 }

@@ -19,8 +19,14 @@
 //     tile is read once for up to 192 output channels.  A weight stage therefore holds the three kd taps
 //     of one (kh,kw).
 //
-// Roles (224 threads): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 MMA issuer (owns TMEM),
-// warp 6 lane 0 weight producer.  Work items = (column, group of 4 planes); every CTA takes a
+//   * UP variant (decoder stages us1.0 / us2.0, med3d.py:83-89): source 1 is given at HALF resolution and
+//     the x2 trilinear (align_corners=True) up-sampling happens inside the kernel: the low-resolution
+//     patch under a plane (<= 11 x 7 voxels x 64 channels per source plane) streams through a small TMA
+//     ring, four extra warps interpolate it into the plane slot in the SWIZZLE_128B layout with the very
+//     arithmetic of K4 (bit-identical values), and the up-sampled tensor is never written to HBM.
+//
+// Roles (224 threads; UP: 352): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 MMA issuer (owns TMEM),
+// warp 6 lane 0 weight producer, UP: warps 7-10 interpolate.  Work items = (column, group of 4 planes); every CTA takes a
 // contiguous range of items (D fastest), so consecutive groups of a column reuse two resident planes.
 #include "conv_plan.h"
 
@@ -30,19 +36,34 @@ static constexpr int SL_W = 8, SL_H = 16, SL_GROUP = 4;      // slab = 8 x 16 vo
 static constexpr int PL_W = SL_W + 2, PL_H = SL_H + 2;       // input plane with halo
 static constexpr int PLANE_BYTES = PL_W * PL_H * 128;        // 23040
 static constexpr int PLANE_PITCH = 23 * 1024;                // slot pitch, 1 KiB aligned for SWIZZLE_128B
-static constexpr int RING = 7;
+#ifndef DRAM_SLAB_RING
+#define DRAM_SLAB_RING 7
+#endif
+static constexpr int RING = DRAM_SLAB_RING;
+static constexpr int RING_UP = 6;                            // plane slots of the UP variant
+static constexpr int LP_W = 7, LP_H = 11;                    // low-resolution patch under a 10 x 18 plane
+static constexpr int LP_BYTES = LP_W * LP_H * 128;           // 9856
+static constexpr int LP_PITCH = 10 * 1024;
+static constexpr int LP_RING = 3;
+static constexpr int UP_WARP0 = 7, UP_THREADS = 128;
 static constexpr int ITEM_PLANES = SL_GROUP + 2;             // 6 input planes feed 4 output planes
 static constexpr int SL_THREADS = 224;
 static constexpr int SL_A_WARP = 4, SL_MMA_WARP = 5, SL_B_WARP = 6;
 static constexpr int SL_BLOCK_K = 64;
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool UP = false>
 struct SlabCfg {
+  static constexpr int RING_ = UP ? RING_UP : RING;
+  static constexpr int THREADS = UP ? SL_THREADS + UP_THREADS : SL_THREADS;
   static constexpr int B_BLOCK_BYTES = BLOCK_N * 128;       // one tap: Cout rows x 64 channels
   static constexpr int B_STAGE_BYTES = 3 * B_BLOCK_BYTES;   // [kd=2; kd=1; kd=0] of one (kh,kw)
-  static constexpr int B_STAGES = BLOCK_N == 64 ? 2 : 4;
+#ifndef DRAM_SLAB_BSTAGES64
+#define DRAM_SLAB_BSTAGES64 2
+#endif
+  static constexpr int B_STAGES = BLOCK_N == 64 ? DRAM_SLAB_BSTAGES64 : 4;
   static constexpr int TMEM_COLS = 2 * SL_GROUP * BLOCK_N;  // 512 (N=64) / 256 (N=32)
-  static constexpr int SMEM_BYTES = 1024 + RING * PLANE_PITCH + B_STAGES * B_STAGE_BYTES + 256;
+  static constexpr int LP_TOTAL = UP ? LP_RING * LP_PITCH : 0;
+  static constexpr int SMEM_BYTES = 1024 + RING_ * PLANE_PITCH + B_STAGES * B_STAGE_BYTES + LP_TOTAL + 256;
 };
 
 struct SlabItem {
@@ -73,12 +94,21 @@ __device__ __forceinline__ uint64_t make_sw128_desc_sbo(uint32_t smem_addr, uint
   return d;
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(SL_THREADS, 1)
+// Low-resolution source range [lo, hi] that the output range [o_lo, o_hi] (clipped to the tensor) reads.
+__device__ __forceinline__ int up_src_lo(int o_lo, float scale, int in_size) {
+  return lin_index_ac(o_lo < 0 ? 0 : o_lo, scale, in_size).i0;
+}
+__device__ __forceinline__ int up_src_hi(int o_hi, int out_size, float scale, int in_size) {
+  return lin_index_ac(o_hi > out_size - 1 ? out_size - 1 : o_hi, scale, in_size).i1;
+}
+
+template <int BLOCK_N, bool UP>
+__global__ void __launch_bounds__((SlabCfg<BLOCK_N, UP>::THREADS), 1)
 conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
                    const __grid_constant__ CUtensorMap map_w, const __grid_constant__ SlabParams p) {
-  using Cfg = SlabCfg<BLOCK_N>;
+  using Cfg = SlabCfg<BLOCK_N, UP>;
   constexpr int B_STAGES = Cfg::B_STAGES;
+  constexpr int RING = Cfg::RING_;  // shadows the namespace constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + RING * PLANE_PITCH;
@@ -92,6 +122,11 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   auto tmem_full = [&](int a) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + a); };
   auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * RING + 2 * B_STAGES + 4);
+  // UP only: low-resolution plane ring behind the barriers' 256-byte block
+  const uint32_t lp_base = bar_base + 256u;
+  auto lp_addr = [&](int s) { return lp_base + (uint32_t)s * LP_PITCH; };
+  auto lp_full = [&](int s) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + 5 + s); };
+  auto lp_empty = [&](int s) { return bar_base + 8u * (2 * RING + 2 * B_STAGES + 5 + LP_RING + s); };
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -109,6 +144,11 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       mbar_init(tmem_full(a), 1);
       mbar_init(tmem_empty(a), 128);
     }
+    if (UP)
+      for (int s = 0; s < LP_RING; ++s) {
+        mbar_init(lp_full(s), 1);
+        mbar_init(lp_empty(s), UP_THREADS);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == SL_MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -127,16 +167,39 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   // contiguous, balanced range of work items for this CTA
   const int item_begin = (int)(((long long)blockIdx.x * p.items_total) / gridDim.x);
   const int item_end = (int)(((long long)(blockIdx.x + 1) * p.items_total) / gridDim.x);
-  const bool single_chunk = p.chunks_total == 1;
+  const bool single_chunk = !UP && p.chunks_total == 1;  // UP layers never reuse planes across items
 
   if (warp == SL_A_WARP) {
     if (lane == 0) {
       unsigned seq_end = 0;
+      unsigned lseq = 0;  // UP: running index of low-resolution planes through the LP ring
       for (int item = item_begin; item < item_end; ++item) {
         const SlabItem it = decode_item(p, item);
         for (int c = 0; c < p.chunks_total; ++c) {
           const bool reuse = single_chunk && item > item_begin && it.g > 0;
           const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
+          seq_end = seq_base + ITEM_PLANES;
+          if (UP && c < p.chunks1) {
+            // the interpolating warps fill the plane slots of this chunk; feed them the low-resolution
+            // planes under output planes q0-1 .. q0+4, in order
+            const int zl0 = up_src_lo(it.q0 - 1, p.up_sd, p.Dl);
+            const int zl1 = up_src_hi(it.q0 + SL_GROUP, p.D, p.up_sd, p.Dl);
+            const int hl0 = up_src_lo(it.h0 - 1, p.up_sh, p.Hl), wl0 = up_src_lo(it.w0 - 1, p.up_sw, p.Wl);
+            for (int zl = zl0; zl <= zl1; ++zl, ++lseq) {
+              const int ls = lseq % LP_RING;
+              mbar_wait(lp_empty(ls), ((lseq / LP_RING) & 1u) ^ 1u);
+              mbar_expect_tx(lp_full(ls), LP_BYTES);
+              tma_load_5d(lp_addr(ls), &map_a1, lp_full(ls), c * SL_BLOCK_K, wl0, hl0, zl, it.sample);
+            }
+            // The plane slots of this chunk are filled by the interpolating warps.  mbarrier waits only
+            // tell phases apart by parity, so every agent that fills plane slots has to observe every
+            // hand-back of every slot, or it could run two phases ahead and take a slot that is still in use.
+            for (int j = 0; j < ITEM_PLANES; ++j) {
+              const unsigned seq = seq_base + j;
+              mbar_wait(plane_empty(seq % RING), ((seq / RING) & 1u) ^ 1u);
+            }
+            continue;
+          }
           for (int j = reuse ? 2 : 0; j < ITEM_PLANES; ++j) {
             const unsigned seq = seq_base + j;
             const int slot = seq % RING;
@@ -149,7 +212,6 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               tma_load_5d(plane_addr(slot), &map_a2, plane_full(slot), (c - p.chunks1) * SL_BLOCK_K, it.w0 - 1,
                           it.h0 - 1, it.q0 - 1 + j, it.sample);
           }
-          seq_end = seq_base + ITEM_PLANES;
         }
       }
     }
@@ -256,7 +318,96 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       }
     }
     __syncwarp();
-  } else {
+  } else if (UP && warp >= UP_WARP0) {
+    // ------------------------------- UP: interpolating warps -------------------------------
+    // Output plane z of the column = 18 x 10 voxel rows of 64 channels; a thread builds 16-byte chunks
+    // (8 channels) of rows: trilinear of 8 low-resolution voxels read from the LP ring, same fp32 operation
+    // order as K4, rounded once to the storage type, stored at the SWIZZLE_128B position the UMMA view expects.
+    const int tid = threadIdx.x - UP_WARP0 * 32;
+    const int is_f16 = p.epi.is_f16;
+    unsigned seq_end = 0, lseq_base = 0;
+    for (int item = item_begin; item < item_end; ++item) {
+      const SlabItem it = decode_item(p, item);
+      for (int c = 0; c < p.chunks_total; ++c) {
+        const unsigned seq_base = seq_end;  // UP layers have more than one chunk: no plane reuse across items
+        seq_end = seq_base + ITEM_PLANES;
+        if (c >= p.chunks1) {  // TMA-filled chunk: only observe the hand-backs (see the producer)
+          for (int j = 0; j < ITEM_PLANES; ++j) {
+            const unsigned seq = seq_base + j;
+            mbar_wait(plane_empty(seq % RING), ((seq / RING) & 1u) ^ 1u);
+          }
+          continue;
+        }
+        const int zl0 = up_src_lo(it.q0 - 1, p.up_sd, p.Dl);
+        const int zl1 = up_src_hi(it.q0 + SL_GROUP, p.D, p.up_sd, p.Dl);
+        const int hl0 = up_src_lo(it.h0 - 1, p.up_sh, p.Hl), wl0 = up_src_lo(it.w0 - 1, p.up_sw, p.Wl);
+        int released = zl0;  // low-resolution planes below this index have been handed back
+        for (int j = 0; j < ITEM_PLANES; ++j) {
+          const unsigned seq = seq_base + j;
+          const int slot = seq % RING;
+          const int z = it.q0 - 1 + j;
+          const bool zok = z >= 0 && z < p.D;
+          mbar_wait(plane_empty(slot), ((seq / RING) & 1u) ^ 1u);
+          LinIdx id = {0, 0, 0.0f, 0.0f};
+          uint32_t lp0 = 0, lp1 = 0;
+          if (zok) {
+            id = lin_index_ac(z, p.up_sd, p.Dl);
+            // planes below id.i0 are not read any more
+            for (; released < id.i0; ++released) mbar_arrive(lp_empty((lseq_base + (unsigned)(released - zl0)) % LP_RING));
+            const unsigned s0 = lseq_base + (unsigned)(id.i0 - zl0), s1 = lseq_base + (unsigned)(id.i1 - zl0);
+            mbar_wait(lp_full(s0 % LP_RING), (s0 / LP_RING) & 1u);
+            mbar_wait(lp_full(s1 % LP_RING), (s1 / LP_RING) & 1u);
+            lp0 = lp_addr(s0 % LP_RING);
+            lp1 = lp_addr(s1 % LP_RING);
+          }
+          const uint32_t dst0 = plane_addr(slot);
+#pragma unroll 1
+          for (int task = tid; task < PL_W * PL_H * 8; task += UP_THREADS) {
+            const int r = task >> 3, c16 = task & 7;
+            const int ph = r / PL_W, pw = r - ph * PL_W;
+            const int oh = it.h0 - 1 + ph, ow = it.w0 - 1 + pw;
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+            if (zok && oh >= 0 && oh < p.H && ow >= 0 && ow < p.W) {
+              const LinIdx ih = lin_index_ac(oh, p.up_sh, p.Hl), iw = lin_index_ac(ow, p.up_sw, p.Wl);
+              const uint32_t o00 = (uint32_t)(((ih.i0 - hl0) * LP_W + (iw.i0 - wl0)) * 128 + c16 * 16);
+              const uint32_t o01 = (uint32_t)(((ih.i0 - hl0) * LP_W + (iw.i1 - wl0)) * 128 + c16 * 16);
+              const uint32_t o10 = (uint32_t)(((ih.i1 - hl0) * LP_W + (iw.i0 - wl0)) * 128 + c16 * 16);
+              const uint32_t o11 = (uint32_t)(((ih.i1 - hl0) * LP_W + (iw.i1 - wl0)) * 128 + c16 * 16);
+              uint32_t a0[4], b0[4], c0[4], d0[4], a1[4], b1[4], c1[4], d1[4];
+              auto lds = [](uint32_t addr, uint32_t (&v)[4]) {
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                             : "r"(addr));
+              };
+              lds(lp0 + o00, a0); lds(lp0 + o01, b0); lds(lp0 + o10, c0); lds(lp0 + o11, d0);
+              lds(lp1 + o00, a1); lds(lp1 + o01, b1); lds(lp1 + o10, c1); lds(lp1 + o11, d1);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 fa0 = unpack2(a0[q], is_f16), fb0 = unpack2(b0[q], is_f16), fc0 = unpack2(c0[q], is_f16),
+                             fd0 = unpack2(d0[q], is_f16);
+                const float2 fa1 = unpack2(a1[q], is_f16), fb1 = unpack2(b1[q], is_f16), fc1 = unpack2(c1[q], is_f16),
+                             fd1 = unpack2(d1[q], is_f16);
+                const float x0 = bilerp_hw(fa0.x, fb0.x, fc0.x, fd0.x, iw.w0, iw.w1, ih.w0, ih.w1);
+                const float x1 = bilerp_hw(fa1.x, fb1.x, fc1.x, fd1.x, iw.w0, iw.w1, ih.w0, ih.w1);
+                const float y0 = bilerp_hw(fa0.y, fb0.y, fc0.y, fd0.y, iw.w0, iw.w1, ih.w0, ih.w1);
+                const float y1 = bilerp_hw(fa1.y, fb1.y, fc1.y, fd1.y, iw.w0, iw.w1, ih.w0, ih.w1);
+                o[q] = pack2(lerp_d(x0, x1, id.w0, id.w1), lerp_d(y0, y1, id.w0, id.w1), is_f16);
+              }
+            }
+            const uint32_t dst = dst0 + (uint32_t)(r * 128) + (uint32_t)((c16 ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(UP_THREADS) : "memory");
+          if (tid == 0) mbar_arrive(plane_full(slot));
+        }
+        // hand back whatever is left of this chunk's low-resolution planes
+        for (; released <= zl1; ++released) mbar_arrive(lp_empty((lseq_base + (unsigned)(released - zl0)) % LP_RING));
+        lseq_base += (unsigned)(zl1 - zl0 + 1);
+      }
+    }
+  } else if (warp < 4) {
     // ------------------------------- epilogue warps 0..3 -------------------------------
     const int row = warp * 32 + lane;
     const int lw = row & (SL_W - 1);
@@ -279,7 +430,9 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
           tmem_wait_ld();
+#ifndef DRAM_SLAB_EXPERIMENT_NO_EPILOGUE  // diagnostic builds only: results are wrong without it
           if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res_row);
+#endif
         }
       }
       tcgen05_fence_before();
@@ -307,12 +460,37 @@ int slab_plan_supported(const dram_conv_desc *d) {
          d->dh == 1 && d->dw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && (d->cout == 32 || d->cout == 64);
 }
 
-template <int BN>
+template <int BN, bool UP>
 static int slab_set_attr() {
-  return check_cuda(cudaFuncSetAttribute(conv3d_slab_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SlabCfg<BN>::SMEM_BYTES),
+  return check_cuda(cudaFuncSetAttribute(conv3d_slab_kernel<BN, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SlabCfg<BN, UP>::SMEM_BYTES),
                     "cudaFuncSetAttribute(conv3d_slab_kernel)");
 }
+
+// ATen's align_corners source index on the host (same fp32 arithmetic as lin_index_ac).
+static void host_lin_index(int dst, float scale, int in_size, int *i0, int *i1) {
+  const float real = scale * (float)dst;
+  int a = (int)real;
+  if (a > in_size - 1) a = in_size - 1;
+  *i0 = a;
+  *i1 = a + ((a < in_size - 1) ? 1 : 0);
+}
+// Largest low-resolution extent read by any window of `win` consecutive outputs starting at k*step - 1.
+static int max_src_span(int out_size, int in_size, int step, int win) {
+  const float scale = ac_scale(in_size, out_size);
+  int worst = 0;
+  for (int o0 = -1; o0 < out_size; o0 += step) {
+    int lo0, lo1, hi0, hi1;
+    const int a = o0 < 0 ? 0 : o0, b = o0 + win - 1 > out_size - 1 ? out_size - 1 : o0 + win - 1;
+    host_lin_index(a, scale, in_size, &lo0, &lo1);
+    host_lin_index(b, scale, in_size, &hi0, &hi1);
+    if (hi1 - lo0 + 1 > worst) worst = hi1 - lo0 + 1;
+  }
+  return worst;
+}
+
+int encode_act_map_plain(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c, int box_c, int bw,
+                         int bh, int is_f16);
 
 int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1, const void *src2,
                    const void *weight, const EpiParams &epi) {
@@ -332,14 +510,32 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
   sp.chunks_total = (d->c1 + d->c2) / SL_BLOCK_K;
   const char *knob = getenv("DRAM_B200_DESC_BASE_OFFSET");
   sp.desc_base_offset_mode = knob ? atoi(knob) : 0;
+  sp.up2x = d->src1_up2x ? 1 : 0;
+  if (sp.up2x) {
+    if (d->cout != 64 || d->c2 <= 0 || (d->di & 1) || (d->hi & 1) || (d->wi & 1)) {
+      set_error("conv3d: src1_up2x needs cout == 64, a second source and even D, H, W (got cout %d, c2 %d, %dx%dx%d)",
+                d->cout, d->c2, d->di, d->hi, d->wi);
+      return DRAM_E_ARG;
+    }
+    sp.Dl = d->di / 2; sp.Hl = d->hi / 2; sp.Wl = d->wi / 2;
+    sp.up_sd = ac_scale(sp.Dl, d->di); sp.up_sh = ac_scale(sp.Hl, d->hi); sp.up_sw = ac_scale(sp.Wl, d->wi);
+    if (max_src_span(d->hi, sp.Hl, SL_H, PL_H) > LP_H || max_src_span(d->wi, sp.Wl, SL_W, PL_W) > LP_W) {
+      set_error("conv3d: src1_up2x low-resolution patch exceeds %dx%d for %dx%d planes", LP_H, LP_W, d->hi, d->wi);
+      return DRAM_E_ARG;
+    }
+  }
   sp.epi = epi;
   pl->block_n = d->cout;
-  pl->stages = RING;
+  pl->stages = sp.up2x ? RING_UP : RING;
   pl->m_tiles = sp.items_total * SL_GROUP;
   pl->n_tiles = 1;
   const int64_t ktot = 27LL * (d->c1 + d->c2);
-  int rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, SL_BLOCK_K, PL_W, PL_H, 1, 1, 1, 1,
-                          epi.is_f16);
+  int rc;
+  if (sp.up2x)
+    rc = encode_act_map_plain(&pl->map_a1, src1, d->n, sp.Dl, sp.Hl, sp.Wl, d->c1, SL_BLOCK_K, LP_W, LP_H, epi.is_f16);
+  else
+    rc = encode_act_map(&pl->map_a1, src1, d->n, d->di, d->hi, d->wi, d->c1, SL_BLOCK_K, PL_W, PL_H, 1, 1, 1, 1,
+                        epi.is_f16);
   if (rc == DRAM_OK) {
     if (d->c2 > 0)
       rc = encode_act_map(&pl->map_a2, src2, d->n, d->di, d->hi, d->wi, d->c2, SL_BLOCK_K, PL_W, PL_H, 1, 1, 1, 1,
@@ -349,12 +545,15 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
   }
   if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, d->cout, epi.is_f16);
   if (rc == DRAM_OK) {
-    if (d->cout == 64) {
+    if (sp.up2x) {
+      pl->smem_bytes = SlabCfg<64, true>::SMEM_BYTES;
+      rc = slab_set_attr<64, true>();
+    } else if (d->cout == 64) {
       pl->smem_bytes = SlabCfg<64>::SMEM_BYTES;
-      rc = slab_set_attr<64>();
+      rc = slab_set_attr<64, false>();
     } else {
       pl->smem_bytes = SlabCfg<32>::SMEM_BYTES;
-      rc = slab_set_attr<32>();
+      rc = slab_set_attr<32, false>();
     }
   }
   return rc;
@@ -362,11 +561,14 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
 
 int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
   if (pl->sp.items_total < ctas) ctas = pl->sp.items_total;
-  dim3 grid(ctas), block(SL_THREADS);
-  if (pl->block_n == 64)
-    conv3d_slab_kernel<64><<<grid, block, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+  dim3 grid(ctas);
+  if (pl->sp.up2x)
+    conv3d_slab_kernel<64, true><<<grid, SlabCfg<64, true>::THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2,
+                                                                                          pl->map_w, pl->sp);
+  else if (pl->block_n == 64)
+    conv3d_slab_kernel<64, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
   else
-    conv3d_slab_kernel<32><<<grid, block, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+    conv3d_slab_kernel<32, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
   DRAM_CHECK_LAUNCH("conv3d_slab_kernel launch");
   return DRAM_OK;
 }

@@ -292,6 +292,29 @@ int encode_act_map(CUtensorMap *map, const void *base, int n, int d, int h, int 
   return DRAM_OK;
 }
 
+// NDHWC activation tensor, un-swizzled rows of box_c channels: box = box_c x bw x bh voxels of one plane.
+int encode_act_map_plain(CUtensorMap *map, const void *base, int n, int d, int h, int w, int c, int box_c, int bw,
+                         int bh, int is_f16) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return DRAM_E_DRIVER;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)d, (cuuint64_t)n};
+  cuuint64_t gstr[4] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2,
+                        (cuuint64_t)d * h * w * c * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                   const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(plain activation %dx%dx%dx%dx%d box %dx%d) -> %d", n, d, h, w, c, bw, bh, (int)r);
+    return DRAM_E_DRIVER;
+  }
+  return DRAM_OK;
+}
+
 int encode_weight_map(CUtensorMap *map, const void *base, int cout, int64_t ktot, int block_n, int is_f16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -435,6 +458,11 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   // ---- plane-ring kernel for 3x3x3 / stride 1 / dilation 1 / Cout <= 64 ----------------------
   const bool want_planes = d->algo == DRAM_CONV_ALGO_PLANES ||
                            (d->algo == DRAM_CONV_ALGO_AUTO && d->tw == 0 && slab_plan_supported(d));
+  if (d->src1_up2x && !(want_planes && slab_plan_supported(d))) {
+    delete pl;
+    set_error("conv3d: src1_up2x is implemented by the plane-ring kernel only (3x3x3, stride 1, dilation 1, cout 64)");
+    return DRAM_E_ARG;
+  }
   if (want_planes) {
     if (!slab_plan_supported(d)) {
       delete pl;

@@ -22,6 +22,10 @@ struct SlabParams {
   int cols_w, cols_h, groups_d, items_total;
   int chunks1, chunks_total;
   int desc_base_offset_mode;   // experiment knob for the UMMA descriptor base-offset field (0 = leave 0)
+  // source 1 given at half resolution and up-sampled x2 (trilinear, align_corners=True) by the kernel
+  int up2x;                    // 0 / 1
+  int Dl, Hl, Wl;              // low-resolution dims (D/2, H/2, W/2)
+  float up_sd, up_sh, up_sw;   // ATen source scales (Dl-1)/(D-1) ...
   EpiParams epi;
 };
 

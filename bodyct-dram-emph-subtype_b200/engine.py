@@ -88,10 +88,11 @@ class Med3DEngine:
 
     # ---------------------------------------------------------------- plan
     def _add_conv(self, name, x1, wb, *, x2=None, kernel=3, stride=1, dilation=1, padding=None, relu=True,
-                  residual=None, res_stride=1, heads=None, store_out=True, tile=None, flops=None):
+                  residual=None, res_stride=1, heads=None, store_out=True, tile=None, flops=None,
+                  upsample_x1=False):
         plan = ops.Conv3dPlan(x1, wb[0], wb[1], x2=x2, scale=wb[2], kernel=kernel, stride=stride, dilation=dilation,
                               padding=padding, relu=relu, residual=residual, res_stride=res_stride,
-                              heads=heads, store_out=store_out, tile=tile)
+                              heads=heads, store_out=store_out, tile=tile, upsample_x1=upsample_x1)
         fl = plan.flops if flops is None else flops
         self.conv_flops += fl
         self.steps.append(_Step(name, plan.run, fl))
@@ -167,16 +168,25 @@ class Med3DEngine:
                 inplanes = planes * e
             feats.append(cur)
         x1, x4 = feats[0], feats[3]
-        # ---- decoder
-        self.up1 = torch.empty((B, D2, H2, W2, x4.shape[4]), dtype=bf, device=dev)
-        self.steps.append(_Step("us1.upsample", lambda: ops.upsample2x(x4, out=self.up1)))
+        # ---- decoder.  The x2 trilinear up-sampling of each stage's input (med3d.py:83, 86) happens inside
+        # the first convolution of the stage (plane-ring kernel, UP variant): the up-sampled tensors are
+        # never written.  DRAM_B200_UPSAMPLE=separate keeps the K4 kernel + plain convolution for A/B runs.
+        fused_up = os.environ.get("DRAM_B200_UPSAMPLE", "fused").lower() != "separate"
         cb = m.us1.conv_blocks
-        t = self._add_conv("us1.0", self.up1, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1).out
+        if fused_up:
+            t = self._add_conv("us1.0", x4, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1, upsample_x1=True).out
+        else:
+            self.up1 = torch.empty((B, D2, H2, W2, x4.shape[4]), dtype=bf, device=dev)
+            self.steps.append(_Step("us1.upsample", lambda: ops.upsample2x(x4, out=self.up1)))
+            t = self._add_conv("us1.0", self.up1, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1).out
         xup1 = self._add_conv("us1.1", t, self._conv_bn("us1.1", cb[1][0], cb[1][1])).out
-        self.up2 = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
-        self.steps.append(_Step("us2.upsample", lambda: ops.upsample2x(xup1, out=self.up2)))
         cb = m.us2.conv_blocks
-        t = self._add_conv("us2.0", self.up2, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x).out
+        if fused_up:
+            t = self._add_conv("us2.0", xup1, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x, upsample_x1=True).out
+        else:
+            self.up2 = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
+            self.steps.append(_Step("us2.upsample", lambda: ops.upsample2x(xup1, out=self.up2)))
+            t = self._add_conv("us2.0", self.up2, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x).out
         xup2 = self._add_conv("us2.1", t, self._conv_bn("us2.1", cb[1][0], cb[1][1])).out
         # ---- us3 + heads fused
         head_ch = tuple(fc.weight.shape[0] for fc in m.fcs)

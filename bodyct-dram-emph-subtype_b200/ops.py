@@ -76,15 +76,19 @@ class Conv3dPlan:
     `residual` is NDHWC bf16 with `res_c <= Cout` channels read at `res_stride` (shortcut A).
     `heads = (head_w [sum_ch, 32] fp32, head_b [sum_ch] fp32, (ch0, ch1), sigmoid)` fuses the
     1x1x1 heads into the epilogue of a 32-channel conv.
+    `upsample_x1=True`: x1 is [N, D/2, H/2, W/2, C1] and is up-sampled x2 (trilinear, align_corners=True,
+    med3d.py:83-86) inside the kernel; x2 (required) is the full-resolution skip tensor.
     """
 
     def __init__(self, x1, weight, bias, *, x2=None, scale=None, kernel=3, stride=1, dilation=1,
                  padding=None, relu=True, residual=None, res_stride=1, heads=None, store_out=True,
-                 out=None, tile=None, algo="auto"):
+                 out=None, tile=None, algo="auto", upsample_x1=False):
         lib = _capi.load()
         _need16(x1, "conv3d x1", 5)
         adt = x1.dtype
         n, di, hi, wi, c1 = x1.shape
+        if upsample_x1:  # x1 is the half-resolution tensor; the kernel up-samples it x2 on the fly
+            di, hi, wi = 2 * di, 2 * hi, 2 * wi
         c2 = 0
         if x2 is not None:
             _need(x2, adt, "conv3d x2", 5)
@@ -115,6 +119,7 @@ class Conv3dPlan:
         d.relu = 1 if relu else 0
         d.dtype = ACT_DTYPES[adt]
         d.algo = _capi.CONV_ALGO[algo]
+        d.src1_up2x = 1 if upsample_x1 else 0
         if residual is not None:
             _need(residual, adt, "conv3d residual", 5)
             d.res_c = residual.shape[4]

@@ -35,7 +35,7 @@ extern "C" {
 #define DRAM_E_LAUNCH (-3)  /* CUDA launch / runtime error                  */
 #define DRAM_E_DRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
-#define DRAM_ABI_VERSION 2
+#define DRAM_ABI_VERSION 3
 
 /* 16-bit storage type of activations and packed weights (same layout, same tensor-core rate). */
 #define DRAM_DTYPE_BF16 0
@@ -100,6 +100,9 @@ typedef struct dram_conv_desc {
   int32_t tw, th, td;
   int32_t dtype;       /* DRAM_DTYPE_BF16 or DRAM_DTYPE_F16: type of src/weight/residual/out */
   int32_t algo;        /* DRAM_CONV_ALGO_*: AUTO picks PLANES when the shape allows it         */
+  int32_t src1_up2x;   /* 1: src1 is [n][di/2][hi/2][wi/2][c1] and is up-sampled x2 (trilinear,    */
+                       /* align_corners=True; med3d.py:83,86) inside the kernel; di,hi,wi stay the  */
+                       /* full-resolution dims.  PLANES kernel, cout == 64, c2 > 0 only             */
 } dram_conv_desc;
 
 typedef struct dram_conv_plan dram_conv_plan; /* opaque: tensor maps + launch geometry */

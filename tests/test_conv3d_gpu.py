@@ -265,3 +265,58 @@ def test_stem_fused_matches_unfold_route(cuda, lib):
     b = ops.stem_conv7(xc, ops.pack_stem_weight_fused(wgt.to(cuda), dtype=torch.float16), bias).float().cpu()
     torch.cuda.synchronize()
     assert (a - b).abs().max().item() <= 2.0 ** -9 * a.abs().max().item()
+
+
+UP_CASES = [
+    # (batch, full-res dims, c1 (up-sampled source), c2 (skip), max_ctas)
+    (1, (8, 16, 8), 64, 64, 0),
+    (2, (12, 36, 20), 128, 64, 0),
+    (1, (16, 32, 48), 64, 64, 3),
+    (1, (6, 18, 10), 192, 64, 2),
+    (1, (40, 20, 24), 64, 128, 5),
+]
+
+
+@pytest.mark.parametrize("case", range(len(UP_CASES)))
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conv_fused_upsample(cuda, lib, case, dt):
+    """Decoder stage (med3d.py:83-89): conv3x3x3(cat([upsample_x2_trilinear_ac(x), skip])).  The plane-ring
+    kernel that up-samples its first source on the fly must equal K4 + plain convolution bit for bit (same
+    fp32 operation order, one rounding to the storage type) and match torch within the conv tolerance."""
+    from dram_b200 import ops
+
+    global DT
+    DT = dt
+    n, dims, c1, c2, max_ctas = UP_CASES[case]
+    d, h, w = dims
+    g = torch.Generator().manual_seed(60 + case)
+    lo = _rand((n, c1, d // 2, h // 2, w // 2), g)
+    skip = _rand((n, c2, d, h, w), g)
+    wgt = _rand((64, c1 + c2, 3, 3, 3), g, scale=(27 * (c1 + c2)) ** -0.5)
+    bias = torch.randn(64, generator=g) * 0.1
+    lo_d, skip_d = ops.to_ndhwc_16(lo.to(cuda), dt), ops.to_ndhwc_16(skip.to(cuda), dt)
+    wp = ops.pack_conv_weight(wgt, dtype=dt).to(cuda)
+    fused = ops.Conv3dPlan(lo_d, wp, bias.to(cuda), x2=skip_d, upsample_x1=True)
+    assert fused.algo == "planes"
+    got = fused.run(max_ctas).clone()
+    up = ops.upsample2x(lo_d)
+    plain = ops.Conv3dPlan(up, wp, bias.to(cuda), x2=skip_d, algo="planes").run()
+    torch.cuda.synchronize()
+    assert torch.equal(got, plain), f"max diff {(got.float() - plain.float()).abs().max().item()}"
+    up_ref = ops.to_ncdhw_f32(up).cpu()  # the 16-bit rounded up-sampled tensor the convolution sees
+    ref = (F.conv3d(torch.cat([up_ref, skip], 1), wgt, None, padding=1) + bias.view(1, -1, 1, 1, 1)).relu()
+    _close(ops.to_ncdhw_f32(got).cpu(), ref, f"fused upsample conv {dims} {c1}+{c2}")
+
+
+def test_conv_fused_upsample_argument_errors(cuda, lib):
+    from dram_b200 import ops
+    from dram_b200._capi import DramError
+
+    lo = torch.zeros((1, 4, 8, 4, 64), dtype=torch.float16, device=cuda)
+    skip = torch.zeros((1, 8, 16, 8, 64), dtype=torch.float16, device=cuda)
+    b = torch.zeros(64, device=cuda)
+    with pytest.raises(DramError):   # no skip tensor
+        ops.Conv3dPlan(lo, torch.zeros((64, 27 * 64), dtype=torch.float16, device=cuda), b, upsample_x1=True)
+    with pytest.raises(DramError):   # cout 128 is not a plane-ring shape
+        ops.Conv3dPlan(lo, torch.zeros((128, 27 * 128), dtype=torch.float16, device=cuda),
+                       torch.zeros(128, device=cuda), x2=skip, upsample_x1=True)

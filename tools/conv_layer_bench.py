@@ -15,6 +15,7 @@ from dram_b200 import ops  # noqa: E402
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ALGO = sys.argv[3] if len(sys.argv) > 3 else "auto"
+ONLY = sys.argv[4].split(",") if len(sys.argv) > 4 else None  # substrings of layer names to keep
 DT = torch.float16
 dev = torch.device("cuda:0")
 
@@ -40,6 +41,8 @@ def main():
     tot_t = tot_f = 0.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, count, div, c1, c2, cout, k, s, dl, tile in LAYERS:
+        if ONLY and not any(o in name for o in ONLY):
+            continue
         dv = (div, div, div) if isinstance(div, int) else div
         dims = tuple(S // q for q in dv)
         k3 = (k, k, k) if isinstance(k, int) else k
