@@ -168,10 +168,12 @@ class Med3DEngine:
                 inplanes = planes * e
             feats.append(cur)
         x1, x4 = feats[0], feats[3]
-        # ---- decoder.  The x2 trilinear up-sampling of each stage's input (med3d.py:83, 86) happens inside
-        # the first convolution of the stage (plane-ring kernel, UP variant): the up-sampled tensors are
-        # never written.  DRAM_B200_UPSAMPLE=separate keeps the K4 kernel + plain convolution for A/B runs.
-        fused_up = os.environ.get("DRAM_B200_UPSAMPLE", "fused").lower() != "separate"
+        # ---- decoder.  Default: K4 up-samples each stage's input (med3d.py:83, 86) and the first convolution
+        # reads it next to the skip tensor.  DRAM_B200_UPSAMPLE=fused moves the up-sampling into that
+        # convolution (plane-ring kernel, UP variant; bit-identical results, the up-sampled tensors are never
+        # written) — measured slower on B200 (5.9 -> 7.4 ms per 256^3 volume): the interpolation of a chunk's
+        # planes cannot overlap the previous chunk's MMAs with only six plane slots, see DESIGN.md.
+        fused_up = os.environ.get("DRAM_B200_UPSAMPLE", "separate").lower() == "fused"
         cb = m.us1.conv_blocks
         if fused_up:
             t = self._add_conv("us1.0", x4, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1, upsample_x1=True).out
