@@ -14,11 +14,10 @@ typedef __nv_bfloat162 bf162;
 
 // Two packed 16-bit activations <-> fp32 for either storage type (f16 != 0: IEEE half, else bf16).
 __device__ __forceinline__ uint32_t pack2(float a, float b, int f16) {
-  if (f16) {
-    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
-    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
+  if (f16) {  // saturating conversion (F2FP.SATFINITE), no inf
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
   bf162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t *>(&h);
@@ -194,10 +193,9 @@ __device__ __forceinline__ float2 unpack2t(uint32_t u) {
 template <bool F16>
 __device__ __forceinline__ uint32_t pack2t(float a, float b) {
   if constexpr (F16) {
-    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
-    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   } else {
     const bf162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);

@@ -30,17 +30,26 @@ static constexpr int BLOCK_K = 64;        // bf16 channels per K-chunk == one 12
 static constexpr int UMMA_K = 16;         // K per tcgen05.mma for 16-bit inputs
 static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS_STAGED = 320;               // + warps 6-9: second half of the epilogue columns
 static constexpr int PRODUCER_WARP = 4;
 static constexpr int MMA_WARP = 5;
 
-template <int BLOCK_N>
+static constexpr int EPI_TILE_BYTES = BLOCK_M * 128;         // staged epilogue: 128 rows x 64 channels
+static constexpr int RES_BUFS = 4;                           // residual tiles in flight (DRAM latency ~ 3 groups)
+
+// STAGED: the epilogue goes through shared memory and TMA (coalesced stores, residual tiles loaded by TMA)
+// instead of one 16-byte global access per lane and row.  Used for the 1x1x1 convolutions of the bottleneck
+// blocks, which are bound by exactly those accesses (K is at most 32 chunks), with BLOCK_N <= 128 so that four
+// operand stages, two output tiles and four residual tiles fit in shared memory together.
+template <int BLOCK_N, bool STAGED = false>
 struct ConvCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4);
+  static constexpr int STAGES = STAGED ? 4 : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  // 1 KiB alignment slack + stages + barriers
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+  static constexpr int EPI_BYTES = STAGED ? (2 + RES_BUFS) * EPI_TILE_BYTES : 0;  // output + residual tiles
+  // 1 KiB alignment slack + stages + epilogue tiles + barriers
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
 
 struct TileCoord {
@@ -67,17 +76,22 @@ __device__ __forceinline__ bool tap_is_padding(int i0, int extent, int stride, i
   return (i0 + (extent - 1) * stride < 0) || (i0 >= in_size);
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, bool STAGED>
+__global__ void __launch_bounds__(STAGED ? NUM_THREADS_STAGED : NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
                    const __grid_constant__ CUtensorMap map_a2,
-                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                   const __grid_constant__ CUtensorMap map_res, const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BLOCK_N, STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1 KiB alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // STAGED: out[2], res[2] tiles of 16 KiB
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  auto out_tile = [&](int b) { return epi_base + (uint32_t)b * EPI_TILE_BYTES; };
+  auto res_tile = [&](int b) { return epi_base + (uint32_t)(2 + b) * EPI_TILE_BYTES; };
+  auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };  // b < RES_BUFS
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -96,8 +110,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 128);
+      mbar_init(tmem_empty_bar(a), STAGED ? 256 : 128);
     }
+    if (STAGED)
+      for (int b = 0; b < RES_BUFS; ++b) mbar_init(res_full(b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -105,6 +121,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
     prefetch_tensormap(&map_a1);
     prefetch_tensormap(&map_a2);
     prefetch_tensormap(&map_w);
+  }
+  if (STAGED && threadIdx.x == 0) {
+    prefetch_tensormap(&map_out);
+    prefetch_tensormap(&map_res);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -203,6 +223,63 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       }
     }
     __syncwarp();
+  } else if (STAGED) {
+    // ------------------------------- epilogue warps 0..3 and 6..9, staged through shared memory + TMA -------------
+    // Work unit = one 64-channel group of one tile ("group", gi counts them across this CTA's tiles).
+    // Thread 0 keeps RES_BUFS residual tiles in flight (TMA, res_full[gi % RES_BUFS]) and sends finished output
+    // tiles with TMA stores; the 256 threads meet at two named barriers per group (out tile free / written).
+    // Eight warps: warp w works on TMEM lane quarter w % 4 (rows 32*(w%4) ...), warps 0-3 on the first 32 columns of
+    // the group, warps 6-9 on the second 32.
+    constexpr int GROUPS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
+    const int quarter = warp & 3, half = warp < 4 ? 0 : 1;
+    const int row = quarter * 32 + lane;
+    const bool has_res = p.staged_res != 0;
+    const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total_groups = my_tiles * GROUPS;
+    auto issue_res = [&](int gi) {  // thread 0 only
+      if (!has_res || gi >= total_groups) return;
+      const int tile = blockIdx.x + (gi / GROUPS) * gridDim.x;
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int rb = gi % RES_BUFS;
+      mbar_expect_tx(res_full(rb), EPI_TILE_BYTES);
+      tma_load_5d(res_tile(rb), &map_res, res_full(rb), t.n0 + (gi % GROUPS) * 64, t.w0, t.h0, t.d0, t.sample);
+    };
+    if (threadIdx.x == 0)
+      for (int g0 = 0; g0 < RES_BUFS; ++g0) issue_res(g0);
+    int acc = 0, gi = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int g = 0; g < GROUPS; ++g, ++gi) {
+        const int b = gi & 1, rb = gi % RES_BUFS;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + half * 32), v);
+        if (has_res) mbar_wait(res_full(rb), (uint32_t)((gi / RES_BUFS) & 1));
+        // the store that last read out_tile(b) (group gi - 2) must be done with shared memory
+        if (threadIdx.x == 0) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        tmem_wait_ld();
+        epilogue_group_staged(p.epi, v, t.n0 + g * 64 + half * 32, row, half, res_tile(rb), has_res, out_tile(b));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) {
+          tma_store_5d(&map_out, out_tile(b), t.n0 + g * 64, t.w0, t.h0, t.d0, t.sample);
+          tma_store_commit();
+          issue_res(gi + RES_BUFS);  // res_tile(rb) has been read by everyone
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   } else {
     // ------------------------------- epilogue warps 0..3 -------------------------------
     const int row = warp * 32 + lane;  // TMEM lane == row of the 128-voxel tile
@@ -366,12 +443,23 @@ extern "C" int dram_conv3d_out_dims(const dram_conv_desc *d, int32_t *dout, int3
   return DRAM_OK;
 }
 
-template <int BN>
+template <int BN, bool STAGED>
 static int set_smem_attr() {
-  return check_cuda(cudaFuncSetAttribute(conv3d_umma_kernel<BN>,
+  return check_cuda(cudaFuncSetAttribute(conv3d_umma_kernel<BN, STAGED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ConvCfg<BN>::SMEM_BYTES),
+                                         ConvCfg<BN, STAGED>::SMEM_BYTES),
                     "cudaFuncSetAttribute(conv3d_umma_kernel)");
+}
+template <int BN, bool STAGED>
+static int fill_tile_cfg(dram_conv_plan *pl) {
+  pl->stages = ConvCfg<BN, STAGED>::STAGES;
+  pl->smem_bytes = ConvCfg<BN, STAGED>::SMEM_BYTES;
+  return set_smem_attr<BN, STAGED>();
+}
+template <int BN, bool STAGED>
+static void launch_tiles(const dram_conv_plan *pl, dim3 grid, cudaStream_t st) {
+  conv3d_umma_kernel<BN, STAGED><<<grid, STAGED ? NUM_THREADS_STAGED : NUM_THREADS, pl->smem_bytes, st>>>(
+      pl->map_a1, pl->map_a2, pl->map_w, pl->map_out, pl->map_res, pl->p);
 }
 
 extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,
@@ -539,12 +627,47 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
       pl->map_a2 = pl->map_a1;
   }
   if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, epi.is_f16);
+  // Staged (shared memory + TMA) epilogue for the 1x1x1 convolutions: they are bound by the epilogue's global
+  // accesses, which the direct path issues as one 16-byte access per lane and row.
+  const bool res_tma = d->res_c == d->cout && d->res_stride == 1 && d->res_d == Do && d->res_h == Ho && d->res_w == Wo;
+  const char *stg = getenv("DRAM_B200_STAGED_EPILOGUE");
+  pl->staged = taps == 1 && block_n >= 64 && d->store_out && d->n_heads == 0 && (d->res_c == 0 || res_tma) &&
+               !(stg && atoi(stg) == 0);
+  if (pl->staged && block_n > 128) {  // re-tile N: the staged configuration holds BLOCK_N <= 128
+    block_n = 128;
+    pl->block_n = block_n;
+    p.num_n_tiles = d->cout / block_n;
+    const int64_t total2 = (int64_t)p.tiles_per_sample * d->n * p.num_n_tiles;
+    if (total2 > 0x7fffffffLL) {
+      delete pl;
+      set_error("conv3d: too many tiles");
+      return DRAM_E_ARG;
+    }
+    p.total_tiles = (int)total2;
+    pl->n_tiles = p.num_n_tiles;
+    rc = rc == DRAM_OK ? encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, epi.is_f16) : rc;
+  }
+  p.staged_res = pl->staged && d->res_c > 0;
+  pl->map_out = pl->map_a1;
+  pl->map_res = pl->map_a1;
+  if (rc == DRAM_OK && pl->staged) {
+    rc = encode_act_map(&pl->map_out, out, d->n, Do, Ho, Wo, d->cout, 64, tw, th, td, 1, 1, 1, epi.is_f16);
+    if (rc == DRAM_OK && p.staged_res)
+      rc = encode_act_map(&pl->map_res, residual, d->n, Do, Ho, Wo, d->cout, 64, tw, th, td, 1, 1, 1, epi.is_f16);
+  }
   if (rc == DRAM_OK) {
-    switch (block_n) {
-      case 32: pl->stages = ConvCfg<32>::STAGES; pl->smem_bytes = ConvCfg<32>::SMEM_BYTES; rc = set_smem_attr<32>(); break;
-      case 64: pl->stages = ConvCfg<64>::STAGES; pl->smem_bytes = ConvCfg<64>::SMEM_BYTES; rc = set_smem_attr<64>(); break;
-      case 128: pl->stages = ConvCfg<128>::STAGES; pl->smem_bytes = ConvCfg<128>::SMEM_BYTES; rc = set_smem_attr<128>(); break;
-      default: pl->stages = ConvCfg<256>::STAGES; pl->smem_bytes = ConvCfg<256>::SMEM_BYTES; rc = set_smem_attr<256>(); break;
+    if (pl->staged) {
+      switch (block_n) {
+        case 64: rc = fill_tile_cfg<64, true>(pl); break;
+        default: rc = fill_tile_cfg<128, true>(pl); break;
+      }
+    } else {
+      switch (block_n) {
+        case 32: rc = fill_tile_cfg<32, false>(pl); break;
+        case 64: rc = fill_tile_cfg<64, false>(pl); break;
+        case 128: rc = fill_tile_cfg<128, false>(pl); break;
+        default: rc = fill_tile_cfg<256, false>(pl); break;
+      }
     }
   }
   if (rc != DRAM_OK) {
@@ -578,20 +701,19 @@ extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, voi
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (plan->kind == 1) return slab_plan_run(plan, ctas, st);
   if (plan->p.total_tiles < ctas) ctas = plan->p.total_tiles;
-  dim3 grid(ctas), block(NUM_THREADS);
-  switch (plan->block_n) {
-    case 32:
-      conv3d_umma_kernel<32><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
-      break;
-    case 64:
-      conv3d_umma_kernel<64><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
-      break;
-    case 128:
-      conv3d_umma_kernel<128><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
-      break;
-    default:
-      conv3d_umma_kernel<256><<<grid, block, plan->smem_bytes, st>>>(plan->map_a1, plan->map_a2, plan->map_w, plan->p);
-      break;
+  dim3 grid(ctas);
+  if (plan->staged) {
+    switch (plan->block_n) {
+      case 64: launch_tiles<64, true>(plan, grid, st); break;
+      default: launch_tiles<128, true>(plan, grid, st); break;
+    }
+  } else {
+    switch (plan->block_n) {
+      case 32: launch_tiles<32, false>(plan, grid, st); break;
+      case 64: launch_tiles<64, false>(plan, grid, st); break;
+      case 128: launch_tiles<128, false>(plan, grid, st); break;
+      default: launch_tiles<256, false>(plan, grid, st); break;
+    }
   }
   DRAM_CHECK_LAUNCH("conv3d_umma_kernel launch");
   return DRAM_OK;

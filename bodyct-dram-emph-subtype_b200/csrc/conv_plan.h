@@ -12,6 +12,7 @@ struct ConvKParams {
   int tiles_w, tiles_h, tiles_d, tiles_per_sample, num_n_tiles, total_tiles;
   int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
   int chunks1, chunks_total;   // 64-channel chunks of source 1 / of both sources
+  int staged_res;              // staged epilogue: 1 = the residual tile comes through TMA as well
   EpiParams epi;
 };
 
@@ -34,6 +35,8 @@ struct SlabParams {
 struct dram_conv_plan {
   int kind;  // 0 = per-tap tiles, 1 = plane ring
   CUtensorMap map_a1, map_a2, map_w;
+  CUtensorMap map_out, map_res;  // staged (TMA store) epilogue of the tile kernel
+  int staged;
   dram::ConvKParams p;
   dram::SlabParams sp;
   int block_n;

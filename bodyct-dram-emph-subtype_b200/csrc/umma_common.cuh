@@ -96,6 +96,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem -> global tile store (bulk async group); the tensor map clips rows outside the tensor.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -174,11 +187,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int is_f16) {
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
   if (is_f16) {
-    // saturate instead of overflowing to inf
-    a = fminf(fmaxf(a, -65504.0f), 65504.0f);
-    b = fminf(fmaxf(b, -65504.0f), 65504.0f);
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
+    // one F2FP.SATFINITE: values beyond +-65504 saturate instead of overflowing to inf
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t *>(&h);
@@ -272,6 +284,66 @@ __device__ __forceinline__ void epilogue_group(const EpiParams &e, const uint32_
       else
         e.head_out1[((size_t)sample * e.head_ch1 + (hc - e.head_ch0)) * plane + sp] = s;
     }
+  }
+}
+
+// Staged variant of one 32-column group: residual row from a SWIZZLE_128B shared-memory tile (or none), result
+// written to a SWIZZLE_128B shared-memory tile that a TMA store sends out.  `row` = tile row, `half` = which 64-byte
+// half of the 128-byte row this group occupies (0 / 1), cg = first global output channel (for scale / bias).
+__device__ __forceinline__ void epilogue_group_staged(const EpiParams &e, const uint32_t (&v)[32], int cg, int row,
+                                                      int half, uint32_t res_tile, bool has_res, uint32_t out_tile) {
+  float y[32];
+  const float4 *b4 = reinterpret_cast<const float4 *>(e.bias + cg);
+  if (e.scale != nullptr) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(e.scale + cg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j), sc = __ldg(s4 + j);
+      y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, b.x);
+      y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, b.y);
+      y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, b.z);
+      y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      y[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+      y[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+      y[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+      y[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+    }
+  }
+  const uint32_t row_off = (uint32_t)row * 128u;
+  if (has_res) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+      uint32_t w[4];
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                   : "r"(res_tile + row_off + chunk));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack2(w[q], e.is_f16);
+        y[8 * j + 2 * q + 0] += f.x;
+        y[8 * j + 2 * q + 1] += f.y;
+      }
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
+    const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_tile + row_off + chunk), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3])
+                 : "memory");
   }
 }
 

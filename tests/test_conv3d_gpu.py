@@ -320,3 +320,38 @@ def test_conv_fused_upsample_argument_errors(cuda, lib):
     with pytest.raises(DramError):   # cout 128 is not a plane-ring shape
         ops.Conv3dPlan(lo, torch.zeros((128, 27 * 128), dtype=torch.float16, device=cuda),
                        torch.zeros(128, device=cuda), x2=skip, upsample_x1=True)
+
+
+STAGED_CASES = [
+    # (batch, dims, cin, cout, residual channels, max_ctas): the 1x1x1 convolutions of the bottleneck blocks
+    (1, (8, 8, 8), 64, 256, 256, 0),        # layer1.x.conv3: expand + full residual
+    (2, (5, 9, 12), 256, 64, 0, 0),         # conv1: reduce, ragged volume (partial tiles, TMA store clipping)
+    (1, (6, 10, 20), 128, 512, 512, 3),     # several tiles per CTA: residual prefetch / store double buffering
+    (1, (4, 8, 8), 512, 128, 0, 1),         # one CTA walks every tile, two column groups per tile
+    (1, (3, 5, 7), 64, 64, 64, 2),          # single 64-channel group per tile
+]
+
+
+@pytest.mark.parametrize("case", range(len(STAGED_CASES)))
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conv_1x1_staged_epilogue(cuda, lib, case, dt):
+    """Bottleneck 1x1x1 convolutions (med3d.py:152-157, 164-184) through the shared-memory + TMA epilogue."""
+    n, dims, cin, cout, res, max_ctas = STAGED_CASES[case]
+    _run_conv(cuda, n, dims, cin, 0, cout, 1, 1, 1, residual=res or None, seed=80 + case, dtype=dt, max_ctas=max_ctas,
+              normalize=(case % 2 == 0))
+
+
+def test_conv_1x1_staged_equals_direct_epilogue(cuda, lib, monkeypatch):
+    """Both epilogues of the tile kernel round the same fp32 values once: identical 16-bit results."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(91)
+    x = ops.to_ndhwc_16(_rand((1, 128, 6, 9, 11), g, dtype=torch.float16).to(cuda), torch.float16)
+    res = ops.to_ndhwc_16(_rand((1, 256, 6, 9, 11), g, dtype=torch.float16).to(cuda), torch.float16)
+    w = ops.pack_conv_weight(_rand((256, 128, 1, 1, 1), g, scale=128 ** -0.5), dtype=torch.float16).to(cuda)
+    b = (torch.randn(256, generator=g) * 0.1).to(cuda)
+    staged = ops.Conv3dPlan(x, w, b, kernel=1, residual=res).run().clone()
+    monkeypatch.setenv("DRAM_B200_STAGED_EPILOGUE", "0")
+    direct = ops.Conv3dPlan(x, w, b, kernel=1, residual=res).run().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(staged, direct)
