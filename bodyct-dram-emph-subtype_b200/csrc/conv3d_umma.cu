@@ -242,7 +242,9 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int rb = gi % RES_BUFS;
       mbar_expect_tx(res_full(rb), EPI_TILE_BYTES);
-      tma_load_5d(res_tile(rb), &map_res, res_full(rb), t.n0 + (gi % GROUPS) * 64, t.w0, t.h0, t.d0, t.sample);
+      const int rs = p.epi.res_stride;
+      tma_load_5d(res_tile(rb), &map_res, res_full(rb), t.n0 + (gi % GROUPS) * 64, t.w0 * rs, t.h0 * rs, t.d0 * rs,
+                  t.sample);
     };
     if (threadIdx.x == 0)
       for (int g0 = 0; g0 < RES_BUFS; ++g0) issue_res(g0);
@@ -629,7 +631,9 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   if (rc == DRAM_OK) rc = encode_weight_map(&pl->map_w, weight, d->cout, ktot, block_n, epi.is_f16);
   // Staged (shared memory + TMA) epilogue for the 1x1x1 convolutions: they are bound by the epilogue's global
   // accesses, which the direct path issues as one 16-byte access per lane and row.
-  const bool res_tma = d->res_c == d->cout && d->res_stride == 1 && d->res_d == Do && d->res_h == Ho && d->res_w == Wo;
+  // The residual tile is a TMA box too: shortcut type A (fewer channels, strided read) falls out of the tensor
+  // map — channel groups beyond res_c are out of bounds and arrive as zeros, the stride is the map's element stride.
+  const bool res_tma = d->res_c % 64 == 0;
   const char *stg = getenv("DRAM_B200_STAGED_EPILOGUE");
   pl->staged = taps == 1 && block_n >= 64 && d->store_out && d->n_heads == 0 && (d->res_c == 0 || res_tma) &&
                !(stg && atoi(stg) == 0);
@@ -653,7 +657,8 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   if (rc == DRAM_OK && pl->staged) {
     rc = encode_act_map(&pl->map_out, out, d->n, Do, Ho, Wo, d->cout, 64, tw, th, td, 1, 1, 1, epi.is_f16);
     if (rc == DRAM_OK && p.staged_res)
-      rc = encode_act_map(&pl->map_res, residual, d->n, Do, Ho, Wo, d->cout, 64, tw, th, td, 1, 1, 1, epi.is_f16);
+      rc = encode_act_map(&pl->map_res, residual, d->n, d->res_d, d->res_h, d->res_w, d->res_c, 64, tw, th, td,
+                          epi.res_stride, epi.res_stride, epi.res_stride, epi.is_f16);
   }
   if (rc == DRAM_OK) {
     if (pl->staged) {

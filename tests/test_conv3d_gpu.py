@@ -329,6 +329,8 @@ STAGED_CASES = [
     (1, (6, 10, 20), 128, 512, 512, 3),     # several tiles per CTA: residual prefetch / store double buffering
     (1, (4, 8, 8), 512, 128, 0, 1),         # one CTA walks every tile, two column groups per tile
     (1, (3, 5, 7), 64, 64, 64, 2),          # single 64-channel group per tile
+    (1, (6, 9, 10), 64, 256, 64, 0),        # layer1.0.conv3: shortcut type A, residual has fewer channels
+    (2, (5, 8, 12), 256, 512, 256, 4),      # layer3.0-like: shortcut A through the residual tensor map
 ]
 
 
@@ -355,3 +357,26 @@ def test_conv_1x1_staged_equals_direct_epilogue(cuda, lib, monkeypatch):
     direct = ops.Conv3dPlan(x, w, b, kernel=1, residual=res).run().clone()
     torch.cuda.synchronize()
     assert torch.equal(staged, direct)
+
+
+def test_conv_1x1_staged_strided_shortcut_a(cuda, lib):
+    """R50 layer2.0.conv3 (med3d.py:103-112, 181): 1x1x1 expand whose residual is the stride-2 subsample of a
+    tensor with fewer channels — through the staged epilogue's residual tensor map (element strides 2, channel
+    groups beyond res_c out of bounds = zeros)."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(93)
+    for dt in (torch.float16, torch.bfloat16):
+        x = _rand((2, 128, 5, 6, 9), g, dtype=dt)
+        res = _rand((2, 256, 10, 12, 18), g, dtype=dt)
+        wgt = _rand((512, 128, 1, 1, 1), g, scale=128 ** -0.5, dtype=dt)
+        bias = torch.randn(512, generator=g) * 0.1
+        ref = F.conv3d(x, wgt, None) + bias.view(1, -1, 1, 1, 1)
+        ref[:, :256] += res[:, :, ::2, ::2, ::2]
+        ref = ref.relu()
+        plan = ops.Conv3dPlan(ops.to_ndhwc_16(x.to(cuda), dt), ops.pack_conv_weight(wgt, dtype=dt).to(cuda),
+                              bias.to(cuda), kernel=1, residual=ops.to_ndhwc_16(res.to(cuda), dt), res_stride=2)
+        got = ops.to_ncdhw_f32(plan.run(3)).cpu()
+        global DT
+        DT = dt
+        _close(got, ref, f"1x1 + strided shortcut A {dt}")
