@@ -107,11 +107,12 @@ class Med3DEngine:
         D2, H2, W2 = (_conv_out(n, 3, 2, 1, 1) for n in (D1, H1, W1))
         D3, H3, W3 = (_conv_out(n, 3, 2, 1, 1) for n in (D2, H2, W2))
         if (2 * D3, 2 * H3, 2 * W3) != (D2, H2, W2) or (2 * D2, 2 * H2, 2 * W2) != (D1, H1, W1):
-            # the reference centre-crops the skip tensor in this case (med3d.py:39-48)
-            raise NotImplementedError(
-                f"input size {self.dims}: each of D,H,W must be 8k or 8k-1 so that the x2 up-sampled maps match "
-                "their skip tensors; cropping skips is not implemented")
-
+            # 2*ceil(n/2) >= n: the x2 up-sampled map is never SMALLER than its skip tensor, so the centre crop of
+            # crop_concat_5d (med3d.py:39-48) is always the identity and a mismatch means "larger" — where the
+            # reference's torch.cat fails with a size error as well
+            raise ValueError(
+                f"input size {self.dims}: each of D, H, W must be 8k or 8k-1 so that the x2 up-sampled maps match "
+                "their skip tensors (the reference's crop_concat_5d/torch.cat raises for other sizes too)")
         # ---- stem: conv(7^3, s2, p3) + BN + ReLU straight from the fp32 image (K2); the older two-kernel
         # route (K2a unfold + K1 7x1x1) stays selectable for A/B runs with DRAM_B200_STEM=unfold
         self.image = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
