@@ -52,30 +52,6 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
 
-struct TileCoord {
-  int n0, sample, d0, h0, w0;
-};
-__device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int tile, int block_n) {
-  TileCoord t;
-  int n_tile = tile % p.num_n_tiles;
-  int m_tile = tile / p.num_n_tiles;
-  t.n0 = n_tile * block_n;
-  t.sample = m_tile / p.tiles_per_sample;
-  int r = m_tile - t.sample * p.tiles_per_sample;
-  int iw = r % p.tiles_w;
-  int r2 = r / p.tiles_w;
-  int ih = r2 % p.tiles_h;
-  int id = r2 / p.tiles_h;
-  t.w0 = iw * p.tw;
-  t.h0 = ih * p.th;
-  t.d0 = id * p.td;
-  return t;
-}
-// True when every input coordinate the tile reads along one axis for this tap is padding.
-__device__ __forceinline__ bool tap_is_padding(int i0, int extent, int stride, int in_size) {
-  return (i0 + (extent - 1) * stride < 0) || (i0 >= in_size);
-}
-
 template <int BLOCK_N, bool STAGED>
 __global__ void __launch_bounds__(STAGED ? NUM_THREADS_STAGED : NUM_THREADS, 1)
 conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
@@ -425,6 +401,11 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 static int conv_out(int in, int k, int s, int d, int p) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
 
+// M256 tile kernel (conv3d_pair.cu)
+int pair_plan_wanted(const dram_conv_desc *d, int block_n, int64_t k_chunks, int64_t m_tiles, int n_tiles);
+int pair_plan_fill(dram_conv_plan *pl);
+int pair_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st);
+
 // plane-ring kernel (conv3d_slab.cu)
 int slab_plan_supported(const dram_conv_desc *d);
 int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1, const void *src2,
@@ -666,6 +647,8 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
         case 64: rc = fill_tile_cfg<64, true>(pl); break;
         default: rc = fill_tile_cfg<128, true>(pl); break;
       }
+    } else if (d->tw == 0 && pair_plan_wanted(d, block_n, (int64_t)taps * p.chunks_total, pl->m_tiles, pl->n_tiles)) {
+      rc = pair_plan_fill(pl);
     } else {
       switch (block_n) {
         case 32: rc = fill_tile_cfg<32, false>(pl); break;
@@ -705,6 +688,7 @@ extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, voi
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (plan->kind == 1) return slab_plan_run(plan, ctas, st);
+  if (plan->pair) return pair_plan_run(plan, ctas, st);
   if (plan->p.total_tiles < ctas) ctas = plan->p.total_tiles;
   dim3 grid(ctas);
   if (plan->staged) {

@@ -13,9 +13,36 @@ struct ConvKParams {
   int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
   int chunks1, chunks_total;   // 64-channel chunks of source 1 / of both sources
   int staged_res;              // staged epilogue: 1 = the residual tile comes through TMA as well
+  int m_tiles_total;           // pair kernel: number of 128-voxel bricks (tiles_per_sample * n)
   EpiParams epi;
 };
 
+
+#ifdef __CUDACC__
+struct TileCoord {
+  int n0, sample, d0, h0, w0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams &p, int tile, int block_n) {
+  TileCoord t;
+  int n_tile = tile % p.num_n_tiles;
+  int m_tile = tile / p.num_n_tiles;
+  t.n0 = n_tile * block_n;
+  t.sample = m_tile / p.tiles_per_sample;
+  int r = m_tile - t.sample * p.tiles_per_sample;
+  int iw = r % p.tiles_w;
+  int r2 = r / p.tiles_w;
+  int ih = r2 % p.tiles_h;
+  int id = r2 / p.tiles_h;
+  t.w0 = iw * p.tw;
+  t.h0 = ih * p.th;
+  t.d0 = id * p.td;
+  return t;
+}
+// True when every input coordinate the tile reads along one axis for this tap is padding.
+__device__ __forceinline__ bool tap_is_padding(int i0, int extent, int stride, int in_size) {
+  return (i0 + (extent - 1) * stride < 0) || (i0 >= in_size);
+}
+#endif
 
 // Plane-ring kernel (conv3d_slab.cu): 3x3x3, stride 1, dilation 1, Cout in {32, 64}
 struct SlabParams {
@@ -37,6 +64,7 @@ struct dram_conv_plan {
   CUtensorMap map_a1, map_a2, map_w;
   CUtensorMap map_out, map_res;  // staged (TMA store) epilogue of the tile kernel
   int staged;
+  int pair;                      // 1 = M256 kernel (conv3d_pair.cu): two bricks share every weight tile
   dram::ConvKParams p;
   dram::SlabParams sp;
   int block_n;

@@ -380,3 +380,29 @@ def test_conv_1x1_staged_strided_shortcut_a(cuda, lib):
         global DT
         DT = dt
         _close(got, ref, f"1x1 + strided shortcut A {dt}")
+
+
+PAIR_CASES = [
+    # (batch, dims, cin, cout, dilation, residual, max_ctas): wide layers with a long K loop -> M256 kernel
+    (1, (8, 8, 8), 256, 256, 2, 256, 0),      # layer3 block: 4 bricks -> 2 pairs
+    (1, (4, 12, 8), 256, 512, 4, 0, 0),       # 3 bricks: the last pair has one brick past the end
+    (2, (6, 10, 10), 512, 512, 4, 512, 3),    # ragged bricks, two n-tiles, several tiles per CTA, batch 2
+    (1, (16, 8, 8), 256, 256, 1, 0, 1),       # one CTA walks every tile: accumulator hand-over across tiles
+]
+
+
+@pytest.mark.parametrize("case", range(len(PAIR_CASES)))
+def test_conv_pair_kernel(cuda, lib, case, monkeypatch):
+    """M256 tile kernel (two bricks per weight tile) against torch, and bit-equal to the M128 tile kernel."""
+    n, dims, cin, cout, dil, res, max_ctas = PAIR_CASES[case]
+    dt = torch.float16 if case % 2 == 0 else torch.bfloat16
+    monkeypatch.setenv("DRAM_B200_PAIR_TILES", "1")   # small test shapes: force what the heuristic keeps for big ones
+    plan = _run_conv(cuda, n, dims, cin, 0, cout, 3, 1, dil, residual=res or None, seed=120 + case, dtype=dt,
+                     max_ctas=max_ctas)
+    assert plan.stages == 3 and plan.algo == "tiles"          # the pair kernel's stage count
+    a = plan.run(max_ctas).clone()
+    monkeypatch.setenv("DRAM_B200_PAIR_TILES", "0")
+    plan128 = _run_conv(cuda, n, dims, cin, 0, cout, 3, 1, dil, residual=res or None, seed=120 + case, dtype=dt)
+    assert plan128.stages == 4
+    torch.cuda.synchronize()
+    assert torch.equal(a, plan128.run())
