@@ -60,6 +60,9 @@ SIGNATURES = {
     "dram_stem_conv7": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_upsample2x_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "dram_upsample2x_plan_destroy": (C.c_int, [_vp]),
+    "dram_upsample2x_plan_run": (C.c_int, [_vp, _i32, _vp]),
     "dram_pool_workspace_bytes": (_sz, [_i32, _i32]),
     "dram_masked_pool": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_dram_workspace_bytes": (_sz, [_i32]),

@@ -175,12 +175,22 @@ class Med3DEngine:
         # written) — measured slower on B200 (5.9 -> 7.4 ms per 256^3 volume): the interpolation of a chunk's
         # planes cannot overlap the previous chunk's MMAs with only six plane slots, see DESIGN.md.
         fused_up = os.environ.get("DRAM_B200_UPSAMPLE", "separate").lower() == "fused"
+        # K4 itself: tensor-core kernel (generated interpolation matrix x source patch) unless DRAM_B200_K4=cuda
+        k4_umma = os.environ.get("DRAM_B200_K4", "umma").lower() != "cuda"
+
+        def add_upsample(name, src, dst):
+            if k4_umma and src.shape[4] % 64 == 0:
+                plan = ops.Upsample2xPlan(src, out=dst)
+                self.steps.append(_Step(name, plan.run))
+            else:
+                self.steps.append(_Step(name, lambda: ops.upsample2x(src, out=dst)))
+
         cb = m.us1.conv_blocks
         if fused_up:
             t = self._add_conv("us1.0", x4, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1, upsample_x1=True).out
         else:
             self.up1 = torch.empty((B, D2, H2, W2, x4.shape[4]), dtype=bf, device=dev)
-            self.steps.append(_Step("us1.upsample", lambda: ops.upsample2x(x4, out=self.up1)))
+            add_upsample("us1.upsample", x4, self.up1)
             t = self._add_conv("us1.0", self.up1, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1).out
         xup1 = self._add_conv("us1.1", t, self._conv_bn("us1.1", cb[1][0], cb[1][1])).out
         cb = m.us2.conv_blocks
@@ -188,7 +198,7 @@ class Med3DEngine:
             t = self._add_conv("us2.0", xup1, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x, upsample_x1=True).out
         else:
             self.up2 = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
-            self.steps.append(_Step("us2.upsample", lambda: ops.upsample2x(xup1, out=self.up2)))
+            add_upsample("us2.upsample", xup1, self.up2)
             t = self._add_conv("us2.0", self.up2, self._conv_bn("us2.0", cb[0][0], cb[0][1]), x2=x).out
         xup2 = self._add_conv("us2.1", t, self._conv_bn("us2.1", cb[1][0], cb[1][1])).out
         # ---- us3 + heads fused

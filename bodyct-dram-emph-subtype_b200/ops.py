@@ -328,6 +328,37 @@ def upsample2x(x, out=None):
     return out
 
 
+class Upsample2xPlan:
+    """K4 on the tensor cores: x [N, D, H, W, C] (C % 64 == 0) -> out [N, 2D, 2H, 2W, C], fixed buffers."""
+
+    def __init__(self, x, out=None):
+        lib = _capi.load()
+        _need16(x, "upsample2x x", 5)
+        n, d, h, w, c = x.shape
+        if out is None:
+            out = torch.empty((n, 2 * d, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+        _need(out, x.dtype, "upsample2x out", 5)
+        if tuple(out.shape) != (n, 2 * d, 2 * h, 2 * w, c):
+            raise ValueError(f"upsample2x: out shape {tuple(out.shape)} does not match x {tuple(x.shape)}")
+        handle = C.c_void_p()
+        check(lib.dram_upsample2x_plan_create(_p(x), _p(out), n, d, h, w, c, ACT_DTYPES[x.dtype], C.byref(handle)),
+              "dram_upsample2x_plan_create")
+        self._handle, self._lib, self._keep, self.out = handle, lib, (x, out), out
+
+    def run(self, max_ctas=0):
+        check(self._lib.dram_upsample2x_plan_run(self._handle, max_ctas, _stream()), "dram_upsample2x_plan_run")
+        return self.out
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.dram_upsample2x_plan_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+
 def masked_pool(dense, mask=None):
     """dense fp32 [N, C, d, h, w]; mask uint8 (binary) or fp32 (weights) [N, D, H, W] or None -> fp32 [N, C]."""
     lib = _capi.load()

@@ -171,6 +171,18 @@ int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, in
 int dram_upsample2x(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
                     int32_t c, int32_t dtype, void *stream);
 
+/*
+ * The same operation on the tensor cores (upsample_umma.cu): per 8x4x4 output brick a generated 128 x 96
+ * interpolation matrix (fp16) times the 96-voxel source patch, one TMA box in and one TMA store out per
+ * 64-channel chunk.  Needs c % 64 == 0; rounds the eight interpolation weights to the storage type (one more
+ * half-ulp-scale error on top of the storage rounding of the result).  x and out are fixed in the plan (tensor maps).
+ */
+typedef struct dram_upsample_plan dram_upsample_plan;
+int dram_upsample2x_plan_create(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
+                                int32_t c, int32_t dtype, dram_upsample_plan **plan);
+int dram_upsample2x_plan_destroy(dram_upsample_plan *plan);
+int dram_upsample2x_plan_run(const dram_upsample_plan *plan, int32_t max_ctas, void *stream);
+
 /* ---- K6: lobe-masked / global pooling (med3d.py:383-387, 284) ---------- */
 /*
  * dense: fp32 [n][ch][d][h][w].  mask: [n][md][mh][mw], uint8 (non-zero = lung)

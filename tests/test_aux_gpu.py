@@ -141,3 +141,29 @@ def test_resize(cuda, lib, shape, size):
     gotm = ops.resize_mask(m.to(torch.uint8).to(cuda), size).cpu().bool()
     assert (got - ref).abs().max().item() < 1e-5
     assert torch.equal(gotm, refm)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("dims,c,n,max_ctas", [((4, 4, 4), 64, 1, 0), ((3, 5, 6), 128, 2, 0), ((8, 7, 9), 64, 1, 3),
+                                               ((9, 3, 5), 192, 1, 1), ((16, 16, 16), 64, 1, 0), ((1, 2, 4), 64, 1, 0)])
+def test_upsample2x_tensor_core(cuda, lib, dims, c, n, max_ctas, dt):
+    """K4 as a tcgen05 GEMM (generated interpolation matrix x source patch) against F.interpolate and K4.
+    Error budget: the eight weights are rounded to the storage type (ulp/2 relative each) before the fp32
+    accumulation, the result once more: <= 2 * ulp * max|x|."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn((n, c) + dims, generator=g).to(dt).float()
+    ref = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    xd = ops.to_ndhwc_16(x.to(cuda), dt)
+    plan = ops.Upsample2xPlan(xd)
+    got = ops.to_ncdhw_f32(plan.run(max_ctas)).cpu()
+    assert got.shape == ref.shape
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    tol = 2 * ulp * x.abs().max().item() + 1e-6
+    assert (got - ref).abs().max().item() <= tol
+    k4 = ops.to_ncdhw_f32(ops.upsample2x(xd)).cpu()
+    assert (got - k4).abs().max().item() <= tol
+    # constants are reproduced to the rounding of the weights (rows of the interpolation matrix sum to one)
+    ones = ops.Upsample2xPlan(torch.ones_like(xd)).run().float()
+    assert (ones - 1.0).abs().max().item() <= 4 * ulp

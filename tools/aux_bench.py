@@ -68,6 +68,12 @@ def main():
     up2 = torch.empty((B, h, h, h, 64), dtype=DT, device=dev)
     ms = timeit(lambda: ops.upsample2x(x1, out=up2))
     report("K4 upsample2x 64ch /4->/2", ms, B * (q ** 3 + h ** 3) * 128)
+    plan1 = ops.Upsample2xPlan(x4, out=up1)
+    ms = timeit(lambda: plan1.run())
+    report("K4 tensor-core 512ch /8->/4", ms, B * (e ** 3 + q ** 3) * 1024)
+    plan2 = ops.Upsample2xPlan(x1, out=up2)
+    ms = timeit(lambda: plan2.run())
+    report("K4 tensor-core 64ch /4->/2", ms, B * (q ** 3 + h ** 3) * 128)
     # K6 pooling, K7 dRAM
     dense0 = torch.rand((B, 1, h, h, h), device=dev)
     dense1 = torch.rand((B, 1, h, h, h), device=dev)
