@@ -262,10 +262,11 @@ def pack_stem_weight(weight, scale=None, dtype=torch.bfloat16, normalize=False):
 
 
 def pack_stem_weight_fused(weight, scale=None, dtype=torch.bfloat16, normalize=False):
-    """conv1.weight [64, 1, 7, 7, 7] -> 16-bit [7 (kd), 8 (kh), 64 (cout), 8 (j)] for `stem_conv7`:
-    element = w[cout, 0, kd, kh, j-1] (* scale[cout]) for kh < 7 and j >= 1, zero otherwise (the
-    kernel's pseudo-channel j reads input column 2*ow - 4 + j).  With `normalize` the per-output-channel
-    power-of-two multiplier is returned as well (see `pow2_normalizer`)."""
+    """conv1.weight [64, 1, 7, 7, 7] -> the 16-bit operand of `stem_conv7`: 28672 values =
+    even kd [kh=8][kd=6,4,2,0][cout=64][j=8] followed by odd kd [kh=8][kd=5,3,1][cout=64][j=8], element =
+    w[cout, 0, kd, kh, j-1] (* scale[cout]) for kh < 7 and j >= 1, zero otherwise (the kernel's pseudo-channel j
+    reads input column 2*ow - 4 + j; one input plane feeds the output planes of one kd parity with a single MMA).
+    With `normalize` the per-output-channel power-of-two multiplier is returned as well (`pow2_normalizer`)."""
     w = weight.detach().to(torch.float32)
     if scale is not None:
         w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
@@ -275,9 +276,11 @@ def pack_stem_weight_fused(weight, scale=None, dtype=torch.bfloat16, normalize=F
     mult = pow2_normalizer(w.reshape(cout, -1)) if normalize else None
     if normalize:
         w = w / mult.view(-1, 1, 1, 1, 1)
-    packed = torch.zeros((7, 8, cout, 8), dtype=torch.float32, device=w.device)
-    packed[:, :7, :, 1:] = w[:, 0].permute(1, 2, 0, 3)  # [kd, kh, cout, kw]
-    packed = packed.to(dtype).contiguous()
+    full = torch.zeros((7, 8, cout, 8), dtype=torch.float32, device=w.device)   # [kd, kh, cout, j]
+    full[:, :7, :, 1:] = w[:, 0].permute(1, 2, 0, 3)
+    even = full[[6, 4, 2, 0]].permute(1, 0, 2, 3)   # [kh, 4, cout, j]
+    odd = full[[5, 3, 1]].permute(1, 0, 2, 3)       # [kh, 3, cout, j]
+    packed = torch.cat([even.reshape(-1), odd.reshape(-1)]).to(dtype).contiguous()
     return (packed, mult.contiguous()) if normalize else packed
 
 
@@ -285,9 +288,9 @@ def stem_conv7(x, weight, bias, scale=None, out=None, relu=True, max_ctas=0):
     """K2: fp32 [N, D, H, W] -> 16-bit NDHWC [N, D', H', W', 64] = relu(conv7^3 s2 p3 * scale + bias)."""
     lib = _capi.load()
     _need(x, torch.float32, "stem_conv7 x", 4)
-    _need16(weight, "stem_conv7 weight", 4)
-    if tuple(weight.shape) != (7, 8, 64, 8):
-        raise ValueError(f"stem_conv7: weight must be [7,8,64,8] (pack_stem_weight_fused), got {tuple(weight.shape)}")
+    _need16(weight, "stem_conv7 weight", 1)
+    if weight.numel() != 7 * 8 * 64 * 8:
+        raise ValueError(f"stem_conv7: weight must hold 28672 values (pack_stem_weight_fused), got {tuple(weight.shape)}")
     _need(bias, torch.float32, "stem_conv7 bias", 1)
     if scale is not None:
         _need(scale, torch.float32, "stem_conv7 scale", 1)

@@ -153,8 +153,9 @@ int dram_stem_expand(const float *x, void *out, int32_t n, int32_t d, int32_t h,
  * are shifted UMMA views / accumulation steps, the 7x64x64 weights stay resident (no unfolded copy
  * of the volume in HBM, unlike dram_stem_expand + dram_conv3d_run).
  *   x      : fp32 [n][d][h][w] (the predict_step `image`, models.py:432)
- *   weight : 16-bit [kd=7][kh=8][cout=64][j=8], element = w[cout][0][kd][kh][j-1] * bn_scale for
- *            kh < 7 and j >= 1, else 0; dram_stem_weight_bytes() bytes
+ *   weight : 16-bit, dram_stem_weight_bytes() bytes: even kd [kh=8][kd=6,4,2,0][cout=64][j=8] followed by
+ *            odd kd [kh=8][kd=5,3,1][cout=64][j=8]; element = w[cout][0][kd][kh][j-1] * bn_scale for kh < 7
+ *            and j >= 1, else 0 (ops.pack_stem_weight_fused)
  *   bias   : fp32 [64] folded BN shift; scale: optional fp32 [64] accumulator multiplier
  *   out    : 16-bit NDHWC [n][(d-1)/2+1][(h-1)/2+1][(w-1)/2+1][64]
  */
