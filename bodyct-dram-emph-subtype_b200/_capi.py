@@ -76,6 +76,11 @@ SIGNATURES = {
     "dram_lung_crop_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dram_lung_crop": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "dram_heatmap_u8": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_conv3d_wgrad_workspace_bytes": (_i64, [C.POINTER(ConvDesc)]),
+    "dram_conv3d_wgrad_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _i32, _i32, _vp, _i64, C.POINTER(_vp)]),
+    "dram_conv3d_wgrad_plan_destroy": (C.c_int, [_vp]),
+    "dram_conv3d_wgrad_plan_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, _pi32, _pi32]),
+    "dram_conv3d_wgrad_run": (C.c_int, [_vp, _i32, _i32, _vp]),
     "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -1,0 +1,215 @@
+"""Backward kernels of the convolutions — first rows of the training path.
+
+The reference has no backward code: `train.py` lets Lightning's automatic optimisation call
+`loss.backward()` (models.py:495-582), so autograd differentiates every `nn.Conv3d` of med3d.py
+(conv3x3x3 :93-100, the decoder convs :67/:76, the bottleneck convs :152-157).  These wrappers produce
+what autograd leaves behind for one convolution:
+
+* `Conv3dWgradPlan`  — `weight.grad` (K9, `dram_conv3d_wgrad_*`: tcgen05 GEMM with the voxels as K);
+* `Conv3dDgradPlan`  — the gradient of the input: a transposed convolution, which for stride 1 *is* a K1
+  convolution of `dy` with the spatially flipped, channel-transposed weights (`pack_dgrad_weight`), so it
+  runs on the forward kernels (plane-ring kernel for Cin <= 64, tile kernel otherwise); stride 2 first
+  scatters `dy` onto the stride lattice of a zeroed buffer (one convolution of the network, layer2.0.conv1);
+* `GradBuckets` — flat fp32 gradient storage that `Conv3dWgradPlan` writes into, all-reduced per bucket
+  over the process group (NCCL over NVLink on the GPUs; data-parallel training, train.py:101 `ddp`).
+
+Activations and their gradients are NDHWC 16-bit (bf16 recommended for gradients); weight gradients fp32.
+There is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi
+from ._capi import ConvDesc, check
+from .ops import ACT_DTYPES, Conv3dPlan, _need, _need16, _p, _stream, _triple, pack_conv_weight
+
+
+def _geometry(kernel, stride, dilation, padding):
+    k, s, dl = _triple(kernel), _triple(stride), _triple(dilation)
+    pad = tuple(dl[i] * (k[i] - 1) // 2 for i in range(3)) if padding is None else _triple(padding)
+    return k, s, dl, pad
+
+
+def conv_out_size(size, k, s, dl, pad):
+    return tuple((size[i] + 2 * pad[i] - dl[i] * (k[i] - 1) - 1) // s[i] + 1 for i in range(3))
+
+
+class Conv3dWgradPlan:
+    """`dw[Cout, cin_total, kd, kh, kw]` fp32 (PyTorch layout) from x [N,D,H,W,Cin] and dy [N,Do,Ho,Wo,Cout].
+
+    `dw` may be a view into a flat gradient bucket (contiguous); `cin_offset`/`cin_total` select the channel
+    range this source fills, so the concatenated decoder input (med3d.py:87) is two plans on one `dw`.
+    """
+
+    def __init__(self, x, dy, *, dw=None, kernel=3, stride=1, dilation=1, padding=None, cin_total=None,
+                 cin_offset=0):
+        lib = _capi.load()
+        _need16(x, "conv3d_wgrad x", 5)
+        _need(dy, x.dtype, "conv3d_wgrad dy", 5)
+        n, di, hi, wi, cin = x.shape
+        cout = dy.shape[4]
+        k, s, dl, pad = _geometry(kernel, stride, dilation, padding)
+        want = (n,) + conv_out_size((di, hi, wi), k, s, dl, pad) + (cout,)
+        if tuple(dy.shape) != want:
+            raise ValueError(f"conv3d_wgrad: dy shape {tuple(dy.shape)} != {want}")
+        cin_total = cin if cin_total is None else cin_total
+        shape = (cout, cin_total) + k
+        if dw is None:
+            dw = torch.zeros(shape, dtype=torch.float32, device=x.device)
+        else:
+            _need(dw, torch.float32, "conv3d_wgrad dw", 5)
+            if tuple(dw.shape) != shape:
+                raise ValueError(f"conv3d_wgrad: dw shape {tuple(dw.shape)} != {shape}")
+        d = ConvDesc()
+        d.n, d.di, d.hi, d.wi, d.c1, d.c2, d.cout = n, di, hi, wi, cin, 0, cout
+        d.kd, d.kh, d.kw = k
+        d.sd, d.sh, d.sw = s
+        d.dd, d.dh, d.dw = dl
+        d.pd, d.ph, d.pw = pad
+        d.dtype = ACT_DTYPES[x.dtype]
+        nbytes = lib.dram_conv3d_wgrad_workspace_bytes(C.byref(d))
+        if nbytes < 0:
+            raise _capi.DramError(f"dram_conv3d_wgrad_workspace_bytes: {_capi.last_error()}")
+        self.workspace = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=x.device)
+        handle = C.c_void_p()
+        check(lib.dram_conv3d_wgrad_plan_create(C.byref(d), _p(x), _p(dy), _p(dw), cin_total, cin_offset,
+                                                _p(self.workspace), int(nbytes), C.byref(handle)),
+              "dram_conv3d_wgrad_plan_create")
+        self._handle, self._lib = handle, lib
+        self._keep = (x, dy, dw)
+        self.dw = dw
+        flops, items, ks, bn = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib.dram_conv3d_wgrad_plan_info(handle, C.byref(flops), C.byref(items), C.byref(ks), C.byref(bn)),
+              "dram_conv3d_wgrad_plan_info")
+        self.flops, self.items, self.kslices, self.block_n = flops.value, items.value, ks.value, bn.value
+
+    def run(self, accumulate=False, max_ctas=0):
+        check(self._lib.dram_conv3d_wgrad_run(self._handle, 1 if accumulate else 0, max_ctas, _stream()),
+              "dram_conv3d_wgrad_run")
+        return self.dw
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                self._lib.dram_conv3d_wgrad_plan_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+
+def pack_dgrad_weight(weight, dtype=torch.bfloat16, cin_range=None, pad_cout_to=64):
+    """[Cout, Cin, kd, kh, kw] -> the packed K1 weight of the transposed convolution:
+    rows = input channels (optionally the slice `cin_range` of a concatenated input), K = flipped taps x Cout
+    (Cout zero-padded to a multiple of `pad_cout_to`, the channel granularity of the forward kernels)."""
+    w = weight.detach().to(torch.float32)
+    if cin_range is not None:
+        w = w[:, cin_range[0]:cin_range[1]]
+    cout = w.shape[0]
+    padc = (-cout) % pad_cout_to
+    if padc:
+        w = torch.cat([w, w.new_zeros((padc,) + tuple(w.shape[1:]))], dim=0)
+    wt = w.flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()  # [Cin, Cout, kd, kh, kw], taps reversed
+    return pack_conv_weight(wt, dtype=dtype)
+
+
+class Conv3dDgradPlan:
+    """dx [N, D, H, W, Cin] (16-bit NDHWC) = conv_transpose3d(dy, weight) for the forward geometry given.
+
+    `weight` is the forward convolution's [Cout, Cin_total, kd, kh, kw] parameter (fp32); `cin_range` picks the
+    channels of one source of a concatenated input.  The transposed convolution runs on the K1 kernels.
+    """
+
+    def __init__(self, dy, weight, in_size, *, kernel=3, stride=1, dilation=1, padding=None, cin_range=None,
+                 out=None, algo="auto"):
+        _need16(dy, "conv3d_dgrad dy", 5)
+        k, s, dl, pad = _geometry(kernel, stride, dilation, padding)
+        n, do, ho, wo, cout = dy.shape
+        in_size = tuple(in_size)
+        if (do, ho, wo) != conv_out_size(in_size, k, s, dl, pad):
+            raise ValueError(f"conv3d_dgrad: dy {tuple(dy.shape)} is not the output of a conv over {in_size}")
+        if weight.shape[0] != cout or tuple(weight.shape[2:]) != k:
+            raise ValueError(f"conv3d_dgrad: weight {tuple(weight.shape)} does not match dy / kernel")
+        self.packed = pack_dgrad_weight(weight, dtype=dy.dtype, cin_range=cin_range).to(dy.device)
+        cin = self.packed.shape[0]
+        self.dy = dy
+        cpad = (-cout) % 64
+        # the K1 convolution reads `src`: dy itself, or dy scattered onto the stride lattice / channel-padded
+        lattice = tuple(in_size[i] + 2 * pad[i] - dl[i] * (k[i] - 1) for i in range(3))
+        if s != (1, 1, 1) or cpad:
+            self.src = torch.zeros((n,) + lattice + (cout + cpad,), dtype=dy.dtype, device=dy.device)
+            self._scatter = self.src[:, ::s[0], ::s[1], ::s[2], :cout][:, :do, :ho, :wo]
+        else:
+            self.src, self._scatter = dy, None
+        tpad = tuple(dl[i] * (k[i] - 1) - pad[i] for i in range(3))
+        if min(tpad) < 0:
+            raise ValueError("conv3d_dgrad: padding larger than dilation*(k-1) is not supported")
+        self.bias = torch.zeros(cin, dtype=torch.float32, device=dy.device)
+        self.plan = Conv3dPlan(self.src, self.packed, self.bias, kernel=k, stride=1, dilation=dl, padding=tpad,
+                               relu=False, out=out, algo=algo)
+        if tuple(self.plan.out_shape[1:4]) != in_size:
+            raise AssertionError(f"conv3d_dgrad: internal size mismatch {self.plan.out_shape} vs {in_size}")
+        self.out = self.plan.out
+        # algorithmic FLOPs of the transposed convolution (not of the zero-inserted one that runs)
+        self.flops = 2 * n * do * ho * wo * cout * cin * k[0] * k[1] * k[2]
+
+    def run(self, max_ctas=0):
+        if self._scatter is not None:
+            self._scatter.copy_(self.dy)
+        return self.plan.run(max_ctas)
+
+
+class GradBuckets:
+    """Flat fp32 gradient storage, split into buckets that are all-reduced independently.
+
+    `named_shapes` = ordered [(name, shape)] in the order gradients become ready (reverse forward order);
+    a bucket closes once it holds `bucket_bytes`.  `view(name)` is the contiguous fp32 tensor a wgrad plan
+    writes into; `reduce_bucket(i)` launches the (asynchronous) average over the process group as soon as the
+    bucket's last gradient has been produced, so the exchange overlaps the rest of the backward pass.
+    """
+
+    def __init__(self, named_shapes, device, bucket_bytes=64 << 20):
+        self.slices, self.bucket_of, bounds = {}, {}, [0]
+        off = 0
+        for name, shape in named_shapes:
+            numel = 1
+            for v in shape:
+                numel *= int(v)
+            self.slices[name] = (off, numel, tuple(shape))
+            self.bucket_of[name] = len(bounds) - 1
+            off += numel
+            if (off - bounds[-1]) * 4 >= bucket_bytes:
+                bounds.append(off)
+        if bounds[-1] != off:
+            bounds.append(off)
+        self.bounds = bounds
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self._work = [None] * self.num_buckets
+
+    @property
+    def num_buckets(self):
+        return len(self.bounds) - 1
+
+    def view(self, name):
+        off, numel, shape = self.slices[name]
+        return self.flat[off:off + numel].view(shape)
+
+    def bucket(self, i):
+        return self.flat[self.bounds[i]:self.bounds[i + 1]]
+
+    def reduce_bucket(self, i, group=None):
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        b = self.bucket(i)
+        b.div_(dist.get_world_size(group))
+        self._work[i] = dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return self._work[i]
+
+    def wait(self):
+        for i, w in enumerate(self._work):
+            if w is not None:
+                w.wait()
+                self._work[i] = None

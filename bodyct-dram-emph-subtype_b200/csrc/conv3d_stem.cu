@@ -36,10 +36,7 @@ static constexpr int ST_WEIGHT_BYTES = ST_W_EVEN_BYTES + ST_W_ODD_BYTES;  // 573
 static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = 8;
 static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 416
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
-static constexpr int ST_PATCH_W = 24;                        // raw columns under 8 outputs: 2*7 + 8 = 22, padded
-static constexpr int ST_STAGE_BYTES = 2048;                  // per producer warp: 38 x 24 16-bit values = 1824
-static constexpr int ST_SMEM_BYTES =
-    1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512 + ST_PROD_WARPS * ST_STAGE_BYTES;
+static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512;
 
 struct StemParams {
   const float *x;       // fp32 [n][D][H][W]
@@ -96,7 +93,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
   auto tmem_full = [&](int a) { return bar_base + 8u * (2 * ST_RING + a); };
   auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * ST_RING + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * ST_RING + 4);
-  const uint32_t stage_base = bar_base + 512u;  // producers' raw-patch staging areas
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -133,13 +129,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
 
   if (warp >= ST_PROD_WARP0) {
     // ------------------------------- producers: unfold kw of one input plane per step -------------
-    // Each producer warp owns every ST_PROD_WARPS-th plane of the stream, so that many planes' global loads are
-    // in flight at once.  Per plane: (1) the raw 38 x 24 patch is read once with coalesced 16-byte loads, rounded
-    // to the storage type and parked in the warp's staging area (the naive per-chunk gather issued 5x as many
-    // load instructions for the same 3.3 KiB); (2) the overlapping 8-wide windows are cut from the staging area.
+    // Each producer warp owns every ST_PROD_WARPS-th plane of the stream, so that many planes' global
+    // loads are in flight at once; a lane builds its chunks in two batches of five (20 8-byte loads
+    // outstanding per lane).
     const int pw = warp - ST_PROD_WARP0;
-    const uint32_t stage = stage_base + (uint32_t)pw * ST_STAGE_BYTES;
-    const bool vec4 = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
     const int is_f16 = p.epi.is_f16;
     unsigned seq_end = 0;
     for (int item = item_begin; item < item_end; ++item) {
@@ -148,50 +142,52 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
       const unsigned seq_base = seq_end - (reuse ? (unsigned)ST_KEEP : 0u);
       seq_end = seq_base + ST_ITEM_PLANES;
       const int ih_base = 2 * it.h0 - 3, iw_base = 2 * it.w0 - 4;
-      const bool cols_inside = vec4 && iw_base >= 0 && iw_base + ST_PATCH_W <= p.W;
       for (int j = reuse ? ST_KEEP : 0; j < ST_ITEM_PLANES; ++j) {
         const unsigned seq = seq_base + j;
         if ((int)(seq % ST_PROD_WARPS) != pw) continue;
         const int slot = seq % ST_RING;
         const int z = 2 * it.q0 - 3 + j;
+        mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
         const bool zok = z >= 0 && z < p.D;
         const float *xz = p.x + ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
-        // (1) patch -> staging, 16-bit [38][24]; a task = 4 consecutive columns of a row
-        __syncwarp();
-        for (int task = lane; task < ST_ROWS * (ST_PATCH_W / 4); task += 32) {
-          const int r = task / (ST_PATCH_W / 4), q = task - r * (ST_PATCH_W / 4);
-          const int ih = ih_base + r, iw = iw_base + 4 * q;
-          float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          if (zok && ih >= 0 && ih < p.H) {
-            const float *row = xz + (size_t)ih * p.W;
-            if (cols_inside) {
-              v = __ldg(reinterpret_cast<const float4 *>(row + iw));
-            } else {
-              if (iw >= 0 && iw < p.W) v.x = __ldg(row + iw);
-              if (iw + 1 >= 0 && iw + 1 < p.W) v.y = __ldg(row + iw + 1);
-              if (iw + 2 >= 0 && iw + 2 < p.W) v.z = __ldg(row + iw + 2);
-              if (iw + 3 >= 0 && iw + 3 < p.W) v.w = __ldg(row + iw + 3);
+        const uint32_t dst0 = plane_addr(slot);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float f[5][8];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int chunk = lane + 32 * (half * 5 + c);
+            const int r = chunk >> 3, owl = chunk & 7;
+            const int ih = ih_base + r, iw0 = iw_base + 2 * owl;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[c][q] = 0.0f;
+            if (chunk < ST_ROWS * ST_W && zok && ih >= 0 && ih < p.H) {
+              const float *row = xz + (size_t)ih * p.W;
+              if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
+                  f[c][2 * q] = v.x;
+                  f[c][2 * q + 1] = v.y;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int iw = iw0 + q;
+                  if (iw >= 0 && iw < p.W) f[c][q] = __ldg(row + iw);
+                }
+              }
             }
           }
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(stage + (uint32_t)(r * ST_PATCH_W + 4 * q) * 2u),
-                       "r"(pack_pair(v.x, v.y, is_f16)), "r"(pack_pair(v.z, v.w, is_f16))
-                       : "memory");
-        }
-        __syncwarp();
-        // (2) staging -> slot: chunk (r, ow) = the 8 values at columns 2*ow .. 2*ow + 7 of patch row r
-        mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
-        const uint32_t dst0 = plane_addr(slot);
-        for (int chunk = lane; chunk < ST_ROWS * ST_W; chunk += 32) {
-          const int r = chunk >> 3, owl = chunk & 7;
-          const uint32_t src = stage + (uint32_t)(r * ST_PATCH_W + 2 * owl) * 2u;
-          uint32_t w0, w1, w2, w3;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(src));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(src + 4u));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w2) : "r"(src + 8u));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w3) : "r"(src + 12u));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)chunk * 16u), "r"(w0), "r"(w1),
-                       "r"(w2), "r"(w3)
-                       : "memory");
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            const int chunk = lane + 32 * (half * 5 + c);
+            if (chunk < ST_ROWS * ST_W)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)chunk * 16u),
+                           "r"(pack_pair(f[c][0], f[c][1], is_f16)), "r"(pack_pair(f[c][2], f[c][3], is_f16)),
+                           "r"(pack_pair(f[c][4], f[c][5], is_f16)), "r"(pack_pair(f[c][6], f[c][7], is_f16))
+                           : "memory");
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(plane_full(slot));

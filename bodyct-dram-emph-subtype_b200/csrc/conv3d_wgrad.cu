@@ -1,0 +1,460 @@
+// K9 — conv3d weight gradient (training path; the reference gets it from autograd through every
+// nn.Conv3d of med3d.py:93-100, 67/76, 152-157 when train.py runs Lightning's automatic optimisation):
+//
+//     dW[cout][cin][kd][kh][kw] = sum over output voxels v of  dy[v][cout] * x[v*stride + tap*dilation - pad][cin]
+//
+// GEMM view: M = (tap, cin) rows, N = cout, K = output voxels.  Both operands are NDHWC 16-bit tensors, so the
+// channels — the GEMM M and N dimensions — are the contiguous axis: a TMA box of 64 voxels x 64 channels lands in
+// shared memory as 64 SWIZZLE_128B rows, which is exactly the MN-major operand layout of tcgen05.mma
+// (cute: ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in elements) with the voxels as K.  Nothing is transposed anywhere.
+//
+//   * A operand = two "units" (a unit = one tap x one 64-channel chunk of x) stacked along M through the
+//     descriptor's leading-dimension offset: M = 128.  The x box of a unit is the output tile shifted by the tap
+//     (stride = tensor-map element stride, zero padding = out-of-bounds fill), exactly the box K1's tile kernel loads.
+//   * B operand = the dy tile, N = min(Cout, 256) channels in 64-channel boxes.
+//   * a work item = (unit pair, cout block, K slice); it streams its voxel tiles through a TMA/mbarrier ring,
+//     accumulates D[128 x N] in TMEM (fp32) and writes it once to a per-slice partial buffer.  Tiles whose x boxes lie
+//     entirely in the padding are skipped.
+//   * dram_wgrad_finish_kernel adds the slices (fixed order: deterministic) and scatters to the PyTorch layout.
+//
+// Roles (192 threads): warps 0-3 epilogue, warp 4 lane 0 TMA producer, warp 5 MMA issuer (owns TMEM).
+#include "conv_plan.h"
+
+namespace dram {
+
+static constexpr int WG_TW = 8, WG_TH = 8, WG_TD = 1;       // voxel tile = 64 output voxels = GEMM-K per stage
+static constexpr int WG_KVOX = WG_TW * WG_TH * WG_TD;
+static constexpr int WG_UNIT_BYTES = WG_KVOX * 128;         // 8 KiB: 64 voxels x 64 channels
+static constexpr int WG_A_BYTES = 2 * WG_UNIT_BYTES;        // M = 128
+static constexpr int WG_THREADS = 192;
+static constexpr int WG_PRODUCER_WARP = 4, WG_MMA_WARP = 5;
+
+template <int BLOCK_N>
+struct WgCfg {
+  static constexpr int B_BYTES = (BLOCK_N / 64) * WG_UNIT_BYTES;
+  static constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;  // 24 / 32 / 48 KiB
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+};
+
+struct WgParams {
+  int n, Do, Ho, Wo, Di, Hi, Wi;
+  int tiles_w, tiles_h, tiles_d, tiles_per_sample, total_vtiles;
+  int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
+  int chunks;       // Cin / 64 of this source
+  int units;        // taps * chunks
+  int a_blocks;     // ceil(units / 2)
+  int n_blocks;     // cout_pad / BLOCK_N
+  int kslices;
+  int items_total;  // a_blocks * n_blocks * kslices
+  int cout, cout_pad;
+  int rows_total;   // a_blocks * 128
+  int is_f16;
+  float *partial;   // [kslices][rows_total][cout_pad]
+};
+
+struct WgItem {
+  int slice, a_blk, n0, vt_begin, vt_end;
+  int u0, u1;  // units of the pair; u1 < 0 when the pair has no second unit
+};
+template <int BLOCK_N>
+__device__ __forceinline__ WgItem decode_wg_item(const WgParams &p, int item) {
+  WgItem it;
+  const int n_blk = item % p.n_blocks;
+  const int r = item / p.n_blocks;
+  it.a_blk = r % p.a_blocks;
+  it.slice = r / p.a_blocks;
+  it.n0 = n_blk * BLOCK_N;
+  it.vt_begin = (int)(((long long)it.slice * p.total_vtiles) / p.kslices);
+  it.vt_end = (int)(((long long)(it.slice + 1) * p.total_vtiles) / p.kslices);
+  it.u0 = 2 * it.a_blk;
+  it.u1 = it.u0 + 1 < p.units ? it.u0 + 1 : -1;
+  return it;
+}
+
+struct WgUnit {
+  int c0, ow, oh, od;  // channel offset and input-coordinate offset of the tap: i = o*stride + off
+};
+__device__ __forceinline__ WgUnit decode_wg_unit(const WgParams &p, int u) {
+  WgUnit r;
+  const int tap = u / p.chunks;
+  r.c0 = (u - tap * p.chunks) * 64;
+  const int zd = tap / (p.kh * p.kw), rem = tap - zd * p.kh * p.kw;
+  const int zh = rem / p.kw, zw = rem - zh * p.kw;
+  r.od = zd * p.dd - p.pd;
+  r.oh = zh * p.dh - p.ph;
+  r.ow = zw * p.dw - p.pw;
+  return r;
+}
+struct WgTile {
+  int sample, d0, h0, w0;
+};
+__device__ __forceinline__ WgTile decode_wg_tile(const WgParams &p, int vt) {
+  WgTile t;
+  t.sample = vt / p.tiles_per_sample;
+  int r = vt - t.sample * p.tiles_per_sample;
+  const int iw = r % p.tiles_w;
+  r /= p.tiles_w;
+  const int ih = r % p.tiles_h;
+  t.w0 = iw * WG_TW;
+  t.h0 = ih * WG_TH;
+  t.d0 = (r / p.tiles_h) * WG_TD;
+  return t;
+}
+// The x box of a unit for this tile lies entirely in the zero padding.
+__device__ __forceinline__ bool wg_unit_is_padding(const WgParams &p, const WgTile &t, const WgUnit &u) {
+  return tap_is_padding(t.d0 * p.sd + u.od, WG_TD, p.sd, p.Di) || tap_is_padding(t.h0 * p.sh + u.oh, WG_TH, p.sh, p.Hi) ||
+         tap_is_padding(t.w0 * p.sw + u.ow, WG_TW, p.sw, p.Wi);
+}
+// A tile is streamed unless every unit of the pair reads only padding; the first tile of a slice is always
+// streamed so that the accumulator is initialised (padding boxes arrive as zeros).
+__device__ __forceinline__ bool wg_tile_is_skipped(const WgParams &p, const WgItem &it, const WgUnit &ua, const WgUnit &ub,
+                                                   int vt, const WgTile &t) {
+  if (vt == it.vt_begin) return false;
+  return wg_unit_is_padding(p, t, ua) && (it.u1 < 0 || wg_unit_is_padding(p, t, ub));
+}
+
+// MN-major SWIZZLE_128B descriptor: 64-element groups along M/N every `lbo` bytes, 8-row groups along K every 1 KiB.
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                    const __grid_constant__ WgParams p) {
+  using Cfg = WgCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto smem_a = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + WG_A_BYTES; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full(a), 1);
+      mbar_init(tmem_empty(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == WG_PRODUCER_WARP && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_dy);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  if (warp == WG_PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+        const WgItem it = decode_wg_item<BLOCK_N>(p, item);
+        const WgUnit ua = decode_wg_unit(p, it.u0), ub = decode_wg_unit(p, it.u1 < 0 ? it.u0 : it.u1);
+        const uint32_t bytes = (uint32_t)(Cfg::B_BYTES + (it.u1 < 0 ? 1 : 2) * WG_UNIT_BYTES);
+        for (int vt = it.vt_begin; vt < it.vt_end; ++vt) {
+          const WgTile t = decode_wg_tile(p, vt);
+          if (wg_tile_is_skipped(p, it, ua, ub, vt, t)) continue;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), bytes);
+          tma_load_5d(smem_a(stage), &map_x, full_bar(stage), ua.c0, t.w0 * p.sw + ua.ow, t.h0 * p.sh + ua.oh,
+                      t.d0 * p.sd + ua.od, t.sample);
+          if (it.u1 >= 0)
+            tma_load_5d(smem_a(stage) + WG_UNIT_BYTES, &map_x, full_bar(stage), ub.c0, t.w0 * p.sw + ub.ow,
+                        t.h0 * p.sh + ub.oh, t.d0 * p.sd + ub.od, t.sample);
+#pragma unroll
+          for (int g = 0; g < BLOCK_N / 64; ++g)
+            tma_load_5d(smem_b(stage) + (uint32_t)(g * WG_UNIT_BYTES), &map_dy, full_bar(stage), it.n0 + g * 64, t.w0,
+                        t.h0, t.d0, t.sample);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == WG_MMA_WARP) {
+    // A and B MN-major (bits 15 and 16 of the instruction descriptor)
+    const uint32_t idesc = make_idesc_16bit(128, BLOCK_N, p.is_f16) | (1u << 15) | (1u << 16);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+      const WgItem it = decode_wg_item<BLOCK_N>(p, item);
+      const WgUnit ua = decode_wg_unit(p, it.u0), ub = decode_wg_unit(p, it.u1 < 0 ? it.u0 : it.u1);
+      mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      uint32_t accumulate = 0;
+      for (int vt = it.vt_begin; vt < it.vt_end; ++vt) {
+        const WgTile t = decode_wg_tile(p, vt);
+        if (wg_tile_is_skipped(p, it, ua, ub, vt, t)) continue;
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < WG_KVOX / 16; ++k) {  // 16 voxels = 16 rows of 128 bytes per K step
+            const uint64_t da = make_sw128_mn_desc(smem_a(stage) + (uint32_t)(k * 16 * 128), WG_UNIT_BYTES);
+            const uint64_t db = make_sw128_mn_desc(smem_b(stage) + (uint32_t)(k * 16 * 128), WG_UNIT_BYTES);
+            umma_bf16(tmem_d, da, db, idesc, (k > 0) ? 1u : accumulate);
+          }
+          umma_commit(empty_bar(stage));
+        }
+        __syncwarp();
+        accumulate = 1;
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (elect_one_sync()) umma_commit(tmem_full(acc));
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps 0..3: accumulator -> partial[slice][row][cout] ----------
+    const int row = warp * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
+      const WgItem it = decode_wg_item<BLOCK_N>(p, item);
+      const bool valid = row < 64 || it.u1 >= 0;  // rows of a missing second unit are garbage
+      float *dst = p.partial + ((size_t)it.slice * p.rows_total + (size_t)it.a_blk * 128 + row) * p.cout_pad + it.n0;
+      mbar_wait(tmem_full(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        tmem_wait_ld();
+        if (valid) {
+          float4 *d4 = reinterpret_cast<float4 *>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// dW[co][cin_offset + ci][tap] (+)= sum over slices of partial[s][(tap*chunks + ci/64)*64 + ci%64][co]
+__global__ void wgrad_finish_kernel(const float *__restrict__ partial, float *__restrict__ dw, int kslices, int rows_total,
+                                    int cout_pad, int cout, int chunks, int taps, int cin_total, int cin_offset,
+                                    int accumulate) {
+  const long long rows = (long long)taps * chunks * 64;
+  const long long total = rows * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    const long long row = i / cout;
+    const int c = (int)(row & 63);
+    const int u = (int)(row >> 6);
+    const int tap = u / chunks, ci = (u - tap * chunks) * 64 + c;
+    float s = 0.0f;
+    for (int k = 0; k < kslices; ++k) s += partial[((size_t)k * rows_total + (size_t)row) * cout_pad + co];
+    float *o = dw + ((size_t)co * cin_total + cin_offset + ci) * taps + tap;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+}  // namespace dram
+
+using namespace dram;
+
+struct dram_wgrad_plan {
+  CUtensorMap map_x, map_dy;
+  WgParams p;
+  int block_n;
+  float *dw;
+  int cin_total, cin_offset, taps;
+  int64_t flops;
+};
+
+static int wg_conv_out(int in, int k, int s, int d, int p) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
+
+// Fills the geometry part of the parameters (everything except pointers); returns 0 or an error.
+static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n) {
+  DRAM_REQUIRE(d, "conv3d_wgrad: null descriptor");
+  DRAM_REQUIRE(d->n > 0 && d->di > 0 && d->hi > 0 && d->wi > 0, "conv3d_wgrad: bad input dims");
+  DRAM_REQUIRE(d->c1 > 0 && d->c1 % 64 == 0 && d->c2 == 0,
+               "conv3d_wgrad: c1 must be a multiple of 64 and c2 == 0 (a concatenated input is two calls with "
+               "cin_offset), got c1 %d c2 %d", d->c1, d->c2);
+  DRAM_REQUIRE(d->cout > 0 && d->cout % 32 == 0 && (d->cout <= 256 || d->cout % 256 == 0),
+               "conv3d_wgrad: cout must be 32, 64, 128, 256 or a multiple of 256, got %d", d->cout);
+  DRAM_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->sd > 0 && d->sh > 0 && d->sw > 0 && d->dd > 0 && d->dh > 0 &&
+                   d->dw > 0 && d->pd >= 0 && d->ph >= 0 && d->pw >= 0,
+               "conv3d_wgrad: bad filter geometry");
+  DRAM_REQUIRE(d->dtype == DRAM_DTYPE_BF16 || d->dtype == DRAM_DTYPE_F16, "conv3d_wgrad: bad dtype");
+  memset(p, 0, sizeof(*p));
+  p->n = d->n; p->Di = d->di; p->Hi = d->hi; p->Wi = d->wi;
+  p->Do = wg_conv_out(d->di, d->kd, d->sd, d->dd, d->pd);
+  p->Ho = wg_conv_out(d->hi, d->kh, d->sh, d->dh, d->ph);
+  p->Wo = wg_conv_out(d->wi, d->kw, d->sw, d->dw, d->pw);
+  DRAM_REQUIRE(p->Do > 0 && p->Ho > 0 && p->Wo > 0, "conv3d_wgrad: empty output");
+  p->kd = d->kd; p->kh = d->kh; p->kw = d->kw; p->sd = d->sd; p->sh = d->sh; p->sw = d->sw;
+  p->dd = d->dd; p->dh = d->dh; p->dw = d->dw; p->pd = d->pd; p->ph = d->ph; p->pw = d->pw;
+  p->tiles_w = ceil_div(p->Wo, WG_TW); p->tiles_h = ceil_div(p->Ho, WG_TH); p->tiles_d = ceil_div(p->Do, WG_TD);
+  p->tiles_per_sample = p->tiles_w * p->tiles_h * p->tiles_d;
+  const int64_t vt = (int64_t)p->tiles_per_sample * d->n;
+  DRAM_REQUIRE(vt <= 0x7fffffffLL, "conv3d_wgrad: too many voxel tiles");
+  p->total_vtiles = (int)vt;
+  p->chunks = d->c1 / 64;
+  p->units = d->kd * d->kh * d->kw * p->chunks;
+  p->a_blocks = (p->units + 1) / 2;
+  p->cout = d->cout;
+  p->cout_pad = (d->cout + 63) / 64 * 64;
+  *block_n = p->cout_pad < 256 ? p->cout_pad : 256;
+  p->n_blocks = p->cout_pad / *block_n;
+  p->rows_total = p->a_blocks * 128;
+  p->is_f16 = d->dtype == DRAM_DTYPE_F16;
+  // K slices: fill the SMs in whole waves; at least 4 voxel tiles per slice
+  const int items = p->a_blocks * p->n_blocks, sms = sm_count() > 0 ? sm_count() : 148;
+  int ks = 1;
+  for (int w = 1; w <= 4; ++w) {
+    const int cand = sms * w / items;
+    if (cand >= 1 && (double)cand * items >= 0.9 * sms * w) {
+      ks = cand;
+      break;
+    }
+    if (cand >= 1) ks = cand;
+  }
+  const int max_ks = p->total_vtiles / 4 > 0 ? p->total_vtiles / 4 : 1;
+  if (ks > max_ks) ks = max_ks;
+  p->kslices = ks;
+  p->items_total = items * ks;
+  return DRAM_OK;
+}
+
+extern "C" int64_t dram_conv3d_wgrad_workspace_bytes(const dram_conv_desc *d) {
+  WgParams p;
+  int bn;
+  if (wg_geometry(d, &p, &bn) != DRAM_OK) return -1;
+  return (int64_t)p.kslices * p.rows_total * p.cout_pad * 4;
+}
+
+extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void *x, const void *dy, float *dw,
+                                             int32_t cin_total, int32_t cin_offset, void *workspace,
+                                             int64_t workspace_bytes, dram_wgrad_plan **plan) {
+  DRAM_REQUIRE(plan, "dram_conv3d_wgrad_plan_create: null plan pointer");
+  *plan = nullptr;
+  DRAM_REQUIRE(x && dy && dw && workspace, "dram_conv3d_wgrad_plan_create: x, dy, dw and workspace are required");
+  WgParams p;
+  int bn;
+  int rc = wg_geometry(d, &p, &bn);
+  if (rc != DRAM_OK) return rc;
+  DRAM_REQUIRE(cin_offset >= 0 && cin_offset + d->c1 <= cin_total,
+               "dram_conv3d_wgrad_plan_create: channel range [%d, %d) outside cin_total %d", cin_offset,
+               cin_offset + d->c1, cin_total);
+  const int64_t need = (int64_t)p.kslices * p.rows_total * p.cout_pad * 4;
+  DRAM_REQUIRE(workspace_bytes >= need, "dram_conv3d_wgrad_plan_create: workspace of %lld bytes, %lld needed",
+               (long long)workspace_bytes, (long long)need);
+  dram_wgrad_plan *pl = new dram_wgrad_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->p = p;
+  pl->p.partial = reinterpret_cast<float *>(workspace);
+  pl->block_n = bn;
+  pl->dw = dw;
+  pl->cin_total = cin_total;
+  pl->cin_offset = cin_offset;
+  pl->taps = d->kd * d->kh * d->kw;
+  pl->flops = 2LL * d->n * p.Do * p.Ho * p.Wo * (int64_t)d->cout * d->c1 * pl->taps;
+  rc = encode_act_map(&pl->map_x, x, d->n, d->di, d->hi, d->wi, d->c1, 64, WG_TW, WG_TH, WG_TD, d->sw, d->sh, d->sd,
+                      p.is_f16);
+  if (rc == DRAM_OK)
+    rc = encode_act_map(&pl->map_dy, dy, d->n, p.Do, p.Ho, p.Wo, d->cout, 64, WG_TW, WG_TH, WG_TD, 1, 1, 1, p.is_f16);
+  if (rc == DRAM_OK) {
+    cudaError_t e;
+    if (bn == 64)
+      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<64>::SMEM_BYTES);
+    else if (bn == 128)
+      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<128>::SMEM_BYTES);
+    else
+      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<256>::SMEM_BYTES);
+    rc = check_cuda(e, "cudaFuncSetAttribute(conv3d_wgrad_kernel)");
+  }
+  if (rc != DRAM_OK) {
+    delete pl;
+    return rc;
+  }
+  *plan = pl;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_wgrad_plan_destroy(dram_wgrad_plan *plan) {
+  delete plan;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_wgrad_plan_info(const dram_wgrad_plan *plan, int64_t *flops, int32_t *items, int32_t *kslices,
+                                           int32_t *block_n) {
+  DRAM_REQUIRE(plan, "dram_conv3d_wgrad_plan_info: null plan");
+  if (flops) *flops = plan->flops;
+  if (items) *items = plan->p.items_total;
+  if (kslices) *kslices = plan->p.kslices;
+  if (block_n) *block_n = plan->block_n;
+  return DRAM_OK;
+}
+
+extern "C" int dram_conv3d_wgrad_run(const dram_wgrad_plan *plan, int32_t accumulate, int32_t max_ctas, void *stream) {
+  DRAM_REQUIRE(plan, "dram_conv3d_wgrad_run: null plan");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int ctas = sm_count();
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  if (plan->p.items_total < ctas) ctas = plan->p.items_total;
+  if (plan->block_n == 64)
+    conv3d_wgrad_kernel<64><<<ctas, WG_THREADS, WgCfg<64>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
+  else if (plan->block_n == 128)
+    conv3d_wgrad_kernel<128><<<ctas, WG_THREADS, WgCfg<128>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
+  else
+    conv3d_wgrad_kernel<256><<<ctas, WG_THREADS, WgCfg<256>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
+  DRAM_CHECK_LAUNCH("conv3d_wgrad_kernel launch");
+  const WgParams &p = plan->p;
+  const long long total = (long long)p.units * 64 * p.cout;
+  wgrad_finish_kernel<<<stream_grid(total, 256), 256, 0, st>>>(p.partial, plan->dw, p.kslices, p.rows_total, p.cout_pad,
+                                                              p.cout, p.chunks, plan->taps, plan->cin_total,
+                                                              plan->cin_offset, accumulate ? 1 : 0);
+  DRAM_CHECK_LAUNCH("wgrad_finish_kernel launch");
+  return DRAM_OK;
+}

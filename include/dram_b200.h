@@ -268,6 +268,33 @@ int dram_heatmap_u8(const float *map, int32_t d, int32_t h, int32_t w, uint8_t *
                     int32_t OW, int32_t z0, int32_t y0, int32_t x0, int32_t cd, int32_t ch, int32_t cw,
                     void *stream);
 
+/* ---- K9: conv3d weight gradient (training path) ------------ */
+/*
+ * The reference has no backward code of its own: train.py (Lightning automatic optimisation,
+ * models.py:495-582) differentiates every nn.Conv3d of med3d.py:93-100, 67/76, 152-157 through
+ * autograd.  This entry computes what autograd leaves in `conv.weight.grad`:
+ *   dw[cout][cin_offset + ci][kd][kh][kw] (+)= sum_v dy[v][cout] * x[v*stride + tap*dilation - pad][ci]
+ * on the tensor cores (both operands MN-major straight from NDHWC, fp32 accumulation in TMEM, K split
+ * over the voxels with a deterministic second pass).  Only the geometry fields of the descriptor are read:
+ * n, di, hi, wi, c1 (channels of x, multiple of 64; c2 must be 0), cout (32, 64, 128, 256 or a multiple
+ * of 256), k*, s*, d*, p*, dtype.
+ *   x  : 16-bit NDHWC [n][di][hi][wi][c1]   (the convolution's input, or one source of a concatenation)
+ *   dy : 16-bit NDHWC [n][do][ho][wo][cout] (gradient of the convolution's output)
+ *   dw : fp32 [cout][cin_total][kd][kh][kw] (PyTorch's weight layout); this call fills the channel range
+ *        [cin_offset, cin_offset + c1) — a concatenated input (med3d.py:87) is two calls
+ *   workspace : dram_conv3d_wgrad_workspace_bytes(d) bytes (negative return: bad descriptor)
+ * run(): accumulate != 0 adds to dw instead of overwriting it.
+ */
+typedef struct dram_wgrad_plan dram_wgrad_plan;
+int64_t dram_conv3d_wgrad_workspace_bytes(const dram_conv_desc *d);
+int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void *x, const void *dy, float *dw,
+                                  int32_t cin_total, int32_t cin_offset, void *workspace,
+                                  int64_t workspace_bytes, dram_wgrad_plan **plan);
+int dram_conv3d_wgrad_plan_destroy(dram_wgrad_plan *plan);
+int dram_conv3d_wgrad_plan_info(const dram_wgrad_plan *plan, int64_t *flops, int32_t *items, int32_t *kslices,
+                                int32_t *block_n);
+int dram_conv3d_wgrad_run(const dram_wgrad_plan *plan, int32_t accumulate, int32_t max_ctas, void *stream);
+
 /* ---- layout helpers ---------------------------------------------------- */
 /* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
 int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,

@@ -1,0 +1,157 @@
+"""Training-path kernels: conv3d weight gradient (K9) and data gradient against autograd on CPU
+(oracle/backward_oracle.py) on the same 16-bit-rounded operands.
+
+Tolerances: dw is an fp32 accumulation of exact 16-bit products, so only the summation order differs:
+|err| <= 1e-4 * max|ref| (+ 1e-5 * |ref|).  dx is rounded once to the storage type: the K1 tolerance
+2^-7 * |ref| + 2^-8 * max|ref| (bf16).  Shapes follow the network's conv families on small,
+ragged volumes: 64->64 (layer1 / decoder), 128->64 (two-chunk input), stride 2, dilation 2 and 4 with Cout 256 /
+512 (two cout blocks), 1x1x1, Cout 32 (us3), the concatenated decoder input (two sources), accumulate mode.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, gen, scale, dtype):
+    return (torch.randn(shape, generator=gen) * scale).to(dtype).float()
+
+
+def _case(cuda, n, dims, cin, cout, k=3, stride=1, dil=1, dtype=torch.bfloat16, seed=0):
+    from oracle import backward_oracle as B
+
+    g = torch.Generator().manual_seed(seed)
+    k3 = (k, k, k) if isinstance(k, int) else k
+    x = _rand((n, cin) + tuple(dims), g, 1.0, dtype)
+    w = _rand((cout, cin) + k3, g, (cin * k3[0] * k3[1] * k3[2]) ** -0.5, dtype)
+    pad = tuple(dil * (kk - 1) // 2 for kk in k3)
+    od = tuple((dims[i] + 2 * pad[i] - dil * (k3[i] - 1) - 1) // stride + 1 for i in range(3))
+    dy = _rand((n, cout) + od, g, 1.0, dtype)
+    dx_ref, dw_ref = B.conv3d_grads(x, w, dy, stride=stride, dilation=dil, padding=pad)
+    return x, w, dy, dx_ref, dw_ref, k3, pad
+
+
+def _close_dw(got, ref, what):
+    err = (got - ref).abs()
+    tol = ref.abs().max() * 1e-4 + ref.abs() * 1e-5
+    assert bool((err <= tol).all()), f"{what}: max err {err.max().item():.4g} vs max|ref| {ref.abs().max().item():.4g}"
+
+
+def _close_dx(got, ref, what, dtype):
+    eps = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    err = (got - ref).abs()
+    tol = ref.abs() * eps + ref.abs().max() * eps / 2
+    assert bool((err <= tol).all()), f"{what}: max err {err.max().item():.4g} vs max|ref| {ref.abs().max().item():.4g}"
+
+
+WGRAD_CASES = [
+    # n, dims, cin, cout, k, stride, dil
+    (1, (8, 8, 8), 64, 64, 3, 1, 1),
+    (2, (5, 9, 11), 64, 64, 3, 1, 1),
+    (1, (6, 10, 9), 128, 64, 3, 1, 1),
+    (1, (9, 10, 12), 64, 128, 3, 2, 1),
+    (1, (7, 9, 10), 128, 256, 3, 1, 2),
+    (1, (9, 9, 12), 64, 512, 3, 1, 4),
+    (1, (6, 7, 9), 256, 64, 1, 1, 1),
+    (2, (4, 9, 17), 64, 32, 3, 1, 1),
+    (1, (5, 6, 7), 192, 128, (1, 3, 3), 1, 1),
+]
+
+
+@pytest.mark.parametrize("n,dims,cin,cout,k,stride,dil", WGRAD_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_wgrad_matches_autograd(cuda, n, dims, cin, cout, k, stride, dil, dtype):
+    from dram_b200 import backward, ops
+
+    if dtype == torch.float16 and (cout, dil) not in ((64, 1), (256, 2)):
+        pytest.skip("fp16 re-runs a subset")
+    x, w, dy, _, dw_ref, k3, pad = _case(cuda, n, dims, cin, cout, k, stride, dil, dtype)
+    plan = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x.to(cuda), dtype), ops.to_ndhwc_16(dy.to(cuda), dtype),
+                                    kernel=k3, stride=stride, dilation=dil, padding=pad)
+    dw = plan.run().cpu()
+    torch.cuda.synchronize()
+    _close_dw(dw, dw_ref, f"wgrad {cin}->{cout} k{k} s{stride} d{dil} (items {plan.items}, slices {plan.kslices})")
+    # deterministic: a second run reproduces the bits; accumulate adds
+    dw2 = plan.run().clone()
+    assert torch.equal(dw2.cpu(), dw)
+    dw3 = plan.run(accumulate=True).cpu()
+    assert torch.allclose(dw3, 2 * dw, rtol=1e-6, atol=0)
+
+
+def test_wgrad_slices_agree(cuda):
+    """A different CTA count changes nothing (the K split is fixed by the plan, not by the launch)."""
+    from dram_b200 import backward, ops
+
+    x, w, dy, _, dw_ref, k3, pad = _case(cuda, 1, (16, 16, 16), 64, 64, seed=3)
+    plan = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x.to(cuda), torch.bfloat16), ops.to_ndhwc_16(dy.to(cuda), torch.bfloat16),
+                                    kernel=k3, padding=pad)
+    a = plan.run().clone()
+    b = plan.run(max_ctas=5).clone()
+    assert plan.kslices > 1
+    assert torch.equal(a, b)
+    _close_dw(a.cpu(), dw_ref, "wgrad 16^3")
+
+
+def test_wgrad_concat_sources(cuda):
+    """The decoder's cat([up(x4), x1]) input (med3d.py:87): one dw, two plans with channel offsets."""
+    from dram_b200 import backward, ops
+
+    dt = torch.bfloat16
+    x, w, dy, _, dw_ref, k3, pad = _case(cuda, 1, (6, 8, 10), 192, 64, seed=5)
+    x1, x2 = x[:, :128].contiguous(), x[:, 128:].contiguous()
+    dyd = ops.to_ndhwc_16(dy.to(cuda), dt)
+    dw = torch.zeros((64, 192, 3, 3, 3), dtype=torch.float32, device=cuda)
+    p1 = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x1.to(cuda), dt), dyd, dw=dw, cin_total=192, cin_offset=0)
+    p2 = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x2.to(cuda), dt), dyd, dw=dw, cin_total=192, cin_offset=128)
+    p1.run()
+    p2.run()
+    _close_dw(dw.cpu(), dw_ref, "wgrad concat")
+
+
+def test_wgrad_rejects_bad_arguments(cuda):
+    from dram_b200 import _capi, backward
+
+    x = torch.zeros((1, 4, 4, 4, 60), dtype=torch.bfloat16, device=cuda)
+    dy = torch.zeros((1, 4, 4, 4, 64), dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(_capi.DramError, match="multiple of 64"):
+        backward.Conv3dWgradPlan(x, dy)
+    with pytest.raises(ValueError, match="dy shape"):
+        backward.Conv3dWgradPlan(torch.zeros((1, 4, 4, 4, 64), dtype=torch.bfloat16, device=cuda),
+                                 torch.zeros((1, 3, 4, 4, 64), dtype=torch.bfloat16, device=cuda))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        backward.Conv3dWgradPlan(torch.zeros((1, 4, 4, 4, 64), dtype=torch.bfloat16), dy)
+
+
+DGRAD_CASES = [
+    (1, (8, 8, 8), 64, 64, 3, 1, 1),
+    (2, (5, 9, 11), 64, 128, 3, 1, 1),
+    (1, (7, 9, 10), 128, 256, 3, 1, 2),
+    (1, (9, 9, 12), 256, 512, 3, 1, 4),
+    (1, (9, 10, 12), 64, 128, 3, 2, 1),
+    (1, (8, 10, 12), 64, 128, 3, 2, 1),
+    (1, (6, 7, 9), 256, 64, 1, 1, 1),
+    (1, (4, 9, 17), 64, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("n,dims,cin,cout,k,stride,dil", DGRAD_CASES)
+def test_dgrad_matches_autograd(cuda, n, dims, cin, cout, k, stride, dil):
+    from dram_b200 import backward, ops
+
+    dtype = torch.bfloat16
+    x, w, dy, dx_ref, _, k3, pad = _case(cuda, n, dims, cin, cout, k, stride, dil, dtype, seed=1)
+    plan = backward.Conv3dDgradPlan(ops.to_ndhwc_16(dy.to(cuda), dtype), w, dims, kernel=k3, stride=stride,
+                                    dilation=dil, padding=pad)
+    dx = ops.to_ncdhw_f32(plan.run()).cpu()
+    _close_dx(dx, dx_ref, f"dgrad {cin}->{cout} k{k} s{stride} d{dil}", dtype)
+
+
+def test_dgrad_concat_source_slice(cuda):
+    """dx of one source of the concatenated decoder input = transposed conv with that channel slice."""
+    from dram_b200 import backward, ops
+
+    dt = torch.bfloat16
+    x, w, dy, dx_ref, _, k3, pad = _case(cuda, 1, (6, 8, 10), 192, 64, seed=7)
+    plan = backward.Conv3dDgradPlan(ops.to_ndhwc_16(dy.to(cuda), dt), w, (6, 8, 10), cin_range=(128, 192))
+    dx = ops.to_ncdhw_f32(plan.run()).cpu()
+    _close_dx(dx, dx_ref[:, 128:], "dgrad concat slice", dt)
