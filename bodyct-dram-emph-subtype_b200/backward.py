@@ -40,10 +40,12 @@ class Conv3dWgradPlan:
 
     `dw` may be a view into a flat gradient bucket (contiguous); `cin_offset`/`cin_total` select the channel
     range this source fills, so the concatenated decoder input (med3d.py:87) is two plans on one `dw`.
+    Two kernels sit behind the entry point: the plane kernel (3x3x3, stride 1, dilation 1, Cout <= 64: layer1 and the
+    decoder) and the streaming kernel (everything else, or `algo="tiles"`).
     """
 
     def __init__(self, x, dy, *, dw=None, kernel=3, stride=1, dilation=1, padding=None, cin_total=None,
-                 cin_offset=0):
+                 cin_offset=0, algo="auto"):
         lib = _capi.load()
         _need16(x, "conv3d_wgrad x", 5)
         _need(dy, x.dtype, "conv3d_wgrad dy", 5)
@@ -68,6 +70,7 @@ class Conv3dWgradPlan:
         d.dd, d.dh, d.dw = dl
         d.pd, d.ph, d.pw = pad
         d.dtype = ACT_DTYPES[x.dtype]
+        d.algo = _capi.CONV_ALGO[algo]  # "tiles" forces the streaming kernel where the plane kernel would be picked
         nbytes = lib.dram_conv3d_wgrad_workspace_bytes(C.byref(d))
         if nbytes < 0:
             raise _capi.DramError(f"dram_conv3d_wgrad_workspace_bytes: {_capi.last_error()}")
@@ -82,7 +85,8 @@ class Conv3dWgradPlan:
         flops, items, ks, bn = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32()
         check(lib.dram_conv3d_wgrad_plan_info(handle, C.byref(flops), C.byref(items), C.byref(ks), C.byref(bn)),
               "dram_conv3d_wgrad_plan_info")
-        self.flops, self.items, self.kslices, self.block_n = flops.value, items.value, ks.value, bn.value
+        self.flops, self.items, self.kslices, self.block_n = flops.value, items.value, ks.value, abs(bn.value)
+        self.algo = "planes" if bn.value < 0 else "stream"
 
     def run(self, accumulate=False, max_ctas=0):
         check(self._lib.dram_conv3d_wgrad_run(self._handle, 1 if accumulate else 0, max_ctas, _stream()),

@@ -18,6 +18,19 @@
 //   * dram_wgrad_finish_kernel adds the slices (fixed order: deterministic) and scatters to the PyTorch layout.
 //
 // Roles (192 threads): warps 0-3 epilogue, warp 4 lane 0 TMA producer, warp 5 MMA issuer (owns TMEM).
+//
+// PLANES variant (3x3x3, stride 1, dilation 1, pad 1, Cout <= 64: layer1 and the whole decoder, where the streaming
+// kernel above is bound by re-reading x once per tap through L2):
+//   * a CTA owns one (kd, 64-channel chunk) "key" and a contiguous range of (column, plane) units, a column being
+//     8 (W) x 16 (H) voxels; a unit pairs output plane t with input plane t + kd - 1, so one stage = one x plane with
+//     halo (10 x 18 voxels, 23 KiB, one TMA box) + one dy plane (128 voxels, 16 KiB): each is fetched ONCE for the
+//     nine (kh, kw) taps of the key;
+//   * the A operand of tap (kh, kw) is the x plane seen through an MN-major descriptor whose start is shifted by
+//     (kh*10 + kw) rows and whose K-group stride is the plane pitch of an h row (10 rows) — nothing moves per tap;
+//     taps (kh=0, kw) and (kh=1, kw) are stacked along M through the leading-dimension offset (10 rows): M = 128;
+//     tap (kh=2, kw) is an M = 64 MMA;
+//   * all nine accumulators (6 x 64 TMEM columns) stay resident for the CTA's whole range and are written once;
+//     the CTAs of the three kd keys walk the same columns at the same pace, so x and dy come from DRAM once.
 #include "conv_plan.h"
 
 namespace dram {
@@ -280,6 +293,221 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// PLANES variant
+// ----------------------------------------------------------------------------------------
+static constexpr int WP_W = 8, WP_H = 16;                        // column footprint
+static constexpr int WP_PW = WP_W + 2, WP_PH = WP_H + 2;         // x plane with halo
+static constexpr int WP_X_BYTES = WP_PW * WP_PH * 128;           // 23040
+static constexpr int WP_X_PITCH = 23 * 1024;
+static constexpr int WP_DY_BYTES = WP_W * WP_H * 128;            // 16384
+static constexpr int WP_STAGE_BYTES = WP_X_PITCH + WP_DY_BYTES;  // 39936
+static constexpr int WP_STAGES = 5;
+static constexpr int WP_TMEM_COLS = 512;                         // 6 accumulators of 64 columns
+static constexpr int WP_SMEM_BYTES = 1024 + WP_STAGES * WP_STAGE_BYTES + 256;
+static constexpr int WP_PARTIAL_FLOATS = 9 * 64 * 64;            // per CTA: [kh*3+kw][cin][cout]
+
+struct WpParams {
+  int n, D, H, W;
+  int cols_w, cols_h, columns;  // columns = n * cols_h * cols_w
+  int chunks, keys;             // keys = 3 * chunks, key = kd * chunks + chunk
+  int ctas_per_key;             // grid = keys * ctas_per_key, CTA b: key b % keys, rank b / keys
+  long long upk;                // units per key = columns * D
+  int is_f16;
+  float *partial;               // [grid][9][64][64]
+};
+
+struct WpUnit {
+  int sample, h0, w0, t;
+};
+__device__ __forceinline__ WpUnit decode_wp_unit(const WpParams &p, long long u) {
+  WpUnit r;
+  const int col = (int)(u / p.D);
+  r.t = (int)(u - (long long)col * p.D);
+  const int per_sample = p.cols_w * p.cols_h;
+  r.sample = col / per_sample;
+  const int c = col - r.sample * per_sample;
+  const int ih = c / p.cols_w;
+  r.h0 = ih * WP_H;
+  r.w0 = (c - ih * p.cols_w) * WP_W;
+  return r;
+}
+
+// MN-major SWIZZLE_128B descriptor with explicit leading (64-element M/N groups) and stride (8-row K groups) offsets.
+__device__ __forceinline__ uint64_t make_sw128_mn_desc2(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv3d_wgrad_planes_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                           const __grid_constant__ WpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + WP_STAGES * WP_STAGE_BYTES;
+  auto smem_x = [&](int s) { return smem_base + (uint32_t)s * WP_STAGE_BYTES; };
+  auto smem_dy = [&](int s) { return smem_base + (uint32_t)s * WP_STAGE_BYTES + WP_X_PITCH; };
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (WP_STAGES + s); };
+  const uint32_t tmem_full = bar_base + 8u * (2 * WP_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * WP_STAGES + 1);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WP_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_slot, WP_TMEM_COLS);
+  if (warp == WG_PRODUCER_WARP && lane == 0) {
+    prefetch_tensormap(&map_x);
+    prefetch_tensormap(&map_dy);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int key = blockIdx.x % p.keys, rank = blockIdx.x / p.keys;
+  const int kd = key / p.chunks, chunk = key - kd * p.chunks;
+  const long long u_lo = (p.upk * rank) / p.ctas_per_key, u_hi = (p.upk * (rank + 1)) / p.ctas_per_key;
+  // Output plane t pairs with input plane t + kd - 1; a unit whose input plane is outside the volume contributes
+  // nothing and is skipped — except the first unit of the range, which initialises the accumulators (its x box is
+  // out of bounds and arrives as zeros).
+  auto skipped = [&](long long u, int t) {
+    const int z = t + kd - 1;
+    return (z < 0 || z >= p.D) && u != u_lo;
+  };
+
+  if (warp == WG_PRODUCER_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long u = u_lo; u < u_hi; ++u) {
+        const WpUnit un = decode_wp_unit(p, u);
+        if (skipped(u, un.t)) continue;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), WP_X_BYTES + WP_DY_BYTES);
+        tma_load_5d(smem_x(stage), &map_x, full_bar(stage), chunk * 64, un.w0 - 1, un.h0 - 1, un.t + kd - 1, un.sample);
+        tma_load_5d(smem_dy(stage), &map_dy, full_bar(stage), 0, un.w0, un.h0, un.t, un.sample);
+        if (++stage == WP_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == WG_MMA_WARP) {
+    const uint32_t mn = (1u << 15) | (1u << 16);
+    const uint32_t idesc_pair = make_idesc_16bit(128, 64, p.is_f16) | mn;
+    const uint32_t idesc_single = make_idesc_16bit(64, 64, p.is_f16) | mn;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (long long u = u_lo; u < u_hi; ++u) {
+      const WpUnit un = decode_wp_unit(p, u);
+      if (skipped(u, un.t)) continue;
+      mbar_wait(full_bar(stage), phase);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t xs = smem_x(stage), ds = smem_dy(stage);
+#pragma unroll
+        for (int j = 0; j < WP_H / 2; ++j) {  // K step = 16 voxels = h rows 2j, 2j+1 of the column
+          const uint64_t db = make_sw128_mn_desc2(ds + (uint32_t)(j * 16 * 128), 1024u, 1024u);
+          const uint32_t acc = (j > 0) ? 1u : accumulate;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint32_t row_pair = (uint32_t)((2 * j) * WP_PW + kw), row_single = (uint32_t)((2 * j + 2) * WP_PW + kw);
+            const uint64_t da_pair = make_sw128_mn_desc2(xs + row_pair * 128u, WP_PW * 128u, WP_PW * 128u);
+            const uint64_t da_single = make_sw128_mn_desc2(xs + row_single * 128u, WP_PW * 128u, WP_PW * 128u);
+            umma_bf16(tmem_base + (uint32_t)((2 * kw) * 64), da_pair, db, idesc_pair, acc);
+            umma_bf16(tmem_base + (uint32_t)((2 * kw + 1) * 64), da_single, db, idesc_single, acc);
+          }
+        }
+        umma_commit(empty_bar(stage));
+      }
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == WP_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    if (elect_one_sync()) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    // ------------------------------- epilogue warps 0..3: nine accumulators -> partial[cta][tap][cin][cout] -------
+    float *base = p.partial + (size_t)blockIdx.x * WP_PARTIAL_FLOATS;
+    mbar_wait(tmem_full, 0u);
+    tcgen05_fence_after();
+    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+    for (int a = 0; a < 6; ++a) {
+      const int kw = a >> 1;
+      const bool single = (a & 1) != 0;
+      // M = 128: TMEM lane = row (rows 0-63: kh = 0, rows 64-127: kh = 1).  M = 64: row r sits in lane (r % 16) +
+      // 32 * (r / 16), i.e. the first 16 lanes of each warp's quarter.
+      const int row = warp * 32 + lane;
+      const int kh = single ? 2 : (row >> 6);
+      const int ci = single ? warp * 16 + lane : (row & 63);
+      const bool valid = !single || lane < 16;
+      float *dst = base + ((size_t)(kh * 3 + kw) * 64 + ci) * 64;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + (uint32_t)(a * 64 + c0), v);
+        tmem_wait_ld();
+        if (valid) {
+          float4 *d4 = reinterpret_cast<float4 *>(dst + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            d4[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == WG_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, WP_TMEM_COLS);
+  }
+}
+
+// dW[co][cin_offset + chunk*64 + ci][kd][kh][kw] (+)= sum over the key's CTAs of partial[cta][kh*3+kw][ci][co]
+__global__ void wgrad_planes_finish_kernel(const float *__restrict__ partial, float *__restrict__ dw, int keys, int chunks,
+                                           int ctas_per_key, int cout, int cin_total, int cin_offset, int accumulate) {
+  const long long total = (long long)keys * 9 * 64 * cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    long long r = i / cout;
+    const int ci = (int)(r & 63);
+    r >>= 6;
+    const int tap9 = (int)(r % 9);
+    const int key = (int)(r / 9);
+    const int kd = key / chunks, chunk = key - kd * chunks;
+    float s = 0.0f;
+    for (int k = 0; k < ctas_per_key; ++k)
+      s += partial[(size_t)(key + k * keys) * WP_PARTIAL_FLOATS + ((size_t)tap9 * 64 + ci) * 64 + co];
+    float *o = dw + ((size_t)co * cin_total + cin_offset + chunk * 64 + ci) * 27 + kd * 9 + tap9;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
 // dW[co][cin_offset + ci][tap] (+)= sum over slices of partial[s][(tap*chunks + ci/64)*64 + ci%64][co]
 __global__ void wgrad_finish_kernel(const float *__restrict__ partial, float *__restrict__ dw, int kslices, int rows_total,
                                     int cout_pad, int cout, int chunks, int taps, int cin_total, int cin_offset,
@@ -305,7 +533,9 @@ using namespace dram;
 
 struct dram_wgrad_plan {
   CUtensorMap map_x, map_dy;
+  int planes;  // 1 = PLANES variant (wp), 0 = streaming variant (p)
   WgParams p;
+  WpParams wp;
   int block_n;
   float *dw;
   int cin_total, cin_offset, taps;
@@ -367,10 +597,37 @@ static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n) {
   return DRAM_OK;
 }
 
+// PLANES variant: geometry it supports and its launch shape (keys <= #SMs so that every CTA owns one key).
+static bool wp_supported(const dram_conv_desc *d) {
+  if (d->algo == DRAM_CONV_ALGO_TILES) return false;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  return d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->dd == 1 && d->dh == 1 &&
+         d->dw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && d->cout <= 64 && 3 * (d->c1 / 64) <= sms;
+}
+static void wp_geometry(const dram_conv_desc *d, WpParams *w) {
+  memset(w, 0, sizeof(*w));
+  w->n = d->n; w->D = d->di; w->H = d->hi; w->W = d->wi;
+  w->cols_w = ceil_div(d->wi, WP_W); w->cols_h = ceil_div(d->hi, WP_H);
+  w->columns = d->n * w->cols_w * w->cols_h;
+  w->chunks = d->c1 / 64;
+  w->keys = 3 * w->chunks;
+  w->upk = (long long)w->columns * d->di;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  long long per_key = sms / w->keys;
+  if (per_key > w->upk) per_key = w->upk;
+  w->ctas_per_key = (int)per_key;
+  w->is_f16 = d->dtype == DRAM_DTYPE_F16;
+}
+
 extern "C" int64_t dram_conv3d_wgrad_workspace_bytes(const dram_conv_desc *d) {
   WgParams p;
   int bn;
   if (wg_geometry(d, &p, &bn) != DRAM_OK) return -1;
+  if (wp_supported(d)) {
+    WpParams w;
+    wp_geometry(d, &w);
+    return (int64_t)w.keys * w.ctas_per_key * WP_PARTIAL_FLOATS * 4;
+  }
   return (int64_t)p.kslices * p.rows_total * p.cout_pad * 4;
 }
 
@@ -387,7 +644,7 @@ extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void
   DRAM_REQUIRE(cin_offset >= 0 && cin_offset + d->c1 <= cin_total,
                "dram_conv3d_wgrad_plan_create: channel range [%d, %d) outside cin_total %d", cin_offset,
                cin_offset + d->c1, cin_total);
-  const int64_t need = (int64_t)p.kslices * p.rows_total * p.cout_pad * 4;
+  const int64_t need = dram_conv3d_wgrad_workspace_bytes(d);
   DRAM_REQUIRE(workspace_bytes >= need, "dram_conv3d_wgrad_plan_create: workspace of %lld bytes, %lld needed",
                (long long)workspace_bytes, (long long)need);
   dram_wgrad_plan *pl = new dram_wgrad_plan();
@@ -400,6 +657,24 @@ extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void
   pl->cin_offset = cin_offset;
   pl->taps = d->kd * d->kh * d->kw;
   pl->flops = 2LL * d->n * p.Do * p.Ho * p.Wo * (int64_t)d->cout * d->c1 * pl->taps;
+  pl->planes = wp_supported(d) ? 1 : 0;
+  if (pl->planes) {
+    wp_geometry(d, &pl->wp);
+    pl->wp.partial = reinterpret_cast<float *>(workspace);
+    rc = encode_act_map(&pl->map_x, x, d->n, d->di, d->hi, d->wi, d->c1, 64, WP_PW, WP_PH, 1, 1, 1, 1, p.is_f16);
+    if (rc == DRAM_OK)
+      rc = encode_act_map(&pl->map_dy, dy, d->n, p.Do, p.Ho, p.Wo, d->cout, 64, WP_W, WP_H, 1, 1, 1, 1, p.is_f16);
+    if (rc == DRAM_OK)
+      rc = check_cuda(cudaFuncSetAttribute(conv3d_wgrad_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WP_SMEM_BYTES),
+                      "cudaFuncSetAttribute(conv3d_wgrad_planes_kernel)");
+    if (rc != DRAM_OK) {
+      delete pl;
+      return rc;
+    }
+    *plan = pl;
+    return DRAM_OK;
+  }
   rc = encode_act_map(&pl->map_x, x, d->n, d->di, d->hi, d->wi, d->c1, 64, WG_TW, WG_TH, WG_TD, d->sw, d->sh, d->sd,
                       p.is_f16);
   if (rc == DRAM_OK)
@@ -431,15 +706,26 @@ extern "C" int dram_conv3d_wgrad_plan_info(const dram_wgrad_plan *plan, int64_t 
                                            int32_t *block_n) {
   DRAM_REQUIRE(plan, "dram_conv3d_wgrad_plan_info: null plan");
   if (flops) *flops = plan->flops;
-  if (items) *items = plan->p.items_total;
-  if (kslices) *kslices = plan->p.kslices;
-  if (block_n) *block_n = plan->block_n;
+  if (items) *items = plan->planes ? plan->wp.keys * plan->wp.ctas_per_key : plan->p.items_total;
+  if (kslices) *kslices = plan->planes ? plan->wp.ctas_per_key : plan->p.kslices;
+  if (block_n) *block_n = plan->planes ? -64 : plan->block_n;  // negative: PLANES variant
   return DRAM_OK;
 }
 
 extern "C" int dram_conv3d_wgrad_run(const dram_wgrad_plan *plan, int32_t accumulate, int32_t max_ctas, void *stream) {
   DRAM_REQUIRE(plan, "dram_conv3d_wgrad_run: null plan");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (plan->planes) {  // the grid is part of the plan (one key per CTA): max_ctas does not apply
+    const WpParams &w = plan->wp;
+    conv3d_wgrad_planes_kernel<<<w.keys * w.ctas_per_key, WG_THREADS, WP_SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, w);
+    DRAM_CHECK_LAUNCH("conv3d_wgrad_planes_kernel launch");
+    const long long total = (long long)w.keys * 9 * 64 * plan->p.cout;
+    wgrad_planes_finish_kernel<<<stream_grid(total, 256), 256, 0, st>>>(w.partial, plan->dw, w.keys, w.chunks,
+                                                                       w.ctas_per_key, plan->p.cout, plan->cin_total,
+                                                                       plan->cin_offset, accumulate ? 1 : 0);
+    DRAM_CHECK_LAUNCH("wgrad_planes_finish_kernel launch");
+    return DRAM_OK;
+  }
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   if (plan->p.items_total < ctas) ctas = plan->p.items_total;

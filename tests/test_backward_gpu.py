@@ -47,6 +47,8 @@ def _close_dx(got, ref, what, dtype):
 WGRAD_CASES = [
     # n, dims, cin, cout, k, stride, dil
     (1, (8, 8, 8), 64, 64, 3, 1, 1),
+    (1, (1, 16, 8), 64, 64, 3, 1, 1),
+    (2, (20, 33, 19), 64, 64, 3, 1, 1),
     (2, (5, 9, 11), 64, 64, 3, 1, 1),
     (1, (6, 10, 9), 128, 64, 3, 1, 1),
     (1, (9, 10, 12), 64, 128, 3, 2, 1),
@@ -60,17 +62,22 @@ WGRAD_CASES = [
 
 @pytest.mark.parametrize("n,dims,cin,cout,k,stride,dil", WGRAD_CASES)
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_wgrad_matches_autograd(cuda, n, dims, cin, cout, k, stride, dil, dtype):
+@pytest.mark.parametrize("algo", ["auto", "tiles"])
+def test_wgrad_matches_autograd(cuda, n, dims, cin, cout, k, stride, dil, dtype, algo):
     from dram_b200 import backward, ops
 
     if dtype == torch.float16 and (cout, dil) not in ((64, 1), (256, 2)):
         pytest.skip("fp16 re-runs a subset")
+    planes_shape = k == 3 and stride == 1 and dil == 1 and cout <= 64
+    if algo == "tiles" and not planes_shape:
+        pytest.skip("the streaming kernel is what auto picks for this shape")
     x, w, dy, _, dw_ref, k3, pad = _case(cuda, n, dims, cin, cout, k, stride, dil, dtype)
     plan = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x.to(cuda), dtype), ops.to_ndhwc_16(dy.to(cuda), dtype),
-                                    kernel=k3, stride=stride, dilation=dil, padding=pad)
+                                    kernel=k3, stride=stride, dilation=dil, padding=pad, algo=algo)
+    assert plan.algo == ("planes" if planes_shape and algo == "auto" else "stream")
     dw = plan.run().cpu()
     torch.cuda.synchronize()
-    _close_dw(dw, dw_ref, f"wgrad {cin}->{cout} k{k} s{stride} d{dil} (items {plan.items}, slices {plan.kslices})")
+    _close_dw(dw, dw_ref, f"wgrad[{plan.algo}] {cin}->{cout} k{k} s{stride} d{dil} (items {plan.items}, slices {plan.kslices})")
     # deterministic: a second run reproduces the bits; accumulate adds
     dw2 = plan.run().clone()
     assert torch.equal(dw2.cpu(), dw)
@@ -84,7 +91,7 @@ def test_wgrad_slices_agree(cuda):
 
     x, w, dy, _, dw_ref, k3, pad = _case(cuda, 1, (16, 16, 16), 64, 64, seed=3)
     plan = backward.Conv3dWgradPlan(ops.to_ndhwc_16(x.to(cuda), torch.bfloat16), ops.to_ndhwc_16(dy.to(cuda), torch.bfloat16),
-                                    kernel=k3, padding=pad)
+                                    kernel=k3, padding=pad, algo="tiles")
     a = plan.run().clone()
     b = plan.run(max_ctas=5).clone()
     assert plan.kslices > 1
