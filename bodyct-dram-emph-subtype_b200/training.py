@@ -1,0 +1,326 @@
+"""Training step of the Med3D seg-reg network on the backward kernels (BASELINE config 5) — a
+first, *hybrid* slice.
+
+What runs where, stated plainly:
+
+* every convolution — forward, data gradient and weight gradient, >99.9 % of the FLOPs of a training step — runs on
+  the hand-written sm_100a kernels (`ops.Conv3dPlan`, `ops.stem_conv7`, `backward.Conv3dDgradPlan`,
+  `backward.Conv3dWgradPlan`) through `ConvFn` / `StemFn`, autograd Functions over NDHWC bf16 activations;
+* the memory-bound glue of training — train-mode BatchNorm (batch statistics + running-stat update), ReLU, residual
+  add, max-pool, x2 trilinear up-sampling, the sigmoid heads, lobe-masked pooling, the three losses and Adam — is still
+  ATen CUDA code driven by autograd on channels-last views of the same buffers (cuDNN disabled).  Hand-written
+  replacements of these are the remaining work of this row; until then `bench.py` reports no training number.
+
+The module takes the drop-in network (`med3d.resnet{18,34,50}segreg()`, reference `state_dict` keys) and reproduces
+what the reference does in `ScanRegLightningModule.shared_step(TRAIN)` (models.py:530-570): forward in train mode
+(med3d.py:369-388), loss = interval regression x2 + 2 x dice + BCE (models.py:495-518, metrics.py:4-47), backward.
+Data-parallel training (train.py:100 `strategy=ddp`) averages the gradients over the process group with one
+all-reduce per bucket (`backward.GradBuckets`; NCCL over NVLink on the GPUs).
+Quirk kept: shortcut type A carries no gradient (`out.data`, med3d.py:110).
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .backward import Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
+from .engine import LAYER_CFG
+
+ACT = torch.bfloat16  # activations and their gradients
+# Test hook: a list here receives (layer name, [sources], dy, weight, [dx per source], dw) clones from every
+# ConvFn.backward so that each layer's dgrad / wgrad can be checked in isolation on the tensors it really saw.
+BACKWARD_TAP = None
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+def _ncdhw(x):
+    """NDHWC tensor -> NCDHW-logical view (channels_last_3d strides) for ATen ops; no copy."""
+    return x.permute(0, 4, 1, 2, 3)
+
+
+def _ndhwc(v):
+    """NCDHW-logical tensor -> contiguous NDHWC (no copy when it already is channels-last)."""
+    return v.permute(0, 2, 3, 4, 1).contiguous()
+
+
+class _PlanCache:
+    """Plans bake device pointers into TMA tensor maps; tensors produced by ATen move between steps only while the
+    caching allocator warms up, so a layer keeps the plan of the last pointer set it saw."""
+
+    def __init__(self):
+        self.key, self.plan = None, None
+
+    def get(self, key, make):
+        if self.key != key:
+            self.plan = None  # release the old buffers first
+            self.plan, self.key = make(), key
+        return self.plan
+
+
+class ConvLayer:
+    """Per-convolution state: geometry + cached forward / dgrad / wgrad plans (index = source of a concatenation)."""
+
+    def __init__(self, name, kernel, stride, dilation):
+        self.name, self.k, self.s, self.dl = name, kernel, stride, dilation
+        self.fwd, self.dgrad, self.wgrad = _PlanCache(), [_PlanCache(), _PlanCache()], [_PlanCache(), _PlanCache()]
+        self.zero_bias = None
+        self.dw = None  # fp32 [Cout, Cin_total, kd, kh, kw], shared by the wgrad plans of both sources
+
+
+class ConvFn(torch.autograd.Function):
+    """y = conv3d(cat([x1, x2]), weight) (+ bias) on NDHWC bf16; x2 optional (decoder concat, med3d.py:87)."""
+
+    @staticmethod
+    def forward(ctx, layer, weight, bias, x1, x2):
+        srcs = [x1] if x2 is None else [x1, x2]
+        cout = weight.shape[0]
+        if layer.zero_bias is None or layer.zero_bias.device != x1.device:
+            layer.zero_bias = torch.zeros(cout, dtype=torch.float32, device=x1.device)
+        packed = ops.pack_conv_weight(weight, dtype=ACT)
+
+        def make():
+            w_buf, b_buf = torch.empty_like(packed), torch.zeros_like(layer.zero_bias)
+            plan = ops.Conv3dPlan(x1, w_buf, b_buf, x2=x2, kernel=layer.k, stride=layer.s, dilation=layer.dl, relu=False)
+            return plan, w_buf, b_buf
+
+        plan, w_buf, b_buf = layer.fwd.get(tuple(t.data_ptr() for t in srcs) + tuple(x1.shape), make)
+        w_buf.copy_(packed)
+        if bias is not None:
+            b_buf.copy_(bias.detach())
+        out = plan.run().detach()  # a fresh alias: the plan-owned buffer itself never carries autograd history
+        ctx.layer, ctx.has_bias = layer, bias is not None
+        ctx.save_for_backward(weight, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        weight, *srcs = ctx.saved_tensors
+        dy = dy.contiguous()
+        cin_total = weight.shape[1]
+        if layer.dw is None or layer.dw.device != dy.device:
+            layer.dw = torch.zeros(tuple(weight.shape), dtype=torch.float32, device=dy.device)
+        grads, off = [None, None], 0
+        for i, x in enumerate(srcs):
+            c = x.shape[4]
+            wp = layer.wgrad[i].get((x.data_ptr(), dy.data_ptr()) + tuple(x.shape), lambda: Conv3dWgradPlan(
+                x, dy, dw=layer.dw, kernel=layer.k, stride=layer.s, dilation=layer.dl, cin_total=cin_total, cin_offset=off))
+            wp.run()
+            if ctx.needs_input_grad[3 + i]:
+                dp = layer.dgrad[i].get((dy.data_ptr(),) + tuple(x.shape), lambda: Conv3dDgradPlan(
+                    dy, weight, tuple(x.shape[1:4]), kernel=layer.k, stride=layer.s, dilation=layer.dl,
+                    cin_range=(off, off + c)))
+                dp.packed.copy_(pack_dgrad_weight(weight, dtype=ACT, cin_range=(off, off + c)))
+                grads[i] = dp.run().detach()
+            off += c
+        db = dy.float().sum(dim=(0, 1, 2, 3)) if ctx.has_bias else None
+        if BACKWARD_TAP is not None:
+            BACKWARD_TAP.append((layer.name, [x.clone() for x in srcs], dy.clone(), weight.detach().clone(),
+                                 [None if g is None else g.clone() for g in grads[:len(srcs)]], layer.dw.clone()))
+        # AccumulateGrad adds layer.dw into weight.grad right away (stream order), so the shared buffer can be reused
+        return None, layer.dw, db, grads[0], grads[1]
+
+
+class StemFn(torch.autograd.Function):
+    """conv1 (7^3, stride 2, 1 -> 64, med3d.py:296-304) on the fused stem kernel; its weight gradient goes through the
+    (kh, kw)-unfolded image (K2a) and the streaming wgrad kernel as a 7x1x1 convolution over 64 pseudo-channels."""
+
+    @staticmethod
+    def forward(ctx, layer, weight, image):
+        if layer.zero_bias is None or layer.zero_bias.device != image.device:
+            layer.zero_bias = torch.zeros(64, dtype=torch.float32, device=image.device)
+        packed = ops.pack_stem_weight_fused(weight, dtype=ACT)
+        out = ops.stem_conv7(image, packed, layer.zero_bias, relu=False)
+        ctx.layer = layer
+        ctx.save_for_backward(image)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        (image,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        unfolded = ops.stem_expand(image, dtype=ACT)  # [N, D, H', W', kh*8 + kw]
+        wp = layer.wgrad[0].get((unfolded.data_ptr(), dy.data_ptr()) + tuple(image.shape), lambda: Conv3dWgradPlan(
+            unfolded, dy, kernel=(7, 1, 1), stride=(2, 1, 1), dilation=1, padding=(3, 0, 0)))
+        dwp = wp.run()  # [64, 64 pseudo-channels, 7, 1, 1]
+        dw = dwp.view(64, 8, 8, 7)[:, :7, :7, :].permute(0, 3, 1, 2).reshape(64, 1, 7, 7, 7).contiguous()
+        return None, dw, None
+
+
+class TrainableMed3D:
+    """Functional train-mode forward of a drop-in seg-reg network (basic or bottleneck blocks) with gradients."""
+
+    def __init__(self, model):
+        if getattr(model, "head_kind", "reg") != "reg":
+            raise ValueError("TrainableMed3D: the regression networks (med3ddram*) are the trained ones (train.py:72)")
+        self.model = model
+        self.layers = {}
+
+    def _layer(self, name, conv):
+        lay = self.layers.get(name)
+        if lay is None:
+            lay = ConvLayer(name, tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.dilation))
+            self.layers[name] = lay
+        return lay
+
+    def _conv(self, name, conv, x1, x2=None):
+        return ConvFn.apply(self._layer(name, conv), conv.weight, conv.bias, x1, x2)
+
+    @staticmethod
+    def _bn(bn, x, relu=True):
+        y = F.batch_norm(_ncdhw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, True, BN_MOMENTUM, bn.eps)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        if relu:
+            y = torch.relu(y)
+        return _ndhwc(y)
+
+    def _block(self, name, blk, x, planes_out):
+        if hasattr(blk, "conv3"):  # Bottleneck, med3d.py:164-184
+            out = self._bn(blk.bn1, self._conv(name + ".conv1", blk.conv1, x))
+            out = self._bn(blk.bn2, self._conv(name + ".conv2", blk.conv2, out))
+            out = self._bn(blk.bn3, self._conv(name + ".conv3", blk.conv3, out), relu=False)
+            stride = blk.conv2.stride[0]
+        else:  # BasicBlock, med3d.py:129-144
+            out = self._bn(blk.bn1, self._conv(name + ".conv1", blk.conv1, x))
+            out = self._bn(blk.bn2, self._conv(name + ".conv2", blk.conv2, out), relu=False)
+            stride = blk.conv1.stride[0]
+        res = x
+        if stride != 1 or x.shape[4] != planes_out:  # shortcut type A (med3d.py:103-112): no gradient (out.data)
+            res = x.detach()[:, ::stride, ::stride, ::stride, :]
+            res = F.pad(res, (0, planes_out - res.shape[4]))
+        return torch.relu(out + res)
+
+    def _up(self, name, us, x, skip):
+        up = F.interpolate(_ncdhw(x).float(), scale_factor=2, mode="trilinear", align_corners=True).to(ACT)
+        up = _ndhwc(up)
+        if tuple(up.shape[1:4]) != tuple(skip.shape[1:4]):
+            raise ValueError(f"{name}: up-sampled {tuple(up.shape)} vs skip {tuple(skip.shape)} (input dims must be 8k)")
+        y = self._bn(us.conv_blocks[0][1], self._conv(name + ".conv_blocks.0.0", us.conv_blocks[0][0], up, skip))
+        return self._bn(us.conv_blocks[1][1], self._conv(name + ".conv_blocks.1.0", us.conv_blocks[1][0], y))
+
+    def forward(self, image, lungs=None):
+        """image [B, D, H, W] fp32 (CUDA), lungs [B, D, H, W] float 0/1 or None ->
+        (dense_outs: 2 x fp32 [B, 1, D/2, H/2, W/2], reg_outs: 2 x fp32 [B]) as med3d.py:369-388."""
+        m = self.model
+        B = image.shape[0]
+        with torch.backends.cudnn.flags(enabled=False):
+            c1 = StemFn.apply(self._layer("conv1", m.conv1), m.conv1.weight, image.float().contiguous())
+            x = self._bn(m.bn1, c1)
+            y = _ndhwc(F.max_pool3d(_ncdhw(x), kernel_size=3, stride=2, padding=1))
+            feats = []
+            for li, stage in enumerate((m.layer1, m.layer2, m.layer3, m.layer4), start=1):
+                planes_out = LAYER_CFG[li - 1][0] * m.expansion
+                for bi, blk in enumerate(stage):
+                    y = self._block(f"layer{li}.{bi}", blk, y, planes_out)
+                feats.append(y)
+            xup1 = self._up("us1", m.us1, feats[3], feats[0])
+            xup2 = self._up("us2", m.us2, xup1, x)
+            xup3 = self._bn(m.us3[1], self._conv("us3.0", m.us3[0], xup2))
+            v = xup3.float()  # [B, D, H, W, 32]; the 1x1x1 heads (med3d.py:329-332, 382) are a 32-long dot per voxel
+            dense = [torch.sigmoid(v @ fc.weight.view(fc.weight.shape[0], 32).t() + fc.bias).permute(0, 4, 1, 2, 3)
+                     for fc in m.fcs]
+            if lungs is None:
+                mask = torch.ones((B, 1) + tuple(dense[0].shape[2:]), device=image.device)
+            else:
+                mask = F.interpolate(lungs.view(B, 1, *lungs.shape[-3:]).float(), dense[0].shape[-3:], mode="nearest")
+            regs = [(d * mask).view(B, -1).sum(dim=-1) / mask.view(B, -1).sum(dim=-1) for d in dense]
+        return dense, regs
+
+
+# ------------------------------------------------------------------------------------------
+# losses of ScanRegLightningModule (models.py:495-518, metrics.py)
+# ------------------------------------------------------------------------------------------
+BETA, GAMMA = 0.7338, 0.2578  # models.py:412-413
+
+
+def regression_label_bands(labels, ratio_mapping, tightness=1.0):
+    """models.py:477-493: class index -> (lo, hi) band of the lesion ratio; class 0 collapses to (0, 0)."""
+    bands = []
+    for c in labels:
+        lo, hi = ratio_mapping[int(c)]
+        if lo < 1e-7:
+            bands.append((0.0, 0.0))
+        else:
+            mid, span = (lo + hi) / 2.0, (hi - lo) * tightness / 2.0
+            bands.append((mid - span, mid + span))
+    return torch.tensor(bands, dtype=torch.float32)
+
+
+def interval_regression_loss(outs, bands, weights):
+    """models.py:495-506."""
+    d = torch.cat([outs.unsqueeze(1), bands], dim=1)
+    d = BETA * d ** GAMMA
+    K = (0.5 * (d[:, 2] - d[:, 1])) ** 2
+    unhinged = (d[:, 0] - (d[:, 2] + d[:, 1]) / 2.0) ** 2 - K
+    return (10.0 * F.leaky_relu(unhinged, negative_slope=0.0) * weights).sum()
+
+
+def dice_coef(y, y_hat, smooth=1e-7):
+    """metrics.py:33-37."""
+    inter = (y_hat.reshape(-1) * y.reshape(-1)).sum()
+    return (2.0 * inter + smooth) / (y.sum() + y_hat.sum() + smooth)
+
+
+def masked_bce(y, y_hat, mask, smoothness=0.85, eps=1e-6):
+    """metrics.py:10-30 (BinaryCrossEntropy.__call__ with a mask)."""
+    t = y.float()
+    alpha = (1.0 - t.sum() / t.shape[0]).clamp(0.3, 0.7)
+    pt = y_hat * t + (1.0 - y_hat) * (1.0 - t)
+    w = alpha * t + (1.0 - alpha) * (1.0 - t)
+    logp = torch.log(pt.clamp(eps, 1.0 - eps))
+    nll = -1.0 * (smoothness * logp * w * mask + logp * w * (1.0 - mask))
+    return nll.sum() / w.sum()
+
+
+def training_loss(dense, regs, lungs, ems, cle_labels, pse_labels, cle_bands, pse_bands, cle_weights, pse_weights):
+    """models.py:547-565: loss_cle + loss_pse + 2 * mul_loss + seg_loss.  lungs/ems [B, D, H, W] float 0/1."""
+    B = lungs.shape[0]
+    loss_cle = interval_regression_loss(regs[0], cle_bands, cle_weights)
+    loss_pse = interval_regression_loss(regs[1], pse_bands, pse_weights)
+    binary = torch.logical_or(cle_labels > 0, pse_labels > 0).float().view(B, 1, 1, 1, 1)
+    size = dense[0].shape[-3:]
+    seg_labels = F.interpolate(ems.view(B, 1, *ems.shape[-3:]).float() * binary, size, mode="nearest").detach()
+    lung_labels = F.interpolate(lungs.view(B, 1, *lungs.shape[-3:]).float(), size, mode="nearest")
+    mul_loss = dice_coef(dense[0] * lung_labels, dense[1] * lung_labels)
+    both = torch.clamp(dense[0] + dense[1], min=0.0, max=1.0)
+    seg_loss = masked_bce(seg_labels, both, lung_labels, smoothness=0.85)
+    return loss_cle + loss_pse + 2.0 * mul_loss + seg_loss
+
+
+class TrainStep:
+    """forward -> loss -> backward -> gradient average over the process group -> Adam (models.py:685-698, lr from args).
+
+    Gradients live in one flat fp32 buffer (`GradBuckets`, parameters in reverse registration order, i.e. roughly the
+    order backward produces them) whose buckets are all-reduced asynchronously.
+    """
+
+    def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None):
+        self.net = TrainableMed3D(model)
+        self.params = [(n, p) for n, p in model.named_parameters()]
+        dev = self.params[0][1].device
+        self.buckets = GradBuckets([(n, tuple(p.shape)) for n, p in reversed(self.params)], dev, bucket_bytes)
+        for n, p in self.params:
+            p.grad = self.buckets.view(n)
+        self.opt = torch.optim.Adam([p for _, p in self.params], lr=lr)
+        self.group = group
+
+    def zero_grad(self):
+        self.buckets.flat.zero_()
+
+    def step(self, batch, cle_bands, pse_bands, cle_weights, pse_weights):
+        self.zero_grad()
+        lungs = batch["lung_mask"].float()
+        dense, regs = self.net.forward(batch["image"], lungs)
+        loss = training_loss(dense, regs, lungs, batch["em_mask"].float(), batch["cls_label"], batch["pse_label"],
+                             cle_bands, pse_bands, cle_weights, pse_weights)
+        loss.backward()
+        for n, p in self.params:  # autograd accumulates into the bucket views in place; keep them attached
+            if p.grad is not None and p.grad.data_ptr() != self.buckets.view(n).data_ptr():
+                self.buckets.view(n).copy_(p.grad)
+                p.grad = self.buckets.view(n)
+        for i in range(self.buckets.num_buckets):
+            self.buckets.reduce_bucket(i, self.group)
+        self.buckets.wait()
+        self.opt.step()
+        return loss.detach()

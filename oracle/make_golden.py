@@ -106,6 +106,62 @@ def gen_predict_step(ref):
     print("predict_step", fix["cle_precentages"].tolist(), fix["pse_precentages"].tolist(), fix["cle_labels"].tolist())
 
 
+def gen_train_step(ref):
+    """One training step of the UNMODIFIED reference network (train mode) with the reference's own loss code
+    (models.py:477-518, 547-565; metrics.py) on CPU: loss, outputs and a fingerprint of every parameter gradient."""
+    from types import SimpleNamespace
+
+    from oracle import training_oracle as T
+
+    case = T.train_case()
+    arch, B = case["arch"], case["batch"]
+    model = ref_shim.model(arch)
+    ref.utils.load_state_dict_greedy(model, case["sd"])
+    model.train()
+    lm = ref.models.ScanRegLightningModule
+    me = SimpleNamespace(beta=0.7338, gamma=0.2578, dice_score=ref.models.BinaryDice(1e-7), bce=ref.models.BinaryCrossEntropy())
+    ds = ref.dataset.COPDGeneSubtyping
+
+    def bands(labels, mapping):  # models.py:477-493 without the .cuda()
+        out = []
+        for c in labels:
+            lo, hi = mapping[int(c)]
+            if lo < 1e-7:
+                out.append((0.0, 0.0))
+            else:
+                m, span = (lo + hi) / 2.0, (hi - lo) * 1.0 / 2.0
+                out.append((m - span, m + span))
+        return torch.FloatTensor(out)
+
+    scans = case["image"].unsqueeze(1)
+    lungs = case["lung_mask"].unsqueeze(1).float()
+    ems = case["em_mask"].unsqueeze(1).float()
+    cle, pse = case["cls_label"], case["pse_label"]
+    cle_b, pse_b = bands(cle, ds.cle_ratio_map), bands(pse, ds.pse_ratio_map)
+    dense, regs = model(scans, lungs)
+    loss_cle = lm._interval_regression_loss(me, regs[0], cle_b, case["cle_weights"])
+    loss_pse = lm._interval_regression_loss(me, regs[1], pse_b, case["pse_weights"])
+    binary = torch.logical_or(cle > 0, pse > 0).long()
+    seg_labels = torch.nn.functional.interpolate(ems * binary.float().view(B, 1, 1, 1, 1), dense[0].shape[-3:],
+                                                 mode="nearest").detach()
+    lung_labels = torch.nn.functional.interpolate(lungs, size=dense[0].shape[-3:], mode="nearest")
+    mul_loss, seg_loss = lm._segmentation_loss(me, dense[0], dense[1], seg_labels, lung_labels)
+    loss = loss_cle + loss_pse + 2.0 * mul_loss + seg_loss
+    loss.backward()
+    grads = {n: p.grad for n, p in model.named_parameters()}
+    small = {n: g.clone() for n, g in grads.items() if g.numel() <= 4096}
+    fix = {
+        "arch": arch, "dims": case["dims"], "batch": B, "weight_seed": case["weight_seed"],
+        "weight_checksum": synthetic.state_dict_checksum(case["sd"]),
+        "loss": float(loss), "parts": [float(loss_cle), float(loss_pse), float(mul_loss), float(seg_loss)],
+        "cle_bands": cle_b, "pse_bands": pse_b,
+        "dense_outs": [d.detach().clone() for d in dense], "reg_outs": [r.detach().clone() for r in regs],
+        "grad_summary": T.grad_summary(grads), "small_grads": small,
+    }
+    torch.save(fix, os.path.join(GOLDEN, "train_step_med3ddram18.pt"))
+    print("train_step loss", fix["loss"], fix["parts"], "params", len(grads))
+
+
 def gen_transforms(ref):
     from argparse import Namespace
 
@@ -169,7 +225,7 @@ def main():
     torch.manual_seed(0)
     ref = ref_shim.load()
     steps = {"layouts": gen_layouts, "forward": gen_forward, "predict": gen_predict_step,
-             "transforms": gen_transforms, "labels": gen_labels}
+             "transforms": gen_transforms, "labels": gen_labels, "train": gen_train_step}
     for name, fn in steps.items():
         if not args.only or name in args.only.split(","):
             fn(ref)

@@ -39,9 +39,14 @@ def batch_norm_eval(sd, prefix, x):
                         sd[prefix + ".bias"], False, 0.0, BN_EPS)
 
 
+# med3d.py:110 builds the shortcut from `out.data`: in training no gradient flows through shortcut type A.
+# The training oracle switches this on; the forward value is the same either way.
+SHORTCUT_DETACH = False
+
+
 def shortcut_a(x, planes, stride):
     """med3d.py:103-112: avg_pool3d(kernel 1, stride) is a strided subsample; pad channels with zeros."""
-    out = x[:, :, ::stride, ::stride, ::stride]
+    out = (x.detach() if SHORTCUT_DETACH else x)[:, :, ::stride, ::stride, ::stride]
     pad = planes - out.shape[1]
     if pad > 0:
         out = torch.cat([out, out.new_zeros((out.shape[0], pad) + tuple(out.shape[2:]))], dim=1)

@@ -138,3 +138,40 @@ def test_oracle_against_live_reference():
         assert torch.equal(a, b)
     for a, b in zip(r_ref, r_or):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# training step: the oracle against the unmodified reference's loss and gradients
+# ------------------------------------------------------------------------------------------
+def test_training_oracle_matches_reference_golden():
+    from oracle import training_oracle as T
+
+    fix = torch.load(os.path.join(GOLDEN, "train_step_med3ddram18.pt"), weights_only=False)
+    case = T.train_case()
+    assert (case["arch"], tuple(case["dims"]), case["batch"]) == (fix["arch"], tuple(fix["dims"]), fix["batch"])
+    assert abs(synthetic.state_dict_checksum(case["sd"]) - fix["weight_checksum"]) <= 1e-6 * abs(fix["weight_checksum"])
+    loss, grads, dense, regs = T.train_step_grads(
+        case["sd"], case["arch"], case["image"], case["lung_mask"], case["em_mask"], case["cls_label"],
+        case["pse_label"], fix["cle_bands"], fix["pse_bands"], case["cle_weights"], case["pse_weights"])
+    assert abs(float(loss) - fix["loss"]) <= 1e-5 * abs(fix["loss"])
+    for a, b in zip(dense + regs, fix["dense_outs"] + fix["reg_outs"]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    assert set(grads) == set(fix["grad_summary"])
+    summ = T.grad_summary(grads)
+    scale = max(v[0] for v in fix["grad_summary"].values())
+    for name, (norm, proj) in fix["grad_summary"].items():
+        assert abs(summ[name][0] - norm) <= 2e-3 * norm + 1e-6 * scale, (name, summ[name], norm)
+        assert abs(summ[name][1] - proj) <= 2e-3 * norm + 1e-6 * scale, (name, summ[name], proj)
+    for name, g in fix["small_grads"].items():
+        assert torch.allclose(grads[name], g, rtol=2e-3, atol=2e-3 * float(g.abs().max()) + 1e-9), name
+
+
+def test_label_bands_follow_the_ratio_maps():
+    from oracle import training_oracle as T
+
+    fix = torch.load(os.path.join(GOLDEN, "train_step_med3ddram18.pt"), weights_only=False)
+    labels = json.load(open(os.path.join(GOLDEN, "labels.json")))
+    case = T.train_case()
+    for key, lab, want in (("cle_map", case["cls_label"], fix["cle_bands"]), ("pse_map", case["pse_label"], fix["pse_bands"])):
+        mapping = {int(k): tuple(v) for k, v in labels[key].items()}
+        assert torch.equal(T.label_bands(lab, mapping), want)
