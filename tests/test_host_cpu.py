@@ -218,3 +218,64 @@ def test_grow_bbox_equals_reference_find_crops():
         want = [(s.start, s.stop) for s in P.find_crops(mask, spacing, 5)]
         assert grow_bbox(bbox, mask.shape, spacing, 5) == want
         assert grow_bbox(bbox, mask.shape, spacing, 0) == [(bbox[0], bbox[1]), (bbox[2], bbox[3]), (bbox[4], bbox[5])]
+
+
+GRAD_BUCKET_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, sys.argv[1])
+import torch
+import torch.distributed as dist
+import dram_b200
+from dram_b200.backward import GradBuckets
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+shapes = [("fcs.0.weight", (1, 32, 1, 1, 1)), ("us3.0.weight", (32, 64, 3, 3, 3)), ("layer1.0.conv1.weight", (64, 64, 3, 3, 3)),
+          ("conv1.weight", (64, 1, 7, 7, 7))]
+b = GradBuckets(shapes, torch.device("cpu"), bucket_bytes=200000)
+for i, (name, shape) in enumerate(shapes):
+    b.view(name).fill_(float((rank + 1) * (i + 1)))
+for i in range(b.num_buckets):
+    b.reduce_bucket(i)
+b.wait()
+want = [(1 + 2) / 2.0 * (i + 1) for i in range(len(shapes))]
+ok = all(bool((b.view(n) == w).all()) for (n, _), w in zip(shapes, want))
+if rank == 0:
+    print(json.dumps({"ok": ok, "buckets": b.num_buckets, "numel": b.flat.numel(), "bounds": b.bounds}))
+dist.destroy_process_group()
+'''
+
+
+def test_gradient_buckets_average_over_two_ranks_gloo(tmp_path):
+    """Host logic of the data-parallel exchange (training.TrainStep / backward.GradBuckets) at world size 2 on CPU:
+    views alias the flat buffer, buckets close at the byte threshold, every bucket is averaged over the ranks."""
+    script = tmp_path / "bucket_worker.py"
+    script.write_text(GRAD_BUCKET_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29671", str(script), ROOT],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"] and res["buckets"] == 3, res
+    assert res["numel"] == 32 + 32 * 64 * 27 + 64 * 64 * 27 + 64 * 343
+
+
+def test_dgrad_weight_packing_is_the_transposed_flipped_filter():
+    """pack_dgrad_weight (CPU-side logic of the data gradient): conv3d(dy, W') with W' = flipped, channel-transposed W
+    equals conv_transpose3d(dy, W) — checked with torch on CPU, including a channel slice of a concatenated input."""
+    import torch.nn.functional as F
+
+    from dram_b200.backward import pack_dgrad_weight
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn((64, 128, 3, 3, 3), generator=g)
+    dy = torch.randn((1, 64, 5, 6, 7), generator=g)
+    for dil, rng in ((1, None), (2, (64, 128))):
+        packed = pack_dgrad_weight(w, dtype=torch.float32, cin_range=rng)  # [Cin, 27 * Cout], tap-major
+        cin = packed.shape[0]
+        wt = packed.view(cin, 3, 3, 3, 64).permute(0, 4, 1, 2, 3)
+        got = F.conv3d(dy, wt, None, 1, dil, dil)
+        ref = F.conv_transpose3d(dy, w, None, 1, dil, 0, 1, dil)
+        ref = ref if rng is None else ref[:, rng[0]:rng[1]]
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
