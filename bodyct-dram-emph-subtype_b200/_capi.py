@@ -81,6 +81,15 @@ SIGNATURES = {
     "dram_conv3d_wgrad_plan_destroy": (C.c_int, [_vp]),
     "dram_conv3d_wgrad_plan_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, _pi32, _pi32]),
     "dram_conv3d_wgrad_run": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "dram_bn_workspace_bytes": (_i64, [_i32]),
+    "dram_bn_stats": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "dram_bn_finalize": (C.c_int, [_vp, C.c_double, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "dram_bn_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _i32, _vp]),
+    "dram_bn_backward_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "dram_bn_backward_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "dram_upsample2x_backward": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_maxpool3d_backward_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    "dram_maxpool3d_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

@@ -22,6 +22,7 @@ import torch
 
 from . import _capi
 from ._capi import ConvDesc, check
+from . import ops
 from .ops import ACT_DTYPES, Conv3dPlan, _need, _need16, _p, _stream, _triple, pack_conv_weight
 
 
@@ -162,6 +163,133 @@ class Conv3dDgradPlan:
         if self._scatter is not None:
             self._scatter.copy_(self.dy)
         return self.plan.run(max_ctas)
+
+
+class Upsample2xFn(torch.autograd.Function):
+    """x2 trilinear up-sampling, align_corners=True (med3d.py:83, 86) on NDHWC 16-bit: K4 forward, K4T backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.in_shape = tuple(x.shape)
+        return ops.upsample2x(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, d, h, w, c = ctx.in_shape
+        dy = dy.contiguous()
+        dx = torch.empty(ctx.in_shape, dtype=dy.dtype, device=dy.device)
+        check(_capi.load().dram_upsample2x_backward(_p(dy), _p(dx), n, d, h, w, c, ACT_DTYPES[dy.dtype], _stream()),
+              "dram_upsample2x_backward")
+        return dx
+
+
+class MaxPool3dFn(torch.autograd.Function):
+    """MaxPool3d(3, stride 2, padding 1) (med3d.py:305) on NDHWC 16-bit: K3 forward, K3T backward (first maximum of a
+    window takes the gradient, as ATen)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.maxpool3d(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        n, d, h, w, c = x.shape
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        lib = _capi.load()
+        ws = torch.empty(int(lib.dram_maxpool3d_backward_workspace_bytes(n, d, h, w, c)), dtype=torch.uint8, device=x.device)
+        check(lib.dram_maxpool3d_backward(_p(x), _p(dy), _p(dx), _p(ws), n, d, h, w, c, ACT_DTYPES[x.dtype], _stream()),
+              "dram_maxpool3d_backward")
+        return dx
+
+
+_BN_WS = {}
+
+
+def _bn_workspace(c, device):
+    key = (device.index, c)
+    ws = _BN_WS.get(key)
+    if ws is None:
+        nbytes = _capi.load().dram_bn_workspace_bytes(c)
+        ws = _BN_WS[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+    return ws
+
+
+class BatchNormTrainFn(torch.autograd.Function):
+    """y = act(batch_norm_train(x) (+ res)) on NDHWC 16-bit rows (K10, `dram_bn_*`): batch statistics, running-stat
+    update (in place on the given buffers), ReLU and residual add fused; backward returns dx, dgamma, dbeta, dres.
+    `group` (a torch.distributed group, or True for the default group) all-reduces the per-channel sums between the
+    two phases of both reductions: SyncBatchNorm as train.py:101 asks for."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, res, relu, eps, momentum, group):
+        lib = _capi.load()
+        _need16(x, "bn_train x")
+        c = x.shape[-1]
+        m = x.numel() // c
+        dt = ACT_DTYPES[x.dtype]
+        if res is not None:
+            _need(res, x.dtype, "bn_train res")
+            if res.shape != x.shape:
+                raise ValueError(f"bn_train: residual {tuple(res.shape)} vs x {tuple(x.shape)}")
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        ws = _bn_workspace(c, x.device)
+        sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        check(lib.dram_bn_stats(_p(x), m, c, dt, _p(sums), _p(ws), _stream()), "dram_bn_stats")
+        count = float(m)
+        world = _sync_world(group)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(sums, group=None if group is True else group)
+            count *= world
+        scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=x.device) for _ in range(4))
+        check(lib.dram_bn_finalize(_p(sums), count, _p(g32), _p(b32), eps, momentum, _p(running_mean), _p(running_var),
+                                   _p(scale), _p(shift), _p(mean), _p(rstd), c, _stream()), "dram_bn_finalize")
+        out = torch.empty_like(x)
+        check(lib.dram_bn_apply(_p(x), _p(scale), _p(shift), _p(res), 1 if relu else 0, _p(out), m, c, dt, _stream()),
+              "dram_bn_apply")
+        ctx.save_for_backward(x, out if relu else None, mean, rstd, g32)
+        ctx.meta = (m, c, dt, group, res is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _capi.load()
+        x, y, mean, rstd, g32 = ctx.saved_tensors
+        m, c, dt, group, has_res = ctx.meta
+        dy = dy.contiguous()
+        ws = _bn_workspace(c, x.device)
+        sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        check(lib.dram_bn_backward_reduce(_p(dy), _p(x), _p(y), _p(mean), _p(rstd), m, c, dt, _p(sums), _p(ws), _stream()),
+              "dram_bn_backward_reduce")
+        dbeta, dgamma = sums[:c].float(), sums[c:].float()  # local sums: the gradient exchange averages them later
+        count = float(m)
+        world = _sync_world(group)
+        if world > 1:
+            import torch.distributed as dist
+
+            sums = sums.clone()
+            dist.all_reduce(sums, group=None if group is True else group)
+            count *= world
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res and ctx.needs_input_grad[5] else None
+        check(lib.dram_bn_backward_apply(_p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g32), _p(sums), count, _p(dx), _p(dres),
+                                         m, c, dt, _stream()), "dram_bn_backward_apply")
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def _sync_world(group):
+    if group is None or group is False:
+        return 1
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(None if group is True else group)
 
 
 class GradBuckets:

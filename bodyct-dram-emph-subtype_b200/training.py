@@ -6,10 +6,14 @@ What runs where, stated plainly:
 * every convolution — forward, data gradient and weight gradient, >99.9 % of the FLOPs of a training step — runs on
   the hand-written sm_100a kernels (`ops.Conv3dPlan`, `ops.stem_conv7`, `backward.Conv3dDgradPlan`,
   `backward.Conv3dWgradPlan`) through `ConvFn` / `StemFn`, autograd Functions over NDHWC bf16 activations;
-* the memory-bound glue of training — train-mode BatchNorm (batch statistics + running-stat update), ReLU, residual
-  add, max-pool, x2 trilinear up-sampling, the sigmoid heads, lobe-masked pooling, the three losses and Adam — is still
-  ATen CUDA code driven by autograd on channels-last views of the same buffers (cuDNN disabled).  Hand-written
-  replacements of these are the remaining work of this row; until then `bench.py` reports no training number.
+* train-mode BatchNorm with its ReLU and residual add (forward: statistics + running-stat update + apply; backward:
+  reduction + apply, optional SyncBatchNorm exchange between the phases) runs on the K10 kernels (`bn_train.cu`,
+  `backward.BatchNormTrainFn`);
+* max-pool and x2 trilinear up-sampling run on K3 / K4 forward and their gather-style adjoints K3T / K4T
+  (`train_glue.cu`, `backward.MaxPool3dFn` / `Upsample2xFn`);
+* what is left of the memory-bound glue — the 1x1x1 sigmoid heads, lobe-masked pooling, the three losses, bias
+  gradients, weight re-packing and Adam — is still ATen CUDA code driven by autograd (cuDNN disabled).  Hand-written replacements of these are the remaining work of this row; until then `bench.py` reports no
+  training number.
 
 The module takes the drop-in network (`med3d.resnet{18,34,50}segreg()`, reference `state_dict` keys) and reproduces
 what the reference does in `ScanRegLightningModule.shared_step(TRAIN)` (models.py:530-570): forward in train mode
@@ -22,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .backward import Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
+from .backward import BatchNormTrainFn, MaxPool3dFn, Upsample2xFn, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
 from .engine import LAYER_CFG
 
 ACT = torch.bfloat16  # activations and their gradients
@@ -150,11 +154,17 @@ class StemFn(torch.autograd.Function):
 class TrainableMed3D:
     """Functional train-mode forward of a drop-in seg-reg network (basic or bottleneck blocks) with gradients."""
 
-    def __init__(self, model):
+    def __init__(self, model, glue="native", sync_bn=None):
+        """glue: "native" = train-mode BatchNorm (+ReLU, +residual) on the K10 kernels; "aten" = the same through ATen
+        (kept for A/B checks).  sync_bn: None/False = per-rank statistics, True or a process group = SyncBatchNorm
+        (train.py:101)."""
         if getattr(model, "head_kind", "reg") != "reg":
             raise ValueError("TrainableMed3D: the regression networks (med3ddram*) are the trained ones (train.py:72)")
+        if glue not in ("native", "aten"):
+            raise ValueError(f"glue must be 'native' or 'aten', got {glue!r}")
         self.model = model
         self.layers = {}
+        self.glue, self.sync_bn = glue, sync_bn
 
     def _layer(self, name, conv):
         lay = self.layers.get(name)
@@ -166,34 +176,40 @@ class TrainableMed3D:
     def _conv(self, name, conv, x1, x2=None):
         return ConvFn.apply(self._layer(name, conv), conv.weight, conv.bias, x1, x2)
 
-    @staticmethod
-    def _bn(bn, x, relu=True):
-        y = F.batch_norm(_ncdhw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, True, BN_MOMENTUM, bn.eps)
+    def _bn(self, bn, x, relu=True, res=None):
+        """relu(bn(x) (+ res)) in train mode."""
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-        if relu:
-            y = torch.relu(y)
-        return _ndhwc(y)
+        if self.glue == "native":
+            return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, relu, bn.eps,
+                                          BN_MOMENTUM, self.sync_bn)
+        y = F.batch_norm(_ncdhw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, True, BN_MOMENTUM, bn.eps)
+        y = _ndhwc(y)
+        if res is not None:
+            y = y + res
+        return torch.relu(y) if relu else y
 
     def _block(self, name, blk, x, planes_out):
         if hasattr(blk, "conv3"):  # Bottleneck, med3d.py:164-184
             out = self._bn(blk.bn1, self._conv(name + ".conv1", blk.conv1, x))
             out = self._bn(blk.bn2, self._conv(name + ".conv2", blk.conv2, out))
-            out = self._bn(blk.bn3, self._conv(name + ".conv3", blk.conv3, out), relu=False)
+            last_bn, last = blk.bn3, self._conv(name + ".conv3", blk.conv3, out)
             stride = blk.conv2.stride[0]
         else:  # BasicBlock, med3d.py:129-144
             out = self._bn(blk.bn1, self._conv(name + ".conv1", blk.conv1, x))
-            out = self._bn(blk.bn2, self._conv(name + ".conv2", blk.conv2, out), relu=False)
+            last_bn, last = blk.bn2, self._conv(name + ".conv2", blk.conv2, out)
             stride = blk.conv1.stride[0]
         res = x
         if stride != 1 or x.shape[4] != planes_out:  # shortcut type A (med3d.py:103-112): no gradient (out.data)
             res = x.detach()[:, ::stride, ::stride, ::stride, :]
-            res = F.pad(res, (0, planes_out - res.shape[4]))
-        return torch.relu(out + res)
+            res = F.pad(res, (0, planes_out - res.shape[4])).contiguous()
+        return self._bn(last_bn, last, relu=True, res=res)  # relu(bn(conv) + residual), fused
 
     def _up(self, name, us, x, skip):
-        up = F.interpolate(_ncdhw(x).float(), scale_factor=2, mode="trilinear", align_corners=True).to(ACT)
-        up = _ndhwc(up)
+        if self.glue == "native":
+            up = Upsample2xFn.apply(x)
+        else:
+            up = _ndhwc(F.interpolate(_ncdhw(x).float(), scale_factor=2, mode="trilinear", align_corners=True).to(ACT))
         if tuple(up.shape[1:4]) != tuple(skip.shape[1:4]):
             raise ValueError(f"{name}: up-sampled {tuple(up.shape)} vs skip {tuple(skip.shape)} (input dims must be 8k)")
         y = self._bn(us.conv_blocks[0][1], self._conv(name + ".conv_blocks.0.0", us.conv_blocks[0][0], up, skip))
@@ -207,7 +223,10 @@ class TrainableMed3D:
         with torch.backends.cudnn.flags(enabled=False):
             c1 = StemFn.apply(self._layer("conv1", m.conv1), m.conv1.weight, image.float().contiguous())
             x = self._bn(m.bn1, c1)
-            y = _ndhwc(F.max_pool3d(_ncdhw(x), kernel_size=3, stride=2, padding=1))
+            if self.glue == "native":
+                y = MaxPool3dFn.apply(x)
+            else:
+                y = _ndhwc(F.max_pool3d(_ncdhw(x), kernel_size=3, stride=2, padding=1))
             feats = []
             for li, stage in enumerate((m.layer1, m.layer2, m.layer3, m.layer4), start=1):
                 planes_out = LAYER_CFG[li - 1][0] * m.expansion

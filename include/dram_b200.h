@@ -295,6 +295,49 @@ int dram_conv3d_wgrad_plan_info(const dram_wgrad_plan *plan, int64_t *flops, int
                                 int32_t *block_n);
 int dram_conv3d_wgrad_run(const dram_wgrad_plan *plan, int32_t accumulate, int32_t max_ctas, void *stream);
 
+/* ---- K10: train-mode BatchNorm3d (+ReLU, +residual), forward and backward ---- */
+/*
+ * What autograd sees of bn(conv(x)) / relu / `out += residual` (med3d.py:129-144, 164-184, 74-80, 371-373) when the
+ * reference trains (model.train(), train.py).  x, res, y, dy, dx, dres: 16-bit NDHWC viewed as [m][c] rows,
+ * c a multiple of 8 with 256 % (c/8) == 0 (8 ... 2048).  All per-channel vectors fp32 [c]; sums fp64 [2][c].
+ *   dram_bn_stats            sums = {sum x, sum x^2} over the m rows (two-phase, deterministic)
+ *   -- the caller may all-reduce `sums` over the process group here (SyncBatchNorm, train.py:101) --
+ *   dram_bn_finalize         mean, rstd = 1/sqrt(var_biased + eps); scale = gamma*rstd; shift = beta - mean*scale;
+ *                            running_mean/var (may be NULL) updated with `momentum`, unbiased variance
+ *   dram_bn_apply            out = act(x*scale + shift (+ res)),  act = ReLU if relu != 0
+ *   dram_bn_backward_reduce  sums = {sum dz, sum dz*xhat}, dz = dy where y > 0 (y = forward output; NULL: no ReLU)
+ *   dram_bn_backward_apply   dx = gamma*rstd*(dz - sums[0]/count - xhat*sums[1]/count); dres = dz (may be NULL)
+ * dgamma = sums[1], dbeta = sums[0] of the backward reduction.  workspace: dram_bn_workspace_bytes(c) bytes.
+ */
+int64_t dram_bn_workspace_bytes(int32_t c);
+int dram_bn_stats(const void *x, int64_t m, int32_t c, int32_t dtype, double *sums, void *workspace, void *stream);
+int dram_bn_finalize(const double *sums, double count, const float *gamma, const float *beta, float eps,
+                     float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                     float *mean, float *rstd, int32_t c, void *stream);
+int dram_bn_apply(const void *x, const float *scale, const float *shift, const void *res, int32_t relu, void *out,
+                  int64_t m, int32_t c, int32_t dtype, void *stream);
+int dram_bn_backward_reduce(const void *dy, const void *x, const void *y, const float *mean, const float *rstd,
+                            int64_t m, int32_t c, int32_t dtype, double *sums, void *workspace, void *stream);
+int dram_bn_backward_apply(const void *dy, const void *x, const void *y, const float *mean, const float *rstd,
+                           const float *gamma, const double *sums, double count, void *dx, void *dres, int64_t m,
+                           int32_t c, int32_t dtype, void *stream);
+
+/* ---- K4T / K3T: backward of the x2 up-sampling and of the max-pool ---- */
+/*
+ * dram_upsample2x_backward: adjoint of K4 (med3d.py:83,86; same ATen index arithmetic): dy [n][2d][2h][2w][c] ->
+ *   dx [n][d][h][w][c].  Gather formulation, fp32 accumulation, deterministic.
+ * dram_maxpool3d_backward: backward of K3 (med3d.py:305): x [n][d][h][w][c] (the pool's input), dy over the pooled
+ *   grid -> dx; a window's gradient goes to its FIRST maximum in (d,h,w) scan order, as ATen's
+ *   max_pool3d_with_indices does (ties are the rule after ReLU): an arg-max pass into `workspace`
+ *   (dram_maxpool3d_backward_workspace_bytes: one byte per pooled element), then a gather pass.  c multiple of 8
+ *   for both.
+ */
+int dram_upsample2x_backward(const void *dy, void *dx, int32_t n, int32_t d, int32_t h, int32_t w, int32_t c,
+                             int32_t dtype, void *stream);
+int64_t dram_maxpool3d_backward_workspace_bytes(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c);
+int dram_maxpool3d_backward(const void *x, const void *dy, void *dx, void *workspace, int32_t n, int32_t d,
+                            int32_t h, int32_t w, int32_t c, int32_t dtype, void *stream);
+
 /* ---- layout helpers ---------------------------------------------------- */
 /* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
 int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,

@@ -25,3 +25,38 @@ def conv3d_grads(x, weight, dy, stride=1, dilation=1, padding=None):
     assert y.shape == dy.shape, (y.shape, dy.shape)
     dx, dw = torch.autograd.grad(y, (x, w), dy)
     return dx, dw
+
+
+def bn_train(x, gamma, beta, res, relu, dy, eps=1e-5, momentum=0.1):
+    """Train-mode nn.BatchNorm3d (+ residual add, + ReLU) as the blocks of med3d.py:129-144 / 164-184 compose it, on
+    CPU fp32 with autograd.  x, res, dy: [N, C, D, H, W].  Returns y, running stats after one update from (0, 1), and
+    the gradients (dx, dgamma, dbeta, dres)."""
+    x = x.detach().clone().requires_grad_(True)
+    g = gamma.detach().clone().requires_grad_(True)
+    b = beta.detach().clone().requires_grad_(True)
+    r = None if res is None else res.detach().clone().requires_grad_(True)
+    rm, rv = torch.zeros_like(gamma), torch.ones_like(gamma)
+    y = F.batch_norm(x, rm, rv, g, b, True, momentum, eps)
+    if r is not None:
+        y = y + r
+    if relu:
+        y = torch.relu(y)
+    ins = (x, g, b) + (() if r is None else (r,))
+    grads = torch.autograd.grad(y, ins, dy)
+    return y.detach(), rm, rv, grads
+
+
+def upsample2x_grad(x, dy):
+    """nn.Upsample(scale_factor=2, mode='trilinear', align_corners=True) (med3d.py:83): output and input gradient."""
+    x = x.detach().clone().requires_grad_(True)
+    y = F.interpolate(x, scale_factor=2, mode="trilinear", align_corners=True)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    return y.detach(), dx
+
+
+def maxpool3d_grad(x, dy):
+    """nn.MaxPool3d(kernel_size=3, stride=2, padding=1) (med3d.py:305): output and input gradient."""
+    x = x.detach().clone().requires_grad_(True)
+    y = F.max_pool3d(x, kernel_size=3, stride=2, padding=1)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    return y.detach(), dx

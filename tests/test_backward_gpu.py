@@ -162,3 +162,112 @@ def test_dgrad_concat_source_slice(cuda):
     plan = backward.Conv3dDgradPlan(ops.to_ndhwc_16(dy.to(cuda), dt), w, (6, 8, 10), cin_range=(128, 192))
     dx = ops.to_ncdhw_f32(plan.run()).cpu()
     _close_dx(dx, dx_ref[:, 128:], "dgrad concat slice", dt)
+
+
+# ------------------------------------------------------------------------------------------
+# K10: train-mode BatchNorm (+ReLU, +residual), forward and backward
+# ------------------------------------------------------------------------------------------
+BN_CASES = [
+    # n, dims, c, with residual, relu
+    (2, (5, 6, 7), 64, False, True),
+    (1, (9, 8, 11), 64, True, True),
+    (2, (4, 4, 4), 512, True, True),
+    (1, (6, 10, 9), 32, False, True),
+    (1, (7, 5, 6), 128, False, False),
+    (1, (3, 4, 5), 2048, True, True),
+    (3, (16, 16, 16), 256, False, True),
+]
+
+
+@pytest.mark.parametrize("n,dims,c,with_res,relu", BN_CASES)
+def test_bn_train_forward_backward_match_autograd(cuda, n, dims, c, with_res, relu):
+    from dram_b200 import backward, ops
+    from oracle import backward_oracle as B
+
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(c + n)
+    x = _rand((n, c) + dims, g, 1.5, dt) + _rand((1, c, 1, 1, 1), g, 1.0, dt)
+    x = x.to(dt).float()
+    res = _rand((n, c) + dims, g, 1.0, dt) if with_res else None
+    dy = _rand((n, c) + dims, g, 1.0, dt)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+    y_ref, rm_ref, rv_ref, grads_ref = B.bn_train(x, gamma, beta, res, relu, dy)
+
+    xd = ops.to_ndhwc_16(x.to(cuda), dt)
+    rd = None if res is None else ops.to_ndhwc_16(res.to(cuda), dt).requires_grad_(True)
+    gd, bd = gamma.to(cuda).requires_grad_(True), beta.to(cuda).requires_grad_(True)
+    xd.requires_grad_(True)
+    rm, rv = torch.zeros(c, device=cuda), torch.ones(c, device=cuda)
+    y = backward.BatchNormTrainFn.apply(xd, gd, bd, rm, rv, rd, relu, 1e-5, 0.1, None)
+    y.backward(ops.to_ndhwc_16(dy.to(cuda), dt))
+    torch.cuda.synchronize()
+
+    _close_dx(ops.to_ncdhw_f32(y.detach()).cpu(), y_ref, "bn y", dt)
+    assert torch.allclose(rm.cpu(), rm_ref, rtol=1e-4, atol=1e-5) and torch.allclose(rv.cpu(), rv_ref, rtol=1e-4, atol=1e-5)
+    dx_ref, dg_ref, db_ref = grads_ref[:3]
+    # dx is rounded once to bf16; its small terms are differences of O(1) quantities, so bound by the tensor's scale
+    err = (ops.to_ncdhw_f32(xd.grad).cpu() - dx_ref).abs()
+    assert bool((err <= dx_ref.abs() * 2.0 ** -7 + dx_ref.abs().max() * 2.0 ** -8).all()), err.max().item()
+    assert torch.allclose(gd.grad.cpu(), dg_ref, rtol=2e-3, atol=2e-3 * float(dg_ref.abs().max()))
+    assert torch.allclose(bd.grad.cpu(), db_ref, rtol=2e-3, atol=2e-3 * float(db_ref.abs().max()))
+    if with_res:
+        _close_dx(ops.to_ncdhw_f32(rd.grad).cpu(), grads_ref[3], "bn dres", dt)
+
+
+def test_bn_train_is_deterministic_and_rejects_bad_shapes(cuda):
+    from dram_b200 import _capi, backward
+
+    x = (torch.randn((2, 8, 8, 8, 64), device=cuda)).to(torch.bfloat16)
+    g, b = torch.ones(64, device=cuda), torch.zeros(64, device=cuda)
+    outs = []
+    for _ in range(2):
+        rm, rv = torch.zeros(64, device=cuda), torch.ones(64, device=cuda)
+        outs.append((backward.BatchNormTrainFn.apply(x, g, b, rm, rv, None, True, 1e-5, 0.1, None), rm, rv))
+    assert all(torch.equal(a, b_) for a, b_ in zip(outs[0], outs[1]))
+    bad = torch.zeros((1, 2, 2, 2, 24), dtype=torch.bfloat16, device=cuda)  # 256 % (24 / 8) != 0
+    with pytest.raises(_capi.DramError, match="channels"):
+        backward.BatchNormTrainFn.apply(bad, torch.ones(24, device=cuda), torch.zeros(24, device=cuda),
+                                        torch.zeros(24, device=cuda), torch.ones(24, device=cuda), None, True, 1e-5, 0.1, None)
+
+
+# ------------------------------------------------------------------------------------------
+# K4T / K3T: backward of the x2 up-sampling and of the max-pool
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dims,c", [(1, (4, 4, 4), 64), (2, (3, 5, 7), 64), (1, (8, 8, 8), 512), (1, (1, 2, 9), 8)])
+def test_upsample2x_backward_matches_autograd(cuda, n, dims, c):
+    from dram_b200 import backward, ops
+    from oracle import backward_oracle as B
+
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(11)
+    x = _rand((n, c) + dims, g, 1.0, dt)
+    dy = _rand((n, c) + tuple(2 * v for v in dims), g, 1.0, dt)
+    y_ref, dx_ref = B.upsample2x_grad(x, dy)
+    xd = ops.to_ndhwc_16(x.to(cuda), dt).requires_grad_(True)
+    y = backward.Upsample2xFn.apply(xd)
+    y.backward(ops.to_ndhwc_16(dy.to(cuda), dt))
+    _close_dx(ops.to_ncdhw_f32(y.detach()).cpu(), y_ref, "upsample y", dt)
+    _close_dx(ops.to_ncdhw_f32(xd.grad).cpu(), dx_ref, "upsample dx", dt)
+
+
+@pytest.mark.parametrize("n,dims,c", [(1, (8, 8, 8), 64), (2, (5, 7, 9), 64), (1, (6, 6, 6), 8), (1, (1, 3, 2), 16)])
+def test_maxpool3d_backward_matches_autograd_with_ties(cuda, n, dims, c):
+    """Post-ReLU inputs: half of the values are exactly zero, so most windows hold ties; the gradient must land on the
+    same element ATen picks (first maximum in scan order) — compared exactly up to the bf16 rounding of sums."""
+    from dram_b200 import backward, ops
+    from oracle import backward_oracle as B
+
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(5)
+    x = _rand((n, c) + dims, g, 1.0, dt).relu()
+    x = (x * 4).round() / 4  # coarse values: ties between positive entries too
+    od = tuple((v - 1) // 2 + 1 for v in dims)
+    dy = _rand((n, c) + od, g, 1.0, dt)
+    y_ref, dx_ref = B.maxpool3d_grad(x, dy)
+    xd = ops.to_ndhwc_16(x.to(cuda), dt).requires_grad_(True)
+    y = backward.MaxPool3dFn.apply(xd)
+    y.backward(ops.to_ndhwc_16(dy.to(cuda), dt))
+    assert torch.equal(ops.to_ncdhw_f32(y.detach()).cpu(), y_ref)
+    got = ops.to_ncdhw_f32(xd.grad).cpu()
+    assert torch.equal((got != 0), (dx_ref != 0)), "gradient routed to different elements"
+    _close_dx(got, dx_ref, "maxpool dx", dt)
