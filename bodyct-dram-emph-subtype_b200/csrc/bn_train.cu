@@ -121,21 +121,24 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sums, double count
   }
 }
 
-// y = act(x * scale + shift (+ res))
+// y = act(x * scale + shift (+ res)).  The grid stride is a multiple of the threads per row (256 % (c/8) == 0), so a
+// thread keeps the same 8 channels for its whole loop and holds their coefficients in registers.
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const uint4 *__restrict__ x, const float *__restrict__ scale,
                                                              const float *__restrict__ shift, const uint4 *__restrict__ res,
                                                              int relu, uint4 *__restrict__ out, long long m, int c,
                                                              int is_f16) {
   const int tpr = c / 8;
   const long long total = m * tpr;
+  const int cg = (int)(threadIdx.x % tpr);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + cg * 8 + j);
+    sh[j] = __ldg(shift + cg * 8 + j);
+  }
   for (long long i = blockIdx.x * (long long)BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
-    const int cg = (int)(i % tpr);
-    float f[8], sc[8], sh[8];
+    float f[8];
     unpack8(__ldg(x + i), is_f16, f);
-    *reinterpret_cast<float4 *>(sc) = __ldg(reinterpret_cast<const float4 *>(scale + cg * 8));
-    *reinterpret_cast<float4 *>(sc + 4) = __ldg(reinterpret_cast<const float4 *>(scale + cg * 8) + 1);
-    *reinterpret_cast<float4 *>(sh) = __ldg(reinterpret_cast<const float4 *>(shift + cg * 8));
-    *reinterpret_cast<float4 *>(sh + 4) = __ldg(reinterpret_cast<const float4 *>(shift + cg * 8) + 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
     if (res != nullptr) {
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const uint4 *
   bn_block_reduce(a, b, c, partial);
 }
 
-// dx = gamma * rstd * (dz - sum_dz / M - xhat * sum_dz_xhat / M);  dres = dz (optional)
+// dx = gamma * rstd * (dz - sum_dz / M - xhat * sum_dz_xhat / M) = A * dz + B * x + C per channel;  dres = dz (optional).
+// As in bn_apply_kernel a thread keeps its 8 channels, so A, B, C are computed once per thread.
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4 *__restrict__ dy, const uint4 *__restrict__ x,
                                                                  const uint4 *__restrict__ y, const float *__restrict__ mean,
                                                                  const float *__restrict__ rstd, const float *__restrict__ gamma,
@@ -197,9 +201,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4 *_
                                                                  int c, int is_f16) {
   const int tpr = c / 8;
   const long long total = m * tpr;
-  const float inv = (float)(1.0 / count);
+  const int cg = (int)(threadIdx.x % tpr);
+  float A[8], B[8], Cc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = cg * 8 + j;
+    const double rs = (double)__ldg(rstd + ch), mu = (double)__ldg(mean + ch), g = (double)__ldg(gamma + ch);
+    const double s1 = sums[ch] / count, s2 = sums[c + ch] / count;
+    A[j] = (float)(g * rs);
+    B[j] = (float)(-g * rs * rs * s2);
+    Cc[j] = (float)(-g * rs * s1 + g * rs * rs * s2 * mu);
+  }
   for (long long i = blockIdx.x * (long long)BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
-    const int cg = (int)(i % tpr);
     float d[8], xv[8], o[8];
     unpack8(__ldg(dy + i), is_f16, d);
     unpack8(__ldg(x + i), is_f16, xv);
@@ -210,12 +223,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const uint4 *_
       for (int j = 0; j < 8; ++j) d[j] = yv[j] > 0.0f ? d[j] : 0.0f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = cg * 8 + j;
-      const float rs = __ldg(rstd + ch), xh = (xv[j] - __ldg(mean + ch)) * rs;
-      const float sdz = (float)sums[ch] * inv, sdzx = (float)sums[c + ch] * inv;
-      o[j] = __ldg(gamma + ch) * rs * (d[j] - sdz - xh * sdzx);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], d[j], fmaf(B[j], xv[j], Cc[j]));
     dx[i] = pack8(o, is_f16);
     if (dres != nullptr) dres[i] = pack8(d, is_f16);
   }
@@ -269,7 +277,7 @@ extern "C" int dram_bn_finalize(const double *sums, double count, const float *g
 extern "C" int dram_bn_apply(const void *x, const float *scale, const float *shift, const void *res, int32_t relu, void *out,
                              int64_t m, int32_t c, int32_t dtype, void *stream) {
   DRAM_REQUIRE(x && scale && shift && out, "dram_bn_apply: null pointer");
-  DRAM_REQUIRE(m > 0 && c > 0 && c % 8 == 0, "dram_bn_apply: channels must be a multiple of 8");
+  DRAM_REQUIRE(bn_shape_ok(m, c), "dram_bn_apply: unsupported shape (m %lld c %d)", (long long)m, c);
   DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_bn_apply: bad dtype");
   bn_apply_kernel<<<stream_grid(m * (c / 8), BN_THREADS), BN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4 *>(x), scale, shift, reinterpret_cast<const uint4 *>(res), relu,
@@ -298,7 +306,7 @@ extern "C" int dram_bn_backward_apply(const void *dy, const void *x, const void 
                                       const float *gamma, const double *sums, double count, void *dx, void *dres, int64_t m,
                                       int32_t c, int32_t dtype, void *stream) {
   DRAM_REQUIRE(dy && x && mean && rstd && gamma && sums && dx, "dram_bn_backward_apply: null pointer");
-  DRAM_REQUIRE(m > 0 && c > 0 && c % 8 == 0 && count >= 1.0, "dram_bn_backward_apply: bad size");
+  DRAM_REQUIRE(bn_shape_ok(m, c) && count >= 1.0, "dram_bn_backward_apply: unsupported shape (m %lld c %d)", (long long)m, c);
   DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_bn_backward_apply: bad dtype");
   bn_bwd_apply_kernel<<<stream_grid(m * (c / 8), BN_THREADS), BN_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4 *>(dy), reinterpret_cast<const uint4 *>(x), reinterpret_cast<const uint4 *>(y), mean, rstd,

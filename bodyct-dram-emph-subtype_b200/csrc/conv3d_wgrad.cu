@@ -42,12 +42,18 @@ static constexpr int WG_A_BYTES = 2 * WG_UNIT_BYTES;        // M = 128
 static constexpr int WG_THREADS = 192;
 static constexpr int WG_PRODUCER_WARP = 4, WG_MMA_WARP = 5;
 
-template <int BLOCK_N>
+// G = unit pairs per work item: with G = 2 one dy tile feeds two M = 128 accumulators (four units), which cuts the
+// bytes pulled through L2 per MMA by a third (BLOCK_N = 256) — the streaming kernel is bound by exactly that.
+template <int BLOCK_N, int G>
 struct WgCfg {
+  static constexpr int A_BYTES = G * WG_A_BYTES;
   static constexpr int B_BYTES = (BLOCK_N / 64) * WG_UNIT_BYTES;
-  static constexpr int STAGE_BYTES = WG_A_BYTES + B_BYTES;  // 24 / 32 / 48 KiB
-  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_FIT = (225 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static constexpr int ACC_BUFS = (2 * G * BLOCK_N <= 512) ? 2 : 1;  // accumulator sets in TMEM
+  static constexpr int TMEM_COLS_RAW = ACC_BUFS * G * BLOCK_N;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
 };
 
@@ -57,34 +63,16 @@ struct WgParams {
   int kd, kh, kw, sd, sh, sw, dd, dh, dw, pd, ph, pw;
   int chunks;       // Cin / 64 of this source
   int units;        // taps * chunks
-  int a_blocks;     // ceil(units / 2)
+  int a_blocks;     // ceil(units / 2): unit pairs = 128-row blocks of the partial buffer
+  int s_blocks;     // ceil(a_blocks / G): groups of G pairs = work items per (cout block, slice)
   int n_blocks;     // cout_pad / BLOCK_N
   int kslices;
-  int items_total;  // a_blocks * n_blocks * kslices
+  int items_total;  // s_blocks * n_blocks * kslices
   int cout, cout_pad;
   int rows_total;   // a_blocks * 128
   int is_f16;
   float *partial;   // [kslices][rows_total][cout_pad]
 };
-
-struct WgItem {
-  int slice, a_blk, n0, vt_begin, vt_end;
-  int u0, u1;  // units of the pair; u1 < 0 when the pair has no second unit
-};
-template <int BLOCK_N>
-__device__ __forceinline__ WgItem decode_wg_item(const WgParams &p, int item) {
-  WgItem it;
-  const int n_blk = item % p.n_blocks;
-  const int r = item / p.n_blocks;
-  it.a_blk = r % p.a_blocks;
-  it.slice = r / p.a_blocks;
-  it.n0 = n_blk * BLOCK_N;
-  it.vt_begin = (int)(((long long)it.slice * p.total_vtiles) / p.kslices);
-  it.vt_end = (int)(((long long)(it.slice + 1) * p.total_vtiles) / p.kslices);
-  it.u0 = 2 * it.a_blk;
-  it.u1 = it.u0 + 1 < p.units ? it.u0 + 1 : -1;
-  return it;
-}
 
 struct WgUnit {
   int c0, ow, oh, od;  // channel offset and input-coordinate offset of the tap: i = o*stride + off
@@ -100,6 +88,31 @@ __device__ __forceinline__ WgUnit decode_wg_unit(const WgParams &p, int u) {
   r.ow = zw * p.dw - p.pw;
   return r;
 }
+
+template <int G>
+struct WgItem {
+  int slice, a_blk0, n0, vt_begin, vt_end;
+  int n_units;           // valid units of this item (1 .. 2G), units a_blk0*2 .. a_blk0*2 + n_units - 1
+  WgUnit unit[2 * G];
+};
+template <int BLOCK_N, int G>
+__device__ __forceinline__ WgItem<G> decode_wg_item(const WgParams &p, int item) {
+  WgItem<G> it;
+  const int n_blk = item % p.n_blocks;
+  const int r = item / p.n_blocks;
+  const int s_blk = r % p.s_blocks;
+  it.slice = r / p.s_blocks;
+  it.a_blk0 = s_blk * G;
+  it.n0 = n_blk * BLOCK_N;
+  it.vt_begin = (int)(((long long)it.slice * p.total_vtiles) / p.kslices);
+  it.vt_end = (int)(((long long)(it.slice + 1) * p.total_vtiles) / p.kslices);
+  const int u0 = 2 * it.a_blk0;
+  it.n_units = p.units - u0 < 2 * G ? p.units - u0 : 2 * G;
+#pragma unroll
+  for (int q = 0; q < 2 * G; ++q) it.unit[q] = decode_wg_unit(p, q < it.n_units ? u0 + q : u0);
+  return it;
+}
+
 struct WgTile {
   int sample, d0, h0, w0;
 };
@@ -120,12 +133,16 @@ __device__ __forceinline__ bool wg_unit_is_padding(const WgParams &p, const WgTi
   return tap_is_padding(t.d0 * p.sd + u.od, WG_TD, p.sd, p.Di) || tap_is_padding(t.h0 * p.sh + u.oh, WG_TH, p.sh, p.Hi) ||
          tap_is_padding(t.w0 * p.sw + u.ow, WG_TW, p.sw, p.Wi);
 }
-// A tile is streamed unless every unit of the pair reads only padding; the first tile of a slice is always
-// streamed so that the accumulator is initialised (padding boxes arrive as zeros).
-__device__ __forceinline__ bool wg_tile_is_skipped(const WgParams &p, const WgItem &it, const WgUnit &ua, const WgUnit &ub,
-                                                   int vt, const WgTile &t) {
+// A tile is streamed unless every unit of the item reads only padding; the first tile of a slice is always
+// streamed so that the accumulators are initialised (padding boxes arrive as zeros).
+template <int G>
+__device__ __forceinline__ bool wg_tile_is_skipped(const WgParams &p, const WgItem<G> &it, int vt, const WgTile &t) {
   if (vt == it.vt_begin) return false;
-  return wg_unit_is_padding(p, t, ua) && (it.u1 < 0 || wg_unit_is_padding(p, t, ub));
+  bool all_pad = true;
+#pragma unroll
+  for (int q = 0; q < 2 * G; ++q)
+    if (q < it.n_units) all_pad = all_pad && wg_unit_is_padding(p, t, it.unit[q]);
+  return all_pad;
 }
 
 // MN-major SWIZZLE_128B descriptor: 64-element groups along M/N every `lbo` bytes, 8-row groups along K every 1 KiB.
@@ -138,17 +155,18 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint3
   return d;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int G>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                     const __grid_constant__ WgParams p) {
-  using Cfg = WgCfg<BLOCK_N>;
+  using Cfg = WgCfg<BLOCK_N, G>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ACC_BUFS = Cfg::ACC_BUFS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
   auto smem_a = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES; };
-  auto smem_b = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + WG_A_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + (uint32_t)s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -186,19 +204,20 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
-        const WgItem it = decode_wg_item<BLOCK_N>(p, item);
-        const WgUnit ua = decode_wg_unit(p, it.u0), ub = decode_wg_unit(p, it.u1 < 0 ? it.u0 : it.u1);
-        const uint32_t bytes = (uint32_t)(Cfg::B_BYTES + (it.u1 < 0 ? 1 : 2) * WG_UNIT_BYTES);
+        const WgItem<G> it = decode_wg_item<BLOCK_N, G>(p, item);
+        const uint32_t bytes = (uint32_t)(Cfg::B_BYTES + it.n_units * WG_UNIT_BYTES);
         for (int vt = it.vt_begin; vt < it.vt_end; ++vt) {
           const WgTile t = decode_wg_tile(p, vt);
-          if (wg_tile_is_skipped(p, it, ua, ub, vt, t)) continue;
+          if (wg_tile_is_skipped<G>(p, it, vt, t)) continue;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), bytes);
-          tma_load_5d(smem_a(stage), &map_x, full_bar(stage), ua.c0, t.w0 * p.sw + ua.ow, t.h0 * p.sh + ua.oh,
-                      t.d0 * p.sd + ua.od, t.sample);
-          if (it.u1 >= 0)
-            tma_load_5d(smem_a(stage) + WG_UNIT_BYTES, &map_x, full_bar(stage), ub.c0, t.w0 * p.sw + ub.ow,
-                        t.h0 * p.sh + ub.oh, t.d0 * p.sd + ub.od, t.sample);
+#pragma unroll
+          for (int q = 0; q < 2 * G; ++q)
+            if (q < it.n_units) {
+              const WgUnit &u = it.unit[q];
+              tma_load_5d(smem_a(stage) + (uint32_t)(q * WG_UNIT_BYTES), &map_x, full_bar(stage), u.c0, t.w0 * p.sw + u.ow,
+                          t.h0 * p.sh + u.oh, t.d0 * p.sd + u.od, t.sample);
+            }
 #pragma unroll
           for (int g = 0; g < BLOCK_N / 64; ++g)
             tma_load_5d(smem_b(stage) + (uint32_t)(g * WG_UNIT_BYTES), &map_dy, full_bar(stage), it.n0 + g * 64, t.w0,
@@ -217,23 +236,28 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
-      const WgItem it = decode_wg_item<BLOCK_N>(p, item);
-      const WgUnit ua = decode_wg_unit(p, it.u0), ub = decode_wg_unit(p, it.u1 < 0 ? it.u0 : it.u1);
+      const WgItem<G> it = decode_wg_item<BLOCK_N, G>(p, item);
+      const int pairs = (it.n_units + 1) / 2;
       mbar_wait(tmem_empty(acc), acc_phase ^ 1u);
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * G * BLOCK_N);
       uint32_t accumulate = 0;
       for (int vt = it.vt_begin; vt < it.vt_end; ++vt) {
         const WgTile t = decode_wg_tile(p, vt);
-        if (wg_tile_is_skipped(p, it, ua, ub, vt, t)) continue;
+        if (wg_tile_is_skipped<G>(p, it, vt, t)) continue;
         mbar_wait(full_bar(stage), phase);
         tcgen05_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < WG_KVOX / 16; ++k) {  // 16 voxels = 16 rows of 128 bytes per K step
-            const uint64_t da = make_sw128_mn_desc(smem_a(stage) + (uint32_t)(k * 16 * 128), WG_UNIT_BYTES);
             const uint64_t db = make_sw128_mn_desc(smem_b(stage) + (uint32_t)(k * 16 * 128), WG_UNIT_BYTES);
-            umma_bf16(tmem_d, da, db, idesc, (k > 0) ? 1u : accumulate);
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              if (g < pairs) {
+                const uint64_t da =
+                    make_sw128_mn_desc(smem_a(stage) + (uint32_t)(g * WG_A_BYTES + k * 16 * 128), WG_UNIT_BYTES);
+                umma_bf16(tmem_d + (uint32_t)(g * BLOCK_N), da, db, idesc, (k > 0) ? 1u : accumulate);
+              }
           }
           umma_commit(empty_bar(stage));
         }
@@ -246,39 +270,44 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
       if (elect_one_sync()) umma_commit(tmem_full(acc));
       __syncwarp();
-      if (++acc == 2) {
+      if (++acc == ACC_BUFS) {
         acc = 0;
         acc_phase ^= 1u;
       }
     }
   } else {
-    // ------------------------------- epilogue warps 0..3: accumulator -> partial[slice][row][cout] ----------
+    // ------------------------------- epilogue warps 0..3: accumulators -> partial[slice][row][cout] ----------
     const int row = warp * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < p.items_total; item += gridDim.x) {
-      const WgItem it = decode_wg_item<BLOCK_N>(p, item);
-      const bool valid = row < 64 || it.u1 >= 0;  // rows of a missing second unit are garbage
-      float *dst = p.partial + ((size_t)it.slice * p.rows_total + (size_t)it.a_blk * 128 + row) * p.cout_pad + it.n0;
+      const WgItem<G> it = decode_wg_item<BLOCK_N, G>(p, item);
       mbar_wait(tmem_full(acc), acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
-        tmem_wait_ld();
-        if (valid) {
-          float4 *d4 = reinterpret_cast<float4 *>(dst + c0);
+      for (int g = 0; g < G; ++g) {
+        // rows of a missing unit (odd tail of the unit list) hold garbage and are not written
+        const bool valid = 2 * g + (row >> 6) < it.n_units;
+        float *dst = p.partial + ((size_t)it.slice * p.rows_total + (size_t)(it.a_blk0 + g) * 128 + row) * p.cout_pad + it.n0;
+        const uint32_t taddr = tmem_base + (uint32_t)((acc * G + g) * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
+        if (2 * g >= it.n_units) break;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          tmem_wait_ld();
+          if (valid) {
+            float4 *d4 = reinterpret_cast<float4 *>(dst + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
+          }
         }
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty(acc));
-      if (++acc == 2) {
+      if (++acc == ACC_BUFS) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -501,29 +530,66 @@ __global__ void wgrad_planes_finish_kernel(const float *__restrict__ partial, fl
     const int key = (int)(r / 9);
     const int kd = key / chunks, chunk = key - kd * chunks;
     float s = 0.0f;
-    for (int k = 0; k < ctas_per_key; ++k)
-      s += partial[(size_t)(key + k * keys) * WP_PARTIAL_FLOATS + ((size_t)tap9 * 64 + ci) * 64 + co];
+    const float *src = partial + (size_t)key * WP_PARTIAL_FLOATS + ((size_t)tap9 * 64 + ci) * 64 + co;
+    const size_t pitch = (size_t)keys * WP_PARTIAL_FLOATS;
+    int k = 0;
+    for (; k + 4 <= ctas_per_key; k += 4) {  // fixed order, four loads in flight
+      const float v0 = __ldg(src + (size_t)k * pitch), v1 = __ldg(src + (size_t)(k + 1) * pitch);
+      const float v2 = __ldg(src + (size_t)(k + 2) * pitch), v3 = __ldg(src + (size_t)(k + 3) * pitch);
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; k < ctas_per_key; ++k) s += __ldg(src + (size_t)k * pitch);
     float *o = dw + ((size_t)co * cin_total + cin_offset + chunk * 64 + ci) * 27 + kd * 9 + tap9;
     *o = accumulate ? *o + s : s;
   }
 }
 
 // dW[co][cin_offset + ci][tap] (+)= sum over slices of partial[s][(tap*chunks + ci/64)*64 + ci%64][co]
-__global__ void wgrad_finish_kernel(const float *__restrict__ partial, float *__restrict__ dw, int kslices, int rows_total,
-                                    int cout_pad, int cout, int chunks, int taps, int cin_total, int cin_offset,
-                                    int accumulate) {
-  const long long rows = (long long)taps * chunks * 64;
-  const long long total = rows * cout;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % cout);
-    const long long row = i / cout;
-    const int c = (int)(row & 63);
-    const int u = (int)(row >> 6);
-    const int tap = u / chunks, ci = (u - tap * chunks) * 64 + c;
+// A CTA owns (chunk, 8 input channels, 8 output channels): it sums the slices of the taps x 8 x 8 block reading
+// 32-byte runs along cout, parks the block in shared memory and writes, per output channel, the [8 ci][taps] run that
+// is contiguous in PyTorch's layout — both sides of the transpose move whole sectors.
+static constexpr int WF_CI = 8, WF_CO = 8;
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float *__restrict__ partial, float *__restrict__ dw, int kslices,
+                                                           int rows_total, int cout_pad, int cout, int chunks, int taps,
+                                                           int cin_total, int cin_offset, int accumulate) {
+  extern __shared__ float tile[];  // [taps * WF_CI][WF_CO + 1]
+  const int co0 = blockIdx.x * WF_CO;
+  const int cib = blockIdx.y;                       // 8-channel block of this source
+  const int chunk = cib / (64 / WF_CI), c0 = (cib % (64 / WF_CI)) * WF_CI;
+  const int n_rows = taps * WF_CI;
+  for (int e = threadIdx.x; e < n_rows * WF_CO; e += blockDim.x) {
+    const int j = e % WF_CO, r = e / WF_CO;         // r = tap * 32 + ci_local
+    const int tap = r / WF_CI, cl = r - tap * WF_CI;
+    const size_t row = (size_t)(tap * chunks + chunk) * 64 + c0 + cl;
     float s = 0.0f;
-    for (int k = 0; k < kslices; ++k) s += partial[((size_t)k * rows_total + (size_t)row) * cout_pad + co];
-    float *o = dw + ((size_t)co * cin_total + cin_offset + ci) * taps + tap;
-    *o = accumulate ? *o + s : s;
+    if (co0 + j < cout) {
+      // the slices are summed in a fixed order; four loads are in flight at a time (the pass is latency-bound)
+      const float *src = partial + row * cout_pad + co0 + j;
+      const size_t pitch = (size_t)rows_total * cout_pad;
+      int k = 0;
+      for (; k + 4 <= kslices; k += 4) {
+        const float v0 = __ldg(src + (size_t)k * pitch), v1 = __ldg(src + (size_t)(k + 1) * pitch);
+        const float v2 = __ldg(src + (size_t)(k + 2) * pitch), v3 = __ldg(src + (size_t)(k + 3) * pitch);
+        s += v0;
+        s += v1;
+        s += v2;
+        s += v3;
+      }
+      for (; k < kslices; ++k) s += __ldg(src + (size_t)k * pitch);
+    }
+    tile[r * (WF_CO + 1) + j] = s;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_rows * WF_CO; e += blockDim.x) {
+    const int j = e / n_rows, q = e - j * n_rows;   // q = ci_local * taps + tap: contiguous in dw for a fixed co
+    if (co0 + j >= cout) continue;
+    const int cl = q / taps, tap = q - cl * taps;
+    const float v = tile[(tap * WF_CI + cl) * (WF_CO + 1) + j];
+    float *o = dw + ((size_t)(co0 + j) * cin_total + cin_offset + chunk * 64 + c0) * taps + q;
+    *o = accumulate ? *o + v : v;
   }
 }
 
@@ -533,6 +599,7 @@ using namespace dram;
 
 struct dram_wgrad_plan {
   CUtensorMap map_x, map_dy;
+  int group;   // unit pairs per work item of the streaming variant (1 or 2)
   int planes;  // 1 = PLANES variant (wp), 0 = streaming variant (p)
   WgParams p;
   WpParams wp;
@@ -545,7 +612,7 @@ struct dram_wgrad_plan {
 static int wg_conv_out(int in, int k, int s, int d, int p) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
 
 // Fills the geometry part of the parameters (everything except pointers); returns 0 or an error.
-static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n) {
+static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n, int *group) {
   DRAM_REQUIRE(d, "conv3d_wgrad: null descriptor");
   DRAM_REQUIRE(d->n > 0 && d->di > 0 && d->hi > 0 && d->wi > 0, "conv3d_wgrad: bad input dims");
   DRAM_REQUIRE(d->c1 > 0 && d->c1 % 64 == 0 && d->c2 == 0,
@@ -557,6 +624,8 @@ static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n) {
                    d->dw > 0 && d->pd >= 0 && d->ph >= 0 && d->pw >= 0,
                "conv3d_wgrad: bad filter geometry");
   DRAM_REQUIRE(d->dtype == DRAM_DTYPE_BF16 || d->dtype == DRAM_DTYPE_F16, "conv3d_wgrad: bad dtype");
+  DRAM_REQUIRE(d->kd * d->kh * d->kw <= 42, "conv3d_wgrad: at most 42 taps (the finish pass keeps taps x 32 x 8 values in "
+               "shared memory); the 7^3 stem goes through its (kh,kw)-unfolded 7x1x1 form");
   memset(p, 0, sizeof(*p));
   p->n = d->n; p->Di = d->di; p->Hi = d->hi; p->Wi = d->wi;
   p->Do = wg_conv_out(d->di, d->kd, d->sd, d->dd, d->pd);
@@ -579,8 +648,12 @@ static int wg_geometry(const dram_conv_desc *d, WgParams *p, int *block_n) {
   p->n_blocks = p->cout_pad / *block_n;
   p->rows_total = p->a_blocks * 128;
   p->is_f16 = d->dtype == DRAM_DTYPE_F16;
+  // two unit pairs per item whenever there are that many (DRAM_B200_WGRAD_GROUP=1 keeps one, for A/B measurements)
+  const char *knob = getenv("DRAM_B200_WGRAD_GROUP");
+  *group = (p->a_blocks >= 2 && !(knob && atoi(knob) == 1)) ? 2 : 1;
+  p->s_blocks = ceil_div(p->a_blocks, *group);
   // K slices: fill the SMs in whole waves; at least 4 voxel tiles per slice
-  const int items = p->a_blocks * p->n_blocks, sms = sm_count() > 0 ? sm_count() : 148;
+  const int items = p->s_blocks * p->n_blocks, sms = sm_count() > 0 ? sm_count() : 148;
   int ks = 1;
   for (int w = 1; w <= 4; ++w) {
     const int cand = sms * w / items;
@@ -619,10 +692,29 @@ static void wp_geometry(const dram_conv_desc *d, WpParams *w) {
   w->is_f16 = d->dtype == DRAM_DTYPE_F16;
 }
 
+// One place for the (BLOCK_N, G) instantiations: ctas == 0 sets the shared-memory attribute, otherwise launches.
+template <int BN, int G>
+static int wg_set_or_launch(const dram_wgrad_plan *pl, int ctas, cudaStream_t st) {
+  if (ctas == 0)
+    return check_cuda(cudaFuncSetAttribute(conv3d_wgrad_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           WgCfg<BN, G>::SMEM_BYTES),
+                      "cudaFuncSetAttribute(conv3d_wgrad_kernel)");
+  conv3d_wgrad_kernel<BN, G><<<ctas, WG_THREADS, WgCfg<BN, G>::SMEM_BYTES, st>>>(pl->map_x, pl->map_dy, pl->p);
+  return DRAM_OK;
+}
+static int wg_dispatch(const dram_wgrad_plan *pl, int ctas, cudaStream_t st) {
+  const int g = pl->group;
+  switch (pl->block_n) {
+    case 64: return g == 2 ? wg_set_or_launch<64, 2>(pl, ctas, st) : wg_set_or_launch<64, 1>(pl, ctas, st);
+    case 128: return g == 2 ? wg_set_or_launch<128, 2>(pl, ctas, st) : wg_set_or_launch<128, 1>(pl, ctas, st);
+    default: return g == 2 ? wg_set_or_launch<256, 2>(pl, ctas, st) : wg_set_or_launch<256, 1>(pl, ctas, st);
+  }
+}
+
 extern "C" int64_t dram_conv3d_wgrad_workspace_bytes(const dram_conv_desc *d) {
   WgParams p;
-  int bn;
-  if (wg_geometry(d, &p, &bn) != DRAM_OK) return -1;
+  int bn, grp;
+  if (wg_geometry(d, &p, &bn, &grp) != DRAM_OK) return -1;
   if (wp_supported(d)) {
     WpParams w;
     wp_geometry(d, &w);
@@ -638,8 +730,8 @@ extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void
   *plan = nullptr;
   DRAM_REQUIRE(x && dy && dw && workspace, "dram_conv3d_wgrad_plan_create: x, dy, dw and workspace are required");
   WgParams p;
-  int bn;
-  int rc = wg_geometry(d, &p, &bn);
+  int bn, grp;
+  int rc = wg_geometry(d, &p, &bn, &grp);
   if (rc != DRAM_OK) return rc;
   DRAM_REQUIRE(cin_offset >= 0 && cin_offset + d->c1 <= cin_total,
                "dram_conv3d_wgrad_plan_create: channel range [%d, %d) outside cin_total %d", cin_offset,
@@ -652,6 +744,7 @@ extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void
   pl->p = p;
   pl->p.partial = reinterpret_cast<float *>(workspace);
   pl->block_n = bn;
+  pl->group = grp;
   pl->dw = dw;
   pl->cin_total = cin_total;
   pl->cin_offset = cin_offset;
@@ -679,16 +772,7 @@ extern "C" int dram_conv3d_wgrad_plan_create(const dram_conv_desc *d, const void
                       p.is_f16);
   if (rc == DRAM_OK)
     rc = encode_act_map(&pl->map_dy, dy, d->n, p.Do, p.Ho, p.Wo, d->cout, 64, WG_TW, WG_TH, WG_TD, 1, 1, 1, p.is_f16);
-  if (rc == DRAM_OK) {
-    cudaError_t e;
-    if (bn == 64)
-      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<64>::SMEM_BYTES);
-    else if (bn == 128)
-      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<128>::SMEM_BYTES);
-    else
-      e = cudaFuncSetAttribute(conv3d_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<256>::SMEM_BYTES);
-    rc = check_cuda(e, "cudaFuncSetAttribute(conv3d_wgrad_kernel)");
-  }
+  if (rc == DRAM_OK) rc = wg_dispatch(pl, 0, nullptr);
   if (rc != DRAM_OK) {
     delete pl;
     return rc;
@@ -729,18 +813,14 @@ extern "C" int dram_conv3d_wgrad_run(const dram_wgrad_plan *plan, int32_t accumu
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   if (plan->p.items_total < ctas) ctas = plan->p.items_total;
-  if (plan->block_n == 64)
-    conv3d_wgrad_kernel<64><<<ctas, WG_THREADS, WgCfg<64>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
-  else if (plan->block_n == 128)
-    conv3d_wgrad_kernel<128><<<ctas, WG_THREADS, WgCfg<128>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
-  else
-    conv3d_wgrad_kernel<256><<<ctas, WG_THREADS, WgCfg<256>::SMEM_BYTES, st>>>(plan->map_x, plan->map_dy, plan->p);
+  int lrc = wg_dispatch(plan, ctas, st);
+  if (lrc != DRAM_OK) return lrc;
   DRAM_CHECK_LAUNCH("conv3d_wgrad_kernel launch");
   const WgParams &p = plan->p;
-  const long long total = (long long)p.units * 64 * p.cout;
-  wgrad_finish_kernel<<<stream_grid(total, 256), 256, 0, st>>>(p.partial, plan->dw, p.kslices, p.rows_total, p.cout_pad,
-                                                              p.cout, p.chunks, plan->taps, plan->cin_total,
-                                                              plan->cin_offset, accumulate ? 1 : 0);
+  const dim3 fgrid(ceil_div(p.cout, WF_CO), p.chunks * (64 / WF_CI));
+  const size_t fsmem = (size_t)plan->taps * WF_CI * (WF_CO + 1) * sizeof(float);
+  wgrad_finish_kernel<<<fgrid, 256, fsmem, st>>>(p.partial, plan->dw, p.kslices, p.rows_total, p.cout_pad, p.cout, p.chunks,
+                                                 plan->taps, plan->cin_total, plan->cin_offset, accumulate ? 1 : 0);
   DRAM_CHECK_LAUNCH("wgrad_finish_kernel launch");
   return DRAM_OK;
 }
