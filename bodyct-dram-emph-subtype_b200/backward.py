@@ -206,6 +206,45 @@ class MaxPool3dFn(torch.autograd.Function):
         return dx
 
 
+class HeadsSigmoidFn(torch.autograd.Function):
+    """The two 1x1x1 regression heads + sigmoid (med3d.py:329-332, 382) on the 32-channel NDHWC feature map:
+    (x [B,D,H,W,32], w0 [1,32,1,1,1], b0 [1], w1, b1) -> two fp32 maps [B,1,D,H,W] (K5T)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1):
+        lib = _capi.load()
+        _need16(x, "heads x", 5)
+        if x.shape[4] != 32 or w0.numel() != 32 or w1.numel() != 32:
+            raise ValueError(f"heads: expected 32 input channels and two 1-channel heads, got x {tuple(x.shape)}")
+        B, D, H, W, _ = x.shape
+        m = B * D * H * W
+        w = torch.cat([w0.detach().reshape(1, 32), w1.detach().reshape(1, 32)]).float().contiguous()
+        b = torch.cat([b0.detach().reshape(1), b1.detach().reshape(1)]).float().contiguous()
+        out0 = torch.empty((B, 1, D, H, W), dtype=torch.float32, device=x.device)
+        out1 = torch.empty_like(out0)
+        check(lib.dram_heads_sigmoid_forward(_p(x), _p(w), _p(b), _p(out0), _p(out1), m, ACT_DTYPES[x.dtype], _stream()),
+              "dram_heads_sigmoid_forward")
+        ctx.save_for_backward(x, w, out0, out1)
+        ctx.shapes = (tuple(w0.shape), tuple(b0.shape), tuple(w1.shape), tuple(b1.shape))
+        return out0, out1
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        lib = _capi.load()
+        x, w, s0, s1 = ctx.saved_tensors
+        m = s0.numel()
+        g0 = (torch.zeros_like(s0) if g0 is None else g0).float().contiguous()
+        g1 = (torch.zeros_like(s1) if g1 is None else g1).float().contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty((2, 32), dtype=torch.float32, device=x.device)
+        db = torch.empty(2, dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(lib.dram_heads_workspace_bytes()), dtype=torch.uint8, device=x.device)
+        check(lib.dram_heads_sigmoid_backward(_p(x), _p(w), _p(s0), _p(s1), _p(g0), _p(g1), _p(dx), _p(dw), _p(db), _p(ws), m,
+                                              ACT_DTYPES[x.dtype], _stream()), "dram_heads_sigmoid_backward")
+        sw0, sb0, sw1, sb1 = ctx.shapes
+        return dx, dw[0].reshape(sw0), db[0:1].reshape(sb0), dw[1].reshape(sw1), db[1:2].reshape(sb1)
+
+
 _BN_WS = {}
 
 
@@ -280,6 +319,18 @@ class BatchNormTrainFn(torch.autograd.Function):
         check(lib.dram_bn_backward_apply(_p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g32), _p(sums), count, _p(dx), _p(dres),
                                          m, c, dt, _stream()), "dram_bn_backward_apply")
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+def channel_sums(x):
+    """Per-channel sum over all rows of an NDHWC 16-bit tensor, fp32 [C] (phase 1+2 of K10's statistics): the bias
+    gradient of a convolution is this of its dy."""
+    lib = _capi.load()
+    _need16(x, "channel_sums x")
+    c = x.shape[-1]
+    sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+    check(lib.dram_bn_stats(_p(x), x.numel() // c, c, ACT_DTYPES[x.dtype], _p(sums), _p(_bn_workspace(c, x.device)), _stream()),
+          "dram_bn_stats")
+    return sums[:c].float()
 
 
 def _sync_world(group):

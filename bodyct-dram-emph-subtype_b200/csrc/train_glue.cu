@@ -224,3 +224,159 @@ extern "C" int dram_maxpool3d_backward(const void *x, const void *dy, void *dx, 
   DRAM_CHECK_LAUNCH("maxpool3d_backward_kernel launch");
   return DRAM_OK;
 }
+
+// K5T — the two 1x1x1 regression heads with their sigmoid (med3d.py:329-332, 382: `fcs`, torch.sigmoid) in training:
+// forward from the 32-channel NDHWC 16-bit feature map to two fp32 maps, and the backward of both
+// (dx 16-bit, dW [2][32], db [2] as a deterministic two-phase reduction).  In inference the same heads are fused into
+// the us3 epilogue (K5); in training us3 is followed by a train-mode BatchNorm, so they run on its output.
+namespace dram {
+
+static constexpr int HD_C = 32, HD_THREADS = 256;
+
+__device__ __forceinline__ void load_row32(const uint4 *x, long long m, int is_f16, float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = __ldg(x + m * 4 + q);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 p = unpack2(u[k], is_f16);
+      f[q * 8 + 2 * k] = p.x;
+      f[q * 8 + 2 * k + 1] = p.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(HD_THREADS) heads_forward_kernel(const uint4 *__restrict__ x, const float *__restrict__ w,
+                                                                  const float *__restrict__ b, float *__restrict__ out0,
+                                                                  float *__restrict__ out1, long long m_total, int is_f16) {
+  __shared__ float sw[2 * HD_C + 2];
+  if (threadIdx.x < 2 * HD_C) sw[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x < 2) sw[2 * HD_C + threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  for (long long m = blockIdx.x * (long long)HD_THREADS + threadIdx.x; m < m_total; m += (long long)gridDim.x * HD_THREADS) {
+    float f[32];
+    load_row32(x, m, is_f16, f);
+    float s0 = sw[2 * HD_C], s1 = sw[2 * HD_C + 1];
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) {
+      s0 = fmaf(sw[c], f[c], s0);
+      s1 = fmaf(sw[HD_C + c], f[c], s1);
+    }
+    out0[m] = 1.0f / (1.0f + expf(-s0));
+    out1[m] = 1.0f / (1.0f + expf(-s1));
+  }
+}
+
+// dlogit_k = g_k * s_k * (1 - s_k);  dx = dlogit_0 * w_0 + dlogit_1 * w_1;  partial[cta][k*33 + c] = sum dlogit_k * x_c,
+// partial[cta][k*33 + 32] = sum dlogit_k   (66 fp64 values per CTA = the [2][33] layout bn_partials_reduce_kernel sums)
+__global__ void __launch_bounds__(HD_THREADS) heads_backward_kernel(const uint4 *__restrict__ x, const float *__restrict__ w,
+                                                                   const float *__restrict__ s0, const float *__restrict__ s1,
+                                                                   const float *__restrict__ g0, const float *__restrict__ g1,
+                                                                   uint4 *__restrict__ dx, double *__restrict__ partial,
+                                                                   long long m_total, int is_f16) {
+  __shared__ float sw[2 * HD_C];
+  __shared__ float red[HD_THREADS / 32][2 * (HD_C + 1)];
+  if (threadIdx.x < 2 * HD_C) sw[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const long long r0 = (m_total * blockIdx.x) / gridDim.x, r1 = (m_total * (blockIdx.x + 1)) / gridDim.x;
+  float a0[HD_C + 1], a1[HD_C + 1];
+#pragma unroll
+  for (int c = 0; c <= HD_C; ++c) a0[c] = a1[c] = 0.0f;
+  for (long long m = r0 + threadIdx.x; m < r1; m += HD_THREADS) {
+    float f[32];
+    load_row32(x, m, is_f16, f);
+    const float p0 = __ldg(s0 + m), p1 = __ldg(s1 + m);
+    const float d0 = __ldg(g0 + m) * p0 * (1.0f - p0), d1 = __ldg(g1 + m) * p1 * (1.0f - p1);
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) {
+      o[c] = fmaf(d0, sw[c], d1 * sw[HD_C + c]);
+      a0[c] = fmaf(d0, f[c], a0[c]);
+      a1[c] = fmaf(d1, f[c], a1[c]);
+    }
+    a0[HD_C] += d0;
+    a1[HD_C] += d1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      dx[m * 4 + q] = make_uint4(pack2(o[q * 8], o[q * 8 + 1], is_f16), pack2(o[q * 8 + 2], o[q * 8 + 3], is_f16),
+                                 pack2(o[q * 8 + 4], o[q * 8 + 5], is_f16), pack2(o[q * 8 + 6], o[q * 8 + 7], is_f16));
+  }
+  // warp shuffle tree, then the eight warps of the CTA in fixed order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c <= HD_C; ++c) {
+    float v0 = a0[c], v1 = a1[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_down_sync(0xffffffffu, v0, o);
+      v1 += __shfl_down_sync(0xffffffffu, v1, o);
+    }
+    if (lane == 0) {
+      red[warp][c] = v0;
+      red[warp][HD_C + 1 + c] = v1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * (HD_C + 1)) {
+    double s = 0.0;
+    for (int k = 0; k < HD_THREADS / 32; ++k) s += (double)red[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * 2 * (HD_C + 1) + threadIdx.x] = s;
+  }
+}
+
+__global__ void heads_partials_reduce_kernel(const double *__restrict__ partial, int ctas, float *__restrict__ dw, float *__restrict__ db) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (u >= 2 * (HD_C + 1)) return;
+  double s = 0.0;
+  for (int b = lane; b < ctas; b += 32) s += partial[(size_t)b * 2 * (HD_C + 1) + u];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const int k = u / (HD_C + 1), c = u - k * (HD_C + 1);
+    if (c < HD_C) dw[k * HD_C + c] = (float)s;
+    else db[k] = (float)s;
+  }
+}
+
+static int heads_ctas(long long m) {
+  long long want = (m + HD_THREADS * 4 - 1) / (HD_THREADS * 4);
+  const long long cap = (long long)(sm_count() > 0 ? sm_count() : 148) * 4;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+}  // namespace dram
+
+extern "C" int64_t dram_heads_workspace_bytes(void) {
+  return (int64_t)((sm_count() > 0 ? sm_count() : 148) * 4) * 2 * (HD_C + 1) * (int64_t)sizeof(double);
+}
+
+extern "C" int dram_heads_sigmoid_forward(const void *x, const float *w, const float *b, float *out0, float *out1, int64_t m,
+                                          int32_t dtype, void *stream) {
+  DRAM_REQUIRE(x && w && b && out0 && out1, "dram_heads_sigmoid_forward: null pointer");
+  DRAM_REQUIRE(m > 0, "dram_heads_sigmoid_forward: empty input");
+  DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_heads_sigmoid_forward: bad dtype");
+  heads_forward_kernel<<<stream_grid(m, HD_THREADS), HD_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4 *>(x), w, b, out0, out1, m, dtype == DRAM_DTYPE_F16);
+  DRAM_CHECK_LAUNCH("heads_forward_kernel launch");
+  return DRAM_OK;
+}
+
+extern "C" int dram_heads_sigmoid_backward(const void *x, const float *w, const float *s0, const float *s1, const float *g0,
+                                           const float *g1, void *dx, float *dw, float *db, void *workspace, int64_t m,
+                                           int32_t dtype, void *stream) {
+  DRAM_REQUIRE(x && w && s0 && s1 && g0 && g1 && dx && dw && db && workspace, "dram_heads_sigmoid_backward: null pointer");
+  DRAM_REQUIRE(m > 0, "dram_heads_sigmoid_backward: empty input");
+  DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_heads_sigmoid_backward: bad dtype");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ctas = heads_ctas(m);
+  heads_backward_kernel<<<ctas, HD_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(x), w, s0, s1, g0, g1,
+                                                     reinterpret_cast<uint4 *>(dx), reinterpret_cast<double *>(workspace), m,
+                                                     dtype == DRAM_DTYPE_F16);
+  DRAM_CHECK_LAUNCH("heads_backward_kernel launch");
+  heads_partials_reduce_kernel<<<ceil_div(2 * (HD_C + 1) * 32, 256), 256, 0, st>>>(reinterpret_cast<const double *>(workspace),
+                                                                                  ctas, dw, db);
+  DRAM_CHECK_LAUNCH("heads_partials_reduce_kernel launch");
+  return DRAM_OK;
+}

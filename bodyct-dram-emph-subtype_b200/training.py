@@ -11,8 +11,9 @@ What runs where, stated plainly:
   `backward.BatchNormTrainFn`);
 * max-pool and x2 trilinear up-sampling run on K3 / K4 forward and their gather-style adjoints K3T / K4T
   (`train_glue.cu`, `backward.MaxPool3dFn` / `Upsample2xFn`);
-* what is left of the memory-bound glue — the 1x1x1 sigmoid heads, lobe-masked pooling, the three losses, bias
-  gradients, weight re-packing and Adam — is still ATen CUDA code driven by autograd (cuDNN disabled).  Hand-written replacements of these are the remaining work of this row; until then `bench.py` reports no
+* the two 1x1x1 sigmoid heads run on K5T (`backward.HeadsSigmoidFn`), conv bias gradients on K10's channel sums;
+* what is left — lobe-masked pooling and the three losses on the single-channel maps, weight re-packing and Adam —
+  is still ATen CUDA code driven by autograd (cuDNN disabled).  Hand-written replacements of these are the remaining work of this row; until then `bench.py` reports no
   training number.
 
 The module takes the drop-in network (`med3d.resnet{18,34,50}segreg()`, reference `state_dict` keys) and reproduces
@@ -26,7 +27,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .backward import BatchNormTrainFn, MaxPool3dFn, Upsample2xFn, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
+from .backward import BatchNormTrainFn, HeadsSigmoidFn, MaxPool3dFn, Upsample2xFn, channel_sums, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
 from .engine import LAYER_CFG
 
 ACT = torch.bfloat16  # activations and their gradients
@@ -116,7 +117,7 @@ class ConvFn(torch.autograd.Function):
                 dp.packed.copy_(pack_dgrad_weight(weight, dtype=ACT, cin_range=(off, off + c)))
                 grads[i] = dp.run().detach()
             off += c
-        db = dy.float().sum(dim=(0, 1, 2, 3)) if ctx.has_bias else None
+        db = channel_sums(dy) if ctx.has_bias else None
         if BACKWARD_TAP is not None:
             BACKWARD_TAP.append((layer.name, [x.clone() for x in srcs], dy.clone(), weight.detach().clone(),
                                  [None if g is None else g.clone() for g in grads[:len(srcs)]], layer.dw.clone()))
@@ -236,9 +237,12 @@ class TrainableMed3D:
             xup1 = self._up("us1", m.us1, feats[3], feats[0])
             xup2 = self._up("us2", m.us2, xup1, x)
             xup3 = self._bn(m.us3[1], self._conv("us3.0", m.us3[0], xup2))
-            v = xup3.float()  # [B, D, H, W, 32]; the 1x1x1 heads (med3d.py:329-332, 382) are a 32-long dot per voxel
-            dense = [torch.sigmoid(v @ fc.weight.view(fc.weight.shape[0], 32).t() + fc.bias).permute(0, 4, 1, 2, 3)
-                     for fc in m.fcs]
+            if self.glue == "native" and len(m.fcs) == 2 and all(fc.weight.shape[0] == 1 for fc in m.fcs):
+                dense = list(HeadsSigmoidFn.apply(xup3, m.fcs[0].weight, m.fcs[0].bias, m.fcs[1].weight, m.fcs[1].bias))
+            else:
+                v = xup3.float()  # [B, D, H, W, 32]; the 1x1x1 heads (med3d.py:329-332, 382) are a 32-long dot per voxel
+                dense = [torch.sigmoid(v @ fc.weight.view(fc.weight.shape[0], 32).t() + fc.bias).permute(0, 4, 1, 2, 3)
+                         for fc in m.fcs]
             if lungs is None:
                 mask = torch.ones((B, 1) + tuple(dense[0].shape[2:]), device=image.device)
             else:

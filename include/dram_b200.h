@@ -338,6 +338,20 @@ int64_t dram_maxpool3d_backward_workspace_bytes(int32_t n, int32_t d, int32_t h,
 int dram_maxpool3d_backward(const void *x, const void *dy, void *dx, void *workspace, int32_t n, int32_t d,
                             int32_t h, int32_t w, int32_t c, int32_t dtype, void *stream);
 
+/* ---- K5T: the two 1x1x1 regression heads + sigmoid in training (med3d.py:329-332, 382) ---- */
+/*
+ * x : 16-bit NDHWC rows [m][32] (us3's output); w fp32 [2][32] (fcs.0.weight, fcs.1.weight), b fp32 [2].
+ * forward : out_k[m] = sigmoid(w_k . x[m] + b_k), fp32 (= the [B,1,D,H,W] dense maps, flat).
+ * backward: from s_k = out_k and g_k = d loss / d out_k: dx 16-bit [m][32], dw fp32 [2][32], db fp32 [2];
+ *           two-phase deterministic reduction, workspace of dram_heads_workspace_bytes() bytes.
+ */
+int64_t dram_heads_workspace_bytes(void);
+int dram_heads_sigmoid_forward(const void *x, const float *w, const float *b, float *out0, float *out1, int64_t m,
+                               int32_t dtype, void *stream);
+int dram_heads_sigmoid_backward(const void *x, const float *w, const float *s0, const float *s1, const float *g0,
+                                const float *g1, void *dx, float *dw, float *db, void *workspace, int64_t m,
+                                int32_t dtype, void *stream);
+
 /* ---- layout helpers ---------------------------------------------------- */
 /* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
 int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,

@@ -271,3 +271,31 @@ def test_maxpool3d_backward_matches_autograd_with_ties(cuda, n, dims, c):
     got = ops.to_ncdhw_f32(xd.grad).cpu()
     assert torch.equal((got != 0), (dx_ref != 0)), "gradient routed to different elements"
     _close_dx(got, dx_ref, "maxpool dx", dt)
+
+
+def test_heads_sigmoid_forward_backward_match_autograd(cuda):
+    """K5T against torch CPU autograd of sigmoid(conv1x1x1(x)) for the two regression heads (med3d.py:329-332, 382)."""
+    import torch.nn.functional as F
+
+    from dram_b200 import backward, ops
+
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(9)
+    x = _rand((2, 32, 5, 6, 7), g, 1.0, dt)
+    ws = [(torch.randn((1, 32, 1, 1, 1), generator=g) * 0.3).requires_grad_(True) for _ in range(2)]
+    bs = [(torch.randn(1, generator=g) * 0.5).requires_grad_(True) for _ in range(2)]
+    gs = [torch.randn((2, 1, 5, 6, 7), generator=g) for _ in range(2)]
+    xr = x.clone().requires_grad_(True)
+    outs_ref = [torch.sigmoid(F.conv3d(xr, w, b)) for w, b in zip(ws, bs)]
+    grads_ref = torch.autograd.grad(outs_ref, [xr] + ws + bs, gs)
+
+    xd = ops.to_ndhwc_16(x.to(cuda), dt).requires_grad_(True)
+    wd = [w.detach().to(cuda).requires_grad_(True) for w in ws]
+    bd = [b.detach().to(cuda).requires_grad_(True) for b in bs]
+    o0, o1 = backward.HeadsSigmoidFn.apply(xd, wd[0], bd[0], wd[1], bd[1])
+    torch.autograd.backward([o0, o1], [gs[0].to(cuda), gs[1].to(cuda)])
+    for got, ref in zip((o0, o1), outs_ref):
+        assert torch.allclose(got.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    _close_dx(ops.to_ncdhw_f32(xd.grad).cpu(), grads_ref[0], "heads dx", dt)
+    for got, ref in zip([w.grad for w in wd] + [b.grad for b in bd], grads_ref[1:]):
+        assert torch.allclose(got.cpu(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max() + 1)), (got.cpu(), ref)
