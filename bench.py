@@ -335,6 +335,106 @@ class _StdoutToStderr:
         os.write(self.real, (text + "\n").encode())
 
 
+def run_train_arm(args, out):
+    """BASELINE config 5: med3ddram training, forward + loss + backward + gradient all-reduce + Adam, bf16 activations,
+    one process per GPU (NCCL), per-GPU batch `--batch` (default 1 here).  Convolutions (fwd/dgrad/wgrad), train-mode
+    BatchNorm(+ReLU, +residual, SyncBN exchange), max-pool, up-sampling and heads run on the hand-written kernels; the
+    losses on the single-channel maps, weight re-packing and Adam are ATen CUDA ops (training
+    step) — stated in `config.glue`.  `value` = volumes/s with the batch resident in HBM, `e2e` copies the batch
+    from pinned host memory every step and reads the loss back."""
+    import dram_b200  # noqa: F401
+    from dram_b200 import med3d, training
+
+    rank, local, world = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dims = parse_dims(args)
+    B = args.batch if args.batch != 4 else 1  # the inference default (4) is not a training batch: C5 is per-GPU batch 1
+    torch.manual_seed(0)  # identical initial weights on every rank
+    factory = {"med3ddram": med3d.resnet34segreg, "med3ddram18": med3d.resnet18segreg, "med3ddram50": med3d.resnet50segreg}
+    model = factory[args.arch]().to(device).train()
+    step = training.TrainStep(model, lr=1e-5, sync_bn=world > 1)
+    hu, lungs, ess = make_volumes(B, dims, device, seed=rank)
+    v = hu.float().clamp(-1150.0, -300.0)
+    v = (v + 1150.0) / 850.0
+    image = (v - v.mean(dim=(1, 2, 3), keepdim=True)) / v.std(dim=(1, 2, 3), keepdim=True)
+    batch = {"image": image.contiguous(), "lung_mask": lungs.bool(), "em_mask": ess.bool(),
+             "cls_label": torch.full((B,), 2, device=device), "pse_label": torch.full((B,), 1, device=device)}
+    bands = (torch.tensor([[0.05, 0.1]] * B, device=device), torch.tensor([[0.01, 0.05]] * B, device=device))
+    w = torch.ones(B, device=device)
+
+    def one(b):
+        return step.step(b, bands[0], bands[1], w, w)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        one(batch)
+    torch.cuda.synchronize()
+    barrier(world)
+    torch.cuda.synchronize()
+    first_sample = sampler.mark() if rank == 0 else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = one(batch)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1), world, device) / args.steps
+    clocks = sampler.stop(skip=first_sample) if rank == 0 else None
+
+    host = {k: t.cpu().pin_memory() for k, t in batch.items()}
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        dev_batch = {k: t.to(device, non_blocking=True) for k, t in host.items()}
+        loss_host.copy_(one(dev_batch).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
+
+    train_flops = step.net.training_flops()  # fprop + dgrad + wgrad of every convolution; the stem has no dgrad
+    peak, peak_src = measured_peaks()
+    achieved = train_flops / (ms_per_step * 1e-3) / 1e12
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "CT volumes/sec med3ddram training (fwd+bwd+all-reduce+Adam)", "mode": "train",
+        "value": world * B / (ms_per_step * 1e-3), "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 operands / f32 accumulate, fp32 master weights and gradients", "data": "synthetic",
+        "config": {"workload": f"{ARCH_NAMES[args.arch]} training step, synthetic {dims[0]}x{dims[1]}x{dims[2]} CT volumes, "
+                               f"batch {B} per GPU, random-init weights",
+                   "global_batch": world * B, "parallelism": f"data-parallel x{world}, bucketed NCCL gradient all-reduce"
+                                                             f"{' + SyncBatchNorm' if world > 1 else ''}",
+                   "glue": "native: conv fwd/dgrad/wgrad, BatchNorm(+ReLU,+residual), max-pool, up-sampling, heads; "
+                           "ATen: losses on 1-channel maps, weight re-packing, Adam",
+                   "l2": "activations per step (> 10 GB) exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks, "loss": float(loss),
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms, "api": "training.TrainStep.step(batch) with the batch copied from pinned host memory "
+                                              "every step and the loss read back"},
+        "gpu_launches": None,
+        "roofline": {"bound": "tensor", "kernel": "whole training step (conv fprop + dgrad + wgrad FLOPs over the step time)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_flops_per_step": train_flops},
+    }
+    out.emit(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -346,11 +446,17 @@ def main():
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default): BASELINE.json's headline metric; train: one data-parallel training step "
+                         "(BASELINE config 5; additional line, not the headline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     sink = _StdoutToStderr()
     if args.impl == "reference":
         run_reference_arm(args, sink)
+        return
+    if args.mode == "train":
+        run_train_arm(args, sink)
         return
 
     rank, local, world = dist_setup(args.gpus)

@@ -68,6 +68,7 @@ class ConvLayer:
         self.name, self.k, self.s, self.dl = name, kernel, stride, dilation
         self.fwd, self.dgrad, self.wgrad = _PlanCache(), [_PlanCache(), _PlanCache()], [_PlanCache(), _PlanCache()]
         self.zero_bias = None
+        self.flops = 0  # algorithmic forward FLOPs (2*M*N*K) of the last call
         self.dw = None  # fp32 [Cout, Cin_total, kd, kh, kw], shared by the wgrad plans of both sources
 
 
@@ -91,6 +92,7 @@ class ConvFn(torch.autograd.Function):
         w_buf.copy_(packed)
         if bias is not None:
             b_buf.copy_(bias.detach())
+        layer.flops = plan.flops
         out = plan.run().detach()  # a fresh alias: the plan-owned buffer itself never carries autograd history
         ctx.layer, ctx.has_bias = layer, bias is not None
         ctx.save_for_backward(weight, *srcs)
@@ -135,6 +137,7 @@ class StemFn(torch.autograd.Function):
             layer.zero_bias = torch.zeros(64, dtype=torch.float32, device=image.device)
         packed = ops.pack_stem_weight_fused(weight, dtype=ACT)
         out = ops.stem_conv7(image, packed, layer.zero_bias, relu=False)
+        layer.flops = 2 * out.numel() * 343
         ctx.layer = layer
         ctx.save_for_backward(image)
         return out
@@ -166,6 +169,14 @@ class TrainableMed3D:
         self.model = model
         self.layers = {}
         self.glue, self.sync_bn = glue, sync_bn
+
+    def training_flops(self):
+        """Algorithmic FLOPs of one training step of the last forward: fprop + dgrad + wgrad of every convolution
+        (2*M*N*K each), the stem without a data gradient."""
+        total = 0
+        for name, lay in self.layers.items():
+            total += lay.flops * (2 if name == "conv1" else 3)
+        return total
 
     def _layer(self, name, conv):
         lay = self.layers.get(name)
@@ -315,21 +326,43 @@ class TrainStep:
     """forward -> loss -> backward -> gradient average over the process group -> Adam (models.py:685-698, lr from args).
 
     Gradients live in one flat fp32 buffer (`GradBuckets`, parameters in reverse registration order, i.e. roughly the
-    order backward produces them) whose buckets are all-reduced asynchronously.
+    order backward produces them).  A post-accumulate hook on every parameter counts its bucket down; the bucket's
+    (asynchronous, NCCL) all-reduce is launched the moment its last gradient lands, so the exchange overlaps the rest
+    of the backward pass.  `sync_bn=True` all-reduces the BatchNorm statistics as well (train.py:101).
     """
 
-    def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None):
-        self.net = TrainableMed3D(model)
+    def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None, sync_bn=False):
+        self.net = TrainableMed3D(model, sync_bn=(group if group is not None else True) if sync_bn else None)
         self.params = [(n, p) for n, p in model.named_parameters()]
         dev = self.params[0][1].device
         self.buckets = GradBuckets([(n, tuple(p.shape)) for n, p in reversed(self.params)], dev, bucket_bytes)
+        self._bucket_size = [0] * self.buckets.num_buckets
         for n, p in self.params:
             p.grad = self.buckets.view(n)
+            b = self.buckets.bucket_of[n]
+            self._bucket_size[b] += 1
+            p.register_post_accumulate_grad_hook(self._make_hook(n, b))
+        self._pending = list(self._bucket_size)
+        self._launched = [False] * self.buckets.num_buckets
         self.opt = torch.optim.Adam([p for _, p in self.params], lr=lr)
         self.group = group
 
+    def _make_hook(self, name, bucket):
+        def hook(param):
+            view = self.buckets.view(name)
+            if param.grad is not None and param.grad.data_ptr() != view.data_ptr():  # autograd replaced the tensor
+                view.copy_(param.grad)
+                param.grad = view
+            self._pending[bucket] -= 1
+            if self._pending[bucket] == 0:
+                self._launched[bucket] = True
+                self.buckets.reduce_bucket(bucket, self.group)
+        return hook
+
     def zero_grad(self):
         self.buckets.flat.zero_()
+        self._pending = list(self._bucket_size)
+        self._launched = [False] * self.buckets.num_buckets
 
     def step(self, batch, cle_bands, pse_bands, cle_weights, pse_weights):
         self.zero_grad()
@@ -338,12 +371,9 @@ class TrainStep:
         loss = training_loss(dense, regs, lungs, batch["em_mask"].float(), batch["cls_label"], batch["pse_label"],
                              cle_bands, pse_bands, cle_weights, pse_weights)
         loss.backward()
-        for n, p in self.params:  # autograd accumulates into the bucket views in place; keep them attached
-            if p.grad is not None and p.grad.data_ptr() != self.buckets.view(n).data_ptr():
-                self.buckets.view(n).copy_(p.grad)
-                p.grad = self.buckets.view(n)
-        for i in range(self.buckets.num_buckets):
-            self.buckets.reduce_bucket(i, self.group)
+        for i in range(self.buckets.num_buckets):  # buckets holding a parameter that received no gradient
+            if not self._launched[i]:
+                self.buckets.reduce_bucket(i, self.group)
         self.buckets.wait()
         self.opt.step()
         return loss.detach()
