@@ -11,9 +11,9 @@ Interface kept from /root/reference/med3d.py:
     nn.BatchNorm3d objects used purely as parameter containers;
   * initialisation as med3d.py:334-339 (kaiming-normal fan_out convolutions, BN weight 1 / bias 0).
 
-What differs: only eval-mode inference on a CUDA (B200) device is implemented.  Calling forward in
-training mode, on CPU tensors, or with an input size the up-sampling path cannot match raises —
-there is deliberately no PyTorch fallback.
+What differs: `forward()` is eval-mode inference on a CUDA (B200) device.  Calling it in training mode, on CPU
+tensors, or with an input size the up-sampling path cannot match raises — there is deliberately no PyTorch
+fallback.  The training step on the same parameters lives in `training.py` (`TrainableMed3D`, `TrainStep`).
 """
 import torch
 import torch.nn as nn
@@ -145,8 +145,8 @@ class _Med3DSegNet(nn.Module):
 
     def forward(self, x, lungs=None):
         if self.training:
-            raise RuntimeError("dram_b200 implements eval-mode inference only (call .eval()); training kernels "
-                               "(dgrad/wgrad, train-mode BN) are not part of this build")
+            raise RuntimeError("this module's forward() is the eval-mode inference path (call .eval()); a training step "
+                               "on the same parameters runs through dram_b200.training.TrainableMed3D / TrainStep")
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise RuntimeError("dram_b200.med3d needs CUDA tensors on a B200; there is no CPU fallback")
         if x.dim() != 5 or x.shape[1] != 1:

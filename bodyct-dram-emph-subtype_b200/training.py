@@ -13,8 +13,8 @@ What runs where, stated plainly:
   (`train_glue.cu`, `backward.MaxPool3dFn` / `Upsample2xFn`);
 * the two 1x1x1 sigmoid heads run on K5T (`backward.HeadsSigmoidFn`), conv bias gradients on K10's channel sums;
 * what is left — lobe-masked pooling and the three losses on the single-channel maps, weight re-packing and Adam —
-  is still ATen CUDA code driven by autograd (cuDNN disabled).  Hand-written replacements of these are the remaining work of this row; until then `bench.py` reports no
-  training number.
+  is still ATen CUDA code driven by autograd (cuDNN disabled).  `bench.py --mode train` measures the step as an
+  additional line and names this remainder in `config.glue`.
 
 The module takes the drop-in network (`med3d.resnet{18,34,50}segreg()`, reference `state_dict` keys) and reproduces
 what the reference does in `ScanRegLightningModule.shared_step(TRAIN)` (models.py:530-570): forward in train mode
