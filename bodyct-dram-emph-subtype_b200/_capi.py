@@ -93,6 +93,7 @@ SIGNATURES = {
     "dram_heads_workspace_bytes": (_i64, []),
     "dram_heads_sigmoid_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dram_heads_sigmoid_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "dram_pack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }

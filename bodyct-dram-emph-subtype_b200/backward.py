@@ -119,6 +119,29 @@ def pack_dgrad_weight(weight, dtype=torch.bfloat16, cin_range=None, pad_cout_to=
     return pack_conv_weight(wt, dtype=dtype)
 
 
+def pack_weight_into(weight, out, *, transpose=False, cin_range=None):
+    """Device-side re-packing of an fp32 Conv3d weight into an existing 16-bit operand buffer (no temporaries):
+    `transpose=False` -> K1's [Cout, taps*Cin] (= ops.pack_conv_weight), `transpose=True` -> the data-gradient operand
+    [Cin, taps*Cout_pad] (= pack_dgrad_weight).  Used by the training step, whose weights change every iteration."""
+    w = weight.detach()
+    _need(w, torch.float32, "pack_weight_into weight", 5)
+    _need16(out, "pack_weight_into out", 2)
+    cout, cin_total = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    c0, c1 = (0, cin_total) if cin_range is None else cin_range
+    if transpose:
+        cout_pad = out.shape[1] // taps
+        want = (c1 - c0, taps * cout_pad)
+    else:
+        cout_pad = cout
+        want = (cout, taps * (c1 - c0))
+    if tuple(out.shape) != want or (transpose and cout_pad < cout):
+        raise ValueError(f"pack_weight_into: out {tuple(out.shape)} does not fit weight {tuple(w.shape)} (want {want})")
+    check(_capi.load().dram_pack_conv_weight(_p(w), _p(out), cout, cin_total, taps, c0, c1 - c0, 1 if transpose else 0,
+                                             cout_pad, ACT_DTYPES[out.dtype], _stream()), "dram_pack_conv_weight")
+    return out
+
+
 class Conv3dDgradPlan:
     """dx [N, D, H, W, Cin] (16-bit NDHWC) = conv_transpose3d(dy, weight) for the forward geometry given.
 

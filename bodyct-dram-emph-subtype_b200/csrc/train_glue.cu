@@ -380,3 +380,56 @@ extern "C" int dram_heads_sigmoid_backward(const void *x, const float *w, const 
   DRAM_CHECK_LAUNCH("heads_partials_reduce_kernel launch");
   return DRAM_OK;
 }
+
+// Weight re-packing for the training step: the fp32 master weights [Cout][Cin][taps] (PyTorch layout) change every
+// optimiser step and the kernels read 16-bit packed copies —
+//   forward / wgrad-free layout  out[co][t][ci]            = w[co][cin0 + ci][t]               (pack_conv_weight)
+//   data-gradient layout         out[ci][t][co (padded)]   = w[co][cin0 + ci][taps - 1 - t]    (pack_dgrad_weight)
+// One thread per output element, coalesced 16-bit writes; the strided fp32 reads of a layer (<= 28 MB) hit in L2.
+namespace dram {
+
+__device__ __forceinline__ uint16_t to16(float v, int is_f16) {
+  if (is_f16) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const uint16_t *>(&h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const uint16_t *>(&h);
+}
+
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float *__restrict__ w, uint16_t *__restrict__ out, int cout,
+                                                         int cin_total, int taps, int cin0, int cin_n, int transpose,
+                                                         int cout_pad, int is_f16) {
+  const long long total = transpose ? (long long)cin_n * taps * cout_pad : (long long)cout * taps * cin_n;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    float v = 0.0f;
+    if (transpose) {
+      const int co = (int)(i % cout_pad);
+      const long long r = i / cout_pad;
+      const int t = (int)(r % taps), ci = (int)(r / taps);
+      if (co < cout) v = __ldg(w + ((size_t)co * cin_total + cin0 + ci) * taps + (taps - 1 - t));
+    } else {
+      const int ci = (int)(i % cin_n);
+      const long long r = i / cin_n;
+      const int t = (int)(r % taps), co = (int)(r / taps);
+      v = __ldg(w + ((size_t)co * cin_total + cin0 + ci) * taps + t);
+    }
+    out[i] = to16(v, is_f16);
+  }
+}
+
+}  // namespace dram
+
+extern "C" int dram_pack_conv_weight(const float *w, void *out, int32_t cout, int32_t cin_total, int32_t taps, int32_t cin0,
+                                     int32_t cin_n, int32_t transpose, int32_t cout_pad, int32_t dtype, void *stream) {
+  DRAM_REQUIRE(w && out, "dram_pack_conv_weight: null pointer");
+  DRAM_REQUIRE(cout > 0 && cin_total > 0 && taps > 0 && cin0 >= 0 && cin_n > 0 && cin0 + cin_n <= cin_total,
+               "dram_pack_conv_weight: bad shape");
+  DRAM_REQUIRE(!transpose || cout_pad >= cout, "dram_pack_conv_weight: cout_pad < cout");
+  DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_pack_conv_weight: bad dtype");
+  const long long total = transpose ? (long long)cin_n * taps * cout_pad : (long long)cout * taps * cin_n;
+  pack_weight_kernel<<<stream_grid(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<uint16_t *>(out), cout, cin_total, taps, cin0, cin_n, transpose, cout_pad, dtype == DRAM_DTYPE_F16);
+  DRAM_CHECK_LAUNCH("pack_weight_kernel launch");
+  return DRAM_OK;
+}

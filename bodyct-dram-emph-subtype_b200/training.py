@@ -12,7 +12,9 @@ What runs where, stated plainly:
 * max-pool and x2 trilinear up-sampling run on K3 / K4 forward and their gather-style adjoints K3T / K4T
   (`train_glue.cu`, `backward.MaxPool3dFn` / `Upsample2xFn`);
 * the two 1x1x1 sigmoid heads run on K5T (`backward.HeadsSigmoidFn`), conv bias gradients on K10's channel sums;
-* what is left — lobe-masked pooling and the three losses on the single-channel maps, weight re-packing and Adam —
+* the per-step re-packing of the fp32 master weights into the kernels' 16-bit operands is one kernel per operand
+  (`backward.pack_weight_into`);
+* what is left — lobe-masked pooling and the three losses on the single-channel maps, shortcut-A slicing and Adam —
   is still ATen CUDA code driven by autograd (cuDNN disabled).  `bench.py --mode train` measures the step as an
   additional line and names this remainder in `config.glue`.
 
@@ -27,7 +29,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .backward import BatchNormTrainFn, HeadsSigmoidFn, MaxPool3dFn, Upsample2xFn, channel_sums, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_dgrad_weight
+from .backward import BatchNormTrainFn, HeadsSigmoidFn, MaxPool3dFn, Upsample2xFn, channel_sums, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_weight_into
 from .engine import LAYER_CFG
 
 ACT = torch.bfloat16  # activations and their gradients
@@ -81,15 +83,16 @@ class ConvFn(torch.autograd.Function):
         cout = weight.shape[0]
         if layer.zero_bias is None or layer.zero_bias.device != x1.device:
             layer.zero_bias = torch.zeros(cout, dtype=torch.float32, device=x1.device)
-        packed = ops.pack_conv_weight(weight, dtype=ACT)
+        taps = weight.shape[2] * weight.shape[3] * weight.shape[4]
 
         def make():
-            w_buf, b_buf = torch.empty_like(packed), torch.zeros_like(layer.zero_bias)
+            w_buf = torch.empty((cout, taps * weight.shape[1]), dtype=ACT, device=x1.device)
+            b_buf = torch.zeros_like(layer.zero_bias)
             plan = ops.Conv3dPlan(x1, w_buf, b_buf, x2=x2, kernel=layer.k, stride=layer.s, dilation=layer.dl, relu=False)
             return plan, w_buf, b_buf
 
         plan, w_buf, b_buf = layer.fwd.get(tuple(t.data_ptr() for t in srcs) + tuple(x1.shape), make)
-        w_buf.copy_(packed)
+        pack_weight_into(weight, w_buf)
         if bias is not None:
             b_buf.copy_(bias.detach())
         layer.flops = plan.flops
@@ -116,7 +119,7 @@ class ConvFn(torch.autograd.Function):
                 dp = layer.dgrad[i].get((dy.data_ptr(),) + tuple(x.shape), lambda: Conv3dDgradPlan(
                     dy, weight, tuple(x.shape[1:4]), kernel=layer.k, stride=layer.s, dilation=layer.dl,
                     cin_range=(off, off + c)))
-                dp.packed.copy_(pack_dgrad_weight(weight, dtype=ACT, cin_range=(off, off + c)))
+                pack_weight_into(weight, dp.packed, transpose=True, cin_range=(off, off + c))
                 grads[i] = dp.run().detach()
             off += c
         db = channel_sums(dy) if ctx.has_bias else None

@@ -352,6 +352,16 @@ int dram_heads_sigmoid_backward(const void *x, const float *w, const float *s0, 
                                 const float *g1, void *dx, float *dw, float *db, void *workspace, int64_t m,
                                 int32_t dtype, void *stream);
 
+/* ---- weight re-packing for the training step ---------------------------- */
+/*
+ * w: fp32 [cout][cin_total][taps] (PyTorch's Conv3d weight, taps = kd*kh*kw) -> 16-bit packed operand of
+ *   transpose == 0: K1's layout   out[co][t][ci]          = w[co][cin0+ci][t],            ci < cin_n
+ *   transpose != 0: dgrad layout  out[ci][t][co < cout_pad] = w[co][cin0+ci][taps-1-t], zero for co >= cout
+ * (the second is the transposed convolution's filter: spatially flipped, channels swapped; backward.pack_dgrad_weight).
+ */
+int dram_pack_conv_weight(const float *w, void *out, int32_t cout, int32_t cin_total, int32_t taps, int32_t cin0,
+                          int32_t cin_n, int32_t transpose, int32_t cout_pad, int32_t dtype, void *stream);
+
 /* ---- layout helpers ---------------------------------------------------- */
 /* fp32 NCDHW -> 16-bit NDHWC and back (test / debugging / hook support). */
 int dram_ncdhw_f32_to_ndhwc_16(const float *x, void *out, int32_t n, int32_t c, int32_t d,

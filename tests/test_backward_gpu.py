@@ -299,3 +299,19 @@ def test_heads_sigmoid_forward_backward_match_autograd(cuda):
     _close_dx(ops.to_ncdhw_f32(xd.grad).cpu(), grads_ref[0], "heads dx", dt)
     for got, ref in zip([w.grad for w in wd] + [b.grad for b in bd], grads_ref[1:]):
         assert torch.allclose(got.cpu(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max() + 1)), (got.cpu(), ref)
+
+
+def test_pack_weight_into_equals_the_torch_packers(cuda):
+    """The device re-packing kernel against ops.pack_conv_weight / backward.pack_dgrad_weight (bit-exact)."""
+    from dram_b200 import backward, ops
+
+    g = torch.Generator().manual_seed(2)
+    for shape, rng in (((64, 128, 3, 3, 3), None), ((32, 64, 3, 3, 3), None), ((64, 192, 3, 3, 3), (128, 192)),
+                       ((256, 64, 1, 1, 1), None)):
+        w = torch.randn(shape, generator=g).to(cuda)
+        for dt in (torch.bfloat16, torch.float16):
+            if rng is None:
+                ref = ops.pack_conv_weight(w, dtype=dt)
+                assert torch.equal(backward.pack_weight_into(w, torch.empty_like(ref)), ref)
+            ref = backward.pack_dgrad_weight(w, dtype=dt, cin_range=rng)
+            assert torch.equal(backward.pack_weight_into(w, torch.empty_like(ref), transpose=True, cin_range=rng), ref)
