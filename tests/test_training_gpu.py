@@ -19,13 +19,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _setup(cuda):
+def _setup(cuda, arch="med3ddram18", batch=2):
     from dram_b200 import med3d
     from oracle import training_oracle as T
 
-    case = T.train_case()
+    case = T.train_case(arch=arch, batch=batch)
     fix = torch.load(os.path.join(GOLDEN, "train_step_med3ddram18.pt"), weights_only=False)
-    model = med3d.resnet18segreg()
+    model = {"med3ddram18": med3d.resnet18segreg, "med3ddram50": med3d.resnet50segreg}[arch]()
     model.load_state_dict(case["sd"])
     model = model.to(cuda).train()
     return case, fix, model
@@ -105,15 +105,17 @@ def test_train_step_loss_and_gradients_reference_loss(cuda, lib):
     _compare_grads(model, grads_ref, 0.6, 0.8)
 
 
-def test_every_conv_backward_in_context_matches_autograd(cuda, lib):
+@pytest.mark.parametrize("arch,n_convs", [("med3ddram18", 21), ("med3ddram50", 53)])
+def test_every_conv_backward_in_context_matches_autograd(cuda, lib, arch, n_convs):
     """Each convolution's dgrad / wgrad inside the real backward pass, checked in isolation on the (x, dy, weight) it
     actually received against autograd on CPU (oracle/backward_oracle.py): all 21 layers of med3ddram18 incl. the
-    stride-2 conv, dilation 2/4, both concatenated decoder inputs and the 32-channel us3."""
+    stride-2 conv, dilation 2/4, both concatenated decoder inputs and the 32-channel us3; and the 53 of the
+    bottleneck network med3ddram50 (1x1x1 convolutions up to 2048 channels, 2304-channel decoder input)."""
     from dram_b200 import ops, training
     from oracle import backward_oracle as B
     from oracle import training_oracle as T
 
-    case, fix, model = _setup(cuda)
+    case, fix, model = _setup(cuda, arch, batch=2 if arch == "med3ddram18" else 1)
     net = training.TrainableMed3D(model)
     training.BACKWARD_TAP = tap = []
     try:
@@ -122,7 +124,7 @@ def test_every_conv_backward_in_context_matches_autograd(cuda, lib):
         torch.cuda.synchronize()
     finally:
         training.BACKWARD_TAP = None
-    assert len(tap) == 21  # every nn.Conv3d except the stem (StemFn) and the 1x1x1 heads
+    assert len(tap) == n_convs  # every nn.Conv3d except the stem (StemFn) and the 1x1x1 heads
     for name, srcs, dy, weight, dxs, dw in tap:
         lay = net.layers[name]
         x = torch.cat([ops.to_ncdhw_f32(s) for s in srcs], dim=1).cpu()
