@@ -338,9 +338,9 @@ class _StdoutToStderr:
 def run_train_arm(args, out):
     """BASELINE config 5: med3ddram training, forward + loss + backward + gradient all-reduce + Adam, bf16 activations,
     one process per GPU (NCCL), per-GPU batch `--batch` (default 1 here).  Convolutions (fwd/dgrad/wgrad), train-mode
-    BatchNorm(+ReLU, +residual, SyncBN exchange), max-pool, up-sampling, heads and weight re-packing run on the
-    hand-written kernels; the losses on the single-channel maps and Adam are ATen CUDA ops (training
-    step) — stated in `config.glue`.  `value` = volumes/s with the batch resident in HBM, `e2e` copies the batch
+    BatchNorm(+ReLU, +residual, SyncBN exchange), max-pool, up-sampling, heads, weight re-packing, the loss with its
+    gradient (K11) and Adam (K12) run on the hand-written kernels; what is left on ATen is named in `config.glue` (see
+    DESIGN.md section 3, training step).  `value` = volumes/s with the batch resident in HBM, `e2e` copies the batch
     from pinned host memory every step and reads the loss back."""
     import dram_b200  # noqa: F401
     from dram_b200 import med3d, training
@@ -421,7 +421,8 @@ def run_train_arm(args, out):
                    "global_batch": world * B, "parallelism": f"data-parallel x{world}, bucketed NCCL gradient all-reduce"
                                                              f"{' + SyncBatchNorm' if world > 1 else ''}",
                    "glue": "native: conv fwd/dgrad/wgrad, BatchNorm(+ReLU,+residual), max-pool, up-sampling, heads; "
-                           "weight re-packing; ATen: losses on 1-channel maps, Adam",
+                           "weight re-packing, loss + gradient (K11), Adam (K12); ATen: shortcut-A slicing/padding, "
+                           "stem weight-gradient re-layout, per-channel dtype casts",
                    "l2": "activations per step (> 10 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks, "loss": float(loss),
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -16,6 +16,7 @@ DRAM_OK = 0
 DRAM_DTYPE_BF16 = 0
 DRAM_DTYPE_F16 = 1
 CONV_ALGO = {"auto": 0, "tiles": 1, "planes": 2}
+LOSS_COEF_HEAD = 16  # DRAM_LOSS_COEF_HEAD
 
 
 class ConvDesc(C.Structure):
@@ -93,6 +94,13 @@ SIGNATURES = {
     "dram_heads_workspace_bytes": (_i64, []),
     "dram_heads_sigmoid_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dram_heads_sigmoid_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "dram_train_loss_workspace_bytes": (_i64, [_i32]),
+    "dram_train_loss_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
+                                          _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "dram_train_loss_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
+                                           _i32, _vp, _vp, _vp]),
+    "dram_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, _i32,
+                                 C.c_float, _vp]),
     "dram_pack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ncdhw_f32_to_ndhwc_16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_ndhwc_16_to_ncdhw_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),

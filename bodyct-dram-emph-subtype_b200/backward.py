@@ -268,6 +268,110 @@ class HeadsSigmoidFn(torch.autograd.Function):
         return dx, dw[0].reshape(sw0), db[0:1].reshape(sb0), dw[1].reshape(sw1), db[1:2].reshape(sb1)
 
 
+class TrainLossFn(torch.autograd.Function):
+    """K11: loss of `ScanRegLightningModule.shared_step(TRAIN)` (models.py:547-565) and its gradient on the two dense
+    maps, fused (`dram_train_loss_forward/backward`).
+
+    (cle_map, pse_map [B,1,D2,H2,W2] fp32; lungs, ems [B,D,H,W] 0/1 bytes or bool; cle_labels, pse_labels int64 [B];
+    cle_bands, pse_bands fp32 [B,2]; cle_weights, pse_weights fp32 [B]) ->
+    (loss scalar, terms fp32 [4] = loss_cle, loss_pse, mul_loss, seg_loss, regs fp32 [B,2] = the lobe-masked means of
+    med3d.py:387).  Only `loss` carries a gradient."""
+
+    @staticmethod
+    def forward(ctx, cle_map, pse_map, lungs, ems, cle_labels, pse_labels, cle_bands, pse_bands, cle_weights, pse_weights,
+                beta=0.7338, gamma=0.2578):
+        lib = _capi.load()
+        _need(cle_map, torch.float32, "train_loss cle_map", 5)
+        _need(pse_map, torch.float32, "train_loss pse_map", 5)
+        if cle_map.shape != pse_map.shape or cle_map.shape[1] != 1:
+            raise ValueError(f"train_loss: maps {tuple(cle_map.shape)} / {tuple(pse_map.shape)} must both be [B,1,D2,H2,W2]")
+        dev = cle_map.device
+        lungs, ems = _mask_u8(lungs, "train_loss lungs"), _mask_u8(ems, "train_loss ems")
+        B, _, d2, h2, w2 = cle_map.shape
+        if lungs.shape != ems.shape or lungs.shape[0] != B:
+            raise ValueError(f"train_loss: masks {tuple(lungs.shape)} / {tuple(ems.shape)} vs batch {B}")
+        d, h, w = lungs.shape[1:]
+
+        def vec(t, dtype, shape, what):
+            t = t.to(device=dev, dtype=dtype).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError(f"train_loss: {what} has shape {tuple(t.shape)}, expected {shape}")
+            return t
+
+        cl, pl = vec(cle_labels, torch.int64, (B,), "cle_labels"), vec(pse_labels, torch.int64, (B,), "pse_labels")
+        cb, pb = vec(cle_bands, torch.float32, (B, 2), "cle_bands"), vec(pse_bands, torch.float32, (B, 2), "pse_bands")
+        cw, pw = vec(cle_weights, torch.float32, (B,), "cle_weights"), vec(pse_weights, torch.float32, (B,), "pse_weights")
+        coef = torch.empty(_capi.LOSS_COEF_HEAD + 4 * B, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.dram_train_loss_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+        check(lib.dram_train_loss_forward(_p(cle_map), _p(pse_map), _p(lungs), _p(ems), _p(cl), _p(pl), _p(cb), _p(pb), _p(cw),
+                                          _p(pw), B, d, h, w, d2, h2, w2, beta, gamma, _p(coef), _p(ws), _stream()),
+              "dram_train_loss_forward")
+        ctx.save_for_backward(cle_map, pse_map, lungs, ems, cl, pl, coef)
+        ctx.geom = (B, d, h, w, d2, h2, w2)
+        loss, terms = coef[0].clone(), coef[1:5].clone()
+        regs = coef[_capi.LOSS_COEF_HEAD:].view(B, 4)[:, :2].clone()
+        ctx.mark_non_differentiable(terms, regs)
+        return loss, terms, regs
+
+    @staticmethod
+    def backward(ctx, gloss, _gterms, _gregs):
+        cle_map, pse_map, lungs, ems, cl, pl, coef = ctx.saved_tensors
+        g0, g1 = torch.empty_like(cle_map), torch.empty_like(pse_map)
+        gl = gloss.to(torch.float32).contiguous()
+        check(_capi.load().dram_train_loss_backward(_p(cle_map), _p(pse_map), _p(lungs), _p(ems), _p(cl), _p(pl), _p(coef),
+                                                    _p(gl), *ctx.geom, _p(g0), _p(g1), _stream()),
+              "dram_train_loss_backward")
+        return (g0, g1) + (None,) * 10
+
+
+def _mask_u8(mask, what):
+    """bool / uint8 0-1 CUDA mask [B,D,H,W] -> contiguous uint8 view (no copy for bool)."""
+    if not mask.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (there is no CPU path)")
+    if mask.dtype == torch.bool:
+        mask = mask.contiguous().view(torch.uint8)
+    elif mask.dtype != torch.uint8:
+        mask = (mask != 0).contiguous().view(torch.uint8)
+    if mask.dim() == 5 and mask.shape[1] == 1:
+        mask = mask[:, 0]
+    if mask.dim() != 4:
+        raise ValueError(f"{what}: expected [B,D,H,W], got {tuple(mask.shape)}")
+    return mask.contiguous()
+
+
+class FlatAdam:
+    """K12: torch.optim.Adam(params, lr) of `configure_optimizers` (models.py:685-698) as one launch per step over flat
+    fp32 buffers.  `flat_param` / `flat_grad` hold every parameter / gradient back to back (the parameters of the
+    network are views into `flat_param`); exp_avg / exp_avg_sq live here.  `lr` may be changed between steps (the
+    reference's ExponentialLR(gamma=0.95) steps once per epoch: `decay_lr()`)."""
+
+    def __init__(self, flat_param, flat_grad, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        _need(flat_param, torch.float32, "FlatAdam flat_param", 1)
+        _need(flat_grad, torch.float32, "FlatAdam flat_grad", 1)
+        if flat_param.shape != flat_grad.shape:
+            raise ValueError(f"FlatAdam: {tuple(flat_param.shape)} parameters vs {tuple(flat_grad.shape)} gradients")
+        self.param, self.grad = flat_param, flat_grad
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(flat_param), torch.zeros_like(flat_param)
+        self.lr, self.betas, self.eps, self.steps = float(lr), (float(betas[0]), float(betas[1])), float(eps), 0
+
+    def step(self, grad_scale=1.0):
+        self.steps += 1
+        check(_capi.load().dram_adam_step(_p(self.param), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq),
+                                          self.param.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.steps,
+                                          grad_scale, _stream()), "dram_adam_step")
+
+    def decay_lr(self, gamma=0.95):
+        self.lr *= gamma
+
+    def state_dict(self):
+        return {"step": self.steps, "lr": self.lr, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+
+    def load_state_dict(self, state):
+        self.steps, self.lr = int(state["step"]), float(state["lr"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+
+
 _BN_WS = {}
 
 

@@ -7,8 +7,10 @@ reference's seven keys and their spelling.  If pytorch_lightning is importable t
 from its LightningModule/LightningDataModule; otherwise from light stand-ins with the same surface,
 so `processor.py` runs without Lightning.
 
-Only inference is implemented: the training/validation/test steps of the reference need the
-backward kernels that are a later row of the plan, and raise NotImplementedError here.
+`ScanRegLightningModule` also carries the reference's training surface (`training_step`, `validation_step`,
+`test_step`, `configure_optimizers`; models.py:530-600, 685-698) on `training.TrainStep` — manual optimisation: one
+call runs forward, loss, backward, the gradient exchange and Adam on the sm_100a kernels.  The classification
+module's training and the epoch-end reporting (confusion matrices, CSVs, debug drawings) are not built.
 """
 import enum
 
@@ -256,6 +258,87 @@ class ScanRegLightningModule(_ScanModule):
     def _ratio_to_label(self, ratios, ratio_mapping):
         labels = [ratio_to_label(r.item(), ratio_mapping) for r in ratios]
         return torch.as_tensor(labels).long().to(ratios.device)
+
+    # ------------------------------------------------------------------ training surface
+    automatic_optimization = False  # under Lightning: training_step does backward + optimiser itself
+
+    def configure_optimizers(self):
+        """The reference returns torch.optim.Adam(lr=args.lr) + ExponentialLR(0.95) (models.py:685-698) for Lightning
+        to drive; here Adam is K12 inside `training_step` and the decay is `on_train_epoch_end`, so there is nothing
+        for the trainer to step."""
+        return None
+
+    def _class_weights(self, name, labels):
+        table = getattr(self, name, None)
+        if table is None:  # models.py:546-551 reads them from the training dataset
+            try:
+                table = getattr(self.trainer.datamodule.datasets[RunningStage.TRAINING], name)
+            except Exception:
+                table = None
+        if table is None:
+            return torch.ones(len(labels), dtype=torch.float32)
+        return torch.tensor([float(table[int(c)]) for c in labels], dtype=torch.float32)
+
+    def train_engine(self):
+        """The `training.TrainStep` behind `training_step` (built on first use; owns the flat parameter, gradient and
+        Adam buffers).  Data-parallel when torch.distributed is initialised: gradient all-reduce per bucket and
+        SyncBatchNorm, as train.py:100-101 ask of Lightning."""
+        eng = getattr(self, "_train_engine", None)
+        if eng is None:
+            import torch.distributed as dist
+
+            from . import training
+
+            if self.model.head_kind != "reg":
+                raise RuntimeError("training_step needs a *dram (regression) architecture (train.py:72)")
+            multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            eng = training.TrainStep(self.model.train(), lr=float(getattr(self.args, "lr", 1e-4)), sync_bn=multi)
+            object.__setattr__(self, "_train_engine", eng)
+        return eng
+
+    def training_step(self, batch, batch_idx):
+        """shared_step(TRAIN), models.py:530-570: returns the reference's dict (`loss` detached: backward and the
+        Adam step already happened) plus the four logged loss terms."""
+        from . import training
+
+        dev = next(self.model.parameters()).device
+        cle_labels, pse_labels = batch["cls_label"].reshape(-1).long(), batch["pse_label"].reshape(-1).long()
+        bands = [training.regression_label_bands(lab.tolist(), table).to(dev)
+                 for lab, table in ((cle_labels, CLE_RATIO_MAP), (pse_labels, PSE_RATIO_MAP))]
+        weights = [self._class_weights(name, lab.tolist()).to(dev)
+                   for name, lab in (("cle_class_weights", cle_labels), ("pse_class_weights", pse_labels))]
+        dev_batch = {"image": self._to_device(batch["image"]).float().contiguous(),
+                     "lung_mask": self._to_device(batch["lung_mask"]), "em_mask": self._to_device(batch["em_mask"]),
+                     "cls_label": cle_labels.to(dev), "pse_label": pse_labels.to(dev)}
+        if not self.model.training:
+            self.model.train()
+        eng = self.train_engine()
+        loss = eng.step(dev_batch, bands[0], bands[1], weights[0], weights[1])
+        regs = eng.last["reg_outs"]
+        out = {"loss": loss, "pred_cle_labels": self._ratio_to_label(regs[0], CLE_RATIO_MAP),
+               "pred_pse_labels": self._ratio_to_label(regs[1], PSE_RATIO_MAP),
+               "cle_labels": cle_labels, "pse_labels": pse_labels,
+               "index": batch["index"].squeeze(-1) if "index" in batch else None}
+        out.update({k: v for k, v in eng.last.items() if k != "reg_outs"})
+        return out
+
+    def on_train_epoch_end(self):
+        eng = getattr(self, "_train_engine", None)
+        if eng is not None:
+            eng.decay_lr(0.95)  # ExponentialLR(gamma=0.95), one step per epoch (models.py:694-697)
+
+    def _eval_step(self, batch, batch_idx):
+        """shared_step(VALID / TEST), models.py:571-582 without the debug drawings: forward, predicted labels."""
+        with torch.no_grad():
+            image = self._to_device(batch["image"]).float()
+            lungs = _as_u8(self._to_device(batch["lung_mask"]))
+            _, regs = self.model.eval()(image.unsqueeze(1).contiguous(), lungs)
+            return {"pred_cle_labels": self._ratio_to_label(regs[0], CLE_RATIO_MAP),
+                    "pred_pse_labels": self._ratio_to_label(regs[1], PSE_RATIO_MAP),
+                    "cle_labels": batch["cls_label"], "pse_labels": batch["pse_label"],
+                    "index": batch["index"].squeeze(-1) if "index" in batch else None}
+
+    validation_step = test_step = _eval_step
 
 
 class ScanCLSLightningModule(_ScanModule):

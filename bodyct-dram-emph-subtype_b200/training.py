@@ -14,9 +14,13 @@ What runs where, stated plainly:
 * the two 1x1x1 sigmoid heads run on K5T (`backward.HeadsSigmoidFn`), conv bias gradients on K10's channel sums;
 * the per-step re-packing of the fp32 master weights into the kernels' 16-bit operands is one kernel per operand
   (`backward.pack_weight_into`);
-* what is left — lobe-masked pooling and the three losses on the single-channel maps, shortcut-A slicing and Adam —
-  is still ATen CUDA code driven by autograd (cuDNN disabled).  `bench.py --mode train` measures the step as an
-  additional line and names this remainder in `config.glue`.
+* lobe-masked pooling + the three losses, forward and gradient, are K11 (`backward.TrainLossFn`, train_loss.cu); Adam is
+  K12, one launch over the flat parameter / gradient buffers (`backward.FlatAdam`); the convolutions' weight gradients
+  are written by K9 straight into the flat gradient buffer (no AccumulateGrad pass);
+* what is left on ATen (cuDNN disabled) is shortcut-A slicing/padding, the stem weight-gradient re-layout and dtype
+  casts of per-channel vectors.  `TrainStep(loss="aten", optimizer="torch")` keeps the earlier ATen loss and
+  torch.optim.Adam for A/B checks.  `bench.py --mode train` measures the step as an additional line and names the
+  remainder in `config.glue`.
 
 The module takes the drop-in network (`med3d.resnet{18,34,50}segreg()`, reference `state_dict` keys) and reproduces
 what the reference does in `ScanRegLightningModule.shared_step(TRAIN)` (models.py:530-570): forward in train mode
@@ -29,7 +33,8 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .backward import BatchNormTrainFn, HeadsSigmoidFn, MaxPool3dFn, Upsample2xFn, channel_sums, Conv3dDgradPlan, Conv3dWgradPlan, GradBuckets, pack_weight_into
+from .backward import (BatchNormTrainFn, Conv3dDgradPlan, Conv3dWgradPlan, FlatAdam, GradBuckets, HeadsSigmoidFn, MaxPool3dFn,
+                       TrainLossFn, Upsample2xFn, channel_sums, pack_weight_into)
 from .engine import LAYER_CFG
 
 ACT = torch.bfloat16  # activations and their gradients
@@ -72,6 +77,9 @@ class ConvLayer:
         self.zero_bias = None
         self.flops = 0  # algorithmic forward FLOPs (2*M*N*K) of the last call
         self.dw = None  # fp32 [Cout, Cin_total, kd, kh, kw], shared by the wgrad plans of both sources
+        # (flat-buffer view of weight.grad, callback): when set, K9 writes the weight gradient there directly and the
+        # callback replaces autograd's post-accumulate hook (TrainStep)
+        self.grad_sink = None
 
 
 class ConvFn(torch.autograd.Function):
@@ -107,13 +115,17 @@ class ConvFn(torch.autograd.Function):
         weight, *srcs = ctx.saved_tensors
         dy = dy.contiguous()
         cin_total = weight.shape[1]
-        if layer.dw is None or layer.dw.device != dy.device:
-            layer.dw = torch.zeros(tuple(weight.shape), dtype=torch.float32, device=dy.device)
+        if layer.grad_sink is not None:
+            dw = layer.grad_sink[0]
+        else:
+            if layer.dw is None or layer.dw.device != dy.device:
+                layer.dw = torch.zeros(tuple(weight.shape), dtype=torch.float32, device=dy.device)
+            dw = layer.dw
         grads, off = [None, None], 0
         for i, x in enumerate(srcs):
             c = x.shape[4]
-            wp = layer.wgrad[i].get((x.data_ptr(), dy.data_ptr()) + tuple(x.shape), lambda: Conv3dWgradPlan(
-                x, dy, dw=layer.dw, kernel=layer.k, stride=layer.s, dilation=layer.dl, cin_total=cin_total, cin_offset=off))
+            wp = layer.wgrad[i].get((x.data_ptr(), dy.data_ptr(), dw.data_ptr()) + tuple(x.shape), lambda: Conv3dWgradPlan(
+                x, dy, dw=dw, kernel=layer.k, stride=layer.s, dilation=layer.dl, cin_total=cin_total, cin_offset=off))
             wp.run()
             if ctx.needs_input_grad[3 + i]:
                 dp = layer.dgrad[i].get((dy.data_ptr(),) + tuple(x.shape), lambda: Conv3dDgradPlan(
@@ -125,9 +137,12 @@ class ConvFn(torch.autograd.Function):
         db = channel_sums(dy) if ctx.has_bias else None
         if BACKWARD_TAP is not None:
             BACKWARD_TAP.append((layer.name, [x.clone() for x in srcs], dy.clone(), weight.detach().clone(),
-                                 [None if g is None else g.clone() for g in grads[:len(srcs)]], layer.dw.clone()))
+                                 [None if g is None else g.clone() for g in grads[:len(srcs)]], dw.clone()))
+        if layer.grad_sink is not None:  # weight.grad is complete in the flat buffer: tell the bucket, skip AccumulateGrad
+            layer.grad_sink[1]()
+            return None, None, db, grads[0], grads[1]
         # AccumulateGrad adds layer.dw into weight.grad right away (stream order), so the shared buffer can be reused
-        return None, layer.dw, db, grads[0], grads[1]
+        return None, dw, db, grads[0], grads[1]
 
 
 class StemFn(torch.autograd.Function):
@@ -230,9 +245,10 @@ class TrainableMed3D:
         y = self._bn(us.conv_blocks[0][1], self._conv(name + ".conv_blocks.0.0", us.conv_blocks[0][0], up, skip))
         return self._bn(us.conv_blocks[1][1], self._conv(name + ".conv_blocks.1.0", us.conv_blocks[1][0], y))
 
-    def forward(self, image, lungs=None):
+    def forward(self, image, lungs=None, with_regs=True):
         """image [B, D, H, W] fp32 (CUDA), lungs [B, D, H, W] float 0/1 or None ->
-        (dense_outs: 2 x fp32 [B, 1, D/2, H/2, W/2], reg_outs: 2 x fp32 [B]) as med3d.py:369-388."""
+        (dense_outs: 2 x fp32 [B, 1, D/2, H/2, W/2], reg_outs: 2 x fp32 [B]) as med3d.py:369-388.
+        `with_regs=False` skips the lobe-masked means (K11 computes them together with the loss) and returns None."""
         m = self.model
         B = image.shape[0]
         with torch.backends.cudnn.flags(enabled=False):
@@ -257,6 +273,8 @@ class TrainableMed3D:
                 v = xup3.float()  # [B, D, H, W, 32]; the 1x1x1 heads (med3d.py:329-332, 382) are a 32-long dot per voxel
                 dense = [torch.sigmoid(v @ fc.weight.view(fc.weight.shape[0], 32).t() + fc.bias).permute(0, 4, 1, 2, 3)
                          for fc in m.fcs]
+            if not with_regs:
+                return dense, None
             if lungs is None:
                 mask = torch.ones((B, 1) + tuple(dense[0].shape[2:]), device=image.device)
             else:
@@ -328,27 +346,61 @@ def training_loss(dense, regs, lungs, ems, cle_labels, pse_labels, cle_bands, ps
 class TrainStep:
     """forward -> loss -> backward -> gradient average over the process group -> Adam (models.py:685-698, lr from args).
 
-    Gradients live in one flat fp32 buffer (`GradBuckets`, parameters in reverse registration order, i.e. roughly the
-    order backward produces them).  A post-accumulate hook on every parameter counts its bucket down; the bucket's
-    (asynchronous, NCCL) all-reduce is launched the moment its last gradient lands, so the exchange overlaps the rest
-    of the backward pass.  `sync_bn=True` all-reduces the BatchNorm statistics as well (train.py:101).
+    Parameters and gradients live in two flat fp32 buffers with the same layout (`GradBuckets`, parameters in reverse
+    registration order, i.e. roughly the order backward produces them); every `nn.Parameter` of the network becomes a
+    view into the parameter buffer, so `state_dict()` / `load_state_dict()` keep working.  K9 writes each convolution's
+    weight gradient straight into its slice; the remaining gradients arrive through autograd's AccumulateGrad.  A
+    bucket's (asynchronous, NCCL) all-reduce is launched the moment its last gradient lands, so the exchange overlaps
+    the rest of the backward pass.  `sync_bn=True` all-reduces the BatchNorm statistics as well (train.py:101).
+
+    loss = "native" (K11, `TrainLossFn`) | "aten" (`training_loss`); optimizer = "native" (K12, `FlatAdam`) | "torch"
+    (torch.optim.Adam).  `last` holds the loss terms and the lobe-masked means of the last step (device tensors).
     """
 
-    def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None, sync_bn=False):
+    def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None, sync_bn=False, loss="native", optimizer="native"):
+        if loss not in ("native", "aten") or optimizer not in ("native", "torch"):
+            raise ValueError(f"TrainStep: loss={loss!r} / optimizer={optimizer!r} (native|aten, native|torch)")
         self.net = TrainableMed3D(model, sync_bn=(group if group is not None else True) if sync_bn else None)
         self.params = [(n, p) for n, p in model.named_parameters()]
         dev = self.params[0][1].device
         self.buckets = GradBuckets([(n, tuple(p.shape)) for n, p in reversed(self.params)], dev, bucket_bytes)
+        self.flat_param = torch.empty_like(self.buckets.flat)
         self._bucket_size = [0] * self.buckets.num_buckets
+        # convolutions that run through ConvFn: everything but the stem (StemFn re-lays its gradient out with ATen) and
+        # the two 1x1x1 heads (HeadsSigmoidFn)
+        conv_weights = {name + ".weight": conv for name, conv in model.named_modules()
+                        if isinstance(conv, torch.nn.Conv3d) and name != "conv1" and not name.startswith("fcs.")}
         for n, p in self.params:
+            off, numel, shape = self.buckets.slices[n]
+            view = self.flat_param[off:off + numel].view(shape)
+            view.copy_(p.data)
+            p.data = view  # the parameter now lives in the flat buffer (same values, same shape)
             p.grad = self.buckets.view(n)
             b = self.buckets.bucket_of[n]
             self._bucket_size[b] += 1
-            p.register_post_accumulate_grad_hook(self._make_hook(n, b))
+            conv = conv_weights.get(n)
+            if conv is not None:
+                self.net._layer(n[:-len(".weight")], conv).grad_sink = (p.grad, self._make_ready(b))
+            else:
+                p.register_post_accumulate_grad_hook(self._make_hook(n, b))
         self._pending = list(self._bucket_size)
         self._launched = [False] * self.buckets.num_buckets
-        self.opt = torch.optim.Adam([p for _, p in self.params], lr=lr)
+        self.loss_kind = loss
+        if optimizer == "native":
+            self.opt = FlatAdam(self.flat_param, self.buckets.flat, lr=lr)
+        else:
+            self.opt = torch.optim.Adam([p for _, p in self.params], lr=lr)
         self.group = group
+        self.last = {}
+
+    def _grad_ready(self, bucket):
+        self._pending[bucket] -= 1
+        if self._pending[bucket] == 0:
+            self._launched[bucket] = True
+            self.buckets.reduce_bucket(bucket, self.group)
+
+    def _make_ready(self, bucket):
+        return lambda: self._grad_ready(bucket)
 
     def _make_hook(self, name, bucket):
         def hook(param):
@@ -356,10 +408,7 @@ class TrainStep:
             if param.grad is not None and param.grad.data_ptr() != view.data_ptr():  # autograd replaced the tensor
                 view.copy_(param.grad)
                 param.grad = view
-            self._pending[bucket] -= 1
-            if self._pending[bucket] == 0:
-                self._launched[bucket] = True
-                self.buckets.reduce_bucket(bucket, self.group)
+            self._grad_ready(bucket)
         return hook
 
     def zero_grad(self):
@@ -367,16 +416,40 @@ class TrainStep:
         self._pending = list(self._bucket_size)
         self._launched = [False] * self.buckets.num_buckets
 
+    def decay_lr(self, gamma=0.95):
+        """ExponentialLR(gamma=0.95), stepped once per epoch by Lightning (models.py:694-697)."""
+        if isinstance(self.opt, FlatAdam):
+            self.opt.decay_lr(gamma)
+        else:
+            for g in self.opt.param_groups:
+                g["lr"] *= gamma
+
     def step(self, batch, cle_bands, pse_bands, cle_weights, pse_weights):
+        last_name, last_param = self.params[-1]
+        if last_param.data_ptr() != self.flat_param.data_ptr() or last_param.grad is None:
+            raise RuntimeError("TrainStep: the network's parameters no longer live in this step's flat buffers (the model "
+                               "was moved or re-typed after TrainStep was built); build a new TrainStep")
         self.zero_grad()
-        lungs = batch["lung_mask"].float()
-        dense, regs = self.net.forward(batch["image"], lungs)
-        loss = training_loss(dense, regs, lungs, batch["em_mask"].float(), batch["cls_label"], batch["pse_label"],
-                             cle_bands, pse_bands, cle_weights, pse_weights)
+        if self.loss_kind == "native":
+            dense, _ = self.net.forward(batch["image"], None, with_regs=False)
+            loss, terms, regs = TrainLossFn.apply(dense[0], dense[1], batch["lung_mask"], batch["em_mask"], batch["cls_label"],
+                                                  batch["pse_label"], cle_bands, pse_bands, cle_weights, pse_weights,
+                                                  BETA, GAMMA)
+            self.last = {"loss_cle": terms[0], "loss_pse": terms[1], "mul_loss": terms[2], "seg_loss": terms[3],
+                         "reg_outs": [regs[:, 0], regs[:, 1]]}
+        else:
+            lungs = batch["lung_mask"].float()
+            dense, regs = self.net.forward(batch["image"], lungs)
+            loss = training_loss(dense, regs, lungs, batch["em_mask"].float(), batch["cls_label"], batch["pse_label"],
+                                 cle_bands, pse_bands, cle_weights, pse_weights)
+            self.last = {"reg_outs": [r.detach() for r in regs]}
         loss.backward()
         for i in range(self.buckets.num_buckets):  # buckets holding a parameter that received no gradient
             if not self._launched[i]:
                 self.buckets.reduce_bucket(i, self.group)
         self.buckets.wait()
         self.opt.step()
+        # the kernels changed the parameters behind autograd's back: bump the version counters (the inference engine
+        # re-packs its weights when they move, engine.Med3DEngine._current_weight_version)
+        torch.autograd.graph.increment_version([p for _, p in self.params])
         return loss.detach()

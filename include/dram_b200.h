@@ -352,6 +352,51 @@ int dram_heads_sigmoid_backward(const void *x, const float *w, const float *s0, 
                                 const float *g1, void *dx, float *dw, float *db, void *workspace, int64_t m,
                                 int32_t dtype, void *stream);
 
+/* ---- K11: the training loss and its gradient ---- */
+/*
+ * What ScanRegLightningModule.shared_step(TRAIN) computes from the two sigmoid maps (models.py:547-565) and what
+ * autograd returns for them, fused: the lobe-masked means (med3d.py:383-387), `_interval_regression_loss`
+ * (models.py:495-506), BinaryDice between the masked maps and the masked BinaryCrossEntropy of clamp(cle + pse, 0, 1)
+ * (models.py:508-518, metrics.py:4-47); total = loss_cle + loss_pse + 2 * mul_loss + seg_loss.
+ *   cle_map, pse_map : fp32 [b][d2][h2][w2] (the dense outputs, values in (0, 1))
+ *   lungs, ems       : 0/1 bytes [b][d][h][w] at scan resolution; sampled with ATen's legacy `nearest` index
+ *   cle_labels, pse_labels : int64 [b] (a scan's `ems` counts only if one of its labels is > 0, models.py:553)
+ *   *_bands fp32 [b][2] = (lo, hi) of `_generate_regression_labels` (models.py:477-493); *_weights fp32 [b]
+ *   coef : fp32 [DRAM_LOSS_COEF_HEAD + 4*b] written by forward, read by backward:
+ *          [TOTAL] [CLE] [PSE] [MUL] [SEG] = the loss and its four terms; 5..15 internal;
+ *          then per sample {mean of cle_map in the lungs, mean of pse_map in the lungs, 2 internal}
+ *          (= reg_outs of med3d.py:387, what `_ratio_to_label` bins, models.py:543-544)
+ *   grad_loss : device pointer to d(objective)/d(loss), or NULL for 1
+ *   grad_cle, grad_pse : fp32, same shape as the maps
+ * Two-phase fixed-order fp64 reduction: results are deterministic.  b <= 64.
+ */
+#define DRAM_LOSS_COEF_TOTAL 0
+#define DRAM_LOSS_COEF_CLE 1
+#define DRAM_LOSS_COEF_PSE 2
+#define DRAM_LOSS_COEF_MUL 3
+#define DRAM_LOSS_COEF_SEG 4
+#define DRAM_LOSS_COEF_HEAD 16
+int64_t dram_train_loss_workspace_bytes(int32_t b);
+int dram_train_loss_forward(const float *cle_map, const float *pse_map, const uint8_t *lungs, const uint8_t *ems,
+                            const int64_t *cle_labels, const int64_t *pse_labels, const float *cle_bands,
+                            const float *pse_bands, const float *cle_weights, const float *pse_weights, int32_t b,
+                            int32_t d, int32_t h, int32_t w, int32_t d2, int32_t h2, int32_t w2, float beta,
+                            float gamma, float *coef, void *workspace, void *stream);
+int dram_train_loss_backward(const float *cle_map, const float *pse_map, const uint8_t *lungs, const uint8_t *ems,
+                             const int64_t *cle_labels, const int64_t *pse_labels, const float *coef,
+                             const float *grad_loss, int32_t b, int32_t d, int32_t h, int32_t w, int32_t d2,
+                             int32_t h2, int32_t w2, float *grad_cle, float *grad_pse, void *stream);
+
+/* ---- K12: Adam over flat buffers (models.py:685-698 `torch.optim.Adam(self.parameters(), lr=...)`) ---- */
+/*
+ * One launch updates every parameter: param, grad, exp_avg, exp_avg_sq are fp32 [n], 16-byte aligned (the flat
+ * buffers of the training step).  torch.optim.Adam's update with amsgrad off and no weight decay:
+ *   g = grad * grad_scale;  m += (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;
+ *   param -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps),   step = 1, 2, ...
+ */
+int dram_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int32_t step, float grad_scale, void *stream);
+
 /* ---- weight re-packing for the training step ---------------------------- */
 /*
  * w: fp32 [cout][cin_total][taps] (PyTorch's Conv3d weight, taps = kd*kh*kw) -> 16-bit packed operand of

@@ -315,3 +315,111 @@ def test_pack_weight_into_equals_the_torch_packers(cuda):
                 assert torch.equal(backward.pack_weight_into(w, torch.empty_like(ref)), ref)
             ref = backward.pack_dgrad_weight(w, dtype=dt, cin_range=rng)
             assert torch.equal(backward.pack_weight_into(w, torch.empty_like(ref), transpose=True, cin_range=rng), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# K11 (training loss + gradient) and K12 (Adam)
+# ------------------------------------------------------------------------------------------
+LOSS_CASES = [
+    # batch, mask dims, map dims, (cle labels, pse labels)
+    (2, (32, 32, 32), (16, 16, 16), ([3, 0], [1, 2])),      # the x2 case of the network
+    (3, (20, 24, 28), (7, 9, 11), ([0, 2, 0], [0, 0, 1])),  # generic legacy-nearest indices; sample 0 has no label
+    (1, (9, 10, 70), (9, 10, 70), ([5], [0])),              # same size, rows longer than two warp passes
+    (2, (16, 16, 16), (8, 8, 8), ([0, 0], [0, 0])),         # no positive label at all: alpha clamps to 0.7
+]
+
+
+@pytest.mark.parametrize("case", LOSS_CASES)
+def test_train_loss_kernel_matches_oracle(cuda, lib, case):
+    """K11 against the CPU oracle of models.py:547-565 (oracle/training_oracle.total_loss, pinned to the reference by
+    the golden training step) and autograd: loss and its four terms within 1e-5 relative, the lobe-masked means within
+    1e-6, the gradient of both maps within 1e-5 of its largest entry (+1e-4 relative).  The maps include sums above 1
+    (clamp(cle + pse, 0, 1) blocks the gradient) and values at the 1e-6 clamp of the cross entropy."""
+    import torch.nn.functional as F
+
+    from dram_b200.backward import TrainLossFn
+    from oracle import training_oracle as T
+
+    B, mdims, dims, (cl, pl) = case
+    g = torch.Generator().manual_seed(B * 100 + dims[0])
+    d0 = torch.rand((B, 1) + dims, generator=g) * 0.8
+    d1 = torch.rand((B, 1) + dims, generator=g) * 0.8
+    d0.view(-1)[:7], d1.view(-1)[:7] = 3e-7, 2e-7   # pt = 1 - 5e-7 > 1 - eps where t = 0, pt = 5e-7 < eps where t = 1
+    lungs = torch.rand((B,) + mdims, generator=g) > 0.45
+    ems = torch.rand((B,) + mdims, generator=g) > 0.7
+    cl, pl = torch.tensor(cl), torch.tensor(pl)
+    from dram_b200.models import CLE_RATIO_MAP, PSE_RATIO_MAP
+    cb, pb = T.label_bands(cl, CLE_RATIO_MAP), T.label_bands(pl, PSE_RATIO_MAP)
+    cw, pw = torch.rand(B, generator=g) + 0.5, torch.rand(B, generator=g) + 0.5
+
+    a, b = d0.clone().requires_grad_(True), d1.clone().requires_grad_(True)
+    lm = F.interpolate(lungs.unsqueeze(1).float(), dims, mode="nearest")
+    regs_ref = [(x * lm).view(B, -1).sum(-1) / lm.view(B, -1).sum(-1) for x in (a, b)]
+    loss_ref = T.total_loss([a, b], regs_ref, lungs.unsqueeze(1).float(), ems.unsqueeze(1).float(), cl, pl, cb, pb, cw, pw)
+    (3.0 * loss_ref).backward()
+
+    x0, x1 = d0.to(cuda).requires_grad_(True), d1.to(cuda).requires_grad_(True)
+    loss, terms, regs = TrainLossFn.apply(x0, x1, lungs.to(cuda), ems.to(cuda), cl.to(cuda), pl.to(cuda), cb.to(cuda),
+                                          pb.to(cuda), cw.to(cuda), pw.to(cuda))
+    (3.0 * loss).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    assert abs(float(terms[0] + terms[1] + 2 * terms[2] + terms[3]) - float(loss)) <= 1e-6 * abs(float(loss))
+    for k in (0, 1):
+        assert torch.allclose(regs[:, k].cpu(), regs_ref[k].detach(), rtol=1e-6, atol=1e-7)
+        got, ref = (x0, x1)[k].grad.cpu(), (a, b)[k].grad
+        tol = ref.abs().max() * 1e-5 + ref.abs() * 1e-4
+        assert bool(((got - ref).abs() <= tol).all()), (k, (got - ref).abs().max().item(), ref.abs().max().item())
+    # deterministic: a second evaluation gives the same bits
+    loss2, _, _ = TrainLossFn.apply(x0.detach(), x1.detach(), lungs.to(cuda), ems.to(cuda), cl.to(cuda), pl.to(cuda),
+                                    cb.to(cuda), pb.to(cuda), cw.to(cuda), pw.to(cuda))
+    assert torch.equal(loss2, loss.detach())
+
+
+def test_train_loss_rejects_bad_input(cuda, lib):
+    from dram_b200.backward import TrainLossFn
+
+    m = torch.rand(2, 1, 4, 4, 4, device=cuda)
+    mask = torch.ones(2, 8, 8, 8, dtype=torch.bool, device=cuda)
+    lab, band, w = torch.zeros(2, dtype=torch.int64), torch.zeros(2, 2), torch.ones(2)
+    with pytest.raises(ValueError, match="cle_bands"):
+        TrainLossFn.apply(m, m.clone(), mask, mask, lab, lab, torch.zeros(2, 3), band, w, w)
+    with pytest.raises(ValueError, match="masks"):
+        TrainLossFn.apply(m, m.clone(), mask[:1], mask[:1], lab, lab, band, band, w, w)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        TrainLossFn.apply(m, m.clone(), mask.cpu(), mask, lab, lab, band, band, w, w)
+
+
+@pytest.mark.parametrize("n", [4096, 1003, 3])
+def test_adam_kernel_matches_torch_adam(cuda, lib, n):
+    """K12 against torch.optim.Adam (models.py:685-698: lr only) on CPU over four steps with fresh gradients, one of
+    them with a changed learning rate: parameters within 1e-6 relative + 1e-7, moments within 1e-6 relative."""
+    from dram_b200.backward import FlatAdam
+
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    flat_p, flat_g = p0.to(cuda), torch.zeros(n, device=cuda)
+    adam = FlatAdam(flat_p, flat_g, lr=1e-3)
+    for it in range(4):
+        grad = torch.randn(n, generator=g) * (10.0 ** (it - 2))
+        grad[::7] = 0.0
+        if it == 2:
+            adam.decay_lr(0.95)
+            opt.param_groups[0]["lr"] *= 0.95
+        ref.grad = grad.clone()
+        opt.step()
+        flat_g.copy_(grad)
+        adam.step()
+    torch.cuda.synchronize()
+    st = opt.state[ref]
+    assert torch.allclose(flat_p.cpu(), ref.detach(), rtol=1e-6, atol=1e-7), (flat_p.cpu() - ref.detach()).abs().max().item()
+    assert torch.allclose(adam.exp_avg.cpu(), st["exp_avg"], rtol=1e-6, atol=1e-12)
+    assert torch.allclose(adam.exp_avg_sq.cpu(), st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
+    # grad_scale folds a division (gradient averaging) into the update
+    p1, p2 = p0.to(cuda), p0.to(cuda)
+    a1, a2 = FlatAdam(p1, flat_g, lr=1e-3), FlatAdam(p2, flat_g * 0.25, lr=1e-3)
+    a1.step(grad_scale=0.25)
+    a2.step()
+    assert torch.equal(p1, p2)

@@ -51,6 +51,18 @@ def test_argument_validation_without_gpu(lib):
     assert lib.dram_maxpool3d(None, None, 1, 8, 8, 8, 64, 0, None) == -1
     assert lib.dram_stem_expand(None, None, 1, 8, 8, 8, 7, None) == -1  # bad dtype code
     assert lib.dram_pool_workspace_bytes(2, 3) == 8 * 2 * 4
+    # K11 / K12 (training tail): null pointers, batch bound, step count from 1, alignment
+    assert lib.dram_train_loss_workspace_bytes(2) >= 2 * 8 * 8
+    assert lib.dram_train_loss_forward(*([None] * 10), 2, 8, 8, 8, 4, 4, 4, 0.7, 0.25, None, None, None) == -1
+    assert "null pointer" in _capi.last_error()
+    assert lib.dram_train_loss_forward(*([16] * 10), 65, 8, 8, 8, 4, 4, 4, 0.7, 0.25, 16, 16, None) == -1
+    assert "batch 65" in _capi.last_error()
+    assert lib.dram_train_loss_backward(*([16] * 7), None, 1, 8, 8, 8, 4, 4, 0, 16, 16, None) == -1
+    assert lib.dram_adam_step(None, None, None, None, 8, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert lib.dram_adam_step(16, 16, 16, 16, 8, 1e-4, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1
+    assert "counts from 1" in _capi.last_error()
+    assert lib.dram_adam_step(16, 16, 20, 16, 8, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert "aligned" in _capi.last_error()
 
 
 def test_ops_refuse_cpu_tensors(lib):

@@ -159,3 +159,92 @@ def test_train_step_updates_and_is_repeatable(cuda, lib):
     assert not torch.equal(model.layer1[0].conv1.weight.detach(), w0)
     for n, p in model.named_parameters():
         assert p.grad.data_ptr() == step.buckets.view(n).data_ptr(), n
+        off = step.buckets.slices[n][0]
+        assert p.data_ptr() == step.flat_param.data_ptr() + 4 * off, n  # parameters are views of the flat buffer
+    # K11's by-products: the four loss terms add up, the lobe-masked means are the reg_outs of med3d.py:387
+    last = step.last
+    total = float(last["loss_cle"] + last["loss_pse"] + 2.0 * last["mul_loss"] + last["seg_loss"])
+    assert abs(total - losses[-1]) <= 1e-5 * abs(losses[-1])
+    assert all(0.0 < float(r) < 1.0 for regs in last["reg_outs"] for r in regs)
+    # the kernels moved the weights behind autograd's back: the version counters say so, and an eval-mode engine
+    # built afterwards sees the trained weights through the usual state_dict
+    assert model.layer1[0].conv1.weight._version >= 4
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    assert torch.equal(sd["layer1.0.conv1.weight"], model.layer1[0].conv1.weight.detach())
+
+
+def test_native_loss_and_adam_equal_the_aten_step(cuda, lib):
+    """TrainStep's native tail (K11 loss, K9 writing into the flat gradient buffer, K12 Adam) against the same step with
+    the ATen loss, autograd's AccumulateGrad and torch.optim.Adam: same loss (1e-5), same gradients (the bf16 backward
+    pass amplifies fp32 rounding differences of the loss gradient a little: cosine >= 0.9999 over all parameters, every
+    convolution weight gradient within 1e-3 of its largest entry), and after one Adam step no weight differs by more
+    than 2 lr (Adam's first update is +-lr wherever the gradient is not tiny)."""
+    from dram_b200 import training
+
+    case, fix, model_a = _setup(cuda)
+    _, _, model_b = _setup(cuda)
+    lr = 1e-4
+    native = training.TrainStep(model_a, lr=lr)
+    aten = training.TrainStep(model_b, lr=lr, loss="aten", optimizer="torch")
+    batch = {k: case[k].to(cuda) for k in ("image", "lung_mask", "em_mask", "cls_label", "pse_label")}
+    args = (fix["cle_bands"].to(cuda), fix["pse_bands"].to(cuda), case["cle_weights"].to(cuda), case["pse_weights"].to(cuda))
+    la, lb = float(native.step(batch, *args)), float(aten.step(batch, *args))
+    torch.cuda.synchronize()
+    assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
+    ga, gb = native.buckets.flat, aten.buckets.flat
+    cos = float(torch.dot(ga, gb) / (ga.norm() * gb.norm()))
+    assert cos >= 0.9999, cos
+    for n, _ in model_a.named_parameters():
+        if n.endswith("conv1.weight") or n.endswith("conv2.weight"):
+            a, b = native.buckets.view(n), aten.buckets.view(n)
+            assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-12, n
+    diff_sum, count = 0.0, 0
+    for (n, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        d = (pa.detach() - pb.detach()).abs()
+        assert float(d.max()) <= 2.0 * lr * 1.01, n
+        diff_sum, count = diff_sum + float(d.sum()), count + d.numel()
+    assert diff_sum / count <= 0.1 * lr, diff_sum / count  # sign flips only where the gradient is rounding noise
+    for r_n, r_a in zip(native.last["reg_outs"], aten.last["reg_outs"]):
+        assert torch.allclose(r_n, r_a, rtol=1e-5, atol=1e-7)
+
+
+def test_lightning_training_step_surface(cuda, lib):
+    """`ScanRegLightningModule.training_step / validation_step` (models.py:530-600): the reference's result keys, the
+    golden loss of the reference's own shared_step(TRAIN) on the first call (class weights looked up per label,
+    models.py:546-551; bands from the ratio maps, models.py:477-493), a decreasing loss, and an inference
+    `predict_step` afterwards that runs on the trained weights."""
+    from argparse import Namespace
+
+    from dram_b200.models import ScanRegLightningModule
+    from oracle import training_oracle as T
+
+    case = T.train_case()
+    fix = torch.load(os.path.join(GOLDEN, "train_step_med3ddram18.pt"), weights_only=False)
+    module = ScanRegLightningModule(Namespace(model_arch="med3ddram18", lr=1e-4))
+    module.model.load_state_dict(case["sd"])
+    module = module.to(cuda)
+    module.cle_class_weights = {0: 2.0, 3: 1.0}   # = case["cle_weights"] for the labels [3, 0]
+    module.pse_class_weights = {1: 1.5, 2: 0.5}   # = case["pse_weights"] for the labels [1, 2]
+    batch = {k: case[k] for k in ("image", "lung_mask", "em_mask", "cls_label", "pse_label")}
+    batch["index"] = torch.arange(2).view(2, 1)
+    assert module.configure_optimizers() is None
+    outs = [module.training_step(batch, i) for i in range(3)]
+    for key in ("loss", "pred_cle_labels", "pred_pse_labels", "cle_labels", "pse_labels", "index",
+                "loss_cle", "loss_pse", "mul_loss", "seg_loss"):
+        assert key in outs[0], key
+    assert abs(float(outs[0]["loss"]) - fix["loss"]) <= 2e-2 * abs(fix["loss"]), (float(outs[0]["loss"]), fix["loss"])
+    assert float(outs[-1]["loss"]) < float(outs[0]["loss"])
+    assert outs[0]["pred_cle_labels"].dtype == torch.int64 and tuple(outs[0]["pred_cle_labels"].shape) == (2,)
+    lr0 = module.train_engine().opt.lr
+    module.on_train_epoch_end()
+    assert abs(module.train_engine().opt.lr - 0.95 * lr0) < 1e-12
+    val = module.validation_step(batch, 0)
+    assert set(val) == {"pred_cle_labels", "pred_pse_labels", "cle_labels", "pse_labels", "index"}
+    pred = module.predict_step({"image": case["image"], "lung_mask": case["lung_mask"], "ess_mask": case["em_mask"]}, 0)
+    assert torch.isfinite(pred["cle_precentages"]).all() and torch.isfinite(pred["cle_dense_outs"]).all()
+    # moving the model re-allocates its parameters: the step refuses to update buffers nobody reads
+    module.model.to(torch.device("cpu")).to(cuda)
+    with pytest.raises(RuntimeError, match="no longer live"):
+        module.train_engine().step({k: v.to(cuda) for k, v in batch.items() if k != "index"},
+                                   fix["cle_bands"].to(cuda), fix["pse_bands"].to(cuda),
+                                   case["cle_weights"].to(cuda), case["pse_weights"].to(cuda))

@@ -1,6 +1,5 @@
-"""Times one hybrid training step (conv fwd/dgrad/wgrad on the sm_100a kernels, glue on ATen; see training.py) of
-med3ddram (ResNet-34) — dev tool, NOT a bench.py number.
-    python tools/train_step_bench.py [size] [batch] [arch]
+"""Times one training step (see training.py) of med3ddram (ResNet-34) — dev tool, NOT a bench.py number.
+    python tools/train_step_bench.py [size] [batch] [arch] [loss: native|aten] [optimizer: native|torch]
 """
 import os
 import sys
@@ -15,13 +14,15 @@ from dram_b200 import med3d, training  # noqa: E402
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ARCH = sys.argv[3] if len(sys.argv) > 3 else "resnet34segreg"
+LOSS = sys.argv[4] if len(sys.argv) > 4 else "native"
+OPT = sys.argv[5] if len(sys.argv) > 5 else "native"
 dev = torch.device("cuda:0")
 
 
 def main():
     torch.manual_seed(0)
     model = getattr(med3d, ARCH)().to(dev).train()
-    step = training.TrainStep(model, lr=1e-5)
+    step = training.TrainStep(model, lr=1e-5, loss=LOSS, optimizer=OPT)
     g = torch.Generator().manual_seed(1)
     lung = torch.zeros((B, S, S, S), dtype=torch.bool)
     lung[:, S // 8: -S // 8, S // 6: -S // 6, S // 8: -S // 8] = True
@@ -43,7 +44,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(f"{ARCH} {S}^3 batch {B}: {ms:.2f} ms per training step (forward + loss + backward + Adam), "
+    print(f"{ARCH} {S}^3 batch {B} loss={LOSS} optimizer={OPT}: {ms:.2f} ms per training step (forward + loss + backward + Adam), "
           f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
     from torch.profiler import ProfilerActivity, profile
 
