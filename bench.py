@@ -401,6 +401,15 @@ def run_train_arm(args, out):
     barrier(world)
     e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
 
+    # one more step under the profiler (all ranks: the step holds collectives) to count this library's launches
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        one(batch)
+        torch.cuda.synchronize()
+    own = sum(e.count for e in prof.key_averages() if "dram::" in e.key)
+    total_kernels = sum(e.count for e in prof.key_averages()
+                        if e.device_type is not None and "DeviceType.CUDA" in str(e.device_type) and "Mem" not in e.key)
     train_flops = step.net.training_flops()  # fprop + dgrad + wgrad of every convolution; the stem has no dgrad
     peak, peak_src = measured_peaks()
     achieved = train_flops / (ms_per_step * 1e-3) / 1e12
@@ -428,7 +437,7 @@ def run_train_arm(args, out):
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "api": "training.TrainStep.step(batch) with the batch copied from pinned host memory "
                                               "every step and the loss read back"},
-        "gpu_launches": None,
+        "gpu_launches": own * args.steps, "launches_per_step": {"dram_b200": own, "all_kernels": total_kernels},
         "roofline": {"bound": "tensor", "kernel": "whole training step (conv fprop + dgrad + wgrad FLOPs over the step time)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_flops_per_step": train_flops},
