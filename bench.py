@@ -353,7 +353,7 @@ def run_train_arm(args, out):
     torch.manual_seed(0)  # identical initial weights on every rank
     factory = {"med3ddram": med3d.resnet34segreg, "med3ddram18": med3d.resnet18segreg, "med3ddram50": med3d.resnet50segreg}
     model = factory[args.arch]().to(device).train()
-    step = training.TrainStep(model, lr=1e-5, sync_bn=world > 1)
+    step = training.TrainStep(model, lr=1e-5, sync_bn=args.sync_bn if world > 1 else False)
     hu, lungs, ess = make_volumes(B, dims, device, seed=rank)
     v = hu.float().clamp(-1150.0, -300.0)
     v = (v + 1150.0) / 850.0
@@ -410,6 +410,8 @@ def run_train_arm(args, out):
     own = sum(e.count for e in prof.key_averages() if "dram::" in e.key)
     total_kernels = sum(e.count for e in prof.key_averages()
                         if e.device_type is not None and "DeviceType.CUDA" in str(e.device_type) and "Mem" not in e.key)
+    if step.peer is not None:
+        step.peer.check()
     train_flops = step.net.training_flops()  # fprop + dgrad + wgrad of every convolution; the stem has no dgrad
     peak, peak_src = measured_peaks()
     achieved = train_flops / (ms_per_step * 1e-3) / 1e12
@@ -428,7 +430,7 @@ def run_train_arm(args, out):
         "config": {"workload": f"{ARCH_NAMES[args.arch]} training step, synthetic {dims[0]}x{dims[1]}x{dims[2]} CT volumes, "
                                f"batch {B} per GPU, random-init weights",
                    "global_batch": world * B, "parallelism": f"data-parallel x{world}, bucketed NCCL gradient all-reduce"
-                                                             f"{' + SyncBatchNorm' if world > 1 else ''}",
+                                                             f"{' + SyncBatchNorm (' + ('K10x peer-memory exchange' if args.sync_bn == 'peer' else 'NCCL') + ')' if world > 1 else ''}",
                    "glue": "native: conv fwd/dgrad/wgrad, BatchNorm(+ReLU,+residual), max-pool, up-sampling, heads; "
                            "weight re-packing, loss + gradient (K11), Adam (K12); ATen: shortcut-A slicing/padding, "
                            "stem weight-gradient re-layout, per-channel dtype casts",
@@ -456,6 +458,8 @@ def main():
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", default="peer", choices=["peer", "nccl"],
+                    help="--mode train on >1 GPU: SyncBatchNorm statistics over the peer-memory kernel (K10x) or NCCL")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer (default): BASELINE.json's headline metric; train: one data-parallel training step "
                          "(BASELINE config 5; additional line, not the headline)")

@@ -17,6 +17,7 @@ DRAM_DTYPE_BF16 = 0
 DRAM_DTYPE_F16 = 1
 CONV_ALGO = {"auto": 0, "tiles": 1, "planes": 2}
 LOSS_COEF_HEAD = 16  # DRAM_LOSS_COEF_HEAD
+PEER_HANDLE_BYTES = 64  # DRAM_PEER_HANDLE_BYTES
 
 
 class ConvDesc(C.Structure):
@@ -94,6 +95,12 @@ SIGNATURES = {
     "dram_heads_workspace_bytes": (_i64, []),
     "dram_heads_sigmoid_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dram_heads_sigmoid_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "dram_peer_exchange_bytes": (_i64, []),
+    "dram_peer_alloc": (C.c_int, [_i64, C.POINTER(_vp), _vp]),
+    "dram_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "dram_peer_close": (C.c_int, [_vp]),
+    "dram_peer_free": (C.c_int, [_vp]),
+    "dram_peer_allreduce_f64": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, C.c_uint64, _vp, _vp]),
     "dram_train_loss_workspace_bytes": (_i64, [_i32]),
     "dram_train_loss_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
                                           _i32, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),

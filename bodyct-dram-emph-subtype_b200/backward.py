@@ -372,6 +372,70 @@ class FlatAdam:
         self.exp_avg_sq.copy_(state["exp_avg_sq"])
 
 
+class PeerExchange:
+    """K10x: the SyncBatchNorm statistics exchange (train.py:101) as one kernel over NVLink peer memory instead of a
+    library collective (`dram_peer_allreduce_f64`, peer_exchange.cu).  One process per GPU on one node, at most 8 ranks.
+    Construction is collective over `group`: every rank allocates its exchange buffer, the CUDA IPC handles travel
+    through `all_gather_object`, every rank maps every peer's buffer, then a barrier.  `all_reduce(sums)` must be called
+    in the same order on every rank (it is: the BatchNorm layers run in the same order everywhere)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        lib = _capi.load()
+        self._lib, self.group = lib, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError(f"PeerExchange: {self.world} ranks; the peer-memory exchange covers one node (<= 8 GPUs)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        own, handle = C.c_void_p(), (C.c_ubyte * _capi.PEER_HANDLE_BYTES)()
+        check(lib.dram_peer_alloc(lib.dram_peer_exchange_bytes(), C.byref(own), handle), "dram_peer_alloc")
+        self._own, self._opened = own.value, []
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self._ptrs = (C.c_void_p * 8)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self._ptrs[r] = self._own
+                continue
+            ptr, buf = C.c_void_p(), (C.c_ubyte * _capi.PEER_HANDLE_BYTES).from_buffer_copy(h)
+            check(lib.dram_peer_open(buf, C.byref(ptr)), f"dram_peer_open (rank {r})")
+            self._ptrs[r] = ptr.value
+            self._opened.append(ptr.value)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.seq = 0
+        dist.barrier(group)  # every buffer is zeroed and mapped everywhere before the first flag is raised
+
+    def all_reduce(self, sums, out=None):
+        """fp64 [n <= 4096] -> the sum over the ranks, the same bits on every rank (`out` may be `sums`)."""
+        _need(sums, torch.float64, "PeerExchange sums", 1)
+        out = torch.empty_like(sums) if out is None else _need(out, torch.float64, "PeerExchange out", 1)
+        self.seq += 1
+        check(self._lib.dram_peer_allreduce_f64(_p(sums), _p(out), sums.numel(), self._ptrs, self.world, self.rank, self.seq,
+                                                _p(self.status), _stream()), "dram_peer_allreduce_f64")
+        return out
+
+    def check(self):
+        """Raises if an exchange gave up waiting for a peer (synchronises the device; call between steps)."""
+        code = int(self.status.item())
+        if code:
+            raise RuntimeError(f"PeerExchange: rank {self.rank} waited > 60 s for rank {code - 1} at some exchange <= {self.seq}")
+
+    def close(self):
+        """Collective: every rank unmaps its peers' buffers, then (after a barrier — CUDA IPC wants the importers gone
+        before the exporter frees) releases its own."""
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.device)
+        for ptr in self._opened:
+            self._lib.dram_peer_close(C.c_void_p(ptr))
+        self._opened = []
+        dist.barrier(self.group)
+        if self._own:
+            self._lib.dram_peer_free(C.c_void_p(self._own))
+            self._own = None
+
+
 _BN_WS = {}
 
 
@@ -387,8 +451,8 @@ def _bn_workspace(c, device):
 class BatchNormTrainFn(torch.autograd.Function):
     """y = act(batch_norm_train(x) (+ res)) on NDHWC 16-bit rows (K10, `dram_bn_*`): batch statistics, running-stat
     update (in place on the given buffers), ReLU and residual add fused; backward returns dx, dgamma, dbeta, dres.
-    `group` (a torch.distributed group, or True for the default group) all-reduces the per-channel sums between the
-    two phases of both reductions: SyncBatchNorm as train.py:101 asks for."""
+    `group` (a torch.distributed group, True for the default group, or a `PeerExchange`) all-reduces the per-channel
+    sums between the two phases of both reductions: SyncBatchNorm as train.py:101 asks for."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, res, relu, eps, momentum, group):
@@ -408,9 +472,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         count = float(m)
         world = _sync_world(group)
         if world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(sums, group=None if group is True else group)
+            _sync_all_reduce(sums, group)
             count *= world
         scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=x.device) for _ in range(4))
         check(lib.dram_bn_finalize(_p(sums), count, _p(g32), _p(b32), eps, momentum, _p(running_mean), _p(running_var),
@@ -436,10 +498,7 @@ class BatchNormTrainFn(torch.autograd.Function):
         count = float(m)
         world = _sync_world(group)
         if world > 1:
-            import torch.distributed as dist
-
-            sums = sums.clone()
-            dist.all_reduce(sums, group=None if group is True else group)
+            sums = _sync_all_reduce(sums, group, in_place=False)
             count *= world
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res and ctx.needs_input_grad[5] else None
@@ -460,9 +519,23 @@ def channel_sums(x):
     return sums[:c].float()
 
 
+def _sync_all_reduce(sums, group, in_place=True):
+    """The statistics exchange of SyncBatchNorm: K10x over peer memory when `group` is a PeerExchange, else NCCL."""
+    if isinstance(group, PeerExchange):
+        return group.all_reduce(sums, out=sums if in_place else None)
+    import torch.distributed as dist
+
+    if not in_place:
+        sums = sums.clone()
+    dist.all_reduce(sums, group=None if group is True else group)
+    return sums
+
+
 def _sync_world(group):
     if group is None or group is False:
         return 1
+    if isinstance(group, PeerExchange):
+        return group.world
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):

@@ -34,7 +34,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .backward import (BatchNormTrainFn, Conv3dDgradPlan, Conv3dWgradPlan, FlatAdam, GradBuckets, HeadsSigmoidFn, MaxPool3dFn,
-                       TrainLossFn, Upsample2xFn, channel_sums, pack_weight_into)
+                       PeerExchange, TrainLossFn, Upsample2xFn, channel_sums, pack_weight_into)
 from .engine import LAYER_CFG
 
 ACT = torch.bfloat16  # activations and their gradients
@@ -351,7 +351,9 @@ class TrainStep:
     view into the parameter buffer, so `state_dict()` / `load_state_dict()` keep working.  K9 writes each convolution's
     weight gradient straight into its slice; the remaining gradients arrive through autograd's AccumulateGrad.  A
     bucket's (asynchronous, NCCL) all-reduce is launched the moment its last gradient lands, so the exchange overlaps
-    the rest of the backward pass.  `sync_bn=True` all-reduces the BatchNorm statistics as well (train.py:101).
+    the rest of the backward pass.  `sync_bn=True` (or "nccl") all-reduces the BatchNorm statistics as well
+    (train.py:101) with NCCL; `sync_bn="peer"` does that exchange with K10x, one kernel over NVLink peer memory per
+    BatchNorm pass (`backward.PeerExchange`; one node, <= 8 ranks; `self.peer.check()` reports a lost peer).
 
     loss = "native" (K11, `TrainLossFn`) | "aten" (`training_loss`); optimizer = "native" (K12, `FlatAdam`) | "torch"
     (torch.optim.Adam).  `last` holds the loss terms and the lobe-masked means of the last step (device tensors).
@@ -360,7 +362,14 @@ class TrainStep:
     def __init__(self, model, lr=1e-4, bucket_bytes=64 << 20, group=None, sync_bn=False, loss="native", optimizer="native"):
         if loss not in ("native", "aten") or optimizer not in ("native", "torch"):
             raise ValueError(f"TrainStep: loss={loss!r} / optimizer={optimizer!r} (native|aten, native|torch)")
-        self.net = TrainableMed3D(model, sync_bn=(group if group is not None else True) if sync_bn else None)
+        if sync_bn not in (False, True, None, "nccl", "peer"):
+            raise ValueError(f"TrainStep: sync_bn={sync_bn!r} (False | True/'nccl' | 'peer')")
+        self.peer = PeerExchange(group) if sync_bn == "peer" else None  # collective: every rank builds it here
+        if self.peer is not None:
+            bn_group = self.peer
+        else:
+            bn_group = (group if group is not None else True) if sync_bn else None
+        self.net = TrainableMed3D(model, sync_bn=bn_group)
         self.params = [(n, p) for n, p in model.named_parameters()]
         dev = self.params[0][1].device
         self.buckets = GradBuckets([(n, tuple(p.shape)) for n, p in reversed(self.params)], dev, bucket_bytes)

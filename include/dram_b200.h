@@ -352,6 +352,32 @@ int dram_heads_sigmoid_backward(const void *x, const float *w, const float *s0, 
                                 const float *g1, void *dx, float *dw, float *db, void *workspace, int64_t m,
                                 int32_t dtype, void *stream);
 
+/* ---- K10x: SyncBatchNorm's statistics exchange over NVLink peer memory (train.py:101 `sync_batchnorm=True`) ---- */
+/*
+ * One process per GPU on one node (<= 8 ranks).  Start-up, once per rank:
+ *   dram_peer_alloc(dram_peer_exchange_bytes(), &own, handle)   cudaMalloc + zero + CUDA IPC handle (64 bytes)
+ *   -- exchange the handles between the ranks (e.g. torch.distributed.all_gather_object) --
+ *   dram_peer_open(handle_of_rank_r, &peer_r) for every other rank; then a barrier.
+ * Per exchange (the all-reduce between dram_bn_stats / dram_bn_backward_reduce and the following pass):
+ *   dram_peer_allreduce_f64(in, out, n, peers, world, rank, seq, status, stream)
+ *     in/out : fp64 [n] on this rank (n = 2*c <= 4096; may alias), out = sum over the ranks in rank order — every rank
+ *              gets the same bits;
+ *     peers  : host array of `world` device pointers, peers[rank] = own buffer;
+ *     seq    : 1, 2, 3, ... the same sequence on every rank (one per exchange);
+ *     status : device int32, 0 = healthy; set non-zero when a peer did not answer within ~60 s, after which every
+ *              call copies in -> out without waiting (check it on the host at a convenient point).
+ * One kernel pushes the sums into every peer's buffer, raises release flags, waits for the peers' flags and adds.
+ * dram_peer_close / dram_peer_free undo open / alloc.  These are the only entry points that own device memory.
+ */
+#define DRAM_PEER_HANDLE_BYTES 64
+int64_t dram_peer_exchange_bytes(void);
+int dram_peer_alloc(int64_t bytes, void **ptr, void *handle64);
+int dram_peer_open(const void *handle64, void **ptr);
+int dram_peer_close(void *ptr);
+int dram_peer_free(void *ptr);
+int dram_peer_allreduce_f64(const double *in, double *out, int32_t n, void *const *peers, int32_t world, int32_t rank,
+                            uint64_t seq, int32_t *status, void *stream);
+
 /* ---- K11: the training loss and its gradient ---- */
 /*
  * What ScanRegLightningModule.shared_step(TRAIN) computes from the two sigmoid maps (models.py:547-565) and what

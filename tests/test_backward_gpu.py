@@ -423,3 +423,56 @@ def test_adam_kernel_matches_torch_adam(cuda, lib, n):
     a1.step(grad_scale=0.25)
     a2.step()
     assert torch.equal(p1, p2)
+
+
+def test_peer_allreduce_protocol_two_ranks_on_one_device(cuda, lib):
+    """K10x's protocol (push rows, release flags, acquire-wait, rank-order sum, four rotating slots, sequence numbers)
+    exercised without a second process: two exchange buffers on one GPU play rank 0 and rank 1, their kernels run on
+    two streams and wait for each other.  40 consecutive exchanges of varying length, in place and out of place; both
+    'ranks' must end with exactly a + b (two-term sums commute, so the bits are the plain fp64 sum).  The real
+    two-process run over CUDA IPC is tools/train_ddp_smoke.py (profiles/train_ddp_n2_*.log)."""
+    import ctypes as C
+
+    from dram_b200 import _capi
+
+    nbytes = lib.dram_peer_exchange_bytes()
+    bufs, handle = [], (C.c_ubyte * _capi.PEER_HANDLE_BYTES)()
+    for _ in range(2):
+        ptr = C.c_void_p()
+        _capi.check(lib.dram_peer_alloc(nbytes, C.byref(ptr), handle), "dram_peer_alloc")
+        bufs.append(ptr.value)
+    peers = (C.c_void_p * 8)()
+    peers[0], peers[1] = bufs
+    status = [torch.zeros(1, dtype=torch.int32, device=cuda) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(2)]
+    g = torch.Generator().manual_seed(5)
+    try:
+        for seq in range(1, 41):
+            n = [128, 256, 4096, 2, 1026][seq % 5]
+            a, b = torch.randn(n, generator=g, dtype=torch.float64), torch.randn(n, generator=g, dtype=torch.float64)
+            ins = [a.to(cuda), b.to(cuda)]
+            outs = ins if seq % 2 else [torch.empty_like(t) for t in ins]
+            torch.cuda.synchronize()
+            for r in (1, 0) if seq % 3 == 0 else (0, 1):  # either 'rank' may arrive first
+                with torch.cuda.stream(streams[r]):
+                    _capi.check(lib.dram_peer_allreduce_f64(ins[r].data_ptr(), outs[r].data_ptr(), n, peers, 2, r, seq,
+                                                            status[r].data_ptr(), streams[r].cuda_stream),
+                                "dram_peer_allreduce_f64")
+            torch.cuda.synchronize()
+            assert int(status[0]) == 0 and int(status[1]) == 0, seq
+            assert torch.equal(outs[0].cpu(), a + b) and torch.equal(outs[1].cpu(), a + b), seq
+        # a single rank is the identity
+        x = torch.randn(130, dtype=torch.float64, device=cuda)
+        y = torch.empty_like(x)
+        solo = (C.c_void_p * 8)()
+        solo[0] = bufs[0]
+        _capi.check(lib.dram_peer_allreduce_f64(x.data_ptr(), y.data_ptr(), 130, solo, 1, 0, 41, status[0].data_ptr(), None),
+                    "dram_peer_allreduce_f64")
+        torch.cuda.synchronize()
+        assert torch.equal(x, y)
+        assert lib.dram_peer_allreduce_f64(x.data_ptr(), y.data_ptr(), 5000, solo, 1, 0, 42, status[0].data_ptr(), None) == -1
+        assert lib.dram_peer_allreduce_f64(x.data_ptr(), y.data_ptr(), 130, solo, 9, 0, 42, status[0].data_ptr(), None) == -1
+    finally:
+        torch.cuda.synchronize()
+        for ptr in bufs:
+            lib.dram_peer_free(C.c_void_p(ptr))

@@ -58,6 +58,9 @@ def test_argument_validation_without_gpu(lib):
     assert lib.dram_train_loss_forward(*([16] * 10), 65, 8, 8, 8, 4, 4, 4, 0.7, 0.25, 16, 16, None) == -1
     assert "batch 65" in _capi.last_error()
     assert lib.dram_train_loss_backward(*([16] * 7), None, 1, 8, 8, 8, 4, 4, 0, 16, 16, None) == -1
+    assert lib.dram_peer_exchange_bytes() >= 4 * 8 * 4096 * 8
+    assert lib.dram_peer_allreduce_f64(None, None, 8, None, 2, 0, 1, None, None) == -1
+    assert lib.dram_peer_open(None, None) == -1 and lib.dram_peer_close(None) == -1 and lib.dram_peer_free(None) == -1
     assert lib.dram_adam_step(None, None, None, None, 8, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
     assert lib.dram_adam_step(16, 16, 16, 16, 8, 1e-4, 0.9, 0.999, 1e-8, 0, 1.0, None) == -1
     assert "counts from 1" in _capi.last_error()
