@@ -412,6 +412,16 @@ def run_train_arm(args, out):
                         if e.device_type is not None and "DeviceType.CUDA" in str(e.device_type) and "Mem" not in e.key)
     if step.peer is not None:
         step.peer.check()
+    ranks_identical = None
+    if world > 1:  # data-parallel replicas must hold the same weights and running statistics, to the bit
+        import torch.distributed as dist
+
+        flat = torch.cat([p.detach().reshape(-1).double() for p in model.parameters()] +
+                         [b.detach().reshape(-1).double() for b in model.buffers()])
+        digest = torch.stack([flat.sum(), flat.abs().sum()])
+        digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        ranks_identical = all(bool(torch.equal(digests[0], d)) for d in digests)
     train_flops = step.net.training_flops()  # fprop + dgrad + wgrad of every convolution; the stem has no dgrad
     peak, peak_src = measured_peaks()
     achieved = train_flops / (ms_per_step * 1e-3) / 1e12
@@ -435,7 +445,7 @@ def run_train_arm(args, out):
                            "weight re-packing, loss + gradient (K11), Adam (K12); ATen: shortcut-A slicing/padding, "
                            "stem weight-gradient re-layout, per-channel dtype casts",
                    "l2": "activations per step (> 10 GB) exceed the 126 MB L2; no explicit flush"},
-        "clocks": clocks, "loss": float(loss),
+        "clocks": clocks, "loss": float(loss), "ranks_identical": ranks_identical,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "api": "training.TrainStep.step(batch) with the batch copied from pinned host memory "
                                               "every step and the loss read back"},
