@@ -455,7 +455,9 @@ class BatchNormTrainFn(torch.autograd.Function):
     sums between the two phases of both reductions: SyncBatchNorm as train.py:101 asks for."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, res, relu, eps, momentum, group):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, res, relu, eps, momentum, group, sink=None):
+        """sink: None, or (fp32 view [2c] of a flat gradient buffer laid out [dbeta | dgamma], callback): backward then
+        writes both parameter gradients there with one copy and calls the callback instead of returning them."""
         lib = _capi.load()
         _need16(x, "bn_train x")
         c = x.shape[-1]
@@ -481,20 +483,26 @@ class BatchNormTrainFn(torch.autograd.Function):
         check(lib.dram_bn_apply(_p(x), _p(scale), _p(shift), _p(res), 1 if relu else 0, _p(out), m, c, dt, _stream()),
               "dram_bn_apply")
         ctx.save_for_backward(x, out if relu else None, mean, rstd, g32)
-        ctx.meta = (m, c, dt, group, res is not None)
+        ctx.meta = (m, c, dt, group, res is not None, sink)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         lib = _capi.load()
         x, y, mean, rstd, g32 = ctx.saved_tensors
-        m, c, dt, group, has_res = ctx.meta
+        m, c, dt, group, has_res, sink = ctx.meta
         dy = dy.contiguous()
         ws = _bn_workspace(c, x.device)
         sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
         check(lib.dram_bn_backward_reduce(_p(dy), _p(x), _p(y), _p(mean), _p(rstd), m, c, dt, _p(sums), _p(ws), _stream()),
               "dram_bn_backward_reduce")
-        dbeta, dgamma = sums[:c].float(), sums[c:].float()  # local sums: the gradient exchange averages them later
+        # local sums (the gradient exchange averages them later): {sum dz, sum dz*xhat} = {dbeta, dgamma}
+        if sink is not None:
+            sink[0].copy_(sums)
+            dbeta = dgamma = None
+        else:
+            local = sums.float()
+            dbeta, dgamma = local[:c], local[c:]
         count = float(m)
         world = _sync_world(group)
         if world > 1:
@@ -504,7 +512,9 @@ class BatchNormTrainFn(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res and ctx.needs_input_grad[5] else None
         check(lib.dram_bn_backward_apply(_p(dy), _p(x), _p(y), _p(mean), _p(rstd), _p(g32), _p(sums), count, _p(dx), _p(dres),
                                          m, c, dt, _stream()), "dram_bn_backward_apply")
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+        if sink is not None:
+            sink[1]()
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
 def channel_sums(x):

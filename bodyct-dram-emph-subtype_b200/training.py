@@ -187,6 +187,9 @@ class TrainableMed3D:
         self.model = model
         self.layers = {}
         self.glue, self.sync_bn = glue, sync_bn
+        self.bn_sinks = {}  # id(BatchNorm3d) -> (flat gradient view [dbeta | dgamma], callback); set by TrainStep
+        self._counters = [m.num_batches_tracked for m in model.modules()
+                          if isinstance(m, torch.nn.BatchNorm3d) and m.num_batches_tracked is not None]
 
     def training_flops(self):
         """Algorithmic FLOPs of one training step of the last forward: fprop + dgrad + wgrad of every convolution
@@ -208,11 +211,9 @@ class TrainableMed3D:
 
     def _bn(self, bn, x, relu=True, res=None):
         """relu(bn(x) (+ res)) in train mode."""
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
         if self.glue == "native":
             return BatchNormTrainFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, res, relu, bn.eps,
-                                          BN_MOMENTUM, self.sync_bn)
+                                          BN_MOMENTUM, self.sync_bn, self.bn_sinks.get(id(bn)))
         y = F.batch_norm(_ncdhw(x), bn.running_mean, bn.running_var, bn.weight, bn.bias, True, BN_MOMENTUM, bn.eps)
         y = _ndhwc(y)
         if res is not None:
@@ -251,6 +252,8 @@ class TrainableMed3D:
         `with_regs=False` skips the lobe-masked means (K11 computes them together with the loss) and returns None."""
         m = self.model
         B = image.shape[0]
+        if self._counters:  # every BatchNorm of the network runs exactly once per forward: one launch for all counters
+            torch._foreach_add_(self._counters, 1)
         with torch.backends.cudnn.flags(enabled=False):
             c1 = StemFn.apply(self._layer("conv1", m.conv1), m.conv1.weight, image.float().contiguous())
             x = self._bn(m.bn1, c1)
@@ -379,6 +382,15 @@ class TrainStep:
         # the two 1x1x1 heads (HeadsSigmoidFn)
         conv_weights = {name + ".weight": conv for name, conv in model.named_modules()
                         if isinstance(conv, torch.nn.Conv3d) and name != "conv1" and not name.startswith("fcs.")}
+        # BatchNorm: bias and weight are neighbours in the flat layout (reverse registration order), and K10's backward
+        # reduction yields [dbeta | dgamma] in one vector: one copy fills both gradients
+        bn_pairs = {}
+        for name, mod in model.named_modules():
+            if isinstance(mod, torch.nn.BatchNorm3d) and mod.weight is not None and mod.bias is not None:
+                ob, nb, _ = self.buckets.slices[name + ".bias"]
+                ow, nw, _ = self.buckets.slices[name + ".weight"]
+                if ob + nb == ow and nb == nw:
+                    bn_pairs[name + ".bias"] = bn_pairs[name + ".weight"] = (mod, ob, nb + nw)
         for n, p in self.params:
             off, numel, shape = self.buckets.slices[n]
             view = self.flat_param[off:off + numel].view(shape)
@@ -390,6 +402,11 @@ class TrainStep:
             conv = conv_weights.get(n)
             if conv is not None:
                 self.net._layer(n[:-len(".weight")], conv).grad_sink = (p.grad, self._make_ready(b))
+            elif n in bn_pairs:
+                mod, start, length = bn_pairs[n]
+                if n.endswith(".weight"):  # registered once per pair; the callback counts both parameters down
+                    pair = (self.buckets.bucket_of[n[:-len("weight")] + "bias"], b)
+                    self.net.bn_sinks[id(mod)] = (self.buckets.flat[start:start + length], self._make_ready_many(pair))
             else:
                 p.register_post_accumulate_grad_hook(self._make_hook(n, b))
         self._pending = list(self._bucket_size)
@@ -410,6 +427,12 @@ class TrainStep:
 
     def _make_ready(self, bucket):
         return lambda: self._grad_ready(bucket)
+
+    def _make_ready_many(self, buckets):
+        def ready():
+            for b in buckets:
+                self._grad_ready(b)
+        return ready
 
     def _make_hook(self, name, bucket):
         def hook(param):
