@@ -539,10 +539,12 @@ def main():
     h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del probe_dst
 
+    copy_streams = int(os.environ.get("DRAM_B200_COPY_STREAMS", "4"))  # DevicePrefetcher's default; 1 = single DMA stream (A/B)
+
     def e2e_pass(n_steps):
         # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's
         # side stream, overlapping the previous step's kernels) and reads its scores back before the next
-        for i, dev_batch in enumerate(DevicePrefetcher((host for _ in range(n_steps)), device)):
+        for i, dev_batch in enumerate(DevicePrefetcher((host for _ in range(n_steps)), device, copy_streams=copy_streams)):
             p = module.predict_step(dev_batch, i)
             res_host[0].copy_(p["cle_precentages"], non_blocking=True)
             res_host[1].copy_(p["pse_precentages"], non_blocking=True)
@@ -562,9 +564,10 @@ def main():
     e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": e2e_ms,
-           "h2d_gbs_idle_probe": h2d_gbs,
+           "h2d_gbs_idle_probe": h2d_gbs, "copy_streams": copy_streams,
            "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> "
-                  "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered)"}
+                  "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered, 16 MB chunks over "
+                  "the copy streams)"}
 
     # ---- roofline of the dominant kernel (conv3d_umma_kernel): per-launch CUDA events ----------
     conv_steps = [s for s in eng.steps if s.flops > 0]

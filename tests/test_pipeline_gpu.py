@@ -137,18 +137,21 @@ def test_processor_end_to_end(cuda, lib, tmp_path):
     assert os.path.isfile(out_dir / "araseptal-emphysema-score.json") and os.path.isfile(out_dir / "results.json")
 
 
-def test_device_prefetcher_delivers_every_batch_intact(cuda, lib):
-    """The double-buffered host->device staging of the predict loop: contents, order, pass-through keys."""
+@pytest.mark.parametrize("shape,streams", [((2, 8, 16, 16), 4), ((2, 67, 250, 256), 4), ((2, 67, 250, 256), 1)])
+def test_device_prefetcher_delivers_every_batch_intact(cuda, lib, shape, streams):
+    """The double-buffered host->device staging of the predict loop: contents, order, pass-through keys — for small
+    tensors (one copy each) and for tensors above the chunk size (34 MB image cut into 3 ragged chunks spread over the
+    copy streams; the mask stays one piece)."""
     from dram_b200.models import DevicePrefetcher
 
     g = torch.Generator().manual_seed(5)
     batches = []
     for i in range(5):
-        batches.append({"image": torch.randn(2, 8, 16, 16, generator=g).pin_memory(),
-                        "lung_mask": (torch.rand(2, 8, 16, 16, generator=g) > 0.5).pin_memory(),
+        batches.append({"image": torch.randn(shape, generator=g).pin_memory(),
+                        "lung_mask": (torch.rand(shape, generator=g) > 0.5).pin_memory(),
                         "uid": [f"scan{i}a", f"scan{i}b"]})
     seen = 0
-    for i, dev_batch in enumerate(DevicePrefetcher(iter(batches), cuda)):
+    for i, dev_batch in enumerate(DevicePrefetcher(iter(batches), cuda, copy_streams=streams)):
         assert dev_batch["image"].is_cuda and dev_batch["lung_mask"].dtype == torch.bool
         # a long-running consumer kernel: the set must not be overwritten while it is still being read
         acc = dev_batch["image"].clone()
