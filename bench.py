@@ -539,7 +539,7 @@ def main():
     h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del probe_dst
 
-    copy_streams = int(os.environ.get("DRAM_B200_COPY_STREAMS", "4"))  # DevicePrefetcher's default; 1 = single DMA stream (A/B)
+    copy_streams = int(os.environ.get("DRAM_B200_COPY_STREAMS", "1"))  # DevicePrefetcher's default; > 1 = chunked over several DMA streams (A/B)
 
     def e2e_pass(n_steps):
         # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's
@@ -566,8 +566,7 @@ def main():
            "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": e2e_ms,
            "h2d_gbs_idle_probe": h2d_gbs, "copy_streams": copy_streams,
            "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> "
-                  "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered, 16 MB chunks over "
-                  "the copy streams)"}
+                  "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered)"}
 
     # ---- roofline of the dominant kernel (conv3d_umma_kernel): per-launch CUDA events ----------
     conv_steps = [s for s in eng.steps if s.flops > 0]

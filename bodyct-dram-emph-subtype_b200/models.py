@@ -133,9 +133,11 @@ class DevicePrefetcher:
     i.  Two device buffer sets are reused in turn; a set is overwritten only after the compute stream has
     passed the point where the caller asked for the following batch.  Non-tensor entries pass through.
 
-    Large tensors are cut into chunks that travel on `copy_streams` streams at once: under a step that keeps
-    the L2 busy a single DMA stream reaches a third of the idle host->device rate (measured: 13-17 GB/s
-    against 47-50 idle, bench.py `e2e`), and several copy engines in flight hide that latency.
+    With `copy_streams` > 1 large tensors are cut into 16 MB chunks that travel on several streams at once.
+    Measured A/B on one box (ResNet-34, 256^3, batch 4; gpurun_out/bench_b4_cs{1,4}_r1o.json): one stream 23.7 ms
+    per step end to end, four streams 24.5 ms — more DMA engines in flight take a little from the kernels and the
+    copy was already hidden — so one stream is the default; the switch is kept for hosts where a single DMA stream
+    cannot keep up (one box of this round showed 9 GB/s under load against 47 GB/s idle).
 
         for batch in DevicePrefetcher(loader, device):
             pred = module.predict_step(batch, i)
@@ -143,7 +145,7 @@ class DevicePrefetcher:
 
     CHUNK_BYTES = 16 << 20
 
-    def __init__(self, loader, device, copy_streams=4):
+    def __init__(self, loader, device, copy_streams=1):
         self.loader, self.device = loader, torch.device(device)
         self.copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(copy_streams)))]
         self.copy_stream = self.copy_streams[0]
