@@ -315,8 +315,16 @@ class ScanRegLightningModule(_ScanModule):
 
             if self.model.head_kind != "reg":
                 raise RuntimeError("training_step needs a *dram (regression) architecture (train.py:72)")
+            import os
+
             multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-            eng = training.TrainStep(self.model.train(), lr=float(getattr(self.args, "lr", 1e-4)), sync_bn=multi)
+            sync_bn = False
+            if multi:
+                # one node with all ranks local (torchrun exports LOCAL_WORLD_SIZE): the statistics travel over NVLink
+                # peer memory (K10x); across nodes NCCL carries them
+                local = int(os.environ.get("LOCAL_WORLD_SIZE", "0"))
+                sync_bn = "peer" if local == dist.get_world_size() <= 8 else "nccl"
+            eng = training.TrainStep(self.model.train(), lr=float(getattr(self.args, "lr", 1e-4)), sync_bn=sync_bn)
             object.__setattr__(self, "_train_engine", eng)
         return eng
 

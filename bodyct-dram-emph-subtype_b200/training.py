@@ -458,7 +458,7 @@ class TrainStep:
 
     def step(self, batch, cle_bands, pse_bands, cle_weights, pse_weights):
         last_name, last_param = self.params[-1]
-        if last_param.data_ptr() != self.flat_param.data_ptr() or last_param.grad is None:
+        if last_param.data_ptr() != self.flat_param.data_ptr():
             raise RuntimeError("TrainStep: the network's parameters no longer live in this step's flat buffers (the model "
                                "was moved or re-typed after TrainStep was built); build a new TrainStep")
         self.zero_grad()

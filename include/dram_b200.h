@@ -10,7 +10,9 @@
  * Conventions
  *   - every pointer is a raw DEVICE pointer owned by the caller unless the
  *     name says host; nothing here allocates device memory, synchronises the
- *     device or changes the current device;
+ *     device or changes the current device (one exception: the
+ *     dram_peer_alloc/open/close/free quartet owns the CUDA-IPC exchange
+ *     buffers of the SyncBatchNorm kernel);
  *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
  *   - activations are NDHWC bf16 ("channels-last 3-D"), dense maps and
  *     scores are fp32 NCDHW exactly as the reference returns them;
@@ -35,7 +37,7 @@ extern "C" {
 #define DRAM_E_LAUNCH (-3)  /* CUDA launch / runtime error                  */
 #define DRAM_E_DRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
-#define DRAM_ABI_VERSION 3
+#define DRAM_ABI_VERSION 4
 
 /* 16-bit storage type of activations and packed weights (same layout, same tensor-core rate). */
 #define DRAM_DTYPE_BF16 0

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_capi.SIGNATURES), (declared ^ set(_capi.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/dram_b200.h but not exported"
-    assert lib.dram_version() == 3
+    assert lib.dram_version() == 4
 
 
 def test_argument_validation_without_gpu(lib):
