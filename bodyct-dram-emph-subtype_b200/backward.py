@@ -1,4 +1,5 @@
-"""Backward kernels of the convolutions — first rows of the training path.
+"""Training-path wrappers: convolution backward, train-mode BatchNorm, pooling / up-sampling adjoints,
+heads, loss (K11), Adam (K12), the SyncBatchNorm peer exchange (K10x) and the gradient buckets.
 
 The reference has no backward code: `train.py` lets Lightning's automatic optimisation call
 `loss.backward()` (models.py:495-582), so autograd differentiates every `nn.Conv3d` of med3d.py

@@ -1,5 +1,4 @@
-"""Training step of the Med3D seg-reg network on the backward kernels (BASELINE config 5) — a
-first, *hybrid* slice.
+"""Training step of the Med3D seg-reg network on the backward kernels (BASELINE config 5).
 
 What runs where, stated plainly:
 
