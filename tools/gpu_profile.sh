@@ -8,7 +8,9 @@ shift
 WHAT=${@:-launches conv aux}
 BENCH="python bench.py --steps 2 --warmup 3 --batch 1 --no-cpu-baseline"
 mkdir -p gpurun_out
-$BENCH > gpurun_out/prof_bench_${TAG}.json 2> gpurun_out/prof_bench_${TAG}.err || exit 1
+if [ "$WHAT" != "traintail" ]; then
+  $BENCH > gpurun_out/prof_bench_${TAG}.json 2> gpurun_out/prof_bench_${TAG}.err || exit 1
+fi
 for w in $WHAT; do
   case $w in
     launches)
@@ -24,6 +26,10 @@ for w in $WHAT; do
       ncu -i /tmp/stem_${TAG}.ncu-rep --page raw --csv > gpurun_out/stem_${TAG}.raw.csv
       ncu -i /tmp/stem_${TAG}.ncu-rep --page source --csv > gpurun_out/stem_${TAG}.src.csv
       ncu -i /tmp/stem_${TAG}.ncu-rep --page details > gpurun_out/stem_${TAG}.details.txt ;;
+    traintail)  # training step: the loss (K11), Adam (K12) and the 38 BatchNorm backward-apply launches of one step
+      ncu --set full --clock-control none -k regex:'adam_kernel|loss_sums|loss_backward|loss_finalize|bn_bwd_apply' -c 50 \
+          -o /tmp/tt_${TAG} python tools/train_step_bench.py 256 1 resnet34segreg native native > gpurun_out/ncu_traintail_${TAG}.log 2>&1
+      ncu -i /tmp/tt_${TAG}.ncu-rep --page raw --csv > gpurun_out/traintail_${TAG}.raw.csv ;;
     aux)
       ncu --set full --clock-control none \
           -k regex:'upsample2x|maxpool3d|dram_upsample_mask|window_|masked_pool_partial' -s 36 -c 9 -o /tmp/aux_${TAG} \
