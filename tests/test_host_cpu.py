@@ -294,3 +294,48 @@ def test_dgrad_weight_packing_is_the_transposed_flipped_filter():
         ref = F.conv_transpose3d(dy, w, None, 1, dil, 0, 1, dil)
         ref = ref if rng is None else ref[:, rng[0]:rng[1]]
         assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_train_step_flat_layout_and_gradient_routing():
+    """Host logic of `training.TrainStep` (no kernel runs): every parameter becomes a view of one flat fp32 buffer with
+    its `.grad` at the same offset of the flat gradient buffer, values and `state_dict()` unchanged; convolution weights
+    (except the stem and the 1x1x1 heads) and BatchNorm weight/bias pairs are routed to gradient sinks, everything else
+    to post-accumulate hooks; bucket counters add up to the parameter count."""
+    from dram_b200 import med3d, training
+
+    model = med3d.resnet18segreg().train()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    step = training.TrainStep(model, optimizer="torch", loss="aten", bucket_bytes=16 << 20)
+    after = model.state_dict()
+    assert list(after) == list(before) and all(torch.equal(before[k], after[k]) for k in before)
+    total = sum(p.numel() for p in model.parameters())
+    assert step.flat_param.numel() == step.buckets.flat.numel() == total
+    for name, p in model.named_parameters():
+        off = step.buckets.slices[name][0]
+        assert p.data_ptr() == step.flat_param.data_ptr() + 4 * off, name
+        assert p.grad.data_ptr() == step.buckets.flat.data_ptr() + 4 * off and p.grad.shape == p.shape, name
+    convs = [n for n, m in model.named_modules() if isinstance(m, torch.nn.Conv3d)]
+    sinks = sorted(n for n, lay in step.net.layers.items() if lay.grad_sink is not None)
+    assert sinks == sorted(n for n in convs if n != "conv1" and not n.startswith("fcs."))
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm3d)]
+    assert len(step.net.bn_sinks) == len(bns) == 22
+    for bn in bns:  # one [dbeta | dgamma] view covering bias.grad then weight.grad
+        view, _ = step.net.bn_sinks[id(bn)]
+        assert view.data_ptr() == bn.bias.grad.data_ptr() and view.numel() == 2 * bn.num_features
+        assert bn.weight.grad.data_ptr() == view.data_ptr() + 4 * bn.num_features
+    hooked = sorted(n for n, p in model.named_parameters() if p._post_accumulate_grad_hooks)
+    assert hooked == sorted(["conv1.weight", "fcs.0.weight", "fcs.0.bias", "fcs.1.weight", "fcs.1.bias", "us3.0.bias"] +
+                            [f"us{i}.conv_blocks.{j}.0.bias" for i in (1, 2) for j in (0, 1)])
+    assert sum(step._bucket_size) == len(list(model.parameters())) and step.buckets.num_buckets >= 2
+    # a bucket is handed to the exchange exactly when its last gradient has been reported
+    fired = []
+    step.buckets.reduce_bucket = lambda i, group=None: fired.append(i)
+    for b, size in enumerate(step._bucket_size):
+        for k in range(size):
+            assert fired.count(b) == 0
+            step._grad_ready(b)
+        assert fired.count(b) == 1
+    with pytest.raises(ValueError, match="sync_bn"):
+        training.TrainStep(med3d.resnet18segreg().train(), optimizer="torch", loss="aten", sync_bn="maybe")
+    with pytest.raises(ValueError, match="loss="):
+        training.TrainStep(med3d.resnet18segreg().train(), optimizer="sgd")

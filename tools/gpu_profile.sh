@@ -26,9 +26,11 @@ for w in $WHAT; do
       ncu -i /tmp/stem_${TAG}.ncu-rep --page raw --csv > gpurun_out/stem_${TAG}.raw.csv
       ncu -i /tmp/stem_${TAG}.ncu-rep --page source --csv > gpurun_out/stem_${TAG}.src.csv
       ncu -i /tmp/stem_${TAG}.ncu-rep --page details > gpurun_out/stem_${TAG}.details.txt ;;
-    traintail)  # training step: the loss (K11), Adam (K12) and the 38 BatchNorm backward-apply launches of one step
-      ncu --set full --clock-control none -k regex:'adam_kernel|loss_sums|loss_backward|loss_finalize|bn_bwd_apply' -c 50 \
-          -o /tmp/tt_${TAG} python tools/train_step_bench.py 256 1 resnet34segreg native native > gpurun_out/ncu_traintail_${TAG}.log 2>&1
+    traintail)  # training step: the loss (K11) and Adam (K12) of the first two steps.  Keep it this small: under
+      # --set full every profiled kernel is replayed ~39 times with the step's whole footprint saved and restored
+      # (≈ 8 s per kernel at 256^3; a 50-kernel capture did not finish in 7 minutes in round 1).
+      ncu --set full --clock-control none -k regex:'adam_kernel|loss_sums|loss_backward|loss_finalize' -c 8 \
+          -o /tmp/tt_${TAG} python tools/train_step_bench.py 128 1 resnet34segreg native native > gpurun_out/ncu_traintail_${TAG}.log 2>&1
       ncu -i /tmp/tt_${TAG}.ncu-rep --page raw --csv > gpurun_out/traintail_${TAG}.raw.csv ;;
     aux)
       ncu --set full --clock-control none \
