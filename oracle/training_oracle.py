@@ -145,3 +145,55 @@ def grad_summary(grads, seed=123):
         r = torch.randn(v.numel(), generator=g, dtype=torch.float64)
         out[name] = (float(v.norm()), float((v * r).sum() / r.norm()))
     return out
+
+
+def loss_closed_form(dense, lungs, ems, cle_labels, pse_labels, cle_bands, pse_bands, cle_w, pse_w):
+    """The same loss as `total_loss` (with the lobe-masked means of med3d.py:387 computed inside) written the way the
+    fused kernel K11 evaluates it: one pass of seven sums per scan, a scalar step, and the gradient of both maps in
+    closed form — no autograd.  Returns (loss, [grad_cle, grad_pse], [reg_cle, reg_pse]).  test_oracle_cpu checks it
+    against autograd of `total_loss`, which is pinned to the reference; the GPU test checks the kernel against
+    `total_loss` directly, so this function is documentation of the derivation with a test attached.
+
+    dense: 2 x [B,1,d,h,w] fp32 in (0,1); lungs / ems: float 0/1 [B,1,D,H,W]."""
+    d0, d1 = dense[0].detach().double(), dense[1].detach().double()
+    B, size = d0.shape[0], d0.shape[-3:]
+    m = F.interpolate(lungs, size=size, mode="nearest").double()
+    flag = torch.logical_or(cle_labels > 0, pse_labels > 0).double().view(B, 1, 1, 1, 1)
+    t = F.interpolate(ems * flag.float(), size, mode="nearest").double()
+    s32 = (dense[0].detach() + dense[1].detach())  # fp32 sum, as the network's outputs are added (models.py:513)
+    both = s32.clamp(0.0, 1.0)
+    pt32 = torch.where(t > 0, both, 1.0 - both)
+    f = torch.where(m > 0, 0.85, 1.0).double()
+    logp = torch.log(pt32.clamp(1e-6, 1.0 - 1e-6)).double() * f
+    flat = lambda v: v.reshape(B, -1).sum(-1)  # noqa: E731
+    S0, S1, M, I = flat(d0 * m), flat(d1 * m), flat(m), flat(d0 * m * d1 * m)
+    T, A1, A0 = flat(t), flat(logp * (t > 0)), flat(logp * (t == 0))
+    regs = [(S0 / M).float(), (S1 / M).float()]
+
+    def interval(x, bands, w):  # models.py:495-506 and d/dx of it
+        dx, dlo, dhi = (BETA * v.double() ** GAMMA for v in (x, bands[:, 0], bands[:, 1]))
+        k, mid = 0.5 * (dhi - dlo), (dhi + dlo) / 2.0
+        u = (dx - mid) ** 2 - k * k
+        on = u > 0
+        loss = (10.0 * u * w.double() * on).sum()
+        grad = torch.where(on, 10.0 * w.double() * 2.0 * (dx - mid) * BETA * GAMMA * x.double() ** (GAMMA - 1.0), 0.0)
+        return loss, grad
+
+    loss_cle, g_cle = interval(regs[0], cle_bands, cle_w)
+    loss_pse, g_pse = interval(regs[1], pse_bands, pse_w)
+    num, den = 2.0 * I.sum() + 1e-7, S0.sum() + S1.sum() + 1e-7
+    mul = num / den
+    alpha = float((1.0 - T.sum() / B).clamp(0.3, 0.7))
+    n_vox = float(B * size[0] * size[1] * size[2])
+    wsum = alpha * T.sum() + (1.0 - alpha) * (n_vox - T.sum())
+    seg = -(alpha * A1.sum() + (1.0 - alpha) * A0.sum()) / wsum
+    loss = loss_cle + loss_pse + 2.0 * mul + seg
+    c1, c2 = 4.0 / den, 2.0 * num / den ** 2
+    # cross entropy through both clamps: ATen passes the gradient on the closed interval [min, max]
+    open_ = (s32 >= 0) & (s32 <= 1) & (pt32 >= 1e-6) & (pt32 <= 1.0 - 1e-6)
+    wv = torch.where(t > 0, alpha, 1.0 - alpha)
+    dl = torch.where(open_, -(wv * f / wsum) / pt32.double() * torch.where(t > 0, 1.0, -1.0), 0.0)
+    shape = (B, 1, 1, 1, 1)
+    grads = [m * ((g_cle / M).view(shape) + c1 * d1 * m - c2) + dl,
+             m * ((g_pse / M).view(shape) + c1 * d0 * m - c2) + dl]
+    return loss.float(), [g.float() for g in grads], regs

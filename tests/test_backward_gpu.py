@@ -363,8 +363,9 @@ def test_train_loss_kernel_matches_oracle(cuda, lib, case):
                                           pb.to(cuda), cw.to(cuda), pw.to(cuda))
     (3.0 * loss).backward()
     torch.cuda.synchronize()
-    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)), (float(loss), float(loss_ref))
-    assert abs(float(terms[0] + terms[1] + 2 * terms[2] + terms[3]) - float(loss)) <= 1e-6 * abs(float(loss))
+    loss_v, ref_v = float(loss.detach()), float(loss_ref.detach())
+    assert abs(loss_v - ref_v) <= 1e-5 * abs(ref_v), (loss_v, ref_v)
+    assert abs(float(terms[0] + terms[1] + 2 * terms[2] + terms[3]) - loss_v) <= 1e-6 * abs(loss_v)
     for k in (0, 1):
         assert torch.allclose(regs[:, k].cpu(), regs_ref[k].detach(), rtol=1e-6, atol=1e-7)
         got, ref = (x0, x1)[k].grad.cpu(), (a, b)[k].grad

@@ -175,3 +175,33 @@ def test_label_bands_follow_the_ratio_maps():
     for key, lab, want in (("cle_map", case["cls_label"], fix["cle_bands"]), ("pse_map", case["pse_label"], fix["pse_bands"])):
         mapping = {int(k): tuple(v) for k, v in labels[key].items()}
         assert torch.equal(T.label_bands(lab, mapping), want)
+
+
+@pytest.mark.parametrize("dims,mdims", [((8, 6, 10), (16, 12, 20)), ((5, 7, 9), (13, 14, 30))])
+def test_closed_form_loss_gradient_equals_autograd(dims, mdims):
+    """K11's derivation (training_oracle.loss_closed_form: seven sums per scan, scalar step, closed-form gradient) against
+    autograd of the restated reference loss `total_loss` (models.py:547-565), including map sums above 1 and values at
+    the 1e-6 clamp of the cross entropy where ATen's clamp stops the gradient."""
+    import torch.nn.functional as F
+
+    from oracle import training_oracle as T
+
+    B = 2
+    g = torch.Generator().manual_seed(dims[0])
+    d0, d1 = torch.rand((B, 1) + dims, generator=g) * 0.8, torch.rand((B, 1) + dims, generator=g) * 0.8
+    d0.view(-1)[:5], d1.view(-1)[:5] = 3e-7, 2e-7
+    lungs = (torch.rand((B, 1) + mdims, generator=g) > 0.5).float()
+    ems = (torch.rand((B, 1) + mdims, generator=g) > 0.7).float()
+    cl, pl = torch.tensor([3, 0]), torch.tensor([1, 0])
+    cb, pb = torch.tensor([[0.1, 0.2], [0.0, 0.0]]), torch.tensor([[0.01, 0.05], [0.0, 0.0]])
+    cw, pw = torch.tensor([1.0, 2.0]), torch.tensor([1.5, 0.5])
+    a, b = d0.clone().requires_grad_(True), d1.clone().requires_grad_(True)
+    lm = F.interpolate(lungs, dims, mode="nearest")
+    regs = [(x * lm).view(B, -1).sum(-1) / lm.view(B, -1).sum(-1) for x in (a, b)]
+    loss = T.total_loss([a, b], regs, lungs, ems, cl, pl, cb, pb, cw, pw)
+    loss.backward()
+    got, grads, got_regs = T.loss_closed_form([d0, d1], lungs, ems, cl, pl, cb, pb, cw, pw)
+    assert abs(float(got) - float(loss.detach())) <= 1e-5 * abs(float(loss.detach()))
+    for k, ref in enumerate((a.grad, b.grad)):
+        assert float((grads[k] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), k
+        assert torch.allclose(got_regs[k], regs[k].detach(), rtol=1e-6)
