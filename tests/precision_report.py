@@ -1,5 +1,6 @@
-"""Dense-map / score error of the B200 path against the CPU oracle for bf16 vs fp16 storage.
-    python tools/precision_report.py [--cases small|all]
+"""TEST INFRASTRUCTURE (a checker script, not collected by pytest; it lives under tests/ because it runs the oracle).
+Dense-map / score error of the B200 path against the CPU oracle for bf16 vs fp16 storage.
+    python tests/precision_report.py [--cases small|all]
 Prints max / p99.9 / mean abs error of the sigmoid dense maps (what becomes the dRAM) and the
 relative error of the pooled scores, per architecture and storage type."""
 import os
