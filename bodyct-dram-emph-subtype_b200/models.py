@@ -134,7 +134,7 @@ class DevicePrefetcher:
     passed the point where the caller asked for the following batch.  Non-tensor entries pass through.
 
     With `copy_streams` > 1 large tensors are cut into 16 MB chunks that travel on several streams at once.
-    Measured A/B on one box (ResNet-34, 256^3, batch 4; gpurun_out/bench_b4_cs{1,4}_r1o.json): one stream 23.7 ms
+    Measured A/B on one box (ResNet-34, 256^3, batch 4; profiles/bench_b4_r1o_copy{1,4}.json): one stream 23.7 ms
     per step end to end, four streams 24.5 ms — more DMA engines in flight take a little from the kernels and the
     copy was already hidden — so one stream is the default; the switch is kept for hosts where a single DMA stream
     cannot keep up (one box of this round showed 9 GB/s under load against 47 GB/s idle).
