@@ -124,20 +124,95 @@ def test_synthetic_volume_statistics():
     assert torch.equal(ct, ct2)
 
 
+LIVE_CASES = [
+    # arch, (D, H, W), batch, with lobe mask
+    ("med3ddram18", (16, 24, 32), 1, True),
+    ("med3ddram", (24, 16, 40), 2, True),      # ResNet-34, batch 2
+    ("med3ddram50", (16, 16, 24), 1, True),    # bottleneck blocks, shortcut A on four stages
+    ("med3ddram18", (16, 16, 16), 2, False),   # lungs=None: the plain mean (med3d.py:383-384, quirk Q3)
+    ("med3d18", (16, 24, 16), 1, False),       # classification heads, global average pool
+    ("med3d", (16, 16, 24), 2, False),
+    ("med3d50", (16, 16, 16), 1, False),
+]
+
+
 @pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
-def test_oracle_against_live_reference():
-    arch, dims = "med3ddram18", (16, 24, 32)
+@pytest.mark.parametrize("arch,dims,batch,with_mask", LIVE_CASES)
+def test_oracle_against_live_reference(arch, dims, batch, with_mask):
+    """The oracle's forward against the unmodified reference module executed here (through oracle/ref_shim.py) on the
+    same seeded weights and inputs: bit-identical dense maps and scores for all six architectures, ragged sizes,
+    batches of two and the lungs=None path.  (Only runs where /root/reference is mounted; the committed golden vectors
+    carry the same pin to the GPU box.)"""
     sd = synthetic.make_state_dict(arch, seed=3, calib_dims=dims)
     ref = ref_shim.model(arch)
     ref.load_state_dict(sd)
-    x, lung, _ = synthetic.make_network_input(5, dims)
+    ref.eval()
+    xs, lungs = zip(*[synthetic.make_network_input(5 + i, dims)[:2] for i in range(batch)])
+    x = torch.stack(xs)[:, None]
+    lung = torch.stack(lungs)[:, None].float() if with_mask else None
     with torch.no_grad():
-        d_ref, r_ref = ref(x[None, None].clone(), lung[None, None].float())
-    d_or, r_or = M.forward(sd, arch, x[None, None], lung[None, None].float())
+        d_ref, r_ref = ref(x.clone(), None if lung is None else lung.clone())
+    d_or, r_or = M.forward(sd, arch, x, lung)
+    assert len(d_ref) == len(d_or) == 2 and len(r_ref) == len(r_or) == 2
     for a, b in zip(d_ref, d_or):
         assert torch.equal(a, b)
     for a, b in zip(r_ref, r_or):
         assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+@pytest.mark.parametrize("arch,dims,batch", [("med3ddram", (16, 24, 32), 3), ("med3ddram50", (16, 16, 24), 1),
+                                              ("med3ddram18", (24, 16, 16), 2)])
+def test_predict_step_oracle_against_live_reference(arch, dims, batch):
+    """`ScanRegLightningModule.predict_step` of the unmodified reference (models.py:430-450, weights loaded the
+    processor.py:85-87 way) against the oracle: dRAM maps, percentages with the batch-wide denominator (quirk Q1),
+    key order and spelling, labels."""
+    from argparse import Namespace
+
+    ref = ref_shim.load()
+    sd = synthetic.make_state_dict(arch, seed=4, calib_dims=dims)
+    with ref_shim.reference_cwd():
+        module = ref.models.ScanRegLightningModule(Namespace(model_arch=arch))
+    ref.utils.load_state_dict_greedy(module, {"model." + k: v for k, v in sd.items()})
+    module.eval()
+    xs, ls, es = zip(*[synthetic.make_network_input(20 + i, dims) for i in range(batch)])
+    b = {"image": torch.stack(xs), "lung_mask": torch.stack(ls).bool(), "ess_mask": torch.stack(es).bool(),
+         "crop_slice": torch.tensor([[[0, d] for d in dims]] * batch), "original_size": torch.tensor([dims] * batch),
+         "uid": [f"v{i}" for i in range(batch)]}
+    with torch.no_grad():
+        want = module.predict_step({k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in b.items()}, 0)
+    got = P.predict_step(sd, arch, {k: b[k] for k in ("image", "lung_mask", "ess_mask")})
+    assert list(got.keys()) == list(want.keys())
+    for k in ("cle_dense_outs", "pse_dense_outs"):
+        assert (got[k] - want[k]).abs().max().item() < 2e-5 and torch.equal(got[k] == 0, want[k] == 0)
+    for k in ("cle_precentages", "pse_precentages"):
+        assert torch.allclose(got[k], want[k], rtol=1e-4)
+    cle_map, pse_map = ref.dataset.COPDGeneSubtyping.cle_ratio_map, ref.dataset.COPDGeneSubtyping.pse_ratio_map
+    assert [P.ratio_to_label(r.item(), P.CLE_RATIO_MAP) for r in got["cle_precentages"]] == \
+        module._ratio_to_label(want["cle_precentages"], cle_map).tolist()
+    assert [P.ratio_to_label(r.item(), P.PSE_RATIO_MAP) for r in got["pse_precentages"]] == \
+        module._ratio_to_label(want["pse_precentages"], pse_map).tolist()
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+@pytest.mark.parametrize("scan_dims,target", [((40, 48, 56), (24, 32, 40)), ((30, 36, 44), (32, 48, 40)),
+                                               ((33, 47, 51), (16, 47, 64))])
+def test_transforms_oracle_against_live_reference(scan_dims, target):
+    """The reference's own transform chain (`SubtypeDataModule._make_transforms(TEST)`, models.py:55-63: window,
+    standardise, in-plane resize + slice pick; down- and up-sampling targets, odd sizes) against the oracle: masks
+    bit-exact, images to 1e-6."""
+    from argparse import Namespace
+
+    ref = ref_shim.load()
+    ct, lobes = synthetic.make_volume(7, scan_dims)
+    sample = P.lung_crop_sample(ct.numpy(), lobes.numpy(), spacing=(1.0, 1.0, 1.0), crop_border=5, uid="s7")
+    tf = ref.models.SubtypeDataModule(Namespace(target_size=target))._make_transforms(ref.models.TEST_PHASE)
+    want = tf({k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sample.items()})
+    got = P.inference_transform(sample, target)
+    assert tuple(got["image"].shape) == tuple(want["image"].shape) == tuple(target)
+    assert torch.equal(got["lung_mask"], want["lung_mask"]) and torch.equal(got["ess_mask"], want["ess_mask"])
+    assert (got["image"] - want["image"]).abs().max().item() < 1e-6
+    assert (got["original_image"] - want["original_image"]).abs().max().item() < 1e-6
 
 
 # ------------------------------------------------------------------------------------------
