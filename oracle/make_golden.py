@@ -106,14 +106,11 @@ def gen_predict_step(ref):
     print("predict_step", fix["cle_precentages"].tolist(), fix["pse_precentages"].tolist(), fix["cle_labels"].tolist())
 
 
-def gen_train_step(ref):
+def reference_train_step(ref, case):
     """One training step of the UNMODIFIED reference network (train mode) with the reference's own loss code
-    (models.py:477-518, 547-565; metrics.py) on CPU: loss, outputs and a fingerprint of every parameter gradient."""
+    (models.py:477-518, 547-565; metrics.py) on CPU -> (loss, [four terms], bands, dense, regs, {name: gradient})."""
     from types import SimpleNamespace
 
-    from oracle import training_oracle as T
-
-    case = T.train_case()
     arch, B = case["arch"], case["batch"]
     model = ref_shim.model(arch)
     ref.utils.load_state_dict_greedy(model, case["sd"])
@@ -149,13 +146,23 @@ def gen_train_step(ref):
     loss = loss_cle + loss_pse + 2.0 * mul_loss + seg_loss
     loss.backward()
     grads = {n: p.grad for n, p in model.named_parameters()}
+    parts = [float(v.detach()) for v in (loss_cle, loss_pse, mul_loss, seg_loss)]
+    return loss.detach(), parts, (cle_b, pse_b), [d.detach() for d in dense], [r.detach() for r in regs], grads
+
+
+def gen_train_step(ref):
+    from oracle import training_oracle as T
+
+    case = T.train_case()
+    arch, B = case["arch"], case["batch"]
+    loss, parts, (cle_b, pse_b), dense, regs, grads = reference_train_step(ref, case)
     small = {n: g.clone() for n, g in grads.items() if g.numel() <= 4096}
     fix = {
         "arch": arch, "dims": case["dims"], "batch": B, "weight_seed": case["weight_seed"],
         "weight_checksum": synthetic.state_dict_checksum(case["sd"]),
-        "loss": float(loss), "parts": [float(loss_cle), float(loss_pse), float(mul_loss), float(seg_loss)],
+        "loss": float(loss), "parts": parts,
         "cle_bands": cle_b, "pse_bands": pse_b,
-        "dense_outs": [d.detach().clone() for d in dense], "reg_outs": [r.detach().clone() for r in regs],
+        "dense_outs": [d.clone() for d in dense], "reg_outs": [r.clone() for r in regs],
         "grad_summary": T.grad_summary(grads), "small_grads": small,
     }
     torch.save(fix, os.path.join(GOLDEN, "train_step_med3ddram18.pt"))

@@ -252,6 +252,33 @@ def test_label_bands_follow_the_ratio_maps():
         assert torch.equal(T.label_bands(lab, mapping), want)
 
 
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
+@pytest.mark.parametrize("arch,dims,batch", [("med3ddram50", (16, 16, 16), 2), ("med3ddram", (16, 16, 24), 1)])
+def test_training_oracle_against_live_reference(arch, dims, batch):
+    """The training oracle (train-mode BatchNorm, detached shortcut A, the reference's loss) against one training step
+    of the unmodified reference network with the reference's own loss code, executed here: loss to 1e-5, every
+    parameter gradient to 2e-3 of the largest gradient — on the bottleneck network (shortcut A on four stages) and on
+    ResNet-34, beyond the committed med3ddram18 golden step."""
+    from oracle import make_golden
+    from oracle import training_oracle as T
+
+    case = T.train_case(batch=batch, dims=dims, arch=arch, seed=6)
+    loss_ref, parts, (cle_b, pse_b), dense_ref, regs_ref, grads_ref = make_golden.reference_train_step(ref_shim.load(), case)
+    loss, grads, dense, regs = T.train_step_grads(case["sd"], arch, case["image"], case["lung_mask"], case["em_mask"],
+                                                  case["cls_label"], case["pse_label"], cle_b, pse_b,
+                                                  case["cle_weights"], case["pse_weights"])
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)), (float(loss), float(loss_ref), parts)
+    for a, b in zip(dense, dense_ref):
+        assert (a - b).abs().max().item() < 2e-5
+    for a, b in zip(regs, regs_ref):
+        assert torch.allclose(a, b, rtol=1e-5)
+    top = max(float(g.abs().max()) for g in grads_ref.values() if g is not None)
+    assert set(grads) == {n for n, g in grads_ref.items() if g is not None}
+    for name, g in grads.items():
+        err = float((g - grads_ref[name]).abs().max())
+        assert err <= 2e-3 * top, (name, err, top)
+
+
 @pytest.mark.parametrize("dims,mdims", [((8, 6, 10), (16, 12, 20)), ((5, 7, 9), (13, 14, 30))])
 def test_closed_form_loss_gradient_equals_autograd(dims, mdims):
     """K11's derivation (training_oracle.loss_closed_form: seven sums per scan, scalar step, closed-form gradient) against
