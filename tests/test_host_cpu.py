@@ -339,3 +339,29 @@ def test_train_step_flat_layout_and_gradient_routing():
         training.TrainStep(med3d.resnet18segreg().train(), optimizer="torch", loss="aten", sync_bn="maybe")
     with pytest.raises(ValueError, match="loss="):
         training.TrainStep(med3d.resnet18segreg().train(), optimizer="sgd")
+
+
+def test_conv_descriptor_mirror_matches_the_header():
+    """`_capi.ConvDesc` (and the mirror shown in INTEGRATION.md) lists the fields of `dram_conv_desc` in the header's
+    order with the header's types — the struct crosses the C-ABI by value layout, so a drift would corrupt every plan."""
+    import ctypes as C
+
+    from dram_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "dram_b200.h")).read()
+    body = header[header.index("typedef struct dram_conv_desc {"):header.index("} dram_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"int32_t\s+([^;]+);", body):
+        for name in decl.split(","):
+            name = name.strip()
+            m = re.match(r"(\w+)\[(\d+)\]", name)
+            fields.append((m.group(1), int(m.group(2))) if m else (name, 1))
+    mirror = [(n, t._length_ if hasattr(t, "_length_") else 1) for n, t in _capi.ConvDesc._fields_]
+    assert mirror == fields, (mirror, fields)
+    assert C.sizeof(_capi.ConvDesc) == 4 * sum(k for _, k in fields)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class ConvDesc(C.Structure)"):]
+    block = block[:block.index("\n\n")]
+    doc_fields = [w for lit in re.findall(r'"([a-z0-9_ ]+)"', block) for w in lit.split()]
+    assert doc_fields == [n for n, _ in fields], doc_fields
