@@ -365,3 +365,38 @@ def test_conv_descriptor_mirror_matches_the_header():
     block = block[:block.index("\n\n")]
     doc_fields = [w for lit in re.findall(r'"([a-z0-9_ ]+)"', block) for w in lit.split()]
     assert doc_fields == [n for n, _ in fields], doc_fields
+
+
+def test_ctypes_signatures_follow_the_header_prototypes():
+    """Every entry of `_capi.SIGNATURES` has the arity and return type of its prototype in include/dram_b200.h, and
+    pointer / integer / floating-point parameters sit in the same positions (a drifted ctypes signature reads garbage
+    off the stack without failing)."""
+    import ctypes as C
+
+    from dram_b200 import _capi
+
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dram_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\n(int|int64_t|size_t)\s+(dram_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header)
+    assert len(protos) == len(_capi.SIGNATURES), (len(protos), len(_capi.SIGNATURES))
+    ret = {"int": C.c_int, "int64_t": C.c_int64, "size_t": C.c_size_t}
+    ints = {C.c_int, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t}
+    floats = {C.c_float, C.c_double}
+    for rtype, name, params in protos:
+        res, args = _capi.SIGNATURES[name]
+        assert res is ret[rtype], name
+        plist = [] if params.strip() in ("", "void") else [p.strip() for p in params.split(",")]
+        assert len(plist) == len(args), (name, len(plist), len(args))
+        for i, (p, a) in enumerate(zip(plist, args)):
+            if "*" in p or "[" in p:
+                kind = "pointer"
+            elif re.match(r"(const\s+)?(float|double)\b", p):
+                kind = "float"
+            else:
+                kind = "int"
+            if kind == "pointer":
+                assert a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or issubclass(a, C._Pointer), (name, i, p, a)
+            elif kind == "float":
+                assert a in floats and (a is C.c_double) == ("double" in p), (name, i, p, a)
+            else:
+                assert a in ints, (name, i, p, a)
+                assert (C.sizeof(a) == 8) == bool(re.search(r"u?int64_t|size_t", p)), (name, i, p, a)
