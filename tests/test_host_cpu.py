@@ -429,3 +429,27 @@ def test_built_library_uses_tensor_cores_and_tma():
     peer = sass_summary.kernel_sass()["dram::peer_allreduce_f64_kernel"]
     for mnemonic in (r"STG\.E\.64\.STRONG\.SYS", r"LDG\.E\.64\.STRONG\.SYS", r"MEMBAR\.SC\.SYS"):
         assert re.search(mnemonic, peer), mnemonic  # st.release.sys flag, ld.acquire.sys poll, __threadfence_system
+
+
+def test_bench_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on stdout
+    with the contract's keys, this run's `cpu_baseline` and a zero-copy `e2e`; under torchrun only rank 0 prints."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "32", "--steps", "2", "--warmup", "1"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, res.stdout
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "volumes/s" and line["higher_is_better"] is True
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["vs_baseline"] is None and line["data"] == "synthetic"
+    assert line["value"] > 0 and abs(line["value"] * line["ms_per_step"] / 1e3 - 1.0) < 1e-6  # one volume per step
+    assert "workload" in line["config"] and "32" in line["config"]["workload"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=600, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
