@@ -5,7 +5,8 @@ two 3x3x3 steps (== one 5x5x5 box) to -2048, crop to the lung bounding box + 5 m
 `ess` mask, and hand the dict to the transform.  With a CUDA `device` these pre-steps run on the GPU
 (`ops.mask_bbox` + `ops.lung_crop`): the scan and the lobe labels are copied to the device
 once (3 bytes per voxel), only the 6 bounding-box integers come back, and the cropped tensors go straight
-into the GPU transform.  Without a device the same steps run in numpy/torch on the CPU.
+into the GPU transform.  There is no CPU path (the CPU restatement of these steps is oracle/pipeline_oracle.py,
+test infrastructure).
 """
 import glob
 import math
@@ -14,10 +15,8 @@ from pathlib import Path
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import mha_io
-from .utils import find_crops
 
 
 def grow_bbox(bbox, shape, spacing, border):
@@ -55,12 +54,6 @@ class SubtypingInference(torch.utils.data.Dataset):
         direction = np.asarray(meta["direction"]).reshape(3, 3)[::-1].flatten().tolist()
         return arr, meta["origin"][::-1], meta["spacing"][::-1], direction
 
-    @staticmethod
-    def dilate_lung(lung):
-        """binary_dilation(lung, full 3x3x3 structure, iterations=2) == 5x5x5 box maximum, zero border."""
-        t = torch.from_numpy(np.ascontiguousarray(lung)).to(torch.float32)[None, None]
-        return F.max_pool3d(t, kernel_size=5, stride=1, padding=2)[0, 0].numpy() > 0
-
     def device_presteps(self, scan, lobe, spacing, uid):
         """dataset.py:66-83 on the GPU; returns the same dict with device tensors (masks as bool)."""
         from . import ops
@@ -91,25 +84,12 @@ class SubtypingInference(torch.utils.data.Dataset):
         lobe, _, _, _ = self.read_image(lobe_file)
         assert lobe.shape == scan.shape, "scan and lobe segmentation have different shapes."
         self.scan_meta_cache[uid] = {"spacing": spacing, "origin": origin, "direction": direction}
-        if self.device is None and hasattr(self.transforms, "_dev") and torch.cuda.is_available():
-            self.device = self.transforms._dev()  # the GPU transform follows: do the pre-steps there too
-        if self.device is not None and self.device.type == "cuda":
-            sample = self.device_presteps(scan, lobe, spacing, uid)
-            return self.transforms(sample) if self.transforms else sample
-        original = scan.copy()
-        lung = lobe > 0
-        scan = scan.copy()
-        scan[~self.dilate_lung(lung)] = -2048
-        sl = find_crops(lung, spacing, self.crop_border)
-        scan_c, lung_c = scan[sl], lung[sl]
-        sample = {
-            "image": scan_c.astype(np.int16),
-            "original_image": original[sl].astype(np.int16),
-            "lung_mask": lung_c > 0,
-            "ess_mask": np.logical_and(scan_c < -910, lung_c > 0),
-            "crop_slice": np.asarray([(s.start, s.stop) for s in sl]),
-            "original_size": np.asarray(scan.shape),
-            "uid": uid,
-        }
-        self.scan_meta_cache[uid] = {"spacing": spacing, "origin": origin, "direction": direction}
+        if self.device is None and torch.cuda.is_available():
+            # the GPU transform follows: the pre-steps run on the same device
+            self.device = self.transforms._dev() if hasattr(self.transforms, "_dev") else \
+                torch.device("cuda", torch.cuda.current_device())
+        if self.device is None or self.device.type != "cuda":
+            raise RuntimeError("SubtypingInference needs a CUDA device: the pre-steps of dataset.py:66-83 run on the GPU "
+                               "(ops.mask_bbox / ops.lung_crop); there is no CPU path")
+        sample = self.device_presteps(scan, lobe, spacing, uid)
         return self.transforms(sample) if self.transforms else sample

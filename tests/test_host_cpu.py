@@ -453,3 +453,24 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=600, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_inference_dataset_has_no_cpu_path(tmp_path):
+    """Without a CUDA device the dataset reads the files and then refuses: the pre-steps of dataset.py:66-83 exist on
+    the GPU only (their CPU restatement is the oracle's, not the product's)."""
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present: the GPU path would run (covered by the -m gpu tests)")
+    from dram_b200 import mha_io
+    from dram_b200.dataset import SubtypingInference
+
+    (tmp_path / "ct").mkdir()
+    (tmp_path / "lobes").mkdir()
+    scan = np.full((6, 8, 10), -800, dtype=np.int16)
+    lobe = np.zeros((6, 8, 10), dtype=np.uint8)
+    lobe[2:4, 2:6, 3:7] = 1
+    mha_io.write_mha(str(tmp_path / "ct" / "a.mha"), scan)
+    mha_io.write_mha(str(tmp_path / "lobes" / "a.mha"), lobe)
+    ds = SubtypingInference(str(tmp_path / "ct"), str(tmp_path / "lobes"))
+    assert len(ds) == 1
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ds[0]
