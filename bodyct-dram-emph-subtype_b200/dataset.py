@@ -77,13 +77,20 @@ class SubtypingInference(torch.utils.data.Dataset):
             "uid": uid,
         }
 
-    def get_data(self, index):
+    def load_raw(self, index):
+        """The file half of `get_data` (dataset.py:57-65): read CT + lobes.  Host only and thread-safe, so the
+        processor's `--workers N` can read ahead on N threads (zlib releases the GIL)."""
         scan_file, lobe_file = self.scan_files[index], self.lobe_files[index]
         uid = Path(scan_file).stem
         scan, origin, spacing, direction = self.read_image(scan_file)
         lobe, _, _, _ = self.read_image(lobe_file)
         assert lobe.shape == scan.shape, "scan and lobe segmentation have different shapes."
-        self.scan_meta_cache[uid] = {"spacing": spacing, "origin": origin, "direction": direction}
+        return {"uid": uid, "scan": scan, "lobe": lobe, "origin": origin, "spacing": spacing, "direction": direction}
+
+    def get_data(self, index, raw=None):
+        raw = self.load_raw(index) if raw is None else raw
+        uid, scan, lobe, spacing = raw["uid"], raw["scan"], raw["lobe"], raw["spacing"]
+        self.scan_meta_cache[uid] = {"spacing": spacing, "origin": raw["origin"], "direction": raw["direction"]}
         if self.device is None and torch.cuda.is_available():
             # the GPU transform follows: the pre-steps run on the same device
             self.device = self.transforms._dev() if hasattr(self.transforms, "_dev") else \

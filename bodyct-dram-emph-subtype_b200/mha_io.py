@@ -7,6 +7,8 @@ raw (optionally zlib-compressed) voxels with x fastest.  Arrays are returned/acc
 TransformMatrix, exactly what sitk's GetSpacing/GetOrigin/GetDirection return.
 """
 import zlib
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -86,3 +88,38 @@ def write_mha(path, arr, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
     with open(path, "wb") as f:
         f.write(("\n".join(lines) + "\n").encode("ascii"))
         f.write(payload)
+
+
+class BackgroundWriter:
+    """`--workers N` of the processor, output side: file writes (zlib, which releases the GIL) run on N threads while
+    the predict loop goes on.  At most 2 N calls are in flight (each holds a full-size volume); an exception of a
+    write surfaces at the next `submit` or at `close()`.  N = 0 runs every call at once in the caller's thread."""
+
+    def __init__(self, workers=0):
+        self.pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="mha-write") if workers > 0 else None
+        self.limit = 2 * max(1, workers)
+        self.pending = deque()
+
+    def submit(self, fn, *args, **kwargs):
+        if self.pool is None:
+            fn(*args, **kwargs)
+            return
+        while len(self.pending) >= self.limit or (self.pending and self.pending[0].done()):
+            self.pending.popleft().result()
+        self.pending.append(self.pool.submit(fn, *args, **kwargs))
+
+    def close(self):
+        try:
+            while self.pending:
+                self.pending.popleft().result()
+        finally:
+            if self.pool is not None:
+                self.pool.shutdown(wait=True)
+                self.pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -92,8 +92,27 @@ class SubtypeDataModule(_DataModuleBase):
         ds = self.predict_dataset()
         indices = shard_indices(len(ds), rank, world_size)
         bs = int(getattr(self.args, "batch_size", 2))
-        for i in range(0, len(indices), bs):
-            yield collate([ds[j] for j in indices[i:i + bs]])
+        workers = int(getattr(self.args, "workers", 0) or 0)
+        if workers <= 0:
+            for i in range(0, len(indices), bs):
+                yield collate([ds[j] for j in indices[i:i + bs]])
+            return
+        # `--workers N` (processor.py:59, the reference's DataLoader workers): N threads read the .mha files of the
+        # scans ahead (file I/O + zlib, GIL released) while the GPU works; the device pre-steps stay in this thread
+        from concurrent.futures import ThreadPoolExecutor
+
+        ahead = workers + bs
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="mha-read") as pool:
+            futures = {}
+            for pos in range(len(indices)):
+                for q in range(pos, min(pos + ahead, len(indices))):
+                    if q not in futures:
+                        futures[q] = pool.submit(ds.load_raw, indices[q])
+                if pos % bs == 0:
+                    samples = []
+                samples.append(ds.get_data(indices[pos], raw=futures.pop(pos).result()))
+                if len(samples) == bs or pos == len(indices) - 1:
+                    yield collate(samples)
 
     def train_dataloader(self):
         raise NotImplementedError("training is not part of this build")

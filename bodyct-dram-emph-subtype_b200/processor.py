@@ -34,7 +34,7 @@ if __package__ in (None, ""):  # executed as a script: import the package under 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from . import ops  # noqa: E402
+from . import mha_io, ops  # noqa: E402
 from .models import (CLE_RATIO_MAP, PSE_RATIO_MAP, RunningStage, ScanCLSLightningModule,  # noqa: E402
                      ScanRegLightningModule, SubtypeDataModule, ratio_to_label)
 from .utils import load_state_dict_greedy, windowing, write_array_to_mha_itk  # noqa: E402
@@ -76,8 +76,9 @@ def load_checkpoint(module, path):
     return True
 
 
-def postprocess_reg(pred, data_module, out_cle, out_pse):
-    """processor.py:111-158 for one batch of predictions; returns the result records."""
+def postprocess_reg(pred, data_module, out_cle, out_pse, writer=None):
+    """processor.py:111-158 for one batch of predictions; returns the result records.  `writer`: a
+    `mha_io.BackgroundWriter` that takes the file writes off this thread (`--workers N`)."""
     records = []
     meta_cache = data_module.datasets[RunningStage.PREDICTING].scan_meta_cache
     B = pred["cle_dense_outs"].shape[0]
@@ -101,7 +102,10 @@ def postprocess_reg(pred, data_module, out_cle, out_pse):
         kw = dict(type=np.uint8, origin=meta["origin"][::-1], spacing=meta["spacing"][::-1],
                   direction=np.asarray(meta["direction"]).reshape(3, 3)[::-1].flatten().tolist())
         for full, folder in zip(heat, (out_cle, out_pse)):
-            write_array_to_mha_itk(folder, [full], [uid], **kw)
+            if writer is None:
+                write_array_to_mha_itk(folder, [full], [uid], **kw)
+            else:
+                writer.submit(write_array_to_mha_itk, folder, [full], [uid], **kw)
     return records
 
 
@@ -128,9 +132,14 @@ def run_rank(args, rank, world_size):
     Path(out_cle).mkdir(parents=True, exist_ok=True)
     Path(out_pse).mkdir(parents=True, exist_ok=True)
     records = []
-    for i, batch in enumerate(data_module.predict_dataloader(rank, world_size)):
-        pred = module.predict_step(batch, i)
-        records += postprocess_reg(pred, data_module, out_cle, out_pse) if is_reg else postprocess_cls(pred)
+    workers = int(getattr(args, "workers", 0) or 0)
+    with mha_io.BackgroundWriter(workers) as writer:  # workers == 0: writes happen in place, as before
+        for i, batch in enumerate(data_module.predict_dataloader(rank, world_size)):
+            pred = module.predict_step(batch, i)
+            if is_reg:
+                records += postprocess_reg(pred, data_module, out_cle, out_pse, writer if workers > 0 else None)
+            else:
+                records += postprocess_cls(pred)
     return records
 
 

@@ -474,3 +474,64 @@ def test_inference_dataset_has_no_cpu_path(tmp_path):
     assert len(ds) == 1
     with pytest.raises(RuntimeError, match="no CPU path"):
         ds[0]
+
+
+def test_background_writer_and_read_ahead(tmp_path):
+    """`--workers N` of the processor (processor.py:59): the output side writes .mha files on N threads with the same
+    bytes as in-place writes and reports a failed write; the input side reads ahead on N threads and hands the loop
+    the same batches, in the same order, as the synchronous loader — for full, ragged and wrap-around-padded shards."""
+    from argparse import Namespace
+
+    from dram_b200 import mha_io
+    from dram_b200.models import SubtypeDataModule
+
+    g = np.random.default_rng(3)
+    vols = [(g.integers(0, 4, size=(20, 64, 64)) * 60).astype(np.uint8) for _ in range(6)]
+    for sub in ("sync", "async"):
+        (tmp_path / sub).mkdir()
+    for i, v in enumerate(vols):
+        mha_io.write_mha(str(tmp_path / "sync" / f"v{i}.mha"), v, spacing=(0.7, 0.7, 1.25))
+    with mha_io.BackgroundWriter(3) as writer:
+        for i, v in enumerate(vols):
+            writer.submit(mha_io.write_mha, str(tmp_path / "async" / f"v{i}.mha"), v, spacing=(0.7, 0.7, 1.25))
+            assert len(writer.pending) <= 6
+    for i in range(6):
+        assert (tmp_path / "sync" / f"v{i}.mha").read_bytes() == (tmp_path / "async" / f"v{i}.mha").read_bytes()
+    writer = mha_io.BackgroundWriter(2)
+    writer.submit(mha_io.write_mha, str(tmp_path / "missing_dir" / "x.mha"), vols[0])
+    with pytest.raises(FileNotFoundError):
+        writer.close()
+    inline = mha_io.BackgroundWriter(0)
+    inline.submit(mha_io.write_mha, str(tmp_path / "inline.mha"), vols[1])
+    assert (tmp_path / "inline.mha").exists() and not inline.pending
+    inline.close()
+
+    class FakeDataset:  # stands in for SubtypingInference: file half on the worker threads, device half in the loop
+        def __init__(self, n):
+            self.n, self.processed = n, []
+
+        def __len__(self):
+            return self.n
+
+        def load_raw(self, index):
+            return {"uid": f"scan{index:02d}", "value": index}
+
+        def get_data(self, index, raw=None):
+            raw = self.load_raw(index) if raw is None else raw
+            assert raw["value"] == index
+            self.processed.append(index)
+            return {"image": torch.full((2, 2), float(index)), "uid": raw["uid"]}
+
+        def __getitem__(self, index):
+            return self.get_data(index)
+
+    for n, bs, workers, rank, world in [(7, 2, 3, 0, 1), (7, 3, 1, 1, 2), (5, 4, 8, 2, 3), (1, 2, 2, 0, 1), (4, 2, 2, 3, 4)]:
+        batches = {}
+        for w in (0, workers):
+            dm = SubtypeDataModule(Namespace(batch_size=bs, workers=w, target_size=(8, 8, 8)))
+            fake = FakeDataset(n)
+            dm.predict_dataset = lambda fake=fake: fake
+            batches[w] = [(b["uid"], b["image"][:, 0, 0].tolist()) for b in dm.predict_dataloader(rank, world)]
+            from dram_b200.models import shard_indices
+            assert fake.processed == shard_indices(n, rank, world)  # the device half runs in order, once per slot
+        assert batches[0] == batches[workers] and len(batches[0]) == -(-len(shard_indices(n, rank, world)) // bs)
