@@ -94,8 +94,10 @@ def test_gpu_transform_matches_reference_golden(cuda, lib):
     assert out["uid"] == "s3" and torch.equal(out["crop_slice"], torch.as_tensor(fix["crop_slice"]))
 
 
-def test_processor_end_to_end(cuda, lib, tmp_path):
-    """Three synthetic scans written as .mha -> processor.py surface -> heat-maps + JSON, against the oracle pipeline."""
+@pytest.mark.parametrize("workers", [0, 2])
+def test_processor_end_to_end(cuda, lib, tmp_path, workers):
+    """Three synthetic scans written as .mha -> processor.py surface -> heat-maps + JSON, against the oracle pipeline;
+    with `--workers 2` the files are read ahead and the heat-maps written on two threads each."""
     from dram_b200 import mha_io, processor
     from dram_b200.models import ScanRegLightningModule  # noqa: F401
 
@@ -114,7 +116,8 @@ def test_processor_end_to_end(cuda, lib, tmp_path):
     # a >4 KiB file: anything smaller is treated as a Git-LFS pointer
     torch.save({"state_dict": sd}, ckpt)
     argv = ["--scan_path", str(scan_dir), "--lobe_path", str(lobe_dir), "--output_path", str(out_dir),
-            "--model_arch", arch, "--target_size", "32,40,48", "--batch_size", "1", "--ckpt_path", str(ckpt)]
+            "--model_arch", arch, "--target_size", "32,40,48", "--batch_size", "1", "--ckpt_path", str(ckpt),
+            "--workers", str(workers)]
     records = processor.run_testing_job(argv)
     assert [r["entity"] for r in records] == ["scan0", "scan1", "scan2"]
     plain = {k[len("model."):]: v for k, v in sd.items()}
