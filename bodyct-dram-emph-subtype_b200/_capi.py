@@ -51,6 +51,7 @@ SIGNATURES = {
     "dram_version": (C.c_int, []),
     "dram_last_error": (C.c_int, [C.c_char_p, _sz]),
     "dram_sm_count": (C.c_int, []),
+    "dram_set_saturation_counter": (C.c_int, [_vp]),
     "dram_conv3d_out_dims": (C.c_int, [C.POINTER(ConvDesc), _pi32, _pi32, _pi32]),
     "dram_conv3d_plan_create": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _vp, C.POINTER(_vp)]),

@@ -1,7 +1,7 @@
 // Library-level entry points of libdram_b200.so: version, per-thread error text, device info.
 #include <string.h>
 
-#include "common.h"
+#include "umma_common.cuh"
 
 namespace dram {
 
@@ -13,6 +13,9 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+
+static thread_local unsigned int *g_sat_counter = nullptr;
+unsigned int *current_sat_counter() { return g_sat_counter; }
 
 int sm_count() {
   // Cached per device; the hot path never switches devices inside one process (one rank = one GPU).
@@ -47,3 +50,9 @@ extern "C" int dram_last_error(char *buf, size_t len) {
 }
 
 extern "C" int dram_sm_count(void) { return dram::sm_count(); }
+
+extern "C" int dram_set_saturation_counter(void *counter_u32) {
+  DRAM_REQUIRE((reinterpret_cast<uintptr_t>(counter_u32) & 3) == 0, "dram_set_saturation_counter: counter must be 4-byte aligned");
+  dram::g_sat_counter = reinterpret_cast<unsigned int *>(counter_u32);
+  return DRAM_OK;
+}

@@ -235,7 +235,9 @@ int pair_plan_fill(dram_conv_plan *pl) {
 
 int pair_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
   if (pl->p.total_tiles < ctas) ctas = pl->p.total_tiles;
-  conv3d_pair_kernel<<<ctas, P_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->p);
+  ConvKParams kp = pl->p;
+  kp.epi = with_sat_counter(kp.epi);
+  conv3d_pair_kernel<<<ctas, P_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, kp);
   DRAM_CHECK_LAUNCH("conv3d_pair_kernel launch");
   return DRAM_OK;
 }

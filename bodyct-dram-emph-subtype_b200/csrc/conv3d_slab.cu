@@ -562,13 +562,15 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
 int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
   if (pl->sp.items_total < ctas) ctas = pl->sp.items_total;
   dim3 grid(ctas);
-  if (pl->sp.up2x)
+  SlabParams sp = pl->sp;
+  sp.epi = with_sat_counter(sp.epi);
+  if (sp.up2x)
     conv3d_slab_kernel<64, true><<<grid, SlabCfg<64, true>::THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2,
-                                                                                          pl->map_w, pl->sp);
+                                                                                          pl->map_w, sp);
   else if (pl->block_n == 64)
-    conv3d_slab_kernel<64, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+    conv3d_slab_kernel<64, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, sp);
   else
-    conv3d_slab_kernel<32, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, pl->sp);
+    conv3d_slab_kernel<32, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, sp);
   DRAM_CHECK_LAUNCH("conv3d_slab_kernel launch");
   return DRAM_OK;
 }

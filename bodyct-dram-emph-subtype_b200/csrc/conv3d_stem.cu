@@ -331,6 +331,7 @@ extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *
   p.epi.out = reinterpret_cast<uint16_t *>(out);
   p.epi.res_stride = 1;
   p.epi.store_out = 1;
+  p.epi = with_sat_counter(p.epi);
   int rc = check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            ST_SMEM_BYTES),
                       "cudaFuncSetAttribute(conv3d_stem_kernel)");

@@ -441,8 +441,10 @@ static int fill_tile_cfg(dram_conv_plan *pl) {
 }
 template <int BN, bool STAGED>
 static void launch_tiles(const dram_conv_plan *pl, dim3 grid, cudaStream_t st) {
+  ConvKParams kp = pl->p;
+  kp.epi = with_sat_counter(kp.epi);
   conv3d_umma_kernel<BN, STAGED><<<grid, STAGED ? NUM_THREADS_STAGED : NUM_THREADS, pl->smem_bytes, st>>>(
-      pl->map_a1, pl->map_a2, pl->map_w, pl->map_out, pl->map_res, pl->p);
+      pl->map_a1, pl->map_a2, pl->map_w, pl->map_out, pl->map_res, kp);
 }
 
 extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1, const void *src2,

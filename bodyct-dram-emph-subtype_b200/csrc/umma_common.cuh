@@ -23,7 +23,17 @@ struct EpiParams {
   const float *head_b;
   float *head_out0;
   float *head_out1;
+  // fp16 storage only: when non-null, every epilogue group whose result exceeds the finite fp16 range (and is
+  // clamped to +-65504 by the saturating conversion) adds one to this device counter (dram_set_saturation_counter)
+  unsigned int *sat_count;
 };
+
+// The calling thread's saturation counter (capi.cu); the conv launchers copy it into the kernel parameters.
+unsigned int *current_sat_counter();
+inline EpiParams with_sat_counter(EpiParams e) {
+  e.sat_count = e.is_f16 ? current_sat_counter() : nullptr;
+  return e;
+}
 
 // ----------------------------------------------------------------------------------------
 // PTX wrappers
@@ -197,6 +207,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_f16) {
 }
 
 
+// Saturation probe (debug / first-run check): one atomic per 32-value group that left the fp16 range.  The branch on
+// e.sat_count is uniform over the grid, so the default (nullptr) costs one predicate per group.
+__device__ __forceinline__ void note_saturation(const EpiParams &e, const float (&y)[32]) {
+  float m = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(y[j]));
+  if (!(m <= 65504.0f)) atomicAdd(e.sat_count, 1u);  // also catches NaN
+}
+
 // Residual row of an output voxel (nullptr when there is no residual or the voxel is out of range).
 __device__ __forceinline__ const uint16_t *residual_row(const EpiParams &e, bool valid, int sample, int od,
                                                         int oh, int ow) {
@@ -251,6 +270,7 @@ __device__ __forceinline__ void epilogue_group(const EpiParams &e, const uint32_
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
   }
+  if (e.sat_count != nullptr && e.store_out) note_saturation(e, y);
   const size_t vox = (((size_t)sample * e.Do + od) * e.Ho + oh) * e.Wo + ow;
   if (e.store_out) {
     uint4 *o4 = reinterpret_cast<uint4 *>(e.out + vox * e.cout + cg);
@@ -335,6 +355,7 @@ __device__ __forceinline__ void epilogue_group_staged(const EpiParams &e, const 
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
   }
+  if (e.sat_count != nullptr) note_saturation(e, y);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t w[4];

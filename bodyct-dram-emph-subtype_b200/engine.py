@@ -47,15 +47,17 @@ class Med3DEngine:
         self._packers = []    # closures that (re)fill the buffers from the module's parameters
         self.steps = []
         self.conv_flops = 0
+        self._graph = None
+        self._sat_counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self._sat_checked_epoch = None
+        self.last_saturation_count = None   # result of the latest probed pass (None: never probed)
         self._build()
-        self._weight_version = self._current_weight_version()
+        self._weights_epoch = model.weights_epoch
 
     # ---------------------------------------------------------------- weights
-    def _current_weight_version(self):
-        v = 0
-        for t in list(self.model.parameters()) + list(self.model.buffers()):
-            v = (v * 1000003 + t._version + (t.data_ptr() & 0xFFFFFF)) & 0xFFFFFFFFFFFF
-        return v
+    # The packed operands follow the module's parameters through `model.weights_epoch`, a counter the module bumps
+    # in load_state_dict / _apply / train<->eval transitions / mark_weights_changed() (med3d._Med3DSegNet); run()
+    # compares two integers.  (Round 1 hashed every parameter's version counter per run: 0.65 ms of host time.)
 
     def _register_weight(self, name, pack_fn):
         """pack_fn() -> (16-bit [cout, K], fp32 bias [cout], fp32 multiplier [cout]) on self.device;
@@ -74,7 +76,7 @@ class Med3DEngine:
         """Re-folds BatchNorm and re-packs every weight in place (after load_state_dict etc.)."""
         for refill in self._packers:
             refill()
-        self._weight_version = self._current_weight_version()
+        self._weights_epoch = self.model.weights_epoch
 
     def _conv_bn(self, name, conv, bn, stem=False):
         def pack():
@@ -227,18 +229,64 @@ class Med3DEngine:
         self._plans_alive = [s.fn for s in self.steps]
 
     # ---------------------------------------------------------------- run
+    def _launch_steps(self):
+        for st in self.steps:
+            st.fn()
+
+    def run_network(self):
+        """The recorded launch sequence on `self.image` -> `self.dense` (engine-owned), on the current stream.
+
+        * fp16 storage: the first pass after the weights changed (`DRAM_B200_SAT_CHECK=first`, default; `always` /
+          `off`) runs with the library's saturation probe on and raises `ops.ActivationOverflow` if any convolution
+          output left the fp16 range (the epilogue clamps to +-65504 silently otherwise) — one 4-byte read-back.
+        * afterwards the sequence is one CUDA graph (captured on first use, `DRAM_B200_GRAPH=0` keeps eager
+          launches): every buffer the kernels touch is engine-owned and address-stable, so a replay is exact."""
+        if self._weights_epoch != self.model.weights_epoch:
+            self.refresh_weights()
+        mode = ops.sat_check_mode()
+        if self.act_dtype == torch.float16 and (
+                mode == "always" or (mode == "first" and self._sat_checked_epoch != self._weights_epoch)):
+            lib = ops._capi.load()
+            self._sat_counter.zero_()
+            ops.check(lib.dram_set_saturation_counter(ops._p(self._sat_counter)), "dram_set_saturation_counter")
+            try:
+                self._launch_steps()
+            finally:
+                lib.dram_set_saturation_counter(None)
+            clamped = int(self._sat_counter.item())
+            self.last_saturation_count = clamped
+            if clamped:
+                raise ops.ActivationOverflow(
+                    f"{clamped} 32-channel output groups exceeded the fp16 range (+-65504) and were clamped: this "
+                    "checkpoint/input needs bf16 storage (model.act_dtype = torch.bfloat16 or DRAM_B200_DTYPE=bf16)")
+            self._sat_checked_epoch = self._weights_epoch
+            return self.dense
+        if not ops.graphs_enabled() or torch.cuda.is_current_stream_capturing():
+            self._launch_steps()
+            return self.dense
+        if self._graph is None:
+            self._launch_steps()  # warm-up outside the capture (lazy function attributes, module loading)
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._launch_steps()
+            self._graph = graph
+        self._graph.replay()
+        return self.dense
+
+    def load_image(self, image):
+        """Copies fp32 [B,(1,)D,H,W] into the engine's input buffer (no-op when it already is that buffer)."""
+        img = image.reshape(self.batch, *self.dims)
+        if img.data_ptr() != self.image.data_ptr():
+            self.image.copy_(img)
+
     def run(self, image, lungs=None):
         """image: fp32 [B, D, H, W] (or [B,1,D,H,W]) on the device.  lungs: None, uint8/bool [B,D,H,W]
         or float [B,(1,)D,H,W].  Returns (dense list fp32 [B,C,d,h,w] — engine-owned buffers that the
         next run overwrites — and the pooled scores list)."""
-        if self._current_weight_version() != self._weight_version:
-            self.refresh_weights()
         B = self.batch
-        img = image.reshape(B, *self.dims)
-        if img.data_ptr() != self.image.data_ptr():
-            self.image.copy_(img)
-        for st in self.steps:
-            st.fn()
+        self.load_image(image)
+        self.run_network()
         mask = None
         if lungs is not None:
             mask = lungs.reshape(B, *lungs.shape[-3:])

@@ -118,6 +118,22 @@ class _Med3DSegNet(nn.Module):
         self._engines = {}
         # 16-bit storage type of activations/weights: None -> ops.default_act_dtype() (env DRAM_B200_DTYPE)
         self.act_dtype = None
+        # Bumped whenever the parameters may have changed; engines re-fold BatchNorm and re-pack their operands when
+        # it differs from the value they packed at.  Covered automatically: load_state_dict (post hook), .to()/.half()
+        # (_apply rebuilds the engines), train() <-> eval() transitions (a training step edits parameters in place).
+        # NOT seen: in-place edits of parameters while the module stays in eval mode (`p.data.mul_(...)`,
+        # `p.copy_(...)`): call mark_weights_changed() after those.
+        self.weights_epoch = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.mark_weights_changed())
+
+    def mark_weights_changed(self):
+        """Tell the cached engines that parameters/buffers were edited in place (see weights_epoch)."""
+        self.weights_epoch += 1
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self.weights_epoch += 1
+        return super().train(mode)
 
     def get_target_layer(self):
         return self.us3

@@ -267,7 +267,8 @@ class ScanRegLightningModule(_ScanModule):
                                    "classification one; use ScanCLSLightningModule for med3d/med3d18/med3d50")
             B, D, H, W = image.shape
             eng = self.model.eval().engine(B, (D, H, W), image.device)
-            dense, _ = eng.run(image, lungs)
+            eng.load_image(image)
+            dense = eng.run_network()  # the lobe-masked means of forward() are not used here (quirk Q2): no K6
             cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
                                                    per_sample_denominator=self.per_sample_percentage)
             return {
@@ -292,7 +293,7 @@ class ScanRegLightningModule(_ScanModule):
             for b in range(B):  # statistics are per volume (intensity_transforms.py:104-114)
                 ops.window_standardize(hu[b], out=eng.image[b])
             lungs, ess = _as_u8(lung_mask), _as_u8(ess_mask)
-            dense, _ = eng.run(eng.image, lungs)
+            dense = eng.run_network()
             cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
                                                    per_sample_denominator=self.per_sample_percentage)
             return {"cle_dense_outs": cle, "pse_dense_outs": pse, "cle_precentages": pct[0],

@@ -30,6 +30,23 @@ def default_act_dtype():
     raise ValueError(f"DRAM_B200_DTYPE={name!r}: expected fp16 or bf16")
 
 
+class ActivationOverflow(RuntimeError):
+    """A convolution output left the finite fp16 range and was clamped (see dram_set_saturation_counter)."""
+
+
+def sat_check_mode():
+    """env DRAM_B200_SAT_CHECK = first (default: probe the first forward after every weight change) | always | off."""
+    mode = os.environ.get("DRAM_B200_SAT_CHECK", "first").lower()
+    if mode not in ("first", "always", "off"):
+        raise ValueError(f"DRAM_B200_SAT_CHECK={mode!r}: expected first, always or off")
+    return mode
+
+
+def graphs_enabled():
+    """env DRAM_B200_GRAPH = 1 (default: the engine replays its launch sequence as one CUDA graph) | 0 (eager)."""
+    return os.environ.get("DRAM_B200_GRAPH", "1").lower() not in ("0", "off", "false", "no")
+
+
 def _need16(t, name, ndim=None):
     if isinstance(t, torch.Tensor) and t.dtype not in ACT_DTYPES:
         raise TypeError(f"{name}: expected bfloat16 or float16, got {t.dtype}")

@@ -62,16 +62,49 @@ def build_parser():
     p.add_argument("--output_path", default="/output", type=str)
     p.add_argument("--local_rank", default=0, type=int, help="not used; kept for compatibility")
     p.add_argument("--ckpt_path", default="best.ckpt", type=str, help="Lightning checkpoint (state_dict under 'state_dict')")
+    p.add_argument("--allow_random_init", action="store_true",
+                   help="tests/benchmarks only: run with random-init weights when the checkpoint is missing or a Git-LFS "
+                        "pointer (recorded in every result's error_messages); without it that is a fatal error")
     return p
 
 
-def load_checkpoint(module, path):
-    """processor.py:85-87.  The reference checkout ships Git-LFS pointers; those (and a missing file)
-    leave the random initialisation in place with a loud warning instead of crashing in torch.load."""
+class CheckpointError(RuntimeError):
+    """The checkpoint the predictions depend on could not be loaded."""
+
+
+RANDOM_INIT_NOTE = "checkpoint missing: predictions come from RANDOM-INIT weights (--allow_random_init)"
+
+
+def _read_checkpoint(path):
+    """A reference checkpoint is what Lightning's ModelCheckpoint wrote under torch 1.12: besides `state_dict` it holds
+    `hyper_parameters = {'args': argparse.Namespace(...)}` (models.py:166 `save_hyperparameters()`), callback and
+    optimiser states.  torch >= 2.6 defaults to `weights_only=True`, which rejects the Namespace: allow-list it, and fall
+    back to the full unpickler (what processor.py:85 of the reference does) for anything else in this trusted file."""
+    import argparse
+    import pickle
+
+    try:
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            return torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError as exc:
+        logging.warning(f"checkpoint '{path}' needs the full unpickler ({str(exc).splitlines()[0]}); it ships with the "
+                        "model and is trusted")
+        return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def load_checkpoint(module, path, allow_random_init=False):
+    """processor.py:85-87.  The reference checkout ships Git-LFS pointers; a pointer or a missing file is a fatal
+    `CheckpointError` (the reference's torch.load fails there too) unless `allow_random_init` — then the random
+    initialisation stays, False is returned and the caller records it in every result."""
     if not os.path.isfile(path) or os.path.getsize(path) < 4096:
-        logging.error(f"checkpoint '{path}' is missing or a Git-LFS pointer: running with random-init weights")
+        msg = (f"checkpoint '{os.path.abspath(path)}' is missing or a Git-LFS pointer (the default 'best.ckpt' is relative "
+               "to the working directory)")
+        if not allow_random_init:
+            raise CheckpointError(msg + "; refusing to write scores from random-init weights "
+                                        "(--allow_random_init overrides, for tests and benchmarks)")
+        logging.error(msg + ": running with random-init weights")
         return False
-    ckpt = torch.load(path, map_location="cpu")
+    ckpt = _read_checkpoint(path)
     load_state_dict_greedy(module, ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
     return True
 
@@ -124,7 +157,7 @@ def run_rank(args, rank, world_size):
     args.device = device
     is_reg = "dram" in args.model_arch  # the split train.py:72 / test.py:62 make
     module = (ScanRegLightningModule if is_reg else ScanCLSLightningModule)(args)
-    load_checkpoint(module, args.ckpt_path)
+    loaded = load_checkpoint(module, args.ckpt_path, allow_random_init=bool(getattr(args, "allow_random_init", False)))
     module = module.to(device).eval()
     data_module = SubtypeDataModule(args)
     out_cle = f"{args.output_path}/images/centrilobular-emphysema-heatmap/"
@@ -140,6 +173,9 @@ def run_rank(args, rank, world_size):
                 records += postprocess_reg(pred, data_module, out_cle, out_pse, writer if workers > 0 else None)
             else:
                 records += postprocess_cls(pred)
+    if not loaded:
+        for r in records:
+            r["error_messages"].append(RANDOM_INIT_NOTE)
     return records
 
 

@@ -480,7 +480,10 @@ class TrainStep:
                 self.buckets.reduce_bucket(i, self.group)
         self.buckets.wait()
         self.opt.step()
-        # the kernels changed the parameters behind autograd's back: bump the version counters (the inference engine
-        # re-packs its weights when they move, engine.Med3DEngine._current_weight_version)
+        # the kernels changed the parameters behind autograd's back: bump the version counters, and tell the
+        # inference engines of the module to re-pack (med3d._Med3DSegNet.weights_epoch)
         torch.autograd.graph.increment_version([p for _, p in self.params])
+        mark = getattr(self.net.model if hasattr(self.net, "model") else self.net, "mark_weights_changed", None)
+        if mark is not None:
+            mark()
         return loss.detach()

@@ -18,8 +18,9 @@
  *     scores are fp32 NCDHW exactly as the reference returns them;
  *   - return value: 0 = DRAM_OK, negative = DRAM_E_*; a message for the last
  *     failure on the calling thread is available from dram_last_error();
- *   - re-entrant; the only global state is the per-thread error string and
- *     the lazily resolved driver entry point for tensor-map encoding.
+ *   - re-entrant; the only global state is per-thread (the error string and
+ *     the optional saturation counter) plus the lazily resolved driver entry
+ *     point for tensor-map encoding.
  */
 #ifndef DRAM_B200_H_
 #define DRAM_B200_H_
@@ -37,7 +38,7 @@ extern "C" {
 #define DRAM_E_LAUNCH (-3)  /* CUDA launch / runtime error                  */
 #define DRAM_E_DRIVER (-4)  /* cuTensorMapEncodeTiled unavailable / failed  */
 
-#define DRAM_ABI_VERSION 4
+#define DRAM_ABI_VERSION 5
 
 /* 16-bit storage type of activations and packed weights (same layout, same tensor-core rate). */
 #define DRAM_DTYPE_BF16 0
@@ -58,6 +59,14 @@ int dram_version(void);
 int dram_last_error(char *buf, size_t len);
 /* Number of SMs of the current device (persistent-grid sizing). */
 int dram_sm_count(void);
+/* fp16 range probe.  With DRAM_DTYPE_F16 storage the convolution epilogues convert with a saturating
+ * cvt (values beyond +-65504 are clamped, never inf).  While a device counter (one uint32, zeroed by the
+ * caller) is registered for the calling thread, every convolution launched from that thread (dram_conv3d_run,
+ * dram_stem_conv7) adds the number of 32-channel output groups that were clamped (or NaN).  NULL (the default)
+ * switches the probe off; the pointer is thread-local state like the error string and is read at launch time,
+ * so a CUDA-graph capture taken while it is NULL contains no probe.  Replaces nothing in the reference: its
+ * fp32 activations (med3d.py:369-388) cannot overflow; this is the guard for the 16-bit storage choice. */
+int dram_set_saturation_counter(void *counter_u32);
 
 /* ---- K1: conv3d implicit GEMM on tcgen05/TMEM, fed by TMA -------------- */
 /*

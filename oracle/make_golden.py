@@ -77,6 +77,39 @@ def gen_forward(ref):
         print(name, [tuple(d.shape) for d in dense], [s.flatten().tolist()[:3] for s in scores])
 
 
+# (arch, dims): the reference's OWN initialisation (med3d.py:334-339: kaiming-normal fan_out convolutions, BatchNorm
+# weight 1 / bias 0 and default running statistics, PyTorch-default conv biases) under torch.manual_seed(REF_INIT_SEED).
+# dram_b200.med3d draws the same random stream (module construction order and init calls are the same), so the GPU
+# test rebuilds these weights from the seed alone; `weight_checksum` guards that.
+REF_INIT_SEED = 20261018
+REF_INIT_CASES = [("med3d", (32, 32, 32)), ("med3d18", (32, 32, 32)), ("med3d50", (24, 32, 32)),
+                  ("med3ddram", (32, 32, 32)), ("med3ddram18", (32, 40, 48)), ("med3ddram50", (32, 32, 32))]
+
+
+def gen_reference_init(ref):
+    for arch, dims in REF_INIT_CASES:
+        torch.manual_seed(REF_INIT_SEED)
+        model = ref_shim.model(arch)
+        sd = model.state_dict()
+        x, lung, _ = batch_inputs(1, dims)
+        logits, acts = [], {}
+        hooks = [fc.register_forward_hook(lambda mod, i, o: logits.append(o.detach().clone())) for fc in model.fcs]
+        for n, mod in model.named_modules():
+            if isinstance(mod, torch.nn.Conv3d):
+                hooks.append(mod.register_forward_hook(lambda mod, i, o, n=n: acts.__setitem__(n, float(o.abs().max()))))
+        with torch.no_grad():
+            dense, scores = model(x.unsqueeze(1).clone(), lung.unsqueeze(1).float())
+        for h in hooks:
+            h.remove()
+        fix = {"arch": arch, "dims": dims, "batch": 1, "with_lungs": True, "init_seed": REF_INIT_SEED,
+               "weight_checksum": synthetic.state_dict_checksum(sd),
+               "dense_outs": [d.clone() for d in dense], "scores": [s.clone() for s in scores],
+               "logits": logits, "max_conv_output": max(acts.values())}
+        torch.save(fix, os.path.join(GOLDEN, f"refinit_{arch}.pt"))
+        print("refinit", arch, dims, "max |conv out|", fix["max_conv_output"], "logit absmax",
+              [float(l.abs().max()) for l in logits], "scores", [sc.flatten().tolist()[:3] for sc in scores])
+
+
 def gen_predict_step(ref):
     from argparse import Namespace
 
@@ -232,7 +265,7 @@ def main():
     torch.manual_seed(0)
     ref = ref_shim.load()
     steps = {"layouts": gen_layouts, "forward": gen_forward, "predict": gen_predict_step,
-             "transforms": gen_transforms, "labels": gen_labels, "train": gen_train_step}
+             "transforms": gen_transforms, "labels": gen_labels, "train": gen_train_step, "refinit": gen_reference_init}
     for name, fn in steps.items():
         if not args.only or name in args.only.split(","):
             fn(ref)

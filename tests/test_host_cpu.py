@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(_capi.SIGNATURES), (declared ^ set(_capi.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/dram_b200.h but not exported"
-    assert lib.dram_version() == 4
+    assert lib.dram_version() == 5
 
 
 def test_argument_validation_without_gpu(lib):
@@ -118,6 +118,39 @@ def test_get_model_by_name_and_greedy_load(tmp_path):
     module = ScanRegLightningModule(Namespace(model_arch="med3ddram18"))
     utils.load_state_dict_greedy(module, {"model." + k: v for k, v in sd.items()})
     assert float(module.model.layer1[0].conv1.weight.mean()) == 0.5
+
+
+def test_checkpoint_loading_policy(tmp_path):
+    """A Lightning-shaped checkpoint (hyper_parameters Namespace, callbacks, optimizer states — what ModelCheckpoint of
+    the reference's train.py writes) loads under torch >= 2.6; a missing file or a Git-LFS pointer is fatal unless
+    --allow_random_init."""
+    from argparse import Namespace
+
+    from dram_b200 import processor
+    from dram_b200.models import ScanRegLightningModule
+
+    module = ScanRegLightningModule(Namespace(model_arch="med3ddram18"))
+    sd = {"model." + k: (torch.full_like(v, 0.25) if v.is_floating_point() else v)
+          for k, v in module.model.state_dict().items()}
+    ckpt = {"epoch": 7, "global_step": 1234, "pytorch-lightning_version": "1.6.4", "state_dict": sd,
+            "hyper_parameters": {"args": Namespace(model_arch="med3ddram18", lr=1e-4, target_size=(128, 224, 288))},
+            "callbacks": {"ModelCheckpoint{'monitor': 'valid_acc'}": {"best_model_score": torch.tensor(0.5)}},
+            "optimizer_states": [{"state": {}, "param_groups": [{"lr": 1e-4}]}], "lr_schedulers": [{"gamma": 0.95}]}
+    path = tmp_path / "best.ckpt"
+    torch.save(ckpt, path)
+    assert processor.load_checkpoint(module, str(path)) is True
+    assert float(module.model.layer1[0].conv1.weight.mean()) == 0.25
+    # something only the full unpickler accepts (a numpy scalar pickled by an old Lightning): still loads
+    ckpt["callbacks"]["x"] = np.float64(1.0)
+    torch.save(ckpt, path)
+    assert processor.load_checkpoint(module, str(path)) is True
+    pointer = tmp_path / "paper.ckpt"
+    pointer.write_text("version https://git-lfs.github.com/spec/v1\noid sha256:0\nsize 1\n")
+    for bad in (str(pointer), str(tmp_path / "absent.ckpt")):
+        with pytest.raises(processor.CheckpointError):
+            processor.load_checkpoint(module, bad)
+        assert processor.load_checkpoint(module, bad, allow_random_init=True) is False
+    assert processor.build_parser().parse_args([]).allow_random_init is False
 
 
 def test_shard_indices_equal_distributed_sampler():

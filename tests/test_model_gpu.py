@@ -27,6 +27,9 @@ def build_model(arch, sd, device, dtype=None):
     return model.to(device).eval()
 
 
+REFINIT_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "refinit_*.pt")))
+
+
 def report(got, ref):
     err = (got - ref).abs().flatten()
     k = max(1, int(err.numel() * 0.999))
@@ -52,7 +55,11 @@ def check_outputs(arch, dense, scores, dense_ref, scores_ref):
         # sample's logit vector (a logit that happens to be ~0 has no meaningful relative error of its own).
         den = ref.abs().clamp_min(1e-3) if head == "reg" else ref.abs().amax(-1, keepdim=True).clamp_min(0.25)
         rel = ((got - ref).abs() / den).max().item()
-        print(f"{arch} score[{k}]: got {got.flatten().tolist()[:6]} ref {ref.flatten().tolist()[:6]} rel {rel:.3g}")
+        # the plain element-wise relative error, reported beside it (DESIGN.md section 6 states the deviation: a class
+        # logit that happens to lie near zero has an unbounded element-wise relative error at any precision)
+        plain = ((got - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+        print(f"{arch} score[{k}]: got {got.flatten().tolist()[:6]} ref {ref.flatten().tolist()[:6]} rel {rel:.3g} "
+              f"(element-wise relative {plain:.3g})")
         assert rel <= 1e-2, f"{arch} score[{k}] rel err {rel}"
         if head == "cls":
             assert torch.equal(got.argmax(-1), ref.argmax(-1)), f"{arch}: argmax class differs"
@@ -118,3 +125,108 @@ def test_forward_rejects_unsupported_use(cuda, lib):
         # 36 -> 18 -> 9 -> 5: the up-sampled map (10) is larger than its skip tensor (9); the reference's torch.cat
         # fails for such sizes too
         model.eval()(torch.zeros(1, 1, 36, 32, 32, device=cuda))
+
+
+@pytest.mark.parametrize("path", REFINIT_FIXTURES, ids=[os.path.basename(p)[:-3] for p in REFINIT_FIXTURES])
+def test_reference_init_weights_match_reference_golden(cuda, lib, path, monkeypatch):
+    """north_star: "random-init weights otherwise" — the reference's own initialisation (med3d.py:334-339), rebuilt
+    from the seed (same random stream as the reference, pinned on CPU by test_oracle_cpu), with the fp16 saturation
+    probe on for every pass.  This initialisation gives class logits / pre-sigmoid values of +-15 ... +-160, so the
+    sigmoid maps sit at 0/1 almost everywhere and a voxel near a zero crossing turns any 16-bit rounding into an O(1)
+    map difference; the errors are therefore asserted on the logit scale (2e-2 of the largest |logit|, the same 2e-2
+    as the dRAM bar) and the sigmoid-map statistics are printed."""
+    from dram_b200 import utils
+
+    monkeypatch.setenv("DRAM_B200_SAT_CHECK", "always")
+    fix = torch.load(path)
+    arch, dims = fix["arch"], tuple(fix["dims"])
+    torch.manual_seed(fix["init_seed"])
+    model = utils.get_model_by_name(arch)
+    sd = model.state_dict()
+    assert abs(synthetic.state_dict_checksum(sd) - fix["weight_checksum"]) <= 1e-9 * abs(fix["weight_checksum"])
+    model = model.to(cuda).eval()
+    x, lung, _ = synthetic.make_network_input(0, dims)
+    dense, scores = model(x[None, None].to(cuda), lung[None, None].float().to(cuda))
+    eng = model.engine(1, dims, cuda)
+    assert eng.act_dtype == torch.float16 and eng.last_saturation_count == 0   # nothing was clamped to +-65504
+    head = M.ARCHS[arch][2]
+    for k, (got, ref, logit_ref) in enumerate(zip(dense, fix["dense_outs"], fix["logits"])):
+        got = got.float().cpu()
+        scale = logit_ref.abs().max().item()
+        if head == "cls":
+            err = (got - ref).abs()
+        else:  # compare on the logit scale where neither side is saturated in fp32
+            ok = (ref > 1e-6) & (ref < 1 - 1e-6) & (got > 1e-6) & (got < 1 - 1e-6)
+            err = (torch.logit(got.double()) - torch.logit(ref.double())).abs()[ok].float()
+            both_sat = ((ref <= 1e-6) & (got <= 1e-5)) | ((ref >= 1 - 1e-6) & (got >= 1 - 1e-5))
+            assert bool((ok | both_sat).all()), f"{arch} map {k}: saturated on one side only"
+        print(f"{arch} refinit dense[{k}]: logit absmax {scale:.4g}, logit err max {err.max().item():.4g} "
+              f"mean {err.mean().item():.4g} (= {err.max().item() / scale:.3g} of the scale); sigmoid/out map " + report(got, ref))
+        assert err.max().item() <= 2e-2 * scale, (arch, k, err.max().item(), scale)
+    for k, (got, ref) in enumerate(zip(scores, fix["scores"])):
+        got = got.float().cpu()
+        if head == "cls":
+            den = ref.abs().amax(-1, keepdim=True)
+            assert torch.equal(got.argmax(-1), ref.argmax(-1)), f"{arch}: argmax class differs"
+        else:
+            den = ref.abs().clamp_min(1e-3)
+        rel = ((got - ref).abs() / den).max().item()
+        print(f"{arch} refinit score[{k}]: got {got.flatten().tolist()} ref {ref.flatten().tolist()} rel {rel:.3g}")
+        assert rel <= 1e-2, (arch, k, rel)
+
+
+def test_fp16_saturation_is_detected_not_silent(cuda, lib, monkeypatch):
+    """fp16 storage clamps at +-65504 in the epilogue (cvt.rn.satfinite); the probe turns that into an error on the
+    first forward after a weight change, bf16 storage runs the same weights, and the check is repeated after
+    load_state_dict."""
+    from dram_b200 import ops
+
+    arch, dims = "med3ddram18", (32, 32, 32)
+    sd = synthetic.make_state_dict(arch, seed=3, calib_dims=dims)
+    hot = dict(sd)
+    hot["layer2.0.bn1.weight"] = sd["layer2.0.bn1.weight"] * 3.0e5   # pushes layer2.0.conv1's output beyond 65504
+    x, lung, _ = synthetic.make_network_input(0, dims)
+    x = x[None, None].to(cuda)
+    model = build_model(arch, hot, cuda, torch.float16)
+    with pytest.raises(ops.ActivationOverflow):
+        model(x, None)
+    with pytest.raises(ops.ActivationOverflow):   # still unchecked-clean: the next call probes again
+        model(x, None)
+    model.act_dtype = torch.bfloat16               # the documented way out
+    d_bf, _ = model(x, None)
+    assert all(bool(torch.isfinite(d).all()) for d in d_bf)
+    model.act_dtype = torch.float16
+    model.load_state_dict(sd)                      # sane weights: the same engine re-packs, re-probes, passes
+    d_ref, s_ref = M.forward(sd, arch, x.cpu(), None)
+    dense, scores = model(x, None)
+    check_outputs(arch, dense, scores, d_ref, s_ref)
+    eng = model.engine(1, dims, cuda)
+    assert eng.last_saturation_count == 0
+    monkeypatch.setenv("DRAM_B200_SAT_CHECK", "off")
+    model.load_state_dict(hot)
+    model(x, None)                                 # probe off: clamps silently (round-1 behaviour), by explicit choice
+
+
+def test_cuda_graph_replay_equals_eager_launches(cuda, lib, monkeypatch):
+    """The engine replays its launch sequence as one CUDA graph after the first (probed, eager) pass: results are
+    bit-identical to eager launches, follow a new input and a load_state_dict, and DRAM_B200_GRAPH=0 keeps eager."""
+    arch, dims = "med3ddram18", (32, 40, 48)
+    sd = synthetic.make_state_dict(arch, seed=8, calib_dims=dims)
+    xs = [synthetic.make_network_input(30 + i, dims)[0][None, None].to(cuda) for i in range(2)]
+    lung = synthetic.make_network_input(30, dims)[1][None, None].to(cuda)
+    monkeypatch.setenv("DRAM_B200_GRAPH", "0")
+    eager = build_model(arch, sd, cuda)
+    want = [[t.clone() for t in sum(eager(x, lung), [])] for x in xs]
+    assert eager.engine(1, dims, cuda)._graph is None
+    monkeypatch.setenv("DRAM_B200_GRAPH", "1")
+    model = build_model(arch, sd, cuda)
+    for rep in range(3):
+        for x, w in zip(xs, want):
+            got = sum(model(x, lung), [])
+            assert all(torch.equal(a, b) for a, b in zip(got, w)), rep
+    assert model.engine(1, dims, cuda)._graph is not None
+    sd2 = synthetic.make_state_dict(arch, seed=9, calib_dims=dims)
+    model.load_state_dict(sd2)
+    eager.load_state_dict(sd2)
+    for x in xs:
+        assert all(torch.equal(a, b) for a, b in zip(sum(model(x, lung), []), sum(eager(x, lung), [])))

@@ -52,6 +52,32 @@ def test_forward_oracle_matches_reference_golden(path):
             assert torch.equal(got.argmax(-1), ref.argmax(-1))
 
 
+REFINIT_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "refinit_*.pt")))
+
+
+@pytest.mark.parametrize("path", REFINIT_FIXTURES, ids=[os.path.basename(p)[:-3] for p in REFINIT_FIXTURES])
+def test_reference_init_fixture_is_reproducible_and_oracle_matches(path):
+    """The reference's OWN initialisation (med3d.py:334-339) under a fixed seed: the drop-in module draws the very
+    same weights (so the GPU test needs only the seed), and the oracle reproduces the reference's outputs on them —
+    including the large, saturating logits this initialisation produces."""
+    import dram_b200  # noqa: F401
+    from dram_b200.utils import get_model_by_name
+
+    fix = torch.load(path)
+    arch, dims = fix["arch"], tuple(fix["dims"])
+    torch.manual_seed(fix["init_seed"])
+    sd = get_model_by_name(arch).state_dict()
+    assert abs(synthetic.state_dict_checksum(sd) - fix["weight_checksum"]) <= 1e-9 * abs(fix["weight_checksum"]), \
+        "dram_b200.med3d no longer draws the reference's random-init weights from the same seed"
+    x, lung, _ = synthetic.make_network_input(0, dims)
+    dense, scores = M.forward(sd, arch, x[None, None], lung[None, None].float())
+    for got, ref in zip(dense, fix["dense_outs"]):
+        assert (got - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    for got, ref in zip(scores, fix["scores"]):
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+    assert fix["max_conv_output"] < 65504.0  # this initialisation stays inside the fp16 range (by a factor > 100)
+
+
 def test_predict_step_oracle_matches_reference_golden():
     fix = torch.load(os.path.join(GOLDEN, "predict_step_med3ddram18.pt"))
     dims, batch = tuple(fix["dims"]), fix["batch"]
