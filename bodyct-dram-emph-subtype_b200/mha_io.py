@@ -3,8 +3,11 @@
 
 A .mha file is an ASCII `Key = Value` header terminated by `ElementDataFile = LOCAL`, followed by the
 raw (optionally zlib-compressed) voxels with x fastest.  Arrays are returned/accepted as numpy
-[z, y, x]; spacing/origin are in ITK order (x, y, z) and the direction is the row-major 3x3
-TransformMatrix, exactly what sitk's GetSpacing/GetOrigin/GetDirection return.
+[z, y, x]; spacing/origin are in ITK order (x, y, z) and `direction` is the row-major 3x3 matrix sitk's
+GetDirection() returns.  In the file, MetaIO stores `TransformMatrix` row i = direction cosines of image axis i —
+the TRANSPOSE of that matrix (itkMetaImageIO.cxx) — so it is transposed on read and on write; header key order,
+`CompressedDataSize` and `AnatomicalOrientation` follow what ITK's writer emits (pinned by the hand-built ITK-layout
+fixtures tests/golden/itk_style_*.mha, oracle/make_mha_fixture.py).
 """
 import zlib
 from collections import deque
@@ -55,12 +58,20 @@ def read_mha(path):
     arr = np.frombuffer(data, dtype=dtype.newbyteorder(">" if msb else "<"), count=count)
     arr = arr.astype(dtype, copy=True).reshape(dims[2], dims[1], dims[0])
     floats = lambda key, default: tuple(float(v) for v in header.get(key, default).split())  # noqa: E731
+    t = floats("TransformMatrix", header.get("Rotation", header.get("Orientation", "1 0 0 0 1 0 0 0 1")))
     meta = {
         "spacing": floats("ElementSpacing", "1 1 1"),
         "origin": floats("Offset", header.get("Position", header.get("Origin", "0 0 0"))),
-        "direction": floats("TransformMatrix", header.get("Orientation", "1 0 0 0 1 0 0 0 1")),
+        "direction": _transpose3(t),
     }
     return arr, meta
+
+
+def _transpose3(m):
+    m = tuple(m)
+    if len(m) != 9:
+        raise ValueError(f"expected a 3x3 direction matrix, got {len(m)} values")
+    return (m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8])
 
 
 def write_mha(path, arr, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
@@ -80,8 +91,8 @@ def write_mha(path, arr, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
     if compress:
         lines.append(f"CompressedDataSize = {len(payload)}")
     lines += [
-        f"TransformMatrix = {fmt(direction)}", f"Offset = {fmt(origin)}", "CenterOfRotation = 0 0 0",
-        "AnatomicalOrientation = RAI", f"ElementSpacing = {fmt(spacing)}",
+        f"TransformMatrix = {fmt(_transpose3(float(v) for v in direction))}", f"Offset = {fmt(origin)}",
+        "CenterOfRotation = 0 0 0", "AnatomicalOrientation = RAI", f"ElementSpacing = {fmt(spacing)}",
         f"DimSize = {arr.shape[2]} {arr.shape[1]} {arr.shape[0]}", f"ElementType = {_NP_TO_MET[arr.dtype]}",
         "ElementDataFile = LOCAL",
     ]

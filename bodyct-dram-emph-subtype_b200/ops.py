@@ -2,8 +2,12 @@
 
 Each wrapper checks shapes/dtypes, allocates the output with torch's caching allocator, passes
 raw device pointers plus the current CUDA stream to libdram_b200.so and returns torch tensors.
-Stateless kernels are also registered as `torch.library` custom ops in the `dram_b200::`
-namespace so they show up in profiler traces and can be captured into CUDA graphs.
+The stateless kernel families are registered as `torch.library.custom_op`s in the `dram_b200::`
+namespace by `custom_ops.py` (imported at the bottom of this module): `torch.ops.dram_b200.conv3d`,
+`.stem_conv7`, `.maxpool3d`, `.upsample2x`, `.masked_pool`, `.dram_upsample_mask`, `.window_standardize`,
+`.resize_image`, `.resize_mask`, `.heatmap_u8`, each with a fake (shape-only) implementation.  The
+functions below are what those ops call; the engine calls them (and its frozen `Conv3dPlan`s) directly
+and replays the whole sequence as one CUDA graph.
 
 Activations are NDHWC 16-bit tensors of shape [N, D, H, W, C]: torch.bfloat16 or torch.float16
 (`ACT_DTYPES`; both run at the same tensor-core rate, fp16 carries 3 more mantissa bits).  There
@@ -529,3 +533,6 @@ def to_ncdhw_f32(x):
     check(_capi.load().dram_ndhwc_16_to_ncdhw_f32(_p(x), _p(out), n, c, d, h, w, ACT_DTYPES[x.dtype], _stream()),
           "dram_ndhwc_16_to_ncdhw_f32")
     return out
+
+
+from . import custom_ops  # noqa: E402,F401  (registers the dram_b200:: torch.library operators)

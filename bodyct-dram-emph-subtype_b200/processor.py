@@ -164,18 +164,27 @@ def run_rank(args, rank, world_size):
     out_pse = f"{args.output_path}/images/paraseptal-emphysema-heatmap/"
     Path(out_cle).mkdir(parents=True, exist_ok=True)
     Path(out_pse).mkdir(parents=True, exist_ok=True)
-    records = []
+    records, notes = [], []
     workers = int(getattr(args, "workers", 0) or 0)
     with mha_io.BackgroundWriter(workers) as writer:  # workers == 0: writes happen in place, as before
         for i, batch in enumerate(data_module.predict_dataloader(rank, world_size)):
-            pred = module.predict_step(batch, i)
+            try:
+                pred = module.predict_step(batch, i)
+            except ops.ActivationOverflow as exc:
+                # fp16 storage (more mantissa) cannot hold this checkpoint's activations:
+                # continue in bf16 (fp32's exponent range) and say so in every record
+                logging.error(f"{exc}; switching this run to bf16 storage")
+                module.model.act_dtype = torch.bfloat16
+                notes.append("fp16 activation overflow detected: run continued with bf16 storage (coarser dRAM values)")
+                pred = module.predict_step(batch, i)
             if is_reg:
                 records += postprocess_reg(pred, data_module, out_cle, out_pse, writer if workers > 0 else None)
             else:
                 records += postprocess_cls(pred)
     if not loaded:
-        for r in records:
-            r["error_messages"].append(RANDOM_INIT_NOTE)
+        notes.append(RANDOM_INIT_NOTE)
+    for r in records:
+        r["error_messages"] += notes
     return records
 
 

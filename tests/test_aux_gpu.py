@@ -167,3 +167,33 @@ def test_upsample2x_tensor_core(cuda, lib, dims, c, n, max_ctas, dt):
     # constants are reproduced to the rounding of the weights (rows of the interpolation matrix sum to one)
     ones = ops.Upsample2xPlan(torch.ones_like(xd)).run().float()
     assert (ones - 1.0).abs().max().item() <= 4 * ulp
+
+
+def test_torch_library_ops_run_capture_and_opcheck(cuda, lib):
+    """The dram_b200:: custom ops give the results of the ctypes wrappers, pass torch.library.opcheck (schema, fake
+    kernel, dispatch) and capture into a CUDA graph whose replay follows new input data."""
+    from dram_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((1, 16, 16, 24, 64), generator=g, device=cuda).half()
+    assert torch.equal(torch.ops.dram_b200.maxpool3d(x), ops.maxpool3d(x))
+    assert torch.equal(torch.ops.dram_b200.upsample2x(x), ops.upsample2x(x))
+    w = (torch.randn((64, 64, 3, 3, 3), generator=g, device=cuda) * 0.05)
+    packed, bias = ops.pack_conv_weight(w, dtype=torch.float16), torch.zeros(64, device=cuda)
+    y = torch.ops.dram_b200.conv3d(x, packed, bias)
+    ref = torch.relu(torch.nn.functional.conv3d(x.permute(0, 4, 1, 2, 3).float(), packed.float().view(64, 3, 3, 3, 64)
+                                                .permute(0, 4, 1, 2, 3), padding=1)).permute(0, 2, 3, 4, 1)
+    assert (y.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    torch.library.opcheck(torch.ops.dram_b200.maxpool3d.default, (x,))
+    torch.library.opcheck(torch.ops.dram_b200.conv3d.default, (x, packed, bias), {"dilation": 2})
+    # graph capture of dispatcher calls: static input, replay after the input changed
+    xs = x.clone()
+    torch.ops.dram_b200.conv3d(xs, packed, bias)  # warm-up (function attributes) outside the capture
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = torch.ops.dram_b200.maxpool3d(torch.ops.dram_b200.conv3d(xs, packed, bias))
+    xs.copy_(torch.randn(xs.shape, generator=g, device=cuda).half())
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ops.maxpool3d(torch.ops.dram_b200.conv3d(xs, packed, bias)))

@@ -153,6 +153,37 @@ def test_checkpoint_loading_policy(tmp_path):
     assert processor.build_parser().parse_args([]).allow_random_init is False
 
 
+def test_torch_library_ops_are_registered_with_fake_kernels():
+    """north_star: "a thin C-ABI torch custom-op extension" — the dram_b200:: namespace exists, every op has a
+    shape-only (fake) kernel so it traces without a GPU, and there is no CPU kernel behind it."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    from dram_b200 import custom_ops, ops  # noqa: F401
+
+    for name in custom_ops.REGISTERED:
+        assert hasattr(torch.ops.dram_b200, name), name
+    with FakeTensorMode():
+        x = torch.empty((2, 8, 10, 12, 64), dtype=torch.float16, device="cuda")
+        assert torch.ops.dram_b200.maxpool3d(x).shape == (2, 4, 5, 6, 64)
+        assert torch.ops.dram_b200.upsample2x(x).shape == (2, 16, 20, 24, 64)
+        w, b = torch.empty((128, 27 * 64), dtype=torch.float16, device="cuda"), torch.empty(128, device="cuda")
+        assert torch.ops.dram_b200.conv3d(x, w, b, stride=2).shape == (2, 4, 5, 6, 128)
+        assert torch.ops.dram_b200.conv3d(x, w, b, dilation=4).shape == (2, 8, 10, 12, 128)
+        img = torch.empty((2, 31, 32, 40), device="cuda")
+        sw = torch.empty(28672, dtype=torch.float16, device="cuda")
+        assert torch.ops.dram_b200.stem_conv7(img, sw, torch.empty(64, device="cuda")).shape == (2, 16, 16, 20, 64)
+        d0 = torch.empty((2, 1, 16, 16, 20), device="cuda")
+        m = torch.empty((2, 31, 32, 40), dtype=torch.uint8, device="cuda")
+        o0, o1, pct = torch.ops.dram_b200.dram_upsample_mask(d0, d0, m, m)
+        assert o0.shape == (2, 1, 31, 32, 40) and pct.shape == (2, 2)
+        assert torch.ops.dram_b200.masked_pool(d0, m).shape == (2, 1)
+        out, stats = torch.ops.dram_b200.window_standardize(torch.empty((31, 32, 40), dtype=torch.int16, device="cuda"))
+        assert out.dtype == torch.float32 and out.shape == (31, 32, 40) and stats.shape == (2,)
+        assert torch.ops.dram_b200.heatmap_u8(d0[0, 0], [1, 30, 2, 31, 3, 39], [40, 48, 56]).dtype == torch.uint8
+    with pytest.raises(NotImplementedError):
+        torch.ops.dram_b200.maxpool3d(torch.zeros(1, 8, 8, 8, 64, dtype=torch.float16))
+
+
 def test_shard_indices_equal_distributed_sampler():
     from torch.utils.data import DistributedSampler
 
@@ -177,6 +208,40 @@ def test_mha_roundtrip(tmp_path):
         assert back.dtype == arr.dtype and np.array_equal(back, arr)
         assert meta["spacing"] == (0.7, 0.7, 1.25) and meta["origin"] == (-10.0, 3.5, 8.0)
         assert meta["direction"] == (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+
+
+def test_mha_reader_on_itk_layout_fixtures(tmp_path):
+    """Files laid out the way ITK's MetaImageIO writes them (key order, CompressedDataSize, 17-digit doubles,
+    TransformMatrix = transposed direction, MSB flag) — built by oracle/make_mha_fixture.py without mha_io — read back
+    as sitk.ReadImage + GetArrayFromImage / GetSpacing / GetOrigin / GetDirection would report them
+    (dataset.py:49-55), and survive the reference's reversed-rows bookkeeping and our writer."""
+    from dram_b200 import mha_io
+
+    with open(os.path.join(GOLDEN, "itk_style_mha.json")) as f:
+        expect = json.load(f)
+    for name, e in expect.items():
+        arr, meta = mha_io.read_mha(os.path.join(GOLDEN, name + ".mha"))
+        nx, ny, nz = e["dims_xyz"]
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        want = ((x * 37 + y * 101 + z * 977) % 4096 - 1024).astype(np.int16) if e["kind"] == "int16" \
+            else ((x * 7 + y * 13 + z * 29) % 6).astype(np.uint8)
+        assert arr.shape == (nz, ny, nx) and arr.dtype == want.dtype and np.array_equal(arr, want), name
+        assert meta["spacing"] == tuple(e["spacing"]) and meta["origin"] == tuple(e["origin"]), name
+        assert np.allclose(meta["direction"], e["direction"], rtol=0, atol=1e-15), name
+        # dataset.py:51-53 reverses to z-y-x, processor.py:146-158 reverses back before writing
+        rev = np.asarray(meta["direction"]).reshape(3, 3)[::-1].flatten().tolist()
+        back = np.asarray(rev).reshape(3, 3)[::-1].flatten().tolist()
+        out = str(tmp_path / (name + "_copy.mha"))
+        mha_io.write_mha(out, arr, spacing=meta["spacing"], origin=meta["origin"], direction=back)
+        arr2, meta2 = mha_io.read_mha(out)
+        assert np.array_equal(arr2, arr) and meta2 == meta, name
+    # the header our writer emits has ITK's keys in ITK's order
+    with open(out, "rb") as f:
+        head = f.read().split(b"ElementDataFile")[0].decode("ascii")
+    with open(os.path.join(GOLDEN, "itk_style_ct_oblique.mha"), "rb") as f:
+        itk_head = f.read().split(b"ElementDataFile")[0].decode("ascii")
+    keys = lambda text: [ln.split("=")[0].strip() for ln in text.strip().splitlines()]  # noqa: E731
+    assert [k for k in keys(itk_head)] == [k for k in keys(head)] + ([] if "CompressedDataSize" in head else [])
 
 
 def test_labels_and_result_merging(tmp_path):

@@ -140,6 +140,51 @@ def test_processor_end_to_end(cuda, lib, tmp_path, workers):
     assert os.path.isfile(out_dir / "araseptal-emphysema-score.json") and os.path.isfile(out_dir / "results.json")
 
 
+def test_processor_c1_med3d18_128cube(cuda, lib, tmp_path):
+    """BASELINE config 1: `processor.py --model_arch med3d18` on one synthetic 128^3-sized CT + lobe mask.  The
+    reference's processor always builds ScanRegLightningModule and breaks in post-processing on a classification
+    architecture (quirk Q4, processor.py:83, 112-122); ours routes med3d* to ScanCLSLightningModule like
+    train.py:72 / test.py:62 and reports the argmax classes (models.py:245-247).  Checked against the oracle:
+    transforms (crop, window, standardise, resize to 128^3) + reference network on CPU.  The checkpoint is a
+    Lightning-shaped file (hyper_parameters Namespace, callbacks)."""
+    from oracle import med3d_oracle as M
+
+    from dram_b200 import mha_io, processor
+
+    arch, scan_dims, target = "med3d18", (140, 150, 160), (128, 128, 128)
+    scan_dir, lobe_dir, out_dir = tmp_path / "ct", tmp_path / "lobes", tmp_path / "out"
+    scan_dir.mkdir()
+    lobe_dir.mkdir()
+    ct, lobes = synthetic.make_volume(77, scan_dims)
+    for folder, arr in ((scan_dir, ct), (lobe_dir, lobes)):
+        mha_io.write_mha(str(folder / "case.mha"), arr.numpy(), spacing=(0.8, 0.8, 1.0), origin=(0.0, 0.0, 0.0))
+    sd = synthetic.make_state_dict(arch, seed=3, calib_dims=(64, 64, 64), prefix="model.")
+    ckpt = tmp_path / "best.ckpt"
+    torch.save({"state_dict": sd, "epoch": 3, "hyper_parameters": {"args": Namespace(model_arch=arch, lr=1e-4)},
+                "callbacks": {}, "optimizer_states": []}, ckpt)
+    argv = ["--scan_path", str(scan_dir), "--lobe_path", str(lobe_dir), "--output_path", str(out_dir),
+            "--model_arch", arch, "--target_size", "128,128,128", "--batch_size", "1", "--ckpt_path", str(ckpt)]
+    records = processor.run_testing_job(argv)
+    assert [r["entity"] for r in records] == ["case"] and records[0]["error_messages"] == []
+    # oracle: spacing is given z-y-x to the crop (dataset.py:51, 72): mha spacing (x,y,z) reversed
+    sample = P.inference_transform(P.lung_crop_sample(ct.numpy(), lobes.numpy(), spacing=(1.0, 0.8, 0.8), crop_border=5,
+                                                      uid="case"), target)
+    plain = {k[len("model."):]: v for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, logits = M.forward(plain, arch, sample["image"][None, None])
+    m = records[0]["metrics"]
+    assert int(m["cle_severity_score"]) == int(logits[0].argmax(-1)) and 0 <= int(m["cle_severity_score"]) <= 5
+    assert int(m["pse_severity_score"]) == int(logits[1].argmax(-1)) and 0 <= int(m["pse_severity_score"]) <= 2
+    first = json.load(open(out_dir / "centrilobular-emphysema-score.json"))
+    assert first["score"] == int(m["cle_severity_score"])
+    assert os.path.isfile(out_dir / "araseptal-emphysema-score.json") and os.path.isfile(out_dir / "results.json")
+    # a missing checkpoint is fatal, unless explicitly allowed — and then every record says so
+    with pytest.raises(processor.CheckpointError):
+        processor.run_testing_job(argv[:-1] + [str(tmp_path / "absent.ckpt")])
+    records = processor.run_testing_job(argv[:-1] + [str(tmp_path / "absent.ckpt"), "--allow_random_init"])
+    assert records[0]["error_messages"] == [processor.RANDOM_INIT_NOTE]
+
+
 @pytest.mark.parametrize("shape,streams", [((2, 8, 16, 16), 4), ((2, 67, 250, 256), 4), ((2, 67, 250, 256), 1)])
 def test_device_prefetcher_delivers_every_batch_intact(cuda, lib, shape, streams):
     """The double-buffered host->device staging of the predict loop: contents, order, pass-through keys — for small
