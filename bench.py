@@ -516,7 +516,7 @@ def main():
     clocks = sampler.stop(skip=first_sample) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    launches_per_step = eng.launches_per_run() + 3 * B + 2  # K8: 3 kernels per volume; K7: kernel + finalize
+    launches_per_step = len(eng.steps) + 2 + 2  # K8 statistics + finalize; the recorded steps (int16-HU stem first); K7 + finalize
 
     # ---- end to end through the public predict_step with pinned host buffers -----------------
     win = eng.image.detach().cpu()  # the standardised fp32 volumes predict_step receives from the transforms

@@ -61,6 +61,8 @@ SIGNATURES = {
     "dram_stem_expand": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_stem_weight_bytes": (_sz, []),
     "dram_stem_conv7": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "dram_stem_conv7_hu": (C.c_int, [_vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
+                                     _i32, _vp]),
     "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_upsample2x_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
@@ -73,6 +75,9 @@ SIGNATURES = {
                                           _i32, _i32, _i32, _i32, _vp]),
     "dram_preprocess_workspace_bytes": (_sz, []),
     "dram_window_standardize": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, _vp]),
+    "dram_preprocess_workspace_bytes_n": (_sz, [_i32]),
+    "dram_window_standardize_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_float, C.c_float, _vp]),
+    "dram_window_stats": (C.c_int, [_vp, _vp, _vp, _i32, _i64, C.c_float, C.c_float, _vp]),
     "dram_resize_image": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_resize_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_mask_bbox": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

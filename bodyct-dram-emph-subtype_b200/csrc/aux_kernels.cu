@@ -4,6 +4,8 @@
 // shared memory beyond what L1/L2 already give (each input element is touched by <= 27
 // neighbouring outputs that sit in the same or the adjacent CTA).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 
@@ -402,6 +404,175 @@ dram_upsample_mask_kernel(const float *__restrict__ dense0, const float *__restr
   double accl = block_sum((double)lung_count, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[2 * n + b], accl);
 }
+
+// ---------------------------------------------------------------------------------------
+// K7, staged variant (the default): a CTA owns RH consecutive output rows of one output plane (b, xd, xh0..).
+//   1. every thread loads the 16-voxel mask segments it owns (uint4 of ess + uint4 of lungs: 32 B in flight per
+//      thread) — the dRAM is zero outside `ess`, which is ~2 % of a chest volume, so the kernel is a masked fill:
+//      what bounds it is bytes in flight, not arithmetic;
+//   2. if any voxel of the CTA's rows lies in `ess`, the half-resolution source brick those rows interpolate from
+//      (2 planes x (RH/2 + 2) rows x w floats x 2 maps, <= 96*w bytes) is staged in shared memory with coalesced
+//      16-byte loads, and the 2 x 8 gathers per voxel read shared memory instead of L1/L2;
+//   3. results leave through 16-byte streaming stores (st.global.cs: the maps are not re-read by this kernel).
+// The interpolation expression and its rounding order are those of the row kernel above (ATen's nesting).
+// sums: double [3n] as above.  grid = (blocks per sample, n).
+// ---------------------------------------------------------------------------------------
+static constexpr int K7_SEG = 16;
+static constexpr int K7_THREADS = 256;
+
+__device__ __forceinline__ unsigned nonzero_bytes(uint32_t w) { return __vsadu4(__vsetne4(w, 0u), 0u); }
+
+template <bool FAST>
+__global__ void __launch_bounds__(K7_THREADS)
+dram_upsample_mask_staged_kernel(const float *__restrict__ dense0, const float *__restrict__ dense1,
+                                 const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
+                                 float *__restrict__ out0, float *__restrict__ out1, double *__restrict__ sums,
+                                 int n, int d, int h, int w, int D, int H, int W, float sd, float sh, float sw,
+                                 int RH, int nr_max) {
+  extern __shared__ float k7_smem[];  // [map 2][plane 2][nr_max][w]
+  __shared__ double scratch[32];
+  const int b = blockIdx.y;
+  const int segs = (W + K7_SEG - 1) / K7_SEG;
+  const int hblocks = (H + RH - 1) / RH;
+  const int groups = D * hblocks;
+  const int items = RH * segs;
+  const int64_t splane = (int64_t)d * h * w;
+  const float *s0 = dense0 + (int64_t)b * splane;
+  const float *s1 = dense1 + (int64_t)b * splane;
+  const int64_t vol = (int64_t)D * H * W;
+  const uint8_t *eb = ess + (int64_t)b * vol;
+  const uint8_t *lb = lungs + (int64_t)b * vol;
+  float *o0 = out0 + (int64_t)b * vol;
+  float *o1 = out1 + (int64_t)b * vol;
+  const int plane_stride = nr_max * w;  // floats per staged plane
+  double acc0 = 0.0, acc1 = 0.0;
+  unsigned lung_count = 0;
+
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int xd = g / hblocks, xh0 = (g - xd * hblocks) * RH;
+    const int rows = min(RH, H - xh0);
+    const LinIdx id = lin_index_ac(xd, sd, d);
+    const int ih_lo = lin_index_ac(xh0, sh, h).i0;
+    const int ih_hi = lin_index_ac(xh0 + rows - 1, sh, h).i1;
+    const int nr = ih_hi - ih_lo + 1;  // <= nr_max by construction (host)
+    // ---- 1. masks of this thread's segments (at most 2 per thread: items <= 2 * K7_THREADS, host-checked)
+    uint4 e4[2], l4[2];
+    int any = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int it = threadIdx.x + k * K7_THREADS;
+      e4[k] = make_uint4(0, 0, 0, 0);
+      l4[k] = make_uint4(0, 0, 0, 0);
+      if (it < items) {
+        const int r = it / segs, sg = it - r * segs;
+        if (r < rows) {
+          const int64_t o = ((int64_t)xd * H + xh0 + r) * W + (int64_t)sg * K7_SEG;
+          if constexpr (FAST) {
+            e4[k] = __ldcs(reinterpret_cast<const uint4 *>(eb + o));
+            l4[k] = __ldcs(reinterpret_cast<const uint4 *>(lb + o));
+          } else {
+            uint8_t *ep = reinterpret_cast<uint8_t *>(&e4[k]), *lp = reinterpret_cast<uint8_t *>(&l4[k]);
+            const int cnt = min(K7_SEG, W - sg * K7_SEG);
+            for (int j = 0; j < cnt; ++j) {
+              ep[j] = eb[o + j];
+              lp[j] = lb[o + j];
+            }
+          }
+          lung_count += nonzero_bytes(l4[k].x) + nonzero_bytes(l4[k].y) + nonzero_bytes(l4[k].z) + nonzero_bytes(l4[k].w);
+          any |= (e4[k].x | e4[k].y | e4[k].z | e4[k].w) != 0;
+        }
+      }
+    }
+    // ---- 2. stage the source brick if anybody needs it (also orders the reuse of the buffer between groups)
+    const int need = __syncthreads_or(any);
+    if (need) {
+      const int row_f4 = w >> 2;  // FAST implies w % 4 == 0 (host)
+      if (FAST) {
+        const int total = 4 * nr * row_f4;  // (map, plane, row, float4)
+        for (int t = threadIdx.x; t < total; t += K7_THREADS) {
+          const int c = t % row_f4;
+          int q = t / row_f4;
+          const int r = q % nr;
+          q /= nr;
+          const int pl = q & 1, mp = q >> 1;
+          const float *src = (mp ? s1 : s0) + ((int64_t)(pl ? id.i1 : id.i0) * h + ih_lo + r) * w;
+          reinterpret_cast<float4 *>(k7_smem + (mp * 2 + pl) * plane_stride + r * w)[c] =
+              __ldg(reinterpret_cast<const float4 *>(src) + c);
+        }
+      } else {
+        const int total = 4 * nr * w;
+        for (int t = threadIdx.x; t < total; t += K7_THREADS) {
+          const int c = t % w;
+          int q = t / w;
+          const int r = q % nr;
+          q /= nr;
+          const int pl = q & 1, mp = q >> 1;
+          const float *src = (mp ? s1 : s0) + ((int64_t)(pl ? id.i1 : id.i0) * h + ih_lo + r) * w;
+          k7_smem[(mp * 2 + pl) * plane_stride + r * w + c] = __ldg(src + c);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- 3. produce the segments
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int it = threadIdx.x + k * K7_THREADS;
+      if (it >= items) continue;
+      const int r = it / segs, sg = it - r * segs;
+      if (r >= rows) continue;
+      const int xh = xh0 + r, xw0 = sg * K7_SEG;
+      const int64_t o = ((int64_t)xd * H + xh) * W + xw0;
+      float v0[K7_SEG], v1[K7_SEG];
+#pragma unroll
+      for (int j = 0; j < K7_SEG; ++j) v0[j] = v1[j] = 0.0f;
+      if ((e4[k].x | e4[k].y | e4[k].z | e4[k].w) != 0) {
+        const LinIdx ih = lin_index_ac(xh, sh, h);
+        const float *p00 = k7_smem + (ih.i0 - ih_lo) * w, *p01 = k7_smem + (ih.i1 - ih_lo) * w;
+        const float *p10 = p00 + plane_stride, *p11 = p01 + plane_stride;
+        const float *q00 = p00 + 2 * plane_stride, *q01 = p01 + 2 * plane_stride;
+        const float *q10 = p10 + 2 * plane_stride, *q11 = p11 + 2 * plane_stride;
+        const uint32_t ew[4] = {e4[k].x, e4[k].y, e4[k].z, e4[k].w};
+#pragma unroll
+        for (int j = 0; j < K7_SEG; ++j) {
+          if ((ew[j >> 2] >> (8 * (j & 3))) & 0xffu) {
+            const LinIdx iw = lin_index_ac(xw0 + j, sw, w);
+            const float a = id.w0 * (ih.w0 * (iw.w0 * p00[iw.i0] + iw.w1 * p00[iw.i1]) +
+                                     ih.w1 * (iw.w0 * p01[iw.i0] + iw.w1 * p01[iw.i1])) +
+                            id.w1 * (ih.w0 * (iw.w0 * p10[iw.i0] + iw.w1 * p10[iw.i1]) +
+                                     ih.w1 * (iw.w0 * p11[iw.i0] + iw.w1 * p11[iw.i1]));
+            const float c = id.w0 * (ih.w0 * (iw.w0 * q00[iw.i0] + iw.w1 * q00[iw.i1]) +
+                                     ih.w1 * (iw.w0 * q01[iw.i0] + iw.w1 * q01[iw.i1])) +
+                            id.w1 * (ih.w0 * (iw.w0 * q10[iw.i0] + iw.w1 * q10[iw.i1]) +
+                                     ih.w1 * (iw.w0 * q11[iw.i0] + iw.w1 * q11[iw.i1]));
+            v0[j] = a;
+            v1[j] = c;
+            acc0 += (double)a;
+            acc1 += (double)c;
+          }
+        }
+      }
+      if constexpr (FAST) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __stcs(reinterpret_cast<float4 *>(o0 + o) + q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
+          __stcs(reinterpret_cast<float4 *>(o1 + o) + q, make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
+        }
+      } else {
+        const int cnt = min(K7_SEG, W - xw0);
+        for (int j = 0; j < cnt; ++j) {
+          o0[o + j] = v0[j];
+          o1[o + j] = v1[j];
+        }
+      }
+    }
+  }
+  acc0 = block_sum(acc0, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[b], acc0);
+  acc1 = block_sum(acc1, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[n + b], acc1);
+  double accl = block_sum((double)lung_count, scratch);
+  if (threadIdx.x == 0) atomicAdd(&sums[2 * n + b], accl);
+}
 __global__ void dram_finalize_kernel(const double *__restrict__ sums, float *__restrict__ pct, int n,
                                      int per_sample) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -423,72 +594,92 @@ __device__ __forceinline__ float window_value(short hu, float lo, float hi) {
   f = fminf(fmaxf(f, lo), hi);
   return (f - lo) / (hi - lo);
 }
-__global__ void window_stats_kernel(const short *__restrict__ hu, double *__restrict__ sums,
-                                    int64_t count, float lo, float hi) {
+// grid = (blocks, n): blockIdx.y = volume.  VEC: 16-byte loads (volumes start 16-byte aligned, count % 8 == 0).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+window_stats_kernel(const short *__restrict__ hu_all, double *__restrict__ sums_all, int64_t count, float lo, float hi) {
   __shared__ double scratch[32];
+  const short *hu = hu_all + (int64_t)blockIdx.y * count;
+  double *sums = sums_all + 2 * blockIdx.y;
   double s = 0.0, s2 = 0.0;
-  const int64_t nvec = count / 8;
-  const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 u = __ldg(hv + i);
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-    float ls = 0.0f, ls2 = 0.0f;  // 8 values in [0,1]: fp32 is exact enough before widening
+  if constexpr (VEC) {
+    const int64_t nvec = count / 8;
+    const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // two independent 16-byte loads in flight per thread and iteration
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 2 * stride) {
+      const uint4 u0 = __ldg(hv + i);
+      const bool two = i + stride < nvec;
+      const uint4 u1 = two ? __ldg(hv + i + stride) : make_uint4(0, 0, 0, 0);
+      const uint32_t uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      float ls = 0.0f, ls2 = 0.0f;  // <= 16 values in [0,1]: fp32 is exact enough before widening
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float a = window_value((short)(uu[q] & 0xffff), lo, hi);
-      const float b = window_value((short)(uu[q] >> 16), lo, hi);
-      ls += a + b;
-      ls2 += a * a + b * b;
+      for (int q = 0; q < 8; ++q) {
+        if (q >= 4 && !two) break;
+        const float a = window_value((short)(uu[q] & 0xffff), lo, hi);
+        const float b = window_value((short)(uu[q] >> 16), lo, hi);
+        ls += a + b;
+        ls2 += a * a + b * b;
+      }
+      s += (double)ls;
+      s2 += (double)ls2;
     }
-    s += (double)ls;
-    s2 += (double)ls2;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int64_t i = nvec * 8; i < count; ++i) {
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
       const float a = window_value(hu[i], lo, hi);
       s += (double)a;
-      s2 += (double)a * a;
+      s2 += (double)(a * a);
     }
+  }
   s = block_sum(s, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[0], s);
   s2 = block_sum(s2, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[1], s2);
 }
+// one thread per volume: stats[v] = (mean, unbiased std); stats_out (optional) gets a copy
 __global__ void window_finalize_kernel(const double *__restrict__ sums, float *__restrict__ stats,
-                                       float *__restrict__ stats_out, int64_t count) {
-  const double n = (double)count;
-  const double mean = sums[0] / n;
-  double var = (sums[1] - n * mean * mean) / (n - 1.0);
+                                       float *__restrict__ stats_out, int64_t count, int n) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const double cnt = (double)count;
+  const double mean = sums[2 * v] / cnt;
+  double var = (sums[2 * v + 1] - cnt * mean * mean) / (cnt - 1.0);
   if (var < 0.0) var = 0.0;
-  stats[0] = (float)mean;
-  stats[1] = (float)sqrt(var);
+  stats[2 * v] = (float)mean;
+  stats[2 * v + 1] = (float)sqrt(var);
   if (stats_out) {
-    stats_out[0] = stats[0];
-    stats_out[1] = stats[1];
+    stats_out[2 * v] = stats[2 * v];
+    stats_out[2 * v + 1] = stats[2 * v + 1];
   }
 }
-__global__ void window_apply_kernel(const short *__restrict__ hu, float *__restrict__ out,
-                                    const float *__restrict__ stats, int64_t count, float lo, float hi) {
-  const float mean = stats[0], sd = stats[1];
-  const int64_t nvec = count / 8;
-  const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
-  float4 *ov = reinterpret_cast<float4 *>(out);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4 u = __ldg(hv + i);
-    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+window_apply_kernel(const short *__restrict__ hu_all, float *__restrict__ out_all, const float *__restrict__ stats,
+                    int64_t count, float lo, float hi) {
+  const short *hu = hu_all + (int64_t)blockIdx.y * count;
+  float *out = out_all + (int64_t)blockIdx.y * count;
+  const float mean = stats[2 * blockIdx.y], sd = stats[2 * blockIdx.y + 1];
+  if constexpr (VEC) {
+    const int64_t nvec = count / 8;
+    const uint4 *hv = reinterpret_cast<const uint4 *>(hu);
+    float4 *ov = reinterpret_cast<float4 *>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      const uint4 u = __ldg(hv + i);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+      float f[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      f[2 * q + 0] = (window_value((short)(uu[q] & 0xffff), lo, hi) - mean) / sd;
-      f[2 * q + 1] = (window_value((short)(uu[q] >> 16), lo, hi) - mean) / sd;
+      for (int q = 0; q < 4; ++q) {
+        f[2 * q + 0] = (window_value((short)(uu[q] & 0xffff), lo, hi) - mean) / sd;
+        f[2 * q + 1] = (window_value((short)(uu[q] >> 16), lo, hi) - mean) / sd;
+      }
+      ov[2 * i + 0] = make_float4(f[0], f[1], f[2], f[3]);
+      ov[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
     }
-    ov[2 * i + 0] = make_float4(f[0], f[1], f[2], f[3]);
-    ov[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+      out[i] = (window_value(hu[i], lo, hi) - mean) / sd;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    for (int64_t i = nvec * 8; i < count; ++i) out[i] = (window_value(hu[i], lo, hi) - mean) / sd;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -680,48 +871,119 @@ extern "C" int dram_dram_upsample_mask(const float *dense0, const float *dense1,
                       "dram_dram_upsample_mask memset");
   if (rc != DRAM_OK) return rc;
   const float sd = ac_scale(d, D), sh = ac_scale(h, H), sw = ac_scale(w, W);
-  const bool vec = (W % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 4 == 0) &&
-                   (((uintptr_t)out0 | (uintptr_t)out1) % 16 == 0);
   DRAM_REQUIRE((int64_t)D * H < 0x7fffffffLL && (int64_t)d * h * w < 0x7fffffffLL,
                "dram_dram_upsample_mask: volume too large for 32-bit row indices");
-  int bps = stream_grid((int64_t)D * H * 32, kThreads, 8) / n;  // one warp per output row
-  if (bps < 1) bps = 1;
   double *sums = reinterpret_cast<double *>(workspace);
-  if (vec)
-    dram_upsample_mask_kernel<4><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
-                                                               n, d, h, w, D, H, W, sd, sh, sw, bps);
-  else
-    dram_upsample_mask_kernel<1><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
-                                                               n, d, h, w, D, H, W, sd, sh, sw, bps);
-  DRAM_CHECK_LAUNCH("dram_upsample_mask_kernel");
+  // Staged kernel: RH rows per CTA so that RH * ceil(W/16) segments keep 256 threads busy (at most two per thread);
+  // the brick of source rows they read is at most nr_max = ceil(RH * (h-1)/(H-1)) + 2 rows per plane.
+  const int segs = ceil_div(W, K7_SEG);
+  int RH = 1;
+  while (RH < 32 && 2 * RH * segs <= 2 * K7_THREADS) RH *= 2;
+  const char *k7_env = getenv("DRAM_B200_K7");
+  const bool staged_ok = RH * segs <= 2 * K7_THREADS && !(k7_env && strcmp(k7_env, "rows") == 0);
+  const int nr_max = (int)ceilf((float)RH * sh) + 2 < h ? (int)ceilf((float)RH * sh) + 2 : h;
+  const size_t smem = (size_t)4 * nr_max * w * sizeof(float);
+  if (staged_ok && smem <= 160 * 1024) {
+    const bool fast = (W % 16 == 0) && (w % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 16 == 0) &&
+                      (((uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)dense0 | (uintptr_t)dense1) % 16 == 0) &&
+                      (((int64_t)D * H * W) % 16 == 0) && (((int64_t)d * h * w) % 4 == 0);
+    const int groups = D * ceil_div(H, RH);
+    int per = (sm_count() * 6) / n;
+    if (per < 1) per = 1;
+    if (per > groups) per = groups;
+    dim3 grid(per, n);
+    if (fast) {
+      rc = check_cuda(cudaFuncSetAttribute(dram_upsample_mask_staged_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute(dram_upsample_mask_staged_kernel)");
+      if (rc != DRAM_OK) return rc;
+      dram_upsample_mask_staged_kernel<true><<<grid, K7_THREADS, smem, st>>>(dense0, dense1, ess, lungs, out0, out1, sums, n,
+                                                                            d, h, w, D, H, W, sd, sh, sw, RH, nr_max);
+    } else {
+      rc = check_cuda(cudaFuncSetAttribute(dram_upsample_mask_staged_kernel<false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                      "cudaFuncSetAttribute(dram_upsample_mask_staged_kernel)");
+      if (rc != DRAM_OK) return rc;
+      dram_upsample_mask_staged_kernel<false><<<grid, K7_THREADS, smem, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
+                                                                             n, d, h, w, D, H, W, sd, sh, sw, RH, nr_max);
+    }
+    DRAM_CHECK_LAUNCH("dram_upsample_mask_staged_kernel");
+  } else {
+    const bool vec = (W % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 4 == 0) &&
+                     (((uintptr_t)out0 | (uintptr_t)out1) % 16 == 0);
+    int bps = stream_grid((int64_t)D * H * 32, kThreads, 8) / n;  // one warp per output row
+    if (bps < 1) bps = 1;
+    if (vec)
+      dram_upsample_mask_kernel<4><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
+                                                                 n, d, h, w, D, H, W, sd, sh, sw, bps);
+    else
+      dram_upsample_mask_kernel<1><<<bps * n, kThreads, 0, st>>>(dense0, dense1, ess, lungs, out0, out1, sums,
+                                                                 n, d, h, w, D, H, W, sd, sh, sw, bps);
+    DRAM_CHECK_LAUNCH("dram_upsample_mask_kernel");
+  }
   dram_finalize_kernel<<<ceil_div(2 * n, 128), 128, 0, st>>>(sums, pct, n, per_sample_denominator);
   DRAM_CHECK_LAUNCH("dram_finalize_kernel");
   return DRAM_OK;
 }
 
 extern "C" size_t dram_preprocess_workspace_bytes(void) { return 2 * sizeof(double) + 2 * sizeof(float); }
+extern "C" size_t dram_preprocess_workspace_bytes_n(int32_t n) {
+  return n > 0 ? (size_t)n * (2 * sizeof(double) + 2 * sizeof(float)) : 0;
+}
+
+// memset + statistics of all n volumes in one launch + finalize; leaves (mean, std) per volume at workspace + 16 n.
+static int window_stats_launch(const int16_t *hu, float *stats_out, void *workspace, int32_t n, int64_t count, float lo,
+                               float hi, cudaStream_t st, bool *vec_out) {
+  DRAM_REQUIRE(hu && workspace, "dram_window_stats: null pointer");
+  DRAM_REQUIRE(n > 0 && n <= 65535, "dram_window_stats: bad volume count");
+  DRAM_REQUIRE(count > 1, "dram_window_stats: need at least 2 voxels for an unbiased std");
+  DRAM_REQUIRE(hi > lo, "dram_window_stats: empty window");
+  DRAM_REQUIRE((uintptr_t)workspace % 8 == 0, "dram_window_stats: workspace must be 8-byte aligned");
+  double *sums = reinterpret_cast<double *>(workspace);
+  float *stats = reinterpret_cast<float *>(sums + 2 * n);
+  int rc = check_cuda(cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * (size_t)n, st), "dram_window_stats memset");
+  if (rc != DRAM_OK) return rc;
+  // 16-byte loads need every volume to start on a 16-byte boundary
+  const bool vec = ((uintptr_t)hu % 16 == 0) && (count % 8 == 0);
+  int per = stream_grid(count / 16 + 1, kThreads, 8) / n;
+  if (per < 1) per = 1;
+  dim3 grid(per, n);
+  if (vec) window_stats_kernel<true><<<grid, kThreads, 0, st>>>(hu, sums, count, lo, hi);
+  else window_stats_kernel<false><<<grid, kThreads, 0, st>>>(hu, sums, count, lo, hi);
+  DRAM_CHECK_LAUNCH("window_stats_kernel");
+  window_finalize_kernel<<<ceil_div(n, 64), 64, 0, st>>>(sums, stats, stats_out, count, n);
+  DRAM_CHECK_LAUNCH("window_finalize_kernel");
+  if (vec_out) *vec_out = vec;
+  return DRAM_OK;
+}
+
+extern "C" int dram_window_stats(const int16_t *hu, float *stats_out, void *workspace, int32_t n, int64_t count,
+                                 float lo, float hi, void *stream) {
+  DRAM_REQUIRE(stats_out, "dram_window_stats: stats_out is required");
+  return window_stats_launch(hu, stats_out, workspace, n, count, lo, hi, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int dram_window_standardize_batch(const int16_t *hu, float *out, float *stats_out, void *workspace,
+                                             int32_t n, int64_t count, float lo, float hi, void *stream) {
+  DRAM_REQUIRE(out, "dram_window_standardize: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = false;
+  int rc = window_stats_launch(hu, stats_out, workspace, n, count, lo, hi, st, &vec);
+  if (rc != DRAM_OK) return rc;
+  vec = vec && ((uintptr_t)out % 16 == 0);
+  const float *stats = reinterpret_cast<const float *>(reinterpret_cast<double *>(workspace) + 2 * n);
+  int per = stream_grid(count / 8 + 1, kThreads, 8) / n;
+  if (per < 1) per = 1;
+  dim3 grid(per, n);
+  if (vec) window_apply_kernel<true><<<grid, kThreads, 0, st>>>(hu, out, stats, count, lo, hi);
+  else window_apply_kernel<false><<<grid, kThreads, 0, st>>>(hu, out, stats, count, lo, hi);
+  DRAM_CHECK_LAUNCH("window_apply_kernel");
+  return DRAM_OK;
+}
 
 extern "C" int dram_window_standardize(const int16_t *hu, float *out, float *stats_out, void *workspace,
                                        int64_t count, float lo, float hi, void *stream) {
-  DRAM_REQUIRE(hu && out && workspace, "dram_window_standardize: null pointer");
-  DRAM_REQUIRE(count > 1, "dram_window_standardize: need at least 2 voxels for an unbiased std");
-  DRAM_REQUIRE(hi > lo, "dram_window_standardize: empty window");
-  DRAM_REQUIRE(((uintptr_t)hu % 16 == 0) && ((uintptr_t)out % 16 == 0),
-               "dram_window_standardize: buffers must be 16-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
-  double *sums = reinterpret_cast<double *>(workspace);
-  float *stats = reinterpret_cast<float *>(sums + 2);
-  int rc = check_cuda(cudaMemsetAsync(workspace, 0, dram_preprocess_workspace_bytes(), st),
-                      "dram_window_standardize memset");
-  if (rc != DRAM_OK) return rc;
-  const int grid = stream_grid(count / 8 + 1, kThreads, 8);
-  window_stats_kernel<<<grid, kThreads, 0, st>>>(hu, sums, count, lo, hi);
-  DRAM_CHECK_LAUNCH("window_stats_kernel");
-  window_finalize_kernel<<<1, 1, 0, st>>>(sums, stats, stats_out, count);
-  DRAM_CHECK_LAUNCH("window_finalize_kernel");
-  window_apply_kernel<<<grid, kThreads, 0, st>>>(hu, out, stats, count, lo, hi);
-  DRAM_CHECK_LAUNCH("window_apply_kernel");
-  return DRAM_OK;
+  return dram_window_standardize_batch(hu, out, stats_out, workspace, 1, count, lo, hi, stream);
 }
 
 extern "C" int dram_resize_image(const float *x, float *out, const int32_t *d_idx, int32_t D, int32_t H,

@@ -39,7 +39,10 @@ static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
 static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512;
 
 struct StemParams {
-  const float *x;       // fp32 [n][D][H][W]
+  const float *x;       // fp32 [n][D][H][W] (kernel variant HU = false)
+  const short *hu;      // int16 HU [n][D][H][W] (HU = true): window + standardise happen in the producers
+  const float *stats;   // HU: fp32 [n][2] = mean, unbiased std of each windowed volume (dram_window_stats)
+  float lo, hi;         // HU: intensity window
   const uint4 *weight;  // 16-bit, even kd [8][4][64][8] then odd kd [8][3][64][8] (ops.pack_stem_weight_fused)
   int n, D, H, W;       // input dims
   int cols_w, cols_h, groups_d, items_total;
@@ -82,6 +85,16 @@ __device__ __forceinline__ uint32_t pack_pair(float a, float b, int is_f16) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// The K8 arithmetic (aux_kernels.cu window_value / window_apply_kernel), so that the fused path feeds the tensor
+// cores exactly the values the two-kernel path would: ((clamp(hu) - lo) / (hi - lo) - mean) / sd in fp32.
+__device__ __forceinline__ float stem_standardize(short hu, float lo, float hi, float mean, float sd) {
+  float f = (float)hu;
+  f = fminf(fmaxf(f, lo), hi);
+  f = (f - lo) / (hi - lo);
+  return (f - mean) / sd;
+}
+
+template <bool HU>
 __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
     // loads are in flight at once; a lane builds its chunks in two batches of five (20 8-byte loads
     // outstanding per lane).
     const int pw = warp - ST_PROD_WARP0;
-    const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
+    const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(HU ? (const void *)p.hu : (const void *)p.x) & (HU ? 3 : 7)) == 0);
     const int is_f16 = p.epi.is_f16;
     unsigned seq_end = 0;
     for (int item = item_begin; item < item_end; ++item) {
@@ -149,7 +162,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
         const int z = 2 * it.q0 - 3 + j;
         mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
         const bool zok = z >= 0 && z < p.D;
-        const float *xz = p.x + ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
+        const size_t plane_off = ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
+        const float *xz = HU ? nullptr : p.x + plane_off;
+        const short *hz = HU ? p.hu + plane_off : nullptr;
+        float mean = 0.0f, sd = 1.0f;
+        if constexpr (HU) {
+          mean = __ldg(p.stats + 2 * it.sample);
+          sd = __ldg(p.stats + 2 * it.sample + 1);
+        }
         const uint32_t dst0 = plane_addr(slot);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -162,19 +182,39 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
 #pragma unroll
             for (int q = 0; q < 8; ++q) f[c][q] = 0.0f;
             if (chunk < ST_ROWS * ST_W && zok && ih >= 0 && ih < p.H) {
-              const float *row = xz + (size_t)ih * p.W;
-              if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
+              if constexpr (HU) {
+                const short *row = hz + (size_t)ih * p.W;
+                if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
+                  uint32_t u[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
-                  f[c][2 * q] = v.x;
-                  f[c][2 * q + 1] = v.y;
+                  for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint32_t *>(row + iw0) + q);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    f[c][2 * q] = stem_standardize((short)(u[q] & 0xffffu), p.lo, p.hi, mean, sd);
+                    f[c][2 * q + 1] = stem_standardize((short)(u[q] >> 16), p.lo, p.hi, mean, sd);
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const int iw = iw0 + q;
+                    if (iw >= 0 && iw < p.W) f[c][q] = stem_standardize(__ldg(row + iw), p.lo, p.hi, mean, sd);
+                  }
                 }
               } else {
+                const float *row = xz + (size_t)ih * p.W;
+                if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const int iw = iw0 + q;
-                  if (iw >= 0 && iw < p.W) f[c][q] = __ldg(row + iw);
+                  for (int q = 0; q < 4; ++q) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
+                    f[c][2 * q] = v.x;
+                    f[c][2 * q + 1] = v.y;
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const int iw = iw0 + q;
+                    if (iw >= 0 && iw < p.W) f[c][q] = __ldg(row + iw);
+                  }
                 }
               }
             }
@@ -302,17 +342,14 @@ using namespace dram;
 
 extern "C" size_t dram_stem_weight_bytes(void) { return ST_WEIGHT_BYTES; }
 
-extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *bias, const float *scale,
-                               void *out, int32_t n, int32_t d, int32_t h, int32_t w, int32_t relu,
-                               int32_t dtype, int32_t max_ctas, void *stream) {
-  DRAM_REQUIRE(x && weight && bias && out, "dram_stem_conv7: null pointer");
+static int stem_launch(StemParams &p, const void *weight, const float *bias, const float *scale, void *out, int32_t n,
+                       int32_t d, int32_t h, int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas, void *stream,
+                       bool from_hu) {
+  DRAM_REQUIRE(weight && bias && out, "dram_stem_conv7: null pointer");
   DRAM_REQUIRE(n > 0 && d > 0 && h > 0 && w > 0, "dram_stem_conv7: empty volume");
   DRAM_REQUIRE(dtype == DRAM_DTYPE_BF16 || dtype == DRAM_DTYPE_F16, "dram_stem_conv7: dtype must be bf16 (0) or fp16 (1)");
   DRAM_REQUIRE((reinterpret_cast<uintptr_t>(weight) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "dram_stem_conv7: weight and out must be 16-byte aligned");
-  StemParams p;
-  memset(&p, 0, sizeof(p));
-  p.x = x;
   p.weight = reinterpret_cast<const uint4 *>(weight);
   p.n = n; p.D = d; p.H = h; p.W = w;
   const int Do = (d - 1) / 2 + 1, Ho = (h - 1) / 2 + 1, Wo = (w - 1) / 2 + 1;
@@ -332,14 +369,42 @@ extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *
   p.epi.res_stride = 1;
   p.epi.store_out = 1;
   p.epi = with_sat_counter(p.epi);
-  int rc = check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           ST_SMEM_BYTES),
-                      "cudaFuncSetAttribute(conv3d_stem_kernel)");
+  int rc = from_hu ? check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ST_SMEM_BYTES), "cudaFuncSetAttribute(conv3d_stem_kernel)")
+                   : check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ST_SMEM_BYTES), "cudaFuncSetAttribute(conv3d_stem_kernel)");
   if (rc != DRAM_OK) return rc;
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   if (p.items_total < ctas) ctas = p.items_total;
-  conv3d_stem_kernel<<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (from_hu)
+    conv3d_stem_kernel<true><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else
+    conv3d_stem_kernel<false><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   DRAM_CHECK_LAUNCH("conv3d_stem_kernel launch");
   return DRAM_OK;
+}
+
+extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *bias, const float *scale,
+                               void *out, int32_t n, int32_t d, int32_t h, int32_t w, int32_t relu,
+                               int32_t dtype, int32_t max_ctas, void *stream) {
+  DRAM_REQUIRE(x, "dram_stem_conv7: null pointer");
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  return stem_launch(p, weight, bias, scale, out, n, d, h, w, relu, dtype, max_ctas, stream, false);
+}
+
+extern "C" int dram_stem_conv7_hu(const int16_t *hu, const float *stats, float lo, float hi, const void *weight,
+                                  const float *bias, const float *scale, void *out, int32_t n, int32_t d, int32_t h,
+                                  int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas, void *stream) {
+  DRAM_REQUIRE(hu && stats, "dram_stem_conv7_hu: null pointer");
+  DRAM_REQUIRE(hi > lo, "dram_stem_conv7_hu: empty window");
+  StemParams p;
+  memset(&p, 0, sizeof(p));
+  p.hu = reinterpret_cast<const short *>(hu);
+  p.stats = stats;
+  p.lo = lo;
+  p.hi = hi;
+  return stem_launch(p, weight, bias, scale, out, n, d, h, w, relu, dtype, max_ctas, stream, true);
 }

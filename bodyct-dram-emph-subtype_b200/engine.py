@@ -134,6 +134,7 @@ class Med3DEngine:
 
             sw = self._register_weight("conv1", pack_stem)
             x = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
+            self.stem_weights, self.stem_out = sw, x   # for the int16-HU stem (predict_step_from_hu)
             self.conv_flops += stem_flops
             self.steps.append(_Step("conv1", lambda: ops.stem_conv7(self.image, sw[0], sw[1], sw[2], out=x),
                                     stem_flops))
@@ -229,12 +230,28 @@ class Med3DEngine:
         self._plans_alive = [s.fn for s in self.steps]
 
     # ---------------------------------------------------------------- run
-    def _launch_steps(self):
-        for st in self.steps:
+    def _launch_steps(self, first=None):
+        (first or self.steps[0].fn)()
+        self._launch_tail()
+
+    def _launch_tail(self):
+        for st in self.steps[1:]:
             st.fn()
 
-    def run_network(self):
+    def hu_stem(self, hu, stats, lo=-1150.0, hi=-300.0):
+        """A replacement for the first recorded step (the stem convolution on `self.image`): the same kernel fed from
+        the int16 HU volumes [B,D,H,W] and their window statistics [B,2] (`ops.window_stats`), K8's apply pass fused
+        into its producers.  Pass it to `run_network(first=...)`."""
+        if not hasattr(self, "stem_weights"):
+            raise RuntimeError("the int16-HU stem needs the fused stem kernel (DRAM_B200_STEM=unfold is set)")
+        if tuple(hu.shape) != (self.batch,) + self.dims:
+            raise ValueError(f"hu shape {tuple(hu.shape)} does not match the engine's {(self.batch,) + self.dims}")
+        w, b, m = self.stem_weights
+        return lambda: ops.stem_conv7_hu(hu, stats, w, b, m, out=self.stem_out, lo=lo, hi=hi)
+
+    def run_network(self, first=None):
         """The recorded launch sequence on `self.image` -> `self.dense` (engine-owned), on the current stream.
+        `first` replaces the first step (see `hu_stem`); it is launched eagerly, the rest replays as a graph.
 
         * fp16 storage: the first pass after the weights changed (`DRAM_B200_SAT_CHECK=first`, default; `always` /
           `off`) runs with the library's saturation probe on and raises `ops.ActivationOverflow` if any convolution
@@ -250,7 +267,7 @@ class Med3DEngine:
             self._sat_counter.zero_()
             ops.check(lib.dram_set_saturation_counter(ops._p(self._sat_counter)), "dram_set_saturation_counter")
             try:
-                self._launch_steps()
+                self._launch_steps(first)
             finally:
                 lib.dram_set_saturation_counter(None)
             clamped = int(self._sat_counter.item())
@@ -262,14 +279,15 @@ class Med3DEngine:
             self._sat_checked_epoch = self._weights_epoch
             return self.dense
         if not ops.graphs_enabled() or torch.cuda.is_current_stream_capturing():
-            self._launch_steps()
+            self._launch_steps(first)
             return self.dense
+        (first or self.steps[0].fn)()   # the stem reads a caller-owned buffer in the HU variant: outside the graph
         if self._graph is None:
-            self._launch_steps()  # warm-up outside the capture (lazy function attributes, module loading)
+            self._launch_tail()  # warm-up outside the capture (lazy function attributes, module loading)
             torch.cuda.current_stream(self.device).synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                self._launch_steps()
+                self._launch_tail()
             self._graph = graph
         self._graph.replay()
         return self.dense

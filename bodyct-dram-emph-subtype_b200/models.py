@@ -281,19 +281,25 @@ class ScanRegLightningModule(_ScanModule):
                 "uids": batch.get("uid"),
             }
 
-    def predict_step_from_hu(self, hu, lung_mask, ess_mask):
-        """The device-resident hot path of SURVEY §8d: int16 HU volumes already at network size
-        [B,D,H,W] -> K8 window+standardise (per volume) -> network -> pooling -> dRAM.  Returns the
-        same dict as predict_step (without the bookkeeping keys)."""
+    def predict_step_from_hu(self, hu, lung_mask, ess_mask, fuse_window=True):
+        """The device-resident hot path of SURVEY §8d: int16 HU volumes already at network size [B,D,H,W] -> K8
+        window + standardise (per volume) -> network -> dRAM.  By default K8 is its statistics pass only and the stem
+        convolution windows and standardises while it loads the int16 volume (same arithmetic, same values; the fp32
+        image is never written); `fuse_window=False` writes the fp32 image first (what predict_step receives from the
+        transforms).  Returns the same dict as predict_step (without the bookkeeping keys)."""
         with torch.no_grad():
             if not hu.is_cuda or hu.dtype != torch.int16:
                 raise RuntimeError("predict_step_from_hu: expected an int16 CUDA tensor [B,D,H,W]")
             B, D, H, W = hu.shape
             eng = self.model.eval().engine(B, (D, H, W), hu.device)
-            for b in range(B):  # statistics are per volume (intensity_transforms.py:104-114)
-                ops.window_standardize(hu[b], out=eng.image[b])
+            hu = hu.contiguous()
+            if fuse_window and hasattr(eng, "stem_weights"):
+                stats = ops.window_stats(hu)  # statistics are per volume (intensity_transforms.py:104-114)
+                dense = eng.run_network(first=eng.hu_stem(hu, stats))
+            else:
+                ops.window_standardize(hu, out=eng.image, batched=True)
+                dense = eng.run_network()
             lungs, ess = _as_u8(lung_mask), _as_u8(ess_mask)
-            dense = eng.run_network()
             cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
                                                    per_sample_denominator=self.per_sample_percentage)
             return {"cle_dense_outs": cle, "pse_dense_outs": pse, "cle_precentages": pct[0],

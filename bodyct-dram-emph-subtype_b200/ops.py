@@ -329,6 +329,32 @@ def stem_conv7(x, weight, bias, scale=None, out=None, relu=True, max_ctas=0):
     return out
 
 
+def stem_conv7_hu(hu, stats, weight, bias, scale=None, out=None, relu=True, lo=-1150.0, hi=-300.0, max_ctas=0):
+    """K2 fed from int16 HU [N, D, H, W] + per-volume window statistics fp32 [N, 2] (`window_stats`): window,
+    standardise (K8's arithmetic), conv 7^3 s2 p3, scale/shift, ReLU in one kernel; the fp32 image never exists."""
+    lib = _capi.load()
+    _need(hu, torch.int16, "stem_conv7_hu hu", 4)
+    _need(stats, torch.float32, "stem_conv7_hu stats", 2)
+    _need16(weight, "stem_conv7_hu weight", 1)
+    if weight.numel() != 7 * 8 * 64 * 8:
+        raise ValueError("stem_conv7_hu: weight must hold 28672 values (pack_stem_weight_fused)")
+    _need(bias, torch.float32, "stem_conv7_hu bias", 1)
+    if scale is not None:
+        _need(scale, torch.float32, "stem_conv7_hu scale", 1)
+    n, d, h, w = hu.shape
+    if tuple(stats.shape) != (n, 2):
+        raise ValueError(f"stem_conv7_hu: stats must be [{n}, 2], got {tuple(stats.shape)}")
+    shape = (n, (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
+    if out is None:
+        out = torch.empty(shape, dtype=weight.dtype, device=hu.device)
+    _need(out, weight.dtype, "stem_conv7_hu out", 5)
+    if tuple(out.shape) != shape:
+        raise ValueError(f"stem_conv7_hu: out shape {tuple(out.shape)} != {shape}")
+    check(lib.dram_stem_conv7_hu(_p(hu), _p(stats), lo, hi, _p(weight), _p(bias), _p(scale), _p(out), n, d, h, w,
+                                 1 if relu else 0, ACT_DTYPES[weight.dtype], max_ctas, _stream()), "dram_stem_conv7_hu")
+    return out
+
+
 def maxpool3d(x, out=None):
     _need16(x, "maxpool3d x", 5)
     n, d, h, w, c = x.shape
@@ -426,17 +452,31 @@ def dram_upsample_mask(dense0, dense1, ess, lungs, size, per_sample_denominator=
     return out0, out1, pct
 
 
-def window_standardize(hu, lo=-1150.0, hi=-300.0, out=None):
-    """K8: int16 HU volume (any shape, one volume) -> fp32 standardised window; returns (out, stats)."""
+def window_standardize(hu, lo=-1150.0, hi=-300.0, out=None, batched=False):
+    """K8: int16 HU -> fp32 standardised window; returns (out, stats).  One volume of any shape (stats fp32 [2]),
+    or with `batched` a stack [N, ...] of volumes with per-volume statistics (stats fp32 [N, 2]) in three launches."""
     lib = _capi.load()
     _need(hu, torch.int16, "window_standardize hu")
+    n = hu.shape[0] if batched else 1
     if out is None:
         out = torch.empty(hu.shape, dtype=torch.float32, device=hu.device)
-    stats = torch.empty(2, dtype=torch.float32, device=hu.device)
-    ws = torch.empty(lib.dram_preprocess_workspace_bytes(), dtype=torch.uint8, device=hu.device)
-    check(lib.dram_window_standardize(_p(hu), _p(out), _p(stats), _p(ws), hu.numel(), lo, hi, _stream()),
+    _need(out, torch.float32, "window_standardize out")
+    stats = torch.empty((n, 2) if batched else (2,), dtype=torch.float32, device=hu.device)
+    ws = torch.empty(lib.dram_preprocess_workspace_bytes_n(n) // 8, dtype=torch.float64, device=hu.device)
+    check(lib.dram_window_standardize_batch(_p(hu), _p(out), _p(stats), _p(ws), n, hu.numel() // n, lo, hi, _stream()),
           "dram_window_standardize")
     return out, stats
+
+
+def window_stats(hu, lo=-1150.0, hi=-300.0):
+    """K8, statistics pass only: int16 HU [N, ...] -> fp32 [N, 2] = (mean, unbiased std) of each windowed volume."""
+    lib = _capi.load()
+    _need(hu, torch.int16, "window_stats hu")
+    n = hu.shape[0]
+    stats = torch.empty((n, 2), dtype=torch.float32, device=hu.device)
+    ws = torch.empty(lib.dram_preprocess_workspace_bytes_n(n) // 8, dtype=torch.float64, device=hu.device)
+    check(lib.dram_window_stats(_p(hu), _p(stats), _p(ws), n, hu.numel() // n, lo, hi, _stream()), "dram_window_stats")
+    return stats
 
 
 def slice_index(d_in, d_out, device):

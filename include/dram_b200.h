@@ -174,6 +174,18 @@ size_t dram_stem_weight_bytes(void);
 int dram_stem_conv7(const float *x, const void *weight, const float *bias, const float *scale,
                     void *out, int32_t n, int32_t d, int32_t h, int32_t w, int32_t relu,
                     int32_t dtype, int32_t max_ctas, void *stream);
+/*
+ * The same kernel fed straight from the int16 HU volume: IntensityWindow + Standardize
+ * (functional.py:13-26, intensity_transforms.py:104-114; wired at models.py:60-61) are evaluated in the
+ * producers with the arithmetic of dram_window_standardize, so the standardised fp32 image is never
+ * written to or re-read from HBM (K8 shrinks to its statistics pass, dram_window_stats).
+ *   hu    : int16 [n][d][h][w];  stats: fp32 [n][2] = (mean, unbiased std) of each windowed volume
+ *   lo/hi : the window (-1150, -300 in the reference)
+ */
+int dram_stem_conv7_hu(const int16_t *hu, const float *stats, float lo, float hi, const void *weight,
+                       const float *bias, const float *scale, void *out, int32_t n, int32_t d, int32_t h,
+                       int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas, void *stream);
+
 
 /* ---- K3: max-pool 3x3x3 stride 2 pad 1 (med3d.py:305, 374) ------------- */
 int dram_maxpool3d(const void *x, void *out, int32_t n, int32_t d, int32_t h, int32_t w,
@@ -229,10 +241,23 @@ int dram_dram_upsample_mask(const float *dense0, const float *dense1, const uint
  * hu: int16 [count]; out: fp32 [count] = (v - mean(v)) / std_unbiased(v) with
  * v = (clamp(hu, lo, hi) - lo) / (hi - lo) in fp32.  One volume per call
  * (statistics are per volume).  stats_out (optional, fp32[2]) = mean, std.
+ * Buffers of any alignment are accepted (16-byte aligned ones take the vector path).
  */
 size_t dram_preprocess_workspace_bytes(void);
 int dram_window_standardize(const int16_t *hu, float *out, float *stats_out, void *workspace,
                             int64_t count, float lo, float hi, void *stream);
+/*
+ * Batched forms: n volumes of `count` voxels each, stored back to back ([n][count]); statistics stay per
+ * volume.  Three launches whatever n is (statistics of all volumes, finalize, apply).  stats_out: fp32 [n][2].
+ * dram_window_stats runs the statistics pass only (for dram_stem_conv7_hu).  Workspace:
+ * dram_preprocess_workspace_bytes_n(n) bytes, 8-byte aligned.  Volumes that do not start on a 16-byte
+ * boundary (count % 8 != 0, or an unaligned base) take a scalar path instead of failing.
+ */
+size_t dram_preprocess_workspace_bytes_n(int32_t n);
+int dram_window_standardize_batch(const int16_t *hu, float *out, float *stats_out, void *workspace,
+                                  int32_t n, int64_t count, float lo, float hi, void *stream);
+int dram_window_stats(const int16_t *hu, float *stats_out, void *workspace, int32_t n, int64_t count,
+                      float lo, float hi, void *stream);
 
 /* ---- K8b: Interpolate transform (spatial_transforms.py:55-97) ---------- */
 /*

@@ -110,6 +110,74 @@ def test_dram_upsample_mask(cuda, lib, dims, size):
     assert torch.allclose(pct_s.cpu()[0], ps, rtol=1e-5)
 
 
+@pytest.mark.parametrize("dims,size,n", [((16, 16, 16), (32, 32, 32), 2), ((8, 12, 16), (16, 24, 64), 3),
+                                         ((12, 10, 64), (24, 20, 512), 1), ((5, 7, 9), (10, 14, 18), 2),
+                                         ((4, 5, 6), (9, 11, 13), 2), ((6, 8, 40), (11, 16, 80), 1),
+                                         ((2, 40, 8), (3, 79, 16), 2)])
+def test_dram_staged_kernel_equals_row_kernel(cuda, lib, dims, size, n, monkeypatch):
+    """K7's shared-memory staged kernel (default; 16-voxel segments, source brick in shared memory, fast and ragged
+    variants) against the round-1 warp-per-row kernel (DRAM_B200_K7=rows): same expression, same rounding order ->
+    bit-identical maps; the fp64 sums agree to the last fp32 bit of the percentages.  Covers aligned sizes (vector
+    path), W = 512 (two segments per thread), ragged sizes and unaligned sample strides (scalar path), sparse and dense
+    `ess`, and empty masks."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(15)
+    d0 = torch.rand((n, 1) + dims, generator=g).to(cuda)
+    d1 = torch.rand((n, 1) + dims, generator=g).to(cuda)
+    lungs = (torch.rand((n,) + size, generator=g) > 0.4)
+    for frac in (0.03, 0.9, 0.0):
+        ess = (lungs & (torch.rand((n,) + size, generator=g) < frac)).to(torch.uint8).to(cuda)
+        lu = lungs.to(torch.uint8).to(cuda)
+        monkeypatch.setenv("DRAM_B200_K7", "rows")
+        r0, r1, rp = ops.dram_upsample_mask(d0, d1, ess, lu, size)
+        monkeypatch.setenv("DRAM_B200_K7", "staged")
+        o0, o1, op = ops.dram_upsample_mask(d0, d1, ess, lu, size)
+        assert torch.equal(o0, r0) and torch.equal(o1, r1), (dims, size, frac)
+        assert torch.allclose(op, rp, rtol=1e-6, atol=0), (op, rp)
+        ref = F.interpolate(d0.cpu(), size=size, mode="trilinear", align_corners=True) * ess.cpu()[:, None].float()
+        assert (o0.cpu() - ref).abs().max().item() < 1e-5
+        assert torch.equal(o0.cpu() == 0, ref == 0)
+
+
+@pytest.mark.parametrize("shape,n", [((16, 16, 16), 3), ((7, 9, 11), 2), ((15, 15, 15), 4), ((8, 8, 24), 1)])
+def test_window_standardize_batched_and_unaligned(cuda, lib, shape, n):
+    """K8 over a stack of volumes in three launches: per-volume statistics, and volumes that do not start on a 16-byte
+    boundary (8k-1 sizes in a batch: count % 8 != 0) take the scalar path instead of failing."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(16)
+    hu = ((torch.randn((n,) + shape, generator=g) * 400 - 700) + 150 * torch.arange(n).view(-1, 1, 1, 1)).round()
+    hu = hu.clamp(-2048, 1500).to(torch.int16)
+    got, stats = ops.window_standardize(hu.to(cuda), batched=True)
+    only = ops.window_stats(hu.to(cuda))
+    assert torch.equal(only, stats) and stats.shape == (n, 2)
+    for b in range(n):
+        v = (torch.clamp(hu[b].float(), min=-1150, max=-300) + 1150) / 850
+        ref = (v - v.mean()) / v.std()
+        assert (got[b].cpu() - ref).abs().max().item() < 2e-5
+        assert abs(stats[b, 0].item() - v.mean().item()) < 1e-6 and abs(stats[b, 1].item() - v.std().item()) < 1e-6
+        one, st1 = ops.window_standardize(hu[b].to(cuda).contiguous())
+        assert (one - got[b]).abs().max().item() < 1e-6   # (fp64 atomics may order differently: last-bit differences)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape,n", [((16, 32, 32), 2), ((15, 31, 23), 2), ((9, 16, 40), 1)])
+def test_stem_from_hu_equals_window_then_stem(cuda, lib, shape, n, dt):
+    """The int16-HU stem (K8's apply pass fused into the producers) gives bit for bit what K8 + the fp32 stem give."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(17)
+    hu = (torch.randn((n,) + shape, generator=g) * 400 - 700).round().clamp(-2048, 1500).to(torch.int16).to(cuda)
+    w = torch.randn((64, 1, 7, 7, 7), generator=g).to(cuda) * 0.05
+    packed, mult = ops.pack_stem_weight_fused(w, dtype=dt, normalize=True)
+    bias = torch.randn(64, generator=g).to(cuda) * 0.1
+    img, stats = ops.window_standardize(hu, batched=True)
+    want = ops.stem_conv7(img, packed, bias, mult)
+    got = ops.stem_conv7_hu(hu, stats, packed, bias, mult)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("shape", [(16, 16, 16), (7, 9, 11)])
 def test_window_standardize(cuda, lib, shape):
     """functional.py:13-26 + intensity_transforms.py:104-114 (unbiased std)."""

@@ -81,13 +81,27 @@ def main():
     ess = (lungs & (torch.rand((B, S, S, S), device=dev) < 0.3).to(torch.uint8))
     ms = timeit(lambda: ops.masked_pool(dense0, lungs))
     report("K6 masked_pool (one map)", ms, B * (h ** 3 * 4 + h ** 3))
-    ms = timeit(lambda: ops.dram_upsample_mask(dense0, dense1, ess, lungs, (S, S, S)))
-    report("K7 dRAM upsample x ess", ms, B * (2 * h ** 3 * 4 + 2 * V + 2 * V * 4))
+    # realistic masks: ellipsoid lungs (24 % of the volume), ess = 8 % of the lung in blobs (bench.make_volumes)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    hu_b, lungs_b, ess_b = bench.make_volumes(B, (S, S, S), dev, seed=0)
+    for tag, e_, l_ in (("random 7.5 % ess", ess, lungs), ("synthetic CT masks", ess_b, lungs_b)):
+        for mode in ("rows", "staged"):
+            os.environ["DRAM_B200_K7"] = mode
+            ms = timeit(lambda: ops.dram_upsample_mask(dense0, dense1, e_, l_, (S, S, S)))
+            report(f"K7 dRAM {mode}, {tag}", ms, B * (2 * h ** 3 * 4 + 2 * V + 2 * V * 4))
+    os.environ.pop("DRAM_B200_K7", None)
     # K8 window + standardise
-    hu = (torch.randn((S, S, S), device=dev) * 400 - 600).round().clamp(-1024, 1500).to(torch.int16)
-    out = torch.empty((S, S, S), dtype=torch.float32, device=dev)
-    ms = timeit(lambda: ops.window_standardize(hu, out=out))
-    report("K8 window+standardise (1 vol)", ms, V * (2 + 2 + 4))
+    hu = hu_b
+    out = torch.empty((B, S, S, S), dtype=torch.float32, device=dev)
+    ms = timeit(lambda: ops.window_standardize(hu, out=out, batched=True))
+    report(f"K8 window+standardise ({B} vol, 3 launches)", ms, B * V * (2 + 2 + 4))
+    ms = timeit(lambda: ops.window_stats(hu))
+    report(f"K8 statistics pass only ({B} vol)", ms, B * V * 2)
+    stats = ops.window_stats(hu)
+    ms = timeit(lambda: ops.stem_conv7_hu(hu, stats, wp, bias, mult, out=x))
+    report("K2 stem fused from int16 HU", ms, B * (V * 2 + h ** 3 * 128), flops=2.0 * B * h ** 3 * 64 * 343)
 
 
 if __name__ == "__main__":
