@@ -5,15 +5,19 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one pass of the device-resident hot path over one batch of B volumes per GPU:
-K8 HU window+standardise -> stem unfold -> 38 tcgen05 conv launches (BN/ReLU/residual/heads fused) ->
-max-pool / x2 up-sampling -> lobe-masked pooling -> dRAM (trilinear to CT size x ess mask) + lesion %.
+K8 HU window statistics -> stem (window + standardise fused into its producers) -> 37 more tcgen05 conv launches
+(BN/ReLU/residual/heads fused) -> max-pool / x2 up-sampling -> dRAM (trilinear to CT size x ess mask) + lesion %.
 Prints ONE JSON line (rank 0).  `value` = volumes/s with the int16 HU volumes and masks already in HBM;
-`e2e` = the same through ScanRegLightningModule.predict_step with pinned HOST buffers (fp32 image + bool
-masks copied host->device and the percentages read back every step).  Multi-GPU: volumes are sharded
-across ranks, no data-path collective (weak scaling); time = max over ranks.
+`e2e` = the same through ScanRegLightningModule.predict_step with pinned HOST buffers: fp32 image + bool masks copied
+host->device every step, and what the product ships copied back every step — both uint8 heat-maps of every volume
+(processor.py:111-158, K f2) and the lesion percentages; `e2e_product` = the same loop fed what processor.py really
+sends (int16 HU + uint8 lobe labels, 3 B/voxel; the lung / LAA-910 masks are made on the device by f1).
+Multi-GPU: volumes are sharded across ranks, no data-path collective (weak scaling); time = max over ranks.
 
 `--impl reference` times the reference's algorithm on the host cores (the oracle port of the reference's
 PyTorch CPU path; /root/reference itself does not exist on the GPU box) on the same config.
+`--impl cudnn` is the GPU yard-stick of SURVEY §8d: the same oracle (= the reference's ATen call sequence) on the
+B200 under this image's torch/cuDNN, fp32 with TF32 convolutions (`value`) and bf16 channels_last_3d (extra field).
 """
 import argparse
 import json
@@ -183,13 +187,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def measured_peaks():
+def measured_peaks(burst=False):
+    """Dense 16-bit tensor peak: the sustained figure (a kernel timed inside a long step) or the burst one."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         with open(path) as f:
             p = json.load(f)
+        if burst:
+            return float(p.get("bf16_tflops", FALLBACK_TFLOPS)), "measured (MEASURED_PEAKS.json bf16_tflops)"
         return float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
     return FALLBACK_TFLOPS, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_pipe(arch, dims):
+    """Tensor-pipe utilisation per convolution family from the committed single-pass ncu capture
+    (profiles/tensor_pipe.json, written by tools/summarize_tensor_pipe.py); None when no capture matches."""
+    path = os.path.join(ROOT, "profiles", "tensor_pipe.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    return t.get(f"{arch}:{'x'.join(str(v) for v in dims)}")
 
 
 def measured_traffic(arch, dims, batch):
@@ -280,6 +298,74 @@ def cpu_baseline(module, dims, arch=ARCH, budget_s=30.0):
         t = cpu_predict_seconds(sd, tuple(dims), arch=arch)
         sample = f"1 full {'x'.join(map(str, dims))} volume, one pass ({t:.2f} s)"
     return {"value": 1.0 / t, "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
+
+
+# --------------------------------------------------------------------------------------------
+# GPU yard-stick: the reference's ATen call sequence (the oracle) under torch/cuDNN on the same B200
+# --------------------------------------------------------------------------------------------
+def cudnn_yardstick(module, dims, arch, batch, device, steps=5, warmup=2):
+    """"the unmodified reference module under torch 2.11/cuDNN on the same B200, fp32-TF32 and bf16".
+    /root/reference does not exist on the GPU box, so the oracle — a functional restatement that issues the very
+    ATen ops of med3d.py / models.py:430-450 — stands in for the module.  Bench-only: the product never imports it.
+    Returns volumes/s for (a) fp32 tensors with TF32 convolutions (cuDNN's default since Ampere), NCDHW as the
+    reference allocates them, and (b) bf16 tensors in channels_last_3d."""
+    from oracle import pipeline_oracle as P
+    from oracle import synthetic
+
+    torch.backends.cudnn.benchmark = True
+    sd32 = {k: v.to(device) for k, v in cpu_state_dict(module).items()}
+    xs, ls, es = zip(*[synthetic.make_network_input(i, dims) for i in range(batch)])
+    base = {"image": torch.stack(xs).to(device), "lung_mask": torch.stack(ls).bool().to(device),
+            "ess_mask": torch.stack(es).bool().to(device)}
+
+    def run(sd, b, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.no_grad():
+            for _ in range(warmup):
+                P.predict_step(sd, arch, b)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                out = P.predict_step(sd, arch, b)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, out
+
+    res = {"unit": "volumes/s", "batch": batch, "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),
+           "what": "oracle.pipeline_oracle.predict_step (the reference's ATen ops: conv3d/batch_norm/relu/max_pool3d/"
+                   "interpolate/cat/sigmoid) on cuda:0, cudnn.benchmark=True, inputs resident, standardised fp32 image in"}
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ms, out32 = run(sd32, base, steps)
+    res["fp32_tf32"] = {"value": batch / (ms * 1e-3), "ms_per_step": ms}
+    try:
+        sd16 = {k: (v.to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else
+                    (v.to(torch.bfloat16) if v.is_floating_point() else v)) for k, v in sd32.items()}
+        b16 = dict(base, image=base["image"].to(torch.bfloat16))
+        # (the 1-channel input is channels-last by construction; every 5-D weight is, so cuDNN runs NDHWC kernels)
+        ms16, out16 = run(sd16, b16, steps)
+        err = (out16["cle_dense_outs"].float() - out32["cle_dense_outs"]).abs().max().item()
+        res["bf16_channels_last_3d"] = {"value": batch / (ms16 * 1e-3), "ms_per_step": ms16,
+                                        "dram_max_abs_vs_fp32": err}
+    except Exception as exc:
+        res["bf16_channels_last_3d"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    return res
+
+
+def run_cudnn_arm(args, out):
+    """`--impl cudnn`: one JSON line, value = fp32/TF32 volumes/s of the yard-stick (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    dims = parse_dims(args)
+    module = build_module(device, args.arch)
+    y = cudnn_yardstick(module, dims, args.arch, args.batch, device, steps=args.steps, warmup=max(1, args.warmup))
+    line = {"impl": "cudnn", "metric": METRIC, "value": y["fp32_tf32"]["value"], "unit": "volumes/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": y["fp32_tf32"]["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 convolutions)",
+            "data": "synthetic", "config": {"workload": workload_name(args.arch, dims, args.batch)}, "gpu_yardstick": y}
+    out.emit(json.dumps(line))
 
 
 def run_reference_arm(args, out):
@@ -466,7 +552,9 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--dims", default="", help="D,H,W (overrides --size), e.g. 400,512,512")
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_NAMES))
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cudnn"])
+    ap.add_argument("--no-yardstick", dest="yardstick", action="store_false",
+                    help="skip the cuDNN yard-stick field of the main line (N=1 only; a few seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-bn", default="peer", choices=["peer", "nccl"],
                     help="--mode train on >1 GPU: SyncBatchNorm statistics over the peer-memory kernel (K10x) or NCCL")
@@ -478,6 +566,9 @@ def main():
     sink = _StdoutToStderr()
     if args.impl == "reference":
         run_reference_arm(args, sink)
+        return
+    if args.impl == "cudnn":
+        run_cudnn_arm(args, sink)
         return
     if args.mode == "train":
         run_train_arm(args, sink)
@@ -516,15 +607,19 @@ def main():
     clocks = sampler.stop(skip=first_sample) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    launches_per_step = len(eng.steps) + 2 + 2  # K8 statistics + finalize; the recorded steps (int16-HU stem first); K7 + finalize
+    launches_per_step = len(eng.steps) + 3 + 2  # K8 statistics + finalize + table; the recorded steps (int16-HU stem first); K7 + finalize
 
     # ---- end to end through the public predict_step with pinned host buffers -----------------
-    win = eng.image.detach().cpu()  # the standardised fp32 volumes predict_step receives from the transforms
-    host = {"image": win.pin_memory(), "lung_mask": lungs.bool().cpu().pin_memory(),
-            "ess_mask": ess.bool().cpu().pin_memory()}
-    h2d = sum(t.numel() * t.element_size() for t in host.values())
-    res_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
+    from dram_b200 import ops
     from dram_b200.models import DevicePrefetcher
+
+    win, _ = ops.window_standardize(hu, batched=True)   # the standardised fp32 volumes predict_step receives from the transforms
+    host = {"image": win.cpu().pin_memory(), "lung_mask": lungs.bool().cpu().pin_memory(),
+            "ess_mask": ess.bool().cpu().pin_memory()}
+    del win
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    D, H, W = dims
+    full_box = [(0, D), (0, H), (0, W)]
 
     # host->device bandwidth of this box for the same buffers (explains e2e when the PCIe link is the limit)
     probe_dst = {k: torch.empty_like(v, device=device) for k, v in host.items()}
@@ -541,38 +636,103 @@ def main():
 
     copy_streams = int(os.environ.get("DRAM_B200_COPY_STREAMS", "1"))  # DevicePrefetcher's default; > 1 = chunked over several DMA streams (A/B)
 
-    def e2e_pass(n_steps):
-        # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's
-        # side stream, overlapping the previous step's kernels) and reads its scores back before the next
-        for i, dev_batch in enumerate(DevicePrefetcher((host for _ in range(n_steps)), device, copy_streams=copy_streams)):
-            p = module.predict_step(dev_batch, i)
-            res_host[0].copy_(p["cle_precentages"], non_blocking=True)
-            res_host[1].copy_(p["pse_precentages"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller consumes the scores of every step
+    class ResultSink:
+        """The output half of the predict loop: per step the two uint8 heat-maps of every volume (f2: resample to the
+        crop box, paste, window to uint8 — here the box is the whole volume) and the percentages go to pinned host
+        memory on a side stream; two buffer sets, a set is reused only after its copy has finished."""
 
-    e2e_pass(2)
-    torch.cuda.synchronize()
-    barrier(world)
-    torch.cuda.synchronize()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    e2e_pass(args.steps)
-    t1.record()
-    torch.cuda.synchronize()
-    barrier(world)
-    e2e_ms = max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps
+        def __init__(self):
+            self.stream = torch.cuda.Stream(device=device)
+            self.dev = [[torch.empty((2, B, D, H, W), dtype=torch.uint8, device=device), torch.empty((2, B), device=device)]
+                        for _ in range(2)]
+            self.host = [[torch.empty((2, B, D, H, W), dtype=torch.uint8).pin_memory(), torch.empty((2, B)).pin_memory()]
+                         for _ in range(2)]
+            self.done = [None, None]
+            self.bytes_per_step = 2 * B * D * H * W + 2 * B * 4
+
+        def push(self, i, pred):
+            k = i % 2
+            if self.done[k] is not None:
+                self.done[k].synchronize()     # the consumer has taken step i-2's results
+            maps, pct = self.dev[k]
+            for m, key in enumerate(("cle_dense_outs", "pse_dense_outs")):
+                for b in range(B):
+                    ops.heatmap_u8(pred[key][b, 0], full_box, dims, out=maps[m, b])
+            pct[0].copy_(pred["cle_precentages"])
+            pct[1].copy_(pred["pse_precentages"])
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                self.host[k][0].copy_(maps, non_blocking=True)
+                self.host[k][1].copy_(pct, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self.done[k] = ev
+
+        def finish(self):
+            for ev in self.done:
+                if ev is not None:
+                    ev.synchronize()
+
+    def e2e_pass(n_steps, batches, step_fn):
+        # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's side
+        # stream, overlapping the previous step's kernels) and every step's heat-maps + scores go back to the host
+        sink = ResultSink()
+        for i, dev_batch in enumerate(DevicePrefetcher((batches for _ in range(n_steps)), device, copy_streams=copy_streams)):
+            sink.push(i, step_fn(dev_batch, i))
+        sink.finish()
+        return sink.bytes_per_step
+
+    def timed_e2e(batches, step_fn):
+        e2e_pass(2, batches, step_fn)
+        torch.cuda.synchronize()
+        barrier(world)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        d2h = e2e_pass(args.steps, batches, step_fn)
+        t1.record()
+        torch.cuda.synchronize()
+        barrier(world)
+        return max_over_ranks(t0.elapsed_time(t1), world, device) / args.steps, d2h
+
+    e2e_ms, d2h = timed_e2e(host, lambda b, i: module.predict_step(b, i))
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": res_host.numel() * 4, "ms_per_step": e2e_ms,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
            "h2d_gbs_idle_probe": h2d_gbs, "copy_streams": copy_streams,
-           "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> "
-                  "percentages to host (pinned fp32 image + bool masks copied every step, double-buffered)"}
+           "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> heatmap_u8 of "
+                  "both dRAMs of every volume + percentages -> pinned host memory (fp32 image + bool masks in, "
+                  "uint8 heat-maps + scores out, every step, double-buffered both ways)"}
 
-    # ---- roofline of the dominant kernel (conv3d_umma_kernel): per-launch CUDA events ----------
+    # the product's own wire format: int16 HU + uint8 lobe labels in (3 B/voxel); lung / ess masks made on the device
+    lobes = (lungs * 3).to(torch.uint8)  # any non-zero label: dataset.py:66 only tests lobe > 0
+    host_p = {"scan": hu.cpu().pin_memory(), "lobes": lobes.cpu().pin_memory()}
+    h2d_p = sum(t.numel() * t.element_size() for t in host_p.values())
+
+    crop_bufs = [(torch.empty((B, D, H, W), dtype=torch.int16, device=device),
+                  torch.empty((B, D, H, W), dtype=torch.uint8, device=device),
+                  torch.empty((B, D, H, W), dtype=torch.uint8, device=device)) for _ in range(2)]
+
+    def product_step(b, i):
+        im, lg, es = crop_bufs[i % 2]
+        for v in range(B):  # f1 (dataset.py:66-80): blank outside the twice-dilated lung, LAA-910 mask; crop = whole volume
+            ops.lung_crop(b["scan"][v], b["lobes"][v], full_box, out=(im[v], lg[v], es[v]))
+        return module.predict_step_from_hu(im, lg, es)
+
+    e2e_p_ms, d2h_p = timed_e2e(host_p, product_step)
+    e2e_product = {"value": world * B / (e2e_p_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d_p,
+                   "d2h_bytes_per_step": d2h_p, "ms_per_step": e2e_p_ms,
+                   "api": "int16 HU + uint8 lobe labels from pinned host memory -> f1 lung_crop (masks on the device) -> "
+                          "predict_step_from_hu -> heatmap_u8 x2 per volume -> uint8 heat-maps + percentages to the host"}
+    del host, host_p, crop_bufs
+
+    # ---- roofline of the convolutions: per-launch CUDA events over eager launches --------------
     conv_steps = [s for s in eng.steps if s.flops > 0]
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in conv_steps]
     conv_ms = 0.0
     reps = min(args.steps, 5)
+    ops.window_standardize(hu, out=eng.image, batched=True)
     for _ in range(reps):
         ci = 0
         for s in eng.steps:
@@ -587,15 +747,23 @@ def main():
         conv_ms += sum(a.elapsed_time(b) for a, b in evs)
     conv_ms /= reps
     conv_flops = sum(s.flops for s in conv_steps)
+    exec_flops = sum(s.executed_flops for s in conv_steps)
     peak, peak_src = measured_peaks()
+    burst = measured_peaks(burst=True)[0]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    executed = exec_flops / (conv_ms * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic(args.arch, dims, B)
     roofline = {"bound": "tensor",
                 "kernel": f"conv3d_stem_kernel + conv3d_slab_kernel + conv3d_umma_kernel ({len(conv_steps)} launches/step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
-                "share_of_step": conv_ms / ms_per_step}
+                "share_of_step": conv_ms / ms_per_step,
+                # what the tensor pipe really executes: zero-padding taps skipped (dilated layers), border tiles and
+                # the stem's K padded (343 -> 448); `achieved` above counts the reference's 2*M*N*K
+                "executed_flops_per_step": exec_flops, "achieved_executed": executed, "frac_executed": executed / peak,
+                "peak_burst": burst, "frac_of_burst": achieved / burst, "frac_executed_of_burst": executed / burst,
+                "tensor_pipe_pct": measured_tensor_pipe(args.arch, dims)}
 
     if world > 1:
         import torch.distributed as dist
@@ -607,15 +775,22 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16 operands / f32 accumulate", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16 operands / f32 accumulate" if eng.act_dtype == torch.float16 else "bf16 operands / f32 accumulate",
+        "data": "synthetic",
         "config": {"workload": workload_name(args.arch, dims, B),
                    "global_batch": world * B, "parallelism": f"volume-sharded x{world}, no collective",
                    "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                   "storage_dtype": str(eng.act_dtype)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+                   "storage_dtype": str(eng.act_dtype), "cuda_graph": ops.graphs_enabled()},
+        "clocks": clocks, "e2e": e2e, "e2e_product": e2e_product, "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
     }
     if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
+    if args.yardstick and world == 1:
+        try:
+            line["gpu_yardstick"] = cudnn_yardstick(module, dims, args.arch, B, device, steps=min(args.steps, 5))
+        except Exception as exc:  # the yard-stick must never cost the headline line
+            line["gpu_yardstick"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     sink.emit(json.dumps(line))
 
 

@@ -58,10 +58,11 @@ SIGNATURES = {
     "dram_conv3d_plan_destroy": (C.c_int, [_vp]),
     "dram_conv3d_run": (C.c_int, [_vp, _i32, _vp]),
     "dram_conv3d_plan_info": (C.c_int, [_vp, C.POINTER(_i64), _pi32, _pi32, _pi32, _pi32]),
+    "dram_conv3d_plan_executed_flops": (C.c_int, [_vp, C.POINTER(_i64)]),
     "dram_stem_expand": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_stem_weight_bytes": (_sz, []),
     "dram_stem_conv7": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "dram_stem_conv7_hu": (C.c_int, [_vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
+    "dram_stem_conv7_hu": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32,
                                      _i32, _vp]),
     "dram_maxpool3d": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_upsample2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "dram_preprocess_workspace_bytes_n": (_sz, [_i32]),
     "dram_window_standardize_batch": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_float, C.c_float, _vp]),
     "dram_window_stats": (C.c_int, [_vp, _vp, _vp, _i32, _i64, C.c_float, C.c_float, _vp]),
+    "dram_window_lut": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_float, C.c_float, _vp]),
     "dram_resize_image": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_resize_mask": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_mask_bbox": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

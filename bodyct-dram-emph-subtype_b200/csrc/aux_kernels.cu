@@ -652,6 +652,14 @@ __global__ void window_finalize_kernel(const double *__restrict__ sums, float *_
     stats_out[2 * v + 1] = stats[2 * v + 1];
   }
 }
+// Table of K8's result for every integer HU value of the window: lut[v][i] = ((lo + i - lo) / (hi - lo) - mean_v) / sd_v,
+// evaluated with the very expression of window_apply_kernel (clamping is the identity inside the window).
+__global__ void window_lut_kernel(const float *__restrict__ stats, float *__restrict__ lut, int size, float lo, float hi) {
+  const int v = blockIdx.y;
+  const float mean = stats[2 * v], sd = stats[2 * v + 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size; i += gridDim.x * blockDim.x)
+    lut[(int64_t)v * size + i] = (window_value((short)((int)lo + i), lo, hi) - mean) / sd;
+}
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 window_apply_kernel(const short *__restrict__ hu_all, float *__restrict__ out_all, const float *__restrict__ stats,
@@ -961,6 +969,23 @@ extern "C" int dram_window_stats(const int16_t *hu, float *stats_out, void *work
                                  float lo, float hi, void *stream) {
   DRAM_REQUIRE(stats_out, "dram_window_stats: stats_out is required");
   return window_stats_launch(hu, stats_out, workspace, n, count, lo, hi, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int dram_window_lut(const int16_t *hu, float *lut, float *stats_out, void *workspace, int32_t n,
+                               int64_t count, float lo, float hi, void *stream) {
+  DRAM_REQUIRE(lut, "dram_window_lut: lut is required");
+  DRAM_REQUIRE(lo == floorf(lo) && hi == floorf(hi) && lo >= -32768.0f && hi <= 32767.0f &&
+                   (int)hi - (int)lo + 1 <= DRAM_WINDOW_LUT_MAX,
+               "dram_window_lut: the window must have integral bounds inside int16 and at most %d values",
+               DRAM_WINDOW_LUT_MAX);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = window_stats_launch(hu, stats_out, workspace, n, count, lo, hi, st, nullptr);
+  if (rc != DRAM_OK) return rc;
+  const float *stats = reinterpret_cast<const float *>(reinterpret_cast<double *>(workspace) + 2 * n);
+  const int size = (int)hi - (int)lo + 1;
+  window_lut_kernel<<<dim3(ceil_div(size, 256), n), 256, 0, st>>>(stats, lut, size, lo, hi);
+  DRAM_CHECK_LAUNCH("window_lut_kernel");
+  return DRAM_OK;
 }
 
 extern "C" int dram_window_standardize_batch(const int16_t *hu, float *out, float *stats_out, void *workspace,

@@ -41,8 +41,8 @@ static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT
 struct StemParams {
   const float *x;       // fp32 [n][D][H][W] (kernel variant HU = false)
   const short *hu;      // int16 HU [n][D][H][W] (HU = true): window + standardise happen in the producers
-  const float *stats;   // HU: fp32 [n][2] = mean, unbiased std of each windowed volume (dram_window_stats)
-  float lo, hi;         // HU: intensity window
+  const float *lut;     // HU: fp32 [n][lut_size], lut[v][i] = standardised value of HU lut_lo + i for volume v
+  int lut_lo, lut_size; // HU: window lower bound (integral) and number of table entries (hi - lo + 1)
   const uint4 *weight;  // 16-bit, even kd [8][4][64][8] then odd kd [8][3][64][8] (ops.pack_stem_weight_fused)
   int n, D, H, W;       // input dims
   int cols_w, cols_h, groups_d, items_total;
@@ -85,13 +85,12 @@ __device__ __forceinline__ uint32_t pack_pair(float a, float b, int is_f16) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-// The K8 arithmetic (aux_kernels.cu window_value / window_apply_kernel), so that the fused path feeds the tensor
-// cores exactly the values the two-kernel path would: ((clamp(hu) - lo) / (hi - lo) - mean) / sd in fp32.
-__device__ __forceinline__ float stem_standardize(short hu, float lo, float hi, float mean, float sd) {
-  float f = (float)hu;
-  f = fminf(fmaxf(f, lo), hi);
-  f = (f - lo) / (hi - lo);
-  return (f - mean) / sd;
+// HU variant: the window clamps every voxel to one of (hi - lo + 1) integer values (851 for the reference's
+// [-1150, -300]), so K8's per-voxel arithmetic ((clamp(hu) - lo) / (hi - lo) - mean) / sd — two IEEE divisions —
+// is tabulated once per volume by dram_window_lut and the producers only clamp (packed 16-bit min/max) and
+// gather from a 3.4 KB table that lives in L1: exactly K8's values, none of its arithmetic in this kernel.
+__device__ __forceinline__ uint32_t stem_lut_index2(uint32_t pair, uint32_t lo2, uint32_t hi2) {
+  return __vsub2(__vmins2(__vmaxs2(pair, lo2), hi2), lo2);  // two signed 16-bit lanes: clamp(hu, lo, hi) - lo
 }
 
 template <bool HU>
@@ -165,11 +164,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
         const size_t plane_off = ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
         const float *xz = HU ? nullptr : p.x + plane_off;
         const short *hz = HU ? p.hu + plane_off : nullptr;
-        float mean = 0.0f, sd = 1.0f;
-        if constexpr (HU) {
-          mean = __ldg(p.stats + 2 * it.sample);
-          sd = __ldg(p.stats + 2 * it.sample + 1);
-        }
+        const float *lut = HU ? p.lut + (size_t)it.sample * p.lut_size : nullptr;
+        const uint32_t lo2 = ((uint32_t)(uint16_t)(short)p.lut_lo) * 0x10001u;
+        const uint32_t hi2 = ((uint32_t)(uint16_t)(short)(p.lut_lo + p.lut_size - 1)) * 0x10001u;
         const uint32_t dst0 = plane_addr(slot);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -190,14 +187,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
                   for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint32_t *>(row + iw0) + q);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    f[c][2 * q] = stem_standardize((short)(u[q] & 0xffffu), p.lo, p.hi, mean, sd);
-                    f[c][2 * q + 1] = stem_standardize((short)(u[q] >> 16), p.lo, p.hi, mean, sd);
+                    const uint32_t ix = stem_lut_index2(u[q], lo2, hi2);
+                    f[c][2 * q] = __ldg(lut + (ix & 0xffffu));
+                    f[c][2 * q + 1] = __ldg(lut + (ix >> 16));
                   }
                 } else {
 #pragma unroll
                   for (int q = 0; q < 8; ++q) {
                     const int iw = iw0 + q;
-                    if (iw >= 0 && iw < p.W) f[c][q] = stem_standardize(__ldg(row + iw), p.lo, p.hi, mean, sd);
+                    if (iw >= 0 && iw < p.W)
+                      f[c][q] = __ldg(lut + (stem_lut_index2((uint32_t)(uint16_t)__ldg(row + iw), lo2, hi2) & 0xffffu));
                   }
                 }
               } else {
@@ -395,16 +394,18 @@ extern "C" int dram_stem_conv7(const float *x, const void *weight, const float *
   return stem_launch(p, weight, bias, scale, out, n, d, h, w, relu, dtype, max_ctas, stream, false);
 }
 
-extern "C" int dram_stem_conv7_hu(const int16_t *hu, const float *stats, float lo, float hi, const void *weight,
-                                  const float *bias, const float *scale, void *out, int32_t n, int32_t d, int32_t h,
-                                  int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas, void *stream) {
-  DRAM_REQUIRE(hu && stats, "dram_stem_conv7_hu: null pointer");
-  DRAM_REQUIRE(hi > lo, "dram_stem_conv7_hu: empty window");
+extern "C" int dram_stem_conv7_hu(const int16_t *hu, const float *lut, int32_t lut_lo, int32_t lut_size,
+                                  const void *weight, const float *bias, const float *scale, void *out, int32_t n,
+                                  int32_t d, int32_t h, int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas,
+                                  void *stream) {
+  DRAM_REQUIRE(hu && lut, "dram_stem_conv7_hu: null pointer");
+  DRAM_REQUIRE(lut_size >= 2 && lut_size <= DRAM_WINDOW_LUT_MAX && lut_lo >= -32768 && lut_lo + lut_size - 1 <= 32767,
+               "dram_stem_conv7_hu: bad table range [%d, %d]", lut_lo, lut_lo + lut_size - 1);
   StemParams p;
   memset(&p, 0, sizeof(p));
   p.hu = reinterpret_cast<const short *>(hu);
-  p.stats = stats;
-  p.lo = lo;
-  p.hi = hi;
+  p.lut = lut;
+  p.lut_lo = lut_lo;
+  p.lut_size = lut_size;
   return stem_launch(p, weight, bias, scale, out, n, d, h, w, relu, dtype, max_ctas, stream, true);
 }

@@ -684,6 +684,50 @@ extern "C" int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops,
   return DRAM_OK;
 }
 
+// What the kernels actually issue to the tensor pipe: full 128-voxel tiles (border tiles are padded), every
+// non-skipped (tap, chunk) stage at the plan's BLOCK_N — i.e. the algorithmic 2*M*N*K minus the taps skipped in the
+// zero padding plus the tile-quantisation padding.
+static bool host_tap_is_padding(int i0, int extent, int stride, int in_size) {
+  return (i0 + (extent - 1) * stride < 0) || (i0 >= in_size);
+}
+static bool host_brick_tap_skipped(const ConvKParams &p, int m_tile, int zd, int zh, int zw) {
+  const int r = m_tile % p.tiles_per_sample;
+  const int iw = r % p.tiles_w, r2 = r / p.tiles_w, ih = r2 % p.tiles_h, id = r2 / p.tiles_h;
+  return host_tap_is_padding(id * p.td * p.sd + zd * p.dd - p.pd, p.td, p.sd, p.Di) ||
+         host_tap_is_padding(ih * p.th * p.sh + zh * p.dh - p.ph, p.th, p.sh, p.Hi) ||
+         host_tap_is_padding(iw * p.tw * p.sw + zw * p.dw - p.pw, p.tw, p.sw, p.Wi);
+}
+
+extern "C" int dram_conv3d_plan_executed_flops(const dram_conv_plan *plan, int64_t *flops) {
+  DRAM_REQUIRE(plan && flops, "dram_conv3d_plan_executed_flops: null argument");
+  if (plan->kind == 1) {  // plane ring: every item issues 4 planes x 27 taps x all chunks, N = cout
+    const SlabParams &sp = plan->sp;
+    *flops = 2LL * sp.items_total * 4 * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
+    return DRAM_OK;
+  }
+  const ConvKParams &p = plan->p;
+  const int m_tiles = plan->m_tiles;
+  int64_t stages = 0;  // (brick, tap) pairs issued, per n-tile
+  if (plan->pair) {
+    for (int pr = 0; 2 * pr < m_tiles; ++pr)
+      for (int zd = 0; zd < p.kd; ++zd)
+        for (int zh = 0; zh < p.kh; ++zh)
+          for (int zw = 0; zw < p.kw; ++zw) {
+            const bool s0 = host_brick_tap_skipped(p, 2 * pr, zd, zh, zw);
+            const bool s1 = 2 * pr + 1 < m_tiles ? host_brick_tap_skipped(p, 2 * pr + 1, zd, zh, zw) : true;
+            if (!(s0 && s1)) stages += 2;  // both bricks run the MMA when either needs the tap
+          }
+  } else {
+    for (int m = 0; m < m_tiles; ++m)
+      for (int zd = 0; zd < p.kd; ++zd)
+        for (int zh = 0; zh < p.kh; ++zh)
+          for (int zw = 0; zw < p.kw; ++zw)
+            if (!host_brick_tap_skipped(p, m, zd, zh, zw)) ++stages;
+  }
+  *flops = 2LL * stages * p.num_n_tiles * 128 * (int64_t)plan->block_n * p.chunks_total * 64;
+  return DRAM_OK;
+}
+
 extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, void *stream) {
   DRAM_REQUIRE(plan, "dram_conv3d_run: null plan");
   int ctas = sm_count();

@@ -29,10 +29,11 @@ def _conv_out(n, k, s, d, p):
 class _Step:
     """One launch of the recorded sequence."""
 
-    __slots__ = ("name", "fn", "flops")
+    __slots__ = ("name", "fn", "flops", "executed_flops")
 
-    def __init__(self, name, fn, flops=0):
+    def __init__(self, name, fn, flops=0, executed_flops=None):
         self.name, self.fn, self.flops = name, fn, flops
+        self.executed_flops = flops if executed_flops is None else executed_flops
 
 
 class Med3DEngine:
@@ -97,7 +98,7 @@ class Med3DEngine:
                               heads=heads, store_out=store_out, tile=tile, upsample_x1=upsample_x1)
         fl = plan.flops if flops is None else flops
         self.conv_flops += fl
-        self.steps.append(_Step(name, plan.run, fl))
+        self.steps.append(_Step(name, plan.run, fl, plan.executed_flops))
         return plan
 
     def _build(self):
@@ -136,8 +137,11 @@ class Med3DEngine:
             x = torch.empty((B, D1, H1, W1, 64), dtype=bf, device=dev)
             self.stem_weights, self.stem_out = sw, x   # for the int16-HU stem (predict_step_from_hu)
             self.conv_flops += stem_flops
+            # the fused stem pads K from 343 to 7 * 8 * 8 = 448 and its tiles to 8 x 16 x 4 output voxels
+            cd = lambda a, b: -(-a // b)  # noqa: E731
+            stem_exec = 2 * B * (cd(D1, 4) * 4) * (cd(H1, 16) * 16) * (cd(W1, 8) * 8) * 64 * 448
             self.steps.append(_Step("conv1", lambda: ops.stem_conv7(self.image, sw[0], sw[1], sw[2], out=x),
-                                    stem_flops))
+                                    stem_flops, stem_exec))
         # ---- maxpool
         self.xp = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)
         self.steps.append(_Step("maxpool", lambda x=x: ops.maxpool3d(x, out=self.xp)))
@@ -238,16 +242,16 @@ class Med3DEngine:
         for st in self.steps[1:]:
             st.fn()
 
-    def hu_stem(self, hu, stats, lo=-1150.0, hi=-300.0):
+    def hu_stem(self, hu, lut, lo=-1150):
         """A replacement for the first recorded step (the stem convolution on `self.image`): the same kernel fed from
-        the int16 HU volumes [B,D,H,W] and their window statistics [B,2] (`ops.window_stats`), K8's apply pass fused
-        into its producers.  Pass it to `run_network(first=...)`."""
+        the int16 HU volumes [B,D,H,W] and their window tables (`ops.window_lut`), K8's apply pass folded into a
+        gather in its producers.  Pass it to `run_network(first=...)`."""
         if not hasattr(self, "stem_weights"):
             raise RuntimeError("the int16-HU stem needs the fused stem kernel (DRAM_B200_STEM=unfold is set)")
         if tuple(hu.shape) != (self.batch,) + self.dims:
             raise ValueError(f"hu shape {tuple(hu.shape)} does not match the engine's {(self.batch,) + self.dims}")
         w, b, m = self.stem_weights
-        return lambda: ops.stem_conv7_hu(hu, stats, w, b, m, out=self.stem_out, lo=lo, hi=hi)
+        return lambda: ops.stem_conv7_hu(hu, lut, w, b, m, out=self.stem_out, lo=lo)
 
     def run_network(self, first=None):
         """The recorded launch sequence on `self.image` -> `self.dense` (engine-owned), on the current stream.

@@ -283,10 +283,10 @@ class ScanRegLightningModule(_ScanModule):
 
     def predict_step_from_hu(self, hu, lung_mask, ess_mask, fuse_window=True):
         """The device-resident hot path of SURVEY §8d: int16 HU volumes already at network size [B,D,H,W] -> K8
-        window + standardise (per volume) -> network -> dRAM.  By default K8 is its statistics pass only and the stem
-        convolution windows and standardises while it loads the int16 volume (same arithmetic, same values; the fp32
-        image is never written); `fuse_window=False` writes the fp32 image first (what predict_step receives from the
-        transforms).  Returns the same dict as predict_step (without the bookkeeping keys)."""
+        window + standardise (per volume) -> network -> dRAM.  By default K8 is its statistics pass plus an 851-entry
+        table per volume, and the stem convolution clamps and gathers while it loads the int16 volume (the same values
+        bit for bit; the fp32 image is never written); `fuse_window=False` writes the fp32 image first (what
+        predict_step receives from the transforms).  Returns the same dict as predict_step (without the bookkeeping keys)."""
         with torch.no_grad():
             if not hu.is_cuda or hu.dtype != torch.int16:
                 raise RuntimeError("predict_step_from_hu: expected an int16 CUDA tensor [B,D,H,W]")
@@ -294,8 +294,8 @@ class ScanRegLightningModule(_ScanModule):
             eng = self.model.eval().engine(B, (D, H, W), hu.device)
             hu = hu.contiguous()
             if fuse_window and hasattr(eng, "stem_weights"):
-                stats = ops.window_stats(hu)  # statistics are per volume (intensity_transforms.py:104-114)
-                dense = eng.run_network(first=eng.hu_stem(hu, stats))
+                lut, _ = ops.window_lut(hu)  # statistics are per volume (intensity_transforms.py:104-114)
+                dense = eng.run_network(first=eng.hu_stem(hu, lut))
             else:
                 ops.window_standardize(hu, out=eng.image, batched=True)
                 dense = eng.run_network()

@@ -200,6 +200,9 @@ class Conv3dPlan:
         self.flops, self.m_tiles, self.n_tiles, self.block_n, self.stages = (
             flops.value, mt.value, nt.value, bn.value, abs(st.value))
         self.algo = "planes" if st.value < 0 else "tiles"
+        ex = C.c_int64()
+        check(lib.dram_conv3d_plan_executed_flops(handle, C.byref(ex)), "dram_conv3d_plan_executed_flops")
+        self.executed_flops = ex.value   # tap skipping and tile padding included (what the tensor pipe really does)
         self.desc = d
 
     def run(self, max_ctas=0):
@@ -329,12 +332,12 @@ def stem_conv7(x, weight, bias, scale=None, out=None, relu=True, max_ctas=0):
     return out
 
 
-def stem_conv7_hu(hu, stats, weight, bias, scale=None, out=None, relu=True, lo=-1150.0, hi=-300.0, max_ctas=0):
-    """K2 fed from int16 HU [N, D, H, W] + per-volume window statistics fp32 [N, 2] (`window_stats`): window,
-    standardise (K8's arithmetic), conv 7^3 s2 p3, scale/shift, ReLU in one kernel; the fp32 image never exists."""
+def stem_conv7_hu(hu, lut, weight, bias, scale=None, out=None, relu=True, lo=-1150, max_ctas=0):
+    """K2 fed from int16 HU [N, D, H, W] + the per-volume table fp32 [N, hi - lo + 1] of `window_lut`: window,
+    standardise (K8's values, tabulated), conv 7^3 s2 p3, scale/shift, ReLU in one kernel; the fp32 image never exists."""
     lib = _capi.load()
     _need(hu, torch.int16, "stem_conv7_hu hu", 4)
-    _need(stats, torch.float32, "stem_conv7_hu stats", 2)
+    _need(lut, torch.float32, "stem_conv7_hu lut", 2)
     _need16(weight, "stem_conv7_hu weight", 1)
     if weight.numel() != 7 * 8 * 64 * 8:
         raise ValueError("stem_conv7_hu: weight must hold 28672 values (pack_stem_weight_fused)")
@@ -342,16 +345,17 @@ def stem_conv7_hu(hu, stats, weight, bias, scale=None, out=None, relu=True, lo=-
     if scale is not None:
         _need(scale, torch.float32, "stem_conv7_hu scale", 1)
     n, d, h, w = hu.shape
-    if tuple(stats.shape) != (n, 2):
-        raise ValueError(f"stem_conv7_hu: stats must be [{n}, 2], got {tuple(stats.shape)}")
+    if lut.shape[0] != n:
+        raise ValueError(f"stem_conv7_hu: lut must have {n} rows, got {tuple(lut.shape)}")
     shape = (n, (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
     if out is None:
         out = torch.empty(shape, dtype=weight.dtype, device=hu.device)
     _need(out, weight.dtype, "stem_conv7_hu out", 5)
     if tuple(out.shape) != shape:
         raise ValueError(f"stem_conv7_hu: out shape {tuple(out.shape)} != {shape}")
-    check(lib.dram_stem_conv7_hu(_p(hu), _p(stats), lo, hi, _p(weight), _p(bias), _p(scale), _p(out), n, d, h, w,
-                                 1 if relu else 0, ACT_DTYPES[weight.dtype], max_ctas, _stream()), "dram_stem_conv7_hu")
+    check(lib.dram_stem_conv7_hu(_p(hu), _p(lut), int(lo), lut.shape[1], _p(weight), _p(bias), _p(scale), _p(out), n, d,
+                                 h, w, 1 if relu else 0, ACT_DTYPES[weight.dtype], max_ctas, _stream()),
+          "dram_stem_conv7_hu")
     return out
 
 
@@ -479,6 +483,22 @@ def window_stats(hu, lo=-1150.0, hi=-300.0):
     return stats
 
 
+def window_lut(hu, lo=-1150, hi=-300):
+    """K8 as a table: int16 HU [N, ...] -> (lut fp32 [N, hi - lo + 1], stats fp32 [N, 2]); lut[v, i] is the value
+    `window_standardize` gives a voxel of HU lo + i of volume v (voxels outside the window clamp to its ends)."""
+    lib = _capi.load()
+    _need(hu, torch.int16, "window_lut hu")
+    if int(lo) != lo or int(hi) != hi:
+        raise ValueError("window_lut: the window bounds must be integers")
+    n = hu.shape[0]
+    lut = torch.empty((n, int(hi) - int(lo) + 1), dtype=torch.float32, device=hu.device)
+    stats = torch.empty((n, 2), dtype=torch.float32, device=hu.device)
+    ws = torch.empty(lib.dram_preprocess_workspace_bytes_n(n) // 8, dtype=torch.float64, device=hu.device)
+    check(lib.dram_window_lut(_p(hu), _p(lut), _p(stats), _p(ws), n, hu.numel() // n, float(lo), float(hi), _stream()),
+          "dram_window_lut")
+    return lut, stats
+
+
 def slice_index(d_in, d_out, device):
     """The D-slice pick of Interpolate (spatial_transforms.py:66), built with the same torch ops."""
     return torch.linspace(0, d_in - 1, d_out).long().to(torch.int32).to(device)
@@ -516,9 +536,10 @@ def mask_bbox(mask):
     return bbox
 
 
-def lung_crop(scan, lobe, crop):
+def lung_crop(scan, lobe, crop, out=None):
     """f1 (dataset.py:66-80): int16 scan + uint8 lobe labels [D,H,W] and crop ((z0,z1),(y0,y1),(x0,x1)) ->
-    (image int16, lung uint8, ess uint8) of the crop size: blanking outside the twice-dilated lung, LAA-910."""
+    (image int16, lung uint8, ess uint8) of the crop size: blanking outside the twice-dilated lung, LAA-910.
+    `out`: optional preallocated (image, lung, ess) of the crop size (e.g. slices of a batch buffer)."""
     lib = _capi.load()
     _need(scan, torch.int16, "lung_crop scan", 3)
     _need(lobe, torch.uint8, "lung_crop lobe", 3)
@@ -527,9 +548,17 @@ def lung_crop(scan, lobe, crop):
     D, H, W = scan.shape
     (z0, z1), (y0, y1), (x0, x1) = [(int(a), int(b)) for a, b in crop]
     cd, ch, cw = z1 - z0, y1 - y0, x1 - x0
-    image = torch.empty((cd, ch, cw), dtype=torch.int16, device=scan.device)
-    lung = torch.empty((cd, ch, cw), dtype=torch.uint8, device=scan.device)
-    ess = torch.empty_like(lung)
+    if out is None:
+        image = torch.empty((cd, ch, cw), dtype=torch.int16, device=scan.device)
+        lung = torch.empty((cd, ch, cw), dtype=torch.uint8, device=scan.device)
+        ess = torch.empty_like(lung)
+    else:
+        image, lung, ess = out
+        _need(image, torch.int16, "lung_crop out image", 3)
+        _need(lung, torch.uint8, "lung_crop out lung", 3)
+        _need(ess, torch.uint8, "lung_crop out ess", 3)
+        if not (tuple(image.shape) == tuple(lung.shape) == tuple(ess.shape) == (cd, ch, cw)):
+            raise ValueError(f"lung_crop: out tensors must have the crop shape {(cd, ch, cw)}")
     ws = torch.empty(lib.dram_lung_crop_workspace_bytes(cd, ch, cw), dtype=torch.uint8, device=scan.device)
     check(lib.dram_lung_crop(_p(scan), _p(lobe), D, H, W, z0, y0, x0, cd, ch, cw, _p(image), _p(lung), _p(ess),
                              _p(ws), _stream()), "dram_lung_crop")

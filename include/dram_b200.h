@@ -145,6 +145,11 @@ int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, void *stream);
 /* Introspection for tests / roofline accounting. */
 int dram_conv3d_plan_info(const dram_conv_plan *plan, int64_t *flops, int32_t *m_tiles,
                           int32_t *n_tiles, int32_t *block_n, int32_t *stages);
+/* FLOPs the plan's kernel really issues to the tensor pipe per run: 2 * 128 * BLOCK_N * 64 for every (tile, tap,
+ * 64-channel chunk) stage it executes.  Differs from the algorithmic 2*M*N*K of dram_conv3d_plan_info by the taps
+ * skipped inside the zero padding (dilated layers: fewer) and by the padding of border tiles (more). */
+int dram_conv3d_plan_executed_flops(const dram_conv_plan *plan, int64_t *flops);
+
 
 /* ---- K2a: stem unfold (feeds K1 with taps 7x1x1, stride 2x1x1) --------- */
 /*
@@ -176,15 +181,18 @@ int dram_stem_conv7(const float *x, const void *weight, const float *bias, const
                     int32_t dtype, int32_t max_ctas, void *stream);
 /*
  * The same kernel fed straight from the int16 HU volume: IntensityWindow + Standardize
- * (functional.py:13-26, intensity_transforms.py:104-114; wired at models.py:60-61) are evaluated in the
- * producers with the arithmetic of dram_window_standardize, so the standardised fp32 image is never
- * written to or re-read from HBM (K8 shrinks to its statistics pass, dram_window_stats).
- *   hu    : int16 [n][d][h][w];  stats: fp32 [n][2] = (mean, unbiased std) of each windowed volume
- *   lo/hi : the window (-1150, -300 in the reference)
+ * (functional.py:13-26, intensity_transforms.py:104-114; wired at models.py:60-61) collapse to a table —
+ * the window clamps every voxel to one of hi - lo + 1 integer values (851 for [-1150, -300]) — that
+ * dram_window_lut fills per volume with K8's own arithmetic; the producers clamp and gather.  The values
+ * are exactly those of dram_window_standardize; the standardised fp32 image is never written to or re-read
+ * from HBM.
+ *   hu  : int16 [n][d][h][w];  lut: fp32 [n][lut_size], entry i = standardised value of HU lut_lo + i
  */
-int dram_stem_conv7_hu(const int16_t *hu, const float *stats, float lo, float hi, const void *weight,
-                       const float *bias, const float *scale, void *out, int32_t n, int32_t d, int32_t h,
-                       int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas, void *stream);
+#define DRAM_WINDOW_LUT_MAX 4096
+int dram_stem_conv7_hu(const int16_t *hu, const float *lut, int32_t lut_lo, int32_t lut_size,
+                       const void *weight, const float *bias, const float *scale, void *out, int32_t n,
+                       int32_t d, int32_t h, int32_t w, int32_t relu, int32_t dtype, int32_t max_ctas,
+                       void *stream);
 
 
 /* ---- K3: max-pool 3x3x3 stride 2 pad 1 (med3d.py:305, 374) ------------- */
@@ -249,7 +257,9 @@ int dram_window_standardize(const int16_t *hu, float *out, float *stats_out, voi
 /*
  * Batched forms: n volumes of `count` voxels each, stored back to back ([n][count]); statistics stay per
  * volume.  Three launches whatever n is (statistics of all volumes, finalize, apply).  stats_out: fp32 [n][2].
- * dram_window_stats runs the statistics pass only (for dram_stem_conv7_hu).  Workspace:
+ * dram_window_stats runs the statistics pass only; dram_window_lut adds the per-volume table
+ * lut[v][i] = standardised value of HU (int)lo + i, i in [0, hi - lo] (integral lo/hi, at most
+ * DRAM_WINDOW_LUT_MAX entries) that dram_stem_conv7_hu gathers from.  Workspace:
  * dram_preprocess_workspace_bytes_n(n) bytes, 8-byte aligned.  Volumes that do not start on a 16-byte
  * boundary (count % 8 != 0, or an unaligned base) take a scalar path instead of failing.
  */
@@ -258,6 +268,8 @@ int dram_window_standardize_batch(const int16_t *hu, float *out, float *stats_ou
                                   int32_t n, int64_t count, float lo, float hi, void *stream);
 int dram_window_stats(const int16_t *hu, float *stats_out, void *workspace, int32_t n, int64_t count,
                       float lo, float hi, void *stream);
+int dram_window_lut(const int16_t *hu, float *lut, float *stats_out, void *workspace, int32_t n,
+                    int64_t count, float lo, float hi, void *stream);
 
 /* ---- K8b: Interpolate transform (spatial_transforms.py:55-97) ---------- */
 /*

@@ -82,11 +82,14 @@ def _calibrating_bn(sd64, stats):
     return bn
 
 
-def make_state_dict(arch, seed=0, calib_dims=(32, 32, 32), prefix="", logit_std=1.5, reg_bias=-2.0):
+def make_state_dict(arch, seed=0, calib_dims=(32, 32, 32), prefix="", logit_std=1.5, reg_bias=-2.0, device=None):
     """Deterministic calibrated-random `state_dict` (fp32) for conf/<arch>.yaml.
 
     Keys/shapes/order equal the reference module's; `prefix='model.'` gives
     the Lightning-checkpoint naming that load_state_dict_greedy expects (utils.py:226-249).
+    `device`: where the fp64 calibration pass runs (default CPU; a CUDA device makes a large calibration volume
+    affordable — the full-size C4 test calibrates on a 1/3-scale volume of the same aspect).  The random draws always
+    come from the CPU generator, the result is returned on the CPU.
     """
     g = torch.Generator().manual_seed(1000003 * seed + 17)
     sd = {}
@@ -117,6 +120,9 @@ def make_state_dict(arch, seed=0, calib_dims=(32, 32, 32), prefix="", logit_std=
     # calibration pass (fp64): sets every BN's running statistics from the activations it sees
     img, _, _ = make_network_input(9000 + seed, calib_dims)
     x = img.double()[None, None]
+    if device is not None:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        x = x.to(device)
     stats = {}
     _, xup3 = M.features(sd, arch, x, bn=_calibrating_bn(sd, stats))
     # heads: O(1) logits on the calibration volume
@@ -129,9 +135,10 @@ def make_state_dict(arch, seed=0, calib_dims=(32, 32, 32), prefix="", logit_std=
         if head == "reg":
             sd[f"fcs.{k}.bias"] = reg_bias - mean
         else:
-            sd[f"fcs.{k}.bias"] = torch.randn(w.shape[0], generator=g, dtype=torch.float64) * 0.5 - mean
+            sd[f"fcs.{k}.bias"] = torch.randn(w.shape[0], generator=g, dtype=torch.float64).to(mean.device) * 0.5 - mean
     out = {}
     for key, v in sd.items():
+        v = v.cpu()
         out[prefix + key] = v.to(torch.float32) if v.dtype == torch.float64 else v
     return out
 

@@ -174,7 +174,14 @@ def test_stem_from_hu_equals_window_then_stem(cuda, lib, shape, n, dt):
     bias = torch.randn(64, generator=g).to(cuda) * 0.1
     img, stats = ops.window_standardize(hu, batched=True)
     want = ops.stem_conv7(img, packed, bias, mult)
-    got = ops.stem_conv7_hu(hu, stats, packed, bias, mult)
+    lut, stats2 = ops.window_lut(hu)
+    assert torch.equal(stats2, stats) and lut.shape == (n, 851)
+    # the table holds K8's value for every HU of the window (and the clamped ends for everything outside)
+    ramp = torch.arange(-1200, -250, dtype=torch.int16, device=cuda).repeat(n, 1)
+    for b in range(n):
+        v = ((ramp[b].float().clamp(-1150, -300) + 1150) / 850 - stats[b, 0]) / stats[b, 1]
+        assert torch.equal(lut[b][(ramp[b].clamp(-1150, -300) + 1150).long()], v)
+    got = ops.stem_conv7_hu(hu, lut, packed, bias, mult)
     assert torch.equal(got, want)
 
 

@@ -155,11 +155,10 @@ def test_reference_init_weights_match_reference_golden(cuda, lib, path, monkeypa
         scale = logit_ref.abs().max().item()
         if head == "cls":
             err = (got - ref).abs()
-        else:  # compare on the logit scale where neither side is saturated in fp32
-            ok = (ref > 1e-6) & (ref < 1 - 1e-6) & (got > 1e-6) & (got < 1 - 1e-6)
-            err = (torch.logit(got.double()) - torch.logit(ref.double())).abs()[ok].float()
-            both_sat = ((ref <= 1e-6) & (got <= 1e-5)) | ((ref >= 1 - 1e-6) & (got >= 1 - 1e-5))
-            assert bool((ok | both_sat).all()), f"{arch} map {k}: saturated on one side only"
+        else:  # compare on the logit scale; fp32 sigmoids saturate near |logit| = 17, so both sides are clamped at
+            # logit(1e-6) = -13.8 / logit(1 - 1e-6) = +13.8 first (beyond that the maps are 0 / 1 to six digits anyway)
+            eps = 1e-6
+            err = (torch.logit(got.double().clamp(eps, 1 - eps)) - torch.logit(ref.double().clamp(eps, 1 - eps))).abs().float()
         print(f"{arch} refinit dense[{k}]: logit absmax {scale:.4g}, logit err max {err.max().item():.4g} "
               f"mean {err.mean().item():.4g} (= {err.max().item() / scale:.3g} of the scale); sigmoid/out map " + report(got, ref))
         assert err.max().item() <= 2e-2 * scale, (arch, k, err.max().item(), scale)

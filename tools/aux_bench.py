@@ -99,8 +99,10 @@ def main():
     report(f"K8 window+standardise ({B} vol, 3 launches)", ms, B * V * (2 + 2 + 4))
     ms = timeit(lambda: ops.window_stats(hu))
     report(f"K8 statistics pass only ({B} vol)", ms, B * V * 2)
-    stats = ops.window_stats(hu)
-    ms = timeit(lambda: ops.stem_conv7_hu(hu, stats, wp, bias, mult, out=x))
+    ms = timeit(lambda: ops.window_lut(hu))
+    report(f"K8 statistics + table ({B} vol)", ms, B * V * 2)
+    lut, _ = ops.window_lut(hu)
+    ms = timeit(lambda: ops.stem_conv7_hu(hu, lut, wp, bias, mult, out=x))
     report("K2 stem fused from int16 HU", ms, B * (V * 2 + h ** 3 * 128), flops=2.0 * B * h ** 3 * 64 * 343)
 
 
