@@ -69,6 +69,7 @@ SIGNATURES = {
     "dram_upsample2x_plan_create": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "dram_upsample2x_plan_destroy": (C.c_int, [_vp]),
     "dram_upsample2x_plan_run": (C.c_int, [_vp, _i32, _vp]),
+    "dram_upconv_axis": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _i32, _i32, _i32, _vp]),
     "dram_pool_workspace_bytes": (_sz, [_i32, _i32]),
     "dram_masked_pool": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dram_dram_workspace_bytes": (_sz, [_i32]),

@@ -29,11 +29,13 @@ def _conv_out(n, k, s, d, p):
 class _Step:
     """One launch of the recorded sequence."""
 
-    __slots__ = ("name", "fn", "flops", "executed_flops")
+    __slots__ = ("name", "fn", "flops", "executed_flops", "conv_part")
 
-    def __init__(self, name, fn, flops=0, executed_flops=None):
+    def __init__(self, name, fn, flops=0, executed_flops=None, conv_part=False):
         self.name, self.fn, self.flops = name, fn, flops
         self.executed_flops = flops if executed_flops is None else executed_flops
+        # launches without FLOPs of their own that belong to a convolution's time (K13's interpolation passes)
+        self.conv_part = conv_part or flops > 0
 
 
 class Med3DEngine:
@@ -193,8 +195,14 @@ class Med3DEngine:
                 self.steps.append(_Step(name, lambda: ops.upsample2x(src, out=dst)))
 
         cb = m.us1.conv_blocks
+        # us1.0 (Cin = 512e + 64 -> 64): by default commuted (K13) — 27 channel-mixing products of x4 at LOW
+        # resolution, a separable gather, and a 64 -> 64 convolution of the skip tensor that takes the gathered
+        # tensor as its residual; DRAM_B200_US1=direct keeps K4 + one convolution over [up(x4) | x1].
+        commute = os.environ.get("DRAM_B200_US1", "commute").lower() != "direct"
         if fused_up:
             t = self._add_conv("us1.0", x4, self._conv_bn("us1.0", cb[0][0], cb[0][1]), x2=x1, upsample_x1=True).out
+        elif commute:
+            t = self._build_commuted_us1(cb[0][0], cb[0][1], x4, x1, (D2, H2, W2), (D3, H3, W3))
         else:
             self.up1 = torch.empty((B, D2, H2, W2, x4.shape[4]), dtype=bf, device=dev)
             add_upsample("us1.upsample", x4, self.up1)
@@ -232,6 +240,37 @@ class Med3DEngine:
         self.dense = us3.head_outs
         self.half_dims = (D1, H1, W1)
         self._plans_alive = [s.fn for s in self.steps]
+
+    def _build_commuted_us1(self, conv, bn, x4, x1, hi, lo):
+        """K13 (csrc/upconv_kernels.cu): relu(bn(conv([up(x4) | x1]))) =
+        relu(scale * conv(x1, W_skip) + shift + G),  G = sum_tap up(z_tap)[o + tap],  z_tap = (scale * W_up,tap) . x4."""
+        dev, bf, B = self.device, self.act_dtype, self.batch
+        c_up = x4.shape[4]
+        (D2, H2, W2), (D3, H3, W3) = hi, lo
+
+        def pack_z():
+            scale, _ = ops.fold_bn(bn, conv.bias)
+            packed, mult = ops.pack_upconv_weight(conv.weight.detach().to(dev), c_up, scale.to(dev), dtype=bf)
+            return packed, torch.zeros(27 * 64, dtype=torch.float32, device=dev), mult
+
+        def pack_skip():
+            scale, shift = ops.fold_bn(bn, conv.bias)
+            packed, mult = ops.pack_conv_weight(conv.weight.detach().to(dev)[:, c_up:], scale.to(dev), dtype=bf,
+                                                normalize=True)
+            return packed, shift.to(dev).float(), mult
+
+        m_hi = B * D2 * H2 * W2
+        wz = self._register_weight("us1.0.z", pack_z)
+        # algorithmic FLOPs: the reference convolves 27 taps of c_up channels at HIGH resolution
+        z = self._add_conv("us1.0.z", x4, wz, kernel=1, relu=False, flops=2 * m_hi * 64 * c_up * 27).out
+        self.us1_r = torch.empty((B, D3, H3, W2, 9 * 64), dtype=bf, device=dev)
+        self.us1_q = torch.empty((B, D3, H2, W2, 3 * 64), dtype=bf, device=dev)
+        self.us1_g = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)
+        self.steps.append(_Step("us1.0.gather_w", lambda: ops.upconv_axis(z, 3, 9, out=self.us1_r), conv_part=True))
+        self.steps.append(_Step("us1.0.gather_h", lambda: ops.upconv_axis(self.us1_r, 2, 3, out=self.us1_q), conv_part=True))
+        self.steps.append(_Step("us1.0.gather_d", lambda: ops.upconv_axis(self.us1_q, 1, 1, out=self.us1_g), conv_part=True))
+        wskip = self._register_weight("us1.0.skip", pack_skip)
+        return self._add_conv("us1.0", x1, wskip, residual=self.us1_g).out
 
     # ---------------------------------------------------------------- run
     def _launch_steps(self, first=None):

@@ -413,6 +413,50 @@ class Upsample2xPlan:
             self._handle = None
 
 
+def upconv_axis(x, axis, groups, out=None):
+    """K13, one axis of the commuted up-sampled convolution.  x: 16-bit [N, d, h, w, C] whose first groups*192 channels
+    are [groups][3 taps of `axis`][64]; returns [N, d', h', w', groups*64] with the size of `axis` (1 = D, 2 = H,
+    3 = W) doubled: out[o] = sum_t lerp(x[.., t, :])(o + t - 1), zero outside (see include/dram_b200.h)."""
+    _need16(x, "upconv_axis x", 5)
+    if axis not in (1, 2, 3):
+        raise ValueError("upconv_axis: axis must be 1 (D), 2 (H) or 3 (W)")
+    n, d, h, w, c = x.shape
+    if c < groups * 192:
+        raise ValueError(f"upconv_axis: {c} channels cannot hold {groups} groups of 3 x 64")
+    shape = [n, d, h, w, groups * 64]
+    shape[axis] *= 2
+    if out is None:
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    _need(out, x.dtype, "upconv_axis out", 5)
+    if list(out.shape) != shape:
+        raise ValueError(f"upconv_axis: out shape {tuple(out.shape)} != {tuple(shape)}")
+    dims = (n, d, h, w)
+    outer = 1
+    for v in dims[:axis]:
+        outer *= v
+    inner = 1
+    for v in dims[axis + 1:]:
+        inner *= v
+    check(_capi.load().dram_upconv_axis(_p(x), _p(out), outer, dims[axis], 2 * dims[axis], inner, groups, c,
+                                        ACT_DTYPES[x.dtype], _stream()), "dram_upconv_axis")
+    return out
+
+
+def pack_upconv_weight(weight, c_up, scale=None, dtype=torch.bfloat16):
+    """The up-sampled half of a decoder convolution [Cout=64, c_up + c_skip, 3, 3, 3] as the 1x1x1 operand of K13's
+    low-resolution product: 16-bit [27*64, c_up], row tap*64 + co = weight[co, :c_up, tap] (* scale[co]), rows
+    normalised by a power of two like `pack_conv_weight(normalize=True)`; returns (packed, multiplier fp32 [27*64])."""
+    w = weight.detach().to(torch.float32)[:, :c_up]
+    if scale is not None:
+        w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
+    cout = w.shape[0]
+    if cout != 64 or tuple(w.shape[2:]) != (3, 3, 3):
+        raise ValueError(f"pack_upconv_weight: expected [64, C, 3, 3, 3], got {tuple(weight.shape)}")
+    rows = w.reshape(cout, c_up, 27).permute(2, 0, 1).reshape(27 * cout, c_up)   # [tap][co] x ci
+    mult = pow2_normalizer(rows)
+    return (rows / mult.view(-1, 1)).to(dtype).contiguous(), mult.contiguous()
+
+
 def masked_pool(dense, mask=None):
     """dense fp32 [N, C, d, h, w]; mask uint8 (binary) or fp32 (weights) [N, D, H, W] or None -> fp32 [N, C]."""
     lib = _capi.load()

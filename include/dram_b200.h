@@ -215,6 +215,24 @@ int dram_upsample2x_plan_create(const void *x, void *out, int32_t n, int32_t d, 
 int dram_upsample2x_plan_destroy(dram_upsample_plan *plan);
 int dram_upsample2x_plan_run(const dram_upsample_plan *plan, int32_t max_ctas, void *stream);
 
+/* ---- K13: the commuted convolution of an up-sampled tensor (med3d.py:83-89, first conv of us1) ---- */
+/*
+ * UpsampleConvBlock5d.forward up-samples x4 (512 / 2048 channels) x2, concatenates the skip tensor and runs a
+ * 3x3x3 convolution with 64 outputs.  Up-sampling acts on space, the filter's channel mixing on channels, so
+ *   conv(up(x), W)[o] = sum_tap up(z_tap)[o + tap],   z_tap = W_tap . x  (27 1x1x1 products at LOW resolution,
+ *   one dram_conv3d_run with 27*64 output channels, tap-major),
+ * and the gather separates per axis.  dram_upconv_axis does one axis:
+ *   in  : 16-bit [outer][l_lo][inner][in_channels], the first groups*3*64 channels of a position being
+ *         [groups][3 taps of this axis][64]
+ *   out : 16-bit [outer][l_hi][inner][groups][64],  l_hi = 2*l_lo in the network (any l_hi works)
+ *   out[.., o, .., g, c] = sum_{t<3, 0 <= o+t-1 < l_hi} lerp(in[.., ., .., g, t, c])(o + t - 1)   (align_corners=True
+ *   source index and weights of ATen; positions outside the volume are the convolution's zero padding).
+ * W pass: outer = N*Dl*Hl, inner = 1, groups = 9; H pass: outer = N*Dl, inner = W, groups = 3; D pass: outer = N,
+ * inner = H*W, groups = 1 -> the 64-channel NDHWC tensor that enters the skip half's convolution as its residual.
+ */
+int dram_upconv_axis(const void *in, void *out, int64_t outer, int32_t l_lo, int32_t l_hi, int64_t inner,
+                     int32_t groups, int32_t in_channels, int32_t dtype, void *stream);
+
 /* ---- K6: lobe-masked / global pooling (med3d.py:383-387, 284) ---------- */
 /*
  * dense: fp32 [n][ch][d][h][w].  mask: [n][md][mh][mw], uint8 (non-zero = lung)

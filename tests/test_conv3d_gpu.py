@@ -406,3 +406,69 @@ def test_conv_pair_kernel(cuda, lib, case, monkeypatch):
     assert plan128.stages == 4
     torch.cuda.synchronize()
     assert torch.equal(a, plan128.run())
+
+
+# ------------------------------------------------------------------------------------------------
+# K13: the commuted convolution of an up-sampled tensor (us1.0)
+# ------------------------------------------------------------------------------------------------
+def _lerp_matrix(l_lo, l_hi):
+    """[l_hi, l_lo] matrix of ATen's linear interpolation with align_corners=True."""
+    eye = torch.eye(l_lo).view(1, l_lo, l_lo)  # [N=1, C=l_lo, L=l_lo]
+    return F.interpolate(eye, size=l_hi, mode="linear", align_corners=True)[0].t().contiguous()
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dims,axis,groups,pad_c", [((3, 4, 5), 3, 9, 0), ((3, 4, 10), 2, 3, 0), ((3, 8, 10), 1, 1, 0),
+                                                    ((2, 5, 3), 3, 9, 64), ((1, 1, 2), 2, 3, 0), ((4, 1, 1), 1, 1, 0)])
+def test_upconv_axis_pass(cuda, lib, dims, axis, groups, pad_c, dt):
+    """One axis of K13 against its definition: out[o, g, c] = sum_t (M x[.., g, t, c])[o + t - 1] with M ATen's
+    align_corners interpolation matrix and zero for positions outside the doubled axis."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(31)
+    n = 2
+    c = groups * 192 + pad_c
+    x = torch.randn((n,) + dims + (c,), generator=g).to(dt)
+    got = ops.upconv_axis(x.to(cuda), axis, groups).float().cpu()
+    l_lo = dims[axis - 1]
+    M = _lerp_matrix(l_lo, 2 * l_lo)                                    # [l_hi, l_lo]
+    xv = x.float()[..., :groups * 192].reshape((n,) + dims + (groups, 3, 64)).movedim(axis, -1)   # [..., g, t, c, L_lo]
+    up = torch.einsum("...l,ol->...o", xv, M)                            # [..., g, t, c, L_hi]
+    ref = torch.zeros(up.shape[:-3] + (64, 2 * l_lo))
+    for t in range(3):
+        lo, hi = max(0, 1 - t), min(2 * l_lo, 2 * l_lo + 1 - t)           # o with 0 <= o + t - 1 < l_hi
+        ref[..., lo:hi] += up[..., t, :, lo + t - 1:hi + t - 1]
+    ref = ref.movedim(-1, axis)                                          # [n, d, h, w, g, c] with the axis doubled
+    ref = ref.reshape(ref.shape[:4] + (groups * 64,))
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= 2 * ulp * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("lo_dims,c_up,n", [((4, 4, 4), 128, 1), ((3, 5, 4), 512, 2), ((8, 4, 6), 256, 1)])
+def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
+    """The whole of K13 — low-resolution 1x1x1 product with 27*64 outputs, three gather passes, 64->64 convolution of the
+    skip tensor with the gathered tensor as residual — against conv3d(cat[upsample(x4), x1]) in fp32 on the CPU."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(32)
+    hi_dims = tuple(2 * v for v in lo_dims)
+    x4 = _rand((n, c_up) + lo_dims, g, dtype=dt)
+    x1 = _rand((n, 64) + hi_dims, g, dtype=dt)
+    wgt = torch.randn((64, c_up + 64, 3, 3, 3), generator=g) * ((c_up + 64) * 27) ** -0.5
+    scale = torch.rand(64, generator=g) + 0.5
+    shift = torch.randn(64, generator=g) * 0.1
+    up = F.interpolate(x4, scale_factor=2, mode="trilinear", align_corners=True)
+    ref = torch.relu(F.conv3d(torch.cat([up, x1], 1), wgt, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
+    x4d, x1d = ops.to_ndhwc_16(x4.to(cuda), dt), ops.to_ndhwc_16(x1.to(cuda), dt)
+    wz, mz = ops.pack_upconv_weight(wgt.to(cuda), c_up, scale.to(cuda), dtype=dt)
+    z = ops.Conv3dPlan(x4d, wz, torch.zeros(27 * 64, device=cuda), scale=mz, kernel=1, relu=False).run()
+    gath = ops.upconv_axis(ops.upconv_axis(ops.upconv_axis(z, 3, 9), 2, 3), 1, 1)
+    ws, ms = ops.pack_conv_weight(wgt.to(cuda)[:, c_up:], scale.to(cuda), dtype=dt, normalize=True)
+    out = ops.Conv3dPlan(x1d, ws, shift.to(cuda), scale=ms, residual=gath).run()
+    got = ops.to_ncdhw_f32(out).cpu()
+    err = (got - ref).abs()
+    # rounding points: z, two intermediate gathers, the gathered tensor, the output (direct route: up(x4), the output)
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    assert err.max().item() <= 6 * ulp * ref.abs().max().item(), (err.max().item(), ref.abs().max().item())

@@ -229,3 +229,26 @@ def test_cuda_graph_replay_equals_eager_launches(cuda, lib, monkeypatch):
     eager.load_state_dict(sd2)
     for x in xs:
         assert all(torch.equal(a, b) for a, b in zip(sum(model(x, lung), []), sum(eager(x, lung), [])))
+
+
+@pytest.mark.parametrize("arch,dims", [("med3ddram18", (32, 40, 48)), ("med3ddram50", (32, 32, 32)), ("med3d", (32, 32, 32))])
+def test_commuted_us1_matches_direct_route_and_oracle(cuda, lib, arch, dims, monkeypatch):
+    """us1.0 runs commuted by default (K13: low-resolution channel mixing + separable gather); DRAM_B200_US1=direct keeps
+    K4 + one convolution over [up(x4) | x1].  Both stay within the parity tolerances of the oracle, and within a few
+    16-bit roundings of each other."""
+    sd = synthetic.make_state_dict(arch, seed=11, calib_dims=dims)
+    x, lung, _ = synthetic.make_network_input(50, dims)
+    x, lungs = x[None, None], lung[None, None].float()
+    d_ref, s_ref = M.forward(sd, arch, x, lungs)
+    outs = {}
+    for mode in ("direct", "commute"):
+        monkeypatch.setenv("DRAM_B200_US1", mode)
+        model = build_model(arch, sd, cuda)
+        dense, scores = model(x.to(cuda), lungs.to(cuda))
+        names = [s.name for s in model.engine(1, dims, cuda).steps]
+        assert ("us1.0.gather_w" in names) == (mode == "commute") and ("us1.upsample" in names) == (mode == "direct")
+        check_outputs(arch, dense, scores, d_ref, s_ref)
+        outs[mode] = [d.cpu() for d in dense]
+    for a, b in zip(outs["direct"], outs["commute"]):
+        print(f"{arch} commute vs direct: max {(a - b).abs().max().item():.4g}")
+        assert (a - b).abs().max().item() <= 2e-2 * max(1.0, b.abs().max().item())
