@@ -241,10 +241,19 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     }
     __syncwarp();
   } else if (warp == SL_MMA_WARP) {
-    {  // the whole warp walks the loops (uniform control flow); one elected lane issues
+    {  // the whole warp walks the loops (uniform control flow); one elected lane issues.
+      // The issuing thread is the bottleneck of this kernel if it spends more than ~30 instructions per MMA (a
+      // single warp retires a dependent instruction every few clocks, an M128 x N64 x K16 MMA lasts 32-48): measured
+      // in round 2, us3 (N = 32) took 90 % of the time of us2.1 (N = 64) — time followed the MMA COUNT, ~95 clocks
+      // each.  So everything that does not change per MMA is hoisted: the plane descriptors are built once per
+      // chunk (six 64-bit values, broadcast so that they live in uniform registers), the (kh, kw) / kd / K-step
+      // offsets are compile-time constants of the fully unrolled loops, and a stage's 24 MMAs are issued from ONE
+      // elected region: two 64-bit uniform adds per tcgen05.mma.
       uint32_t idesc[3];
 #pragma unroll
       for (int nb = 0; nb < 3; ++nb) idesc[nb] = make_idesc_16bit(128, (nb + 1) * BLOCK_N, p.epi.is_f16);
+      const uint64_t desc_a_const = make_sw128_desc_sbo(0u, PL_W * 128, 0);
+      const uint64_t desc_b_const = make_sw128_desc(0u);
       int stage = 0;
       uint32_t phase = 0;
       unsigned seq_end = 0;
@@ -260,49 +269,84 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
           const bool next_reuse = single_chunk && (item + 1 < item_end) && (it.g + 1 < p.groups_d);
           const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
           seq_end = seq_base + ITEM_PLANES;
+          // per-plane constants of this chunk: A descriptor of the slot base, barrier addresses / parities
+          uint64_t da_plane[ITEM_PLANES];
+          uint32_t full_bar[ITEM_PLANES], full_par[ITEM_PLANES], empty_bar[ITEM_PLANES];
+#pragma unroll
+          for (int j = 0; j < ITEM_PLANES; ++j) {
+            const unsigned seq = seq_base + j;
+            const int slot = seq % RING;
+            uint32_t pa = plane_addr(slot);
+            if (p.desc_base_offset_mode) pa |= 0u;  // (knob kept for the plan struct; the base-offset field stays 0)
+            pa = __shfl_sync(0xffffffffu, pa, 0);   // provably warp-uniform -> uniform registers
+            da_plane[j] = desc_a_const | (uint64_t)((pa & 0x3FFFFu) >> 4);
+            full_bar[j] = plane_full(slot);
+            full_par[j] = (seq / RING) & 1u;
+            empty_bar[j] = plane_empty(slot);
+          }
+          const bool first_chunk = c == 0;
+#pragma unroll
           for (int hw = 0; hw < 9; ++hw) {
-            const int kh = hw / 3, kw = hw - 3 * kh;
+            constexpr int kRowBytes = 128;
+            const int kh = hw / 3, kw = hw - 3 * kh;                       // constants after unrolling
+            const uint32_t row_off16 = (uint32_t)((kh * PL_W + kw) * kRowBytes) >> 4;
             mbar_wait(b_full(stage), phase);
             tcgen05_fence_after();
-            const uint32_t row_off = (uint32_t)(kh * PL_W + kw) * 128u;
-            const bool first = (c == 0 && hw == 0);  // accumulators are initialised tile by tile
+            uint32_t bb = b_addr(stage);
+            bb = __shfl_sync(0xffffffffu, bb, 0);
+            const uint64_t db_stage = desc_b_const | (uint64_t)((bb & 0x3FFFFu) >> 4);
+            if (hw == 0) {
+              // planes of this chunk arrive in order during its first stage: wait for each just before its MMAs
 #pragma unroll
-            for (int j = 0; j < ITEM_PLANES; ++j) {
-              const unsigned seq = seq_base + j;
-              const int slot = seq % RING;
-              if (hw == 0) {  // planes of this chunk arrive in order during its first stage
-                mbar_wait(plane_full(slot), (seq / RING) & 1u);
+              for (int j = 0; j < ITEM_PLANES; ++j) {
+                mbar_wait(full_bar[j], full_par[j]);
                 tcgen05_fence_after();
-              }
-              // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
-              const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
-              const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
-              const uint64_t da = make_sw128_desc_sbo(plane_addr(slot) + row_off, PL_W * 128, p.desc_base_offset_mode);
-              const uint64_t db = make_sw128_desc(b_addr(stage) + (uint32_t)((2 - kd_hi) * Cfg::B_BLOCK_BYTES));
-              const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
-              if (elect_one_sync()) {
-                if (first) {
+                const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+                const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+                const uint64_t da = da_plane[j] + row_off16;
+                const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
+                const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
+                if (elect_one_sync()) {
+                  if (first_chunk) {  // accumulators are initialised tile by tile: tile t's first touch is kd == 0
 #pragma unroll
-                  for (int q = 0; q < nblk; ++q) {  // tile t_min + q, kd = kd_hi - q; its first touch is kd == 0
-                    const uint64_t dbq = db + (uint64_t)((q * Cfg::B_BLOCK_BYTES) >> 4);
+                    for (int q = 0; q < nblk; ++q) {
+                      const uint64_t dbq = db + (uint64_t)((q * Cfg::B_BLOCK_BYTES) >> 4);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_bf16(dcol + (uint32_t)(q * BLOCK_N), da + (uint64_t)(2 * k), dbq + (uint64_t)(2 * k), idesc[0],
+                                  (k > 0 || kd_hi - q > 0) ? 1u : 0u);
+                    }
+                  } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      umma_bf16(dcol + (uint32_t)(q * BLOCK_N), da + (uint64_t)(2 * k), dbq + (uint64_t)(2 * k), idesc[0],
-                                (k > 0 || kd_hi - q > 0) ? 1u : 0u);
+                      umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
                   }
-                } else {
+                }
+                __syncwarp();
+              }
+              if (elect_one_sync()) umma_commit(b_empty(stage));
+              __syncwarp();
+            } else {
+              if (elect_one_sync()) {
+#pragma unroll
+                for (int j = 0; j < ITEM_PLANES; ++j) {
+                  // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
+                  const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+                  const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+                  const uint64_t da = da_plane[j] + row_off16;
+                  const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
+                  const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
+                  // last stage of the chunk: hand each plane back as soon as its MMAs are issued so the
+                  // producer refills the ring while the remaining planes of this stage are still computing
+                  if (hw == 8 && (j < SL_GROUP || !next_reuse)) umma_commit(empty_bar[j]);
                 }
-                // last stage of the chunk: hand each plane back as soon as its MMAs are issued so the
-                // producer refills the ring while the remaining planes of this stage are still computing
-                if (hw == 8 && (j < SL_GROUP || !next_reuse)) umma_commit(plane_empty(slot));
+                umma_commit(b_empty(stage));
               }
               __syncwarp();
             }
-            if (elect_one_sync()) umma_commit(b_empty(stage));
-            __syncwarp();
             if (++stage == B_STAGES) {
               stage = 0;
               phase ^= 1u;

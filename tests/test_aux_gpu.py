@@ -180,7 +180,13 @@ def test_stem_from_hu_equals_window_then_stem(cuda, lib, shape, n, dt):
     ramp = torch.arange(-1200, -250, dtype=torch.int16, device=cuda).repeat(n, 1)
     for b in range(n):
         v = ((ramp[b].float().clamp(-1150, -300) + 1150) / 850 - stats[b, 0]) / stats[b, 1]
-        assert torch.equal(lut[b][(ramp[b].clamp(-1150, -300) + 1150).long()], v)
+        # (torch divides by a Python scalar through a reciprocal multiply: last-bit differences from K8's IEEE division)
+        assert torch.allclose(lut[b][(ramp[b].clamp(-1150, -300) + 1150).long()], v, rtol=1e-6, atol=1e-7)
+        # ... and K8 itself on the ramp, shifted to this volume's statistics, is reproduced exactly
+    k8, _ = ops.window_standardize(hu, batched=True)
+    for b in range(n):
+        idx = (hu[b].clamp(-1150, -300) + 1150).long()
+        assert torch.equal(lut[b][idx], k8[b])
     got = ops.stem_conv7_hu(hu, lut, packed, bias, mult)
     assert torch.equal(got, want)
 
