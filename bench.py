@@ -607,7 +607,7 @@ def main():
     clocks = sampler.stop(skip=first_sample) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    launches_per_step = len(eng.steps) + 3 + 2  # K8 statistics + finalize + table; the recorded steps (int16-HU stem first); K7 + finalize
+    launches_per_step = len(eng.steps) + 3 + 2  # K8 statistics + finalize + apply; the recorded steps; K7 + finalize
 
     # ---- end to end through the public predict_step with pinned host buffers -----------------
     from dram_b200 import ops

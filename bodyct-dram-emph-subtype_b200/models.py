@@ -281,18 +281,24 @@ class ScanRegLightningModule(_ScanModule):
                 "uids": batch.get("uid"),
             }
 
-    def predict_step_from_hu(self, hu, lung_mask, ess_mask, fuse_window=True):
+    def predict_step_from_hu(self, hu, lung_mask, ess_mask, fuse_window=None):
         """The device-resident hot path of SURVEY §8d: int16 HU volumes already at network size [B,D,H,W] -> K8
-        window + standardise (per volume) -> network -> dRAM.  By default K8 is its statistics pass plus an 851-entry
-        table per volume, and the stem convolution clamps and gathers while it loads the int16 volume (the same values
-        bit for bit; the fp32 image is never written); `fuse_window=False` writes the fp32 image first (what
-        predict_step receives from the transforms).  Returns the same dict as predict_step (without the bookkeeping keys)."""
+        window + standardise (per volume) -> network -> dRAM.  `fuse_window=True`: K8 is its statistics pass plus an
+        851-entry table per volume, and the stem convolution clamps and gathers while it loads the int16 volume (the
+        same values bit for bit; the fp32 image is never written).  `fuse_window=False`: K8 writes the fp32 image first
+        (what predict_step receives from the transforms).  Default (None): env DRAM_B200_FUSE_WINDOW, else False — the
+        stem kernel is bound by its producers' instruction issue, and the table gathers cost it more (0.38 against
+        0.23 ms per 256^3 volume, profiles/aux_metrics_r2b.csv) than K8's apply pass saves (0.03 ms).  Returns the same dict as predict_step (without the bookkeeping keys)."""
         with torch.no_grad():
             if not hu.is_cuda or hu.dtype != torch.int16:
                 raise RuntimeError("predict_step_from_hu: expected an int16 CUDA tensor [B,D,H,W]")
             B, D, H, W = hu.shape
             eng = self.model.eval().engine(B, (D, H, W), hu.device)
             hu = hu.contiguous()
+            if fuse_window is None:
+                import os
+
+                fuse_window = os.environ.get("DRAM_B200_FUSE_WINDOW", "0").lower() in ("1", "on", "true", "yes")
             if fuse_window and hasattr(eng, "stem_weights"):
                 lut, _ = ops.window_lut(hu)  # statistics are per volume (intensity_transforms.py:104-114)
                 dense = eng.run_network(first=eng.hu_stem(hu, lut))

@@ -65,8 +65,8 @@ def test_predict_step_from_hu_matches_oracle(cuda, lib):
         assert (out[k].cpu() - ref[k]).abs().max().item() <= 2e-2
     for k in ("cle_precentages", "pse_precentages"):
         assert torch.allclose(out[k].cpu(), ref[k], rtol=1e-2)
-    # the fused route (statistics pass + int16 stem) and the two-kernel route (fp32 image written first) agree exactly
-    plain = module.predict_step_from_hu(hu.to(cuda), lung.to(cuda), ess.to(cuda), fuse_window=False)
+    # the fused route (statistics pass + table + int16 stem) and the two-kernel route (fp32 image written first) agree exactly
+    plain = module.predict_step_from_hu(hu.to(cuda), lung.to(cuda), ess.to(cuda), fuse_window=True)
     for k in ("cle_dense_outs", "pse_dense_outs"):
         assert torch.equal(plain[k], out[k])
 
