@@ -16,6 +16,7 @@ DRAM_OK = 0
 DRAM_DTYPE_BF16 = 0
 DRAM_DTYPE_F16 = 1
 CONV_ALGO = {"auto": 0, "tiles": 1, "planes": 2}
+CONV_EPILOGUE = {"auto": 0, "direct": 1, "staged": 2}
 LOSS_COEF_HEAD = 16  # DRAM_LOSS_COEF_HEAD
 PEER_HANDLE_BYTES = 64  # DRAM_PEER_HANDLE_BYTES
 
@@ -40,6 +41,7 @@ class ConvDesc(C.Structure):
         ("dtype", C.c_int32),
         ("algo", C.c_int32),
         ("src1_up2x", C.c_int32),
+        ("epilogue", C.c_int32),
     ]
 
 

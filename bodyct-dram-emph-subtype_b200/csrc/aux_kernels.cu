@@ -573,6 +573,114 @@ dram_upsample_mask_staged_kernel(const float *__restrict__ dense0, const float *
   double accl = block_sum((double)lung_count, scratch);
   if (threadIdx.x == 0) atomicAdd(&sums[2 * n + b], accl);
 }
+
+// ---------------------------------------------------------------------------------------
+// K7, lean variant of the staged kernel for the common shapes (W a power-of-two multiple of 16 between 64 and 1024,
+// w = W/2... any w % 4 == 0, everything 16-byte aligned).  Round-2 ncu: both K7 kernels moved their 168 MB at 13 % of
+// the DRAM peak with no unit saturated — they were bound by instruction issue (index decoding with 64-bit divisions,
+// two work items per thread, 32-element value arrays).  Here one CTA = one output plane slice of RY rows (grid =
+// (H/RY, D, n): no division anywhere), thread (sx, ry) owns ONE 16-voxel segment: 2 x 16-byte mask loads, a block
+// vote, and — for the ~90 % of CTAs without an `ess` voxel — eight 16-byte streaming stores of zeros and one integer
+// warp reduction for the lung count.  CTAs that do meet `ess` stage the source brick in shared memory as before.
+// ---------------------------------------------------------------------------------------
+template <int LOG_SX>
+__global__ void __launch_bounds__(256)
+dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__restrict__ dense1,
+                               const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
+                               float *__restrict__ out0, float *__restrict__ out1, double *__restrict__ sums, int n,
+                               int d, int h, int w, int D, int H, int W, float sd, float sh, float sw, int nr_max) {
+  extern __shared__ float k7_smem[];  // [map 2][plane 2][nr_max][w]
+  __shared__ double scratch[32];
+  __shared__ unsigned lung_part[8];
+  constexpr int SX = 1 << LOG_SX, RY = 256 >> LOG_SX;
+  const int sx = threadIdx.x & (SX - 1), ry = threadIdx.x >> LOG_SX;
+  const int b = blockIdx.z, xd = blockIdx.y, xh0 = blockIdx.x * RY;
+  const int xh = xh0 + ry;
+  const bool row_ok = xh < H;
+  const int64_t vol = (int64_t)D * H * W;
+  const int64_t o = (int64_t)b * vol + ((int64_t)xd * H + xh) * W + sx * K7_SEG;
+  uint4 e4 = make_uint4(0, 0, 0, 0), l4 = make_uint4(0, 0, 0, 0);
+  if (row_ok) {
+    e4 = __ldcs(reinterpret_cast<const uint4 *>(ess + o));
+    l4 = __ldcs(reinterpret_cast<const uint4 *>(lungs + o));
+  }
+  const unsigned lung_count = nonzero_bytes(l4.x) + nonzero_bytes(l4.y) + nonzero_bytes(l4.z) + nonzero_bytes(l4.w);
+  const int mine = (e4.x | e4.y | e4.z | e4.w) != 0;
+  const int need = __syncthreads_or(mine);
+  double acc0 = 0.0, acc1 = 0.0;
+  float v0[K7_SEG], v1[K7_SEG];
+#pragma unroll
+  for (int j = 0; j < K7_SEG; ++j) v0[j] = v1[j] = 0.0f;
+  if (need) {
+    const LinIdx id = lin_index_ac(xd, sd, d);
+    const int rows = min(RY, H - xh0);
+    const int ih_lo = lin_index_ac(xh0, sh, h).i0;
+    const int nr = lin_index_ac(xh0 + rows - 1, sh, h).i1 - ih_lo + 1;  // <= nr_max (host)
+    const int plane_stride = nr_max * w;
+    const float *s0 = dense0 + (int64_t)b * d * h * w, *s1 = dense1 + (int64_t)b * d * h * w;
+    const int row_f4 = w >> 2, total = 4 * nr * row_f4;
+    for (int t = threadIdx.x; t < total; t += 256) {
+      const int c = t % row_f4;
+      int q = t / row_f4;
+      const int r = q % nr;
+      q /= nr;
+      const int pl = q & 1, mp = q >> 1;
+      const float *src = (mp ? s1 : s0) + ((int64_t)(pl ? id.i1 : id.i0) * h + ih_lo + r) * w;
+      reinterpret_cast<float4 *>(k7_smem + (mp * 2 + pl) * plane_stride + r * w)[c] = __ldg(reinterpret_cast<const float4 *>(src) + c);
+    }
+    __syncthreads();
+    if (mine) {
+      const LinIdx ih = lin_index_ac(xh, sh, h);
+      const float *p00 = k7_smem + (ih.i0 - ih_lo) * w, *p01 = k7_smem + (ih.i1 - ih_lo) * w;
+      const float *p10 = p00 + plane_stride, *p11 = p01 + plane_stride;
+      const float *q00 = p00 + 2 * plane_stride, *q01 = p01 + 2 * plane_stride;
+      const float *q10 = p10 + 2 * plane_stride, *q11 = p11 + 2 * plane_stride;
+      const uint32_t ew[4] = {e4.x, e4.y, e4.z, e4.w};
+      const int xw0 = sx * K7_SEG;
+#pragma unroll
+      for (int j = 0; j < K7_SEG; ++j) {
+        if ((ew[j >> 2] >> (8 * (j & 3))) & 0xffu) {
+          const LinIdx iw = lin_index_ac(xw0 + j, sw, w);
+          const float a = id.w0 * (ih.w0 * (iw.w0 * p00[iw.i0] + iw.w1 * p00[iw.i1]) +
+                                   ih.w1 * (iw.w0 * p01[iw.i0] + iw.w1 * p01[iw.i1])) +
+                          id.w1 * (ih.w0 * (iw.w0 * p10[iw.i0] + iw.w1 * p10[iw.i1]) +
+                                   ih.w1 * (iw.w0 * p11[iw.i0] + iw.w1 * p11[iw.i1]));
+          const float c = id.w0 * (ih.w0 * (iw.w0 * q00[iw.i0] + iw.w1 * q00[iw.i1]) +
+                                   ih.w1 * (iw.w0 * q01[iw.i0] + iw.w1 * q01[iw.i1])) +
+                          id.w1 * (ih.w0 * (iw.w0 * q10[iw.i0] + iw.w1 * q10[iw.i1]) +
+                                   ih.w1 * (iw.w0 * q11[iw.i0] + iw.w1 * q11[iw.i1]));
+          v0[j] = a;
+          v1[j] = c;
+          acc0 += (double)a;
+          acc1 += (double)c;
+        }
+      }
+    }
+  }
+  if (row_ok) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __stcs(reinterpret_cast<float4 *>(out0 + o) + q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
+      __stcs(reinterpret_cast<float4 *>(out1 + o) + q, make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
+    }
+  }
+  // lung count: integer warp reductions, one atomic per CTA; map sums only where the CTA met `ess`
+  const unsigned wsum = __reduce_add_sync(0xffffffffu, lung_count);
+  if ((threadIdx.x & 31) == 0) lung_part[threadIdx.x >> 5] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += lung_part[i];
+    if (tot) atomicAdd(&sums[2 * n + b], (double)tot);
+  }
+  if (need) {
+    acc0 = block_sum(acc0, scratch);
+    if (threadIdx.x == 0) atomicAdd(&sums[b], acc0);
+    acc1 = block_sum(acc1, scratch);
+    if (threadIdx.x == 0) atomicAdd(&sums[n + b], acc1);
+  }
+}
 __global__ void dram_finalize_kernel(const double *__restrict__ sums, float *__restrict__ pct, int n,
                                      int per_sample) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -891,6 +999,43 @@ extern "C" int dram_dram_upsample_mask(const float *dense0, const float *dense1,
   const bool staged_ok = RH * segs <= 2 * K7_THREADS && !(k7_env && strcmp(k7_env, "rows") == 0);
   const int nr_max = (int)ceilf((float)RH * sh) + 2 < h ? (int)ceilf((float)RH * sh) + 2 : h;
   const size_t smem = (size_t)4 * nr_max * w * sizeof(float);
+  // lean kernel: W = 16 * 2^k segments per row (k = 2..6), one CTA per RY-row slice of a plane
+  int log_sx = -1;
+  for (int k = 2; k <= 6; ++k)
+    if (W == (K7_SEG << k)) log_sx = k;
+  const bool aligned16 = (w % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 16 == 0) &&
+                         (((uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)dense0 | (uintptr_t)dense1) % 16 == 0) &&
+                         (((int64_t)D * H * W) % 16 == 0) && (((int64_t)d * h * w) % 4 == 0);
+  const bool lean_env = !(k7_env && (strcmp(k7_env, "rows") == 0 || strcmp(k7_env, "staged") == 0));
+  if (lean_env && log_sx >= 0 && aligned16 && D <= 65535 && n <= 65535) {
+    const int RY = 256 >> log_sx;
+    const int nr_lean = (int)ceilf((float)RY * sh) + 2 < h ? (int)ceilf((float)RY * sh) + 2 : h;
+    const size_t smem_lean = (size_t)4 * nr_lean * w * sizeof(float);
+    if (smem_lean <= 160 * 1024) {
+      dim3 grid(ceil_div(H, RY), D, n);
+#define DRAM_K7_LEAN(LS)                                                                                                  \
+  do {                                                                                                                    \
+    rc = check_cuda(cudaFuncSetAttribute(dram_upsample_mask_lean_kernel<LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem_lean),                                                                 \
+                    "cudaFuncSetAttribute(dram_upsample_mask_lean_kernel)");                                              \
+    if (rc != DRAM_OK) return rc;                                                                                         \
+    dram_upsample_mask_lean_kernel<LS><<<grid, 256, smem_lean, st>>>(dense0, dense1, ess, lungs, out0, out1, sums, n, d,  \
+                                                                     h, w, D, H, W, sd, sh, sw, nr_lean);                 \
+  } while (0)
+      switch (log_sx) {
+        case 2: DRAM_K7_LEAN(2); break;
+        case 3: DRAM_K7_LEAN(3); break;
+        case 4: DRAM_K7_LEAN(4); break;
+        case 5: DRAM_K7_LEAN(5); break;
+        default: DRAM_K7_LEAN(6); break;
+      }
+#undef DRAM_K7_LEAN
+      DRAM_CHECK_LAUNCH("dram_upsample_mask_lean_kernel");
+      dram_finalize_kernel<<<ceil_div(2 * n, 128), 128, 0, st>>>(sums, pct, n, per_sample_denominator);
+      DRAM_CHECK_LAUNCH("dram_finalize_kernel");
+      return DRAM_OK;
+    }
+  }
   if (staged_ok && smem <= 160 * 1024) {
     const bool fast = (W % 16 == 0) && (w % 4 == 0) && (((uintptr_t)ess | (uintptr_t)lungs) % 16 == 0) &&
                       (((uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)dense0 | (uintptr_t)dense1) % 16 == 0) &&

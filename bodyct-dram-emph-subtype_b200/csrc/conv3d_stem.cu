@@ -147,6 +147,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
     const int pw = warp - ST_PROD_WARP0;
     const bool vec2 = (p.W & 1) == 0 && ((reinterpret_cast<uintptr_t>(HU ? (const void *)p.hu : (const void *)p.x) & (HU ? 3 : 7)) == 0);
     const int is_f16 = p.epi.is_f16;
+    // Round-2 finding (ncu: 60 M warp instructions per 256^3 volume at IPC 1.2, nothing else saturated): this kernel
+    // is bound by instruction issue, and the producers' per-chunk index arithmetic was the largest part.  A lane's ten
+    // chunks of a plane are (slot row r0 + 4k, column owl) for k = 0..9 with r0 = lane / 8 and owl = lane % 8 fixed,
+    // so everything but the row step 4k*W is computed once per item: the lane's offset inside the plane, which of its
+    // four 2-element pairs lie inside the volume (W even: a pair never straddles the edge) and which rows do.
+    const int owl = lane & 7, r0 = lane >> 3;
     unsigned seq_end = 0;
     for (int item = item_begin; item < item_end; ++item) {
       const StemItem it = decode_stem_item(p, item);
@@ -154,6 +160,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
       const unsigned seq_base = seq_end - (reuse ? (unsigned)ST_KEEP : 0u);
       seq_end = seq_base + ST_ITEM_PLANES;
       const int ih_base = 2 * it.h0 - 3, iw_base = 2 * it.w0 - 4;
+      const int ih_l = ih_base + r0, iw_l = iw_base + 2 * owl;   // this lane's first row / first column
+      unsigned wmask = 0, kmask = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (iw_l + 2 * q >= 0 && iw_l + 2 * q + 1 < p.W) wmask |= 1u << q;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const int ih = ih_l + 4 * k;
+        if (r0 + 4 * k < ST_ROWS && ih >= 0 && ih < p.H) kmask |= 1u << k;
+      }
+      const long long lane_off = (long long)ih_l * p.W + iw_l;   // may be negative at the low borders (never dereferenced there)
+      const long long row_step = 4LL * p.W;
       for (int j = reuse ? ST_KEEP : 0; j < ST_ITEM_PLANES; ++j) {
         const unsigned seq = seq_base + j;
         if ((int)(seq % ST_PROD_WARPS) != pw) continue;
@@ -162,70 +180,99 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
         mbar_wait(plane_empty(slot), ((seq / ST_RING) & 1u) ^ 1u);
         const bool zok = z >= 0 && z < p.D;
         const size_t plane_off = ((size_t)it.sample * p.D + (zok ? z : 0)) * p.H * (size_t)p.W;
-        const float *xz = HU ? nullptr : p.x + plane_off;
-        const short *hz = HU ? p.hu + plane_off : nullptr;
-        const float *lut = HU ? p.lut + (size_t)it.sample * p.lut_size : nullptr;
-        const uint32_t lo2 = ((uint32_t)(uint16_t)(short)p.lut_lo) * 0x10001u;
-        const uint32_t hi2 = ((uint32_t)(uint16_t)(short)(p.lut_lo + p.lut_size - 1)) * 0x10001u;
-        const uint32_t dst0 = plane_addr(slot);
+        const uint32_t dst0 = plane_addr(slot) + (uint32_t)lane * 16u;
+        if (vec2) {
+          const unsigned km = zok ? kmask : 0u;
+          if constexpr (HU) {
+            const short *base = p.hu + plane_off;
+            const float *lut = p.lut + (size_t)it.sample * p.lut_size;
+            const uint32_t lo2 = ((uint32_t)(uint16_t)(short)p.lut_lo) * 0x10001u;
+            const uint32_t hi2 = ((uint32_t)(uint16_t)(short)(p.lut_lo + p.lut_size - 1)) * 0x10001u;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float f[5][8];
+            for (int half = 0; half < 2; ++half) {
+              uint32_t u[5][4];
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const int chunk = lane + 32 * (half * 5 + c);
-            const int r = chunk >> 3, owl = chunk & 7;
-            const int ih = ih_base + r, iw0 = iw_base + 2 * owl;
+              for (int c = 0; c < 5; ++c) {
+                const int k = half * 5 + c;
+                const uint32_t *ptr = reinterpret_cast<const uint32_t *>(base + (lane_off + row_step * k));
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[c][q] = 0.0f;
-            if (chunk < ST_ROWS * ST_W && zok && ih >= 0 && ih < p.H) {
-              if constexpr (HU) {
-                const short *row = hz + (size_t)ih * p.W;
-                if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
-                  uint32_t u[4];
+                for (int q = 0; q < 4; ++q) u[c][q] = ((km >> k) & (wmask >> q) & 1u) ? __ldg(ptr + q) : 0u;
+              }
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) u[q] = __ldg(reinterpret_cast<const uint32_t *>(row + iw0) + q);
+              for (int c = 0; c < 5; ++c) {
+                const int k = half * 5 + c;
+                uint32_t w[4];
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const uint32_t ix = stem_lut_index2(u[q], lo2, hi2);
-                    f[c][2 * q] = __ldg(lut + (ix & 0xffffu));
-                    f[c][2 * q + 1] = __ldg(lut + (ix >> 16));
+                for (int q = 0; q < 4; ++q) {
+                  float a = 0.0f, b = 0.0f;
+                  if ((km >> k) & (wmask >> q) & 1u) {
+                    const uint32_t ix = stem_lut_index2(u[c][q], lo2, hi2);
+                    a = __ldg(lut + (ix & 0xffffu));
+                    b = __ldg(lut + (ix >> 16));
                   }
-                } else {
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const int iw = iw0 + q;
-                    if (iw >= 0 && iw < p.W)
-                      f[c][q] = __ldg(lut + (stem_lut_index2((uint32_t)(uint16_t)__ldg(row + iw), lo2, hi2) & 0xffffu));
-                  }
+                  w[q] = pack_pair(a, b, is_f16);
                 }
-              } else {
-                const float *row = xz + (size_t)ih * p.W;
-                if (vec2 && iw0 >= 0 && iw0 + 8 <= p.W) {
+                if (r0 + 4 * k < ST_ROWS)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)k * 512u), "r"(w[0]), "r"(w[1]),
+                               "r"(w[2]), "r"(w[3])
+                               : "memory");
+              }
+            }
+          } else {
+            const float *base = p.x + plane_off;
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float2 v = __ldg(reinterpret_cast<const float2 *>(row + iw0) + q);
-                    f[c][2 * q] = v.x;
-                    f[c][2 * q + 1] = v.y;
-                  }
-                } else {
+            for (int half = 0; half < 2; ++half) {
+              float2 v[5][4];
 #pragma unroll
-                  for (int q = 0; q < 8; ++q) {
-                    const int iw = iw0 + q;
-                    if (iw >= 0 && iw < p.W) f[c][q] = __ldg(row + iw);
-                  }
-                }
+              for (int c = 0; c < 5; ++c) {
+                const int k = half * 5 + c;
+                const float2 *ptr = reinterpret_cast<const float2 *>(base + (lane_off + row_step * k));
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  v[c][q] = ((km >> k) & (wmask >> q) & 1u) ? __ldg(ptr + q) : make_float2(0.0f, 0.0f);
+              }
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                const int k = half * 5 + c;
+                if (r0 + 4 * k < ST_ROWS)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)k * 512u),
+                               "r"(pack_pair(v[c][0].x, v[c][0].y, is_f16)), "r"(pack_pair(v[c][1].x, v[c][1].y, is_f16)),
+                               "r"(pack_pair(v[c][2].x, v[c][2].y, is_f16)), "r"(pack_pair(v[c][3].x, v[c][3].y, is_f16))
+                               : "memory");
               }
             }
           }
+        } else {
+          // generic path (odd W or an unaligned volume): element-wise bounds checks
+          const float *xz = HU ? nullptr : p.x + plane_off;
+          const short *hz = HU ? p.hu + plane_off : nullptr;
+          const float *lut = HU ? p.lut + (size_t)it.sample * p.lut_size : nullptr;
+          const uint32_t lo2 = ((uint32_t)(uint16_t)(short)p.lut_lo) * 0x10001u;
+          const uint32_t hi2 = ((uint32_t)(uint16_t)(short)(p.lut_lo + p.lut_size - 1)) * 0x10001u;
+#pragma unroll 1
+          for (int k = 0; k < 10; ++k) {
+            const int r = r0 + 4 * k;
+            if (r >= ST_ROWS) break;
+            const int ih = ih_base + r;
+            float f[8];
 #pragma unroll
-          for (int c = 0; c < 5; ++c) {
-            const int chunk = lane + 32 * (half * 5 + c);
-            if (chunk < ST_ROWS * ST_W)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)chunk * 16u),
-                           "r"(pack_pair(f[c][0], f[c][1], is_f16)), "r"(pack_pair(f[c][2], f[c][3], is_f16)),
-                           "r"(pack_pair(f[c][4], f[c][5], is_f16)), "r"(pack_pair(f[c][6], f[c][7], is_f16))
-                           : "memory");
+            for (int q = 0; q < 8; ++q) f[q] = 0.0f;
+            if (zok && ih >= 0 && ih < p.H) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int iw = iw_l + q;
+                if (iw >= 0 && iw < p.W) {
+                  if constexpr (HU)
+                    f[q] = __ldg(lut + (stem_lut_index2((uint32_t)(uint16_t)__ldg(hz + (size_t)ih * p.W + iw), lo2, hi2) & 0xffffu));
+                  else
+                    f[q] = __ldg(xz + (size_t)ih * p.W + iw);
+                }
+              }
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + (uint32_t)k * 512u),
+                         "r"(pack_pair(f[0], f[1], is_f16)), "r"(pack_pair(f[2], f[3], is_f16)),
+                         "r"(pack_pair(f[4], f[5], is_f16)), "r"(pack_pair(f[6], f[7], is_f16))
+                         : "memory");
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -233,9 +280,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
       }
     }
   } else if (warp == ST_MMA_WARP) {
+    // One elected lane issues; everything that does not change per MMA is hoisted (see conv3d_slab.cu): the weights are
+    // resident, so every B descriptor is a compile-time offset from one descriptor built here, and a plane's A
+    // descriptor is built once — two 64-bit uniform adds per tcgen05.mma.
     uint32_t idesc[4];
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) idesc[nb] = make_idesc_16bit(128, (nb + 1) * 64, p.epi.is_f16);
+    uint32_t wb = __shfl_sync(0xffffffffu, w_base, 0);
+    const uint64_t db_even = make_nosw_desc(wb, 4u * 1024u, 128u);                    // kd even: K (kh) stride 4 KiB
+    const uint64_t db_odd = make_nosw_desc(wb + ST_W_EVEN_BYTES, 3u * 1024u, 128u);   // kd odd: 3 KiB
     unsigned seq_end = 0;
     int buf = 0;
     uint32_t buf_phase = 0;
@@ -254,33 +307,32 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
         const int slot = seq % ST_RING;
         mbar_wait(plane_full(slot), (seq / ST_RING) & 1u);
         tcgen05_fence_after();
-        const uint32_t a_base = plane_addr(slot);
+        uint32_t a_base = plane_addr(slot);
+        a_base = __shfl_sync(0xffffffffu, a_base, 0);
+        const uint64_t da_plane = make_nosw_desc(a_base, 128u, 256u);
         // Input plane j feeds output planes t = t_lo .. t_hi through kd = j - 2t (same parity as j, descending as
         // t ascends).  Their accumulators are adjacent TMEM columns and the weights of one parity are stored
         // kd-descending, so ONE MMA with N = 64 * (t_hi - t_lo + 1) covers them all: the A tile (the bound
         // at N = 64, see conv3d_slab.cu) is read once for up to four output planes.
-        constexpr int kOdd = 0;
         const int t_lo = j > 6 ? (j - 5) / 2 : 0, t_hi = j / 2 < ST_GROUP - 1 ? j / 2 : ST_GROUP - 1;
         const int nblk = t_hi - t_lo + 1, kd_hi = j - 2 * t_lo;
-        const bool odd = (j & 1) != kOdd;
-        // plane of the weight region, K (kh) stride and block index of kd_hi inside the region
-        const uint32_t region = odd ? w_base + ST_W_EVEN_BYTES : w_base;
-        const uint32_t kh_stride = odd ? 3u * 1024u : 4u * 1024u;
-        const uint32_t blk0 = (uint32_t)(((odd ? 5 : 6) - kd_hi) / 2);
+        const bool odd = (j & 1) != 0;
+        const uint64_t db_region = odd ? db_odd : db_even;
+        const uint32_t kh_stride16 = (odd ? 3u * 1024u : 4u * 1024u) >> 4;
+        const uint32_t blk0 = (uint32_t)(((odd ? 5 : 6) - kd_hi) / 2);   // block index of kd_hi inside the region
         // the accumulator of output plane t is first touched by kd = 0, i.e. by the LAST block of an even plane
         const bool first_touch = !odd && (j / 2 <= ST_GROUP - 1);
+        const uint32_t d0 = tmem_d0 + (uint32_t)(t_lo * 64);
         if (elect_one_sync()) {
 #pragma unroll
           for (int pr = 0; pr < 4; ++pr) {  // kh pairs (0,1) (2,3) (4,5) (6,7): K = 16 per MMA
-            const uint64_t da = make_nosw_desc(a_base + (uint32_t)(2 * pr) * 128u, 128u, 256u);
-            const uint32_t b0 = region + (uint32_t)(2 * pr) * kh_stride + blk0 * 1024u;
-            const uint32_t d0 = tmem_d0 + (uint32_t)(t_lo * 64);
+            const uint64_t da = da_plane + (uint64_t)(((uint32_t)(2 * pr) * 128u) >> 4);
+            const uint64_t db = db_region + (uint64_t)((uint32_t)(2 * pr) * kh_stride16 + ((blk0 * 1024u) >> 4));
             const int acc_blocks = first_touch ? nblk - 1 : nblk;
-            if (acc_blocks > 0)
-              umma_bf16(d0, da, make_nosw_desc(b0, kh_stride, 128u), idesc[acc_blocks - 1], 1u);
+            if (acc_blocks > 0) umma_bf16(d0, da, db, idesc[acc_blocks - 1], 1u);
             if (first_touch)
-              umma_bf16(d0 + (uint32_t)((nblk - 1) * 64), da, make_nosw_desc(b0 + (uint32_t)(nblk - 1) * 1024u, kh_stride, 128u),
-                        idesc[0], pr > 0 ? 1u : 0u);
+              umma_bf16(d0 + (uint32_t)((nblk - 1) * 64), da, db + (uint64_t)(((uint32_t)(nblk - 1) * 1024u) >> 4), idesc[0],
+                        pr > 0 ? 1u : 0u);
           }
           if (j < ST_ITEM_PLANES - ST_KEEP || !next_reuse) umma_commit(plane_empty(slot));
         }

@@ -468,6 +468,8 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   DRAM_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv3d: padding must be >= 0");
   DRAM_REQUIRE(d->dtype == DRAM_DTYPE_BF16 || d->dtype == DRAM_DTYPE_F16, "conv3d: dtype must be bf16 (0) or fp16 (1)");
   DRAM_REQUIRE(d->algo >= DRAM_CONV_ALGO_AUTO && d->algo <= DRAM_CONV_ALGO_PLANES, "conv3d: bad algo %d", d->algo);
+  DRAM_REQUIRE(d->epilogue >= DRAM_CONV_EPILOGUE_AUTO && d->epilogue <= DRAM_CONV_EPILOGUE_STAGED, "conv3d: bad epilogue %d",
+               d->epilogue);
   DRAM_REQUIRE(d->store_out == 0 || out != nullptr, "conv3d: out is required when store_out != 0");
   DRAM_REQUIRE(d->store_out != 0 || d->n_heads > 0, "conv3d: nothing to write");
 
@@ -618,8 +620,14 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   // map — channel groups beyond res_c are out of bounds and arrive as zeros, the stride is the map's element stride.
   const bool res_tma = d->res_c % 64 == 0;
   const char *stg = getenv("DRAM_B200_STAGED_EPILOGUE");
-  pl->staged = taps == 1 && block_n >= 64 && d->store_out && d->n_heads == 0 && (d->res_c == 0 || res_tma) &&
-               !(stg && atoi(stg) == 0);
+  const bool staged_ok = taps == 1 && block_n >= 64 && d->store_out && d->n_heads == 0 && (d->res_c == 0 || res_tma);
+  if (d->epilogue == DRAM_CONV_EPILOGUE_STAGED && !staged_ok) {
+    delete pl;
+    set_error("conv3d: the staged epilogue needs a 1x1x1 filter, cout %% 64 == 0, a stored output, no heads and res_c %% 64 == 0");
+    return DRAM_E_ARG;
+  }
+  pl->staged = staged_ok && d->epilogue != DRAM_CONV_EPILOGUE_DIRECT &&
+               (d->epilogue == DRAM_CONV_EPILOGUE_STAGED || !(stg && atoi(stg) == 0));
   if (pl->staged && block_n > 128) {  // re-tile N: the staged configuration holds BLOCK_N <= 128
     block_n = 128;
     pl->block_n = block_n;

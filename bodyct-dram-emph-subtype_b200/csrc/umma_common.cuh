@@ -215,6 +215,14 @@ __device__ __forceinline__ void note_saturation(const EpiParams &e, const float 
   for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(y[j]));
   if (!(m <= 65504.0f)) atomicAdd(e.sat_count, 1u);  // also catches NaN
 }
+// ReLU folded into the conversion (cvt ... .relu clamps negative results to zero): saves one FMNMX per value in the
+// epilogues, which matter for the instruction-issue-bound kernels (stem, 1x1x1 convolutions).
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b, int is_f16) {
+  uint32_t r;
+  if (is_f16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 
 // Residual row of an output voxel (nullptr when there is no residual or the voxel is out of range).
 __device__ __forceinline__ const uint16_t *residual_row(const EpiParams &e, bool valid, int sample, int od,
@@ -266,7 +274,9 @@ __device__ __forceinline__ void epilogue_group(const EpiParams &e, const uint32_
       }
     }
   }
-  if (e.relu) {
+  // the fp32 ReLU is only needed by the heads and the saturation probe; otherwise the conversion does it
+  const bool relu_in_cvt = e.relu && !(HEADS && e.n_heads > 0) && e.sat_count == nullptr;
+  if (e.relu && !relu_in_cvt) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
   }
@@ -274,12 +284,22 @@ __device__ __forceinline__ void epilogue_group(const EpiParams &e, const uint32_
   const size_t vox = (((size_t)sample * e.Do + od) * e.Ho + oh) * e.Wo + ow;
   if (e.store_out) {
     uint4 *o4 = reinterpret_cast<uint4 *>(e.out + vox * e.cout + cg);
+    if (relu_in_cvt) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t w[4];
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
-      o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int q = 0; q < 4; ++q) w[q] = pack2_relu(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
+        o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
+        o4[j] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   }
   if (HEADS && e.n_heads > 0) {
@@ -351,7 +371,8 @@ __device__ __forceinline__ void epilogue_group_staged(const EpiParams &e, const 
       }
     }
   }
-  if (e.relu) {
+  const bool relu_in_cvt = e.relu && e.sat_count == nullptr;
+  if (e.relu && !relu_in_cvt) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
   }
@@ -360,7 +381,9 @@ __device__ __forceinline__ void epilogue_group_staged(const EpiParams &e, const 
   for (int j = 0; j < 4; ++j) {
     uint32_t w[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
+    for (int q = 0; q < 4; ++q)
+      w[q] = relu_in_cvt ? pack2_relu(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16)
+                         : pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], e.is_f16);
     const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_tile + row_off + chunk), "r"(w[0]), "r"(w[1]),
                  "r"(w[2]), "r"(w[3])

@@ -94,10 +94,10 @@ class Med3DEngine:
     # ---------------------------------------------------------------- plan
     def _add_conv(self, name, x1, wb, *, x2=None, kernel=3, stride=1, dilation=1, padding=None, relu=True,
                   residual=None, res_stride=1, heads=None, store_out=True, tile=None, flops=None,
-                  upsample_x1=False):
+                  upsample_x1=False, epilogue="auto"):
         plan = ops.Conv3dPlan(x1, wb[0], wb[1], x2=x2, scale=wb[2], kernel=kernel, stride=stride, dilation=dilation,
                               padding=padding, relu=relu, residual=residual, res_stride=res_stride,
-                              heads=heads, store_out=store_out, tile=tile, upsample_x1=upsample_x1)
+                              heads=heads, store_out=store_out, tile=tile, upsample_x1=upsample_x1, epilogue=epilogue)
         fl = plan.flops if flops is None else flops
         self.conv_flops += fl
         self.steps.append(_Step(name, plan.run, fl, plan.executed_flops))
@@ -251,7 +251,7 @@ class Med3DEngine:
         def pack_z():
             scale, _ = ops.fold_bn(bn, conv.bias)
             packed, mult = ops.pack_upconv_weight(conv.weight.detach().to(dev), c_up, scale.to(dev), dtype=bf)
-            return packed, torch.zeros(27 * 64, dtype=torch.float32, device=dev), mult
+            return packed, torch.zeros(packed.shape[0], dtype=torch.float32, device=dev), mult
 
         def pack_skip():
             scale, shift = ops.fold_bn(bn, conv.bias)
@@ -262,7 +262,9 @@ class Med3DEngine:
         m_hi = B * D2 * H2 * W2
         wz = self._register_weight("us1.0.z", pack_z)
         # algorithmic FLOPs: the reference convolves 27 taps of c_up channels at HIGH resolution
-        z = self._add_conv("us1.0.z", x4, wz, kernel=1, relu=False, flops=2 * m_hi * 64 * c_up * 27).out
+        # N tile 256 with the direct epilogue: an N = 128 staged tile pulls 128 B/clk/SM of operands through L2 for this
+        # short K loop (404 TFLOP/s measured with N = 64), N = 256 halves the activation re-reads
+        z = self._add_conv("us1.0.z", x4, wz, kernel=1, relu=False, flops=2 * m_hi * 64 * c_up * 27, epilogue="direct").out
         self.us1_r = torch.empty((B, D3, H3, W2, 9 * 64), dtype=bf, device=dev)
         self.us1_q = torch.empty((B, D3, H2, W2, 3 * 64), dtype=bf, device=dev)
         self.us1_g = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)

@@ -103,7 +103,7 @@ class Conv3dPlan:
 
     def __init__(self, x1, weight, bias, *, x2=None, scale=None, kernel=3, stride=1, dilation=1,
                  padding=None, relu=True, residual=None, res_stride=1, heads=None, store_out=True,
-                 out=None, tile=None, algo="auto", upsample_x1=False):
+                 out=None, tile=None, algo="auto", upsample_x1=False, epilogue="auto"):
         lib = _capi.load()
         _need16(x1, "conv3d x1", 5)
         adt = x1.dtype
@@ -141,6 +141,7 @@ class Conv3dPlan:
         d.dtype = ACT_DTYPES[adt]
         d.algo = _capi.CONV_ALGO[algo]
         d.src1_up2x = 1 if upsample_x1 else 0
+        d.epilogue = _capi.CONV_EPILOGUE[epilogue]
         if residual is not None:
             _need(residual, adt, "conv3d residual", 5)
             d.res_c = residual.shape[4]
@@ -442,10 +443,11 @@ def upconv_axis(x, axis, groups, out=None):
     return out
 
 
-def pack_upconv_weight(weight, c_up, scale=None, dtype=torch.bfloat16):
+def pack_upconv_weight(weight, c_up, scale=None, dtype=torch.bfloat16, pad_rows_to=256):
     """The up-sampled half of a decoder convolution [Cout=64, c_up + c_skip, 3, 3, 3] as the 1x1x1 operand of K13's
-    low-resolution product: 16-bit [27*64, c_up], row tap*64 + co = weight[co, :c_up, tap] (* scale[co]), rows
-    normalised by a power of two like `pack_conv_weight(normalize=True)`; returns (packed, multiplier fp32 [27*64])."""
+    low-resolution product: 16-bit [R, c_up], row tap*64 + co = weight[co, :c_up, tap] (* scale[co]), rows
+    normalised by a power of two like `pack_conv_weight(normalize=True)`, R = 27*64 rounded up to `pad_rows_to` with
+    zero rows; returns (packed, multiplier fp32 [R])."""
     w = weight.detach().to(torch.float32)[:, :c_up]
     if scale is not None:
         w = w * scale.to(torch.float32).view(-1, 1, 1, 1, 1)
@@ -454,7 +456,13 @@ def pack_upconv_weight(weight, c_up, scale=None, dtype=torch.bfloat16):
         raise ValueError(f"pack_upconv_weight: expected [64, C, 3, 3, 3], got {tuple(weight.shape)}")
     rows = w.reshape(cout, c_up, 27).permute(2, 0, 1).reshape(27 * cout, c_up)   # [tap][co] x ci
     mult = pow2_normalizer(rows)
-    return (rows / mult.view(-1, 1)).to(dtype).contiguous(), mult.contiguous()
+    packed = (rows / mult.view(-1, 1)).to(dtype)
+    if pad_rows_to > 1 and packed.shape[0] % pad_rows_to:
+        # zero rows up to a multiple of the GEMM's N tile (27 * 64 = 1728 -> 1792 = 7 * 256); K13's W pass skips them
+        extra = pad_rows_to - packed.shape[0] % pad_rows_to
+        packed = torch.cat([packed, packed.new_zeros((extra, c_up))])
+        mult = torch.cat([mult, mult.new_ones(extra)])
+    return packed.contiguous(), mult.contiguous()
 
 
 def masked_pool(dense, mask=None):

@@ -52,6 +52,9 @@ extern "C" {
 #define DRAM_CONV_ALGO_AUTO 0
 #define DRAM_CONV_ALGO_TILES 1
 #define DRAM_CONV_ALGO_PLANES 2
+#define DRAM_CONV_EPILOGUE_AUTO 0
+#define DRAM_CONV_EPILOGUE_DIRECT 1
+#define DRAM_CONV_EPILOGUE_STAGED 2
 
 /* ---- library ---------------------------------------------------------- */
 int dram_version(void);
@@ -114,6 +117,9 @@ typedef struct dram_conv_desc {
   int32_t src1_up2x;   /* 1: src1 is [n][di/2][hi/2][wi/2][c1] and is up-sampled x2 (trilinear,    */
                        /* align_corners=True; med3d.py:83,86) inside the kernel; di,hi,wi stay the  */
                        /* full-resolution dims.  PLANES kernel, cout == 64, c2 > 0 only             */
+  int32_t epilogue;    /* TILES kernel: DRAM_CONV_EPILOGUE_AUTO (0: staged for 1x1x1 filters), _DIRECT (1: one */
+                       /* 16-byte store per lane and row, BLOCK_N up to 256) or _STAGED (2: 128 x 64 tiles     */
+                       /* through shared memory + TMA stores, BLOCK_N <= 128; 1x1x1 filters only)              */
 } dram_conv_desc;
 
 typedef struct dram_conv_plan dram_conv_plan; /* opaque: tensor maps + launch geometry */

@@ -463,7 +463,8 @@ def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
     ref = torch.relu(F.conv3d(torch.cat([up, x1], 1), wgt, None, padding=1) * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1))
     x4d, x1d = ops.to_ndhwc_16(x4.to(cuda), dt), ops.to_ndhwc_16(x1.to(cuda), dt)
     wz, mz = ops.pack_upconv_weight(wgt.to(cuda), c_up, scale.to(cuda), dtype=dt)
-    z = ops.Conv3dPlan(x4d, wz, torch.zeros(27 * 64, device=cuda), scale=mz, kernel=1, relu=False).run()
+    assert wz.shape == (1792, c_up) and not bool(wz[1728:].any())    # padded to 7 N-tiles of 256 with zero rows
+    z = ops.Conv3dPlan(x4d, wz, torch.zeros(wz.shape[0], device=cuda), scale=mz, kernel=1, relu=False, epilogue="direct").run()
     gath = ops.upconv_axis(ops.upconv_axis(ops.upconv_axis(z, 3, 9), 2, 3), 1, 1)
     ws, ms = ops.pack_conv_weight(wgt.to(cuda)[:, c_up:], scale.to(cuda), dtype=dt, normalize=True)
     out = ops.Conv3dPlan(x1d, ws, shift.to(cuda), scale=ms, residual=gath).run()

@@ -87,7 +87,7 @@ def main():
 
     hu_b, lungs_b, ess_b = bench.make_volumes(B, (S, S, S), dev, seed=0)
     for tag, e_, l_ in (("random 7.5 % ess", ess, lungs), ("synthetic CT masks", ess_b, lungs_b)):
-        for mode in ("rows", "staged"):
+        for mode in ("rows", "staged", "lean"):
             os.environ["DRAM_B200_K7"] = mode
             ms = timeit(lambda: ops.dram_upsample_mask(dense0, dense1, e_, l_, (S, S, S)))
             report(f"K7 dRAM {mode}, {tag}", ms, B * (2 * h ** 3 * 4 + 2 * V + 2 * V * 4))
