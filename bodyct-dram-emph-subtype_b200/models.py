@@ -332,6 +332,14 @@ class ScanRegLightningModule(_ScanModule):
             except Exception:
                 table = None
         if table is None:
+            # the reference reads the table from its training dataset and fails without one (models.py:546-551);
+            # uniform weights change the loss, so say so once instead of silently training something else
+            if not getattr(self, "_warned_class_weights", False):
+                import warnings
+
+                warnings.warn(f"{name} not set on the module or its datamodule's training dataset: using uniform class "
+                              "weights (the reference raises here)", RuntimeWarning, stacklevel=3)
+                object.__setattr__(self, "_warned_class_weights", True)
             return torch.ones(len(labels), dtype=torch.float32)
         return torch.tensor([float(table[int(c)]) for c in labels], dtype=torch.float32)
 
@@ -390,6 +398,23 @@ class ScanRegLightningModule(_ScanModule):
         eng = getattr(self, "_train_engine", None)
         if eng is not None:
             eng.decay_lr(0.95)  # ExponentialLR(gamma=0.95), one step per epoch (models.py:694-697)
+            if eng.peer is not None:
+                eng.peer.check()  # a SyncBatchNorm exchange that timed out fell back to local statistics: fail loudly
+
+    # Lightning's checkpoint hooks: the optimiser lives in K12's flat buffers, not in configure_optimizers(), so its
+    # state (Adam moments, step count, decayed learning rate) travels in the checkpoint under its own key.
+    def on_save_checkpoint(self, checkpoint):
+        eng = getattr(self, "_train_engine", None)
+        if eng is not None and hasattr(eng.opt, "exp_avg"):
+            checkpoint["dram_b200_flat_adam"] = {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v)
+                                                 for k, v in eng.opt.state_dict().items()}
+
+    def on_load_checkpoint(self, checkpoint):
+        state = checkpoint.get("dram_b200_flat_adam")
+        if state is not None:
+            eng = self.train_engine()
+            if hasattr(eng.opt, "exp_avg"):
+                eng.opt.load_state_dict(state)
 
     def _eval_step(self, batch, batch_idx):
         """shared_step(VALID / TEST), models.py:571-582 without the debug drawings: forward, predicted labels."""

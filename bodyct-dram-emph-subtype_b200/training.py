@@ -480,6 +480,9 @@ class TrainStep:
                 self.buckets.reduce_bucket(i, self.group)
         self.buckets.wait()
         self.opt.step()
+        self.steps_done = getattr(self, "steps_done", 0) + 1
+        if self.peer is not None and self.steps_done % 256 == 0:
+            self.peer.check()  # one 4-byte read-back every 256 steps: ranks must not drift apart on local statistics
         # the kernels changed the parameters behind autograd's back: bump the version counters, and tell the
         # inference engines of the module to re-pack (med3d._Med3DSegNet.weights_epoch)
         torch.autograd.graph.increment_version([p for _, p in self.params])

@@ -247,6 +247,21 @@ def test_lightning_training_step_surface(cuda, lib):
     lr0 = module.train_engine().opt.lr
     module.on_train_epoch_end()
     assert abs(module.train_engine().opt.lr - 0.95 * lr0) < 1e-12
+    # Lightning checkpoint hooks: Adam's moments, step count and the decayed learning rate survive a save / load
+    ckpt = {"state_dict": {k: v.detach().clone() for k, v in module.state_dict().items()}}
+    module.on_save_checkpoint(ckpt)
+    saved = ckpt["dram_b200_flat_adam"]
+    assert saved["step"] == 3 and abs(saved["lr"] - 0.95 * lr0) < 1e-12 and not saved["exp_avg"].is_cuda
+    fresh = ScanRegLightningModule(Namespace(model_arch="med3ddram18", lr=1e-4))
+    fresh.load_state_dict(ckpt["state_dict"])
+    fresh = fresh.to(cuda)
+    fresh.on_load_checkpoint(ckpt)
+    opt = fresh.train_engine().opt
+    assert opt.steps == 3 and abs(opt.lr - 0.95 * lr0) < 1e-12
+    assert torch.equal(opt.exp_avg.cpu(), saved["exp_avg"]) and torch.equal(opt.exp_avg_sq.cpu(), saved["exp_avg_sq"])
+    with pytest.warns(RuntimeWarning, match="class weights"):
+        fresh.training_step(batch, 0)   # no class-weight table anywhere: uniform weights, said out loud
+    del fresh
     val = module.validation_step(batch, 0)
     assert set(val) == {"pred_cle_labels", "pred_pse_labels", "cle_labels", "pse_labels", "index"}
     pred = module.predict_step({"image": case["image"], "lung_mask": case["lung_mask"], "ess_mask": case["em_mask"]}, 0)
