@@ -328,20 +328,42 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               __syncwarp();
             } else {
               if (elect_one_sync()) {
+                // Issue order inside a stage.  Consecutive tcgen05.mma on the SAME accumulator columns serialise on
+                // the accumulate (measured: ~34 clocks per instruction on top of its operand-read time, whatever N),
+                // so the K steps are the OUTER loop and the planes are visited in an order in which neighbours write
+                // disjoint output tiles: plane j feeds tiles {j-2..j} & [0,3] -> 0:{0} 4:{2,3} 1:{0,1} 5:{3} 2:{0,1,2}
+                // 3:{1,2,3}: only 2 -> 3 (and nothing across K steps: 3 -> 0) share columns.
+#ifndef DRAM_SLAB_MMA_ORDER
+#define DRAM_SLAB_MMA_ORDER 1
+#endif
+                constexpr int kOrder[2][ITEM_PLANES] = {{0, 1, 2, 3, 4, 5}, {0, 4, 1, 5, 2, 3}};
+#if DRAM_SLAB_MMA_ORDER == 0
 #pragma unroll
-                for (int j = 0; j < ITEM_PLANES; ++j) {
-                  // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
-                  const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
-                  const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
-                  const uint64_t da = da_plane[j] + row_off16;
-                  const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
-                  const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
+                for (int jj = 0; jj < ITEM_PLANES; ++jj) {
+                  const int j = kOrder[0][jj];
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
+                  for (int k = 0; k < 4; ++k) {
+#else
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                  for (int jj = 0; jj < ITEM_PLANES; ++jj) {
+                    const int j = kOrder[1][jj];
+#endif
+                    // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
+                    const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+                    const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+                    const uint64_t da = da_plane[j] + row_off16;
+                    const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
+                    const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
                     umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
-                  // last stage of the chunk: hand each plane back as soon as its MMAs are issued so the
-                  // producer refills the ring while the remaining planes of this stage are still computing
-                  if (hw == 8 && (j < SL_GROUP || !next_reuse)) umma_commit(empty_bar[j]);
+                  }
+                }
+                // last stage of the chunk: hand the planes back (the commits track every MMA issued so far)
+                if (hw == 8) {
+#pragma unroll
+                  for (int j = 0; j < ITEM_PLANES; ++j)
+                    if (j < SL_GROUP || !next_reuse) umma_commit(empty_bar[j]);
                 }
                 umma_commit(b_empty(stage));
               }
