@@ -657,7 +657,19 @@ dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__
       }
     }
   }
-  if (row_ok) {
+  if (!need) {
+    // no `ess` voxel in this slice (~90 % of the CTAs of a chest volume): the slice's RY rows are one contiguous run of
+    // RY * W floats per map — fill it with fully coalesced 16-byte stores (lane-consecutive addresses: 4 L1 wavefronts
+    // per instruction instead of the 16 of the per-segment layout below)
+    const int rows = min(RY, H - xh0);
+    const int64_t slice = (int64_t)b * vol + ((int64_t)xd * H + xh0) * W;
+    const int n4 = rows * (W >> 2);
+    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int t = threadIdx.x; t < n4; t += 256) {
+      __stcs(reinterpret_cast<float4 *>(out0 + slice) + t, z4);
+      __stcs(reinterpret_cast<float4 *>(out1 + slice) + t, z4);
+    }
+  } else if (row_ok) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       __stcs(reinterpret_cast<float4 *>(out0 + o) + q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));

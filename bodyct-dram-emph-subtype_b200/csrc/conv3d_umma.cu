@@ -41,13 +41,16 @@ static constexpr int RES_BUFS = 4;                           // residual tiles i
 // instead of one 16-byte global access per lane and row.  Used for the 1x1x1 convolutions of the bottleneck
 // blocks, which are bound by exactly those accesses (K is at most 32 chunks), with BLOCK_N <= 128 so that four
 // operand stages, two output tiles and four residual tiles fit in shared memory together.
+// BLOCK_N = 256 staged: for 1x1x1 convolutions WITHOUT a residual (K13's low-resolution product, the bottleneck blocks'
+// first convolution): no residual tiles, three operand stages of 48 KiB.
 template <int BLOCK_N, bool STAGED = false>
 struct ConvCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = STAGED ? 4 : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
+  static constexpr int STAGES = STAGED ? (BLOCK_N == 256 ? 3 : 4) : ((BLOCK_N <= 64) ? 8 : (BLOCK_N == 128 ? 6 : 4));
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr int EPI_BYTES = STAGED ? (2 + RES_BUFS) * EPI_TILE_BYTES : 0;  // output + residual tiles
+  static constexpr int RES_TILES = BLOCK_N == 256 ? 0 : RES_BUFS;
+  static constexpr int EPI_BYTES = STAGED ? (2 + RES_TILES) * EPI_TILE_BYTES : 0;  // output + residual tiles
   // 1 KiB alignment slack + stages + epilogue tiles + barriers
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
 };
@@ -628,7 +631,10 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   }
   pl->staged = staged_ok && d->epilogue != DRAM_CONV_EPILOGUE_DIRECT &&
                (d->epilogue == DRAM_CONV_EPILOGUE_STAGED || !(stg && atoi(stg) == 0));
-  if (pl->staged && block_n > 128) {  // re-tile N: the staged configuration holds BLOCK_N <= 128
+  // BLOCK_N = 256 staged exists without residual tiles only, and only on request (DRAM_CONV_EPILOGUE_STAGED): AUTO keeps
+  // the N = 128 tiling that the bottleneck blocks were tuned with
+  const bool staged256 = pl->staged && block_n == 256 && d->res_c == 0 && d->epilogue == DRAM_CONV_EPILOGUE_STAGED;
+  if (pl->staged && block_n > 128 && !staged256) {  // re-tile N: the staged configuration with residual tiles holds BLOCK_N <= 128
     block_n = 128;
     pl->block_n = block_n;
     p.num_n_tiles = d->cout / block_n;
@@ -655,6 +661,7 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
     if (pl->staged) {
       switch (block_n) {
         case 64: rc = fill_tile_cfg<64, true>(pl); break;
+        case 256: rc = fill_tile_cfg<256, true>(pl); break;
         default: rc = fill_tile_cfg<128, true>(pl); break;
       }
     } else if (d->tw == 0 && pair_plan_wanted(d, block_n, (int64_t)taps * p.chunks_total, pl->m_tiles, pl->n_tiles)) {
@@ -748,6 +755,7 @@ extern "C" int dram_conv3d_run(const dram_conv_plan *plan, int32_t max_ctas, voi
   if (plan->staged) {
     switch (plan->block_n) {
       case 64: launch_tiles<64, true>(plan, grid, st); break;
+      case 256: launch_tiles<256, true>(plan, grid, st); break;
       default: launch_tiles<128, true>(plan, grid, st); break;
     }
   } else {

@@ -40,25 +40,24 @@ __device__ __forceinline__ void upconv_fma8(float (&acc)[8], const uint4 u, floa
   }
 }
 
+// Thread block = (8 channel groups, G tap groups, P output positions), 8 * G * P <= 256: the channel / tap-group part of
+// the index is the thread's coordinate, only the position is decoded (32-bit divisions, once per thread) — the first
+// version decoded a flat 64-bit index with six divisions and was bound by them (2 TB/s).
 template <bool F16>
 __global__ void __launch_bounds__(256)
-upconv_axis_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int64_t outer, int L_lo, int L_hi, int64_t inner,
-                   int G, int in_g_stride /* uint4 units between tap groups of one input position */, float scale) {
-  const int64_t total = outer * L_hi * inner * G * 8;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(t & 7);
-    int64_t v = t >> 3;
-    const int g = (int)(v % G);
-    v /= G;
-    const int64_t isp = v % inner;
-    v /= inner;
-    const int o = (int)(v % L_hi);
-    const int64_t ou = v / L_hi;
+upconv_axis_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, unsigned positions, int L_lo, int L_hi, unsigned inner,
+                   int G, int in_g_stride /* uint4 units per input position */, float scale) {
+  const int c8 = threadIdx.x, g = threadIdx.y;
+  for (unsigned pos = blockIdx.x * blockDim.z + threadIdx.z; pos < positions; pos += gridDim.x * blockDim.z) {
+    const unsigned isp = pos % inner;
+    const unsigned v = pos / inner;
+    const int o = (int)(v % (unsigned)L_hi);
+    const unsigned ou = v / (unsigned)L_hi;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-    const uint4 *base = in + ((ou * L_lo * inner + isp) * (int64_t)in_g_stride) + (int64_t)g * 24 + c8;
-    const int64_t lstride = inner * (int64_t)in_g_stride;  // uint4 units between consecutive low-resolution positions
+    const uint4 *base = in + ((int64_t)ou * L_lo * inner + isp) * (int64_t)in_g_stride + g * 24 + c8;
+    const int64_t lstride = (int64_t)inner * in_g_stride;  // uint4 units between consecutive low-resolution positions
 #pragma unroll
     for (int tap = 0; tap < 3; ++tap) {
       const int p = o + tap - 1;
@@ -69,22 +68,18 @@ upconv_axis_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int64_
       upconv_fma8<F16>(acc, a, li.w0);
       upconv_fma8<F16>(acc, b, li.w1);
     }
-    uint4 r;
+    uint32_t w[4];
     if constexpr (F16) {
-      uint32_t w[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[q]) : "f"(acc[2 * q + 1]), "f"(acc[2 * q]));
-      r = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      uint32_t w[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
         w[q] = *reinterpret_cast<const uint32_t *>(&h);
       }
-      r = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    out[t] = r;
+    out[((int64_t)pos * G + g) * 8 + c8] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -102,15 +97,23 @@ extern "C" int dram_upconv_axis(const void *in, void *out, int64_t outer, int32_
                in_channels, groups);
   DRAM_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "dram_upconv_axis: buffers must be 16-byte aligned");
-  const int64_t total = outer * l_hi * inner * groups * 8;
-  const int grid = stream_grid(total, 256, 8);
+  const int64_t positions = outer * l_hi * inner;
+  DRAM_REQUIRE(positions < 0xffffffffLL && inner < 0xffffffffLL && groups <= 32,
+               "dram_upconv_axis: too many output positions for 32-bit indexing");
+  const int per_block = 256 / (8 * groups) > 0 ? 256 / (8 * groups) : 1;
+  const dim3 block(8, groups, per_block);
+  int64_t want = ceil_div64(positions, per_block);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(want < cap ? want : cap);
   const float scale = ac_scale(l_lo, l_hi);
   if (dtype == DRAM_DTYPE_F16)
-    upconv_axis_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4 *>(in), reinterpret_cast<uint4 *>(out), outer, l_lo, l_hi, inner, groups, in_channels / 8, scale);
+    upconv_axis_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(in), reinterpret_cast<uint4 *>(out), (unsigned)positions, l_lo, l_hi, (unsigned)inner, groups,
+        in_channels / 8, scale);
   else
-    upconv_axis_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4 *>(in), reinterpret_cast<uint4 *>(out), outer, l_lo, l_hi, inner, groups, in_channels / 8, scale);
+    upconv_axis_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4 *>(in), reinterpret_cast<uint4 *>(out), (unsigned)positions, l_lo, l_hi, (unsigned)inner, groups,
+        in_channels / 8, scale);
   DRAM_CHECK_LAUNCH("upconv_axis_kernel");
   return DRAM_OK;
 }

@@ -262,9 +262,11 @@ class Med3DEngine:
         m_hi = B * D2 * H2 * W2
         wz = self._register_weight("us1.0.z", pack_z)
         # algorithmic FLOPs: the reference convolves 27 taps of c_up channels at HIGH resolution
-        # N tile 256 with the direct epilogue: an N = 128 staged tile pulls 128 B/clk/SM of operands through L2 for this
-        # short K loop (404 TFLOP/s measured with N = 64), N = 256 halves the activation re-reads
-        z = self._add_conv("us1.0.z", x4, wz, kernel=1, relu=False, flops=2 * m_hi * 64 * c_up * 27, epilogue="direct").out
+        # N tile 256 (an N = 128 tile pulls 128 B/clk/SM of operands through L2 for this short K loop; N = 64 measured
+        # 404 TFLOP/s).  Epilogue: staged through shared memory + TMA stores by default — the direct epilogue writes
+        # the 3.5 KB rows of z 16 bytes per lane, half a sector each; DRAM_B200_US1_EPILOGUE=direct for A/B runs.
+        z_epi = os.environ.get("DRAM_B200_US1_EPILOGUE", "staged").lower()
+        z = self._add_conv("us1.0.z", x4, wz, kernel=1, relu=False, flops=2 * m_hi * 64 * c_up * 27, epilogue=z_epi).out
         self.us1_r = torch.empty((B, D3, H3, W2, 9 * 64), dtype=bf, device=dev)
         self.us1_q = torch.empty((B, D3, H2, W2, 3 * 64), dtype=bf, device=dev)
         self.us1_g = torch.empty((B, D2, H2, W2, 64), dtype=bf, device=dev)

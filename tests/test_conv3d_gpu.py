@@ -464,7 +464,11 @@ def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
     x4d, x1d = ops.to_ndhwc_16(x4.to(cuda), dt), ops.to_ndhwc_16(x1.to(cuda), dt)
     wz, mz = ops.pack_upconv_weight(wgt.to(cuda), c_up, scale.to(cuda), dtype=dt)
     assert wz.shape == (1792, c_up) and not bool(wz[1728:].any())    # padded to 7 N-tiles of 256 with zero rows
-    z = ops.Conv3dPlan(x4d, wz, torch.zeros(wz.shape[0], device=cuda), scale=mz, kernel=1, relu=False, epilogue="direct").run()
+    zplan = ops.Conv3dPlan(x4d, wz, torch.zeros(wz.shape[0], device=cuda), scale=mz, kernel=1, relu=False, epilogue="staged")
+    assert zplan.block_n == 256    # the staged epilogue without residual tiles keeps the 256-wide N tile
+    z = zplan.run()
+    zd = ops.Conv3dPlan(x4d, wz, torch.zeros(wz.shape[0], device=cuda), scale=mz, kernel=1, relu=False, epilogue="direct").run()
+    assert torch.equal(z, zd)      # staged and direct epilogues: same arithmetic, same bits
     gath = ops.upconv_axis(ops.upconv_axis(ops.upconv_axis(z, 3, 9), 2, 3), 1, 1)
     ws, ms = ops.pack_conv_weight(wgt.to(cuda)[:, c_up:], scale.to(cuda), dtype=dt, normalize=True)
     out = ops.Conv3dPlan(x1d, ws, shift.to(cuda), scale=ms, residual=gath).run()
