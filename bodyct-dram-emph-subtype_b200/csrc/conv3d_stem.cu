@@ -36,7 +36,8 @@ static constexpr int ST_WEIGHT_BYTES = ST_W_EVEN_BYTES + ST_W_ODD_BYTES;  // 573
 static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = 8;
 static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 416
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
-static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 512;
+static constexpr int ST_OUT_TILE_BYTES = 128 * 128;           // staged epilogue: 128 voxels x 64 channels, SWIZZLE_128B
+static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 2 * ST_OUT_TILE_BYTES + 512;
 
 struct StemParams {
   const float *x;       // fp32 [n][D][H][W] (kernel variant HU = false)
@@ -94,11 +95,13 @@ __device__ __forceinline__ uint32_t stem_lut_index2(uint32_t pair, uint32_t lo2,
 }
 
 template <bool HU>
-__global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid_constant__ StemParams p) {
+__global__ void __launch_bounds__(ST_THREADS, 1)
+conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base + ST_RING * ST_PLANE_BYTES;
-  const uint32_t bar_base = w_base + ST_WEIGHT_BYTES;
+  const uint32_t out_base = w_base + ST_WEIGHT_BYTES;   // 1 KiB aligned: 95 KiB of planes + 56 KiB of weights
+  const uint32_t bar_base = out_base + 2 * ST_OUT_TILE_BYTES;
   auto plane_addr = [&](int s) { return smem_base + (uint32_t)s * ST_PLANE_BYTES; };
   auto plane_full = [&](int s) { return bar_base + 8u * s; };
   auto plane_empty = [&](int s) { return bar_base + 8u * (ST_RING + s); };
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == ST_MMA_WARP) tmem_alloc(tmem_slot, ST_TMEM_COLS);
+  if (threadIdx.x == 0) prefetch_tensormap(&map_out);
   // resident weights: plain 16-byte copies, made visible to the tensor-core (async) proxy below
   for (int i = threadIdx.x; i < ST_WEIGHT_BYTES / 16; i += ST_THREADS) {
     const uint4 v = __ldg(p.weight + i);
@@ -347,28 +351,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
     }
   } else {
     // ------------------------------- epilogue warps 0..3 -------------------------------
+    // Staged through shared memory: a lane owns one voxel (row) of the 8 x 16 tile and writes its 64 channels into a
+    // SWIZZLE_128B tile; one thread sends the finished 16 KiB tile with ONE TMA store (full 128-byte lines; the tensor
+    // map clips voxels outside the volume).  The direct form — four 16-byte stores per lane and 32-channel group, each
+    // to a different 128-byte line — kept the L1/LSU pipe 70 % busy with half-filled sectors (ncu, round 2) in a
+    // kernel that writes 268 MB per 256^3 volume.
     const int row = warp * 32 + lane;
-    const int lw = row & (ST_W - 1);
-    const int lh = row >> 3;
-    int buf = 0;
+    int buf = 0, ob = 0;
     uint32_t buf_phase = 0;
     for (int item = item_begin; item < item_end; ++item) {
       const StemItem it = decode_stem_item(p, item);
-      const int oh = it.h0 + lh, ow = it.w0 + lw;
       mbar_wait(tmem_full(buf), buf_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int t = 0; t < ST_GROUP; ++t) {
         const int od = it.q0 + t;
-        const bool valid = (od < p.epi.Do) && (oh < p.epi.Ho) && (ow < p.epi.Wo);
         const uint32_t taddr = tmem_base + (uint32_t)((buf * ST_GROUP + t) * 64) + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tile = out_base + (uint32_t)ob * ST_OUT_TILE_BYTES;
+        // the store that last read this tile (two tiles ago) must be done with shared memory
+        if (threadIdx.x == 0) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
         for (int c0 = 0; c0 < 64; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
           tmem_wait_ld();
-          if (valid) epilogue_group<false>(p.epi, v, c0, it.sample, od, oh, ow, nullptr);
+          epilogue_group_staged(p.epi, v, c0, row, c0 >> 5, 0u, false, tile);
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 0 && od < p.epi.Do) {
+          tma_store_5d(&map_out, tile, 0, it.w0, it.h0, od, it.sample);
+          tma_store_commit();
+        }
+        ob ^= 1;
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty(buf));
@@ -377,6 +393,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) conv3d_stem_kernel(const __grid
         buf_phase ^= 1u;
       }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
   tcgen05_fence_before();
@@ -425,13 +442,16 @@ static int stem_launch(StemParams &p, const void *weight, const float *bias, con
                    : check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      ST_SMEM_BYTES), "cudaFuncSetAttribute(conv3d_stem_kernel)");
   if (rc != DRAM_OK) return rc;
+  CUtensorMap map_out;  // one output plane of an item: 64 channels x 8 (W) x 16 (H) voxels, SWIZZLE_128B rows
+  rc = encode_act_map(&map_out, out, n, Do, Ho, Wo, 64, 64, ST_W, ST_H, 1, 1, 1, 1, p.epi.is_f16);
+  if (rc != DRAM_OK) return rc;
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
   if (p.items_total < ctas) ctas = p.items_total;
   if (from_hu)
-    conv3d_stem_kernel<true><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    conv3d_stem_kernel<true><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(map_out, p);
   else
-    conv3d_stem_kernel<false><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    conv3d_stem_kernel<false><<<ctas, ST_THREADS, ST_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(map_out, p);
   DRAM_CHECK_LAUNCH("conv3d_stem_kernel launch");
   return DRAM_OK;
 }
