@@ -173,6 +173,9 @@ def test_train_step_updates_and_is_repeatable(cuda, lib):
     assert torch.equal(sd["layer1.0.conv1.weight"], model.layer1[0].conv1.weight.detach())
 
 
+WGRAD_ROUTE_TOL = 1e-3
+
+
 def test_native_loss_and_adam_equal_the_aten_step(cuda, lib):
     """TrainStep's native tail (K11 loss, K9 writing into the flat gradient buffer, K12 Adam) against the plain autograd
     route on a second copy of the network: ATen loss (`training.training_loss`), gradients accumulated by autograd's
@@ -200,13 +203,18 @@ def test_native_loss_and_adam_equal_the_aten_step(cuda, lib):
     assert abs(la - lb) <= 1e-5 * abs(lb), (la, lb)
     for r_n, r_b in zip(native.last["reg_outs"], regs):
         assert torch.allclose(r_n, r_b.detach(), rtol=1e-5, atol=1e-7)
-    dot = na = nb = 0.0
+    dot = na = nb = worst = 0.0
     for n, pb in model_b.named_parameters():
         ga, gb = native.buckets.view(n).double(), pb.grad.double()
         dot, na, nb = dot + float((ga * gb).sum()), na + float((ga * ga).sum()), nb + float((gb * gb).sum())
         if n.endswith("conv1.weight") or n.endswith("conv2.weight") or ".conv_blocks." in n and n.endswith("0.weight"):
-            assert float((ga - gb).abs().max()) <= 1e-3 * float(gb.abs().max()) + 1e-12, n
+            rel = float((ga - gb).abs().max()) / (float(gb.abs().max()) + 1e-30)
+            if rel > 5e-4:
+                print(f"weight gradient {n}: native vs autograd route differ by {rel:.3g} of the largest entry")
+            worst = max(worst, rel)
     cos = dot / (na ** 0.5 * nb ** 0.5)
+    print(f"native vs autograd route: worst convolution weight gradient difference {worst:.3g} of its largest entry, cosine {cos:.7f}")
+    assert worst <= WGRAD_ROUTE_TOL, worst
     assert cos >= 0.9999, cos
     torch.optim.Adam(model_b.parameters(), lr=lr).step()
     diff_sum, count = 0.0, 0
