@@ -328,13 +328,16 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               __syncwarp();
             } else {
               if (elect_one_sync()) {
-                // Issue order inside a stage.  Consecutive tcgen05.mma on the SAME accumulator columns serialise on
-                // the accumulate (measured: ~34 clocks per instruction on top of its operand-read time, whatever N),
-                // so the K steps are the OUTER loop and the planes are visited in an order in which neighbours write
-                // disjoint output tiles: plane j feeds tiles {j-2..j} & [0,3] -> 0:{0} 4:{2,3} 1:{0,1} 5:{3} 2:{0,1,2}
-                // 3:{1,2,3}: only 2 -> 3 (and nothing across K steps: 3 -> 0) share columns.
+                // Issue order inside a stage: plane by plane, the four K steps of a plane back to back (order 0).
+                // Tried and REJECTED (order 1, kept behind -DDRAM_SLAB_MMA_ORDER=1 for the record): K steps outermost
+                // and the planes visited as 0,4,1,5,2,3 so that neighbouring instructions write disjoint output tiles.
+                // It ran 2-3 % faster, but the results were no longer reproducible: the training test that feeds two
+                // bit-identical gradient tensors through two copies of the network got weight gradients that differed
+                // by up to 1 % of their largest entry (0 with order 0) — instructions whose accumulator column ranges
+                // overlap only PARTLY (plane j writes tiles {j-2..j}) do not appear to be ordered against each other
+                // once independent instructions sit between them.
 #ifndef DRAM_SLAB_MMA_ORDER
-#define DRAM_SLAB_MMA_ORDER 1
+#define DRAM_SLAB_MMA_ORDER 0
 #endif
                 constexpr int kOrder[2][ITEM_PLANES] = {{0, 1, 2, 3, 4, 5}, {0, 4, 1, 5, 2, 3}};
 #if DRAM_SLAB_MMA_ORDER == 0
