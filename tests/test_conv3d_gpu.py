@@ -477,3 +477,39 @@ def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
     # rounding points: z, two intermediate gathers, the gathered tensor, the output (direct route: up(x4), the output)
     ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
     assert err.max().item() <= 6 * ulp * ref.abs().max().item(), (err.max().item(), ref.abs().max().item())
+
+
+@pytest.mark.parametrize("c1,c2,cout,k,dil,dims", [(64, 0, 64, 3, 1, (24, 64, 64)), (64, 64, 64, 3, 1, (16, 48, 64)),
+                                                   (64, 0, 32, 3, 1, (24, 64, 64)), (128, 0, 256, 3, 2, (16, 16, 16)),
+                                                   (256, 0, 128, 1, 1, (16, 16, 32))])
+def test_convolutions_are_reproducible_bit_for_bit(cuda, lib, c1, c2, cout, k, dil, dims):
+    """Same buffers, same plan, six launches: identical bits.  (Round 2 tried an MMA issue order in the plane-ring
+    kernel that interleaved instructions with partially overlapping accumulator ranges; it was faster and NOT
+    reproducible — this is the test that guards the in-order issue, on shapes large enough to keep every SM busy.)"""
+    from dram_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x1 = torch.randn((2,) + dims + (c1,), generator=g, device=cuda).half()
+    x2 = torch.randn((2,) + dims + (c2,), generator=g, device=cuda).half() if c2 else None
+    w = (torch.randn((cout, k ** 3 * (c1 + c2)), generator=g, device=cuda) * 0.02).half()
+    heads = (torch.randn(2, 32, device=cuda), torch.zeros(2, device=cuda), (1, 1), True) if cout == 32 else None
+    plan = ops.Conv3dPlan(x1, w, torch.zeros(cout, device=cuda), x2=x2, kernel=k, dilation=dil, heads=heads,
+                          store_out=heads is None)
+    outs = []
+    for _ in range(6):
+        plan.run()
+        outs.append((plan.head_outs[0] if heads else plan.out).clone())
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+def test_stem_is_reproducible_bit_for_bit(cuda, lib):
+    from dram_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randn((2, 48, 96, 128), generator=g, device=cuda)
+    w = torch.randn((64, 1, 7, 7, 7), generator=g, device=cuda) * 0.05
+    packed, mult = ops.pack_stem_weight_fused(w, dtype=torch.float16, normalize=True)
+    bias = torch.zeros(64, device=cuda)
+    outs = [ops.stem_conv7(x, packed, bias, mult).clone() for _ in range(6)]
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
