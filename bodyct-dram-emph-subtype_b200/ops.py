@@ -485,8 +485,8 @@ def masked_pool(dense, mask=None):
     return out
 
 
-def dram_upsample_mask(dense0, dense1, ess, lungs, size, per_sample_denominator=False):
-    """K7: returns (out0, out1 fp32 [N,1,D,H,W], pct fp32 [2, N])."""
+def dram_upsample_mask(dense0, dense1, ess, lungs, size, per_sample_denominator=False, out=None):
+    """K7: returns (out0, out1 fp32 [N,1,D,H,W], pct fp32 [2, N]).  `out`: optional preallocated (out0, out1)."""
     lib = _capi.load()
     _need(dense0, torch.float32, "dram dense0", 5)
     _need(dense1, torch.float32, "dram dense1", 5)
@@ -498,8 +498,15 @@ def dram_upsample_mask(dense0, dense1, ess, lungs, size, per_sample_denominator=
     D, H, W = size
     if tuple(ess.shape) != (n, D, H, W) or tuple(lungs.shape) != (n, D, H, W):
         raise ValueError("dram_upsample_mask: mask shape mismatch")
-    out0 = torch.empty((n, 1, D, H, W), dtype=torch.float32, device=dense0.device)
-    out1 = torch.empty_like(out0)
+    if out is None:
+        out0 = torch.empty((n, 1, D, H, W), dtype=torch.float32, device=dense0.device)
+        out1 = torch.empty_like(out0)
+    else:
+        out0, out1 = out
+        _need(out0, torch.float32, "dram out0", 5)
+        _need(out1, torch.float32, "dram out1", 5)
+        if tuple(out0.shape) != (n, 1, D, H, W) or tuple(out1.shape) != (n, 1, D, H, W):
+            raise ValueError("dram_upsample_mask: out tensors must be [N,1,D,H,W]")
     pct = torch.empty((2, n), dtype=torch.float32, device=dense0.device)
     ws = torch.empty(lib.dram_dram_workspace_bytes(n), dtype=torch.uint8, device=dense0.device)
     check(lib.dram_dram_upsample_mask(_p(dense0), _p(dense1), _p(ess), _p(lungs), _p(out0), _p(out1), _p(pct),
