@@ -543,6 +543,45 @@ def run_train_arm(args, out):
     out.emit(json.dumps(line))
 
 
+def training_field(device, dims, arch, steps):
+    """BASELINE config 5 as an extra FIELD of the default line (N = 1 only; `--mode train` prints the full line and is
+    what runs under torchrun): one training step = forward + loss + backward + Adam on the hand-written kernels, bf16
+    activations, per-GPU batch 1, batch resident in HBM."""
+    import dram_b200  # noqa: F401
+    from dram_b200 import med3d, training
+
+    torch.manual_seed(0)
+    factory = {"med3ddram": med3d.resnet34segreg, "med3ddram18": med3d.resnet18segreg, "med3ddram50": med3d.resnet50segreg}
+    model = factory[arch]().to(device).train()
+    step = training.TrainStep(model, lr=1e-5, sync_bn=False)
+    hu, lungs, ess = make_volumes(1, dims, device, seed=0)
+    v = (hu.float().clamp(-1150.0, -300.0) + 1150.0) / 850.0
+    image = (v - v.mean(dim=(1, 2, 3), keepdim=True)) / v.std(dim=(1, 2, 3), keepdim=True)
+    batch = {"image": image.contiguous(), "lung_mask": lungs.bool(), "em_mask": ess.bool(),
+             "cls_label": torch.full((1,), 2, device=device), "pse_label": torch.full((1,), 1, device=device)}
+    bands = (torch.tensor([[0.05, 0.1]], device=device), torch.tensor([[0.01, 0.05]], device=device))
+    w = torch.ones(1, device=device)
+    for _ in range(3):
+        step.step(batch, bands[0], bands[1], w, w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step.step(batch, bands[0], bands[1], w, w)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    flops = step.net.training_flops()
+    peak, _ = measured_peaks()
+    out = {"metric": "CT volumes/sec med3ddram training (fwd+bwd+Adam), batch 1, 1 GPU", "value": 1.0 / (ms * 1e-3),
+           "unit": "volumes/s", "ms_per_step": ms, "steps": steps, "dtype": "bf16 operands / f32 accumulate",
+           "loss": float(loss), "roofline_frac": flops / (ms * 1e-3) / 1e12 / peak,
+           "algorithmic_flops_per_step": flops, "full_line": "python bench.py --mode train (torchrun for N > 1)"}
+    del step, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -553,6 +592,8 @@ def main():
     ap.add_argument("--dims", default="", help="D,H,W (overrides --size), e.g. 400,512,512")
     ap.add_argument("--arch", default=ARCH, choices=sorted(ARCH_NAMES))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cudnn"])
+    ap.add_argument("--no-train-field", dest="train_field", action="store_false",
+                    help="skip the `training` field of the main line (config 5 at N=1, batch 1; ~15 s)")
     ap.add_argument("--no-yardstick", dest="yardstick", action="store_false",
                     help="skip the cuDNN yard-stick field of the main line (N=1 only; a few seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -787,6 +828,13 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:  # reported at N=1 only
         line["cpu_baseline"] = cpu_baseline(module, dims, args.arch)
+    if args.train_field and world == 1 and args.arch == ARCH:
+        try:
+            module.model._engines.clear()
+            torch.cuda.empty_cache()
+            line["training"] = training_field(device, dims, args.arch, steps=min(args.steps, 10))
+        except Exception as exc:  # never at the cost of the headline line
+            line["training"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if args.yardstick and world == 1:
         try:
             line["gpu_yardstick"] = cudnn_yardstick(module, dims, args.arch, B, device, steps=min(args.steps, 5))
