@@ -717,7 +717,8 @@ extern "C" int dram_conv3d_plan_executed_flops(const dram_conv_plan *plan, int64
   DRAM_REQUIRE(plan && flops, "dram_conv3d_plan_executed_flops: null argument");
   if (plan->kind == 1) {  // plane ring: every item issues 4 planes x 27 taps x all chunks, N = cout
     const SlabParams &sp = plan->sp;
-    *flops = 2LL * sp.items_total * 4 * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
+    const int group = plan->block_n == 128 ? 2 : 4;  // output planes per item (conv3d_slab.cu slab_group)
+    *flops = 2LL * sp.items_total * group * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
     return DRAM_OK;
   }
   const ConvKParams &p = plan->p;
