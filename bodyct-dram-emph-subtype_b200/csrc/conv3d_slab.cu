@@ -476,22 +476,36 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     for (int item = item_begin; item < item_end; ++item) {
       const SlabItem it = decode_item(p, item, Cfg::GROUP);
       const int oh = it.h0 + lh, ow = it.w0 + lw;
+      // residual rows are loaded one 32-channel group ahead (also across the planes of the item); the first one
+      // before the wait for the accumulator
+      auto res_ptr = [&](int t) {
+        const int od = it.q0 + t;
+        const bool valid = (od < p.D) && (oh < p.H) && (ow < p.W);
+        return residual_row(p.epi, valid, it.sample, od, oh, ow);
+      };
+      constexpr int GROUPS_PER_PLANE = BLOCK_N / 32;
+      ResGroup res = load_residual_group(p.epi, res_ptr(0), 0);
       mbar_wait(tmem_full(buf), buf_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int t = 0; t < SL_GROUP; ++t) {
         const int od = it.q0 + t;
         const bool valid = (od < p.D) && (oh < p.H) && (ow < p.W);
-        const uint16_t *res_row = residual_row(p.epi, valid, it.sample, od, oh, ow);
+        const uint16_t *res_row = res_ptr(t);
         const uint32_t taddr = tmem_base + (uint32_t)((buf * SL_GROUP + t) * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int gq = 0; gq < GROUPS_PER_PLANE; ++gq) {
+          const int c0 = gq * 32;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          ResGroup next;
+          if (gq + 1 < GROUPS_PER_PLANE) next = load_residual_group(p.epi, res_row, c0 + 32);
+          else next = load_residual_group(p.epi, t + 1 < SL_GROUP ? res_ptr(t + 1) : nullptr, 0);
           tmem_wait_ld();
 #ifndef DRAM_SLAB_EXPERIMENT_NO_EPILOGUE  // diagnostic builds only: results are wrong without it
-          if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res_row);
+          if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res);
 #endif
+          res = next;
         }
       }
       tcgen05_fence_before();
