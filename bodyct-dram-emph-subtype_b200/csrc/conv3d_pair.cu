@@ -184,12 +184,15 @@ conv3d_pair_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       mbar_wait(tmem_full_bar, acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(brick * P_BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+      ResGroup res = load_residual_group(p.epi, res_row, t.n0);
 #pragma unroll 1
       for (int c0 = 0; c0 < P_BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        const ResGroup next = load_residual_group(p.epi, c0 + 32 < P_BLOCK_N ? res_row : nullptr, t.n0 + c0 + 32);
         tmem_wait_ld();
-        if (valid) epilogue_group<false>(p.epi, v, t.n0 + c0, t.sample, od, oh, ow, res_row);
+        if (valid) epilogue_group<false>(p.epi, v, t.n0 + c0, t.sample, od, oh, ow, res);
+        res = next;
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty_bar);

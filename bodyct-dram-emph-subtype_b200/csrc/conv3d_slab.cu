@@ -32,7 +32,10 @@
 
 namespace dram {
 
-static constexpr int SL_W = 8, SL_H = 16, SL_GROUP = 4;      // slab = 8 x 16 voxels, 4 planes per item
+static constexpr int SL_W = 8, SL_H = 16;                    // slab = 8 x 16 voxels
+// Output planes per work item: 4 for Cout 32 / 64; 2 for Cout 128 (TMEM holds 2 x GROUP x Cout fp32 columns = 512, and
+// with two output planes a plane feeds at most two of them, so the kd-stacked N stays <= 256).
+__host__ __device__ constexpr int slab_group(int block_n) { return block_n == 128 ? 2 : 4; }
 static constexpr int PL_W = SL_W + 2, PL_H = SL_H + 2;       // input plane with halo
 static constexpr int PLANE_BYTES = PL_W * PL_H * 128;        // 23040
 static constexpr int PLANE_PITCH = 23 * 1024;                // slot pitch, 1 KiB aligned for SWIZZLE_128B
@@ -46,22 +49,24 @@ static constexpr int LP_BYTES = LP_W * LP_H * 128;           // 9856
 static constexpr int LP_PITCH = 10 * 1024;
 static constexpr int LP_RING = 3;
 static constexpr int UP_WARP0 = 7, UP_THREADS = 128;
-static constexpr int ITEM_PLANES = SL_GROUP + 2;             // 6 input planes feed 4 output planes
 static constexpr int SL_THREADS = 224;
 static constexpr int SL_A_WARP = 4, SL_MMA_WARP = 5, SL_B_WARP = 6;
 static constexpr int SL_BLOCK_K = 64;
 
 template <int BLOCK_N, bool UP = false>
 struct SlabCfg {
-  static constexpr int RING_ = UP ? RING_UP : RING;
+  static constexpr int GROUP = slab_group(BLOCK_N);
+  static constexpr int ITEM_PLANES = GROUP + 2;             // input planes that feed GROUP output planes
+  static constexpr int MAX_BLK = GROUP < 3 ? GROUP : 3;     // output planes one input plane feeds (kd stacked along N)
+  static constexpr int RING_ = UP ? RING_UP : (BLOCK_N == 128 ? 5 : RING);
   static constexpr int THREADS = UP ? SL_THREADS + UP_THREADS : SL_THREADS;
   static constexpr int B_BLOCK_BYTES = BLOCK_N * 128;       // one tap: Cout rows x 64 channels
   static constexpr int B_STAGE_BYTES = 3 * B_BLOCK_BYTES;   // [kd=2; kd=1; kd=0] of one (kh,kw)
 #ifndef DRAM_SLAB_BSTAGES64
 #define DRAM_SLAB_BSTAGES64 2
 #endif
-  static constexpr int B_STAGES = BLOCK_N == 64 ? DRAM_SLAB_BSTAGES64 : 4;
-  static constexpr int TMEM_COLS = 2 * SL_GROUP * BLOCK_N;  // 512 (N=64) / 256 (N=32)
+  static constexpr int B_STAGES = BLOCK_N == 64 ? DRAM_SLAB_BSTAGES64 : (BLOCK_N == 128 ? 2 : 4);
+  static constexpr int TMEM_COLS = 2 * GROUP * BLOCK_N;     // 512 (N = 64, 128) / 256 (N = 32)
   static constexpr int LP_TOTAL = UP ? LP_RING * LP_PITCH : 0;
   static constexpr int SMEM_BYTES = 1024 + RING_ * PLANE_PITCH + B_STAGES * B_STAGE_BYTES + LP_TOTAL + 256;
 };
@@ -69,11 +74,11 @@ struct SlabCfg {
 struct SlabItem {
   int sample, w0, h0, q0, g;
 };
-__device__ __forceinline__ SlabItem decode_item(const SlabParams &p, int item) {
+__device__ __forceinline__ SlabItem decode_item(const SlabParams &p, int item, int group) {
   SlabItem it;
   const int col = item / p.groups_d;
   it.g = item - col * p.groups_d;
-  it.q0 = it.g * SL_GROUP;
+  it.q0 = it.g * group;
   const int per_sample = p.cols_w * p.cols_h;
   it.sample = col / per_sample;
   const int r = col - it.sample * per_sample;
@@ -109,6 +114,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
   using Cfg = SlabCfg<BLOCK_N, UP>;
   constexpr int B_STAGES = Cfg::B_STAGES;
   constexpr int RING = Cfg::RING_;  // shadows the namespace constant
+  constexpr int SL_GROUP = Cfg::GROUP, ITEM_PLANES = Cfg::ITEM_PLANES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_base = smem_base + RING * PLANE_PITCH;
@@ -174,7 +180,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       unsigned seq_end = 0;
       unsigned lseq = 0;  // UP: running index of low-resolution planes through the LP ring
       for (int item = item_begin; item < item_end; ++item) {
-        const SlabItem it = decode_item(p, item);
+        const SlabItem it = decode_item(p, item, Cfg::GROUP);
         for (int c = 0; c < p.chunks_total; ++c) {
           const bool reuse = single_chunk && item > item_begin && it.g > 0;
           const unsigned seq_base = seq_end - (reuse ? 2u : 0u);
@@ -249,9 +255,9 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       // chunk (six 64-bit values, broadcast so that they live in uniform registers), the (kh, kw) / kd / K-step
       // offsets are compile-time constants of the fully unrolled loops, and a stage's 24 MMAs are issued from ONE
       // elected region: two 64-bit uniform adds per tcgen05.mma.
-      uint32_t idesc[3];
+      uint32_t idesc[Cfg::MAX_BLK];
 #pragma unroll
-      for (int nb = 0; nb < 3; ++nb) idesc[nb] = make_idesc_16bit(128, (nb + 1) * BLOCK_N, p.epi.is_f16);
+      for (int nb = 0; nb < Cfg::MAX_BLK; ++nb) idesc[nb] = make_idesc_16bit(128, (nb + 1) * BLOCK_N, p.epi.is_f16);
       const uint64_t desc_a_const = make_sw128_desc_sbo(0u, PL_W * 128, 0);
       const uint64_t desc_b_const = make_sw128_desc(0u);
       int stage = 0;
@@ -260,7 +266,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
       int buf = 0;
       uint32_t buf_phase = 0;
       for (int item = item_begin; item < item_end; ++item) {
-        const SlabItem it = decode_item(p, item);
+        const SlabItem it = decode_item(p, item, Cfg::GROUP);
         mbar_wait(tmem_empty(buf), buf_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t tmem_d0 = tmem_base + (uint32_t)(buf * SL_GROUP * BLOCK_N);
@@ -328,39 +334,23 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               __syncwarp();
             } else {
               if (elect_one_sync()) {
-                // Issue order inside a stage: plane by plane, the four K steps of a plane back to back (order 0).
-                // Tried and REJECTED (order 1, kept behind -DDRAM_SLAB_MMA_ORDER=1 for the record): K steps outermost
-                // and the planes visited as 0,4,1,5,2,3 so that neighbouring instructions write disjoint output tiles.
-                // It ran 2-3 % faster, but the results were no longer reproducible: the training test that feeds two
-                // bit-identical gradient tensors through two copies of the network got weight gradients that differed
-                // by up to 1 % of their largest entry (0 with order 0) — instructions whose accumulator column ranges
-                // overlap only PARTLY (plane j writes tiles {j-2..j}) do not appear to be ordered against each other
-                // once independent instructions sit between them.
-#ifndef DRAM_SLAB_MMA_ORDER
-#define DRAM_SLAB_MMA_ORDER 0
-#endif
-                constexpr int kOrder[2][ITEM_PLANES] = {{0, 1, 2, 3, 4, 5}, {0, 4, 1, 5, 2, 3}};
-#if DRAM_SLAB_MMA_ORDER == 0
+                // Issue order inside a stage: plane by plane, the four K steps of a plane back to back.  (Tried and
+                // REJECTED in round 2: K steps outermost with the planes visited as 0,4,1,5,2,3 so that neighbouring
+                // instructions write disjoint output tiles — 2-3 % faster, but results were no longer reproducible:
+                // two bit-identical gradient tensors pushed through two copies of the network gave weight gradients
+                // differing by up to 1 % (exactly 0 in order).  Instructions whose accumulator column ranges overlap
+                // only PARTLY are evidently not ordered against each other once independent ones sit between them.)
 #pragma unroll
-                for (int jj = 0; jj < ITEM_PLANES; ++jj) {
-                  const int j = kOrder[0][jj];
+                for (int j = 0; j < ITEM_PLANES; ++j) {
+                  // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
+                  const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+                  const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+                  const uint64_t da = da_plane[j] + row_off16;
+                  const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
+                  const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-#else
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                  for (int jj = 0; jj < ITEM_PLANES; ++jj) {
-                    const int j = kOrder[1][jj];
-#endif
-                    // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
-                    const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
-                    const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
-                    const uint64_t da = da_plane[j] + row_off16;
-                    const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
-                    const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
+                  for (int k = 0; k < 4; ++k)
                     umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
-                  }
                 }
                 // last stage of the chunk: hand the planes back (the commits track every MMA issued so far)
                 if (hw == 8) {
@@ -396,7 +386,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     const int is_f16 = p.epi.is_f16;
     unsigned seq_end = 0, lseq_base = 0;
     for (int item = item_begin; item < item_end; ++item) {
-      const SlabItem it = decode_item(p, item);
+      const SlabItem it = decode_item(p, item, Cfg::GROUP);
       for (int c = 0; c < p.chunks_total; ++c) {
         const unsigned seq_base = seq_end;  // UP layers have more than one chunk: no plane reuse across items
         seq_end = seq_base + ITEM_PLANES;
@@ -484,24 +474,38 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
     int buf = 0;
     uint32_t buf_phase = 0;
     for (int item = item_begin; item < item_end; ++item) {
-      const SlabItem it = decode_item(p, item);
+      const SlabItem it = decode_item(p, item, Cfg::GROUP);
       const int oh = it.h0 + lh, ow = it.w0 + lw;
+      // residual rows are loaded one 32-channel group ahead (also across the planes of the item); the first one
+      // before the wait for the accumulator
+      auto res_ptr = [&](int t) {
+        const int od = it.q0 + t;
+        const bool valid = (od < p.D) && (oh < p.H) && (ow < p.W);
+        return residual_row(p.epi, valid, it.sample, od, oh, ow);
+      };
+      constexpr int GROUPS_PER_PLANE = BLOCK_N / 32;
+      ResGroup res = load_residual_group(p.epi, res_ptr(0), 0);
       mbar_wait(tmem_full(buf), buf_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int t = 0; t < SL_GROUP; ++t) {
         const int od = it.q0 + t;
         const bool valid = (od < p.D) && (oh < p.H) && (ow < p.W);
-        const uint16_t *res_row = residual_row(p.epi, valid, it.sample, od, oh, ow);
+        const uint16_t *res_row = res_ptr(t);
         const uint32_t taddr = tmem_base + (uint32_t)((buf * SL_GROUP + t) * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        for (int gq = 0; gq < GROUPS_PER_PLANE; ++gq) {
+          const int c0 = gq * 32;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+          ResGroup next;
+          if (gq + 1 < GROUPS_PER_PLANE) next = load_residual_group(p.epi, res_row, c0 + 32);
+          else next = load_residual_group(p.epi, t + 1 < SL_GROUP ? res_ptr(t + 1) : nullptr, 0);
           tmem_wait_ld();
 #ifndef DRAM_SLAB_EXPERIMENT_NO_EPILOGUE  // diagnostic builds only: results are wrong without it
-          if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res_row);
+          if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, c0, it.sample, od, oh, ow, res);
 #endif
+          res = next;
         }
       }
       tcgen05_fence_before();
@@ -525,8 +529,14 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 // host
 // ----------------------------------------------------------------------------------------
 int slab_plan_supported(const dram_conv_desc *d) {
+  // Cout 128 (layer2 of the basic-block nets, the 3x3x3 of layer2's bottlenecks): two output planes per item; the
+  // per-tap tile kernel pulls 32 KiB of operands per 392 MMA clocks through L2 there and reached 31 % tensor-pipe
+  // utilisation (profiles/tensor_pipe_r2b.md).  DRAM_B200_SLAB128=0 keeps those layers on the tile kernel.
+  const char *k128 = getenv("DRAM_B200_SLAB128");
+  const bool allow128 = !(k128 && atoi(k128) == 0) && d->n_heads == 0;
   return d->kd == 3 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->dd == 1 &&
-         d->dh == 1 && d->dw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 && (d->cout == 32 || d->cout == 64);
+         d->dh == 1 && d->dw == 1 && d->pd == 1 && d->ph == 1 && d->pw == 1 &&
+         (d->cout == 32 || d->cout == 64 || (d->cout == 128 && allow128));
 }
 
 template <int BN, bool UP>
@@ -568,7 +578,8 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
   sp.n = d->n; sp.D = d->di; sp.H = d->hi; sp.W = d->wi;
   sp.cols_w = ceil_div(d->wi, SL_W);
   sp.cols_h = ceil_div(d->hi, SL_H);
-  sp.groups_d = ceil_div(d->di, SL_GROUP);
+  const int group = slab_group(d->cout);
+  sp.groups_d = ceil_div(d->di, group);
   const int64_t items = (int64_t)d->n * sp.cols_w * sp.cols_h * sp.groups_d;
   if (items > 0x7fffffffLL) {
     set_error("conv3d(planes): too many work items");
@@ -596,7 +607,7 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
   sp.epi = epi;
   pl->block_n = d->cout;
   pl->stages = sp.up2x ? RING_UP : RING;
-  pl->m_tiles = sp.items_total * SL_GROUP;
+  pl->m_tiles = sp.items_total * group;
   pl->n_tiles = 1;
   const int64_t ktot = 27LL * (d->c1 + d->c2);
   int rc;
@@ -620,6 +631,10 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
     } else if (d->cout == 64) {
       pl->smem_bytes = SlabCfg<64>::SMEM_BYTES;
       rc = slab_set_attr<64, false>();
+    } else if (d->cout == 128) {
+      pl->smem_bytes = SlabCfg<128>::SMEM_BYTES;
+      pl->stages = SlabCfg<128>::RING_;
+      rc = slab_set_attr<128, false>();
     } else {
       pl->smem_bytes = SlabCfg<32>::SMEM_BYTES;
       rc = slab_set_attr<32, false>();
@@ -638,6 +653,8 @@ int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
                                                                                           pl->map_w, sp);
   else if (pl->block_n == 64)
     conv3d_slab_kernel<64, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, sp);
+  else if (pl->block_n == 128)
+    conv3d_slab_kernel<128, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, sp);
   else
     conv3d_slab_kernel<32, false><<<grid, SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2, pl->map_w, sp);
   DRAM_CHECK_LAUNCH("conv3d_slab_kernel launch");

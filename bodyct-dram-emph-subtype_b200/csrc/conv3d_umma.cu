@@ -274,6 +274,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       const int od = t.d0 + ld, oh = t.h0 + lh, ow = t.w0 + lw;
       const bool valid = (od < p.Do) && (oh < p.Ho) && (ow < p.Wo);
       const uint16_t *res_row = residual_row(p.epi, valid, t.sample, od, oh, ow);
+      ResGroup res = load_residual_group(p.epi, res_row, t.n0);  // in flight while this warp waits for the accumulator
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(warp * 32) << 16);
@@ -281,8 +282,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
+        const ResGroup next = load_residual_group(p.epi, c0 + 32 < BLOCK_N ? res_row : nullptr, t.n0 + c0 + 32);
         tmem_wait_ld();
-        if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, t.n0 + c0, t.sample, od, oh, ow, res_row);
+        if (valid) epilogue_group<BLOCK_N == 32>(p.epi, v, t.n0 + c0, t.sample, od, oh, ow, res);
+        res = next;
       }
       tcgen05_fence_before();
       mbar_arrive(tmem_empty_bar(acc));  // 128 arrivals hand the accumulator back to the issuer
@@ -717,7 +720,8 @@ extern "C" int dram_conv3d_plan_executed_flops(const dram_conv_plan *plan, int64
   DRAM_REQUIRE(plan && flops, "dram_conv3d_plan_executed_flops: null argument");
   if (plan->kind == 1) {  // plane ring: every item issues 4 planes x 27 taps x all chunks, N = cout
     const SlabParams &sp = plan->sp;
-    *flops = 2LL * sp.items_total * 4 * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
+    const int group = plan->block_n == 128 ? 2 : 4;  // output planes per item (conv3d_slab.cu slab_group)
+    *flops = 2LL * sp.items_total * group * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
     return DRAM_OK;
   }
   const ConvKParams &p = plan->p;

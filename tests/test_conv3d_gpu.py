@@ -170,6 +170,11 @@ PLANE_CASES = [
     (1, (9, 18, 10), 64, 64, 64, {}),
     (1, (8, 16, 16), 64, 0, 32, {"heads": ((1, 1), True)}),           # us3 + regression heads
     (2, (6, 16, 24), 64, 0, 32, {"heads": ((6, 3), False), "max_ctas": 2}),
+    (1, (8, 16, 16), 128, 0, 128, {}),                                # layer2: Cout 128, two output planes per item
+    (2, (9, 18, 20), 128, 0, 128, {"residual": 128}),                 # ragged groups (odd D), residual
+    (1, (12, 32, 16), 128, 0, 128, {"max_ctas": 2, "residual": 128}), # several items per CTA
+    (1, (7, 16, 8), 64, 0, 128, {"max_ctas": 1}),                     # one chunk: plane reuse between items of a column
+    (1, (6, 10, 12), 128, 64, 128, {}),                               # two sources
 ]
 
 
@@ -189,7 +194,9 @@ def test_conv_algo_dispatch(cuda, lib):
     assert p.algo == "tiles"
     p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 2)                 # dilation 2 -> tiles
     assert p.algo == "tiles"
-    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 128, 3, 1, 1)                # cout 128 -> tiles
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 128, 3, 1, 1)                # cout 128 -> planes (two planes per item)
+    assert p.algo == "planes"
+    p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 256, 3, 1, 1)                # cout 256 -> tiles
     assert p.algo == "tiles"
 
 
@@ -480,6 +487,7 @@ def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
 
 
 @pytest.mark.parametrize("c1,c2,cout,k,dil,dims", [(64, 0, 64, 3, 1, (24, 64, 64)), (64, 64, 64, 3, 1, (16, 48, 64)),
+                                                   (128, 0, 128, 3, 1, (32, 32, 32)),
                                                    (64, 0, 32, 3, 1, (24, 64, 64)), (128, 0, 256, 3, 2, (16, 16, 16)),
                                                    (256, 0, 128, 1, 1, (16, 16, 32))])
 def test_convolutions_are_reproducible_bit_for_bit(cuda, lib, c1, c2, cout, k, dil, dims):

@@ -49,7 +49,8 @@ def test_convolution_kernels_stay_inside_their_output(cuda, lib, dt):
     _conv(cuda, (5, 9, 11), 64, 64, dt=dt)                      # plane ring, ragged slabs
     _conv(cuda, (7, 17, 9), 64, 32, dt=dt)                      # plane ring N = 32 (output stored)
     _conv(cuda, (6, 10, 14), 64, 64, c2=64, res=True, dt=dt)    # two sources + residual
-    _conv(cuda, (5, 7, 9), 128, 128, dt=dt)                     # tiles N = 128, partial tiles
+    _conv(cuda, (5, 7, 9), 128, 128, dt=dt)                     # plane ring N = 128 (two planes per item), ragged
+    _conv(cuda, (5, 7, 9), 128, 128, dil=2, dt=dt)              # tiles N = 128, partial tiles
     _conv(cuda, (9, 7, 5), 64, 128, stride=2, dt=dt)            # stride 2
     _conv(cuda, (6, 6, 10), 128, 256, dil=2, dt=dt)             # N = 256, dilation (tap skipping)
     _conv(cuda, (5, 6, 7), 256, 512, dil=4, res=True, dt=dt, n=2)
