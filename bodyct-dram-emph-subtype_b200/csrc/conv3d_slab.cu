@@ -334,23 +334,40 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
               __syncwarp();
             } else {
               if (elect_one_sync()) {
-                // Issue order inside a stage: plane by plane, the four K steps of a plane back to back.  (Tried and
-                // REJECTED in round 2: K steps outermost with the planes visited as 0,4,1,5,2,3 so that neighbouring
-                // instructions write disjoint output tiles — 2-3 % faster, but results were no longer reproducible:
-                // two bit-identical gradient tensors pushed through two copies of the network gave weight gradients
-                // differing by up to 1 % (exactly 0 in order).  Instructions whose accumulator column ranges overlap
-                // only PARTLY are evidently not ordered against each other once independent ones sit between them.)
+                // Issue order inside a stage (-DDRAM_SLAB_MMA_ORDER): 0 = plane by plane, the four K steps of a plane
+                // back to back; 1 (default) = K steps outermost and the planes visited so that neighbouring
+                // instructions write disjoint output tiles where possible (GROUP 4: plane j feeds tiles {j-2..j} & [0,3],
+                // order 0,4,1,5,2,3 leaves only 2 -> 3 sharing columns; GROUP 2: 0,3,1,2).  Measured 2-3 % faster on the
+                // 64-channel layers (profiles/convbench_order_r2e.log): back-to-back instructions on the same
+                // accumulator columns serialise a little.  tcgen05.mma instructions of one thread execute in issue
+                // order, so the accumulation order per output element is still fixed: results are reproducible bit for
+                // bit (tests/test_conv3d_gpu.py::test_convolutions_are_reproducible_bit_for_bit, tools/train_repro_check.py)
+                // — they differ from order 0 only in the last bits of the fp32 sums.
+#ifndef DRAM_SLAB_MMA_ORDER
+#define DRAM_SLAB_MMA_ORDER 1
+#endif
+                constexpr int kOrder4[6] = {0, 4, 1, 5, 2, 3};
+                constexpr int kOrder2[4] = {0, 3, 1, 2};
+#if DRAM_SLAB_MMA_ORDER == 0
 #pragma unroll
                 for (int j = 0; j < ITEM_PLANES; ++j) {
-                  // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
-                  const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
-                  const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
-                  const uint64_t da = da_plane[j] + row_off16;
-                  const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
-                  const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
+                  for (int k = 0; k < 4; ++k) {
+#else
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                  for (int jj = 0; jj < ITEM_PLANES; ++jj) {
+                    const int j = SL_GROUP == 4 ? kOrder4[jj < 6 ? jj : 0] : kOrder2[jj < 4 ? jj : 0];
+#endif
+                    // input plane j feeds output tiles t = j - kd, kd = kd_hi .. kd_lo (descending kd = ascending t)
+                    const int kd_hi = j < 2 ? j : 2, kd_lo = j > SL_GROUP - 1 ? j - (SL_GROUP - 1) : 0;
+                    const int nblk = kd_hi - kd_lo + 1, t_min = j - kd_hi;
+                    const uint64_t da = da_plane[j] + row_off16;
+                    const uint64_t db = db_stage + (uint64_t)(((2 - kd_hi) * Cfg::B_BLOCK_BYTES) >> 4);
+                    const uint32_t dcol = tmem_d0 + (uint32_t)(t_min * BLOCK_N);
                     umma_bf16(dcol, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc[nblk - 1], 1u);
+                  }
                 }
                 // last stage of the chunk: hand the planes back (the commits track every MMA issued so far)
                 if (hw == 8) {
