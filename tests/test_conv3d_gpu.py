@@ -491,9 +491,9 @@ def test_commuted_upsampled_conv_equals_direct(cuda, lib, lo_dims, c_up, n, dt):
                                                    (64, 0, 32, 3, 1, (24, 64, 64)), (128, 0, 256, 3, 2, (16, 16, 16)),
                                                    (256, 0, 128, 1, 1, (16, 16, 32))])
 def test_convolutions_are_reproducible_bit_for_bit(cuda, lib, c1, c2, cout, k, dil, dims):
-    """Same buffers, same plan, six launches: identical bits.  (Round 2 tried an MMA issue order in the plane-ring
-    kernel that interleaved instructions with partially overlapping accumulator ranges; it was faster and NOT
-    reproducible — this is the test that guards the in-order issue, on shapes large enough to keep every SM busy.)"""
+    """Same buffers, same plan, six launches: identical bits — on shapes large enough to keep every SM busy.  Guards the
+    issue order of the plane-ring kernel (K steps outermost, planes interleaved: instructions with partially overlapping
+    accumulator ranges in flight) and every other ordering assumption of the convolution kernels."""
     from dram_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(41)
