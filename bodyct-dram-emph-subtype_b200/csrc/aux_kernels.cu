@@ -589,10 +589,13 @@ dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__
                                const uint8_t *__restrict__ ess, const uint8_t *__restrict__ lungs,
                                float *__restrict__ out0, float *__restrict__ out1, double *__restrict__ sums, int n,
                                int d, int h, int w, int D, int H, int W, float sd, float sh, float sw, int nr_max) {
-  extern __shared__ float k7_smem[];  // [map 2][plane 2][nr_max][w]
+  extern __shared__ __align__(128) float k7_smem[];  // [2 maps][4096] output staging, then [map 2][plane 2][nr_max][w]
   __shared__ double scratch[32];
   __shared__ unsigned lung_part[8];
   constexpr int SX = 1 << LOG_SX, RY = 256 >> LOG_SX;
+  constexpr int SLICE = 256 * K7_SEG;                // RY rows x W voxels = 4096 floats = 16 KiB per map
+  float *stage = k7_smem;
+  float *brick = k7_smem + 2 * SLICE;
   const int sx = threadIdx.x & (SX - 1), ry = threadIdx.x >> LOG_SX;
   const int b = blockIdx.z, xd = blockIdx.y, xh0 = blockIdx.x * RY;
   const int xh = xh0 + ry;
@@ -626,12 +629,12 @@ dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__
       q /= nr;
       const int pl = q & 1, mp = q >> 1;
       const float *src = (mp ? s1 : s0) + ((int64_t)(pl ? id.i1 : id.i0) * h + ih_lo + r) * w;
-      reinterpret_cast<float4 *>(k7_smem + (mp * 2 + pl) * plane_stride + r * w)[c] = __ldg(reinterpret_cast<const float4 *>(src) + c);
+      reinterpret_cast<float4 *>(brick + (mp * 2 + pl) * plane_stride + r * w)[c] = __ldg(reinterpret_cast<const float4 *>(src) + c);
     }
     __syncthreads();
     if (mine) {
       const LinIdx ih = lin_index_ac(xh, sh, h);
-      const float *p00 = k7_smem + (ih.i0 - ih_lo) * w, *p01 = k7_smem + (ih.i1 - ih_lo) * w;
+      const float *p00 = brick + (ih.i0 - ih_lo) * w, *p01 = brick + (ih.i1 - ih_lo) * w;
       const float *p10 = p00 + plane_stride, *p11 = p01 + plane_stride;
       const float *q00 = p00 + 2 * plane_stride, *q01 = p01 + 2 * plane_stride;
       const float *q10 = p10 + 2 * plane_stride, *q11 = p11 + 2 * plane_stride;
@@ -657,23 +660,29 @@ dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__
       }
     }
   }
-  if (!need) {
-    // no `ess` voxel in this slice (~90 % of the CTAs of a chest volume): the slice's RY rows are one contiguous run of
-    // RY * W floats per map — fill it with fully coalesced 16-byte stores (lane-consecutive addresses: 4 L1 wavefronts
-    // per instruction instead of the 16 of the per-segment layout below)
-    const int rows = min(RY, H - xh0);
-    const int64_t slice = (int64_t)b * vol + ((int64_t)xd * H + xh0) * W;
-    const int n4 = rows * (W >> 2);
-    const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    for (int t = threadIdx.x; t < n4; t += 256) {
-      __stcs(reinterpret_cast<float4 *>(out0 + slice) + t, z4);
-      __stcs(reinterpret_cast<float4 *>(out1 + slice) + t, z4);
-    }
-  } else if (row_ok) {
+  // Output: the slice's rows are ONE contiguous run of rows * W floats per map.  It leaves through the bulk-copy engine
+  // (cp.async.bulk shared -> global, one instruction per map issued by one thread) instead of per-lane stores: st.global
+  // streams topped out near 2 TB/s in this library's write-heavy kernels, TMA stores reach 4.7 (K4).  Slices without an
+  // `ess` voxel (~90 % of a chest volume) send the same zeroed 16 KiB tile to both maps.
+  {
+    float4 *mine0 = reinterpret_cast<float4 *>(stage + threadIdx.x * K7_SEG);
+    float4 *mine1 = reinterpret_cast<float4 *>(stage + SLICE + threadIdx.x * K7_SEG);  // thread (sx, ry) = ry * SX + sx
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      __stcs(reinterpret_cast<float4 *>(out0 + o) + q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
-      __stcs(reinterpret_cast<float4 *>(out1 + o) + q, make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
+      mine0[q] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+      if (need) mine1[q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int rows = min(RY, H - xh0);
+      const int64_t slice = (int64_t)b * vol + ((int64_t)xd * H + xh0) * W;
+      const uint32_t bytes = (uint32_t)rows * (uint32_t)W * 4u;
+      const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(stage);
+      const uint32_t s1 = need ? s0 + SLICE * 4u : s0;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out0 + slice), "r"(s0), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out1 + slice), "r"(s1), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
   // lung count: integer warp reductions, one atomic per CTA; map sums only where the CTA met `ess`
@@ -692,6 +701,7 @@ dram_upsample_mask_lean_kernel(const float *__restrict__ dense0, const float *__
     acc1 = block_sum(acc1, scratch);
     if (threadIdx.x == 0) atomicAdd(&sums[n + b], acc1);
   }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tiles are read before the CTA leaves
 }
 __global__ void dram_finalize_kernel(const double *__restrict__ sums, float *__restrict__ pct, int n,
                                      int per_sample) {
@@ -1022,7 +1032,7 @@ extern "C" int dram_dram_upsample_mask(const float *dense0, const float *dense1,
   if (lean_env && log_sx >= 0 && aligned16 && D <= 65535 && n <= 65535) {
     const int RY = 256 >> log_sx;
     const int nr_lean = (int)ceilf((float)RY * sh) + 2 < h ? (int)ceilf((float)RY * sh) + 2 : h;
-    const size_t smem_lean = (size_t)4 * nr_lean * w * sizeof(float);
+    const size_t smem_lean = (size_t)(2 * 256 * K7_SEG + 4 * nr_lean * w) * sizeof(float);  // 2 output tiles + the brick
     if (smem_lean <= 160 * 1024) {
       dim3 grid(ceil_div(H, RY), D, n);
 #define DRAM_K7_LEAN(LS)                                                                                                  \
