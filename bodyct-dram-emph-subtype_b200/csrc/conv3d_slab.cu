@@ -28,6 +28,8 @@
 // Roles (224 threads; UP: 352): warps 0-3 epilogue, warp 4 lane 0 plane producer, warp 5 MMA issuer (owns TMEM),
 // warp 6 lane 0 weight producer, UP: warps 7-10 interpolate.  Work items = (column, group of 4 planes); every CTA takes a
 // contiguous range of items (D fastest), so consecutive groups of a column reuse two resident planes.
+#include <string.h>
+
 #include "conv_plan.h"
 
 namespace dram {
@@ -543,6 +545,212 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_cons
 }
 
 // ----------------------------------------------------------------------------------------
+// Streaming variant for Cin 64 -> Cout 32 (us3, med3d.py:90): the 27 taps (108 KiB) stay RESIDENT in shared memory,
+// so nothing forces work items of a few planes.  The CTA walks a column plane by plane; input plane z feeds output
+// planes z-1, z, z+1 through kd = 2, 1, 0, whose accumulators are adjacent 32-column blocks of a 16-block TMEM ring —
+// EVERY interior MMA is the full kd stack (N = 96), against an average of N = 64 over the 6 planes of a 4-plane item,
+// and a plane is fetched once instead of 6/4 times.  The issue rate is what bounds this layer (each tcgen05.mma costs
+// ~34 clk + max(N/2, (128+N)/4)): 37 MMAs of ~90 clk per output plane instead of 54 of ~82.
+//
+// Work = contiguous ranges of (column, output plane) steps, D fastest; a CTA's range is cut into segments, one per
+// column it touches: output planes [t0, t1) <- input planes max(t0-1, 0) .. min(t1, D-1).  Roles as above (warps 0-3
+// epilogue, 4 planes, 5 MMA, 6 loads the weights once).
+// ----------------------------------------------------------------------------------------
+struct StreamCfg {
+  static constexpr int RING_ = 5;                            // plane slots
+  static constexpr int W_HW_BYTES = 3 * 32 * 128;            // [kd=2; kd=1; kd=0] of one (kh,kw): 96 rows x 64 channels
+  static constexpr int W_BYTES = 9 * W_HW_BYTES;             // 110592
+  static constexpr int TMEM_BLOCKS = 16, TMEM_COLS = 512;    // ring of 32-column accumulators
+  static constexpr int SMEM_BYTES = 1024 + RING_ * PLANE_PITCH + W_BYTES + 512;
+};
+
+struct StreamSeg {
+  int sample, w0, h0, t0, t1;
+};
+__device__ __forceinline__ StreamSeg stream_segment(const SlabParams &p, int step, int step_end) {
+  StreamSeg s;
+  const int col = step / p.D;
+  s.t0 = step - col * p.D;
+  const int left = step_end - step;
+  s.t1 = s.t0 + left < p.D ? s.t0 + left : p.D;
+  const int per_sample = p.cols_w * p.cols_h;
+  s.sample = col / per_sample;
+  const int r = col - s.sample * per_sample;
+  const int ih = r / p.cols_w;
+  s.w0 = (r - ih * p.cols_w) * SL_W;
+  s.h0 = ih * SL_H;
+  return s;
+}
+
+__global__ void __launch_bounds__(SL_THREADS, 1)
+conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ SlabParams p) {
+  constexpr int RING = StreamCfg::RING_;
+  constexpr int NBLK = StreamCfg::TMEM_BLOCKS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base + RING * PLANE_PITCH;
+  const uint32_t bar_base = w_base + StreamCfg::W_BYTES;
+  auto plane_addr = [&](int s) { return smem_base + (uint32_t)s * PLANE_PITCH; };
+  auto plane_full = [&](int s) { return bar_base + 8u * s; };
+  auto plane_empty = [&](int s) { return bar_base + 8u * (RING + s); };
+  const uint32_t w_full = bar_base + 8u * (2 * RING);
+  auto tmem_full = [&](unsigned b) { return bar_base + 8u * (2 * RING + 1 + b); };
+  auto tmem_empty = [&](unsigned b) { return bar_base + 8u * (2 * RING + 1 + NBLK + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * RING + 1 + 2 * NBLK);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) {
+      mbar_init(plane_full(s), 1);
+      mbar_init(plane_empty(s), 1);
+    }
+    mbar_init(w_full, 1);
+    for (int b = 0; b < NBLK; ++b) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == SL_MMA_WARP) tmem_alloc(tmem_slot, StreamCfg::TMEM_COLS);
+  if (warp == SL_A_WARP && lane == 0) prefetch_tensormap(&map_a);
+  if (warp == SL_B_WARP && lane == 0) prefetch_tensormap(&map_w);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int step_begin = (int)(((long long)blockIdx.x * p.steps_total) / gridDim.x);
+  const int step_end = (int)(((long long)(blockIdx.x + 1) * p.steps_total) / gridDim.x);
+
+  if (warp == SL_B_WARP) {
+    if (lane == 0) {  // the whole filter, once: 27 boxes of 32 rows x 64 channels
+      mbar_expect_tx(w_full, StreamCfg::W_BYTES);
+      for (int hw = 0; hw < 9; ++hw)
+        for (int blk = 0; blk < 3; ++blk)
+          tma_load_2d(w_base + (uint32_t)(hw * StreamCfg::W_HW_BYTES + blk * 32 * 128), &map_w, w_full,
+                      ((2 - blk) * 9 + hw) * SL_BLOCK_K, 0);
+    }
+    __syncwarp();
+  } else if (warp == SL_A_WARP) {
+    if (lane == 0) {
+      unsigned pseq = 0;
+      for (int step = step_begin; step < step_end;) {
+        const StreamSeg sg = stream_segment(p, step, step_end);
+        const int z_first = sg.t0 > 0 ? sg.t0 - 1 : 0, z_last = sg.t1 < p.D ? sg.t1 : p.D - 1;
+        for (int z = z_first; z <= z_last; ++z, ++pseq) {
+          const int slot = pseq % RING;
+          mbar_wait(plane_empty(slot), ((pseq / RING) & 1u) ^ 1u);
+          mbar_expect_tx(plane_full(slot), PLANE_BYTES);
+          tma_load_5d(plane_addr(slot), &map_a, plane_full(slot), 0, sg.w0 - 1, sg.h0 - 1, z, sg.sample);
+        }
+        step += sg.t1 - sg.t0;
+      }
+    }
+    __syncwarp();
+  } else if (warp == SL_MMA_WARP) {
+    const uint32_t idesc1 = make_idesc_16bit(128, 32, p.epi.is_f16), idesc2 = make_idesc_16bit(128, 64, p.epi.is_f16),
+                   idesc3 = make_idesc_16bit(128, 96, p.epi.is_f16);
+    auto idesc_of = [&](int n) { return n == 1 ? idesc1 : (n == 2 ? idesc2 : idesc3); };
+    const uint64_t desc_a_const = make_sw128_desc_sbo(0u, PL_W * 128, 0);
+    mbar_wait(w_full, 0u);
+    tcgen05_fence_after();
+    uint32_t wb = __shfl_sync(0xffffffffu, w_base, 0);
+    const uint64_t db_base = make_sw128_desc(0u) | (uint64_t)((wb & 0x3FFFFu) >> 4);
+    unsigned pseq = 0, oseq0 = 0;
+    for (int step = step_begin; step < step_end;) {
+      const StreamSeg sg = stream_segment(p, step, step_end);
+      const int z_first = sg.t0 > 0 ? sg.t0 - 1 : 0, z_last = sg.t1 < p.D ? sg.t1 : p.D - 1;
+      for (int z = z_first; z <= z_last; ++z, ++pseq) {
+        // output planes this input plane feeds: t = z-1 (kd 2), z (kd 1), z+1 (kd 0), clipped to the segment
+        const int lo = z - 1 > sg.t0 ? z - 1 : sg.t0, hi = z + 1 < sg.t1 - 1 ? z + 1 : sg.t1 - 1;
+        const int nblk = hi - lo + 1;
+        // accumulator blocks touched for the first time by this plane have to be drained by the epilogue
+        for (int t = (z == z_first ? lo : z + 1); t <= hi; ++t) {
+          const unsigned o = oseq0 + (unsigned)(t - sg.t0);
+          mbar_wait(tmem_empty(o % NBLK), ((o / NBLK) & 1u) ^ 1u);
+        }
+        const int slot = pseq % RING;
+        mbar_wait(plane_full(slot), (pseq / RING) & 1u);
+        tcgen05_fence_after();
+        uint32_t pa = plane_addr(slot);
+        pa = __shfl_sync(0xffffffffu, pa, 0);
+        const uint64_t da_plane = desc_a_const | (uint64_t)((pa & 0x3FFFFu) >> 4);
+        const unsigned b_lo = (oseq0 + (unsigned)(lo - sg.t0)) % NBLK;
+        const int n1 = nblk < (int)(NBLK - b_lo) ? nblk : (int)(NBLK - b_lo), n2 = nblk - n1;  // ring wrap: two runs
+        const int bblk = lo - z + 1;  // weight block (0 = kd 2) of the first output plane
+        const uint32_t d1 = tmem_base + b_lo * 32u, d2 = tmem_base;
+        const uint64_t db1 = db_base + (uint64_t)((bblk * 32 * 128) >> 4), db2 = db1 + (uint64_t)((n1 * 32 * 128) >> 4);
+        const uint32_t id1 = idesc_of(n1), id2 = idesc_of(n2 > 0 ? n2 : 1);
+        const bool fresh_all = z == z_first;
+        if (elect_one_sync()) {
+          // (kh,kw) = (0,0), K step 0, block by block: a block's first MMA overwrites, the others accumulate
+          for (int q = 0; q < nblk; ++q) {
+            const int t = lo + q;
+            const unsigned bq = (b_lo + (unsigned)q) % NBLK;
+            umma_bf16(tmem_base + bq * 32u, da_plane, db1 + (uint64_t)((q * 32 * 128) >> 4), idesc1,
+                      (fresh_all || t == z + 1) ? 0u : 1u);
+          }
+#pragma unroll
+          for (int hw = 0; hw < 9; ++hw) {
+            const int kh = hw / 3, kw = hw - 3 * kh;
+            const uint32_t row_off16 = (uint32_t)((kh * PL_W + kw) * 128) >> 4;
+            const uint32_t w_off16 = (uint32_t)(hw * StreamCfg::W_HW_BYTES) >> 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (hw == 0 && k == 0) continue;
+              umma_bf16(d1, da_plane + (uint64_t)(row_off16 + 2 * k), db1 + (uint64_t)(w_off16 + 2 * k), id1, 1u);
+              if (n2 > 0)
+                umma_bf16(d2, da_plane + (uint64_t)(row_off16 + 2 * k), db2 + (uint64_t)(w_off16 + 2 * k), id2, 1u);
+            }
+          }
+          umma_commit(plane_empty(slot));
+          if (z - 1 >= sg.t0) umma_commit(tmem_full((oseq0 + (unsigned)(z - 1 - sg.t0)) % NBLK));
+          if (z == p.D - 1 && sg.t1 == p.D) umma_commit(tmem_full((oseq0 + (unsigned)(z - sg.t0)) % NBLK));
+        }
+        __syncwarp();
+      }
+      oseq0 += (unsigned)(sg.t1 - sg.t0);
+      step += sg.t1 - sg.t0;
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const int lw = row & (SL_W - 1), lh = row >> 3;
+    unsigned oseq = 0;
+    for (int step = step_begin; step < step_end;) {
+      const StreamSeg sg = stream_segment(p, step, step_end);
+      const int oh = sg.h0 + lh, ow = sg.w0 + lw;
+      const bool valid = oh < p.H && ow < p.W;
+#pragma unroll 1
+      for (int t = sg.t0; t < sg.t1; ++t, ++oseq) {
+        const unsigned blk = oseq % NBLK;
+        const ResGroup res = load_residual_group(p.epi, residual_row(p.epi, valid, sg.sample, t, oh, ow), 0);
+        mbar_wait(tmem_full(blk), (oseq / NBLK) & 1u);
+        tcgen05_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + blk * 32u + ((uint32_t)(warp * 32) << 16), v);
+        tmem_wait_ld();
+        tcgen05_fence_before();
+        mbar_arrive(tmem_empty(blk));  // the block's values are in registers: hand it back before the arithmetic
+        if (valid) epilogue_group<true>(p.epi, v, 0, sg.sample, t, oh, ow, res);
+      }
+      step += sg.t1 - sg.t0;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == SL_MMA_WARP) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, StreamCfg::TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
 // host
 // ----------------------------------------------------------------------------------------
 int slab_plan_supported(const dram_conv_desc *d) {
@@ -622,9 +830,18 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
     }
   }
   sp.epi = epi;
+  // Cin 64 -> Cout 32 with one source (us3): weights-resident streaming kernel; DRAM_B200_US3=ring keeps the items
+  const char *us3 = getenv("DRAM_B200_US3");
+  sp.stream = (d->cout == 32 && sp.chunks_total == 1 && !sp.up2x && !(us3 && strcmp(us3, "ring") == 0)) ? 1 : 0;
+  const int64_t steps = (int64_t)d->n * sp.cols_w * sp.cols_h * d->di;
+  if (steps > 0x7fffffffLL) {
+    set_error("conv3d(planes): too many plane steps");
+    return DRAM_E_ARG;
+  }
+  sp.steps_total = (int)steps;
   pl->block_n = d->cout;
   pl->stages = sp.up2x ? RING_UP : RING;
-  pl->m_tiles = sp.items_total * group;
+  pl->m_tiles = sp.stream ? sp.steps_total : sp.items_total * group;
   pl->n_tiles = 1;
   const int64_t ktot = 27LL * (d->c1 + d->c2);
   int rc;
@@ -652,6 +869,12 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
       pl->smem_bytes = SlabCfg<128>::SMEM_BYTES;
       pl->stages = SlabCfg<128>::RING_;
       rc = slab_set_attr<128, false>();
+    } else if (sp.stream) {
+      pl->smem_bytes = StreamCfg::SMEM_BYTES;
+      pl->stages = StreamCfg::RING_;
+      rc = check_cuda(cudaFuncSetAttribute(conv3d_stream32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           StreamCfg::SMEM_BYTES),
+                      "cudaFuncSetAttribute(conv3d_stream32_kernel)");
     } else {
       pl->smem_bytes = SlabCfg<32>::SMEM_BYTES;
       rc = slab_set_attr<32, false>();
@@ -661,10 +884,16 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
 }
 
 int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
-  if (pl->sp.items_total < ctas) ctas = pl->sp.items_total;
-  dim3 grid(ctas);
   SlabParams sp = pl->sp;
   sp.epi = with_sat_counter(sp.epi);
+  if (sp.stream) {
+    if (sp.steps_total < ctas) ctas = sp.steps_total;
+    conv3d_stream32_kernel<<<dim3(ctas), SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_w, sp);
+    DRAM_CHECK_LAUNCH("conv3d_stream32_kernel launch");
+    return DRAM_OK;
+  }
+  if (pl->sp.items_total < ctas) ctas = pl->sp.items_total;
+  dim3 grid(ctas);
   if (sp.up2x)
     conv3d_slab_kernel<64, true><<<grid, SlabCfg<64, true>::THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_a2,
                                                                                           pl->map_w, sp);

@@ -720,6 +720,11 @@ extern "C" int dram_conv3d_plan_executed_flops(const dram_conv_plan *plan, int64
   DRAM_REQUIRE(plan && flops, "dram_conv3d_plan_executed_flops: null argument");
   if (plan->kind == 1) {  // plane ring: every item issues 4 planes x 27 taps x all chunks, N = cout
     const SlabParams &sp = plan->sp;
+    if (sp.stream) {  // every (output plane, kd) pair inside the volume is one N = 32 block of 9 x 4 MMAs; no D padding
+      const int64_t cols = (int64_t)sp.n * sp.cols_w * sp.cols_h;
+      *flops = 2LL * cols * (3LL * sp.D - 2) * 128 * 32 * 9 * 64;
+      return DRAM_OK;
+    }
     const int group = plan->block_n == 128 ? 2 : 4;  // output planes per item (conv3d_slab.cu slab_group)
     *flops = 2LL * sp.items_total * group * 128 * (int64_t)plan->block_n * 27 * sp.chunks_total * 64;
     return DRAM_OK;

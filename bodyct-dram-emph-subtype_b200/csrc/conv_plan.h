@@ -54,6 +54,9 @@ struct SlabParams {
   int up2x;                    // 0 / 1
   int Dl, Hl, Wl;              // low-resolution dims (D/2, H/2, W/2)
   float up_sd, up_sh, up_sw;   // ATen source scales (Dl-1)/(D-1) ...
+  // weights-resident streaming kernel (Cin 64 -> Cout 32): work = (column, output plane) steps
+  int stream;                  // 0 / 1
+  int steps_total;             // n * cols_w * cols_h * D
   EpiParams epi;
 };
 

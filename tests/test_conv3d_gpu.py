@@ -187,6 +187,44 @@ def test_conv_plane_ring_kernel(cuda, lib, case, dt):
               normalize=(case % 2 == 0), **kw)
 
 
+STREAM_CASES = [
+    # n, dims, kwargs: Cin 64 -> Cout 32, one source = the weights-resident streaming kernel (us3)
+    (1, (40, 16, 8), {"max_ctas": 1}),                                 # one CTA, one column: the 16-block TMEM ring wraps twice
+    (1, (40, 16, 16), {"max_ctas": 3, "heads": ((1, 1), True)}),       # columns cut mid-way: halo planes at both cuts
+    (2, (21, 20, 12), {"max_ctas": 5, "heads": ((6, 3), False)}),      # ragged H / W, odd D, two samples
+    (1, (1, 16, 8), {}),                                               # D = 1: the only plane is first and last
+    (1, (2, 16, 8), {"max_ctas": 2}),                                  # one output plane per CTA
+    (1, (19, 32, 24), {"residual": 32}),                               # residual rows, 148 > steps / few steps per CTA
+    (2, (33, 16, 8), {"max_ctas": 7, "residual": 32, "heads": ((1, 1), True)}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(STREAM_CASES)))
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_conv_streaming_kernel(cuda, lib, case, dt):
+    """us3 (med3d.py:90): planes stream past resident weights; every way a CTA's range can cut a column."""
+    n, dims, kw = STREAM_CASES[case]
+    _run_conv(cuda, n, dims, 64, 0, 32, 3, 1, 1, dtype=dt, algo="planes", expect_algo="planes", seed=140 + case,
+              normalize=(case % 2 == 1), **kw)
+
+
+def test_conv_streaming_equals_plane_items(cuda, lib, monkeypatch):
+    """DRAM_B200_US3=ring keeps the 4-plane work items for Cout 32: same operands, same fp32 sums up to their order."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(151)
+    x = ops.to_ndhwc_16(_rand((1, 64, 24, 32, 16), g, dtype=torch.float16).to(cuda), torch.float16)
+    wp = ops.pack_conv_weight(_rand((32, 64, 3, 3, 3), g, scale=1728 ** -0.5, dtype=torch.float16),
+                              dtype=torch.float16).to(cuda)
+    bias = (torch.randn(32, generator=g) * 0.1).to(cuda)
+    a = ops.Conv3dPlan(x, wp, bias, algo="planes").run(5).float().clone()
+    monkeypatch.setenv("DRAM_B200_US3", "ring")
+    b = ops.Conv3dPlan(x, wp, bias, algo="planes").run(5).float().clone()
+    torch.cuda.synchronize()
+    assert (a - b).abs().max().item() <= 2.0 ** -9 * max(1.0, b.abs().max().item())
+    assert a.abs().sum().item() > 0
+
+
 def test_conv_algo_dispatch(cuda, lib):
     p = _run_conv(cuda, 1, (8, 16, 16), 64, 0, 64, 3, 1, 1)                 # auto -> planes
     assert p.algo == "planes"
