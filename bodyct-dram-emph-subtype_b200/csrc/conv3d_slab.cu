@@ -582,15 +582,11 @@ __device__ __forceinline__ StreamSeg stream_segment(const SlabParams &p, int ste
   return s;
 }
 
-// SPLIT: the 36 MMAs of a plane alternate between two accumulator sets (TMEM columns [0,256) and [256,512), 8 blocks
-// each) that the epilogue adds: consecutive instructions never accumulate into the same columns.
-template <bool SPLIT>
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                        const __grid_constant__ SlabParams p) {
   constexpr int RING = StreamCfg::RING_;
-  constexpr int NBLK = SPLIT ? StreamCfg::TMEM_BLOCKS / 2 : StreamCfg::TMEM_BLOCKS;
-  constexpr uint32_t SET_COLS = 256;
+  constexpr int NBLK = StreamCfg::TMEM_BLOCKS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = smem_base + RING * PLANE_PITCH;
@@ -691,15 +687,13 @@ conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t id1 = idesc_of(n1), id2 = idesc_of(n2 > 0 ? n2 : 1);
         const bool fresh_all = z == z_first;
         if (elect_one_sync()) {
-          // a set's first MMA of the plane goes block by block: a block's first touch overwrites, the others accumulate
-#pragma unroll
-          for (int set = 0; set < (SPLIT ? 2 : 1); ++set)
-            for (int q = 0; q < nblk; ++q) {
-              const int t = lo + q;
-              const unsigned bq = (b_lo + (unsigned)q) % NBLK;
-              umma_bf16(tmem_base + (uint32_t)set * SET_COLS + bq * 32u, da_plane + (uint64_t)(2 * set),
-                        db1 + (uint64_t)(((q * 32 * 128) >> 4) + 2 * set), idesc1, (fresh_all || t == z + 1) ? 0u : 1u);
-            }
+          // (kh,kw) = (0,0), K step 0, block by block: a block's first MMA overwrites, the others accumulate
+          for (int q = 0; q < nblk; ++q) {
+            const int t = lo + q;
+            const unsigned bq = (b_lo + (unsigned)q) % NBLK;
+            umma_bf16(tmem_base + bq * 32u, da_plane, db1 + (uint64_t)((q * 32 * 128) >> 4), idesc1,
+                      (fresh_all || t == z + 1) ? 0u : 1u);
+          }
 #pragma unroll
           for (int hw = 0; hw < 9; ++hw) {
             const int kh = hw / 3, kw = hw - 3 * kh;
@@ -707,12 +701,10 @@ conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t w_off16 = (uint32_t)(hw * StreamCfg::W_HW_BYTES) >> 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (hw == 0 && k < (SPLIT ? 2 : 1)) continue;
-              const uint32_t set_off = SPLIT ? (uint32_t)(k & 1) * SET_COLS : 0u;
-              umma_bf16(d1 + set_off, da_plane + (uint64_t)(row_off16 + 2 * k), db1 + (uint64_t)(w_off16 + 2 * k), id1, 1u);
+              if (hw == 0 && k == 0) continue;
+              umma_bf16(d1, da_plane + (uint64_t)(row_off16 + 2 * k), db1 + (uint64_t)(w_off16 + 2 * k), id1, 1u);
               if (n2 > 0)
-                umma_bf16(d2 + set_off, da_plane + (uint64_t)(row_off16 + 2 * k), db2 + (uint64_t)(w_off16 + 2 * k), id2,
-                          1u);
+                umma_bf16(d2, da_plane + (uint64_t)(row_off16 + 2 * k), db2 + (uint64_t)(w_off16 + 2 * k), id2, 1u);
             }
           }
           umma_commit(plane_empty(slot));
@@ -741,13 +733,6 @@ conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tcgen05_fence_after();
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + blk * 32u + ((uint32_t)(warp * 32) << 16), v);
-        if (SPLIT) {
-          uint32_t v2[32];
-          tmem_ld_32x32b_x32(tmem_base + SET_COLS + blk * 32u + ((uint32_t)(warp * 32) << 16), v2);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        }
         tmem_wait_ld();
         tcgen05_fence_before();
         mbar_arrive(tmem_empty(blk));  // the block's values are in registers: hand it back before the arithmetic
@@ -848,7 +833,6 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
   // Cin 64 -> Cout 32 with one source (us3): weights-resident streaming kernel; DRAM_B200_US3=ring keeps the items
   const char *us3 = getenv("DRAM_B200_US3");
   sp.stream = (d->cout == 32 && sp.chunks_total == 1 && !sp.up2x && !(us3 && strcmp(us3, "ring") == 0)) ? 1 : 0;
-  if (sp.stream && us3 && strcmp(us3, "split") == 0) sp.stream = 2;  // two accumulator sets (see the kernel)
   const int64_t steps = (int64_t)d->n * sp.cols_w * sp.cols_h * d->di;
   if (steps > 0x7fffffffLL) {
     set_error("conv3d(planes): too many plane steps");
@@ -888,13 +872,9 @@ int slab_plan_fill(dram_conv_plan *pl, const dram_conv_desc *d, const void *src1
     } else if (sp.stream) {
       pl->smem_bytes = StreamCfg::SMEM_BYTES;
       pl->stages = StreamCfg::RING_;
-      rc = check_cuda(cudaFuncSetAttribute(conv3d_stream32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      rc = check_cuda(cudaFuncSetAttribute(conv3d_stream32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            StreamCfg::SMEM_BYTES),
                       "cudaFuncSetAttribute(conv3d_stream32_kernel)");
-      if (rc == DRAM_OK)
-        rc = check_cuda(cudaFuncSetAttribute(conv3d_stream32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             StreamCfg::SMEM_BYTES),
-                        "cudaFuncSetAttribute(conv3d_stream32_kernel)");
     } else {
       pl->smem_bytes = SlabCfg<32>::SMEM_BYTES;
       rc = slab_set_attr<32, false>();
@@ -908,10 +888,7 @@ int slab_plan_run(const dram_conv_plan *pl, int ctas, cudaStream_t st) {
   sp.epi = with_sat_counter(sp.epi);
   if (sp.stream) {
     if (sp.steps_total < ctas) ctas = sp.steps_total;
-    if (sp.stream == 2)
-      conv3d_stream32_kernel<true><<<dim3(ctas), SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_w, sp);
-    else
-      conv3d_stream32_kernel<false><<<dim3(ctas), SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_w, sp);
+    conv3d_stream32_kernel<<<dim3(ctas), SL_THREADS, pl->smem_bytes, st>>>(pl->map_a1, pl->map_w, sp);
     DRAM_CHECK_LAUNCH("conv3d_stream32_kernel launch");
     return DRAM_OK;
   }

@@ -201,11 +201,8 @@ STREAM_CASES = [
 
 @pytest.mark.parametrize("case", range(len(STREAM_CASES)))
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("mode", ["stream", "split"])
-def test_conv_streaming_kernel(cuda, lib, case, dt, mode, monkeypatch):
-    """us3 (med3d.py:90): planes stream past resident weights; every way a CTA's range can cut a column.  `split` =
-    the variant with two accumulator sets that the epilogue adds."""
-    monkeypatch.setenv("DRAM_B200_US3", mode)
+def test_conv_streaming_kernel(cuda, lib, case, dt):
+    """us3 (med3d.py:90): planes stream past resident weights; every way a CTA's range can cut a column."""
     n, dims, kw = STREAM_CASES[case]
     _run_conv(cuda, n, dims, 64, 0, 32, 3, 1, 1, dtype=dt, algo="planes", expect_algo="planes", seed=140 + case,
               normalize=(case % 2 == 1), **kw)
