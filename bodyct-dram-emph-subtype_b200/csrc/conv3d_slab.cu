@@ -582,6 +582,25 @@ __device__ __forceinline__ StreamSeg stream_segment(const SlabParams &p, int ste
   return s;
 }
 
+// K steps 1..35 of one input plane of the streaming kernel (step 0 is issued block by block by the caller).
+// WRAP: the plane's accumulator blocks wrap around the TMEM ring, so every step is two instructions.
+template <bool WRAP>
+__device__ __forceinline__ void stream_issue_plane(uint32_t d1, uint32_t d2, uint64_t da_plane, uint64_t db1,
+                                                   uint64_t db2, uint32_t id1, uint32_t id2) {
+#pragma unroll
+  for (int hw = 0; hw < 9; ++hw) {
+    const int kh = hw / 3, kw = hw - 3 * kh;
+    const uint32_t row_off16 = (uint32_t)((kh * PL_W + kw) * 128) >> 4;
+    const uint32_t w_off16 = (uint32_t)(hw * StreamCfg::W_HW_BYTES) >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (hw == 0 && k == 0) continue;
+      umma_bf16(d1, da_plane + (uint64_t)(row_off16 + 2 * k), db1 + (uint64_t)(w_off16 + 2 * k), id1, 1u);
+      if (WRAP) umma_bf16(d2, da_plane + (uint64_t)(row_off16 + 2 * k), db2 + (uint64_t)(w_off16 + 2 * k), id2, 1u);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(SL_THREADS, 1)
 conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                        const __grid_constant__ SlabParams p) {
@@ -694,18 +713,13 @@ conv3d_stream32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             umma_bf16(tmem_base + bq * 32u, da_plane, db1 + (uint64_t)((q * 32 * 128) >> 4), idesc1,
                       (fresh_all || t == z + 1) ? 0u : 1u);
           }
-#pragma unroll
-          for (int hw = 0; hw < 9; ++hw) {
-            const int kh = hw / 3, kw = hw - 3 * kh;
-            const uint32_t row_off16 = (uint32_t)((kh * PL_W + kw) * 128) >> 4;
-            const uint32_t w_off16 = (uint32_t)(hw * StreamCfg::W_HW_BYTES) >> 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (hw == 0 && k == 0) continue;
-              umma_bf16(d1, da_plane + (uint64_t)(row_off16 + 2 * k), db1 + (uint64_t)(w_off16 + 2 * k), id1, 1u);
-              if (n2 > 0)
-                umma_bf16(d2, da_plane + (uint64_t)(row_off16 + 2 * k), db2 + (uint64_t)(w_off16 + 2 * k), id2, 1u);
-            }
+          // The other 35 K steps.  14 planes of 16 take the first branch: ONE instruction per step (two uniform 64-bit
+          // adds each).  Keeping the ring-wrap instruction predicated in the same loop made the issuing thread the
+          // bottleneck: predicated-off uniform instructions still wait on the scoreboard (ncu source view, round 2).
+          if (n2 == 0) {
+            stream_issue_plane<false>(d1, d2, da_plane, db1, db2, id1, id2);
+          } else {
+            stream_issue_plane<true>(d1, d2, da_plane, db1, db2, id1, id2);
           }
           umma_commit(plane_empty(slot));
           if (z - 1 >= sg.t0) umma_commit(tmem_full((oseq0 + (unsigned)(z - 1 - sg.t0)) % NBLK));

@@ -9,6 +9,7 @@ for n in 1 4; do
   echo "stream  n=$n: $(timeout 120 python tools/conv_one.py $n 128 128 128 64 0 32 3 1 1 | tail -1)"
   echo "ring    n=$n: $(DRAM_B200_US3=ring timeout 120 python tools/conv_one.py $n 128 128 128 64 0 32 3 1 1 | tail -1)"
 done 2>&1 | tee gpurun_out/us3_stream_${TAG}.log
+[ "$2" = "quick" ] && exit 0
 timeout 900 python -m pytest tests/test_model_gpu.py tests/test_fullsize_gpu.py -m gpu -q -rf -k "not properties" > gpurun_out/pytest_model_${TAG}.log 2>&1
 tail -4 gpurun_out/pytest_model_${TAG}.log
 python bench.py --steps 20 --warmup 3 --no-yardstick --no-cpu-baseline --no-train-field > gpurun_out/bench_b4_${TAG}.json 2> gpurun_out/bench_b4_${TAG}.err
