@@ -19,7 +19,11 @@ x1 = torch.randn((n, d, h, w, c1), device=dev).to(DT)
 x2 = torch.randn((n, d, h, w, c2), device=dev).to(DT) if c2 else None
 wgt = (torch.randn(cout, k ** 3 * (c1 + c2), device=dev) * 0.02).to(DT)
 bias = torch.zeros(cout, device=dev)
-plan = ops.Conv3dPlan(x1, wgt, bias, x2=x2, kernel=k, stride=s, dilation=dl, algo=algo)
+heads = None
+if os.environ.get("HEADS") and cout == 32:  # us3: the two fused 1x1x1 heads + sigmoid, activation not stored
+    heads = (torch.randn(2, 32, device=dev) * 0.1, torch.zeros(2, device=dev), (1, 1), True)
+plan = ops.Conv3dPlan(x1, wgt, bias, x2=x2, kernel=k, stride=s, dilation=dl, algo=algo, heads=heads,
+                      store_out=heads is None)
 res = None
 if res_c:
     res = torch.randn(plan.out_shape[:4] + (res_c,), device=dev).to(DT)
