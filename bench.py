@@ -795,7 +795,7 @@ def main():
     executed = exec_flops / (conv_ms * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic(args.arch, dims, B)
     roofline = {"bound": "tensor",
-                "kernel": f"conv3d_stem_kernel + conv3d_slab_kernel + conv3d_umma_kernel (+ upconv_axis_kernel of the "
+                "kernel": f"conv3d_stem_kernel + conv3d_slab_kernel + conv3d_stream32_kernel + conv3d_umma_kernel (+ upconv_axis_kernel of the "
                           f"commuted us1.0; {len(conv_steps)} launches/step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
