@@ -104,6 +104,21 @@ def main():
     lut, _ = ops.window_lut(hu)
     ms = timeit(lambda: ops.stem_conv7_hu(hu, lut, wp, bias, mult, out=x))
     report("K2 stem fused from int16 HU", ms, B * (V * 2 + h ** 3 * 128), flops=2.0 * B * h ** 3 * 64 * 343)
+    # f1 / f2: the device pre-/post-steps of the product path (whole volume as the crop, and an interior crop box)
+    lobes = (lungs_b[0] * 3).to(torch.uint8)
+    cle, _, _ = ops.dram_upsample_mask(dense0, dense1, ess_b, lungs_b, (S, S, S))
+    dram0 = cle[0, 0].contiguous()
+    c0, c1 = S // 8, S - S // 8 - 3
+    for tag, box in (("whole volume", ((0, S), (0, S), (0, S))), ("interior crop", ((c0, c1), (c0 + 1, c1 - 2), (c0 + 3, c1)))):
+        cd, chh, cww = (b - a for a, b in box)
+        outs = (torch.empty((cd, chh, cww), dtype=torch.int16, device=dev),
+                torch.empty((cd, chh, cww), dtype=torch.uint8, device=dev),
+                torch.empty((cd, chh, cww), dtype=torch.uint8, device=dev))
+        ms = timeit(lambda: ops.lung_crop(hu_b[0], lobes, box, out=outs))
+        report(f"f1 lung_crop, {tag}", ms, cd * chh * cww * (2 + 1 + 2 + 1 + 1))
+        heat = torch.empty((S, S, S), dtype=torch.uint8, device=dev)
+        ms = timeit(lambda: ops.heatmap_u8(dram0, box, (S, S, S), out=heat))
+        report(f"f2 heatmap_u8, {tag}", ms, V * 4 + V)
 
 
 if __name__ == "__main__":
