@@ -220,29 +220,42 @@ heatmap_u8_kernel(const float *__restrict__ map, uint8_t *__restrict__ out, int 
     const LinIdx id = lin_index_ac(z, sd, d), ih = lin_index_ac(y, sh, h);
     const float *r00 = map + ((int64_t)id.i0 * h + ih.i0) * w, *r01 = map + ((int64_t)id.i0 * h + ih.i1) * w;
     const float *r10 = map + ((int64_t)id.i1 * h + ih.i0) * w, *r11 = map + ((int64_t)id.i1 * h + ih.i1) * w;
-    for (int gx0 = 0; gx0 < OW; gx0 += 32) {
-      const int gx = gx0 + lane;
-      const int x = gx - x0;
-      const bool in = gx < OW && x >= 0 && x < cw;
-      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f, c0 = 0.f, c1 = 0.f, e0 = 0.f, e1 = 0.f;
-      XEntry xe = XEntry{0, 0, 0.f, 0.f};
-      if (in) {
-        xe = xtab[x];
-        a0 = __ldg(r00 + xe.i0); a1 = __ldg(r00 + xe.i1);
-        b0 = __ldg(r01 + xe.i0); b1 = __ldg(r01 + xe.i1);
-        c0 = __ldg(r10 + xe.i0); c1 = __ldg(r10 + xe.i1);
-        e0 = __ldg(r11 + xe.i0); e1 = __ldg(r11 + xe.i1);
+    // four 32-voxel stretches per trip: their 32 loads are issued before any of them is used
+    for (int gx0 = 0; gx0 < OW; gx0 += 128) {
+      float a0[4], a1[4], b0[4], b1[4], c0[4], c1[4], e0[4], e1[4];
+      XEntry xe[4];
+      bool in[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gx = gx0 + 32 * q + lane, x = gx - x0;
+        in[q] = gx < OW && x >= 0 && x < cw;
+        xe[q] = in[q] ? xtab[x] : XEntry{0, 0, 0.f, 0.f};
       }
-      const uint32_t any = __float_as_uint(a0) | __float_as_uint(a1) | __float_as_uint(b0) | __float_as_uint(b1) |
-                           __float_as_uint(c0) | __float_as_uint(c1) | __float_as_uint(e0) | __float_as_uint(e1);
-      uint8_t u = 0;
-      if (__ballot_sync(0xffffffffu, any != 0u) != 0u) {
-        float v = id.w0 * (ih.w0 * (xe.w0 * a0 + xe.w1 * a1) + ih.w1 * (xe.w0 * b0 + xe.w1 * b1)) +
-                  id.w1 * (ih.w0 * (xe.w0 * c0 + xe.w1 * c1) + ih.w1 * (xe.w0 * e0 + xe.w1 * e1));
-        v = fminf(fmaxf(v, 0.0f), 1.0f);
-        u = in ? (uint8_t)(int)((double)v * 255.0) : 0;  // numpy: float64 product, astype(uint8) truncates
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a0[q] = a1[q] = b0[q] = b1[q] = c0[q] = c1[q] = e0[q] = e1[q] = 0.f;
+        if (in[q]) {
+          a0[q] = __ldg(r00 + xe[q].i0); a1[q] = __ldg(r00 + xe[q].i1);
+          b0[q] = __ldg(r01 + xe[q].i0); b1[q] = __ldg(r01 + xe[q].i1);
+          c0[q] = __ldg(r10 + xe[q].i0); c1[q] = __ldg(r10 + xe[q].i1);
+          e0[q] = __ldg(r11 + xe[q].i0); e1[q] = __ldg(r11 + xe[q].i1);
+        }
       }
-      if (gx < OW) orow[gx] = u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gx = gx0 + 32 * q + lane;
+        const uint32_t any = __float_as_uint(a0[q]) | __float_as_uint(a1[q]) | __float_as_uint(b0[q]) |
+                             __float_as_uint(b1[q]) | __float_as_uint(c0[q]) | __float_as_uint(c1[q]) |
+                             __float_as_uint(e0[q]) | __float_as_uint(e1[q]);
+        uint8_t u = 0;
+        if (__ballot_sync(0xffffffffu, any != 0u) != 0u) {
+          float v = id.w0 * (ih.w0 * (xe[q].w0 * a0[q] + xe[q].w1 * a1[q]) + ih.w1 * (xe[q].w0 * b0[q] + xe[q].w1 * b1[q])) +
+                    id.w1 * (ih.w0 * (xe[q].w0 * c0[q] + xe[q].w1 * c1[q]) + ih.w1 * (xe[q].w0 * e0[q] + xe[q].w1 * e1[q]));
+          v = fminf(fmaxf(v, 0.0f), 1.0f);
+          u = in[q] ? (uint8_t)(int)((double)v * 255.0) : 0;  // numpy: float64 product, astype(uint8) truncates
+        }
+        if (gx < OW) orow[gx] = u;
+      }
     }
   }
 }
