@@ -37,7 +37,8 @@ static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = 8;
 static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 416
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
 static constexpr int ST_OUT_TILE_BYTES = 128 * 128;           // staged epilogue: 128 voxels x 64 channels, SWIZZLE_128B
-static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 2 * ST_OUT_TILE_BYTES + 512;
+static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 2 * ST_OUT_TILE_BYTES + 512 + 512;
+static constexpr int ST_SLICE_H = 4;                          // rows of the 8 x 16 tile one epilogue warp owns (32 voxels)
 
 struct StemParams {
   const float *x;       // fp32 [n][D][H][W] (kernel variant HU = false)
@@ -108,6 +109,7 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
   auto tmem_full = [&](int a) { return bar_base + 8u * (2 * ST_RING + a); };
   auto tmem_empty = [&](int a) { return bar_base + 8u * (2 * ST_RING + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * ST_RING + 4);
+  const uint32_t sb_base = bar_base + 512u;  // fp32 scale[64] then shift[64] of the epilogue
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -131,6 +133,12 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(w_base + 16u * i), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+  }
+  if (threadIdx.x < 64) {  // the epilogue's per-channel scale / shift: read from shared memory (broadcast), not per group from global
+    const float sc = p.epi.scale != nullptr ? __ldg(p.epi.scale + threadIdx.x) : 1.0f;
+    const float sh = __ldg(p.epi.bias + threadIdx.x);
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_base + 4u * threadIdx.x), "f"(sc) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(sb_base + 256u + 4u * threadIdx.x), "f"(sh) : "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tcgen05_fence_before();
@@ -352,15 +360,22 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
   } else {
     // ------------------------------- epilogue warps 0..3 -------------------------------
     // Staged through shared memory: a lane owns one voxel (row) of the 8 x 16 tile and writes its 64 channels into a
-    // SWIZZLE_128B tile; one thread sends the finished 16 KiB tile with ONE TMA store (full 128-byte lines; the tensor
-    // map clips voxels outside the volume).  The direct form — four 16-byte stores per lane and 32-channel group, each
-    // to a different 128-byte line — kept the L1/LSU pipe 70 % busy with half-filled sectors (ncu, round 2) in a
-    // kernel that writes 268 MB per 256^3 volume.
+    // SWIZZLE_128B tile; full 128-byte lines leave through TMA stores (the tensor map clips voxels outside the volume).
+    // The direct form — four 16-byte stores per lane and 32-channel group, each to a different 128-byte line — kept
+    // the L1/LSU pipe 70 % busy with half-filled sectors (ncu, round 2) in a kernel that writes 268 MB per 256^3 volume.
+    // Round 2, second capture (profiles/stem_r2v.md): the producers and the MMA warp WAIT (for free slots / a free
+    // accumulator); the four epilogue warps are the critical path — 2.7 k clocks per output plane against 1.4 k of MMAs.
+    // So: each warp stores its own 32-voxel slice (4 rows of the tile, its own bulk groups: no CTA-level barrier),
+    // both 32-channel groups are read from tensor memory before the first is used, and scale / shift come from
+    // shared memory instead of sixteen global loads per group.
     const int row = warp * 32 + lane;
     int buf = 0, ob = 0;
     uint32_t buf_phase = 0;
+    const bool relu_in_cvt = p.epi.relu && p.epi.sat_count == nullptr;
+    const uint32_t row_off = (uint32_t)row * 128u;
     for (int item = item_begin; item < item_end; ++item) {
       const StemItem it = decode_stem_item(p, item);
+      const bool slice_ok = it.h0 + ST_SLICE_H * warp < p.epi.Ho;
       mbar_wait(tmem_full(buf), buf_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -368,21 +383,54 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
         const int od = it.q0 + t;
         const uint32_t taddr = tmem_base + (uint32_t)((buf * ST_GROUP + t) * 64) + ((uint32_t)(warp * 32) << 16);
         const uint32_t tile = out_base + (uint32_t)ob * ST_OUT_TILE_BYTES;
-        // the store that last read this tile (two tiles ago) must be done with shared memory
-        if (threadIdx.x == 0) tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + (uint32_t)c0, v);
-          tmem_wait_ld();
-          epilogue_group_staged(p.epi, v, c0, row, c0 >> 5, 0u, false, tile);
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(taddr, v[0]);
+        tmem_ld_32x32b_x32(taddr + 32u, v[1]);
+        // the store that last read this slice (two planes ago) must be done with shared memory
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        tmem_wait_ld();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 sc, sh;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w)
+                         : "r"(sb_base + (uint32_t)(half * 128 + j * 16)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
+                         : "r"(sb_base + 256u + (uint32_t)(half * 128 + j * 16)));
+            y[4 * j + 0] = fmaf(__uint_as_float(v[half][4 * j + 0]), sc.x, sh.x);
+            y[4 * j + 1] = fmaf(__uint_as_float(v[half][4 * j + 1]), sc.y, sh.y);
+            y[4 * j + 2] = fmaf(__uint_as_float(v[half][4 * j + 2]), sc.z, sh.z);
+            y[4 * j + 3] = fmaf(__uint_as_float(v[half][4 * j + 3]), sc.w, sh.w);
+          }
+          if (p.epi.relu && !relu_in_cvt) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+          }
+          if (p.epi.sat_count != nullptr) note_saturation(p.epi, y);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              w[q] = relu_in_cvt ? pack2_relu(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16)
+                                 : pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16);
+            const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + row_off + chunk), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 0 && od < p.epi.Do) {
-          tma_store_5d(&map_out, tile, 0, it.w0, it.h0, od, it.sample);
-          tma_store_commit();
+        __syncwarp();
+        if (lane == 0) {
+          if (od < p.epi.Do && slice_ok)
+            tma_store_5d(&map_out, tile + (uint32_t)warp * (32u * 128u), 0, it.w0, it.h0 + ST_SLICE_H * warp, od, it.sample);
+          tma_store_commit();  // also when nothing was stored: wait_group.read<1> above counts one group per plane
         }
         ob ^= 1;
       }
@@ -393,7 +441,7 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
         buf_phase ^= 1u;
       }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
   tcgen05_fence_before();
@@ -442,8 +490,8 @@ static int stem_launch(StemParams &p, const void *weight, const float *bias, con
                    : check_cuda(cudaFuncSetAttribute(conv3d_stem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      ST_SMEM_BYTES), "cudaFuncSetAttribute(conv3d_stem_kernel)");
   if (rc != DRAM_OK) return rc;
-  CUtensorMap map_out;  // one output plane of an item: 64 channels x 8 (W) x 16 (H) voxels, SWIZZLE_128B rows
-  rc = encode_act_map(&map_out, out, n, Do, Ho, Wo, 64, 64, ST_W, ST_H, 1, 1, 1, 1, p.epi.is_f16);
+  CUtensorMap map_out;  // one epilogue warp's slice of an output plane: 64 channels x 8 (W) x 4 (H) voxels, SWIZZLE_128B rows
+  rc = encode_act_map(&map_out, out, n, Do, Ho, Wo, 64, 64, ST_W, ST_SLICE_H, 1, 1, 1, 1, p.epi.is_f16);
   if (rc != DRAM_OK) return rc;
   int ctas = sm_count();
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
