@@ -33,8 +33,11 @@ static constexpr int ST_KEEP = 5;                            // planes shared wi
 static constexpr int ST_W_EVEN_BYTES = 8 * 4 * 64 * 16;      // [kh][kd = 6,4,2,0][cout][8 halves] = 32768
 static constexpr int ST_W_ODD_BYTES = 8 * 3 * 64 * 16;       // [kh][kd = 5,3,1][cout][8 halves] = 24576
 static constexpr int ST_WEIGHT_BYTES = ST_W_EVEN_BYTES + ST_W_ODD_BYTES;  // 57344
-static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = 8;
-static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 416
+#ifndef DRAM_STEM_PROD_WARPS
+#define DRAM_STEM_PROD_WARPS 11
+#endif
+static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = DRAM_STEM_PROD_WARPS;  // 5 + 11 = 16 warps: 512 threads x 128 registers = the whole register file
+static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 512
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
 static constexpr int ST_OUT_TILE_BYTES = 128 * 128;           // staged epilogue: 128 voxels x 64 channels, SWIZZLE_128B
 static constexpr int ST_SMEM_BYTES = 1024 + ST_RING * ST_PLANE_BYTES + ST_WEIGHT_BYTES + 2 * ST_OUT_TILE_BYTES + 512 + 512;
