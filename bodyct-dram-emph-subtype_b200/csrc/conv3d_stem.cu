@@ -343,11 +343,14 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
           for (int pr = 0; pr < 4; ++pr) {  // kh pairs (0,1) (2,3) (4,5) (6,7): K = 16 per MMA
             const uint64_t da = da_plane + (uint64_t)(((uint32_t)(2 * pr) * 128u) >> 4);
             const uint64_t db = db_region + (uint64_t)((uint32_t)(2 * pr) * kh_stride16 + ((blk0 * 1024u) >> 4));
-            const int acc_blocks = first_touch ? nblk - 1 : nblk;
-            if (acc_blocks > 0) umma_bf16(d0, da, db, idesc[acc_blocks - 1], 1u);
-            if (first_touch)
-              umma_bf16(d0 + (uint32_t)((nblk - 1) * 64), da, db + (uint64_t)(((uint32_t)(nblk - 1) * 1024u) >> 4), idesc[0],
-                        pr > 0 ? 1u : 0u);
+            // only the very first K step of a fresh accumulator block has to overwrite: that one MMA is split off,
+            // the other three kh pairs run the full kd stack (the split cost 12 % of the item's MMA clocks)
+            if (first_touch && pr == 0) {
+              if (nblk > 1) umma_bf16(d0, da, db, idesc[nblk - 2], 1u);
+              umma_bf16(d0 + (uint32_t)((nblk - 1) * 64), da, db + (uint64_t)(((uint32_t)(nblk - 1) * 1024u) >> 4), idesc[0], 0u);
+            } else {
+              umma_bf16(d0, da, db, idesc[nblk - 1], 1u);
+            }
           }
           if (j < ST_ITEM_PLANES - ST_KEEP || !next_reuse) umma_commit(plane_empty(slot));
         }
