@@ -33,9 +33,10 @@ static constexpr int ST_KEEP = 5;                            // planes shared wi
 static constexpr int ST_W_EVEN_BYTES = 8 * 4 * 64 * 16;      // [kh][kd = 6,4,2,0][cout][8 halves] = 32768
 static constexpr int ST_W_ODD_BYTES = 8 * 3 * 64 * 16;       // [kh][kd = 5,3,1][cout][8 halves] = 24576
 static constexpr int ST_WEIGHT_BYTES = ST_W_EVEN_BYTES + ST_W_ODD_BYTES;  // 57344
-// Warp roles: 8 epilogue warps (two per TMEM lane quadrant, one 32-channel half each), the MMA warp, 7 producers —
-// 16 warps x 32 threads x 128 registers = the whole register file.
-static constexpr int ST_EPI_WARPS = 8, ST_MMA_WARP = 8, ST_PROD_WARP0 = 9, ST_PROD_WARPS = 7;
+#ifndef DRAM_STEM_PROD_WARPS
+#define DRAM_STEM_PROD_WARPS 11
+#endif
+static constexpr int ST_MMA_WARP = 4, ST_PROD_WARP0 = 5, ST_PROD_WARPS = DRAM_STEM_PROD_WARPS;  // 5 + 11 = 16 warps: 512 threads x 128 registers = the whole register file
 static constexpr int ST_THREADS = (ST_PROD_WARP0 + ST_PROD_WARPS) * 32;  // 512
 static constexpr int ST_TMEM_COLS = 2 * ST_GROUP * 64;       // 512
 static constexpr int ST_OUT_TILE_BYTES = 128 * 128;           // staged epilogue: 128 voxels x 64 channels, SWIZZLE_128B
@@ -123,7 +124,7 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full(a), 1);
-      mbar_init(tmem_empty(a), ST_EPI_WARPS * 32);
+      mbar_init(tmem_empty(a), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -363,78 +364,78 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
       }
     }
   } else {
-    // ------------------------------- epilogue warps 0..7 -------------------------------
-    // Staged through shared memory: a lane owns one voxel (row) of the 8 x 16 tile and writes channels into a
+    // ------------------------------- epilogue warps 0..3 -------------------------------
+    // Staged through shared memory: a lane owns one voxel (row) of the 8 x 16 tile and writes its 64 channels into a
     // SWIZZLE_128B tile; full 128-byte lines leave through TMA stores (the tensor map clips voxels outside the volume).
     // The direct form — four 16-byte stores per lane and 32-channel group, each to a different 128-byte line — kept
     // the L1/LSU pipe 70 % busy with half-filled sectors (ncu, round 2) in a kernel that writes 268 MB per 256^3 volume.
-    // Round 2, later captures (profiles/stem_r2v.md, stem_r2aa.md): the producers and the MMA warp WAIT (for free slots /
-    // a free accumulator); the epilogue warps are the critical path — ~290 instructions per output plane and thread at
-    // one instruction per ~7 clocks.  So: scale / shift come from shared memory instead of sixteen global loads per
-    // group; a quadrant of the tile (32 voxels = 4 rows) is stored by its own TMA store with its own bulk groups (no
-    // CTA-level barrier); and two warps share a quadrant, one 32-channel half each (a 64-thread named barrier pairs them).
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const bool storer = half == 0 && lane == 0;
+    // Round 2, second capture (profiles/stem_r2v.md): the producers and the MMA warp WAIT (for free slots / a free
+    // accumulator); the four epilogue warps are the critical path — 2.7 k clocks per output plane against 1.4 k of MMAs.
+    // So: each warp stores its own 32-voxel slice (4 rows of the tile, its own bulk groups: no CTA-level barrier),
+    // both 32-channel groups are read from tensor memory before the first is used, and scale / shift come from
+    // shared memory instead of sixteen global loads per group.
+    const int row = warp * 32 + lane;
     int buf = 0, ob = 0;
     uint32_t buf_phase = 0;
     const bool relu_in_cvt = p.epi.relu && p.epi.sat_count == nullptr;
     const uint32_t row_off = (uint32_t)row * 128u;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
     for (int item = item_begin; item < item_end; ++item) {
       const StemItem it = decode_stem_item(p, item);
-      const bool slice_ok = it.h0 + ST_SLICE_H * quad < p.epi.Ho;
+      const bool slice_ok = it.h0 + ST_SLICE_H * warp < p.epi.Ho;
       mbar_wait(tmem_full(buf), buf_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int t = 0; t < ST_GROUP; ++t) {
         const int od = it.q0 + t;
-        const uint32_t taddr =
-            tmem_base + (uint32_t)((buf * ST_GROUP + t) * 64 + half * 32) + ((uint32_t)(quad * 32) << 16);
+        const uint32_t taddr = tmem_base + (uint32_t)((buf * ST_GROUP + t) * 64) + ((uint32_t)(warp * 32) << 16);
         const uint32_t tile = out_base + (uint32_t)ob * ST_OUT_TILE_BYTES;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr, v);
-        // the store that last read this quadrant of the tile (two planes ago) must be done with shared memory
-        if (storer) tma_store_wait_read<1>();
-        pair_sync();
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(taddr, v[0]);
+        tmem_ld_32x32b_x32(taddr + 32u, v[1]);
+        // the store that last read this slice (two planes ago) must be done with shared memory
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
         tmem_wait_ld();
-        float y[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 sc, sh;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w)
-                       : "r"(sb_base + (uint32_t)(half * 128 + j * 16)));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
-                       : "r"(sb_base + 256u + (uint32_t)(half * 128 + j * 16)));
-          y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-        }
-        if (p.epi.relu && !relu_in_cvt) {
+        for (int half = 0; half < 2; ++half) {
+          float y[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
-        }
-        if (p.epi.sat_count != nullptr) note_saturation(p.epi, y);
+          for (int j = 0; j < 8; ++j) {
+            float4 sc, sh;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sc.x), "=f"(sc.y), "=f"(sc.z), "=f"(sc.w)
+                         : "r"(sb_base + (uint32_t)(half * 128 + j * 16)));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sh.x), "=f"(sh.y), "=f"(sh.z), "=f"(sh.w)
+                         : "r"(sb_base + 256u + (uint32_t)(half * 128 + j * 16)));
+            y[4 * j + 0] = fmaf(__uint_as_float(v[half][4 * j + 0]), sc.x, sh.x);
+            y[4 * j + 1] = fmaf(__uint_as_float(v[half][4 * j + 1]), sc.y, sh.y);
+            y[4 * j + 2] = fmaf(__uint_as_float(v[half][4 * j + 2]), sc.z, sh.z);
+            y[4 * j + 3] = fmaf(__uint_as_float(v[half][4 * j + 3]), sc.w, sh.w);
+          }
+          if (p.epi.relu && !relu_in_cvt) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t w[4];
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+          }
+          if (p.epi.sat_count != nullptr) note_saturation(p.epi, y);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            w[q] = relu_in_cvt ? pack2_relu(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16)
-                               : pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16);
-          const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + row_off + chunk), "r"(w[0]), "r"(w[1]),
-                       "r"(w[2]), "r"(w[3])
-                       : "memory");
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              w[q] = relu_in_cvt ? pack2_relu(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16)
+                                 : pack2(y[8 * j + 2 * q], y[8 * j + 2 * q + 1], p.epi.is_f16);
+            const uint32_t chunk = (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + row_off + chunk), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3])
+                         : "memory");
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        pair_sync();
-        if (storer) {
+        __syncwarp();
+        if (lane == 0) {
           if (od < p.epi.Do && slice_ok)
-            tma_store_5d(&map_out, tile + (uint32_t)quad * (32u * 128u), 0, it.w0, it.h0 + ST_SLICE_H * quad, od, it.sample);
+            tma_store_5d(&map_out, tile + (uint32_t)warp * (32u * 128u), 0, it.w0, it.h0 + ST_SLICE_H * warp, od, it.sample);
           tma_store_commit();  // also when nothing was stored: wait_group.read<1> above counts one group per plane
         }
         ob ^= 1;
@@ -446,7 +447,7 @@ conv3d_stem_kernel(const __grid_constant__ CUtensorMap map_out, const __grid_con
         buf_phase ^= 1u;
       }
     }
-    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   }
 
   tcgen05_fence_before();
