@@ -296,6 +296,18 @@ class Med3DEngine:
         w, b, m = self.stem_weights
         return lambda: ops.stem_conv7_hu(hu, lut, w, b, m, out=self.stem_out, lo=lo)
 
+    def image_stem(self, image):
+        """A replacement for the first recorded step that reads the caller's fp32 image [B,(1,)D,H,W] in place instead
+        of the engine's own input buffer: saves the device-to-device copy of `load_image` (2 x 67 MB per 256^3 volume)
+        in `predict_step`.  Pass it to `run_network(first=...)`."""
+        if not hasattr(self, "stem_weights"):
+            raise RuntimeError("image_stem needs the fused stem kernel (DRAM_B200_STEM=unfold is set)")
+        img = image.reshape(self.batch, *self.dims)
+        if img.dtype != torch.float32 or not img.is_contiguous():
+            raise ValueError("image_stem: expected a contiguous fp32 image")
+        w, b, m = self.stem_weights
+        return lambda: ops.stem_conv7(img, w, b, m, out=self.stem_out)
+
     def run_network(self, first=None):
         """The recorded launch sequence on `self.image` -> `self.dense` (engine-owned), on the current stream.
         `first` replaces the first step (see `hu_stem`); it is launched eagerly, the rest replays as a graph.

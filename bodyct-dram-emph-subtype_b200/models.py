@@ -267,8 +267,12 @@ class ScanRegLightningModule(_ScanModule):
                                    "classification one; use ScanCLSLightningModule for med3d/med3d18/med3d50")
             B, D, H, W = image.shape
             eng = self.model.eval().engine(B, (D, H, W), image.device)
-            eng.load_image(image)
-            dense = eng.run_network()  # the lobe-masked means of forward() are not used here (quirk Q2): no K6
+            # the lobe-masked means of forward() are not used here (quirk Q2): no K6
+            if hasattr(eng, "stem_weights"):
+                dense = eng.run_network(first=eng.image_stem(image))  # the stem reads the batch's image in place
+            else:
+                eng.load_image(image)
+                dense = eng.run_network()
             cle, pse, pct = ops.dram_upsample_mask(dense[0], dense[1], ess, lungs, (D, H, W),
                                                    per_sample_denominator=self.per_sample_percentage)
             return {
