@@ -618,6 +618,8 @@ def main():
     rank, local, world = dist_setup(args.gpus)
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    from dram_b200.utils import bind_to_gpu_cpus
+    cpu_binding = bind_to_gpu_cpus(local)  # before any pinned allocation: host buffers land on the GPU's NUMA node
     dims = parse_dims(args)
     B = args.batch
     module = build_module(device, args.arch)
@@ -822,7 +824,8 @@ def main():
         "config": {"workload": workload_name(args.arch, dims, B),
                    "global_batch": world * B, "parallelism": f"volume-sharded x{world}, no collective",
                    "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
-                   "storage_dtype": str(eng.act_dtype), "cuda_graph": ops.graphs_enabled()},
+                   "storage_dtype": str(eng.act_dtype), "cuda_graph": ops.graphs_enabled(),
+                   "cpu_binding": cpu_binding},
         "clocks": clocks, "e2e": e2e, "e2e_product": e2e_product, "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
     }

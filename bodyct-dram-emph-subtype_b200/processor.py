@@ -154,6 +154,9 @@ def postprocess_cls(pred):
 def run_rank(args, rank, world_size):
     device = torch.device("cuda", rank % max(1, torch.cuda.device_count()))
     torch.cuda.set_device(device)
+    if world_size > 1:  # one process per GPU: keep its host buffers and reader / writer threads on the GPU's NUMA node
+        from .utils import bind_to_gpu_cpus
+        bind_to_gpu_cpus(device.index)
     args.device = device
     is_reg = "dram" in args.model_arch  # the split train.py:72 / test.py:62 make
     module = (ScanRegLightningModule if is_reg else ScanCLSLightningModule)(args)

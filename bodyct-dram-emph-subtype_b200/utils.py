@@ -113,3 +113,32 @@ def cat_all_gather(tensors):
     gathered = [torch.ones_like(tensors) for _ in range(dist.get_world_size())]
     dist.all_gather(gathered, tensors, async_op=False)
     return torch.cat(gathered, dim=0)
+
+
+def bind_to_gpu_cpus(gpu_index):
+    """Host-side placement for the one-process-per-GPU runs: binds the calling thread (and the threads it starts later)
+    to the CPUs NVML names as local to the GPU, so that pinned host buffers — first-touch allocated — and the copy
+    threads sit on the GPU's NUMA node.  Returns a short description, or None when NVML / the cpuset does not allow it
+    (nothing changes then).  DRAM_B200_NUMA=0 turns it off."""
+    if os.environ.get("DRAM_B200_NUMA", "1").lower() in ("0", "off", "false", "no"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:  # NVML counts physical devices; CUDA indices follow CUDA_VISIBLE_DEVICES
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            entry = ids[gpu_index]
+            handle = pynvml.nvmlDeviceGetHandleByUUID(entry) if entry.startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(entry))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = sorted(os.sched_getaffinity(0))
+        return f"nvml ideal CPUs of GPU {gpu_index}: {len(after)} of {before} ({after[0]}-{after[-1]})"
+    except Exception as exc:  # no NVML, no permission, CPUs outside the container's cpuset ...
+        logging.getLogger(__name__).debug("bind_to_gpu_cpus(%s) skipped: %s", gpu_index, exc)
+        return None
+
