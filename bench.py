@@ -677,6 +677,7 @@ def main():
     h2d_gbs = 3 * h2d / (p0.elapsed_time(p1) * 1e-3) / 1e9
     del probe_dst
 
+    e2e_diag = os.environ.get("DRAM_B200_E2E_DIAG", "")  # "" | nod2h | noh2d: A/B of the copy legs, never a bench value
     copy_streams = int(os.environ.get("DRAM_B200_COPY_STREAMS", "1"))  # DevicePrefetcher's default; > 1 = chunked over several DMA streams (A/B)
 
     class ResultSink:
@@ -707,8 +708,9 @@ def main():
             ready.record()
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ready)
-                self.host[k][0].copy_(maps, non_blocking=True)
-                self.host[k][1].copy_(pct, non_blocking=True)
+                if e2e_diag != "nod2h":  # diagnostic runs only (the line says so in e2e.api)
+                    self.host[k][0].copy_(maps, non_blocking=True)
+                    self.host[k][1].copy_(pct, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
             self.done[k] = ev
@@ -722,8 +724,13 @@ def main():
         # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's side
         # stream, overlapping the previous step's kernels) and every step's heat-maps + scores go back to the host
         sink = ResultSink()
-        for i, dev_batch in enumerate(DevicePrefetcher((batches for _ in range(n_steps)), device, copy_streams=copy_streams)):
-            sink.push(i, step_fn(dev_batch, i))
+        if e2e_diag == "noh2d":  # diagnostic: the batch is staged once, no host->device copy per step
+            dev_batch = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in batches.items()}
+            for i in range(n_steps):
+                sink.push(i, step_fn(dev_batch, i))
+        else:
+            for i, dev_batch in enumerate(DevicePrefetcher((batches for _ in range(n_steps)), device, copy_streams=copy_streams)):
+                sink.push(i, step_fn(dev_batch, i))
         sink.finish()
         return sink.bytes_per_step
 
@@ -744,7 +751,8 @@ def main():
     e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
            "h2d_gbs_idle_probe": h2d_gbs, "copy_streams": copy_streams,
-           "api": "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> heatmap_u8 of "
+           "api": ("" if not e2e_diag else f"DIAGNOSTIC RUN ({e2e_diag}), not an end-to-end number: ") +
+                  "for batch in DevicePrefetcher(host_batches): ScanRegLightningModule.predict_step(batch) -> heatmap_u8 of "
                   "both dRAMs of every volume + percentages -> pinned host memory (fp32 image + bool masks in, "
                   "uint8 heat-maps + scores out, every step, double-buffered both ways)"}
 

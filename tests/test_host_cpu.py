@@ -633,3 +633,20 @@ def test_background_writer_and_read_ahead(tmp_path):
             from dram_b200.models import shard_indices
             assert fake.processed == shard_indices(n, rank, world)  # the device half runs in order, once per slot
         assert batches[0] == batches[workers] and len(batches[0]) == -(-len(shard_indices(n, rank, world)) // bs)
+
+
+def test_gpu_cpu_binding_is_optional(monkeypatch):
+    """`utils.bind_to_gpu_cpus` (one process per GPU: pinned buffers on the GPU's NUMA node) never raises: without
+    NVML / a GPU it reports None and leaves the affinity alone; DRAM_B200_NUMA=0 turns it off."""
+    from dram_b200.utils import bind_to_gpu_cpus
+
+    before = os.sched_getaffinity(0)
+    res = bind_to_gpu_cpus(0)
+    assert res is None or isinstance(res, str)
+    if res is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+    monkeypatch.setenv("DRAM_B200_NUMA", "0")
+    assert bind_to_gpu_cpus(0) is None
+    assert os.sched_getaffinity(0) == before
+

@@ -231,6 +231,29 @@ def test_cuda_graph_replay_equals_eager_launches(cuda, lib, monkeypatch):
         assert all(torch.equal(a, b) for a, b in zip(sum(model(x, lung), []), sum(eager(x, lung), [])))
 
 
+def test_stem_reads_the_callers_image_in_place(cuda, lib):
+    """`engine.image_stem` (used by predict_step): the stem convolution launched on the batch's own fp32 tensor gives
+    the bits of the route that first copies the image into the engine's buffer — also from a view at an odd offset
+    (the stem's generic load path) and with the rest of the network replayed as a graph."""
+    arch, dims = "med3ddram18", (32, 40, 48)
+    model = build_model(arch, synthetic.make_state_dict(arch, seed=12, calib_dims=dims), cuda)
+    eng = model.engine(2, dims, cuda)
+    flat = torch.zeros(2 * 32 * 40 * 48 + 3, device=cuda)
+    for rep in range(2):
+        img = torch.stack([synthetic.make_network_input(50 + 2 * rep + i, dims)[0] for i in range(2)]).to(cuda)
+        eng.load_image(img)
+        want = [t.clone() for t in eng.run_network()]
+        eng.image.zero_()
+        got = [t.clone() for t in eng.run_network(first=eng.image_stem(img))]
+        assert all(torch.equal(a, b) for a, b in zip(got, want)), rep
+        view = flat[3:].view(2, *dims)          # 12-byte offset: not 16-byte aligned
+        view.copy_(img)
+        got = [t.clone() for t in eng.run_network(first=eng.image_stem(view))]
+        assert all(torch.equal(a, b) for a, b in zip(got, want)), rep
+    with pytest.raises(ValueError):
+        eng.image_stem(img.double())
+
+
 @pytest.mark.parametrize("arch,dims", [("med3ddram18", (32, 40, 48)), ("med3ddram50", (32, 32, 32)), ("med3d", (32, 32, 32))])
 def test_commuted_us1_matches_direct_route_and_oracle(cuda, lib, arch, dims, monkeypatch):
     """us1.0 runs commuted by default (K13: low-resolution channel mixing + separable gather); DRAM_B200_US1=direct keeps
