@@ -724,7 +724,7 @@ def main():
     # locking them inside the timed region cost 7-10 % of a 20-step run at one GPU and far more with eight processes
     # pinning at once (the e2e / value ratio fell 0.95 -> 0.82 -> 0.67 at 1 / 2 / 8 GPUs with neither copy leg to blame:
     # profiles/e2e_copy_legs_r2n2c.log).
-    sink = ResultSink()
+    result_sink = ResultSink()
 
     def e2e_pass(n_steps, batches, step_fn):
         # the user-facing predict loop: every step copies ITS host batch to the device (on the prefetcher's side
@@ -732,12 +732,12 @@ def main():
         if e2e_diag == "noh2d":  # diagnostic: the batch is staged once, no host->device copy per step
             dev_batch = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in batches.items()}
             for i in range(n_steps):
-                sink.push(i, step_fn(dev_batch, i))
+                result_sink.push(i, step_fn(dev_batch, i))
         else:
             for i, dev_batch in enumerate(DevicePrefetcher((batches for _ in range(n_steps)), device, copy_streams=copy_streams)):
-                sink.push(i, step_fn(dev_batch, i))
-        sink.finish()
-        return sink.bytes_per_step
+                result_sink.push(i, step_fn(dev_batch, i))
+        result_sink.finish()
+        return result_sink.bytes_per_step
 
     def timed_e2e(batches, step_fn):
         e2e_pass(2, batches, step_fn)
@@ -781,7 +781,7 @@ def main():
                    "d2h_bytes_per_step": d2h_p, "ms_per_step": e2e_p_ms,
                    "api": "int16 HU + uint8 lobe labels from pinned host memory -> f1 lung_crop (masks on the device) -> "
                           "predict_step_from_hu -> heatmap_u8 x2 per volume -> uint8 heat-maps + percentages to the host"}
-    del host, host_p, crop_bufs, sink
+    del host, host_p, crop_bufs, result_sink
 
     # ---- roofline of the convolutions: per-launch CUDA events over eager launches --------------
     conv_steps = [s for s in eng.steps if s.conv_part]  # K13's gather passes count into the convolutions' time
