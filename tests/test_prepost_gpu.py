@@ -52,6 +52,36 @@ def test_lung_presteps_match_oracle_bit_exact(cuda, lib, case):
     assert np.array_equal(ess.cpu().numpy().astype(bool), ref["ess_mask"])
 
 
+@pytest.mark.parametrize("shape,crop,density", [
+    ((20, 40, 150), ((3, 17), (5, 33), (37, 129)), 0.02),    # crop inside the volume: the 2-voxel halo outside it counts
+    ((12, 33, 70), ((0, 12), (0, 33), (0, 70)), 0.3),        # whole volume, zero border at every face, dense mask
+    ((9, 24, 64), ((1, 9), (0, 24), (0, 64)), 0.05),         # crop width 64: 8-voxel vector stores, word-aligned rows
+    ((7, 11, 40), ((2, 5), (3, 4), (33, 40)), 0.1),          # one row, 7 voxels wide at the right face
+    ((6, 9, 131), ((0, 6), (2, 9), (1, 131)), 0.01),         # 130 wide: five bit words, ragged tail
+])
+def test_lung_crop_any_box_against_scipy(cuda, lib, shape, crop, density):
+    """f1 for arbitrary crop boxes (dataset.py:66-80 only produces boxes around the lung): two dilations with the full
+    3x3x3 structure computed by scipy on the whole volume, then cropped — the bit-mask kernels must agree exactly,
+    including for lung voxels just outside the box and at the volume faces."""
+    from scipy import ndimage
+
+    from dram_b200 import ops
+
+    g = np.random.default_rng(sum(shape))
+    ct = g.integers(-1100, 300, size=shape).astype(np.int16)
+    lobes = ((g.random(shape) < density) * g.integers(1, 6, size=shape)).astype(np.uint8)
+    lung = lobes > 0
+    dil = ndimage.binary_dilation(lung, structure=np.ones((3, 3, 3), bool), iterations=2)
+    sl = tuple(slice(a, b) for a, b in crop)
+    want_image = np.where(dil, ct, np.int16(-2048))[sl]
+    want_lung = lung[sl]
+    want_ess = (want_image < -910) & want_lung
+    image, lung_c, ess = ops.lung_crop(torch.from_numpy(ct).to(cuda), torch.from_numpy(lobes).to(cuda), crop)
+    assert np.array_equal(image.cpu().numpy(), want_image)
+    assert np.array_equal(lung_c.cpu().numpy().astype(bool), want_lung)
+    assert np.array_equal(ess.cpu().numpy().astype(bool), want_ess)
+
+
 def test_mask_bbox_empty_and_full(cuda, lib):
     from dram_b200 import ops
 
@@ -77,6 +107,30 @@ def test_heatmap_u8_matches_oracle(cuda, lib, dims, orig, crop):
     diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
     assert diff.max() <= 1
     assert (diff != 0).mean() <= 1e-3
+    outside = np.ones(orig, bool)
+    outside[tuple(slice(a, b) for a, b in crop)] = False
+    assert not got[outside].any()
+
+
+@pytest.mark.parametrize("dims,orig,crop", [
+    ((20, 24, 160), (30, 40, 300), ((2, 29), (1, 38), (7, 291))),    # wide rows: several 128-voxel trips, ragged tail
+    ((16, 16, 16), (20, 20, 150), ((0, 20), (0, 20), (0, 150))),     # whole volume, strong up-sampling along x
+])
+def test_heatmap_u8_sparse_map(cuda, lib, dims, orig, crop):
+    """A dRAM is zero outside `ess`: the kernel skips the arithmetic of 32-voxel stretches whose eight sources are all
+    zero.  A map of isolated blobs (most stretches empty, blobs cut by stretch borders) against the oracle."""
+    from dram_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    dense = torch.zeros((1,) + dims)
+    for _ in range(12):
+        z, y, x = (int(torch.randint(0, n - 2, (1,), generator=g)) for n in dims)
+        dense[0, z:z + 3, y:y + 2, x:x + 5] = torch.rand((3, 2, 5), generator=g)[: dims[0] - z, : dims[1] - y, : dims[2] - x]
+    ref = P.postprocess_scan(dense, np.asarray(crop), orig)
+    got = ops.heatmap_u8(dense[0].contiguous().to(cuda), crop, orig).cpu().numpy()
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+    assert (got != 0).any() and (got == 0).mean() > 0.5
     outside = np.ones(orig, bool)
     outside[tuple(slice(a, b) for a, b in crop)] = False
     assert not got[outside].any()
