@@ -199,7 +199,7 @@ def measured_peaks(burst=False):
     return FALLBACK_TFLOPS, "fallback (B200_PROFILING.md)"
 
 
-def measured_tensor_pipe(arch, dims):
+def measured_tensor_pipe(arch, dims, batch=1):
     """Tensor-pipe utilisation per convolution family from the committed single-pass ncu capture
     (profiles/tensor_pipe.json, written by tools/summarize_tensor_pipe.py); None when no capture matches."""
     path = os.path.join(ROOT, "profiles", "tensor_pipe.json")
@@ -207,7 +207,8 @@ def measured_tensor_pipe(arch, dims):
         return None
     with open(path) as f:
         t = json.load(f)
-    return t.get(f"{arch}:{'x'.join(str(v) for v in dims)}")
+    key = f"{arch}:{'x'.join(str(v) for v in dims)}"
+    return t.get(f"{key}:b{batch}", t.get(key))  # a capture at this batch size if there is one, else the batch-1 capture
 
 
 def measured_traffic(arch, dims, batch):
@@ -820,7 +821,7 @@ def main():
                 # the stem's K padded (343 -> 448); `achieved` above counts the reference's 2*M*N*K
                 "executed_flops_per_step": exec_flops, "achieved_executed": executed, "frac_executed": executed / peak,
                 "peak_burst": burst, "frac_of_burst": achieved / burst, "frac_executed_of_burst": executed / burst,
-                "tensor_pipe_pct": measured_tensor_pipe(args.arch, dims)}
+                "tensor_pipe_pct": measured_tensor_pipe(args.arch, dims, B)}
 
     if world > 1:
         import torch.distributed as dist
