@@ -70,7 +70,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
   const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
   auto out_tile = [&](int b) { return epi_base + (uint32_t)b * EPI_TILE_BYTES; };
   auto res_tile = [&](int b) { return epi_base + (uint32_t)(2 + b) * EPI_TILE_BYTES; };
-  auto res_full = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };  // b < RES_BUFS
+  auto res_full = [&](int q, int b) { return bar_base + 8u * (2 * STAGES + 5 + q * RES_BUFS + b); };  // q < 4, b < RES_BUFS
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -92,7 +92,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
       mbar_init(tmem_empty_bar(a), STAGED ? 256 : 128);
     }
     if (STAGED)
-      for (int b = 0; b < RES_BUFS; ++b) mbar_init(res_full(b), 1);
+      for (int b = 0; b < 4 * RES_BUFS; ++b) mbar_init(res_full(0, b), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -205,27 +205,35 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
   } else if (STAGED) {
     // ------------------------------- epilogue warps 0..3 and 6..9, staged through shared memory + TMA -------------
     // Work unit = one 64-channel group of one tile ("group", gi counts them across this CTA's tiles).
-    // Thread 0 keeps RES_BUFS residual tiles in flight (TMA, res_full[gi % RES_BUFS]) and sends finished output
-    // tiles with TMA stores; the 256 threads meet at two named barriers per group (out tile free / written).
     // Eight warps: warp w works on TMEM lane quarter w % 4 (rows 32*(w%4) ...), warps 0-3 on the first 32 columns of
-    // the group, warps 6-9 on the second 32.
+    // the group, warps 6-9 on the second 32.  The two warps of a quarter own that quarter's 32 rows of the tiles: one
+    // of their lanes keeps RES_BUFS residual slices (4 KiB each) in flight and sends the finished output slice with its
+    // own TMA store (tensor-map box = the 32 voxels of the quarter), and the pair meets at a 64-thread named barrier.
+    // Round 2, ncu of 64 -> 256 + residual at 100x128x128 (profiles/conv_1x1_r2k1.md): with ONE thread storing whole
+    // tiles and two 256-thread barriers per group the epilogue warps spent a quarter of their time at those barriers.
     constexpr int GROUPS = BLOCK_N >= 64 ? BLOCK_N / 64 : 1;
+    constexpr uint32_t SLICE_BYTES = EPI_TILE_BYTES / 4;
     const int quarter = warp & 3, half = warp < 4 ? 0 : 1;
     const int row = quarter * 32 + lane;
+    const bool storer = half == 0 && lane == 0;
+    // where the quarter's first row sits inside the tw x th x td brick
+    const int row0 = quarter * 32;
+    const int qw = row0 & (p.tw - 1), qh = (row0 >> p.tw_log2) & (p.th - 1), qd = row0 >> (p.tw_log2 + p.th_log2);
     const bool has_res = p.staged_res != 0;
     const int my_tiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total_groups = my_tiles * GROUPS;
-    auto issue_res = [&](int gi) {  // thread 0 only
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
+    auto issue_res = [&](int gi) {  // the quarter's storer only
       if (!has_res || gi >= total_groups) return;
       const int tile = blockIdx.x + (gi / GROUPS) * gridDim.x;
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int rb = gi % RES_BUFS;
-      mbar_expect_tx(res_full(rb), EPI_TILE_BYTES);
+      mbar_expect_tx(res_full(quarter, rb), SLICE_BYTES);
       const int rs = p.epi.res_stride;
-      tma_load_5d(res_tile(rb), &map_res, res_full(rb), t.n0 + (gi % GROUPS) * 64, t.w0 * rs, t.h0 * rs, t.d0 * rs,
-                  t.sample);
+      tma_load_5d(res_tile(rb) + (uint32_t)quarter * SLICE_BYTES, &map_res, res_full(quarter, rb),
+                  t.n0 + (gi % GROUPS) * 64, (t.w0 + qw) * rs, (t.h0 + qh) * rs, (t.d0 + qd) * rs, t.sample);
     };
-    if (threadIdx.x == 0)
+    if (storer)
       for (int g0 = 0; g0 < RES_BUFS; ++g0) issue_res(g0);
     int acc = 0, gi = 0;
     uint32_t acc_phase = 0;
@@ -239,18 +247,20 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
         const int b = gi & 1, rb = gi % RES_BUFS;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + (uint32_t)(g * 64 + half * 32), v);
-        if (has_res) mbar_wait(res_full(rb), (uint32_t)((gi / RES_BUFS) & 1));
-        // the store that last read out_tile(b) (group gi - 2) must be done with shared memory
-        if (threadIdx.x == 0) tma_store_wait_read<1>();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (has_res) mbar_wait(res_full(quarter, rb), (uint32_t)((gi / RES_BUFS) & 1));
+        // the store that last read this quarter of out_tile(b) (group gi - 2) must be done with shared memory
+        if (storer) tma_store_wait_read<1>();
+        pair_sync();
         tmem_wait_ld();
         epilogue_group_staged(p.epi, v, t.n0 + g * 64 + half * 32, row, half, res_tile(rb), has_res, out_tile(b));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 0) {
-          tma_store_5d(&map_out, out_tile(b), t.n0 + g * 64, t.w0, t.h0, t.d0, t.sample);
-          tma_store_commit();
-          issue_res(gi + RES_BUFS);  // res_tile(rb) has been read by everyone
+        pair_sync();
+        if (storer) {
+          if (t.w0 + qw < p.Wo && t.h0 + qh < p.Ho && t.d0 + qd < p.Do)  // a quarter of a border tile can lie outside
+            tma_store_5d(&map_out, out_tile(b) + (uint32_t)quarter * SLICE_BYTES, t.n0 + g * 64, t.w0 + qw, t.h0 + qh,
+                         t.d0 + qd, t.sample);
+          tma_store_commit();  // one bulk group per group even when nothing is stored (wait_group.read 1 counts them)
+          issue_res(gi + RES_BUFS);  // both warps of the quarter have read its slice of res_tile(rb)
         }
       }
       tcgen05_fence_before();
@@ -260,7 +270,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map_a1,
         acc_phase ^= 1u;
       }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
   } else {
     // ------------------------------- epilogue warps 0..3 -------------------------------
     const int row = warp * 32 + lane;  // TMEM lane == row of the 128-voxel tile
@@ -655,9 +665,11 @@ extern "C" int dram_conv3d_plan_create(const dram_conv_desc *d, const void *src1
   pl->map_out = pl->map_a1;
   pl->map_res = pl->map_a1;
   if (rc == DRAM_OK && pl->staged) {
-    rc = encode_act_map(&pl->map_out, out, d->n, Do, Ho, Wo, d->cout, 64, tw, th, td, 1, 1, 1, epi.is_f16);
+    // the staged epilogue moves quarter tiles: 32 consecutive rows of the tw x th x td brick (w fastest) are a box too
+    const int qbw = tw < 32 ? tw : 32, qbh = (32 / qbw) < th ? 32 / qbw : th, qbd = 32 / (qbw * qbh);
+    rc = encode_act_map(&pl->map_out, out, d->n, Do, Ho, Wo, d->cout, 64, qbw, qbh, qbd, 1, 1, 1, epi.is_f16);
     if (rc == DRAM_OK && p.staged_res)
-      rc = encode_act_map(&pl->map_res, residual, d->n, d->res_d, d->res_h, d->res_w, d->res_c, 64, tw, th, td,
+      rc = encode_act_map(&pl->map_res, residual, d->n, d->res_d, d->res_h, d->res_w, d->res_c, 64, qbw, qbh, qbd,
                           epi.res_stride, epi.res_stride, epi.res_stride, epi.is_f16);
   }
   if (rc == DRAM_OK) {
